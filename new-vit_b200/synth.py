@@ -1,0 +1,130 @@
+"""Deterministic synthetic weights and volumes for MST-DINOv2.
+
+There is no network on the build or GPU machines, so hub weights and datasets are replaced by
+synthetic ones (BASELINE.json: "random-init weights ... synthetic inputs").  The generator
+follows the reference's init distributions (reference
+`mst/models/extern/dinov2/vision_transformer.py:172-177,332-337`, `mst/models/dino.py:84-103`)
+but draws from its own seeded CPU generator so that the *same* state_dict can be rebuilt on any
+machine and loaded into the reference model, the oracle and the CUDA path alike.
+
+Two departures from the pure init, both deliberate so that parity tests exercise every term:
+biases / LayerNorm affine parameters are small random values instead of exact 0 / 1, and the
+``peaky`` variant scales the attention projections so that softmax rows are far from uniform
+(random-init maps are within a factor 2 of uniform, which makes argmax tests meaningless).
+"""
+from collections import OrderedDict
+
+import torch
+
+# (embed dim, depth, heads) -- reference vision_transformer.py:340-396
+VIT_CFG = {"s": (384, 12, 6), "b": (768, 12, 12), "l": (1024, 24, 16)}
+PATCH = 14
+SLICE_HEADS = 12  # reference dino.py:87
+
+
+def _tn(g, shape, std):
+    t = torch.empty(shape, dtype=torch.float32)
+    torch.nn.init.trunc_normal_(t, std=std, a=-2 * std, b=2 * std, generator=g)
+    return t
+
+
+def _n(g, shape, std):
+    return torch.randn(shape, generator=g, dtype=torch.float32) * std
+
+
+def _u(g, shape, bound):
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * bound
+
+
+def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=224,
+                    layerscale=False, chunked_names=True):
+    """Return an OrderedDict with the reference's state_dict key layout.
+
+    variant: "init"  -- reference-like init distributions
+             "peaky" -- same, attention projections scaled up (sharp attention maps)
+    """
+    assert variant in ("init", "peaky")
+    E, depth, _heads = VIT_CFG[model_size]
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000003 * seed + {"s": 1, "b": 2, "l": 3}[model_size] + (17 if variant == "peaky" else 0))
+    npatch = (img_size // PATCH) ** 2
+    sd = OrderedDict()
+    sd["cls_token"] = _n(g, (1, 1, E), 1.0)
+    sd["encoder.cls_token"] = _n(g, (1, 1, E), 0.02)
+    sd["encoder.pos_embed"] = _tn(g, (1, 1 + npatch, E), 0.02)
+    sd["encoder.mask_token"] = torch.zeros(1, E)
+    fan_in = 3 * PATCH * PATCH
+    sd["encoder.patch_embed.proj.weight"] = _u(g, (E, 3, PATCH, PATCH), (1.0 / fan_in) ** 0.5)
+    sd["encoder.patch_embed.proj.bias"] = _u(g, (E,), (1.0 / fan_in) ** 0.5)
+    qkv_gain = 6.0 if variant == "peaky" else 1.0
+    for i in range(depth):
+        p = f"encoder.blocks.0.{i}." if chunked_names else f"encoder.blocks.{i}."
+        sd[p + "norm1.weight"] = 1.0 + _n(g, (E,), 0.05)
+        sd[p + "norm1.bias"] = _n(g, (E,), 0.02)
+        w = _tn(g, (3 * E, E), 0.02)
+        w[: 2 * E] *= qkv_gain
+        sd[p + "attn.qkv.weight"] = w
+        sd[p + "attn.qkv.bias"] = _n(g, (3 * E,), 0.02)
+        sd[p + "attn.proj.weight"] = _tn(g, (E, E), 0.02)
+        sd[p + "attn.proj.bias"] = _n(g, (E,), 0.02)
+        if layerscale:
+            sd[p + "ls1.gamma"] = 1.0 + _n(g, (E,), 0.1)
+        sd[p + "norm2.weight"] = 1.0 + _n(g, (E,), 0.05)
+        sd[p + "norm2.bias"] = _n(g, (E,), 0.02)
+        sd[p + "mlp.fc1.weight"] = _tn(g, (4 * E, E), 0.02)
+        sd[p + "mlp.fc1.bias"] = _n(g, (4 * E,), 0.02)
+        sd[p + "mlp.fc2.weight"] = _tn(g, (E, 4 * E), 0.02)
+        sd[p + "mlp.fc2.bias"] = _n(g, (E,), 0.02)
+        if layerscale:
+            sd[p + "ls2.gamma"] = 1.0 + _n(g, (E,), 0.1)
+    sd["encoder.norm.weight"] = 1.0 + _n(g, (E,), 0.05)
+    sd["encoder.norm.bias"] = _n(g, (E,), 0.02)
+    q = "slice_fusion.layers.0."
+    xav = (6.0 / (E + 3 * E)) ** 0.5
+    w = _u(g, (3 * E, E), xav)
+    if variant == "peaky":
+        w[: 2 * E] *= 3.0
+    sd[q + "self_attn.in_proj_weight"] = w
+    sd[q + "self_attn.in_proj_bias"] = _n(g, (3 * E,), 0.02)
+    lin = (1.0 / E) ** 0.5
+    sd[q + "self_attn.out_proj.weight"] = _u(g, (E, E), lin)
+    sd[q + "self_attn.out_proj.bias"] = _n(g, (E,), 0.02)
+    sd[q + "linear1.weight"] = _u(g, (E, E), lin)
+    sd[q + "linear1.bias"] = _u(g, (E,), lin)
+    sd[q + "linear2.weight"] = _u(g, (E, E), lin)
+    sd[q + "linear2.bias"] = _u(g, (E,), lin)
+    sd[q + "norm1.weight"] = 1.0 + _n(g, (E,), 0.05)
+    sd[q + "norm1.bias"] = _n(g, (E,), 0.02)
+    sd[q + "norm2.weight"] = 1.0 + _n(g, (E,), 0.05)
+    sd[q + "norm2.bias"] = _n(g, (E,), 0.02)
+    sd["slice_fusion.norm.weight"] = 1.0 + _n(g, (E,), 0.05)
+    sd["slice_fusion.norm.bias"] = _n(g, (E,), 0.02)
+    sd["linear.weight"] = _u(g, (out_ch, E), lin)
+    sd["linear.bias"] = _u(g, (out_ch,), lin)
+    return sd
+
+
+def make_volume(B=1, D=32, H=224, W=224, seed=0, pin_memory=False):
+    """Synthetic z-normalised volume batch [B,1,D,H,W] fp32 (reference input contract:
+    `mst/data/datasets/dataset_3d_duke.py:43`, `augmentations_3d.py:23-29`)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7919 * seed + 13)
+    x = torch.randn((B, 1, D, H, W), generator=g, dtype=torch.float32)
+    # a smooth low-frequency component so that slices/patches are not exchangeable
+    zz = torch.linspace(-1, 1, D).view(1, 1, D, 1, 1)
+    yy = torch.linspace(-1, 1, H).view(1, 1, 1, H, 1)
+    xx = torch.linspace(-1, 1, W).view(1, 1, 1, 1, W)
+    bb = torch.arange(B, dtype=torch.float32).view(B, 1, 1, 1, 1)
+    x = x + 1.5 * torch.sin(3.0 * xx + bb) * torch.cos(2.0 * yy - 0.5 * bb) * (0.3 + zz * zz)
+    if pin_memory:
+        x = x.pin_memory()
+    return x
+
+
+def make_padding_mask(B, D, seed=0):
+    """Bool [B,D], True = ignore (reference dino.py:147-150). Volume 0 is never masked."""
+    m = torch.zeros(B, D, dtype=torch.bool)
+    for b in range(1, B):
+        keep = D - ((b * 5 + seed) % (D // 2)) - 1
+        m[b, keep:] = True
+    return m

@@ -1,0 +1,231 @@
+"""ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU (PyTorch fp32) restatement of the reference's MST-DINOv2 hot path, written as plain
+functions over a state_dict so that it can run on the GPU box where `/root/reference` does not
+exist.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl
+reference` legs may import this module; the product package (`new-vit_b200/`) never does.
+
+Pinning: the reference holds no golden vectors or asserting tests for this path (SURVEY.md
+section 4 -- "parity unpinned" by the reference's own tests).  The oracle is therefore pinned
+against outputs of the reference itself, run in the dev container through
+`oracle/ref_harness.py`: `tests/golden/make_golden.py` committed `tests/golden/*.npz`, and
+`tests/test_oracle.py` checks this file against them (and, when `/root/reference` is present,
+against the live reference model).
+
+Every function cites the reference file:line it restates (paths relative to /root/reference).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+PATCH = 14
+
+
+def _blk_prefix(sd, i):
+    # local model: encoder.blocks.0.<i>. (BlockChunk wrapper, vision_transformer.py:153-160);
+    # hub model: encoder.blocks.<i>.
+    p = f"encoder.blocks.0.{i}."
+    if p + "norm1.weight" in sd:
+        return p
+    return f"encoder.blocks.{i}."
+
+
+def encoder_depth(sd):
+    d = 0
+    while _blk_prefix(sd, d) + "norm1.weight" in sd:
+        d += 1
+    return d
+
+
+def interpolate_pos_encoding(pos_embed, npatch, w, h, interpolate_offset=0.1):
+    """vision_transformer.py:179-211."""
+    N = pos_embed.shape[1] - 1
+    if npatch == N and w == h:
+        return pos_embed
+    pos_embed = pos_embed.float()
+    class_pos = pos_embed[:, 0]
+    patch_pos = pos_embed[:, 1:]
+    dim = pos_embed.shape[-1]
+    w0, h0 = w // PATCH, h // PATCH
+    M = int(math.sqrt(N))
+    assert N == M * M
+    kwargs = {}
+    if interpolate_offset:
+        kwargs["scale_factor"] = (float(w0 + interpolate_offset) / M, float(h0 + interpolate_offset) / M)
+    else:
+        kwargs["size"] = (w0, h0)
+    patch_pos = F.interpolate(patch_pos.reshape(1, M, M, dim).permute(0, 3, 1, 2), mode="bicubic",
+                              antialias=False, **kwargs)
+    assert (w0, h0) == patch_pos.shape[-2:]
+    patch_pos = patch_pos.permute(0, 2, 3, 1).reshape(1, -1, dim)
+    return torch.cat((class_pos.unsqueeze(0), patch_pos), dim=1)
+
+
+def encoder_attention(sd, p, x, heads):
+    """layers/attention.py:56-69 (the explicit-softmax path; xFormers is not installed)."""
+    B, N, C = x.shape
+    qkv = F.linear(x, sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"])
+    qkv = qkv.reshape(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    scale = (C // heads) ** -0.5
+    q, k, v = qkv[0] * scale, qkv[1], qkv[2]          # scale into q BEFORE q@k^T (attention.py:60)
+    attn = (q @ k.transpose(-2, -1)).softmax(dim=-1)  # [B, heads, N, N]
+    o = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    o = F.linear(o, sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"])
+    return o, attn
+
+
+def encoder_forward(sd, img, heads, keep_all_maps=False):
+    """DinoVisionTransformer.forward (vision_transformer.py:324-329) on `[BD,3,H,W]`.
+
+    Returns normed CLS `[BD,E]` and the last block's attention `[BD,heads,N,N]` (or all 12).
+    """
+    BD, _, H, W = img.shape
+    assert H % PATCH == 0 and W % PATCH == 0, "patch_embed.py:72-73"
+    # patch_embed.py:75-77: Conv2d(k=s=14) -> flatten(2).transpose(1,2)
+    x = F.conv2d(img, sd["encoder.patch_embed.proj.weight"], sd["encoder.patch_embed.proj.bias"], stride=PATCH)
+    x = x.flatten(2).transpose(1, 2)
+    # vision_transformer.py:219-220
+    x = torch.cat((sd["encoder.cls_token"].expand(BD, -1, -1), x), dim=1)
+    x = x + interpolate_pos_encoding(sd["encoder.pos_embed"], x.shape[1] - 1, W, H)
+    maps = []
+    depth = encoder_depth(sd)
+    for i in range(depth):
+        p = _blk_prefix(sd, i)
+        # block.py:112-113, LayerNorm eps 1e-6 (vision_transformer.py:95), LayerScale (layer_scale.py:26-27)
+        a, attn = encoder_attention(sd, p, F.layer_norm(x, x.shape[-1:], sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-6), heads)
+        if p + "ls1.gamma" in sd:
+            a = a * sd[p + "ls1.gamma"]
+        x = x + a
+        h = F.layer_norm(x, x.shape[-1:], sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-6)
+        h = F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+        h = F.gelu(h)  # exact erf GELU (mlp.py:30)
+        h = F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+        if p + "ls2.gamma" in sd:
+            h = h * sd[p + "ls2.gamma"]
+        x = x + h
+        if keep_all_maps or i == depth - 1:
+            maps.append(attn)
+    x = F.layer_norm(x, x.shape[-1:], sd["encoder.norm.weight"], sd["encoder.norm.bias"], 1e-6)
+    return x[:, 0], maps
+
+
+def slice_transformer(sd, x, key_padding_mask, heads=12):
+    """nn.TransformerEncoder(num_layers=1, norm) over the custom pre-LN layer
+    (utils/transformer_blocks.py:524-573, 29-318; dino.py:84-96).  Explicit bmm/softmax path
+    (`:266-295`), which the reference takes when save_attn=True; the SDPA path differs by ~2e-7.
+    x: [B,L,E]; key_padding_mask: bool [B,L] (True = ignore) or None.
+    Returns [B,L,E] and per-head weights [B,heads,L,L]."""
+    q_ = "slice_fusion.layers.0."
+    B, L, E = x.shape
+    hd = E // heads
+    h = F.layer_norm(x, (E,), sd[q_ + "norm1.weight"], sd[q_ + "norm1.bias"], 1e-5)
+    qkv = F.linear(h, sd[q_ + "self_attn.in_proj_weight"], sd[q_ + "self_attn.in_proj_bias"])
+    q, k, v = qkv.chunk(3, dim=-1)
+    q = q.reshape(B, L, heads, hd).transpose(1, 2) * math.sqrt(1.0 / hd)  # transformer_blocks.py:268
+    k = k.reshape(B, L, heads, hd).transpose(1, 2)
+    v = v.reshape(B, L, heads, hd).transpose(1, 2)
+    s = q @ k.transpose(-2, -1)
+    if key_padding_mask is not None:  # additive -inf on key columns (transformer_blocks.py:244-252)
+        s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
+    w = s.softmax(dim=-1)
+    o = (w @ v).transpose(1, 2).reshape(B, L, E)
+    o = F.linear(o, sd[q_ + "self_attn.out_proj.weight"], sd[q_ + "self_attn.out_proj.bias"])
+    x = x + o
+    h = F.layer_norm(x, (E,), sd[q_ + "norm2.weight"], sd[q_ + "norm2.bias"], 1e-5)
+    h = F.linear(F.relu(F.linear(h, sd[q_ + "linear1.weight"], sd[q_ + "linear1.bias"])),
+                 sd[q_ + "linear2.weight"], sd[q_ + "linear2.bias"])  # ReLU FFN (transformer_blocks.py:484,585)
+    x = x + h
+    x = F.layer_norm(x, (E,), sd["slice_fusion.norm.weight"], sd["slice_fusion.norm.bias"], 1e-5)  # dino.py:95
+    return x, w
+
+
+@torch.no_grad()
+def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps=False):
+    """DinoV2ClassifierSlice.forward (dino.py:110-167), default configuration
+    (slice_fusion='transformer', no bottleneck, no slice pos-emb, no rotary).
+
+    Returns a dict: logits [B,out], feat [B,E], enc_cls [BD,E], plane_cls [BD,heads,N] (row 0 of
+    the last encoder block's attention), slice_cls [B,12,L] (row 0 of slice attention), and the
+    full maps under 'maps' / 'maps_slice' as the reference stores them (dino.py:241,249)."""
+    sd = {k: v.float() for k, v in sd.items()}
+    B, C, D, H, W = source.shape
+    assert C == 1
+    E = sd["encoder.pos_embed"].shape[-1]
+    if enc_heads is None:
+        enc_heads = E // 64
+    x = source.float().permute(0, 2, 1, 3, 4).reshape(B * D * C, H, W)  # dino.py:125
+    x = x[:, None].repeat(1, 3, 1, 1)                                    # dino.py:126-127
+    enc_cls, maps = encoder_forward(sd, x, enc_heads, keep_all_maps)     # dino.py:131
+    x = enc_cls.reshape(B, D, E)                                         # dino.py:138
+    x = torch.cat([sd["cls_token"].repeat(B, 1, 1), x], dim=1)           # dino.py:145
+    kpm = None
+    if src_key_padding_mask is not None:                                 # dino.py:147-150
+        kpm = torch.cat([torch.zeros((B, 1), dtype=torch.bool), src_key_padding_mask.bool()], dim=1)
+    x, w = slice_transformer(sd, x, kpm)                                 # dino.py:152
+    feat = x[:, 0]                                                       # dino.py:153
+    logits = F.linear(feat, sd["linear.weight"], sd["linear.bias"])      # dino.py:166
+    return {
+        "logits": logits, "feat": feat, "enc_cls": enc_cls,
+        "plane_cls": maps[-1][:, :, 0, :].clone(), "slice_cls": w[:, :, 0, :].clone(),
+        "maps": maps, "maps_slice": [w],
+    }
+
+
+def get_plane_attention(plane_cls):
+    """dino.py:189-195 on the CLS row [BD,heads,N]: drop CLS column, zero patch 0, renormalise."""
+    a = plane_cls[:, :, 1:].clone()
+    a[:, :, 0] = 0
+    a = a / a.sum(dim=-1, keepdim=True)
+    return a
+
+
+def get_slice_attention(slice_cls):
+    """dino.py:173-187 on the CLS row [B,heads,L] -> [B*D,1,1]."""
+    s = slice_cls[:, :, 1:].clone()
+    s = s / s.sum(dim=-1, keepdim=True)
+    s = s.mean(dim=1)
+    return s.reshape(-1)[:, None, None]
+
+
+def get_attention_maps(plane_cls, slice_cls):
+    """dino.py:197-202 -> [BD,heads,P]."""
+    return get_slice_attention(slice_cls) * get_plane_attention(plane_cls)
+
+
+def get_attention_cls(maps):
+    """dino.py:204-212 attention rollout over all encoder blocks."""
+    a = maps[-1]
+    for m in reversed(maps[:-1]):
+        a = torch.matmul(m, a)
+    return a
+
+
+def saliency(plane_cls, slice_cls, B, D, H, W):
+    """scripts/main_predict.py:70-105,161-162 generalised from B=1 to a batch:
+    head-mean of get_attention_maps -> [B,1,D,g,g] -> trilinear upsample to [B,1,D,H,W];
+    slice weights broadcast to the source shape.  Returns (coarse, full, weight_slice)."""
+    w = get_attention_maps(plane_cls, slice_cls).mean(dim=1)  # main_predict.py:73-74
+    g = int(w.shape[-1] ** 0.5)                                # main_predict.py:93-94
+    coarse = w.reshape(B, 1, D, g, g)                          # main_predict.py:100 (B=1 there)
+    full = F.interpolate(coarse, size=(D, H, W), mode="trilinear")  # main_predict.py:161-162
+    ws = get_slice_attention(slice_cls).mean(dim=1)            # main_predict.py:103-104
+    ws = ws.reshape(B, 1, D, 1, 1).expand(B, 1, D, H, W)
+    return coarse, full, ws
+
+
+def bilinear14_reference(coarse, H, W):
+    """with depth scale 1 the trilinear upsample equals per-slice bilinear with
+    align_corners=False; plain-loop restatement used to pin the CUDA kernel's index math."""
+    B, _, D, g, _ = coarse.shape
+    out = torch.empty(B, 1, D, H, W, dtype=coarse.dtype)
+    sy_scale, sx_scale = g / H, g / W
+    ys = ((torch.arange(H, dtype=torch.float32) + 0.5) * sy_scale - 0.5).clamp(min=0)
+    xs = ((torch.arange(W, dtype=torch.float32) + 0.5) * sx_scale - 0.5).clamp(min=0)
+    y0 = ys.floor().long(); x0 = xs.floor().long()
+    y1 = (y0 + 1).clamp(max=g - 1); x1 = (x0 + 1).clamp(max=g - 1)
+    ly = (ys - y0).view(1, 1, 1, H, 1); lx = (xs - x0).view(1, 1, 1, 1, W)
+    v00 = coarse[..., y0, :][..., x0]; v01 = coarse[..., y0, :][..., x1]
+    v10 = coarse[..., y1, :][..., x0]; v11 = coarse[..., y1, :][..., x1]
+    out = (1 - ly) * ((1 - lx) * v00 + lx * v01) + ly * ((1 - lx) * v10 + lx * v11)
+    return out

@@ -1,0 +1,80 @@
+"""Generate the golden vectors under tests/golden/ by running the REAL reference model.
+
+Run in the dev container only (needs /root/reference):   python tests/golden/make_golden.py
+The reference is imported through oracle/ref_harness.py (stub modules for the packages that
+are missing here).  Weights and inputs come from new-vit_b200/synth.py, which is deterministic,
+so the GPU box can rebuild the identical state_dict / volumes and compare against these files.
+
+Per case we store what the hot path produces:
+  logits, logits_nosave (save_attn=False -> SDPA path), feat (without_linear), enc_cls,
+  plane_cls = attention_maps[-1][:,:,0,:]   (captured before the getters mutate it in place),
+  slice_cls = attention_maps_slice[-1][:,:,0,:],
+  attn_maps = get_attention_maps(), slice_attn = get_slice_attention(),
+  sal_sub   = run_pred()'s trilinear-upsampled map (scripts/main_predict.py:70-105,161-162),
+              computed per volume (the script hard-codes batch 1) and subsampled [::7, ::7].
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_harness import build_reference_model  # noqa: E402
+import new_vit_b200.synth as synth  # noqa: E402
+
+CASES = {
+    # name: (model_size, variant, B, D, H, W, masked, weight seed, volume seed)
+    "s_init_b2": ("s", "init", 2, 32, 224, 224, False, 0, 0),
+    "s_peaky_mask_b2": ("s", "peaky", 2, 32, 224, 224, True, 1, 1),
+    "s_init_small": ("s", "init", 1, 5, 112, 112, False, 2, 2),
+    "s_peaky_small_mask_b3": ("s", "peaky", 3, 7, 112, 112, True, 3, 3),
+}
+
+
+def run_case(name):
+    size, variant, B, D, H, W, masked, wseed, vseed = CASES[name]
+    sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=H)
+    model = build_reference_model(sd, out_ch=2, model_size=size)
+    x = synth.make_volume(B, D, H, W, seed=vseed)
+    mask = synth.make_padding_mask(B, D, seed=vseed) if masked else None
+    out = {}
+    with torch.no_grad():
+        out["logits_nosave"] = model(x, src_key_padding_mask=mask, save_attn=False)
+        out["feat"] = model(x, src_key_padding_mask=mask, save_attn=False, without_linear=True)
+        out["logits"] = model(x, src_key_padding_mask=mask, save_attn=True)
+        out["plane_cls"] = model.attention_maps[-1][:, :, 0, :].clone()
+        out["slice_cls"] = model.attention_maps_slice[-1][:, :, 0, :].clone()
+        out["attn_maps"] = model.get_attention_maps().clone()
+        out["slice_attn"] = model.get_slice_attention().clone()
+        # encoder CLS features: run the encoder alone
+        xs = x.permute(0, 2, 1, 3, 4).reshape(B * D, H, W)[:, None].repeat(1, 3, 1, 1)
+        out["enc_cls"] = model.encoder(xs)
+        # saliency exactly as scripts/main_predict.py does it, one volume at a time
+        subs = []
+        for b in range(B):
+            xb = x[b:b + 1]
+            mb = None if mask is None else mask[b:b + 1]
+            model(xb, src_key_padding_mask=mb, save_attn=True)
+            w = model.get_attention_maps()
+            w = w.mean(dim=1)
+            g = int(w.shape[-1] ** 0.5)
+            w = w.view(1, 1, D, g, g)
+            w = F.interpolate(w, size=xb.shape[2:], mode="trilinear")
+            subs.append(w[0, 0, :, ::7, ::7].clone())
+            if b == 0:
+                out["sal_sum_b0"] = w.double().sum().float().reshape(1)
+        out["sal_sub"] = torch.stack(subs)
+    meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
+                        meta=np.array(repr(meta)), **{k: v.numpy() for k, v in out.items()})
+    print(name, "logits", out["logits"].tolist())
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    for n in (sys.argv[1:] or CASES):
+        run_case(n)
