@@ -1,0 +1,243 @@
+"""MST-DINOv2 forward throughput (BASELINE.json metric: volumes/s and slices/s, % of bf16 tensor peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch 64] [--saliency]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+One "step" = one forward of a batch of synthetic volumes (config 2: 64 x 32 x 224 x 224, bf16, random-init
+ViT-S/14) per GPU.  Volumes shard whole across GPUs (weak scaling, no data-path collective; logits are
+all-gathered once per step).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic matmul FLOPs, ViT-S/14 @224, 32 slices
+FLOP_PER_SLICE_S = 12_247_123_968
+FLOP_SLICE_TRANSFORMER_S = 60_066_816
+
+
+def flops_per_volume(D=32):
+    return FLOP_PER_SLICE_S * D + FLOP_SLICE_TRANSFORMER_S
+
+
+def gemm_flops_executed(BD, N=257, E=384, depth=12, KP=256):
+    """Tensor-core FLOPs the tcgen05 GEMM launches of one forward really execute (last block runs proj/MLP on the
+    CLS rows only; the patch GEMM runs with K padded to 256 on channel-summed weights)."""
+    M = BD * N
+    per_layer_full = 2 * M * E * (3 * E + E + 4 * E + 4 * E)
+    last = 2 * M * E * 3 * E + 2 * BD * E * (E + 4 * E + 4 * E)
+    return 2 * BD * (N - 1) * KP * E + (depth - 1) * per_layer_full + last
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(steps, warmup, threads=None):
+    """Time the oracle (CPU port of the reference path) on one synthetic volume per step."""
+    import torch
+    from new_vit_b200 import synth
+    from oracle import mst_oracle as O
+    torch.set_num_threads(threads or os.cpu_count())
+    sd = synth.make_state_dict("s", 2, seed=0)
+    x = synth.make_volume(1, 32, 224, 224, seed=0)
+    for _ in range(warmup):
+        O.forward(sd, x)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.forward(sd, x)
+        ts.append(time.perf_counter() - t0)
+    return {"value": 1.0 / statistics.median(ts), "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} x 1 volume 32x224x224 fp32 (oracle/mst_oracle.py, torch CPU), median; min {min(ts):.3f}s"}, ts
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="volumes per GPU per step")
+    ap.add_argument("--slices", type=int, default=32)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--saliency", action="store_true", help="config 3: save_attn + full-resolution saliency volume")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    cfg = {"workload": f"MST-DINOv2 (DinoV2ClassifierSlice, random-init ViT-S/14) {args.precision} inference, "
+                       f"{args.batch} volumes x {args.slices} slices x 224x224 per GPU"
+                       + (" + --get_attention saliency maps" if args.saliency else ""),
+           "volumes_per_gpu": args.batch, "slices": args.slices, "img": 224, "parallelism": f"volume-sharded dp{world}",
+           "l2_policy": "inputs larger than L2 (411 MB fp32 per step; 0.4-1.6 GB activations per kernel)"}
+
+    if args.impl == "reference":
+        # The reference is a Python/PyTorch package that cannot travel to the GPU box; its path is timed through
+        # the oracle port on the host cores (bounded sample: one volume per step).
+        if rank != 0:
+            return
+        base, ts = cpu_baseline(max(1, args.steps), max(1, args.warmup))
+        v = base["value"]
+        print(json.dumps({"impl": "reference", "metric": "volumes_per_sec", "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.median(ts),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "slices_per_sec": v * 32, "config": dict(cfg, workload=cfg["workload"] + " [CPU: 1 volume per step]"),
+                          "cpu_baseline": base,
+                          "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, D = args.batch, args.slices
+    torch.manual_seed(0)
+    model = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=args.precision).to(dev).eval()
+    model.load_state_dict(synth.make_state_dict("s", 2, seed=0))
+    x_host = synth.make_volume(B, D, 224, 224, seed=rank).pin_memory()
+    x_dev = x_host.to(dev)
+    gathered = [torch.empty(B, 2, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step(src):
+        with torch.no_grad():
+            y = model(src, save_attn=args.saliency)
+            if args.saliency:
+                model.saliency_volume()
+            if world > 1:
+                dist.all_gather(gathered, y)  # only the logits are gathered
+        return y
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step(x_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-resident timing ----
+    l0 = model.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    launches = (model.launch_count() - l0) + (2 * args.steps if args.saliency else 0)
+    # ---- end-to-end timing: pinned host input -> H2D -> forward -> logits D2H, every step ----
+    step(x_host).cpu()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        y = step(x_host)
+        y_host = y.cpu()
+    e1.record()
+    barrier()
+    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    sampler.stop_flag = True
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms_step = ms.item() / args.steps
+    ms_step_e2e = ms_e2e.item() / args.steps
+    vols = B * world
+    value = vols / (ms_step * 1e-3)
+    e2e = vols / (ms_step_e2e * 1e-3)
+
+    # ---- per-kernel device time (CUDA events on the launch stream, separate profiled pass of the same steps) ----
+    prof = None
+    if not args.no_profile and rank == 0:
+        model.profile_begin()
+        for _ in range(args.steps):
+            with torch.no_grad():
+                model(x_dev, save_attn=args.saliency)
+        prof = model.profile_end()
+    out = None
+    if rank == 0:
+        peaks = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "_src": "fallback"}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks.update(json.load(f)); peaks["_src"] = "measured"
+        except Exception:
+            pass
+        roof = None
+        kernels = {}
+        if prof:
+            gemm_cats = ["gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_cls_rows"]
+            gemm_ms = sum(prof[c][0] for c in gemm_cats) / args.steps
+            gemm_n = sum(prof[c][1] for c in gemm_cats) // args.steps
+            fl = gemm_flops_executed(B * D)
+            ach = fl / (gemm_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"kernel": "gemm_tc_kernel (tcgen05/TMA/TMEM bf16 GEMM family, %d launches/step)" % gemm_n, "bound": "tensor",
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                    "peak_kind": f"{peaks['_src']} sustained (kernel timed inside a long step); burst {peaks['bf16_tflops']}",
+                    "frac_of_burst": ach / peaks["bf16_tflops"], "flops_per_step": fl, "ms_per_step": gemm_ms, "traffic": None}
+            tot = sum(v[0] for v in prof.values()) / args.steps
+            for k, (m_, n_) in prof.items():
+                kernels[k] = {"ms_per_step": m_ / args.steps, "launches_per_step": n_ / args.steps, "share": (m_ / args.steps) / tot if tot else 0}
+            kernels["_sum_ms_per_step"] = tot
+        base = None
+        if not args.no_cpu_baseline and world == 1:
+            base, _ = cpu_baseline(3, 1)
+        model_tflops = value * flops_per_volume(D) / 1e12
+        out = {"metric": "volumes_per_sec", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+               "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
+               "slices_per_sec": value * D,
+               "model_tflops": model_tflops, "model_frac_of_bf16_burst_peak": model_tflops / (peaks["bf16_tflops"] * world),
+               "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_step_e2e,
+                       "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+               "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": base, "kernels": kernels}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

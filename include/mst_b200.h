@@ -1,0 +1,111 @@
+/* mst_b200.h -- C ABI of the B200-native MST-DINOv2 hot path (libmst_b200.so).
+ *
+ * The reference (gabrielfnayres/new-vit) has no FFI: its seam for this path is the Python class
+ * `mst.models.DinoV2ClassifierSlice` (reference mst/models/dino.py:32-275).  These entry points are what a
+ * binding for that class calls (ctypes stub: new-vit_b200/_cabi.py; INTEGRATION.md shows the reference-side
+ * patch).  Plain pointers and sizes only; every pointer named "dev" / every tensor argument is a DEVICE
+ * pointer owned by the caller; `stream` is a cudaStream_t passed as void*.  All functions return 0 on
+ * success, non-zero on failure with a message available from mst_last_error().  No function synchronises
+ * the device except mst_finalize_weights and mst_destroy.  One handle per GPU; a handle is not thread-safe.
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef MST_B200_H_
+#define MST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MST_ABI_VERSION 1
+#if defined(__GNUC__)
+#define MST_API __attribute__((visibility("default")))
+#else
+#define MST_API
+#endif
+
+enum { MST_PRECISION_FP32 = 0, MST_PRECISION_BF16 = 1 };
+
+/* Architecture of one DinoV2ClassifierSlice instance.  Replaces the constructor arguments of
+ * reference dino.py:33-103 (model_size -> embed_dim/depth/enc_heads per vision_transformer.py:340-396). */
+typedef struct mst_config {
+    int32_t embed_dim;   /* 384 (ViT-S/14), 768 (ViT-B/14), 1024 (ViT-L/14); head_dim is always 64 */
+    int32_t depth;       /* encoder blocks, 12 for S/B */
+    int32_t enc_heads;   /* embed_dim / 64 */
+    int32_t slice_heads; /* 12 (dino.py:87) */
+    int32_t out_ch;      /* classes (dino.py:103) */
+    int32_t pos_tokens;  /* rows of encoder.pos_embed = 1 + (img/14)^2 the weights were built for (257 @224) */
+    int32_t precision;   /* MST_PRECISION_FP32: CUDA-core parity mode; MST_PRECISION_BF16: tcgen05 tensor cores */
+    int32_t device;      /* CUDA device ordinal */
+} mst_config;
+
+typedef struct mst_handle_s* mst_handle;
+
+MST_API int mst_abi_version(void);
+MST_API const char* mst_last_error(void);
+
+/* dino.py:33 (__init__): allocate the weight store for `cfg` on cfg->device. */
+MST_API int mst_create(const mst_config* cfg, mst_handle* out);
+MST_API int mst_destroy(mst_handle h);
+
+/* state_dict()/load_state_dict() (SURVEY.md section 5 key layout; base_model.py:67-81).  `name` is the
+ * reference's state_dict key ("encoder.blocks.0.3.attn.qkv.weight", "slice_fusion.layers.0.linear1.bias",
+ * "cls_token", ...; both the chunked "blocks.0.<i>" and the hub "blocks.<i>" spellings; optional
+ * "ls1.gamma"/"ls2.gamma").  dev_fp32 holds `numel` fp32 values on the device.  "encoder.mask_token" is
+ * accepted and ignored (unused by the path). */
+MST_API int mst_set_weight(mst_handle h, const char* name, const float* dev_fp32, int64_t numel, void* stream);
+/* Pack the weights for the selected precision (bf16 conversion, 1/8 attention scale folded into Wq/bq,
+ * LayerScale folded into proj/fc2, conv weight summed over the 3 identical RGB channels, slice-transformer
+ * matrices transposed).  Fails if a required tensor was never set.  Synchronises `stream`. */
+MST_API int mst_finalize_weights(mst_handle h, void* stream);
+
+/* Bytes of scratch mst_forward needs for a [B,1,D,H,W] batch. */
+MST_API int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W, size_t* bytes);
+
+/* DinoV2ClassifierSlice.forward (dino.py:110-167).
+ *   src        [B,1,D,H,W] fp32 (H, W multiples of 14; (H/14)*(W/14)+1 == pos_tokens; else error)
+ *   pad_mask   nullable [B,D] uint8, non-zero = ignore slice (dino.py:147-150)
+ *   logits     [B,out_ch] fp32                         feat       nullable [B,embed_dim] (without_linear, dino.py:164)
+ *   enc_cls    nullable [B*D,embed_dim]: encoder output per slice (dino.py:131)
+ *   plane_cls  nullable [B*D,enc_heads,pos_tokens]: row 0 of the LAST encoder block's attention -- the only part
+ *              of attention_maps the getters read (dino.py:190-192)
+ *   slice_cls  nullable [B,slice_heads,D+1]: row 0 of the slice attention (dino.py:174-175) */
+MST_API int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
+                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* get_plane_attention / get_slice_attention / get_attention_maps (dino.py:173-202) and the caller's
+ * head-mean + reshape + trilinear upsample (scripts/main_predict.py:73-74,100,161-162), batched.
+ *   attn_maps  nullable [B*D,enc_heads,P] (get_attention_maps)   plane_attn nullable [B*D,enc_heads,P] (get_plane_attention)
+ *   slice_attn nullable [B*D] (get_slice_attention)
+ *   coarse     nullable [B,1,D,gh,gw] (required when full != NULL)   full nullable [B,1,D,H,W] */
+MST_API int mst_saliency(const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
+                 int32_t slice_heads, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
+                 float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream);
+
+/* Instrumentation: kernels launched by this handle so far; per-category device time (CUDA events recorded on the
+ * caller's stream around every launch between begin and end; end synchronises the device).  `ms`/`launches` must
+ * hold at least 16 entries; mst_profile_categories() names them, comma separated, in order. */
+MST_API unsigned long long mst_launch_count(mst_handle h);
+MST_API const char* mst_profile_categories(void);
+MST_API int mst_profile_begin(mst_handle h);
+MST_API int mst_profile_end(mst_handle h, double* ms, int64_t* launches, int32_t n);
+
+/* Kernel-level entry points (unit parity tests and micro-benchmarks call the same kernels the forward uses).
+ * mode: 0 bias, 1 bias+GELU(erf), 2 bias+residual.  A [M,K], W [N,K] (nn.Linear layout), out/res [M,N]. */
+MST_API int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode,
+                         const float* bias, const void* res, void* out, void* stream);
+MST_API int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, int32_t K, int32_t mode,
+                        const float* bias, const float* res, float* out, void* stream);
+/* qkv [BD*N, 3*heads*64] (q pre-scaled) -> out [BD*N, heads*64] */
+MST_API int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
+MST_API int mst_kernel_attention_f32(const float* qkv, float* out, int32_t BD, int32_t N, int32_t heads, void* stream);
+MST_API int mst_kernel_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t E,
+                              float eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MST_B200_H_ */

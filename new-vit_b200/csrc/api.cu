@@ -1,0 +1,562 @@
+// C ABI (include/mst_b200.h): handle, weight store + packing, forward orchestration, saliency.
+#include <stdarg.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mst_b200.h"
+#include "common.cuh"
+
+namespace mst {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+constexpr int KP = 256;  // im2col K (196) padded to a multiple of the 64-wide TMA box
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing kernels
+// ---------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T cvt(float v);
+template <> __device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 cvt<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// dst[n,k] = W[n,k] * (rowscale ? rowscale[n] : 1) * (n < nscaled ? s : 1);  bias likewise
+template <typename T>
+__global__ void pack_linear_kernel(const float* __restrict__ W, const float* __restrict__ b, const float* __restrict__ rowscale,
+                                   int nscaled, float s, T* __restrict__ Wd, float* __restrict__ bd, int N, int K) {
+    const int64_t total = static_cast<int64_t>(N) * K;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int n = static_cast<int>(i / K);
+        float f = (rowscale ? rowscale[n] : 1.0f) * (n < nscaled ? s : 1.0f);
+        Wd[i] = cvt<T>(W[i] * f);
+        if (i % K == 0) bd[n] = b[n] * f;
+    }
+}
+// conv weight [E,3,14,14] -> [E,KP]: sum over the 3 identical input channels (dino.py:127 repeats gray -> RGB)
+template <typename T>
+__global__ void pack_patch_kernel(const float* __restrict__ W, T* __restrict__ Wd, int E) {
+    const int total = E * KP;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int n = i / KP, c = i % KP;
+        float v = 0.f;
+        if (c < 196) v = (W[(n * 3 + 0) * 196 + c] + W[(n * 3 + 1) * 196 + c]) + W[(n * 3 + 2) * 196 + c];
+        Wd[i] = cvt<T>(v);
+    }
+}
+// posb[p,n] = pos[1+p,n] + conv_bias[n];  cls_pos0[n] = cls[n] + pos[0,n]   (vision_transformer.py:219-220)
+__global__ void pack_pos_kernel(const float* __restrict__ pos, const float* __restrict__ cls, const float* __restrict__ cbias,
+                                float* __restrict__ posb, float* __restrict__ cls_pos0, int P, int E) {
+    const int total = (P + 1) * E;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int t = i / E, n = i % E;
+        if (t == 0) cls_pos0[n] = cls[n] + pos[n];
+        else posb[(t - 1) * E + n] = pos[i] + cbias[n];
+    }
+}
+__global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int N, int K) {  // W[N,K] -> Wt[K,N]
+    const int64_t total = static_cast<int64_t>(N) * K;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(i / N), n = static_cast<int>(i % N);
+        Wt[i] = W[static_cast<int64_t>(n) * K + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// handle
+// ---------------------------------------------------------------------------------------------------
+struct Layer {
+    void *wqkv = nullptr, *wproj = nullptr, *wfc1 = nullptr, *wfc2 = nullptr;
+    float *bqkv = nullptr, *bproj = nullptr, *bfc1 = nullptr, *bfc2 = nullptr;
+    const float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
+};
+
+}  // namespace mst
+
+namespace mst {
+enum Cat { CAT_IM2COL = 0, CAT_GEMM_PATCH, CAT_LAYERNORM, CAT_GEMM_QKV, CAT_ATTENTION, CAT_GEMM_PROJ, CAT_GEMM_FC1,
+           CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, NUM_CAT };
+static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion";
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int cat; size_t e0, e1; };
+    std::vector<Rec> recs;
+    cudaEvent_t next() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+};
+}  // namespace mst
+
+struct mst_handle_s {
+    mst::Profiler prof;
+    unsigned long long launches = 0;
+    mst_config cfg;
+    int num_sms = 0;
+    bool finalized = false;
+    std::map<std::string, float*> master;       // canonical name -> device fp32 (owned)
+    std::map<std::string, int64_t> expected;    // canonical name -> numel
+    std::map<std::string, bool> have;
+    std::vector<void*> owned;                   // packed buffers
+    std::vector<mst::Layer> layers;
+    void* wpatch = nullptr;
+    float *posb = nullptr, *cls_pos0 = nullptr;
+    mst::SliceWeights sw{};
+};
+
+namespace mst {
+
+static size_t elem_size(const mst_config& c) { return c.precision == MST_PRECISION_BF16 ? 2 : 4; }
+
+static void expected_names(mst_handle h) {
+    const int E = h->cfg.embed_dim, C = h->cfg.out_ch;
+    auto& x = h->expected;
+    x["cls_token"] = E;
+    x["encoder.cls_token"] = E;
+    x["encoder.pos_embed"] = static_cast<int64_t>(h->cfg.pos_tokens) * E;
+    x["encoder.patch_embed.proj.weight"] = static_cast<int64_t>(E) * 3 * 196;
+    x["encoder.patch_embed.proj.bias"] = E;
+    for (int i = 0; i < h->cfg.depth; ++i) {
+        const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+        x[p + "norm1.weight"] = E; x[p + "norm1.bias"] = E;
+        x[p + "attn.qkv.weight"] = 3LL * E * E; x[p + "attn.qkv.bias"] = 3 * E;
+        x[p + "attn.proj.weight"] = 1LL * E * E; x[p + "attn.proj.bias"] = E;
+        x[p + "norm2.weight"] = E; x[p + "norm2.bias"] = E;
+        x[p + "mlp.fc1.weight"] = 4LL * E * E; x[p + "mlp.fc1.bias"] = 4 * E;
+        x[p + "mlp.fc2.weight"] = 4LL * E * E; x[p + "mlp.fc2.bias"] = E;
+    }
+    x["encoder.norm.weight"] = E; x["encoder.norm.bias"] = E;
+    const std::string q = "slice_fusion.layers.0.";
+    x[q + "self_attn.in_proj_weight"] = 3LL * E * E; x[q + "self_attn.in_proj_bias"] = 3 * E;
+    x[q + "self_attn.out_proj.weight"] = 1LL * E * E; x[q + "self_attn.out_proj.bias"] = E;
+    x[q + "linear1.weight"] = 1LL * E * E; x[q + "linear1.bias"] = E;
+    x[q + "linear2.weight"] = 1LL * E * E; x[q + "linear2.bias"] = E;
+    x[q + "norm1.weight"] = E; x[q + "norm1.bias"] = E;
+    x[q + "norm2.weight"] = E; x[q + "norm2.bias"] = E;
+    x["slice_fusion.norm.weight"] = E; x["slice_fusion.norm.bias"] = E;
+    x["linear.weight"] = 1LL * C * E; x["linear.bias"] = C;
+}
+
+// "encoder.blocks.0.7.x" (BlockChunk naming, vision_transformer.py:153-160) -> "encoder.blocks.7.x"
+static std::string canonical_name(const std::string& name) {
+    const std::string pre = "encoder.blocks.";
+    if (name.compare(0, pre.size(), pre) != 0) return name;
+    size_t p = pre.size(), e = name.find('.', p);
+    if (e == std::string::npos) return name;
+    const size_t e2 = name.find('.', e + 1);
+    if (e2 != std::string::npos) {
+        bool digits = e2 > e + 1;
+        for (size_t i = e + 1; i < e2; ++i) digits = digits && isdigit(static_cast<unsigned char>(name[i]));
+        if (digits) return pre + name.substr(e + 1);
+    }
+    return name;
+}
+
+template <typename T>
+static int alloc_dev(mst_handle h, T** p, size_t count) {
+    void* q = nullptr;
+    MST_CHECK_CUDA(cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 16));
+    h->owned.push_back(q);
+    *p = static_cast<T*>(q);
+    return 0;
+}
+
+template <typename T>
+static int pack_linear(mst_handle h, const std::string& wname, const std::string& bname, const float* rowscale, int nscaled,
+                       float s, int N, int K, void** Wd, float** bd, cudaStream_t st) {
+    T* w;
+    MST_PROPAGATE(alloc_dev<T>(h, &w, static_cast<size_t>(N) * K));
+    MST_PROPAGATE(alloc_dev<float>(h, bd, N));
+    pack_linear_kernel<T><<<1024, 256, 0, st>>>(h->master[wname], h->master[bname], rowscale, nscaled, s, w, *bd, N, K);
+    MST_CHECK_CUDA(cudaGetLastError());
+    *Wd = w;
+    return 0;
+}
+
+static int transposed(mst_handle h, const std::string& name, int N, int K, const float** out, cudaStream_t st) {
+    float* t;
+    MST_PROPAGATE(alloc_dev<float>(h, &t, static_cast<size_t>(N) * K));
+    transpose_kernel<<<512, 256, 0, st>>>(h->master[name], t, N, K);
+    MST_CHECK_CUDA(cudaGetLastError());
+    *out = t;
+    return 0;
+}
+
+template <typename T>
+static int finalize_t(mst_handle h, cudaStream_t st) {
+    const int E = h->cfg.embed_dim, P = h->cfg.pos_tokens - 1;
+    h->layers.assign(h->cfg.depth, Layer());
+    for (int i = 0; i < h->cfg.depth; ++i) {
+        const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+        Layer& L = h->layers[i];
+        const float* g1 = h->have.count(p + "ls1.gamma") ? h->master[p + "ls1.gamma"] : nullptr;
+        const float* g2 = h->have.count(p + "ls2.gamma") ? h->master[p + "ls2.gamma"] : nullptr;
+        // q rows (first E outputs) carry the 1/sqrt(64) attention scale (attention.py:60): exact power of two
+        MST_PROPAGATE(pack_linear<T>(h, p + "attn.qkv.weight", p + "attn.qkv.bias", nullptr, E, 0.125f, 3 * E, E, &L.wqkv, &L.bqkv, st));
+        MST_PROPAGATE(pack_linear<T>(h, p + "attn.proj.weight", p + "attn.proj.bias", g1, 0, 1.f, E, E, &L.wproj, &L.bproj, st));
+        MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc1.weight", p + "mlp.fc1.bias", nullptr, 0, 1.f, 4 * E, E, &L.wfc1, &L.bfc1, st));
+        MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc2.weight", p + "mlp.fc2.bias", g2, 0, 1.f, E, 4 * E, &L.wfc2, &L.bfc2, st));
+        L.n1w = h->master[p + "norm1.weight"]; L.n1b = h->master[p + "norm1.bias"];
+        L.n2w = h->master[p + "norm2.weight"]; L.n2b = h->master[p + "norm2.bias"];
+    }
+    T* wp;
+    MST_PROPAGATE(alloc_dev<T>(h, &wp, static_cast<size_t>(E) * KP));
+    pack_patch_kernel<T><<<256, 256, 0, st>>>(h->master["encoder.patch_embed.proj.weight"], wp, E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    h->wpatch = wp;
+    MST_PROPAGATE(alloc_dev<float>(h, &h->posb, static_cast<size_t>(P) * E));
+    MST_PROPAGATE(alloc_dev<float>(h, &h->cls_pos0, E));
+    pack_pos_kernel<<<256, 256, 0, st>>>(h->master["encoder.pos_embed"], h->master["encoder.cls_token"],
+                                         h->master["encoder.patch_embed.proj.bias"], h->posb, h->cls_pos0, P, E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    const std::string q = "slice_fusion.layers.0.";
+    SliceWeights& s = h->sw;
+    s.cls_token = h->master["cls_token"];
+    s.n1w = h->master[q + "norm1.weight"]; s.n1b = h->master[q + "norm1.bias"];
+    s.n2w = h->master[q + "norm2.weight"]; s.n2b = h->master[q + "norm2.bias"];
+    s.nfw = h->master["slice_fusion.norm.weight"]; s.nfb = h->master["slice_fusion.norm.bias"];
+    s.in_b = h->master[q + "self_attn.in_proj_bias"]; s.out_b = h->master[q + "self_attn.out_proj.bias"];
+    s.l1_b = h->master[q + "linear1.bias"]; s.l2_b = h->master[q + "linear2.bias"]; s.head_b = h->master["linear.bias"];
+    MST_PROPAGATE(transposed(h, q + "self_attn.in_proj_weight", 3 * E, E, &s.in_wt, st));
+    MST_PROPAGATE(transposed(h, q + "self_attn.out_proj.weight", E, E, &s.out_wt, st));
+    MST_PROPAGATE(transposed(h, q + "linear1.weight", E, E, &s.l1_wt, st));
+    MST_PROPAGATE(transposed(h, q + "linear2.weight", E, E, &s.l2_wt, st));
+    MST_PROPAGATE(transposed(h, "linear.weight", h->cfg.out_ch, E, &s.head_wt, st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------
+struct Workspace {
+    void *A0, *x, *xn, *qkv, *hid, *ao_cls, *xc, *xcn, *hc;
+    float *enc_cls, *hs;
+    size_t total;
+};
+static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t* base) {
+    const size_t es = elem_size(c);
+    const int64_t E = c.embed_dim, BD = static_cast<int64_t>(B) * D, P = static_cast<int64_t>(H / 14) * (W / 14), N = P + 1, M = BD * N;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~static_cast<size_t>(255); return p; };
+    Workspace w;
+    w.A0 = take(BD * P * KP * es);
+    w.x = take(M * E * es);
+    w.xn = take(M * E * es);
+    w.qkv = take(M * 3 * E * es);
+    w.hid = take(M * 4 * E * es);
+    w.ao_cls = take(BD * E * es);
+    w.xc = take(BD * E * es);
+    w.xcn = take(BD * E * es);
+    w.hc = take(BD * 4 * E * es);
+    w.enc_cls = static_cast<float*>(take(BD * E * 4));
+    w.hs = static_cast<float*>(take(static_cast<size_t>(B) * (D + 1) * E * 4));
+    w.total = off;
+    return w;
+}
+
+template <typename T> struct Ops;
+template <> struct Ops<bf16> {
+    static int gemm(mst_handle h, const void* A, int64_t lda, const void* W, int M, int N, int K, int mode, const EpiParams& ep, cudaStream_t st) {
+        MST_REQUIRE(lda == K, "bf16 gemm expects a dense A (lda == K)");
+        return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, h->num_sms, st);
+    }
+    static int attention(const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
+        return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, st);
+    }
+};
+template <> struct Ops<float> {
+    static int gemm(mst_handle, const void* A, int64_t lda, const void* W, int M, int N, int K, int mode, const EpiParams& ep, cudaStream_t st) {
+        return gemm_f32_simt(static_cast<const float*>(A), lda, static_cast<const float*>(W), M, N, K, mode, ep, st);
+    }
+    static int attention(const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
+        return launch_attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), BD, N, heads, st);
+    }
+};
+
+// one kernel launch, counted, and bracketed by events when profiling is on
+#define MST_LAUNCH(cat, call)                                                             \
+    do {                                                                                  \
+        size_t _e0 = 0;                                                                   \
+        if (h->prof.on) { _e0 = h->prof.used; cudaEventRecord(h->prof.next(), st); }      \
+        MST_PROPAGATE(call);                                                              \
+        h->launches++;                                                                    \
+        if (h->prof.on) { cudaEventRecord(h->prof.next(), st); h->prof.recs.push_back({cat, _e0, _e0 + 1}); } \
+    } while (0)
+
+template <typename T>
+static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W, const uint8_t* pad_mask, float* logits,
+                     float* feat, float* enc_cls_out, float* plane_cls, float* slice_cls, const Workspace& ws, cudaStream_t st) {
+    const mst_config& c = h->cfg;
+    const int E = c.embed_dim, BD = B * D, P = (H / 14) * (W / 14), N = P + 1;
+    const int64_t M64 = static_cast<int64_t>(BD) * N;
+    MST_REQUIRE(M64 * 4 * E < (1LL << 40) && M64 < (1LL << 31) - 256, "batch too large: %lld tokens", (long long)M64);
+    const int M = static_cast<int>(M64);
+    T* x = static_cast<T*>(ws.x);
+    T* xn = static_cast<T*>(ws.xn);
+
+    // patch embedding + CLS/pos (K1-K3)
+    MST_LAUNCH(CAT_IM2COL, launch_im2col<T>(src, static_cast<T*>(ws.A0), x, h->cls_pos0, BD, H, W, KP, E, st));
+    {
+        EpiParams ep{};
+        ep.posb = h->posb; ep.P = P; ep.out = x; ep.ldo = E;
+        MST_LAUNCH(CAT_GEMM_PATCH, Ops<T>::gemm(h, ws.A0, KP, h->wpatch, BD * P, E, KP, EPI_PATCH, ep, st));
+    }
+    for (int l = 0; l < c.depth; ++l) {
+        const Layer& L = h->layers[l];
+        const bool last = (l == c.depth - 1);
+        // x = x + ls1(attn(norm1(x)))                                   (block.py:112)
+        MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n1w, L.n1b, M, E, 1e-6f, st)));
+        {
+            EpiParams ep{};
+            ep.bias = L.bqkv; ep.out = ws.qkv; ep.ldo = 3 * E;
+            MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, xn, E, L.wqkv, M, 3 * E, E, EPI_BIAS, ep, st));
+        }
+        if (!last) {
+            MST_LAUNCH(CAT_ATTENTION, Ops<T>::attention(ws.qkv, xn, BD, N, c.enc_heads, st));  // xn is dead: reuse as attention output
+            {
+                EpiParams ep{};
+                ep.bias = L.bproj; ep.res = x; ep.ldr = E; ep.out = x; ep.ldo = E;
+                MST_LAUNCH(CAT_GEMM_PROJ, Ops<T>::gemm(h, xn, E, L.wproj, M, E, E, EPI_BIAS_RES, ep, st));
+            }
+            // x = x + ls2(mlp(norm2(x)))                                  (block.py:113)
+            MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n2w, L.n2b, M, E, 1e-6f, st)));
+            {
+                EpiParams ep{};
+                ep.bias = L.bfc1; ep.out = ws.hid; ep.ldo = 4 * E;
+                MST_LAUNCH(CAT_GEMM_FC1, Ops<T>::gemm(h, xn, E, L.wfc1, M, 4 * E, E, EPI_BIAS_GELU, ep, st));
+            }
+            {
+                EpiParams ep{};
+                ep.bias = L.bfc2; ep.res = x; ep.ldr = E; ep.out = x; ep.ldo = E;
+                MST_LAUNCH(CAT_GEMM_FC2, Ops<T>::gemm(h, ws.hid, 4 * E, L.wfc2, M, E, 4 * E, EPI_BIAS_RES, ep, st));
+            }
+        } else {
+            // Last block: only token 0 of each slice is consumed downstream (vision_transformer.py:265,329), so
+            // the query side, proj and the MLP run on the BD CLS rows only; K/V still come from every token.
+            T* ao = static_cast<T*>(ws.ao_cls);
+            T* xc = static_cast<T*>(ws.xc);
+            T* xcn = static_cast<T*>(ws.xcn);
+            MST_LAUNCH(CAT_CLS_ATTENTION, launch_cls_attention<T>(static_cast<const T*>(ws.qkv), ao, plane_cls, BD, N, c.enc_heads, st));
+            {
+                EpiParams ep{};
+                ep.bias = L.bproj; ep.res = x; ep.ldr = static_cast<int64_t>(N) * E; ep.out = xc; ep.ldo = E;
+                MST_LAUNCH(CAT_GEMM_CLS_ROWS, Ops<T>::gemm(h, ao, E, L.wproj, BD, E, E, EPI_BIAS_RES, ep, st));
+            }
+            MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(xc, E, xcn, E, L.n2w, L.n2b, BD, E, 1e-6f, st)));
+            {
+                EpiParams ep{};
+                ep.bias = L.bfc1; ep.out = ws.hc; ep.ldo = 4 * E;
+                MST_LAUNCH(CAT_GEMM_CLS_ROWS, Ops<T>::gemm(h, xcn, E, L.wfc1, BD, 4 * E, E, EPI_BIAS_GELU, ep, st));
+            }
+            {
+                EpiParams ep{};
+                ep.bias = L.bfc2; ep.res = xc; ep.ldr = E; ep.out = xc; ep.ldo = E;
+                MST_LAUNCH(CAT_GEMM_CLS_ROWS, Ops<T>::gemm(h, ws.hc, 4 * E, L.wfc2, BD, E, 4 * E, EPI_BIAS_RES, ep, st));
+            }
+            // final encoder LayerNorm on the CLS rows (vision_transformer.py:263-265), fp32 out
+            float* enc = enc_cls_out ? enc_cls_out : ws.enc_cls;
+            MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, float>(xc, E, enc, E, h->master["encoder.norm.weight"],
+                                                                 h->master["encoder.norm.bias"], BD, E, 1e-6f, st)));
+            MST_LAUNCH(CAT_SLICE_FUSION, launch_slice_fusion(enc, pad_mask, h->sw, ws.hs, logits, feat, slice_cls, B, D, E,
+                                                         c.slice_heads, c.out_ch, st));
+        }
+    }
+    return 0;
+}
+
+}  // namespace mst
+
+// ---------------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------------
+using namespace mst;
+
+extern "C" {
+
+int mst_abi_version(void) { return MST_ABI_VERSION; }
+const char* mst_last_error(void) { return g_err.c_str(); }
+
+int mst_create(const mst_config* cfg, mst_handle* out) {
+    MST_REQUIRE(cfg && out, "mst_create: null argument");
+    MST_REQUIRE(cfg->embed_dim == 384 || cfg->embed_dim == 768 || cfg->embed_dim == 1024,
+                "mst_create: embed_dim %d unsupported (384/768/1024)", cfg->embed_dim);
+    MST_REQUIRE(cfg->enc_heads * 64 == cfg->embed_dim, "mst_create: enc_heads*64 must equal embed_dim");
+    MST_REQUIRE(cfg->depth >= 1 && cfg->out_ch >= 1 && cfg->pos_tokens >= 2, "mst_create: bad depth/out_ch/pos_tokens");
+    MST_REQUIRE(cfg->slice_heads >= 1 && cfg->slice_heads <= 16 && cfg->embed_dim % cfg->slice_heads == 0, "mst_create: bad slice_heads");
+    MST_REQUIRE(cfg->precision == MST_PRECISION_FP32 || cfg->precision == MST_PRECISION_BF16, "mst_create: bad precision");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    MST_REQUIRE(e == cudaSuccess && ndev > 0, "mst_create: no CUDA device (%s); this library has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    MST_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "mst_create: device %d out of range", cfg->device);
+    MST_CHECK_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    MST_CHECK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    MST_REQUIRE(prop.major == 10, "mst_create: device is sm_%d%d; this library is built for sm_100a (B200) only", prop.major, prop.minor);
+    mst_handle h = new mst_handle_s();
+    h->cfg = *cfg;
+    h->num_sms = prop.multiProcessorCount;
+    expected_names(h);
+    *out = h;
+    return 0;
+}
+
+int mst_destroy(mst_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : h->master) cudaFree(kv.second);
+    for (void* p : h->owned) cudaFree(p);
+    for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
+    delete h;
+    return 0;
+}
+
+int mst_set_weight(mst_handle h, const char* name, const float* dev_fp32, int64_t numel, void* stream) {
+    MST_REQUIRE(h && name && dev_fp32, "mst_set_weight: null argument");
+    const std::string key = canonical_name(name);
+    if (key == "encoder.mask_token") return 0;
+    int64_t want = -1;
+    auto it = h->expected.find(key);
+    if (it != h->expected.end()) want = it->second;
+    else if (key.size() > 10 && (key.rfind(".ls1.gamma") == key.size() - 10 || key.rfind(".ls2.gamma") == key.size() - 10)) want = h->cfg.embed_dim;
+    MST_REQUIRE(want >= 0, "mst_set_weight: unexpected tensor '%s'", name);
+    MST_REQUIRE(want == numel, "mst_set_weight: '%s' has %lld elements, expected %lld", name, (long long)numel, (long long)want);
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    float*& dst = h->master[key];
+    if (!dst) MST_CHECK_CUDA(cudaMalloc(&dst, numel * sizeof(float)));
+    MST_CHECK_CUDA(cudaMemcpyAsync(dst, dev_fp32, numel * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    h->have[key] = true;
+    h->finalized = false;
+    return 0;
+}
+
+int mst_finalize_weights(mst_handle h, void* stream) {
+    MST_REQUIRE(h, "mst_finalize_weights: null handle");
+    for (auto& kv : h->expected) MST_REQUIRE(h->have.count(kv.first), "mst_finalize_weights: tensor '%s' was never set", kv.first.c_str());
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MST_CHECK_CUDA(cudaStreamSynchronize(st));
+    for (void* p : h->owned) cudaFree(p);
+    h->owned.clear();
+    if (h->cfg.precision == MST_PRECISION_BF16) {
+        MST_PROPAGATE(tma_init());
+        MST_PROPAGATE(finalize_t<bf16>(h, st));
+    } else {
+        MST_PROPAGATE(finalize_t<float>(h, st));
+    }
+    MST_CHECK_CUDA(cudaStreamSynchronize(st));
+    h->finalized = true;
+    return 0;
+}
+
+static int check_shape(mst_handle h, int B, int D, int H, int W) {
+    MST_REQUIRE(B >= 1 && D >= 1, "empty batch: B=%d D=%d", B, D);
+    MST_REQUIRE(H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0,
+                "Input image height/width (%d, %d) is not a multiple of patch size 14", H, W);  // patch_embed.py:72-73
+    MST_REQUIRE((H / 14) * (W / 14) + 1 == h->cfg.pos_tokens,
+                "input %dx%d gives %d tokens but pos_embed has %d: set an interpolated pos_embed for this size first",
+                H, W, (H / 14) * (W / 14) + 1, h->cfg.pos_tokens);
+    return 0;
+}
+
+int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W, size_t* bytes) {
+    MST_REQUIRE(h && bytes, "mst_workspace_bytes: null argument");
+    MST_PROPAGATE(check_shape(h, B, D, H, W));
+    *bytes = carve(h->cfg, B, D, H, W, nullptr).total;
+    return 0;
+}
+
+int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
+                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, void* workspace,
+                size_t workspace_bytes, void* stream) {
+    MST_REQUIRE(h && src && logits && workspace, "mst_forward: null argument");
+    MST_REQUIRE(h->finalized, "mst_forward: weights not finalized");
+    MST_PROPAGATE(check_shape(h, B, D, H, W));
+    MST_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mst_forward: workspace must be 256-byte aligned");
+    Workspace ws = carve(h->cfg, B, D, H, W, static_cast<uint8_t*>(workspace));
+    MST_REQUIRE(ws.total <= workspace_bytes, "mst_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (h->cfg.precision == MST_PRECISION_BF16)
+        return forward_t<bf16>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, ws, st);
+    return forward_t<float>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, ws, st);
+}
+
+int mst_saliency(const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
+                 int32_t slice_heads, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
+                 float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream) {
+    MST_REQUIRE(plane_cls && slice_cls, "mst_saliency: null argument");
+    MST_REQUIRE(B >= 1 && D >= 1 && gh >= 1 && gw >= 1, "mst_saliency: empty input");
+    return launch_saliency(plane_cls, slice_cls, B, D, enc_heads, slice_heads, gh, gw, H, W, attn_maps, plane_attn, slice_attn, coarse, full,
+                           static_cast<cudaStream_t>(stream));
+}
+
+const char* mst_profile_categories(void) { return kCatNames; }
+unsigned long long mst_launch_count(mst_handle h) { return h ? h->launches : 0; }
+int mst_profile_begin(mst_handle h) {
+    MST_REQUIRE(h, "mst_profile_begin: null handle");
+    h->prof.on = true; h->prof.used = 0; h->prof.recs.clear();
+    return 0;
+}
+int mst_profile_end(mst_handle h, double* ms, int64_t* launches, int32_t n) {
+    MST_REQUIRE(h && ms && launches && n >= NUM_CAT, "mst_profile_end: need room for %d categories", (int)NUM_CAT);
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    MST_CHECK_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+    for (auto& r : h->prof.recs) {
+        float t = 0.f;
+        MST_CHECK_CUDA(cudaEventElapsedTime(&t, h->prof.pool[r.e0], h->prof.pool[r.e1]));
+        ms[r.cat] += t; launches[r.cat] += 1;
+    }
+    h->prof.on = false; h->prof.used = 0; h->prof.recs.clear();
+    return 0;
+}
+
+static int num_sms_current() {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode, const float* bias,
+                         const void* res, void* out, void* stream) {
+    MST_REQUIRE(A && W && out && bias && mode >= 0 && mode <= 2, "mst_kernel_gemm_bf16: bad argument");
+    EpiParams ep{};
+    ep.bias = bias; ep.res = res; ep.ldr = N; ep.out = out; ep.ldo = N;
+    return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, num_sms_current(),
+                        static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, int32_t K, int32_t mode, const float* bias,
+                        const float* res, float* out, void* stream) {
+    MST_REQUIRE(A && W && out && bias && mode >= 0 && mode <= 2, "mst_kernel_gemm_f32: bad argument");
+    EpiParams ep{};
+    ep.bias = bias; ep.res = res; ep.ldr = N; ep.out = out; ep.ldo = N;
+    return gemm_f32_simt(A, K, W, M, N, K, mode, ep, static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
+    MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16: null argument");
+    return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_attention_f32(const float* qkv, float* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
+    MST_REQUIRE(qkv && out, "mst_kernel_attention_f32: null argument");
+    return launch_attention_f32(qkv, out, BD, N, heads, static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t E,
+                              float eps, void* stream) {
+    MST_REQUIRE(x && y && gamma && beta, "mst_kernel_layernorm_bf16: null argument");
+    return launch_layernorm<bf16, bf16>(static_cast<const bf16*>(x), E, static_cast<bf16*>(y), E, gamma, beta, rows, E, eps,
+                                        static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Shared declarations for the MST-DINOv2 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace mst {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (C-ABI returns int status; message via mst_last_error) -----------------------
+void set_error(const char* fmt, ...);
+#define MST_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            mst::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+#define MST_REQUIRE(cond, ...)                 \
+    do {                                       \
+        if (!(cond)) {                         \
+            mst::set_error(__VA_ARGS__);       \
+            return 1;                          \
+        }                                      \
+    } while (0)
+#define MST_PROPAGATE(expr)        \
+    do {                           \
+        int _s = (expr);           \
+        if (_s != 0) return _s;    \
+    } while (0)
+
+// ---- GEMM epilogues --------------------------------------------------------------------------------
+// C[row, n] = epi(acc[row, n]) for  acc = A[M,K] . W[N,K]^T  (nn.Linear convention: W is [out, in]).
+enum EpiMode : int {
+    EPI_BIAS = 0,       // out = acc + bias[n]
+    EPI_BIAS_GELU = 1,  // out = gelu_erf(acc + bias[n])                (reference mlp.py:35-36)
+    EPI_BIAS_RES = 2,   // out = res[row*ldr + n] + acc + bias[n]       (block.py:112-113; LayerScale folded in W,b)
+    EPI_PATCH = 3       // out[(row/P)*(P+1) + 1 + row%P, n] = acc + posb[(row%P)*N + n]   (patch_embed.py:75-77 +
+                        //                                      vision_transformer.py:219-220; bias folded in posb)
+};
+
+struct EpiParams {
+    const float* bias;   // [N] fp32 (EPI_BIAS*, EPI_BIAS_RES)
+    const void* res;     // residual rows, same dtype as out (EPI_BIAS_RES)
+    int64_t ldr;         // residual row stride in elements
+    const float* posb;   // [P, N] fp32 (EPI_PATCH)
+    int P;               // patches per slice (EPI_PATCH)
+    void* out;           // output, dtype T
+    int64_t ldo;         // output row stride in elements
+};
+
+// erf via the rational minimax on [-4,4] (max abs error 3.8e-7 in fp32; checked against math.erf).
+__device__ __forceinline__ float erf_fast(float x) {
+    x = fminf(fmaxf(x, -4.0f), 4.0f);
+    const float x2 = x * x;
+    float p = -2.72614225801306e-10f;
+    p = fmaf(p, x2, 2.77068142495902e-08f);
+    p = fmaf(p, x2, -2.10102402082508e-06f);
+    p = fmaf(p, x2, -5.69250639462346e-05f);
+    p = fmaf(p, x2, -7.34990630326855e-04f);
+    p = fmaf(p, x2, -2.95459980854025e-03f);
+    p = fmaf(p, x2, -1.60960333262415e-02f);
+    p *= x;
+    float q = -1.45660718464996e-05f;
+    q = fmaf(q, x2, -2.13374055278905e-04f);
+    q = fmaf(q, x2, -1.68282697438203e-03f);
+    q = fmaf(q, x2, -7.37332916720468e-03f);
+    q = fmaf(q, x2, -1.42647390514189e-02f);
+    return __fdividef(p, q);
+}
+template <bool kExact>
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float e = kExact ? erff(x * 0.70710678118654752f) : erf_fast(x * 0.70710678118654752f);
+    const float hx = 0.5f * x;
+    return fmaf(hx, e, hx);
+}
+
+// ---- kernel launchers (each returns 0 or sets the error and returns non-zero) ----------------------
+struct TmaDesc {  // opaque 128-byte CUtensorMap
+    alignas(64) uint8_t bytes[128];
+};
+int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
+int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_rows);
+
+// bf16 tensor-core GEMM (tcgen05 + TMA + TMEM). A: [M,K] bf16 row-major (lda=K), W: [N,K] bf16 row-major.
+int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
+                 cudaStream_t stream);
+// fp32 CUDA-core GEMM (fp32 parity mode). A: [M,K] fp32 (lda), W: [N,K] fp32.
+int gemm_f32_simt(const float* A, int64_t lda, const float* W, int M, int N, int K, int mode, const EpiParams& ep,
+                  cudaStream_t stream);
+
+template <typename T>
+int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, int BD, int H, int W, int KP, int E,
+                  cudaStream_t stream);
+template <typename TIn, typename TOut>
+int launch_layernorm(const TIn* x, int64_t ldx, TOut* y, int64_t ldy, const float* gamma, const float* beta, int rows,
+                     int E, float eps, cudaStream_t stream);
+int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, cudaStream_t stream);
+int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads, cudaStream_t stream);
+template <typename T>
+int launch_cls_attention(const T* qkv, T* out_cls, float* plane_cls, int BD, int N, int heads, cudaStream_t stream);
+
+struct SliceWeights {  // fp32, linear weights pre-transposed to [in][out]
+    const float *cls_token, *n1w, *n1b, *in_wt, *in_b, *out_wt, *out_b, *n2w, *n2b, *l1_wt, *l1_b, *l2_wt, *l2_b, *nfw,
+        *nfb, *head_wt, *head_b;
+};
+int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,
+                        float* logits, float* feat, float* slice_cls, int B, int D, int E, int heads, int out_ch,
+                        cudaStream_t stream);
+int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int gh,
+                    int gw, int H, int W, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full,
+                    cudaStream_t stream);
+
+}  // namespace mst

@@ -1,0 +1,327 @@
+// bf16 GEMM on the 5th-gen tensor cores:  acc[M,N] = A[M,K] . W[N,K]^T,  fused epilogues (common.cuh).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 (1 lane)  TMA producer   : A k-chunks (128 x 64 bf16, 128B swizzle) through a STAGES-deep ring
+//   warp 1 (1 lane)  MMA issuer     : tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction
+//   warp 2           TMEM allocator : 2 accumulator stages of BN fp32 columns (epilogue overlaps next tile)
+//   warps 4..7       epilogue       : tcgen05.ld 32x32b -> bias / GELU / residual / pos-embed -> bf16 -> HBM
+//
+// Weight-resident mode (KCH > 0): K <= 384, so the whole [BN x K] weight slab (<= 144 KB) is loaded into
+// shared memory ONCE per CTA and only A streams; each CTA owns one n-block and walks m-blocks.  This cuts
+// the L2->SM traffic per 128x192x384 tile from 240 KB to 96 KB, which is what bounds a K=384 GEMM here
+// (DESIGN.md "GEMM roofline").  Streaming mode (KCH == 0) rings both operands (fc2, K = 1536).
+#include <cuda.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mst {
+
+// ---------------------------------------------------------------------------------------------------
+// TMA descriptor creation (driver entry point resolved at run time; the library does not link libcuda)
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+int tma_init() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MST_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MST_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available (driver too old?)");
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return 0;
+}
+
+int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_rows) {
+    MST_PROPAGATE(tma_init());
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
+    MST_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    MST_REQUIRE((row_stride_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
+    MST_REQUIRE(box_inner * 2 == 128 && box_rows <= 256, "TMA box must be 64 bf16 wide and <= 256 rows");
+    cuuint64_t gdim[2] = {inner, rows};
+    cuuint64_t gstride[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                          const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu)", (int)r,
+                (unsigned long long)inner, (unsigned long long)rows);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int GEMM_THREADS = 256;
+
+template <int BN, int KCH, int STAGES>
+struct GemmSmem {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int B_BUFS = KCH > 0 ? KCH : STAGES;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+    static constexpr int BAR_OFF = B_OFF + B_BUFS * B_TILE_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 1 + 4;
+    static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
+};
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiParams& ep, int64_t row, int M, int N,
+                                               int n0) {
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (row >= M) return;
+    int64_t orow = row;
+    if (MODE == EPI_PATCH) {
+        const int p = static_cast<int>(row % ep.P);
+        orow = (row / ep.P) * (ep.P + 1) + 1 + p;
+        const float4* pb = reinterpret_cast<const float4*>(ep.posb + static_cast<int64_t>(p) * N + n0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(pb + i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+    } else {
+        const float4* pb = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 b = __ldg(pb + i);
+            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+        }
+    }
+    if (MODE == EPI_BIAS_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+    }
+    if (MODE == EPI_BIAS_RES) {
+        const uint4* pr = reinterpret_cast<const uint4*>(static_cast<const bf16*>(ep.res) + row * ep.ldr + n0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 u = pr[i];
+            float2 f;
+            f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+            f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+            f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+            f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+        }
+    }
+    uint4* po = reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        po[i] = u;
+    }
+}
+
+template <int BN, int KCH, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, int M, int N, int K, int mode,
+               EpiParams ep) {
+    using L = GemmSmem<BN, KCH, STAGES>;
+    constexpr bool kResident = KCH > 0;
+    constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
+    static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* sA = smem + L::A_OFF;
+    uint8_t* sB = smem + L::B_OFF;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* bfull_bar = bars + 2 * STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES + 1;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 3;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n_tiles = N / BN;
+    const int m_tiles = (M + BM - 1) / BM;
+    const int kchunks = K / BK;
+
+    // tile sequence of this CTA
+    int t_first, t_step, t_count;
+    if (kResident) {  // one n-block per CTA; m-blocks strided by the group size
+        const int gs = gridDim.x / n_tiles;
+        const int m0 = blockIdx.x / n_tiles;
+        t_first = m0; t_step = gs;
+        t_count = m0 < m_tiles ? (m_tiles - m0 + gs - 1) / gs : 0;
+    } else {
+        const int total = m_tiles * n_tiles;
+        t_first = blockIdx.x; t_step = gridDim.x;
+        t_count = t_first < total ? (total - t_first + t_step - 1) / t_step : 0;
+    }
+    const int n_fixed = blockIdx.x % n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(bfull_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            if (kResident && t_count > 0) {
+                mbar_arrive_expect_tx(bfull_bar, KCH * L::B_TILE_BYTES);
+                for (int kc = 0; kc < KCH; ++kc)
+                    tma_load_2d(sB + kc * L::B_TILE_BYTES, &tmB, bfull_bar, kc * BK, n_fixed * BN);
+            }
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < t_count; ++it) {
+                const int t = t_first + it * t_step;
+                const int m_blk = kResident ? t : t / n_tiles;
+                const int n_blk = kResident ? n_fixed : t % n_tiles;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + (kResident ? 0 : L::B_TILE_BYTES));
+                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, m_blk * BM);
+                    if (!kResident)
+                        tma_load_2d(sB + stage * L::B_TILE_BYTES, &tmB, &full_bar[stage], kc * BK, n_blk * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+            if (kResident && t_count > 0) { mbar_wait(bfull_bar, 0); tc_fence_after_sync(); }
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int it = 0; it < t_count; ++it) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + (kResident ? kc : stage) * L::B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        umma_bf16_ss(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
+                                     umma_desc_sw128_kmajor(b_addr + k * 32), idesc, (kc | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int w = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may access
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int it = 0; it < t_count; ++it) {
+            const int t = t_first + it * t_step;
+            const int m_blk = kResident ? t : t / n_tiles;
+            const int n_blk = kResident ? n_fixed : t % n_tiles;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after_sync();
+            const int64_t row = static_cast<int64_t>(m_blk) * BM + w * 32 + lane;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + static_cast<uint32_t>(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(taddr + c * 32, r);
+                tmem_ld_wait();
+                const int n0 = n_blk * BN + c * 32;
+                switch (mode) {
+                    case EPI_BIAS: epilogue_chunk<EPI_BIAS>(r, ep, row, M, N, n0); break;
+                    case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(r, ep, row, M, N, n0); break;
+                    case EPI_BIAS_RES: epilogue_chunk<EPI_BIAS_RES>(r, ep, row, M, N, n0); break;
+                    default: epilogue_chunk<EPI_PATCH>(r, ep, row, M, N, n0); break;
+                }
+            }
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc<kTmemCols>(tmem_base);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host launcher
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int KCH, int STAGES>
+static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, int M, int N, int K, int mode, const EpiParams& ep,
+                      int num_sms, cudaStream_t stream) {
+    using L = GemmSmem<BN, KCH, STAGES>;
+    auto kern = gemm_tc_kernel<BN, KCH, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
+        attr_set = true;
+    }
+    const int n_tiles = N / BN;
+    const int m_tiles = (M + BM - 1) / BM;
+    int grid;
+    if (KCH > 0) {
+        int gs = num_sms / n_tiles;
+        if (gs < 1) gs = 1;
+        if (gs > m_tiles) gs = m_tiles;
+        grid = gs * n_tiles;
+    } else {
+        grid = m_tiles * n_tiles < num_sms ? m_tiles * n_tiles : num_sms;
+    }
+    kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, M, N, K, mode, ep);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
+                 cudaStream_t stream) {
+    MST_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
+    MST_REQUIRE(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
+    MST_REQUIRE(N % 192 == 0 || N % 128 == 0, "gemm: N=%d must be a multiple of 192 or 128", N);
+    MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
+    TmaDesc tmA, tmB;
+    MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
+    if (N % 192 == 0) {
+        MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
+        if (K == 384) return launch_cfg<192, 6, 4>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
+        if (K == 256) return launch_cfg<192, 4, 4>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
+        return launch_cfg<192, 0, 5>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
+    }
+    MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 128));
+    return launch_cfg<128, 0, 6>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
+}
+
+}  // namespace mst

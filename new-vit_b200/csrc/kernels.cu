@@ -1,0 +1,694 @@
+// HBM-bound and small kernels of the MST-DINOv2 path: im2col(+CLS row), LayerNorm, CLS-row attention,
+// fp32 CUDA-core attention and GEMM (fp32 parity mode), the slice transformer, and the saliency
+// combiner + upsampler.  All arithmetic that the reference does in fp32 statistics (LN mean/var,
+// softmax) is fp32 here too.
+#include <math_constants.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mst {
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// block-wide sum; `red` must hold >= 33 floats; all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nw ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < nw ? red[lane] : -CUDART_INF_F;
+        t = warp_max(t);
+        if (lane == 0) red[32] = t;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec4<bf16> {
+    static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        const float2 a = unpack_bf16x2(t.x), b = unpack_bf16x2(t.y);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+        uint2 t;
+        t.x = pack_bf16x2(v[0], v[1]);
+        t.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = t;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// im2col: src [BD,H,W] fp32 -> A0 [BD*P, KP] (column ky*14+kx, zero padded to KP), plus the CLS token
+// row of every slice: x[s*(P+1)] = cls_token + pos_embed[0].  Replaces the rearrange + 3x repeat +
+// conv unfold of reference dino.py:125-127 / patch_embed.py:75-77 (the RGB copies are never
+// materialised: the conv weight is channel-summed at pack time).
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ src, T* __restrict__ A0, T* __restrict__ x,
+                                                      const float* __restrict__ cls_pos0, int H, int W, int KP, int E) {
+    extern __shared__ float tile[];  // [14][W]
+    const int gh = H / 14, gw = W / 14, P = gh * gw;
+    const int s = blockIdx.x / gh, py = blockIdx.x % gh;
+    const float* base = src + (static_cast<int64_t>(s) * H + py * 14) * W;
+    for (int i = threadIdx.x; i < 14 * W; i += blockDim.x) tile[i] = __ldg(base + i);
+    __syncthreads();
+    for (int px = 0; px < gw; ++px) {
+        T* orow = A0 + (static_cast<int64_t>(s) * P + py * gw + px) * KP;
+        for (int c = threadIdx.x; c < KP; c += blockDim.x) {
+            float v = 0.f;
+            if (c < 196) v = tile[(c / 14) * W + px * 14 + (c % 14)];
+            orow[c] = from_f<T>(v);
+        }
+    }
+    if (py == 0) {
+        T* xrow = x + static_cast<int64_t>(s) * (P + 1) * E;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) xrow[e] = from_f<T>(cls_pos0[e]);
+    }
+}
+
+template <typename T>
+int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, int BD, int H, int W, int KP, int E,
+                  cudaStream_t stream) {
+    const int gh = H / 14;
+    im2col_kernel<T><<<BD * gh, 256, 14 * W * sizeof(float), stream>>>(src, A0, x, cls_pos0, H, W, KP, E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_im2col<float>(const float*, float*, float*, const float*, int, int, int, int, int, cudaStream_t);
+template int launch_im2col<bf16>(const float*, bf16*, bf16*, const float*, int, int, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm over rows of E (E % 128 == 0): one warp per row, two-pass in registers, fp32 statistics.
+// (reference block.py:91,94 eps 1e-6; vision_transformer.py:263)
+// ---------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, int E>
+__global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ x, int64_t ldx, TOut* __restrict__ y,
+                                                         int64_t ldy, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int rows, float eps) {
+    constexpr int V = E / 128;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const TIn* xr = x + static_cast<int64_t>(row) * ldx;
+    float v[V][4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        Vec4<TIn>::load(xr + i * 128 + lane * 4, v[i]);
+        s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
+    const float mean = warp_sum(s) * (1.0f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float d = v[i][j] - mean;
+            q = fmaf(d, d, q);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+    TOut* yr = y + static_cast<int64_t>(row) * ldy;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = i * 128 + lane * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        float o[4];
+        o[0] = fmaf((v[i][0] - mean) * rstd, g.x, b.x);
+        o[1] = fmaf((v[i][1] - mean) * rstd, g.y, b.y);
+        o[2] = fmaf((v[i][2] - mean) * rstd, g.z, b.z);
+        o[3] = fmaf((v[i][3] - mean) * rstd, g.w, b.w);
+        Vec4<TOut>::store(yr + c, o);
+    }
+}
+
+template <typename TIn, typename TOut>
+int launch_layernorm(const TIn* x, int64_t ldx, TOut* y, int64_t ldy, const float* gamma, const float* beta, int rows,
+                     int E, float eps, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    const int grid = (rows + 7) / 8;
+    if (E == 384) layernorm_kernel<TIn, TOut, 384><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, eps);
+    else if (E == 768) layernorm_kernel<TIn, TOut, 768><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, eps);
+    else if (E == 1024) layernorm_kernel<TIn, TOut, 1024><<<grid, 256, 0, stream>>>(x, ldx, y, ldy, gamma, beta, rows, eps);
+    else MST_REQUIRE(false, "layernorm: unsupported embed dim %d", E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_layernorm<float, float>(const float*, int64_t, float*, int64_t, const float*, const float*, int, int, float, cudaStream_t);
+template int launch_layernorm<bf16, bf16>(const bf16*, int64_t, bf16*, int64_t, const float*, const float*, int, int, float, cudaStream_t);
+template int launch_layernorm<bf16, float>(const bf16*, int64_t, float*, int64_t, const float*, const float*, int, int, float, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------
+// CLS-row attention of one encoder block (head_dim 64): for (slice, head) the CLS query against all N
+// keys.  Used for the LAST block, whose other query rows are dead (only x[:,0] is consumed,
+// vision_transformer.py:265,329), and it is the side output the saliency path needs: row 0 of the
+// last block's attention (reference dino.py:190-192 reads attention_maps[-1][:, :, 0, :]).
+// q is pre-scaled (0.125 folded into Wq,bq at pack time; attention.py:60).
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) cls_attention_kernel(const T* __restrict__ qkv, T* __restrict__ out_cls,
+                                                             float* __restrict__ plane_cls, int N, int heads) {
+    extern __shared__ float sm[];  // p[N] | q[64] | red[40] | part[128]
+    float* p = sm;
+    float* q = sm + N;
+    float* red = q + 64;
+    float* part = red + 40;
+    const int s = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int E = heads * 64;
+    const int64_t ld = 3 * E;
+    const T* base = qkv + static_cast<int64_t>(s) * N * ld;
+    if (threadIdx.x < 64) q[threadIdx.x] = to_f<T>(base[h * 64 + threadIdx.x]);
+    __syncthreads();
+    float lmax = -CUDART_INF_F;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const T* kr = base + j * ld + E + h * 64;
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < 64; d += 4) {
+            float kv[4];
+            Vec4<T>::load(kr + d, kv);
+            acc = fmaf(q[d], kv[0], acc); acc = fmaf(q[d + 1], kv[1], acc);
+            acc = fmaf(q[d + 2], kv[2], acc); acc = fmaf(q[d + 3], kv[3], acc);
+        }
+        p[j] = acc;
+        lmax = fmaxf(lmax, acc);
+    }
+    const float m = block_max(lmax, red);
+    float lsum = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float e = expf(p[j] - m);
+        p[j] = e;
+        lsum += e;
+    }
+    const float inv = 1.0f / block_sum(lsum, red);
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float pj = p[j] * inv;
+        p[j] = pj;
+        if (plane_cls) plane_cls[(static_cast<int64_t>(s) * heads + h) * N + j] = pj;
+    }
+    __syncthreads();
+    const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
+    float acc = 0.f;
+    for (int j = half; j < N; j += 2) acc = fmaf(p[j], to_f<T>(base[j * ld + 2 * E + h * 64 + d]), acc);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64) out_cls[static_cast<int64_t>(s) * E + h * 64 + d] = from_f<T>(part[d] + part[64 + d]);
+}
+
+template <typename T>
+int launch_cls_attention(const T* qkv, T* out_cls, float* plane_cls, int BD, int N, int heads, cudaStream_t stream) {
+    const size_t smem = (N + 64 + 40 + 128) * sizeof(float);
+    cls_attention_kernel<T><<<BD * heads, 128, smem, stream>>>(qkv, out_cls, plane_cls, N, heads);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+template int launch_cls_attention<float>(const float*, float*, float*, int, int, int, cudaStream_t);
+template int launch_cls_attention<bf16>(const bf16*, bf16*, float*, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 CUDA-core attention (fp32 parity mode only): one CTA per (slice, head), K and V in shared memory.
+// softmax(q k^T) v with q pre-scaled (attention.py:56-69).  N <= 384.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ATT32_WARPS = 8;
+constexpr int ATT32_MAXJ = 12;
+__global__ void __launch_bounds__(ATT32_WARPS * 32) attention_f32_kernel(const float* __restrict__ qkv,
+                                                                          float* __restrict__ out, int N, int heads) {
+    extern __shared__ float sm[];
+    float* Ks = sm;                 // [N][65]
+    float* Vs = Ks + N * 65;        // [N][64]
+    float* qs = Vs + N * 64;        // [warps][64]
+    float* ps = qs + ATT32_WARPS * 64;  // [warps][N]
+    const int s = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int E = heads * 64;
+    const int64_t ld = 3 * E;
+    const float* base = qkv + static_cast<int64_t>(s) * N * ld;
+    for (int i = threadIdx.x; i < N * 64; i += blockDim.x) {
+        const int j = i >> 6, d = i & 63;
+        Ks[j * 65 + d] = base[j * ld + E + h * 64 + d];
+        Vs[j * 64 + d] = base[j * ld + 2 * E + h * 64 + d];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* q = qs + warp * 64;
+    float* p = ps + warp * N;
+    for (int r = warp; r < N; r += ATT32_WARPS) {
+        q[lane] = base[r * ld + h * 64 + lane];
+        q[lane + 32] = base[r * ld + h * 64 + lane + 32];
+        __syncwarp();
+        float sc[ATT32_MAXJ];
+        float lmax = -CUDART_INF_F;
+#pragma unroll
+        for (int jj = 0; jj < ATT32_MAXJ; ++jj) {
+            const int j = jj * 32 + lane;
+            float acc = -CUDART_INF_F;
+            if (j < N) {
+                acc = 0.f;
+                const float* kr = Ks + j * 65;
+#pragma unroll 16
+                for (int d = 0; d < 64; ++d) acc = fmaf(q[d], kr[d], acc);
+            }
+            sc[jj] = acc;
+            lmax = fmaxf(lmax, acc);
+        }
+        const float m = warp_max(lmax);
+        float lsum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < ATT32_MAXJ; ++jj) {
+            const int j = jj * 32 + lane;
+            const float e = j < N ? expf(sc[jj] - m) : 0.f;
+            sc[jj] = e;
+            lsum += e;
+        }
+        const float inv = 1.0f / warp_sum(lsum);
+#pragma unroll
+        for (int jj = 0; jj < ATT32_MAXJ; ++jj) {
+            const int j = jj * 32 + lane;
+            if (j < N) p[j] = sc[jj] * inv;
+        }
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < N; ++j) {
+            const float pj = p[j];
+            a0 = fmaf(pj, Vs[j * 64 + lane], a0);
+            a1 = fmaf(pj, Vs[j * 64 + lane + 32], a1);
+        }
+        float* o = out + (static_cast<int64_t>(s) * N + r) * E + h * 64;
+        o[lane] = a0;
+        o[lane + 32] = a1;
+        __syncwarp();
+    }
+}
+
+int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads, cudaStream_t stream) {
+    MST_REQUIRE(N <= ATT32_MAXJ * 32, "fp32 attention supports at most %d tokens per slice (got %d)", ATT32_MAXJ * 32, N);
+    const size_t smem = (static_cast<size_t>(N) * 65 + N * 64 + ATT32_WARPS * 64 + ATT32_WARPS * N) * sizeof(float);
+    MST_REQUIRE(smem <= 227 * 1024, "fp32 attention: %zu bytes of shared memory needed", smem);
+    static bool attr = false;
+    if (!attr) {
+        MST_CHECK_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    attention_f32_kernel<<<BD * heads, ATT32_WARPS * 32, smem, stream>>>(qkv, out, N, heads);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 CUDA-core GEMM (fp32 parity mode only): 64x64 tile, BK 16, 4x4 micro-tile, same epilogues.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ W,
+                                                        int M, int N, int K, int mode, EpiParams ep) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Ws[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    const int lr = threadIdx.x >> 2, lk = (threadIdx.x & 3) * 4;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + lr < M) a = *reinterpret_cast<const float4*>(A + static_cast<int64_t>(m0 + lr) * lda + k0 + lk);
+        const float4 w = *reinterpret_cast<const float4*>(W + static_cast<int64_t>(n0 + lr) * K + k0 + lk);
+        As[lk + 0][lr] = a.x; As[lk + 1][lr] = a.y; As[lk + 2][lr] = a.z; As[lk + 3][lr] = a.w;
+        Ws[lk + 0][lr] = w.x; Ws[lk + 1][lr] = w.y; Ws[lk + 2][lr] = w.z; Ws[lk + 3][lr] = w.w;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 wv = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], w4[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = m0 + ty * 4 + i;
+        if (row >= M) continue;
+        const int n = n0 + tx * 4;
+        float v[4] = {acc[i][0], acc[i][1], acc[i][2], acc[i][3]};
+        int64_t orow = row;
+        if (mode == EPI_PATCH) {
+            const int p = static_cast<int>(row % ep.P);
+            orow = (row / ep.P) * (ep.P + 1) + 1 + p;
+            const float4 b = *reinterpret_cast<const float4*>(ep.posb + static_cast<int64_t>(p) * N + n);
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        } else {
+            const float4 b = *reinterpret_cast<const float4*>(ep.bias + n);
+            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+        }
+        if (mode == EPI_BIAS_GELU) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = gelu_erf<true>(v[j]);
+        }
+        if (mode == EPI_BIAS_RES) {
+            const float4 r = *reinterpret_cast<const float4*>(static_cast<const float*>(ep.res) + row * ep.ldr + n);
+            v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+        }
+        *reinterpret_cast<float4*>(static_cast<float*>(ep.out) + orow * ep.ldo + n) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
+int gemm_f32_simt(const float* A, int64_t lda, const float* W, int M, int N, int K, int mode, const EpiParams& ep,
+                  cudaStream_t stream) {
+    MST_REQUIRE(M > 0 && N % 64 == 0 && K % 16 == 0 && lda % 4 == 0, "fp32 gemm: bad shape M=%d N=%d K=%d", M, N, K);
+    dim3 grid(N / 64, (M + 63) / 64);
+    MST_REQUIRE(grid.y <= 65535, "fp32 gemm: M=%d too large for the parity path", M);
+    gemm_f32_kernel<<<grid, 256, 0, stream>>>(A, lda, W, M, N, K, mode, ep);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Slice transformer + head, one CTA per volume (reference dino.py:145-166,
+// utils/transformer_blocks.py:524-587 norm_first branch, :29-318 attention).
+//
+// Only token 0 (the slice-CLS) of the single layer's output is consumed (dino.py:153), so only the CLS
+// query is evaluated, and K/V are never materialised:   s[h,j] = q_h.(Wk_h n_j + bk_h) = (Wk_h^T q_h).n_j + q_h.bk_h
+// and   o_h = sum_j p[h,j] (Wv_h n_j + bv_h) = Wv_h (sum_j p[h,j] n_j) + bv_h   (softmax rows sum to 1).
+// Exact re-association of the reference's arithmetic, all fp32.  Emits p[h,:] = row 0 of the slice attention
+// (what get_slice_attention reads, dino.py:174-175).  Weights are fp32, pre-transposed to [in][out].
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_layernorm(const float* in, float* out, const float* g, const float* b, int E,
+                                                float eps, float* red) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) s += in[i];
+    const float mean = block_sum(s, red) / E;
+    float q = 0.f;
+    for (int i = threadIdx.x; i < E; i += blockDim.x) { const float d = in[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(block_sum(q, red) / E + eps);
+    for (int i = threadIdx.x; i < E; i += blockDim.x) out[i] = fmaf((in[i] - mean) * rstd, g[i], b[i]);
+    __syncthreads();
+}
+// out[n] = act(sum_k in[k] * Wt[k*ldw + n] + bias[n]) (+ res[n]);  in/out in shared memory
+__device__ __forceinline__ void block_matvec(const float* in, const float* __restrict__ Wt, int ldw, const float* __restrict__ bias,
+                                             const float* res, float* out, int K, int Nout, bool relu, float scale) {
+    for (int n = threadIdx.x; n < Nout; n += blockDim.x) {
+        float a0 = 0.f, a1 = 0.f;
+        int k = 0;
+        for (; k + 1 < K; k += 2) {
+            a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
+            a1 = fmaf(in[k + 1], __ldg(Wt + static_cast<int64_t>(k + 1) * ldw + n), a1);
+        }
+        if (k < K) a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
+        float v = (a0 + a1 + bias[n]) * scale;
+        if (relu) v = fmaxf(v, 0.f);
+        if (res) v += res[n];
+        out[n] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restrict__ enc_cls, const uint8_t* __restrict__ pad_mask,
+                                                            SliceWeights w, float* __restrict__ hs_all, float* __restrict__ logits,
+                                                            float* __restrict__ feat, float* __restrict__ slice_cls, int D, int E,
+                                                            int heads, int out_ch) {
+    extern __shared__ float sm[];
+    const int L = D + 1, hd = E / heads;
+    float* x0 = sm;                 // [E]  raw CLS token (residual)
+    float* n0 = x0 + E;             // [E]  LN1(token 0)
+    float* q = n0 + E;              // [E]
+    float* qk = q + E;              // [heads][E]
+    float* hbar = qk + heads * E;   // [heads][E]
+    float* t0 = hbar + heads * E;   // [E]
+    float* t1 = t0 + E;             // [E]
+    float* t2 = t1 + E;             // [E]
+    float* cterm = t2 + E;          // [heads] (padded to 32)
+    float* red = cterm + 32;        // [40]
+    float* p = red + 40;            // [heads][L]
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    float* hs = hs_all + static_cast<int64_t>(b) * L * E;
+
+    // 1. tokens = [cls_token, enc_cls[b, 0..D-1]]; hs[l] = LN1(token l)   (dino.py:145; transformer_blocks.py:566)
+    for (int l = warp; l < L; l += nwarps) {
+        const float* src = l == 0 ? w.cls_token : enc_cls + (static_cast<int64_t>(b) * D + l - 1) * E;
+        float s = 0.f;
+        for (int i = lane; i < E; i += 32) s += src[i];
+        const float mean = warp_sum(s) / E;
+        float v = 0.f;
+        for (int i = lane; i < E; i += 32) { const float d = src[i] - mean; v = fmaf(d, d, v); }
+        const float rstd = rsqrtf(warp_sum(v) / E + 1e-5f);
+        for (int i = lane; i < E; i += 32) {
+            const float o = fmaf((src[i] - mean) * rstd, w.n1w[i], w.n1b[i]);
+            hs[static_cast<int64_t>(l) * E + i] = o;
+            if (l == 0) { n0[i] = o; x0[i] = src[i]; }
+        }
+    }
+    __syncthreads();
+    // 2. q = (Wq n0 + bq) / sqrt(hd)                                    (transformer_blocks.py:166,268)
+    block_matvec(n0, w.in_wt, 3 * E, w.in_b, nullptr, q, E, E, false, rsqrtf(static_cast<float>(hd)));
+    // 3. qk[h][k] = sum_d q[h,d] Wk[h*hd+d][k];  cterm[h] = q_h . bk_h
+    for (int idx = threadIdx.x; idx < heads * E; idx += blockDim.x) {
+        const int h = idx / E, k = idx % E;
+        const float* wr = w.in_wt + static_cast<int64_t>(k) * 3 * E + E + h * hd;
+        float a = 0.f;
+        for (int d = 0; d < hd; ++d) a = fmaf(q[h * hd + d], __ldg(wr + d), a);
+        qk[idx] = a;
+    }
+    if (threadIdx.x < heads) {
+        float a = 0.f;
+        for (int d = 0; d < hd; ++d) a = fmaf(q[threadIdx.x * hd + d], w.in_b[E + threadIdx.x * hd + d], a);
+        cterm[threadIdx.x] = a;
+    }
+    __syncthreads();
+    // 4. scores, key-padding mask -> -inf (transformer_blocks.py:244-252; CLS column never masked, dino.py:149-150)
+    for (int task = warp; task < heads * L; task += nwarps) {
+        const int h = task / L, j = task % L;
+        const float* hr = hs + static_cast<int64_t>(j) * E;
+        float a = 0.f;
+        for (int k = lane; k < E; k += 32) a = fmaf(qk[h * E + k], hr[k], a);
+        a = warp_sum(a) + cterm[h];
+        if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(b) * D + j - 1]) a = -CUDART_INF_F;
+        if (lane == 0) p[h * L + j] = a;
+    }
+    __syncthreads();
+    // 5. softmax per head
+    for (int h = warp; h < heads; h += nwarps) {
+        float m = -CUDART_INF_F;
+        for (int j = lane; j < L; j += 32) m = fmaxf(m, p[h * L + j]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int j = lane; j < L; j += 32) { const float e = expf(p[h * L + j] - m); p[h * L + j] = e; s += e; }
+        const float inv = 1.0f / warp_sum(s);
+        for (int j = lane; j < L; j += 32) {
+            const float pj = p[h * L + j] * inv;
+            p[h * L + j] = pj;
+            if (slice_cls) slice_cls[(static_cast<int64_t>(b) * heads + h) * L + j] = pj;
+        }
+    }
+    __syncthreads();
+    // 6. hbar[h][k] = sum_j p[h][j] hs[j][k]
+    for (int k = threadIdx.x; k < E; k += blockDim.x) {
+        float acc[16];
+#pragma unroll
+        for (int h = 0; h < 16; ++h) acc[h] = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float hv = hs[static_cast<int64_t>(j) * E + k];
+#pragma unroll
+            for (int h = 0; h < 16; ++h)
+                if (h < heads) acc[h] = fmaf(p[h * L + j], hv, acc[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < 16; ++h)
+            if (h < heads) hbar[h * E + k] = acc[h];
+    }
+    __syncthreads();
+    // 7. o[n] = Wv[n,:] . hbar[head(n)] + bv[n]
+    for (int n = threadIdx.x; n < E; n += blockDim.x) {
+        const float* hb = hbar + (n / hd) * E;
+        float a = 0.f;
+        for (int k = 0; k < E; ++k) a = fmaf(hb[k], __ldg(w.in_wt + static_cast<int64_t>(k) * 3 * E + 2 * E + n), a);
+        t0[n] = a + w.in_b[2 * E + n];
+    }
+    __syncthreads();
+    // 8. x1 = x0 + out_proj(o)                                           (transformer_blocks.py:566)
+    block_matvec(t0, w.out_wt, E, w.out_b, x0, t1, E, E, false, 1.0f);
+    // 9. x2 = x1 + W2 relu(W1 LN2(x1) + b1) + b2                         (transformer_blocks.py:567,585)
+    block_layernorm(t1, t0, w.n2w, w.n2b, E, 1e-5f, red);
+    block_matvec(t0, w.l1_wt, E, w.l1_b, nullptr, t2, E, E, true, 1.0f);
+    block_matvec(t2, w.l2_wt, E, w.l2_b, t1, t0, E, E, false, 1.0f);
+    // 10. final LayerNorm (dino.py:95), feature = row 0 (dino.py:153), logits (dino.py:166)
+    block_layernorm(t0, t1, w.nfw, w.nfb, E, 1e-5f, red);
+    if (feat)
+        for (int i = threadIdx.x; i < E; i += blockDim.x) feat[static_cast<int64_t>(b) * E + i] = t1[i];
+    for (int c = warp; c < out_ch; c += nwarps) {
+        float a = 0.f;
+        for (int k = lane; k < E; k += 32) a = fmaf(t1[k], w.head_wt[static_cast<int64_t>(k) * out_ch + c], a);
+        a = warp_sum(a);
+        if (lane == 0) logits[static_cast<int64_t>(b) * out_ch + c] = a + w.head_b[c];
+    }
+}
+
+int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,
+                        float* logits, float* feat, float* slice_cls, int B, int D, int E, int heads, int out_ch,
+                        cudaStream_t stream) {
+    MST_REQUIRE(heads <= 16 && E % heads == 0, "slice transformer: heads=%d E=%d unsupported", heads, E);
+    const int L = D + 1;
+    const size_t smem = (static_cast<size_t>(6) * E + 2 * heads * E + 32 + 40 + heads * L) * sizeof(float);
+    MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
+    static bool attr = false;
+    if (!attr) {
+        MST_CHECK_CUDA(cudaFuncSetAttribute(slice_fusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr = true;
+    }
+    slice_fusion_kernel<<<B, 384, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, E, heads, out_ch);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Saliency combiner (reference dino.py:173-202 + scripts/main_predict.py:73-74,100) and the x14 upsampler
+// (main_predict.py:161-162: trilinear with depth scale 1 == per-slice bilinear, align_corners=False).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __restrict__ plane_cls, const float* __restrict__ slice_cls,
+                                                                int D, int heads, int sheads, int P,
+                                                                float* __restrict__ attn_maps, float* __restrict__ plane_attn,
+                                                                float* __restrict__ slice_attn, float* __restrict__ coarse) {
+    extern __shared__ float sm[];  // acc[P] | red[40] | wsl[1]
+    float* acc = sm;
+    float* red = sm + P;
+    float* wsl = red + 40;
+    const int s = blockIdx.x, b = s / D, d = s % D, L = D + 1, N = P + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // slice weight: mean over heads of S[b,h,1+d] / sum_j S[b,h,1+j]          (dino.py:174-181)
+    if (warp == 0) {
+        float wacc = 0.f;
+        for (int h = 0; h < sheads; ++h) {
+            const float* sr = slice_cls + (static_cast<int64_t>(b) * sheads + h) * L + 1;
+            float t = 0.f;
+            for (int j = lane; j < D; j += 32) t += sr[j];
+            t = warp_sum(t);
+            wacc += sr[d] / t;
+        }
+        if (lane == 0) *wsl = wacc / sheads;
+    }
+    for (int i = threadIdx.x; i < P; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const float wslice = *wsl;
+    (void)nwarps;
+    for (int h = 0; h < heads; ++h) {
+        const float* pr = plane_cls + (static_cast<int64_t>(s) * heads + h) * N + 1;  // drop the CLS column (dino.py:192)
+        float t = 0.f;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) t += (i == 0) ? 0.f : pr[i];  // patch 0 := 0 (dino.py:193)
+        const float tot = block_sum(t, red);
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            const float a = (i == 0) ? 0.f : pr[i] / tot;                           // dino.py:194
+            const float m = wslice * a;                                             // dino.py:201
+            if (attn_maps) attn_maps[(static_cast<int64_t>(s) * heads + h) * P + i] = m;
+            if (plane_attn) plane_attn[(static_cast<int64_t>(s) * heads + h) * P + i] = a;
+            acc[i] += m;
+        }
+    }
+    if (coarse)
+        for (int i = threadIdx.x; i < P; i += blockDim.x) coarse[static_cast<int64_t>(s) * P + i] = acc[i] / heads;  // main_predict.py:73-74
+    if (slice_attn && threadIdx.x == 0) slice_attn[s] = wslice;
+}
+
+__global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __restrict__ coarse, float* __restrict__ full,
+                                                                 int gh, int gw, int H, int W, int rows_per_cta) {
+    extern __shared__ float c[];  // [gh*gw]
+    const int s = blockIdx.x;
+    const int y_begin = blockIdx.y * rows_per_cta;
+    const int y_end = min(H, y_begin + rows_per_cta);
+    for (int i = threadIdx.x; i < gh * gw; i += blockDim.x) c[i] = coarse[static_cast<int64_t>(s) * gh * gw + i];
+    __syncthreads();
+    const float sy = static_cast<float>(gh) / static_cast<float>(H), sx = static_cast<float>(gw) / static_cast<float>(W);
+    float* out = full + static_cast<int64_t>(s) * H * W;
+    const int W4 = W >> 2;
+    if ((W & 3) == 0) {
+        for (int idx = y_begin * W4 + threadIdx.x; idx < y_end * W4; idx += blockDim.x) {
+            const int y = idx / W4, x4 = (idx % W4) * 4;
+            const float fy = fmaxf(sy * (y + 0.5f) - 0.5f, 0.f);
+            const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, gh - 1);
+            const float ly = fy - y0, hy = 1.f - ly;
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float fx = fmaxf(sx * (x4 + j + 0.5f) - 0.5f, 0.f);
+                const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, gw - 1);
+                const float lx = fx - x0, hx = 1.f - lx;
+                o[j] = hy * (hx * c[y0 * gw + x0] + lx * c[y0 * gw + x1]) + ly * (hx * c[y1 * gw + x0] + lx * c[y1 * gw + x1]);
+            }
+            __stcs(reinterpret_cast<float4*>(out + static_cast<int64_t>(y) * W + x4), make_float4(o[0], o[1], o[2], o[3]));
+        }
+    } else {
+        for (int idx = y_begin * W + threadIdx.x; idx < y_end * W; idx += blockDim.x) {
+            const int y = idx / W, x = idx % W;
+            const float fy = fmaxf(sy * (y + 0.5f) - 0.5f, 0.f);
+            const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, gh - 1);
+            const float ly = fy - y0, hy = 1.f - ly;
+            const float fx = fmaxf(sx * (x + 0.5f) - 0.5f, 0.f);
+            const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, gw - 1);
+            const float lx = fx - x0, hx = 1.f - lx;
+            out[idx] = hy * (hx * c[y0 * gw + x0] + lx * c[y0 * gw + x1]) + ly * (hx * c[y1 * gw + x0] + lx * c[y1 * gw + x1]);
+        }
+    }
+}
+
+int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int gh,
+                    int gw, int H, int W, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full,
+                    cudaStream_t stream) {
+    const int P = gh * gw, BD = B * D;
+    MST_REQUIRE(coarse != nullptr || full == nullptr, "saliency: the full-resolution map needs the coarse buffer");
+    saliency_combine_kernel<<<BD, 256, (P + 48) * sizeof(float), stream>>>(plane_cls, slice_cls, D, heads, slice_heads, P,
+                                                                          attn_maps, plane_attn, slice_attn, coarse);
+    MST_CHECK_CUDA(cudaGetLastError());
+    if (full) {
+        const int rows_per_cta = 32;
+        dim3 grid(BD, (H + rows_per_cta - 1) / rows_per_cta);
+        saliency_upsample_kernel<<<grid, 256, P * sizeof(float), stream>>>(coarse, full, gh, gw, H, W, rows_per_cta);
+        MST_CHECK_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace mst

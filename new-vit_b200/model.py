@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's `mst.models.DinoV2ClassifierSlice` (reference
+mst/models/dino.py:32-275) and of `run_pred` (scripts/main_predict.py:55-164) over the C-ABI CUDA
+library.  Same constructor arguments, same `state_dict` key layout, same forward / getter
+signatures and error behaviour; the arithmetic runs in libmst_b200.so (hand-written sm_100a
+kernels).  PyTorch is used for device memory, streams and parameter bookkeeping only.
+
+Not mirrored yet (raise NotImplementedError): pretrained hub weights
+(no network), registers, bottleneck, slice position embedding, rotary encodings,
+slice_fusion in {'linear','average'}, get_attention_cls (needs all 12 full maps).
+"""
+import torch
+import torch.nn as nn
+
+from new_vit_b200 import _cabi, synth
+from new_vit_b200._cabi import MSTError  # noqa: F401
+
+
+# ---- parameter containers that reproduce the reference's module tree (names only; never called) ----
+class _Attn(nn.Module):
+    def __init__(self, E):
+        super().__init__()
+        self.qkv = nn.Linear(E, 3 * E)
+        self.proj = nn.Linear(E, E)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, E):
+        super().__init__()
+        self.fc1 = nn.Linear(E, 4 * E)
+        self.fc2 = nn.Linear(4 * E, E)
+
+
+class _Block(nn.Module):
+    def __init__(self, E):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(E, eps=1e-6)
+        self.attn = _Attn(E)
+        self.norm2 = nn.LayerNorm(E, eps=1e-6)
+        self.mlp = _Mlp(E)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, E):
+        super().__init__()
+        self.proj = nn.Conv2d(3, E, kernel_size=14, stride=14)
+
+
+class _Encoder(nn.Module):
+    """Key layout of DinoVisionTransformer built by vit_small/base (block_chunks=1 => blocks.0.<i>)."""
+
+    def __init__(self, E, depth, heads, pos_tokens):
+        super().__init__()
+        self.num_features = self.embed_dim = E
+        self.num_heads = heads
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, E))
+        self.pos_embed = nn.Parameter(torch.zeros(1, pos_tokens, E))
+        self.mask_token = nn.Parameter(torch.zeros(1, E))
+        self.patch_embed = _PatchEmbed(E)
+        self.blocks = nn.ModuleList([nn.ModuleList([_Block(E) for _ in range(depth)])])
+        self.norm = nn.LayerNorm(E, eps=1e-6)
+
+
+class _SliceLayer(nn.Module):
+    def __init__(self, E, heads):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(E, heads, dropout=0.0, batch_first=True)
+        self.linear1 = nn.Linear(E, E)
+        self.linear2 = nn.Linear(E, E)
+        self.norm1 = nn.LayerNorm(E)
+        self.norm2 = nn.LayerNorm(E)
+
+
+class _SliceFusion(nn.Module):
+    def __init__(self, E, heads):
+        super().__init__()
+        self.layers = nn.ModuleList([_SliceLayer(E, heads)])
+        self.norm = nn.LayerNorm(E)
+
+
+class DinoV2ClassifierSlice(nn.Module):
+    """Drop-in for reference `mst.models.DinoV2ClassifierSlice` (dino.py:32)."""
+
+    def __init__(self, in_ch, out_ch, spatial_dims=2, pretrained=True, save_attn=False,
+                 rotary_positional_encoding=None, optimizer_kwargs={'lr': 1e-6, 'weight_decay': 1e-2},
+                 model_size='s', use_registers=False, use_bottleneck=False, use_slice_pos_emb=False,
+                 enable_linear=True, enable_trans=True, slice_fusion='transformer', freeze=False,
+                 precision='bf16', img_size=224, **kwargs):
+        super().__init__()
+        if pretrained:
+            raise NotImplementedError(
+                "pretrained=True downloads hub weights (dino.py:59-63); this machine is offline. "
+                "Construct with pretrained=False and load a checkpoint with load_state_dict().")
+        for flag, val in (("rotary_positional_encoding", rotary_positional_encoding), ("use_registers", use_registers),
+                          ("use_bottleneck", use_bottleneck), ("use_slice_pos_emb", use_slice_pos_emb)):
+            if val:
+                raise NotImplementedError(f"{flag} is not built yet (SURVEY.md 8f)")
+        if slice_fusion != 'transformer' or not enable_linear:
+            raise NotImplementedError("only slice_fusion='transformer' with the linear head is built (SURVEY.md 8f)")
+        if model_size not in synth.VIT_CFG:
+            raise ValueError(f"model_size {model_size!r} unsupported")
+        if precision not in _cabi.PRECISION:
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        E, depth, heads = synth.VIT_CFG[model_size]
+        self.in_ch, self.out_ch, self.spatial_dims = in_ch, out_ch, spatial_dims
+        self.optimizer_kwargs = optimizer_kwargs
+        self.save_attn = save_attn
+        self.attention_maps = []
+        self.attention_maps_slice = []
+        self.use_registers = use_registers
+        self.slice_fusion_type = slice_fusion
+        self.precision = precision
+        self.model_size = model_size
+        pos_tokens = 1 + (img_size // 14) ** 2
+        self.encoder = _Encoder(E, depth, heads, pos_tokens)
+        self.emb_ch = E
+        self.slice_fusion = _SliceFusion(E, synth.SLICE_HEADS)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, E))
+        self.linear = nn.Linear(E, out_ch)
+        # reference init distributions, drawn from the global torch RNG
+        sd = synth.make_state_dict(model_size, out_ch, seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()),
+                                   img_size=img_size)
+        nn.Module.load_state_dict(self, sd, strict=True)
+        if freeze:
+            for p in self.encoder.parameters():
+                p.requires_grad = False
+        self._handle = None
+        self._handle_key = None
+        self._dirty = True
+        self._workspace = None
+        self._last = None
+        self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_dirty", True))
+
+    # -- Lightning-style conveniences the callers use (base_model.py) --------------------------------
+    @property
+    def device(self):
+        return self.cls_token.device
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._dirty = True
+        return r
+
+    # -- weights -> C handle --------------------------------------------------------------------------
+    def _release(self):
+        if self._handle is not None:
+            _cabi.lib().mst_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def sync_weights(self):
+        """(Re)pack the current parameters into the CUDA library (call after in-place edits)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise MSTError("DinoV2ClassifierSlice runs on a CUDA device only (no CPU fallback): call .cuda() first")
+        L = _cabi.lib()
+        E = self.emb_ch
+        key = (dev.index or 0, self.precision, self.encoder.pos_embed.shape[1])
+        if self._handle is None or self._handle_key != key:
+            self._release()
+            cfg = _cabi.MstConfig(E, len(self.encoder.blocks[0]), self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
+                                  self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0])
+            h = _cabi.ctypes.c_void_p()
+            _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))
+            self._handle, self._handle_key = h, key
+        with torch.cuda.device(dev):
+            stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            keep = []
+            for name, t in self.state_dict().items():
+                t32 = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(t32)
+                _cabi.check(L.mst_set_weight(self._handle, name.encode(), _cabi.ptr(t32), t32.numel(), stream))
+            _cabi.check(L.mst_finalize_weights(self._handle, stream))
+        self._dirty = False
+
+    # -- forward (dino.py:110-167) ---------------------------------------------------------------------
+    def forward(self, source, save_attn=False, src_key_padding_mask=None, **kwargs):
+        if self._dirty or self._handle is None:
+            self.sync_weights()
+        dev = self.device
+        x = source.to(dev)                                  # dino.py:121
+        if x.dim() != 5:
+            raise ValueError(f"expected source [B, C, D, H, W], got {tuple(x.shape)}")
+        B, C, D, H, W = x.shape
+        assert C == 1, "More than one channel"             # dino.py:14 / the (b d c) flatten at :125
+        assert H % 14 == 0 and W % 14 == 0, \
+            f"Input image height {H} / width {W} is not a multiple of patch size 14"   # patch_embed.py:72-73
+        x = x.to(torch.float32).contiguous()
+        L = _cabi.lib()
+        E, heads = self.emb_ch, self.encoder.num_heads
+        N = (H // 14) * (W // 14) + 1
+        mask = None
+        if src_key_padding_mask is not None:               # dino.py:147-150
+            mask = src_key_padding_mask.to(dev).to(torch.uint8).contiguous()
+            if tuple(mask.shape) != (B, D):
+                raise ValueError(f"src_key_padding_mask must be [B, D] = {(B, D)}, got {tuple(mask.shape)}")
+        with torch.cuda.device(dev):
+            logits = torch.empty((B, self.out_ch), device=dev, dtype=torch.float32)
+            feat = torch.empty((B, E), device=dev, dtype=torch.float32)
+            plane = torch.empty((B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None
+            slc = torch.empty((B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
+            enc = torch.empty((B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
+            need = _cabi.ctypes.c_size_t()
+            _cabi.check(L.mst_workspace_bytes(self._handle, B, D, H, W, _cabi.ctypes.byref(need)))
+            if self._workspace is None or self._workspace.numel() < need.value or self._workspace.device != dev:
+                self._workspace = None
+                self._workspace = torch.empty(need.value, device=dev, dtype=torch.uint8)
+            stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _cabi.check(L.mst_forward(self._handle, _cabi.ptr(x), B, D, H, W, _cabi.ptr(mask), _cabi.ptr(logits),
+                                      _cabi.ptr(feat), _cabi.ptr(enc), _cabi.ptr(plane), _cabi.ptr(slc),
+                                      _cabi.ptr(self._workspace), self._workspace.numel(), stream))
+        if save_attn:
+            # The reference keeps 12 x [BD,heads,N,N] (dino.py:241); its getters only ever read row 0 of the last
+            # one.  We keep that row, shaped [BD,heads,1,N] so that `attention_maps[-1][:, :, 0, 1:]` still works.
+            self.attention_maps = [plane.unsqueeze(2)]
+            self.attention_maps_slice = [slc.unsqueeze(2)]
+            self._last = (B, D, H, W)
+        self._enc_cls = enc
+        if kwargs.get('without_linear', False):             # dino.py:164-165
+            return feat
+        return logits
+
+    # -- instrumentation ------------------------------------------------------------------------------------
+    def launch_count(self):
+        """CUDA kernels launched by this model's handle so far."""
+        return int(_cabi.lib().mst_launch_count(self._handle)) if self._handle is not None else 0
+
+    def profile_begin(self):
+        if self._dirty or self._handle is None:
+            self.sync_weights()
+        _cabi.check(_cabi.lib().mst_profile_begin(self._handle))
+
+    def profile_end(self):
+        """{category: (milliseconds, launches)} accumulated since profile_begin (synchronises the device)."""
+        ms = (_cabi.ctypes.c_double * 16)()
+        n = (_cabi.ctypes.c_int64 * 16)()
+        _cabi.check(_cabi.lib().mst_profile_end(self._handle, ms, n, 16))
+        names = _cabi.lib().mst_profile_categories().decode().split(",")
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(names)}
+
+    # -- getters (dino.py:173-212) ---------------------------------------------------------------------
+    def _saliency(self, want_maps=False, want_plane=False, want_slice=False, want_coarse=False, want_full=False, size=None):
+        if not self.attention_maps or not self.attention_maps_slice:
+            raise IndexError("list index out of range")    # what the reference raises before a save_attn forward
+        plane = self.attention_maps[-1][:, :, 0, :].contiguous()
+        slc = self.attention_maps_slice[-1][:, :, 0, :].contiguous()
+        dev = plane.device
+        BD, heads, N = plane.shape
+        B, sheads, L = slc.shape
+        D = L - 1
+        P = N - 1
+        if self._last is not None and self._last[0] * self._last[1] == BD:
+            H, W = self._last[2], self._last[3]
+        else:
+            g = int(P ** 0.5)
+            H = W = 14 * g
+        gh, gw = H // 14, W // 14
+        if size is not None:
+            H, W = size
+        with torch.cuda.device(dev):
+            maps = torch.empty((BD, heads, P), device=dev, dtype=torch.float32) if want_maps else None
+            pl = torch.empty((BD, heads, P), device=dev, dtype=torch.float32) if want_plane else None
+            sl = torch.empty((BD,), device=dev, dtype=torch.float32) if want_slice else None
+            coarse = torch.empty((B, 1, D, gh, gw), device=dev, dtype=torch.float32) if (want_coarse or want_full) else None
+            full = torch.empty((B, 1, D, H, W), device=dev, dtype=torch.float32) if want_full else None
+            stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _cabi.check(_cabi.lib().mst_saliency(_cabi.ptr(plane), _cabi.ptr(slc), B, D, heads, sheads, gh, gw, H, W,
+                                                 _cabi.ptr(maps), _cabi.ptr(pl), _cabi.ptr(sl), _cabi.ptr(coarse), _cabi.ptr(full), stream))
+        return maps, pl, sl, coarse, full
+
+    def get_slice_attention(self):
+        """[B*D, 1, 1] (dino.py:173-187)."""
+        return self._saliency(want_slice=True)[2][:, None, None]
+
+    def get_plane_attention(self):
+        """[B*D, heads, P]: CLS->patch attention of the last block, patch 0 zeroed, renormalised (dino.py:189-195)."""
+        return self._saliency(want_plane=True)[1]
+
+    def get_attention_maps(self):
+        """[B*D, heads, P] = slice attention x plane attention (dino.py:197-202)."""
+        return self._saliency(want_maps=True)[0]
+
+    def get_attention_cls(self):
+        raise NotImplementedError("attention rollout needs all 12 full maps (dino.py:204-212); SURVEY.md 8f.3")
+
+    def saliency_volume(self, size=None):
+        """Batched form of main_predict.py:73-74,93-105,161-162: returns
+        (weight [B,1,D,H,W] upsampled map, weight_slice [B,1,D,1,1] slice weights)."""
+        _, _, sl, coarse, full = self._saliency(want_slice=True, want_full=True, size=size)
+        B, _, D = coarse.shape[:3]
+        return full, sl.view(B, 1, D, 1, 1)
+
+
+def _pred_trans(model, source, src_key_padding_mask, save_attn=False, use_softmax=True):
+    """scripts/main_predict.py:55-106, generalised from batch 1 to batch B."""
+    with torch.no_grad():
+        pred = model(source, src_key_padding_mask=src_key_padding_mask, save_attn=save_attn)
+    if use_softmax:
+        pred = torch.softmax(pred, dim=-1)
+    if not save_attn:
+        return pred, None, None
+    weight, weight_slice = model.saliency_volume(size=tuple(source.shape[3:]))
+    weight_slice = weight_slice.expand(*source.shape)
+    return pred, weight, weight_slice
+
+
+def run_pred(model, batch, save_attn=False, use_softmax=True, use_tta=False):
+    """scripts/main_predict.py:133-164.  The x14 upsample (F.interpolate trilinear, :161-162) is linear and
+    commutes with the flips/average of TTA, so it is applied inside `_pred_trans` by the fused kernel."""
+    source, mask = batch['source'], batch.get('src_key_padding_mask', None)
+    pred, weight, weight_slice = _pred_trans(model, source, mask, save_attn, use_softmax)
+    if use_tta:
+        weight_slice = weight_slice.clone() if weight_slice is not None else None
+        for flip_dim in [(2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)]:
+            # the reference passes the un-flipped padding mask to the flipped volume (main_predict.py:149): mirrored
+            p_i, w_i, ws_i = _pred_trans(model, torch.flip(source, flip_dim), mask, save_attn, use_softmax)
+            pred = pred + p_i
+            if save_attn:
+                weight = weight + torch.flip(w_i, flip_dim)
+                weight_slice = weight_slice + torch.flip(ws_i, flip_dim)
+        pred = pred / 8
+        if save_attn:
+            weight = weight / 8
+            weight_slice = weight_slice / 8
+    return pred, weight, weight_slice

@@ -1,0 +1,152 @@
+"""Kernel-level parity (GPU): each CUDA kernel, called through the C ABI, against a plain PyTorch fp32
+reference of the same op on the same inputs."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from new_vit_b200 import _cabi
+    return _cabi, _cabi.lib()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _gelu(x):
+    return torch.nn.functional.gelu(x)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 192, 64), (1000, 384, 384), (647, 1152, 384), (300, 1536, 384),
+                                   (520, 384, 1536), (64, 384, 256), (4112, 1152, 384), (40000, 384, 384),
+                                   (257, 256, 128), (20000, 384, 1536)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gemm_bf16_tcgen05(M, N, K, mode):
+    cabi, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K + mode)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 1.0).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5)).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    out = torch.full((M, N), float("nan"), device="cuda").bfloat16()
+    cabi.check(L.mst_kernel_gemm_bf16(cabi.ptr(A), cabi.ptr(W), M, N, K, mode, cabi.ptr(bias), cabi.ptr(res),
+                                      cabi.ptr(out), _stream()))
+    torch.cuda.synchronize()
+    ref = A.float() @ W.float().t() + bias
+    if mode == 1:
+        ref = _gelu(ref)
+    if mode == 2:
+        ref = ref + res.float()
+    # fp32 accumulate, one bf16 rounding at the end: 2^-8 relative
+    torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=8e-3)
+
+
+def test_gemm_bf16_inplace_residual():
+    cabi, L = _lib()
+    M, N, K = 777, 384, 384
+    A = torch.randn(M, K, device="cuda").bfloat16()
+    W = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    x = torch.randn(M, N, device="cuda").bfloat16()
+    ref = x.float() + A.float() @ W.float().t() + bias
+    cabi.check(L.mst_kernel_gemm_bf16(cabi.ptr(A), cabi.ptr(W), M, N, K, 2, cabi.ptr(bias), cabi.ptr(x), cabi.ptr(x), _stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(x.float(), ref, rtol=8e-3, atol=8e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(130, 384, 384), (257, 1152, 384), (100, 384, 1536), (65, 384, 256)])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gemm_f32(M, N, K, mode):
+    cabi, L = _lib()
+    A = torch.randn(M, K, device="cuda")
+    W = torch.randn(N, K, device="cuda") * K ** -0.5
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda")
+    cabi.check(L.mst_kernel_gemm_f32(cabi.ptr(A), cabi.ptr(W), M, N, K, mode, cabi.ptr(bias), cabi.ptr(res), cabi.ptr(out), _stream()))
+    torch.cuda.synchronize()
+    ref = (A.double() @ W.double().t() + bias.double())
+    if mode == 1:
+        ref = _gelu(ref)
+    if mode == 2:
+        ref = ref + res.double()
+    torch.testing.assert_close(out.double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def _attn_ref(qkv, BD, N, heads):
+    E = heads * 64
+    q, k, v = qkv.float().reshape(BD, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    p = (q @ k.transpose(-2, -1)).softmax(-1)  # q is pre-scaled
+    return (p @ v).transpose(1, 2).reshape(BD * N, E)
+
+
+@pytest.mark.parametrize("BD,N,heads", [(3, 257, 6), (2, 65, 6), (2, 325, 12), (1, 16, 6), (2, 33, 6)])
+def test_attention_bf16(BD, N, heads):
+    cabi, L = _lib()
+    E = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(N)
+    qkv = torch.randn(BD * N, 3 * E, device="cuda", generator=g)
+    qkv[:, :E] *= 0.5  # sharper than uniform, like a scaled q
+    qkv = qkv.bfloat16()
+    out = torch.full((BD * N, E), float("nan"), device="cuda").bfloat16()
+    cabi.check(L.mst_kernel_attention_bf16(cabi.ptr(qkv), cabi.ptr(out), BD, N, heads, _stream()))
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, BD, N, heads)
+    # P is rounded to bf16 before P.V and the output to bf16: ~2^-8 relative on O(1) values
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("BD,N,heads", [(2, 257, 6), (1, 65, 6), (1, 325, 12)])
+def test_attention_f32(BD, N, heads):
+    cabi, L = _lib()
+    E = heads * 64
+    qkv = torch.randn(BD * N, 3 * E, device="cuda")
+    out = torch.full((BD * N, E), float("nan"), device="cuda")
+    cabi.check(L.mst_kernel_attention_f32(cabi.ptr(qkv), cabi.ptr(out), BD, N, heads, _stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, _attn_ref(qkv, BD, N, heads), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,E", [(1000, 384), (7, 384), (513, 768)])
+def test_layernorm_bf16(rows, E):
+    cabi, L = _lib()
+    x = (torch.randn(rows, E, device="cuda") * 3 + 1).bfloat16()
+    g = torch.randn(E, device="cuda")
+    b = torch.randn(E, device="cuda")
+    y = torch.empty_like(x)
+    cabi.check(L.mst_kernel_layernorm_bf16(cabi.ptr(x), cabi.ptr(y), cabi.ptr(g), cabi.ptr(b), rows, E, 1e-6, _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (E,), g, b, 1e-6)
+    torch.testing.assert_close(y.float(), ref, rtol=8e-3, atol=8e-3)
+
+
+def test_saliency_upsample_matches_trilinear():
+    cabi, L = _lib()
+    B, D, heads, sheads, g = 2, 5, 6, 12, 16
+    plane = torch.rand(B * D, heads, g * g + 1, device="cuda")
+    plane = plane / plane.sum(-1, keepdim=True)
+    slc = torch.rand(B, sheads, D + 1, device="cuda")
+    slc = slc / slc.sum(-1, keepdim=True)
+    H = W = 224
+    maps = torch.empty(B * D, heads, g * g, device="cuda")
+    pl = torch.empty_like(maps)
+    sl = torch.empty(B * D, device="cuda")
+    coarse = torch.empty(B, 1, D, g, g, device="cuda")
+    full = torch.empty(B, 1, D, H, W, device="cuda")
+    cabi.check(L.mst_saliency(cabi.ptr(plane), cabi.ptr(slc), B, D, heads, sheads, g, g, H, W, cabi.ptr(maps), cabi.ptr(pl),
+                              cabi.ptr(sl), cabi.ptr(coarse), cabi.ptr(full), _stream()))
+    torch.cuda.synchronize()
+    from oracle import mst_oracle as O
+    rp, rs = plane.cpu(), slc.cpu()
+    torch.testing.assert_close(maps.cpu(), O.get_attention_maps(rp, rs), rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(pl.cpu(), O.get_plane_attention(rp), rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(sl.cpu(), O.get_slice_attention(rs).reshape(-1), rtol=1e-5, atol=1e-9)
+    rc, rf, _ = O.saliency(rp, rs, B, D, H, W)
+    torch.testing.assert_close(coarse.cpu(), rc, rtol=1e-5, atol=1e-9)
+    torch.testing.assert_close(full.cpu(), rf, rtol=1e-5, atol=float(rf.max()) * 1e-6)
+    # indexing is bit-exact: same argmax voxel
+    assert torch.equal(full.cpu().reshape(B, -1).argmax(-1), rf.reshape(B, -1).argmax(-1))

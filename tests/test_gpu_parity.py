@@ -1,0 +1,143 @@
+"""End-to-end parity (GPU): new_vit_b200.DinoV2ClassifierSlice (CUDA via the C ABI) against
+ (1) the golden vectors produced by the real reference (tests/golden/*.npz) and
+ (2) the oracle on fresh seeded inputs,
+in both precisions.  Tolerances are BASELINE.json's: fp32 logits 1e-4 relative; bf16 logits 2e-2
+absolute and attention-map cosine >= 0.999; argmax/indexing bit-exact (checked in fp32 mode, and in
+bf16 mode on the peaky weight set where the maps are not near-uniform)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import case_inputs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2"]
+
+
+def _model(sd, precision, img_size):
+    from new_vit_b200 import DinoV2ClassifierSlice
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=precision, img_size=img_size).cuda().eval()
+    m.load_state_dict(sd)
+    return m
+
+
+def _cos(a, b):
+    return F.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+
+
+def _run(m, x, mask):
+    with torch.no_grad():
+        logits = m(x, save_attn=True, src_key_padding_mask=mask, return_enc_cls=True)
+        enc = m._enc_cls.cpu()
+        feat = m(x, src_key_padding_mask=mask, without_linear=True).cpu()
+        out = dict(logits=logits.cpu(), feat=feat, enc_cls=enc,
+                   plane_cls=m.attention_maps[-1][:, :, 0, :].cpu(), slice_cls=m.attention_maps_slice[-1][:, :, 0, :].cpu(),
+                   attn_maps=m.get_attention_maps().cpu(), slice_attn=m.get_slice_attention().cpu(),
+                   plane_attn=m.get_plane_attention().cpu())
+        full, wsl = m.saliency_volume()
+        out["full"] = full.cpu()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_fp32_matches_reference_golden(name):
+    meta, g = load_golden(name)
+    sd, x, mask = case_inputs(meta)
+    r = _run(_model(sd, "fp32", meta["H"]), x, mask)
+    B = meta["B"]
+    scale = g["logits"].abs().max().item()
+    assert (r["logits"] - g["logits"]).abs().max().item() <= 1e-4 * max(scale, 1.0), (r["logits"], g["logits"])
+    torch.testing.assert_close(r["feat"], g["feat"], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(r["enc_cls"], g["enc_cls"], rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(r["plane_cls"], g["plane_cls"], rtol=2e-4, atol=1e-7)
+    torch.testing.assert_close(r["slice_cls"], g["slice_cls"], rtol=2e-4, atol=1e-7)
+    assert r["attn_maps"].shape == g["attn_maps"].shape and r["slice_attn"].shape == g["slice_attn"].shape
+    torch.testing.assert_close(r["attn_maps"], g["attn_maps"], rtol=3e-4, atol=1e-9)
+    torch.testing.assert_close(r["slice_attn"], g["slice_attn"], rtol=3e-4, atol=1e-9)
+    # bit-exact indexing: argmax of the head-mean map per volume and argmax slice
+    assert torch.equal(r["attn_maps"].mean(1).reshape(B, -1).argmax(-1), g["attn_maps"].mean(1).reshape(B, -1).argmax(-1))
+    assert torch.equal(r["slice_attn"].reshape(B, -1).argmax(-1), g["slice_attn"].reshape(B, -1).argmax(-1))
+    torch.testing.assert_close(r["full"][:, 0, :, ::7, ::7], g["sal_sub"], rtol=3e-4, atol=float(g["sal_sub"].max()) * 1e-5)
+    if meta["masked"]:
+        assert (r["slice_attn"].reshape(B, -1)[mask] == 0).all()  # masked slices get exactly zero attention
+
+
+@pytest.mark.parametrize("name", GOLDENS)
+def test_bf16_matches_reference_golden(name):
+    meta, g = load_golden(name)
+    sd, x, mask = case_inputs(meta)
+    r = _run(_model(sd, "bf16", meta["H"]), x, mask)
+    B = meta["B"]
+    err = (r["logits"] - g["logits"]).abs().max().item()
+    assert err <= 2e-2, f"bf16 logits differ by {err}: {r['logits']} vs {g['logits']}"
+    assert _cos(r["attn_maps"], g["attn_maps"]) >= 0.999
+    assert _cos(r["plane_cls"], g["plane_cls"]) >= 0.999
+    assert _cos(r["slice_cls"], g["slice_cls"]) >= 0.999
+    assert _cos(r["full"][:, 0, :, ::7, ::7], g["sal_sub"]) >= 0.999
+    assert r["attn_maps"].shape == g["attn_maps"].shape
+    if meta["variant"] == "peaky":  # maps are far from uniform: argmax slice must agree
+        assert torch.equal(r["slice_attn"].reshape(B, -1).argmax(-1), g["slice_attn"].reshape(B, -1).argmax(-1))
+    if meta["masked"]:
+        assert (r["slice_attn"].reshape(B, -1)[mask] == 0).all()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_against_oracle_fresh_inputs(precision):
+    from new_vit_b200 import synth
+    from oracle import mst_oracle as O
+    B, D, H, W = 3, 6, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=11, variant="peaky")
+    x = synth.make_volume(B, D, H, W, seed=12)
+    mask = synth.make_padding_mask(B, D, seed=2)
+    ref = O.forward(sd, x, mask)
+    r = _run(_model(sd, precision, H), x, mask)
+    err = (r["logits"] - ref["logits"]).abs().max().item()
+    if precision == "fp32":
+        assert err <= 1e-4 * max(ref["logits"].abs().max().item(), 1.0)
+        torch.testing.assert_close(r["plane_attn"], O.get_plane_attention(ref["plane_cls"]), rtol=3e-4, atol=1e-9)
+    else:
+        assert err <= 2e-2
+    assert _cos(r["attn_maps"], O.get_attention_maps(ref["plane_cls"], ref["slice_cls"])) >= 0.999
+
+
+def test_batch_composition_invariance_and_properties():
+    """Size-independent properties at a larger batch (the oracle would take minutes here):
+    each volume's result is independent of its batch neighbours (bit-exact), per-volume head-mean maps sum
+    to 1, masked slices weigh 0, and the saliency volume integrates to H*W/P of the coarse map."""
+    from new_vit_b200 import synth
+    B, D, H, W = 6, 32, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=3, variant="peaky")
+    x = synth.make_volume(B, D, H, W, seed=4)
+    mask = synth.make_padding_mask(B, D, seed=0)
+    m = _model(sd, "bf16", H)
+    with torch.no_grad():
+        y = m(x, save_attn=True, src_key_padding_mask=mask).cpu()
+        maps = m.get_attention_maps().cpu()
+        sl = m.get_slice_attention().cpu().reshape(B, D)
+        full, _ = m.saliency_volume()
+        full = full.cpu()
+        for b in (0, 3, 5):
+            yb = m(x[b:b + 1], save_attn=True, src_key_padding_mask=mask[b:b + 1]).cpu()
+            assert torch.equal(yb[0], y[b])
+            assert torch.equal(m.get_attention_maps().cpu(), maps[b * D:(b + 1) * D])
+    torch.testing.assert_close(maps.mean(1).reshape(B, -1).sum(-1), torch.ones(B), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(sl.sum(-1), torch.ones(B), rtol=1e-5, atol=1e-5)
+    assert (sl[mask] == 0).all()
+    assert torch.isfinite(y).all() and torch.isfinite(full).all()
+    # bilinear x14 with edge clamping preserves the mean to within the border effect
+    torch.testing.assert_close(full.reshape(B, -1).mean(-1) * 256, torch.ones(B), rtol=5e-2, atol=0)
+
+
+def test_errors_mirror_reference():
+    from new_vit_b200 import DinoV2ClassifierSlice
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False).cuda().eval()
+    with pytest.raises(AssertionError):   # patch_embed.py:72-73
+        m(torch.zeros(1, 1, 2, 225, 224))
+    with pytest.raises(AssertionError):   # dino.py:14 spirit: one channel
+        m(torch.zeros(1, 3, 2, 224, 224))
+    with pytest.raises(IndexError):       # getters before a save_attn forward (dino.py:174: list index)
+        m.get_attention_maps()
+    y = m(torch.zeros(1, 1, 2, 224, 224), target=torch.zeros(1), uid=["a"])  # extra kwargs swallowed (base_model.py:155)
+    assert y.shape == (1, 2)

@@ -1,0 +1,69 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host mirror keeps the
+reference's state_dict layout and error behaviour, synthetic data is deterministic."""
+import ctypes
+
+import pytest
+import torch
+
+from new_vit_b200 import _cabi, synth
+
+
+def test_library_loads_and_exports_all_declared_symbols():
+    L = _cabi.lib()
+    names = _cabi.declared_symbols()
+    assert len(names) >= 14 and "mst_forward" in names and "mst_saliency" in names
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.mst_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a GPU every compute entry point must fail loudly."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _cabi.lib()
+    cfg = _cabi.MstConfig(384, 12, 6, 12, 2, 257, 1, 0)
+    h = ctypes.c_void_p()
+    assert L.mst_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
+    assert b"no CUDA device" in L.mst_last_error()
+    from new_vit_b200 import DinoV2ClassifierSlice
+    from new_vit_b200._cabi import MSTError
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False)
+    with pytest.raises(MSTError):
+        m(torch.zeros(1, 1, 2, 224, 224))
+
+
+def test_state_dict_layout_matches_reference():
+    from new_vit_b200 import DinoV2ClassifierSlice
+    m = DinoV2ClassifierSlice(in_ch=1, out_ch=2, pretrained=False)
+    sd = m.state_dict()
+    ref = synth.make_state_dict("s", 2, seed=0)
+    assert list(sd.keys()) == list(ref.keys()) and len(sd) == 168
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref[k].shape), k
+    assert m.encoder.num_features == 384 and m.emb_ch == 384
+    m.load_state_dict(ref)
+    assert torch.equal(m.state_dict()["encoder.blocks.0.3.attn.qkv.weight"], ref["encoder.blocks.0.3.attn.qkv.weight"])
+    from oracle import ref_harness
+    if ref_harness.reference_available():
+        real = ref_harness.build_reference_model()
+        assert list(real.state_dict().keys()) == list(sd.keys())
+        real.load_state_dict(sd)  # our checkpoints load into the reference and vice versa
+
+
+def test_unbuilt_options_raise():
+    from new_vit_b200 import DinoV2ClassifierSlice
+    for kw in (dict(pretrained=True), dict(use_bottleneck=True), dict(slice_fusion="average"),
+               dict(rotary_positional_encoding="RoPE"), dict(use_slice_pos_emb=True), dict(use_registers=True)):
+        args = dict(in_ch=1, out_ch=2, pretrained=False)
+        args.update(kw)
+        with pytest.raises(NotImplementedError):
+            DinoV2ClassifierSlice(**args)
+
+
+def test_synth_is_deterministic():
+    a, b = synth.make_state_dict("s", 2, seed=4, variant="peaky"), synth.make_state_dict("s", 2, seed=4, variant="peaky")
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert torch.equal(synth.make_volume(1, 3, 28, 28, seed=9), synth.make_volume(1, 3, 28, 28, seed=9))
+    m = synth.make_padding_mask(4, 32, seed=1)
+    assert m.shape == (4, 32) and not m[0].any() and m[1:].any()
