@@ -127,7 +127,7 @@ def test_batch_composition_invariance_and_properties():
     assert (sl[mask] == 0).all()
     assert torch.isfinite(y).all() and torch.isfinite(full).all()
     # bilinear x14 with edge clamping preserves the mean to within the border effect
-    torch.testing.assert_close(full.reshape(B, -1).mean(-1) * 256, torch.ones(B), rtol=5e-2, atol=0)
+    torch.testing.assert_close(full.reshape(B, -1).mean(-1) * 256 * D, torch.ones(B), rtol=5e-2, atol=0)
 
 
 def test_errors_mirror_reference():
