@@ -39,8 +39,9 @@ enum EpiMode : int {
     EPI_BIAS = 0,       // out = acc + bias[n]
     EPI_BIAS_GELU = 1,  // out = gelu_erf(acc + bias[n])                (reference mlp.py:35-36)
     EPI_BIAS_RES = 2,   // out = res[row*ldr + n] + acc + bias[n]       (block.py:112-113; LayerScale folded in W,b)
-    EPI_PATCH = 3       // out[(row/P)*(P+1) + 1 + row%P, n] = acc + posb[(row%P)*N + n]   (patch_embed.py:75-77 +
+    EPI_PATCH = 3,      // out[(row/P)*(P+1) + 1 + row%P, n] = acc + posb[(row%P)*N + n]   (patch_embed.py:75-77 +
                         //                                      vision_transformer.py:219-220; bias folded in posb)
+    EPI_BIAS_ACCUM = 4  // out[row, n] += acc + bias[n]   (in-place residual update; bf16 path: TMA reduce-add)
 };
 
 struct EpiParams {
@@ -72,6 +73,17 @@ __device__ __forceinline__ float erf_fast(float x) {
     q = fmaf(q, x2, -1.42647390514189e-02f);
     return __fdividef(p, q);
 }
+// bf16-path GELU: x*Phi(x) with Phi(x) ~ 0.5*(1 + tanh(x*(c0 + c1 x^2 + c2 x^4))), coefficients fitted to the exact
+// erf form (max abs deviation 2.5e-5 over all x; the bf16 output ulp is >= 2.4e-4 for |y| >= 0.06), one MUFU op.
+// x^2 is clamped so the odd polynomial keeps its sign for outliers (|x| > 8 -> tanh = +-1 -> y = x or 0).
+__device__ __forceinline__ float gelu_tanh_fit(float x) {
+    float t, x2 = fminf(x * x, 64.0f);
+    float p = fmaf(-3.51516788e-04f, x2, 3.70056460e-02f);
+    p = fmaf(p, x2, 7.97507884e-01f);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
 template <bool kExact>
 __device__ __forceinline__ float gelu_erf(float x) {
     const float e = kExact ? erff(x * 0.70710678118654752f) : erf_fast(x * 0.70710678118654752f);
@@ -85,7 +97,7 @@ struct TmaDesc {  // opaque 128-byte CUtensorMap
 };
 int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                     uint32_t box_inner, uint32_t box_rows);
+                     uint32_t box_inner, uint32_t box_rows, bool swizzle128 = true);
 
 // bf16 tensor-core GEMM (tcgen05 + TMA + TMEM). A: [M,K] bf16 row-major (lda=K), W: [N,K] bf16 row-major.
 int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,

@@ -1,10 +1,13 @@
 // bf16 GEMM on the 5th-gen tensor cores:  acc[M,N] = A[M,K] . W[N,K]^T,  fused epilogues (common.cuh).
 //
-// One persistent CTA per SM, warp-specialised:
+// One persistent CTA per SM, warp-specialised (384 threads):
 //   warp 0 (1 lane)  TMA producer   : A k-chunks (128 x 64 bf16, 128B swizzle) through a STAGES-deep ring
 //   warp 1 (1 lane)  MMA issuer     : tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction
 //   warp 2           TMEM allocator : 2 accumulator stages of BN fp32 columns (epilogue overlaps next tile)
-//   warps 4..7       epilogue       : tcgen05.ld 32x32b -> bias / GELU / residual / pos-embed -> bf16 -> HBM
+//   warps 4..11      epilogue       : warp e reads TMEM lane quadrant e%4, column half e/4 (tcgen05.ld 32x32b),
+//                                     applies bias / GELU / residual, packs bf16 into a private 32x32 staging tile
+//                                     in shared memory and hands it to the TMA store engine (coalesced, clipped
+//                                     at M; in-place residual update = TMA reduce-add, no residual read at all).
 //
 // Weight-resident mode (KCH > 0): K <= 384, so the whole [BN x K] weight slab (<= 144 KB) is loaded into
 // shared memory ONCE per CTA and only A streams; each CTA owns one n-block and walks m-blocks.  This cuts
@@ -35,20 +38,20 @@ int tma_init() {
 }
 
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                     uint32_t box_inner, uint32_t box_rows) {
+                     uint32_t box_inner, uint32_t box_rows, bool swizzle128) {
     MST_PROPAGATE(tma_init());
     static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
     MST_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
     MST_REQUIRE((row_stride_elems * 2) % 16 == 0, "TMA row pitch must be a multiple of 16 bytes");
-    MST_REQUIRE(box_inner * 2 == 128 && box_rows <= 256, "TMA box must be 64 bf16 wide and <= 256 rows");
+    MST_REQUIRE((!swizzle128 || box_inner * 2 == 128) && (box_inner * 2) % 16 == 0 && box_rows <= 256, "bad TMA box");
     cuuint64_t gdim[2] = {inner, rows};
     cuuint64_t gstride[1] = {row_stride_elems * 2};
     cuuint32_t box[2] = {box_inner, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                           const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu)", (int)r,
                 (unsigned long long)inner, (unsigned long long)rows);
     return 0;
@@ -60,7 +63,9 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t ro
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+constexpr int STG_BYTES = 32 * 32 * 2;  // per-warp staging tile: 32 rows x 32 bf16
 
 template <int BN, int KCH, int STAGES>
 struct GemmSmem {
@@ -68,23 +73,23 @@ struct GemmSmem {
     static constexpr int B_BUFS = KCH > 0 ? KCH : STAGES;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-    static constexpr int BAR_OFF = B_OFF + B_BUFS * B_TILE_BYTES;
+    static constexpr int STG_OFF = B_OFF + B_BUFS * B_TILE_BYTES;
+    static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 1 + 4;
     static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
+    static_assert(DYN_BYTES <= 232448, "shared memory budget (227 KB)");
 };
 
+// acc (+bias, activation, residual) for 32 consecutive columns of one row -> 16 packed bf16x2
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const EpiParams& ep, int64_t row, int M, int N,
-                                               int n0) {
+__device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t (&o)[16], const EpiParams& ep, int64_t row,
+                                              bool row_ok, int N, int n0) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (row >= M) return;
-    int64_t orow = row;
     if (MODE == EPI_PATCH) {
         const int p = static_cast<int>(row % ep.P);
-        orow = (row / ep.P) * (ep.P + 1) + 1 + p;
         const float4* pb = reinterpret_cast<const float4*>(ep.posb + static_cast<int64_t>(p) * N + n0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -101,40 +106,35 @@ __device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const Ep
     }
     if (MODE == EPI_BIAS_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf<false>(v[i]);
+        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fit(v[i]);
     }
     if (MODE == EPI_BIAS_RES) {
-        const uint4* pr = reinterpret_cast<const uint4*>(static_cast<const bf16*>(ep.res) + row * ep.ldr + n0);
+        if (row_ok) {
+            const uint4* pr = reinterpret_cast<const uint4*>(static_cast<const bf16*>(ep.res) + row * ep.ldr + n0);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint4 u = pr[i];
-            float2 f;
-            f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-            f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-            f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-            f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+            for (int i = 0; i < 4; ++i) {
+                const uint4 u = __ldg(pr + i);
+                float2 f;
+                f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
+                f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
+                f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
+                f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+            }
         }
     }
-    uint4* po = reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        uint4 u;
-        u.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-        u.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-        u.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-        u.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        po[i] = u;
-    }
+    for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 }
 
 template <int BN, int KCH, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, int M, int N, int K, int mode,
-               EpiParams ep) {
+gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, const __grid_constant__ TmaDesc tmC,
+               int M, int N, int K, int mode, EpiParams ep) {
     using L = GemmSmem<BN, KCH, STAGES>;
     constexpr bool kResident = KCH > 0;
     constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+    constexpr int CHUNKS_PER_WARP = BN / 64;  // each epilogue warp covers BN/2 columns in 32-column chunks
+    static_assert(2 * BN <= 512 && BN % 64 == 0, "two accumulator stages must fit TMEM");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -171,11 +171,12 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(bfull_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
@@ -239,7 +240,11 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int w = warp - 4;  // == warp % 4: TMEM lane quadrant this warp may access
+        const int e = warp - 4;
+        const int q = e & 3;    // == warp % 4: the TMEM lane quadrant this warp may access
+        const int hf = e >> 2;  // column half
+        uint8_t* stg = smem + L::STG_OFF + e * STG_BYTES;
+        uint4* stg_row = reinterpret_cast<uint4*>(stg + lane * 64);
         int acc = 0; uint32_t acc_phase = 0;
         for (int it = 0; it < t_count; ++it) {
             const int t = t_first + it * t_step;
@@ -247,19 +252,45 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             const int n_blk = kResident ? n_fixed : t % n_tiles;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after_sync();
-            const int64_t row = static_cast<int64_t>(m_blk) * BM + w * 32 + lane;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(w * 32) << 16) + static_cast<uint32_t>(acc * BN);
+            const int row0 = m_blk * BM + q * 32;
+            const int64_t row = static_cast<int64_t>(row0) + lane;
+            const bool row_ok = row < M;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
+                                   static_cast<uint32_t>(acc * BN + hf * (BN / 2));
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
+            for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+                uint32_t r[32], o[16];
                 tmem_ld_32x32b_x32(taddr + c * 32, r);
                 tmem_ld_wait();
-                const int n0 = n_blk * BN + c * 32;
+                const int n0 = n_blk * BN + hf * (BN / 2) + c * 32;
                 switch (mode) {
-                    case EPI_BIAS: epilogue_chunk<EPI_BIAS>(r, ep, row, M, N, n0); break;
-                    case EPI_BIAS_GELU: epilogue_chunk<EPI_BIAS_GELU>(r, ep, row, M, N, n0); break;
-                    case EPI_BIAS_RES: epilogue_chunk<EPI_BIAS_RES>(r, ep, row, M, N, n0); break;
-                    default: epilogue_chunk<EPI_PATCH>(r, ep, row, M, N, n0); break;
+                    case EPI_BIAS:
+                    case EPI_BIAS_ACCUM: epilogue_math<EPI_BIAS>(r, o, ep, row, row_ok, N, n0); break;
+                    case EPI_BIAS_GELU: epilogue_math<EPI_BIAS_GELU>(r, o, ep, row, row_ok, N, n0); break;
+                    case EPI_BIAS_RES: epilogue_math<EPI_BIAS_RES>(r, o, ep, row, row_ok, N, n0); break;
+                    default: epilogue_math<EPI_PATCH>(r, o, ep, row, row_ok, N, n0); break;
+                }
+                if (mode == EPI_PATCH) {
+                    // rows are re-mapped (one CLS row inserted per slice): direct 64-byte row stores
+                    if (row_ok) {
+                        const int64_t orow = (row / ep.P) * (ep.P + 1) + 1 + (row % ep.P);
+                        uint4* po = reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    }
+                } else {
+                    // staging tile must no longer be read by the previous TMA store of this warp
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) stg_row[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, stg, n0, row0);
+                        else tma_store_2d(&tmC, stg, n0, row0);
+                        tma_store_commit();
+                    }
                 }
             }
             tc_fence_before_sync();
@@ -267,6 +298,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
+        if (lane == 0) tma_store_wait_all<0>();  // all output bytes are in global memory before the CTA retires
+        __syncwarp();
     }
 
     tc_fence_before_sync();
@@ -281,8 +314,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
 // host launcher
 // ---------------------------------------------------------------------------------------------------
 template <int BN, int KCH, int STAGES>
-static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, int M, int N, int K, int mode, const EpiParams& ep,
-                      int num_sms, cudaStream_t stream) {
+static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC, int M, int N, int K, int mode,
+                      const EpiParams& ep, int num_sms, cudaStream_t stream) {
     using L = GemmSmem<BN, KCH, STAGES>;
     auto kern = gemm_tc_kernel<BN, KCH, STAGES>;
     static bool attr_set = false;
@@ -301,7 +334,7 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, int M, int N, int 
     } else {
         grid = m_tiles * n_tiles < num_sms ? m_tiles * n_tiles : num_sms;
     }
-    kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, M, N, K, mode, ep);
+    kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, mode, ep);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -312,16 +345,21 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
     MST_REQUIRE(N % 192 == 0 || N % 128 == 0, "gemm: N=%d must be a multiple of 192 or 128", N);
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
-    TmaDesc tmA, tmB;
+    // in-place residual update: let the TMA engine do `out += acc + bias` (no residual read by the SM)
+    if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) mode = EPI_BIAS_ACCUM;
+    TmaDesc tmA, tmB, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
+    // output map (unused by EPI_PATCH, whose rows are re-mapped): 32x32 boxes, no swizzle
+    const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1) : static_cast<uint64_t>(M);
+    MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false));
     if (N % 192 == 0) {
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
-        if (K == 384) return launch_cfg<192, 6, 4>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
-        if (K == 256) return launch_cfg<192, 4, 4>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
-        return launch_cfg<192, 0, 5>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
+        if (K == 384) return launch_cfg<192, 6, 4>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        if (K == 256) return launch_cfg<192, 4, 4>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        return launch_cfg<192, 0, 5>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
     }
     MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 128));
-    return launch_cfg<128, 0, 6>(tmA, tmB, M, N, K, mode, ep, num_sms, stream);
+    return launch_cfg<128, 0, 6>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
 }
 
 }  // namespace mst
