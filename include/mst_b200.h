@@ -99,8 +99,10 @@ MST_API int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_
                          const float* bias, const void* res, void* out, void* stream);
 MST_API int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, int32_t K, int32_t mode,
                         const float* bias, const float* res, float* out, void* stream);
-/* qkv [BD*N, 3*heads*64] (q pre-scaled) -> out [BD*N, heads*64] */
+/* qkv [BD*N, 3*heads*64] (q pre-scaled) -> out [BD*N, heads*64].  _bf16 picks the tcgen05 kernel for N == 257 and the
+ * warp-MMA kernel otherwise; _bf16_warp_mma always runs the latter. */
 MST_API int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
+MST_API int mst_kernel_attention_bf16_warp_mma(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_attention_f32(const float* qkv, float* out, int32_t BD, int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t E,
                               float eps, void* stream);

@@ -269,7 +269,9 @@ template <> struct Ops<bf16> {
         MST_REQUIRE(lda == K, "bf16 gemm expects a dense A (lda == K)");
         return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, h->num_sms, st);
     }
-    static int attention(const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
+    static int attention(mst_handle h, const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
+        if (N == 257)  // ViT @224: tcgen05 kernel; other token counts: warp-MMA kernel
+            return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
         return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, st);
     }
 };
@@ -277,7 +279,7 @@ template <> struct Ops<float> {
     static int gemm(mst_handle, const void* A, int64_t lda, const void* W, int M, int N, int K, int mode, const EpiParams& ep, cudaStream_t st) {
         return gemm_f32_simt(static_cast<const float*>(A), lda, static_cast<const float*>(W), M, N, K, mode, ep, st);
     }
-    static int attention(const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
+    static int attention(mst_handle, const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
         return launch_attention_f32(static_cast<const float*>(qkv), static_cast<float*>(out), BD, N, heads, st);
     }
 };
@@ -321,7 +323,7 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
             MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, xn, E, L.wqkv, M, 3 * E, E, EPI_BIAS, ep, st));
         }
         if (!last) {
-            MST_LAUNCH(CAT_ATTENTION, Ops<T>::attention(ws.qkv, xn, BD, N, c.enc_heads, st));  // xn is dead: reuse as attention output
+            MST_LAUNCH(CAT_ATTENTION, Ops<T>::attention(h, ws.qkv, xn, BD, N, c.enc_heads, st));  // xn is dead: reuse as attention output
             {
                 EpiParams ep{};
                 ep.bias = L.bproj; ep.res = x; ep.ldr = E; ep.out = x; ep.ldo = E;
@@ -546,6 +548,13 @@ int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, in
 }
 int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
     MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16: null argument");
+    if (N == 257)
+        return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
+                                      static_cast<cudaStream_t>(stream));
+    return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_attention_bf16_warp_mma(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
+    MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16_warp_mma: null argument");
     return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, static_cast<cudaStream_t>(stream));
 }
 int mst_kernel_attention_f32(const float* qkv, float* out, int32_t BD, int32_t N, int32_t heads, void* stream) {

@@ -57,6 +57,25 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t ro
     return 0;
 }
 
+// 3D view [d2][d1][d0] (d0 contiguous), box {box0, box1, 1}; out-of-range rows read as zero / are not written
+int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+                     uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128) {
+    MST_PROPAGATE(tma_init());
+    MST_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+    MST_REQUIRE((stride1_elems * 2) % 16 == 0 && (stride2_elems * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
+    MST_REQUIRE((!swizzle128 || box0 * 2 == 128) && box1 <= 256, "bad TMA box");
+    cuuint64_t gdim[3] = {d0, d1, d2};
+    cuuint64_t gstride[2] = {stride1_elems * 2, stride2_elems * 2};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                          const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3D) failed with CUresult %d", (int)r);
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------------

@@ -100,6 +100,25 @@ def test_attention_bf16(BD, N, heads):
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize("BD,heads", [(1, 6), (25, 6), (130, 6), (40, 12)])
+def test_attention_tcgen05_257(BD, heads):
+    """N == 257 routes to the tcgen05 kernel; many items per CTA exercise the stage ring and barrier phases."""
+    cabi, L = _lib()
+    N, E = 257, heads * 64
+    g = torch.Generator(device="cuda").manual_seed(BD)
+    qkv = torch.randn(BD * N, 3 * E, device="cuda", generator=g)
+    qkv[:, :E] *= 0.6
+    qkv = qkv.bfloat16()
+    out = torch.full((BD * N, E), float("nan"), device="cuda").bfloat16()
+    out2 = torch.full((BD * N, E), float("nan"), device="cuda").bfloat16()
+    cabi.check(L.mst_kernel_attention_bf16(cabi.ptr(qkv), cabi.ptr(out), BD, N, heads, _stream()))
+    cabi.check(L.mst_kernel_attention_bf16_warp_mma(cabi.ptr(qkv), cabi.ptr(out2), BD, N, heads, _stream()))
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, BD, N, heads)
+    torch.testing.assert_close(out2.float(), ref, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
 @pytest.mark.parametrize("BD,N,heads", [(2, 257, 6), (1, 65, 6), (1, 325, 12)])
 def test_attention_f32(BD, N, heads):
     cabi, L = _lib()
