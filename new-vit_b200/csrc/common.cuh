@@ -97,7 +97,7 @@ struct TmaDesc {  // opaque 128-byte CUtensorMap
 };
 int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency)
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                     uint32_t box_inner, uint32_t box_rows, bool swizzle128 = true);
+                     uint32_t box_inner, uint32_t box_rows, bool swizzle128 = true, bool swizzle64 = false);
 
 int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                      uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128);

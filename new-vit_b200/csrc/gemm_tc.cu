@@ -4,10 +4,12 @@
 //   warp 0 (1 lane)  TMA producer   : A k-chunks (128 x 64 bf16, 128B swizzle) through a STAGES-deep ring
 //   warp 1 (1 lane)  MMA issuer     : tcgen05.mma cta_group::1, M=128, N=BN, K=16 per instruction
 //   warp 2           TMEM allocator : 2 accumulator stages of BN fp32 columns (epilogue overlaps next tile)
-//   warps 4..11      epilogue       : warp e reads TMEM lane quadrant e%4, column half e/4 (tcgen05.ld 32x32b),
-//                                     applies bias / GELU / residual, packs bf16 into a private 32x32 staging tile
-//                                     in shared memory and hands it to the TMA store engine (coalesced, clipped
-//                                     at M; in-place residual update = TMA reduce-add, no residual read at all).
+//   warps 4..11      epilogue       : warp e reads TMEM lane quadrant e%4, column half e/4 (tcgen05.ld 32x32b, the next
+//                                     chunk's load in flight while the current one is processed), adds bias (smem
+//                                     cache) / GELU / residual, packs bf16, transposes each 32x32 block through a
+//                                     private swizzled smem tile and writes 8 rows x 64 B per store instruction; the
+//                                     in-place residual update is a 16-byte vector reduction (REDG.ADD.BF16x8), so
+//                                     the SM never reads the residual.
 //
 // Weight-resident mode (KCH > 0): K <= 384, so the whole [BN x K] weight slab (<= 144 KB) is loaded into
 // shared memory ONCE per CTA and only A streams; each CTA owns one n-block and walks m-blocks.  This cuts
@@ -38,7 +40,7 @@ int tma_init() {
 }
 
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_elems,
-                     uint32_t box_inner, uint32_t box_rows, bool swizzle128) {
+                     uint32_t box_inner, uint32_t box_rows, bool swizzle128, bool swizzle64) {
     MST_PROPAGATE(tma_init());
     static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
     MST_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -50,7 +52,7 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t ro
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                           const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE),
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MST_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu rows=%llu)", (int)r,
                 (unsigned long long)inner, (unsigned long long)rows);
@@ -84,26 +86,31 @@ constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
-constexpr int STG_BYTES = 32 * 32 * 2;  // per-warp staging tile: 32 rows x 32 bf16
+constexpr int STG_TILE = 32 * 32 * 2;   // staging tile: 32 rows x 32 bf16
 
-template <int BN, int KCH, int STAGES>
+
+template <int BN, int KCH, int STAGES, int NSTG>
 struct GemmSmem {
+    static constexpr int STG_BYTES = NSTG * STG_TILE;  // per warp; NSTG == 2: one TMA store in flight while the next tile fills
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int B_BUFS = KCH > 0 ? KCH : STAGES;
+    static constexpr int BIAS_FLOATS = KCH > 0 ? BN : 2048;  // resident: this CTA's n-block; streaming: the whole vector
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
     static constexpr int STG_OFF = B_OFF + B_BUFS * B_TILE_BYTES;
-    static constexpr int BAR_OFF = STG_OFF + EPI_WARPS * STG_BYTES;
+    static constexpr int BIAS_OFF = STG_OFF + EPI_WARPS * STG_BYTES;
+    static constexpr int BAR_OFF = BIAS_OFF + BIAS_FLOATS * 4;
     static constexpr int NUM_BARS = 2 * STAGES + 1 + 4;
     static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
     static_assert(DYN_BYTES <= 232448, "shared memory budget (227 KB)");
 };
 
-// acc (+bias, activation, residual) for 32 consecutive columns of one row -> 16 packed bf16x2
+// acc + bias (activation, residual) for 32 consecutive columns of one row -> 16 packed bf16x2.
+// `bias` points to the 32 bias values of this chunk (shared memory cache or global).
 template <int MODE>
-__device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t (&o)[16], const EpiParams& ep, int64_t row,
-                                              bool row_ok, int N, int n0) {
+__device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t (&o)[16], const EpiParams& ep,
+                                              const float* bias, bool bias_smem, int64_t row, bool row_ok, int N, int n0) {
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
@@ -116,11 +123,21 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
             v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
         }
     } else {
-        const float4* pb = reinterpret_cast<const float4*>(ep.bias + n0);
+        if (bias_smem) {
+            const uint32_t sb = smem_u32(bias);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(pb + i);
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            for (int i = 0; i < 8; ++i) {
+                float4 b;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sb + i * 16));
+                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
+        } else {
+            const float4* pb = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 b = __ldg(pb + i);
+                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            }
         }
     }
     if (MODE == EPI_BIAS_GELU) {
@@ -145,20 +162,53 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
     for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 }
 
-template <int BN, int KCH, int STAGES>
+__device__ __forceinline__ void red_add_bf16x8(void* gptr, const uint4& v) {
+    asm volatile("red.global.v4.bf16x2.add.noftz [%0], {%1, %2, %3, %4};" ::"l"(gptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// One 32x32 bf16 block (lane = row, o = its 32 columns) -> global, coalesced: the block is transposed through a
+// per-warp, XOR-swizzled shared-memory tile so that every store instruction writes 8 rows x 64 contiguous bytes
+// (8 LSU wavefronts instead of 32).  ACCUM: 16-byte vector reductions (REDG.ADD.BF16x8) instead of stores.
+__device__ __forceinline__ void store_block_32x32(uint8_t* stg, const uint32_t (&o)[16], int lane, int mode, const EpiParams& ep,
+                                                  int row0, int M, int n0) {
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(stg + lane * 64 + ((i ^ sw) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    __syncwarp();
+    const int pc = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = k * 8 + (lane >> 2);
+        const uint4 u = *reinterpret_cast<const uint4*>(stg + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+        const int64_t row = static_cast<int64_t>(row0) + r;
+        if (row < M) {
+            int64_t orow = row;
+            if (mode == EPI_PATCH) orow = (row / ep.P) * (ep.P + 1) + 1 + (row % ep.P);
+            bf16* dst = static_cast<bf16*>(ep.out) + orow * ep.ldo + n0 + pc * 8;
+            if (mode == EPI_BIAS_ACCUM) red_add_bf16x8(dst, u);
+            else *reinterpret_cast<uint4*>(dst) = u;
+        }
+    }
+    __syncwarp();
+}
+
+template <int BN, int KCH, int STAGES, int NSTG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, const __grid_constant__ TmaDesc tmC,
                int M, int N, int K, int mode, EpiParams ep) {
-    using L = GemmSmem<BN, KCH, STAGES>;
+    using L = GemmSmem<BN, KCH, STAGES, NSTG>;
     constexpr bool kResident = KCH > 0;
     constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
     constexpr int CHUNKS_PER_WARP = BN / 64;  // each epilogue warp covers BN/2 columns in 32-column chunks
-    static_assert(2 * BN <= 512 && BN % 64 == 0, "two accumulator stages must fit TMEM");
+    static_assert(2 * BN <= 512 && (CHUNKS_PER_WARP == 2 || CHUNKS_PER_WARP == 3), "tile shape");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t* sA = smem + L::A_OFF;
     uint8_t* sB = smem + L::B_OFF;
+    float* sBias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + STAGES;
@@ -199,6 +249,13 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    // bias cache (EPI_PATCH has no bias vector)
+    const bool bias_cached = mode != EPI_PATCH && (kResident || N <= L::BIAS_FLOATS);
+    if (bias_cached && warp >= 4) {
+        const int cnt = kResident ? BN : N;
+        const float* src = ep.bias + (kResident ? n_fixed * BN : 0);
+        for (int i = threadIdx.x - 128; i < cnt; i += EPI_WARPS * 32) sBias[i] = __ldg(src + i);
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -229,65 +286,69 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
-            if (kResident && t_count > 0) { mbar_wait(bfull_bar, 0); tc_fence_after_sync(); }
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int it = 0; it < t_count; ++it) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        // ===================== MMA issuer =====================
+        // The whole warp runs this loop convergently (operands stay in uniform registers; a single-lane loop made
+        // ptxas route every descriptor through ELECT/R2UR and the issue loop, not the tensor pipe, set the pace);
+        // one elected lane issues.  Descriptors are a constant high word + (smem address >> 4) in the low word.
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B | version 1 | SWIZZLE_128B
+        const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFF) >> 4;
+        const uint32_t b_lo0 = (smem_u32(sB) & 0x3FFFF) >> 4;
+        if (kResident && t_count > 0) { mbar_wait(bfull_bar, 0); tc_fence_after_sync(); }
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int it = 0; it < t_count; ++it) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                for (int kc = 0; kc < kchunks; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after_sync();
-                    const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_addr = smem_u32(sB + (kResident ? kc : stage) * L::B_TILE_BYTES);
+                const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
+                const uint32_t b_lo = b_lo0 + (kResident ? kc : stage) * (L::B_TILE_BYTES >> 4);
+                if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_bf16_ss(d_tmem, umma_desc_sw128_kmajor(a_addr + k * 32),
-                                     umma_desc_sw128_kmajor(b_addr + k * 32), idesc, (kc | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_ss(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
+                                     (kc | k) != 0 ? 1u : 0u);
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (kc == kchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                 }
-                umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int e = warp - 4;
         const int q = e & 3;    // == warp % 4: the TMEM lane quadrant this warp may access
         const int hf = e >> 2;  // column half
-        uint8_t* stg = smem + L::STG_OFF + e * STG_BYTES;
-        uint4* stg_row = reinterpret_cast<uint4*>(stg + lane * 64);
+        uint8_t* stg = smem + L::STG_OFF + e * L::STG_BYTES;
+        int stg_sel = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int it = 0; it < t_count; ++it) {
             const int t = t_first + it * t_step;
             const int m_blk = kResident ? t : t / n_tiles;
             const int n_blk = kResident ? n_fixed : t % n_tiles;
-            mbar_wait(&tfull_bar[acc], acc_phase);
-            tc_fence_after_sync();
             const int row0 = m_blk * BM + q * 32;
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < M;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) +
-                                   static_cast<uint32_t>(acc * BN + hf * (BN / 2));
-#pragma unroll 1
-            for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
-                uint32_t r[32], o[16];
-                tmem_ld_32x32b_x32(taddr + c * 32, r);
-                tmem_ld_wait();
-                const int n0 = n_blk * BN + hf * (BN / 2) + c * 32;
+            const int col0 = hf * (BN / 2);                       // first column of this warp inside the tile
+            const int nbase = n_blk * BN + col0;                  // ... and in the output
+            const float* bias0 = bias_cached ? sBias + (kResident ? col0 : nbase) : (mode == EPI_PATCH ? nullptr : ep.bias + nbase);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
+
+            auto process = [&](const uint32_t (&r)[32], int c) {
+                uint32_t o[16];
+                const int n0 = nbase + c * 32;
+                const float* b = bias0 + c * 32;
                 switch (mode) {
                     case EPI_BIAS:
-                    case EPI_BIAS_ACCUM: epilogue_math<EPI_BIAS>(r, o, ep, row, row_ok, N, n0); break;
-                    case EPI_BIAS_GELU: epilogue_math<EPI_BIAS_GELU>(r, o, ep, row, row_ok, N, n0); break;
-                    case EPI_BIAS_RES: epilogue_math<EPI_BIAS_RES>(r, o, ep, row, row_ok, N, n0); break;
-                    default: epilogue_math<EPI_PATCH>(r, o, ep, row, row_ok, N, n0); break;
+                    case EPI_BIAS_ACCUM: epilogue_math<EPI_BIAS>(r, o, ep, b, bias_cached, row, row_ok, N, n0); break;
+                    case EPI_BIAS_GELU: epilogue_math<EPI_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0); break;
+                    case EPI_BIAS_RES: epilogue_math<EPI_BIAS_RES>(r, o, ep, b, bias_cached, row, row_ok, N, n0); break;
+                    default: epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0); break;
                 }
                 if (mode == EPI_PATCH) {
                     // rows are re-mapped (one CLS row inserted per slice): direct 64-byte row stores
@@ -298,23 +359,48 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                         for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     }
                 } else {
-                    // staging tile must no longer be read by the previous TMA store of this warp
-                    if (lane == 0) tma_store_wait_read<0>();
+                    // the tile written two stores ago must no longer be read by its TMA store
+                    uint8_t* tile = stg + stg_sel * STG_TILE;
+                    if (NSTG == 2) stg_sel ^= 1;
+                    if (lane == 0) tma_store_wait_read<NSTG - 1>();
                     __syncwarp();
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) stg_row[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(tile + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
+                            make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, stg, n0, row0);
-                        else tma_store_2d(&tmC, stg, n0, row0);
+                        if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, tile, n0, row0);
+                        else tma_store_2d(&tmC, tile, n0, row0);
                         tma_store_commit();
                     }
                 }
+            };
+            auto release_tmem = [&]() {  // every tcgen05.ld of this tile has completed
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            };
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after_sync();
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32b_x32(taddr, ra);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(taddr + 32, rb);  // in flight while chunk 0 is processed
+            process(ra, 0);
+            tmem_ld_wait();
+            if (CHUNKS_PER_WARP == 2) {
+                release_tmem();
+                process(rb, 1);
+            } else {
+                tmem_ld_32x32b_x32(taddr + 64, ra);
+                process(rb, 1);
+                tmem_ld_wait();
+                release_tmem();
+                process(ra, 2);
             }
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
         if (lane == 0) tma_store_wait_all<0>();  // all output bytes are in global memory before the CTA retires
@@ -332,11 +418,11 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
 // ---------------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int KCH, int STAGES>
+template <int BN, int KCH, int STAGES, int NSTG>
 static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC, int M, int N, int K, int mode,
                       const EpiParams& ep, int num_sms, cudaStream_t stream) {
-    using L = GemmSmem<BN, KCH, STAGES>;
-    auto kern = gemm_tc_kernel<BN, KCH, STAGES>;
+    using L = GemmSmem<BN, KCH, STAGES, NSTG>;
+    auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG>;
     static bool attr_set = false;
     if (!attr_set) {
         MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -364,21 +450,23 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
     MST_REQUIRE(N % 192 == 0 || N % 128 == 0, "gemm: N=%d must be a multiple of 192 or 128", N);
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
-    // in-place residual update: let the TMA engine do `out += acc + bias` (no residual read by the SM)
+    // in-place residual update: `out += acc + bias` as 16-byte vector reductions (no residual read by the SM)
     if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) mode = EPI_BIAS_ACCUM;
     TmaDesc tmA, tmB, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
-    // output map (unused by EPI_PATCH, whose rows are re-mapped): 32x32 boxes, no swizzle
+    // output map (unused by EPI_PATCH, whose rows are re-mapped): 32x32 boxes, 64B swizzle (conflict-free staging writes)
     const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1) : static_cast<uint64_t>(M);
-    MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false));
+    MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
     if (N % 192 == 0) {
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
-        if (K == 384) return launch_cfg<192, 6, 4>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-        if (K == 256) return launch_cfg<192, 4, 4>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-        return launch_cfg<192, 0, 5>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        // GELU epilogue (fc1) is the longest: give it two staging tiles per warp and a 3-deep A ring instead
+        if (K == 384 && mode == EPI_BIAS_GELU) return launch_cfg<192, 6, 3, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        if (K == 384) return launch_cfg<192, 6, 4, 1>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        if (K == 256) return launch_cfg<192, 4, 4, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        return launch_cfg<192, 0, 5, 1>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
     }
     MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 128));
-    return launch_cfg<128, 0, 6>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+    return launch_cfg<128, 0, 5, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
 }
 
 }  // namespace mst

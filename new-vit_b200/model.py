@@ -127,6 +127,9 @@ class DinoV2ClassifierSlice(nn.Module):
         self._handle_key = None
         self._dirty = True
         self._workspace = None
+        self._h2d = None
+        self._copy_stream = None
+        self.h2d_chunk_volumes = 8   # host batches larger than this are pipelined H2D || compute
         self._last = None
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_dirty", True))
 
@@ -182,14 +185,12 @@ class DinoV2ClassifierSlice(nn.Module):
         if self._dirty or self._handle is None:
             self.sync_weights()
         dev = self.device
-        x = source.to(dev)                                  # dino.py:121
-        if x.dim() != 5:
-            raise ValueError(f"expected source [B, C, D, H, W], got {tuple(x.shape)}")
-        B, C, D, H, W = x.shape
+        if source.dim() != 5:
+            raise ValueError(f"expected source [B, C, D, H, W], got {tuple(source.shape)}")
+        B, C, D, H, W = source.shape
         assert C == 1, "More than one channel"             # dino.py:14 / the (b d c) flatten at :125
         assert H % 14 == 0 and W % 14 == 0, \
             f"Input image height {H} / width {W} is not a multiple of patch size 14"   # patch_embed.py:72-73
-        x = x.to(torch.float32).contiguous()
         L = _cabi.lib()
         E, heads = self.emb_ch, self.encoder.num_heads
         N = (H // 14) * (W // 14) + 1
@@ -198,6 +199,12 @@ class DinoV2ClassifierSlice(nn.Module):
             mask = src_key_padding_mask.to(dev).to(torch.uint8).contiguous()
             if tuple(mask.shape) != (B, D):
                 raise ValueError(f"src_key_padding_mask must be [B, D] = {(B, D)}, got {tuple(mask.shape)}")
+        # `source.to(self.device)` (dino.py:121).  A host batch is moved in chunks of whole volumes on a copy stream so
+        # that the H2D transfer of chunk k+1 overlaps the kernels of chunk k (volumes are independent: results are
+        # bit-identical to a single call, tests/test_gpu_parity.py::test_batch_composition...).
+        chunk = B
+        if source.device.type == "cpu" and self.h2d_chunk_volumes and B > self.h2d_chunk_volumes:
+            chunk = self.h2d_chunk_volumes
         with torch.cuda.device(dev):
             logits = torch.empty((B, self.out_ch), device=dev, dtype=torch.float32)
             feat = torch.empty((B, E), device=dev, dtype=torch.float32)
@@ -205,14 +212,42 @@ class DinoV2ClassifierSlice(nn.Module):
             slc = torch.empty((B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
             enc = torch.empty((B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
             need = _cabi.ctypes.c_size_t()
-            _cabi.check(L.mst_workspace_bytes(self._handle, B, D, H, W, _cabi.ctypes.byref(need)))
+            _cabi.check(L.mst_workspace_bytes(self._handle, chunk, D, H, W, _cabi.ctypes.byref(need)))
             if self._workspace is None or self._workspace.numel() < need.value or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need.value, device=dev, dtype=torch.uint8)
-            stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _cabi.check(L.mst_forward(self._handle, _cabi.ptr(x), B, D, H, W, _cabi.ptr(mask), _cabi.ptr(logits),
-                                      _cabi.ptr(feat), _cabi.ptr(enc), _cabi.ptr(plane), _cabi.ptr(slc),
-                                      _cabi.ptr(self._workspace), self._workspace.numel(), stream))
+            cur = torch.cuda.current_stream()
+            stream = _cabi.ctypes.c_void_p(cur.cuda_stream)
+
+            def run(xc, b0, nb):
+                sl = lambda t, per: None if t is None else t[b0 * per:(b0 + nb) * per]
+                _cabi.check(L.mst_forward(self._handle, _cabi.ptr(xc), nb, D, H, W, _cabi.ptr(sl(mask, 1)),
+                                          _cabi.ptr(sl(logits, 1)), _cabi.ptr(sl(feat, 1)), _cabi.ptr(sl(enc, D)),
+                                          _cabi.ptr(sl(plane, D)), _cabi.ptr(sl(slc, 1)),
+                                          _cabi.ptr(self._workspace), self._workspace.numel(), stream))
+
+            if chunk == B:
+                x = source.to(dev).to(torch.float32).contiguous()
+                run(x, 0, B)
+            else:
+                src = source if source.dtype == torch.float32 else source.float()
+                if self._h2d is None or self._h2d[0].shape[1:] != (1, D, H, W) or self._h2d[0].device != dev:
+                    self._h2d = [torch.empty((chunk, 1, D, H, W), device=dev, dtype=torch.float32) for _ in range(2)]
+                    self._copy_stream = torch.cuda.Stream(device=dev)
+                copied = [torch.cuda.Event() for _ in range(2)]
+                freed = [torch.cuda.Event() for _ in range(2)]
+                nchunks = (B + chunk - 1) // chunk
+                self._copy_stream.wait_stream(cur)   # buffers may still be read by a previous forward
+                for k in range(nchunks):
+                    b0, nb, buf = k * chunk, min(chunk, B - k * chunk), self._h2d[k & 1]
+                    with torch.cuda.stream(self._copy_stream):
+                        if k >= 2:
+                            self._copy_stream.wait_event(freed[k & 1])
+                        buf[:nb].copy_(src[b0:b0 + nb], non_blocking=True)
+                        copied[k & 1].record(self._copy_stream)
+                    cur.wait_event(copied[k & 1])
+                    run(buf, b0, nb)
+                    freed[k & 1].record(cur)
         if save_attn:
             # The reference keeps 12 x [BD,heads,N,N] (dino.py:241); its getters only ever read row 0 of the last
             # one.  We keep that row, shaped [BD,heads,1,N] so that `attention_maps[-1][:, :, 0, 1:]` still works.

@@ -130,6 +130,26 @@ def test_batch_composition_invariance_and_properties():
     torch.testing.assert_close(full.reshape(B, -1).mean(-1) * 256 * D, torch.ones(B), rtol=5e-2, atol=0)
 
 
+def test_pipelined_host_input_is_bit_identical():
+    """Host batches are moved in chunks of whole volumes on a copy stream (H2D overlapped with compute); the result
+    must be bit-identical to the single-call path, including the attention rows and the padding mask slicing."""
+    from new_vit_b200 import synth
+    B, D, H, W = 5, 4, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=21, variant="peaky")
+    x = synth.make_volume(B, D, H, W, seed=22).pin_memory()
+    mask = synth.make_padding_mask(B, D, seed=1)
+    m = _model(sd, "bf16", H)
+    with torch.no_grad():
+        y0 = m(x.cuda(), save_attn=True, src_key_padding_mask=mask).cpu()
+        maps0 = m.get_attention_maps().cpu()
+        m.h2d_chunk_volumes = 2          # 3 chunks: 2 + 2 + 1 volumes
+        y1 = m(x, save_attn=True, src_key_padding_mask=mask).cpu()
+        maps1 = m.get_attention_maps().cpu()
+        y2 = m(x, save_attn=True, src_key_padding_mask=mask).cpu()  # buffers reused on the second call
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    assert torch.equal(maps0, maps1)
+
+
 def test_errors_mirror_reference():
     from new_vit_b200 import DinoV2ClassifierSlice
     m = DinoV2ClassifierSlice(1, 2, pretrained=False).cuda().eval()
