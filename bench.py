@@ -125,6 +125,7 @@ def main():
     import torch
     import torch.distributed as dist
     from new_vit_b200 import DinoV2ClassifierSlice, synth
+    from new_vit_b200.dist import gather_volumes
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -136,7 +137,6 @@ def main():
     model.load_state_dict(synth.make_state_dict("s", 2, seed=0))
     x_host = synth.make_volume(B, D, 224, 224, seed=rank).pin_memory()
     x_dev = x_host.to(dev)
-    gathered = [torch.empty(B, 2, device=dev) for _ in range(world)] if world > 1 else None
 
     def step(src):
         with torch.no_grad():
@@ -144,7 +144,7 @@ def main():
             if args.saliency:
                 model.saliency_volume()
             if world > 1:
-                dist.all_gather(gathered, y)  # only the logits are gathered
+                y = gather_volumes(y, B * world)  # only the [B,2] logits cross NVLink
         return y
 
     def barrier():

@@ -32,6 +32,8 @@ CASES = {
     "s_peaky_mask_b2": ("s", "peaky", 2, 32, 224, 224, True, 1, 1),
     "s_init_small": ("s", "init", 1, 5, 112, 112, False, 2, 2),
     "s_peaky_small_mask_b3": ("s", "peaky", 3, 7, 112, 112, True, 3, 3),
+    # config 4 of BASELINE.json: ViT-B/14 encoder at 252x252 (256x256 is rejected by the reference, patch_embed.py:72-73)
+    "b_peaky_252_mask_b2": ("b", "peaky", 2, 3, 252, 252, True, 4, 4),
 }
 
 

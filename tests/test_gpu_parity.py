@@ -12,12 +12,12 @@ from conftest import case_inputs, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2"]
+GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2"]
 
 
-def _model(sd, precision, img_size):
+def _model(sd, precision, img_size, size="s"):
     from new_vit_b200 import DinoV2ClassifierSlice
-    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=precision, img_size=img_size).cuda().eval()
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=precision, img_size=img_size, model_size=size).cuda().eval()
     m.load_state_dict(sd)
     return m
 
@@ -45,7 +45,7 @@ def _run(m, x, mask):
 def test_fp32_matches_reference_golden(name):
     meta, g = load_golden(name)
     sd, x, mask = case_inputs(meta)
-    r = _run(_model(sd, "fp32", meta["H"]), x, mask)
+    r = _run(_model(sd, "fp32", meta["H"], meta["size"]), x, mask)
     B = meta["B"]
     scale = g["logits"].abs().max().item()
     assert (r["logits"] - g["logits"]).abs().max().item() <= 1e-4 * max(scale, 1.0), (r["logits"], g["logits"])
@@ -68,7 +68,7 @@ def test_fp32_matches_reference_golden(name):
 def test_bf16_matches_reference_golden(name):
     meta, g = load_golden(name)
     sd, x, mask = case_inputs(meta)
-    r = _run(_model(sd, "bf16", meta["H"]), x, mask)
+    r = _run(_model(sd, "bf16", meta["H"], meta["size"]), x, mask)
     B = meta["B"]
     err = (r["logits"] - g["logits"]).abs().max().item()
     assert err <= 2e-2, f"bf16 logits differ by {err}: {r['logits']} vs {g['logits']}"

@@ -8,7 +8,7 @@ from oracle import mst_oracle as O
 from oracle import ref_harness
 
 SMALL = ["s_init_small", "s_peaky_small_mask_b3"]
-FULL = ["s_init_b2", "s_peaky_mask_b2"]
+FULL = ["s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2"]
 
 
 def _check(name):
