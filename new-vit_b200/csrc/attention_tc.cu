@@ -2,22 +2,22 @@
 //     out[s, i, h*64:(h+1)*64] = softmax(q_i . K^T) V      per (slice s, head h), q pre-scaled
 // (reference layers/attention.py:56-69).  Persistent, one CTA per SM, 512 threads; items = (slice, head).
 //
-// The 257 = 1 + 2*128 tokens are split as: two query tiles of 128 PATCH tokens (tokens 1..128, 129..256) on the
-// tensor cores, and the single CLS query on CUDA cores from the same shared-memory K/V tiles.
+// 257 = 1 + 2*128: the two query tiles are the 256 PATCH tokens (tokens 1..128, 129..256) and run on the tensor
+// cores against the 256 PATCH keys; the CLS token is handled on CUDA cores both as a key (one extra score column
+// per query row, folded into the row max / sum and added to O as a rank-1 term p0 * v_cls) and as a query (warps
+// 12-15, from the same shared-memory K/V tiles).  Splitting the CLS key off makes a score tile exactly 256 TMEM
+// columns, so TWO tiles are in flight (2 x 256 = all 512 columns): each 256-column buffer holds S (fp32), is then
+// overwritten in place by P (bf16 pairs, columns [0,64) and [128,192)) and receives O in the columns [64,128) that
+// P does not use.  While the softmax warps work on tile g the tensor pipe computes S(g+1) and O(g-1).
 //
-//   warp 0      TMA producer: per item Q0,Q1 (128x64), K, V (272x64: 128+128+16 rows, rows >= 257 zero-filled by
-//               the 3D tensor map) into a 2-stage ring (100 KB per stage, 128B swizzle)
-//   warp 1      MMA issuer:  S[128x272] = Q K^T   (SS: N=256 + N=16, K=64 -> 8 tcgen05.mma)
-//                            O[128x64]  = P V     (TS: A = P from TMEM, B = V MN-major from smem, 17 x K=16)
-//   warp 2      TMEM allocator (512 columns: S 272 fp32 | P 136 (bf16 pairs) | O 64 fp32)
-//   warps 4-11  softmax: warp (quadrant q = w%4, half hf) owns 32 rows x 136 score columns; pass 1 row max
-//               (exchanged between the two halves through smem), pass 2 p = 2^(s*log2e - m*log2e) -> bf16 pairs
-//               -> tcgen05.st into P; partial row sums to smem
-//   warps 12-15 CLS query on CUDA cores (scores, softmax, P.V from the smem tiles) and the O epilogue
-//               (tcgen05.ld O, 1/l, bf16, swizzled staging tile, TMA store)
-//
-// Per tile the MMA issuer queues QK(g+1) ahead of PV(g), so the tensor pipe works while the softmax warps are in
-// pass 1 of the next tile; the kernel is bound by the exponentials (MUFU), not by the tensor pipe.
+//   warp 0      TMA producer: per item Q0,Q1 (128x64), K, V (tokens 1..256) and 16-row boxes holding K/V of token 0,
+//               2-stage ring (100 KB per stage, 128B swizzle)
+//   warp 1      MMA issuer (warp-convergent, one elected lane):
+//                 S = Q K^T   SS, M128 N256 K16 x 4        O = P V   TS (A = P from TMEM), V MN-major, N64 K16 x 16
+//   warp 2      TMEM allocator
+//   warps 4-11  softmax + O epilogue: warp (quadrant q = w%4, half hf) owns 32 rows x 128 score columns
+//   warps 12-15 CLS query on CUDA cores
+// The kernel is bound by the exponentials (MUFU: 2*128*256 per item at 16/clk/SM), not by the tensor pipe.
 #include <math_constants.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -26,21 +26,22 @@ namespace mst {
 
 namespace atc {
 constexpr int N_TOK = 257;
-constexpr int KEYS_PAD = 272;               // 17 x 16
 constexpr int Q_TILE_BYTES = 128 * 128;     // 16 KB
-constexpr int KV_BYTES = KEYS_PAD * 128;    // 34816
-constexpr int STAGE_BYTES = 2 * Q_TILE_BYTES + 2 * KV_BYTES;  // 102400
+constexpr int KV_BYTES = 256 * 128;         // 32 KB: tokens 1..256
+constexpr int KV0_BYTES = 16 * 128;         // 2 KB: tokens 0..15, only row 0 (CLS) is used
+constexpr int STAGE_BYTES = 2 * Q_TILE_BYTES + 2 * KV_BYTES + 2 * KV0_BYTES;  // 102400
+constexpr int OFF_K = 2 * Q_TILE_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_K0 = OFF_V + KV_BYTES, OFF_V0 = OFF_K0 + KV0_BYTES;
 constexpr int NUM_STAGES = 2;
-constexpr int OSTG_OFF = NUM_STAGES * STAGE_BYTES;            // 4 x 4 KB O staging tiles
-constexpr int STATS_OFF = OSTG_OFF + 8 * 2048;                // [2 parity][max h0, max h1, sum h0, sum h1][128] floats
-constexpr int CLS_OFF = STATS_OFF + 2 * 2 * 2 * 128 * 4;      // pbuf[272] + red[16] + part[128] floats
+constexpr int OSTG_OFF = NUM_STAGES * STAGE_BYTES;            // 8 x 2 KB O staging tiles
+constexpr int STATS_OFF = OSTG_OFF + 8 * 2048;                // [2 parity][6 kinds][128] floats
+constexpr int STATS_KINDS = 7;                                // max h0, max h1, sum h0, sum h1, dot h0, dot h1, p0 (CLS key)
+constexpr int CLS_OFF = STATS_OFF + 2 * STATS_KINDS * 128 * 4;  // pbuf[272] + red[16] + part[256] floats
 constexpr int BAR_OFF = CLS_OFF + (272 + 16 + 256) * 4;
-constexpr int NUM_BARS = 2 * NUM_STAGES + 1 + 2 + 1 + 1;      // kv_full[2], kv_empty[2], s_full, sp_done[2], o_full, o_free
+constexpr int NUM_BARS = 2 * NUM_STAGES + 2 + 2 + 2 + 2;      // kv_full[2], kv_empty[2], s_full[2], sp_done[2], o_full[2], o_free[2]
 constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
 constexpr int DYN_BYTES = TOTAL + 1024;
 static_assert(DYN_BYTES <= 232448, "shared memory budget");
 constexpr int THREADS = 512;
-constexpr uint32_t TM_S = 0, TM_P = 272, TM_O = 408;
 constexpr float LOG2E = 1.4426950408889634f;
 }  // namespace atc
 
@@ -58,32 +59,35 @@ __device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_
 }
 
 // pass-2 math for 32 score columns already in registers: p = 2^(s*log2e - mb) -> 16 packed bf16 pairs; returns sum(p)
-template <bool kMasked>
-__device__ __forceinline__ float softmax_math32(const uint32_t (&r)[32], uint32_t (&o)[16], float mb, int n_valid) {
+__device__ __forceinline__ float softmax_math32(const uint32_t (&r)[32], uint32_t (&o)[16], float mb) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-        float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), atc::LOG2E, -mb));
-        float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), atc::LOG2E, -mb));
-        if (kMasked) {
-            if (i >= n_valid) p0 = 0.f;
-            if (i + 1 >= n_valid) p1 = 0.f;
-        }
+        const float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), atc::LOG2E, -mb));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), atc::LOG2E, -mb));
         o[i >> 1] = pack_bf16x2(p0, p1);
         s0 += p0;
         s1 += p1;
     }
     return s0 + s1;
 }
-template <bool kMasked>
-__device__ __forceinline__ float max32(const uint32_t (&r)[32], float m, int n_valid) {
+__device__ __forceinline__ float max32(const uint32_t (&r)[32], float m) {
     float a = m, b = -CUDART_INF_F;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-        if (!kMasked || i < n_valid) a = fmaxf(a, __uint_as_float(r[i]));
-        if (!kMasked || i + 1 < n_valid) b = fmaxf(b, __uint_as_float(r[i + 1]));
+        a = fmaxf(a, __uint_as_float(r[i]));
+        b = fmaxf(b, __uint_as_float(r[i + 1]));
     }
     return fmaxf(a, b);
+}
+// dot of 8 bf16 (one 16-byte chunk) with 8 floats
+__device__ __forceinline__ float dot8(const uint4& u, const float* q, float a) {
+    float2 f;
+    f = unpack_bf16x2(u.x); a = fmaf(q[0], f.x, a); a = fmaf(q[1], f.y, a);
+    f = unpack_bf16x2(u.y); a = fmaf(q[2], f.x, a); a = fmaf(q[3], f.y, a);
+    f = unpack_bf16x2(u.z); a = fmaf(q[4], f.x, a); a = fmaf(q[5], f.y, a);
+    f = unpack_bf16x2(u.w); a = fmaf(q[6], f.x, a); a = fmaf(q[7], f.y, a);
+    return a;
 }
 
 __global__ void __launch_bounds__(atc::THREADS, 1)
@@ -93,30 +97,31 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
     using namespace atc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    float* stats = reinterpret_cast<float*>(smem + STATS_OFF);  // [parity][max h0, max h1, sum h0, sum h1][128]
+    float* stats = reinterpret_cast<float*>(smem + STATS_OFF);
     float* clsbuf = reinterpret_cast<float*>(smem + CLS_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-    uint64_t* kv_full = bars;
-    uint64_t* kv_empty = bars + NUM_STAGES;
-    uint64_t* s_full = bars + 2 * NUM_STAGES;
-    uint64_t* sp_done = bars + 2 * NUM_STAGES + 1;  // [2]
-    uint64_t* o_full = bars + 2 * NUM_STAGES + 3;
-    uint64_t* o_free = bars + 2 * NUM_STAGES + 4;
+    uint64_t* kv_full = bars;        // [2] TMA -> everyone
+    uint64_t* kv_empty = bars + 2;   // [2] 1 (MMA commit) + 4 (CLS-query warps) + 8 (softmax warps, after their last epilogue)
+    uint64_t* s_full = bars + 4;     // [2] MMA -> softmax: S(g) complete in buffer g&1
+    uint64_t* sp_done = bars + 6;    // [2] softmax -> MMA: P(g) written (and S consumed)
+    uint64_t* o_full = bars + 8;     // [2] MMA -> softmax: O(g) complete
+    uint64_t* o_free = bars + 10;    // [2] softmax -> MMA: O(g) read out, buffer g&1 reusable
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int E = heads * 64;
     const int my_items = blockIdx.x < num_items ? (num_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int n_tiles = 2 * my_items;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); tma_prefetch_desc(&mapO);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NUM_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 5); }
-        mbar_init(s_full, 1);
-        mbar_init(&sp_done[0], 8); mbar_init(&sp_done[1], 8);
-        mbar_init(o_full, 1);
-        mbar_init(o_free, 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 13);
+            mbar_init(&s_full[i], 1); mbar_init(&sp_done[i], 8);
+            mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 8);
+        }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_ptr_smem);
@@ -132,177 +137,179 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
                 const int item = blockIdx.x + it * gridDim.x;
                 const int s = item / heads, h = item % heads;
                 const int st = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_wait(&kv_empty[st], ((it >> 1) & 1) ^ 1);
                 uint8_t* base = smem + st * STAGE_BYTES;
-                uint8_t* sK = base + 2 * Q_TILE_BYTES;
-                uint8_t* sV = sK + KV_BYTES;
                 mbar_arrive_expect_tx(&kv_full[st], STAGE_BYTES);
-                tma_load_3d(base, &map128, &kv_full[st], h * 64, 1, s);                   // Q tile 0: tokens 1..128
-                tma_load_3d(base + Q_TILE_BYTES, &map128, &kv_full[st], h * 64, 129, s);  // Q tile 1: tokens 129..256
-                tma_load_3d(sK, &map128, &kv_full[st], E + h * 64, 0, s);
-                tma_load_3d(sK + 16384, &map128, &kv_full[st], E + h * 64, 128, s);
-                tma_load_3d(sK + 32768, &map16, &kv_full[st], E + h * 64, 256, s);        // token 256 + 15 zero rows
-                tma_load_3d(sV, &map128, &kv_full[st], 2 * E + h * 64, 0, s);
-                tma_load_3d(sV + 16384, &map128, &kv_full[st], 2 * E + h * 64, 128, s);
-                tma_load_3d(sV + 32768, &map16, &kv_full[st], 2 * E + h * 64, 256, s);
+                tma_load_3d(base, &map128, &kv_full[st], h * 64, 1, s);                      // Q tile 0: tokens 1..128
+                tma_load_3d(base + Q_TILE_BYTES, &map128, &kv_full[st], h * 64, 129, s);     // Q tile 1: tokens 129..256
+                tma_load_3d(base + OFF_K, &map128, &kv_full[st], E + h * 64, 1, s);          // K tokens 1..128
+                tma_load_3d(base + OFF_K + 16384, &map128, &kv_full[st], E + h * 64, 129, s);
+                tma_load_3d(base + OFF_V, &map128, &kv_full[st], 2 * E + h * 64, 1, s);
+                tma_load_3d(base + OFF_V + 16384, &map128, &kv_full[st], 2 * E + h * 64, 129, s);
+                tma_load_3d(base + OFF_K0, &map16, &kv_full[st], E + h * 64, 0, s);          // row 0 = K of the CLS token
+                tma_load_3d(base + OFF_V0, &map16, &kv_full[st], 2 * E + h * 64, 0, s);
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc_s256 = umma_idesc_bf16_f32(128, 256);
-            constexpr uint32_t idesc_s16 = umma_idesc_bf16_f32(128, 16);
-            constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(128, 64) | (1u << 16);  // B (V) is MN-major
-            const int n_tiles = 2 * my_items;
-            auto issue_pv = [&](int g) {  // O = P(g) . V(item of g)
-                const int it = g >> 1;
-                const uint32_t v_addr = smem_u32(smem + (it & 1) * STAGE_BYTES + 2 * Q_TILE_BYTES + KV_BYTES);
-#pragma unroll 1
-                for (int j = 0; j < KEYS_PAD / 16; ++j)
-                    umma_bf16_ts(tmem_base + TM_O, tmem_base + TM_P + 8 * j,
-                                 umma_desc_sw128_mnmajor(v_addr + j * 2048, KV_BYTES), idesc_pv, j != 0 ? 1u : 0u);
-                umma_commit(o_full);
-                if (g & 1) umma_commit(&kv_empty[it & 1]);  // last tensor-core read of this stage
-            };
-            for (int g = 0; g < n_tiles; ++g) {
-                const int it = g >> 1, t = g & 1, st = it & 1;
-                if (t == 0) { mbar_wait(&kv_full[st], (it >> 1) & 1); tc_fence_after_sync(); }
-                if (g > 0) {  // S free and P(g-1) complete
-                    mbar_wait(&sp_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
-                    tc_fence_after_sync();
-                }
-                const uint32_t q_addr = smem_u32(smem + st * STAGE_BYTES + t * Q_TILE_BYTES);
-                const uint32_t k_addr = smem_u32(smem + st * STAGE_BYTES + 2 * Q_TILE_BYTES);
+        // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
+        constexpr uint32_t idesc_s = umma_idesc_bf16_f32(128, 256);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16_f32(128, 64) | (1u << 16);              // B (V) is MN-major
+        constexpr uint32_t kDescHiK = (1024u >> 4) | (1u << 14) | (2u << 29);                  // K-major SW128, SBO 1024
+        constexpr uint32_t kDescHiV = (1024u >> 4) | (1u << 14) | (2u << 29);                  // MN-major SW128: same fields
+        constexpr uint32_t kLboV = (static_cast<uint32_t>(KV_BYTES) >> 4) << 16;               // LBO (unused: N == 64)
+        const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFF) >> 4;
+        auto issue_pv = [&](int g) {  // O(g) = P(g) . V(item of g), into columns [64,128) of buffer g&1
+            const int it = g >> 1;
+            const uint32_t buf = tmem_base + static_cast<uint32_t>((g & 1) * 256);
+            const uint32_t v_lo = smem_lo + (((it & 1) * STAGE_BYTES + OFF_V) >> 4);
+            if (elect_one_sync()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t da = umma_desc_sw128_kmajor(q_addr + k * 32);
-                    umma_bf16_ss(tmem_base + TM_S, da, umma_desc_sw128_kmajor(k_addr + k * 32), idesc_s256, k != 0 ? 1u : 0u);
-                    umma_bf16_ss(tmem_base + TM_S + 256, da, umma_desc_sw128_kmajor(k_addr + 256 * 128 + k * 32), idesc_s16,
-                                 k != 0 ? 1u : 0u);
-                }
-                umma_commit(s_full);
-                if (g > 0) {
-                    if (g > 1) { mbar_wait(o_free, (g - 2) & 1); tc_fence_after_sync(); }
-                    issue_pv(g - 1);
-                }
+                for (int j = 0; j < 16; ++j)
+                    umma_bf16_ts(buf + 64, buf + (j < 8 ? 8 * j : 128 + 8 * (j - 8)),
+                                 make_desc((v_lo + j * (2048 >> 4)) | kLboV, kDescHiV), idesc_pv, j != 0 ? 1u : 0u);
+                umma_commit(&o_full[g & 1]);
+                if (g & 1) umma_commit(&kv_empty[it & 1]);  // last tensor-core read of this stage
             }
-            if (n_tiles > 0) {
-                const int g = n_tiles;  // drain: PV of the last tile
-                mbar_wait(&sp_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            __syncwarp();
+        };
+        for (int g = 0; g < n_tiles; ++g) {
+            const int it = g >> 1, t = g & 1, st = it & 1, b = g & 1;
+            if (t == 0) { mbar_wait(&kv_full[st], (it >> 1) & 1); tc_fence_after_sync(); }
+            if (g >= 2) { mbar_wait(&o_free[b], ((g - 2) >> 1) & 1); tc_fence_after_sync(); }   // O(g-2) read out
+            {
+                const uint32_t q_lo = smem_lo + ((st * STAGE_BYTES + t * Q_TILE_BYTES) >> 4);
+                const uint32_t k_lo = smem_lo + ((st * STAGE_BYTES + OFF_K) >> 4);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem_base + static_cast<uint32_t>(b * 256), make_desc(q_lo + 2 * k, kDescHiK),
+                                     make_desc(k_lo + 2 * k, kDescHiK), idesc_s, k != 0 ? 1u : 0u);
+                    umma_commit(&s_full[b]);
+                }
+                __syncwarp();
+            }
+            if (g > 0) {  // P(g-1) complete
+                mbar_wait(&sp_done[b ^ 1], ((g - 1) >> 1) & 1);
                 tc_fence_after_sync();
-                if (g > 1) { mbar_wait(o_free, (g - 2) & 1); tc_fence_after_sync(); }
                 issue_pv(g - 1);
             }
         }
-        __syncwarp();
+        if (n_tiles > 0) {
+            const int g = n_tiles;  // drain: PV of the last tile
+            mbar_wait(&sp_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            tc_fence_after_sync();
+            issue_pv(g - 1);
+        }
     } else if (warp >= 4 && warp < 12) {
         // ===================== softmax + O epilogue =====================
         const int e = warp - 4, q = e & 3, hf = e >> 2;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
-        const uint32_t ts = tmem_base + lane_base + TM_S + hf * 136;
-        const uint32_t tp = tmem_base + lane_base + TM_P + hf * 68;
-        const uint32_t to = tmem_base + lane_base + TM_O + hf * 32;
         const int row = q * 32 + lane;
-        const int n_tiles = 2 * my_items;
         uint8_t* ostg = smem + OSTG_OFF + e * 2048;  // 32 rows x 32 dims bf16
         uint4* ostg_row = reinterpret_cast<uint4*>(ostg + lane * 64);
-        const int last_valid = N_TOK - (136 + 96);  // valid columns in the last 32-chunk of half 1 (25)
 
-        // O(g) -> 1/l -> bf16 -> staging tile -> TMA store   (runs once PV(g) has completed)
+        // O(g) + p0 * v_cls -> 1/l -> bf16 -> staging tile -> TMA store   (runs once PV(g) has completed)
         auto epilogue = [&](int g) {
-            mbar_wait(o_full, g & 1);
-            mbar_wait(&sp_done[g & 1], (g >> 1) & 1);  // acquire the partner warp's row sums of tile g
+            const int b = g & 1, it = g >> 1;
+            mbar_wait(&o_full[b], (g >> 1) & 1);
             tc_fence_after_sync();
             uint32_t r[32];
-            tmem_ld_32x32b_x32(to, r);
+            tmem_ld_32x32b_x32(tmem_base + lane_base + static_cast<uint32_t>(b * 256 + 64 + hf * 32), r);
             tmem_ld_wait();
             tc_fence_before_sync();
-            const float* st_sum = stats + ((g & 1) * 4 + 2) * 128;
-            const float inv = 1.0f / (st_sum[row] + st_sum[128 + row]);
+            const float* st = stats + b * STATS_KINDS * 128;
+            const float inv = 1.0f / (st[2 * 128 + row] + st[3 * 128 + row]);
+            const float p0 = st[6 * 128 + row];
             __syncwarp();
-            if (lane == 0) { mbar_arrive(o_free); tma_store_wait_read<0>(); }
+            if (lane == 0) { mbar_arrive(&o_free[b]); tma_store_wait_read<0>(); }
             __syncwarp();
+            const uint8_t* v0 = smem + (it & 1) * STAGE_BYTES + OFF_V0 + hf * 64;  // V of the CLS token, dims hf*32..+31
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                const uint4 vv = *reinterpret_cast<const uint4*>(v0 + c * 16);  // token 0 -> row 0: chunks unswizzled
+                float2 f;
                 uint4 u;
-                u.x = pack_bf16x2(__uint_as_float(r[8 * c + 0]) * inv, __uint_as_float(r[8 * c + 1]) * inv);
-                u.y = pack_bf16x2(__uint_as_float(r[8 * c + 2]) * inv, __uint_as_float(r[8 * c + 3]) * inv);
-                u.z = pack_bf16x2(__uint_as_float(r[8 * c + 4]) * inv, __uint_as_float(r[8 * c + 5]) * inv);
-                u.w = pack_bf16x2(__uint_as_float(r[8 * c + 6]) * inv, __uint_as_float(r[8 * c + 7]) * inv);
+                f = unpack_bf16x2(vv.x);
+                u.x = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 0])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 1])) * inv);
+                f = unpack_bf16x2(vv.y);
+                u.y = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 2])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 3])) * inv);
+                f = unpack_bf16x2(vv.z);
+                u.z = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 4])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 5])) * inv);
+                f = unpack_bf16x2(vv.w);
+                u.w = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 6])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 7])) * inv);
                 ostg_row[c] = u;
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                const int item = blockIdx.x + (g >> 1) * gridDim.x;
+                if (g & 1) mbar_arrive(&kv_empty[it & 1]);  // V_cls of this stage is no longer needed by this warp
+                const int item = blockIdx.x + it * gridDim.x;
                 tma_store_3d(&mapO, ostg, (item % heads) * 64 + hf * 32, 1 + (g & 1) * 128 + q * 32, item / heads);
                 tma_store_commit();
             }
         };
 
         for (int g = 0; g < n_tiles; ++g) {
-            float* st_max = stats + ((g & 1) * 4 + 0) * 128;
-            float* st_sum = stats + ((g & 1) * 4 + 2) * 128;
-            mbar_wait(s_full, g & 1);
+            const int b = g & 1, it = g >> 1, t = g & 1, stg = it & 1;
+            float* st = stats + b * STATS_KINDS * 128;
+            const uint32_t ts = tmem_base + lane_base + static_cast<uint32_t>(b * 256 + hf * 128);  // S columns of this warp
+            const uint32_t tp = ts;                                                                  // P overwrites them in place
+            mbar_wait(&s_full[b], (g >> 1) & 1);
             tc_fence_after_sync();
             uint32_t ra[32], rb[32];
-            // ---- pass 1: row max over this warp's 136 columns; the next TMEM load is in flight while reducing ----
-            float m = -CUDART_INF_F;
-            tmem_ld_32x32b_x32(ts, ra); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 32, rb); m = max32<false>(ra, m, 32); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 64, ra); m = max32<false>(rb, m, 32); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 96, rb); m = max32<false>(ra, m, 32); tmem_ld_wait();
-            if (hf == 0) {
-                uint32_t r8[8];
-                tmem_ld_32x32b_x8(ts + 128, r8);
-                m = max32<false>(rb, m, 32);
-                tmem_ld_wait();
+            tmem_ld_32x32b_x32(ts, ra);
+            // ---- CLS key: partial dot q_row . k_cls over dims hf*32..+31 (CUDA cores, from the smem tiles) ----
+            float dot = 0.f;
+            {
+                const uint8_t* qrow = smem + stg * STAGE_BYTES + t * Q_TILE_BYTES + row * 128;
+                const uint8_t* k0 = smem + stg * STAGE_BYTES + OFF_K0 + hf * 64;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) m = fmaxf(m, __uint_as_float(r8[i]));
-            } else {
-                m = max32<true>(rb, m, last_valid);
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 kk = *reinterpret_cast<const uint4*>(k0 + c * 16);
+                    const uint4 qq = *reinterpret_cast<const uint4*>(qrow + (((hf * 4 + c) ^ (row & 7)) << 4));
+                    float kf[8];
+                    float2 f;
+                    f = unpack_bf16x2(kk.x); kf[0] = f.x; kf[1] = f.y;
+                    f = unpack_bf16x2(kk.y); kf[2] = f.x; kf[3] = f.y;
+                    f = unpack_bf16x2(kk.z); kf[4] = f.x; kf[5] = f.y;
+                    f = unpack_bf16x2(kk.w); kf[6] = f.x; kf[7] = f.y;
+                    dot = dot8(qq, kf, dot);
+                }
             }
-            st_max[hf * 128 + row] = m;
+            // ---- pass 1: row max over this warp's 128 columns; the next TMEM load is in flight while reducing ----
+            float m = -CUDART_INF_F;
+            tmem_ld_wait();
+            tmem_ld_32x32b_x32(ts + 32, rb); m = max32(ra, m); tmem_ld_wait();
+            tmem_ld_32x32b_x32(ts + 64, ra); m = max32(rb, m); tmem_ld_wait();
+            tmem_ld_32x32b_x32(ts + 96, rb); m = max32(ra, m); tmem_ld_wait();
+            m = max32(rb, m);
+            st[hf * 128 + row] = m;
+            st[(4 + hf) * 128 + row] = dot;
             named_bar_sync(2 + q, 64);  // the two column halves of this lane quadrant
-            m = fmaxf(m, st_max[(hf ^ 1) * 128 + row]);
+            const float s0 = dot + st[(4 + (hf ^ 1)) * 128 + row];  // score against the CLS key
+            m = fmaxf(fmaxf(m, st[(hf ^ 1) * 128 + row]), s0);
             const float mb = m * LOG2E;
-            // ---- previous tile: PV(g-1) has finished -> its P columns are free and its O can be stored ----
+            // ---- previous tile: PV(g-1) has finished -> store O(g-1), hand its buffer back to the MMA warp ----
             if (g > 0) epilogue(g - 1);
-            // ---- pass 2 ----
+            // ---- pass 2: P in place over S ----
             float sum = 0.f;
             uint32_t o[16];
             tmem_ld_32x32b_x32(ts, ra); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 32, rb); sum += softmax_math32<false>(ra, o, mb, 32); tmem_st_32x32b_x16(tp, o); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 64, ra); sum += softmax_math32<false>(rb, o, mb, 32); tmem_st_32x32b_x16(tp + 16, o); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 96, rb); sum += softmax_math32<false>(ra, o, mb, 32); tmem_st_32x32b_x16(tp + 32, o); tmem_ld_wait();
-            {
-                uint32_t o4[4] = {0u, 0u, 0u, 0u};
-                if (hf == 0) {
-                    uint32_t r8[8];
-                    tmem_ld_32x32b_x8(ts + 128, r8);
-                    sum += softmax_math32<false>(rb, o, mb, 32);
-                    tmem_st_32x32b_x16(tp + 48, o);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 8; i += 2) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(r8[i]), LOG2E, -mb));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(r8[i + 1]), LOG2E, -mb));
-                        o4[i >> 1] = pack_bf16x2(p0, p1);
-                        sum += p0 + p1;
-                    }
-                } else {
-                    sum += softmax_math32<true>(rb, o, mb, last_valid);
-                    tmem_st_32x32b_x16(tp + 48, o);
-                }
-                tmem_st_32x32b_x4(tp + 64, o4);  // half 1: keys 264..271 are padding -> P = 0
+            tmem_ld_32x32b_x32(ts + 32, rb); sum += softmax_math32(ra, o, mb); tmem_st_32x32b_x16(tp, o); tmem_ld_wait();
+            tmem_ld_32x32b_x32(ts + 64, ra); sum += softmax_math32(rb, o, mb); tmem_st_32x32b_x16(tp + 16, o); tmem_ld_wait();
+            tmem_ld_32x32b_x32(ts + 96, rb); sum += softmax_math32(ra, o, mb); tmem_st_32x32b_x16(tp + 32, o); tmem_ld_wait();
+            sum += softmax_math32(rb, o, mb); tmem_st_32x32b_x16(tp + 48, o);
+            if (hf == 0) {
+                const float p0 = ex2_approx(fmaf(s0, LOG2E, -mb));
+                st[6 * 128 + row] = p0;  // rank-1 term of the epilogue
+                sum += p0;
             }
-            st_sum[hf * 128 + row] = sum;
+            st[(2 + hf) * 128 + row] = sum;
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sp_done[g & 1]);
+            if (lane == 0) mbar_arrive(&sp_done[b]);
         }
         if (n_tiles > 0) epilogue(n_tiles - 1);
         if (lane == 0) tma_store_wait_all<0>();
@@ -311,15 +318,15 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
         // ===================== CLS query (token 0) on CUDA cores, decoupled from the tensor pipeline =====================
         const int q = warp - 12;
         const int te = threadIdx.x - 384;   // 0..127
-        float* pbuf = clsbuf;               // [272]
+        float* pbuf = clsbuf;               // [272]: p for keys token 1..256 at [0,256), CLS key at [256]
         float* red = clsbuf + 272;          // [16]
         float* part = clsbuf + 288;         // [4 key quarters][64 dims]
         for (int it = 0; it < my_items; ++it) {
             const int item = blockIdx.x + it * gridDim.x;
             const int s = item / heads, h = item % heads;
             const int st = it & 1;
-            const uint8_t* sK = smem + st * STAGE_BYTES + 2 * Q_TILE_BYTES;
-            const uint8_t* sV = sK + KV_BYTES;
+            const uint8_t* sK = smem + st * STAGE_BYTES + OFF_K;
+            const uint8_t* sV = smem + st * STAGE_BYTES + OFF_V;
             float qv[64];
             {
                 const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<int64_t>(s) * N_TOK) * 3 * E + h * 64);
@@ -334,8 +341,8 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
                 }
             }
             mbar_wait(&kv_full[st], (it >> 1) & 1);
-            // scores: keys te and te+128 together (independent chains), key 256 by thread 0
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            // scores: patch keys te and te+128 together (independent chains); the CLS key by thread 0
+            float a0 = 0.f, a1 = 0.f;
             {
                 const int j0 = te, j1 = te + 128;
                 const uint8_t* k0 = sK + j0 * 128;
@@ -344,71 +351,51 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
                 for (int c = 0; c < 8; ++c) {
                     const uint4 u = *reinterpret_cast<const uint4*>(k0 + ((c ^ (j0 & 7)) << 4));
                     const uint4 w = *reinterpret_cast<const uint4*>(k1 + ((c ^ (j1 & 7)) << 4));
-                    float2 f, g2;
-                    f = unpack_bf16x2(u.x); g2 = unpack_bf16x2(w.x);
-                    a0 = fmaf(qv[8 * c + 0], f.x, a0); a1 = fmaf(qv[8 * c + 1], f.y, a1);
-                    b0 = fmaf(qv[8 * c + 0], g2.x, b0); b1 = fmaf(qv[8 * c + 1], g2.y, b1);
-                    f = unpack_bf16x2(u.y); g2 = unpack_bf16x2(w.y);
-                    a0 = fmaf(qv[8 * c + 2], f.x, a0); a1 = fmaf(qv[8 * c + 3], f.y, a1);
-                    b0 = fmaf(qv[8 * c + 2], g2.x, b0); b1 = fmaf(qv[8 * c + 3], g2.y, b1);
-                    f = unpack_bf16x2(u.z); g2 = unpack_bf16x2(w.z);
-                    a0 = fmaf(qv[8 * c + 4], f.x, a0); a1 = fmaf(qv[8 * c + 5], f.y, a1);
-                    b0 = fmaf(qv[8 * c + 4], g2.x, b0); b1 = fmaf(qv[8 * c + 5], g2.y, b1);
-                    f = unpack_bf16x2(u.w); g2 = unpack_bf16x2(w.w);
-                    a0 = fmaf(qv[8 * c + 6], f.x, a0); a1 = fmaf(qv[8 * c + 7], f.y, a1);
-                    b0 = fmaf(qv[8 * c + 6], g2.x, b0); b1 = fmaf(qv[8 * c + 7], g2.y, b1);
+                    a0 = dot8(u, qv + 8 * c, a0);
+                    a1 = dot8(w, qv + 8 * c, a1);
                 }
             }
-            const float sc0 = a0 + a1, sc1 = b0 + b1;
-            float sc2 = -CUDART_INF_F;
+            float a2 = -CUDART_INF_F;
             if (te == 0) {
-                float c0 = 0.f, c1 = 0.f;
-                const uint8_t* k2 = sK + 256 * 128;  // 256 & 7 == 0: chunks unswizzled
+                const uint8_t* k2 = smem + st * STAGE_BYTES + OFF_K0;  // row 0: chunks unswizzled
+                float c0 = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(k2 + (c << 4));
-                    float2 f;
-                    f = unpack_bf16x2(u.x); c0 = fmaf(qv[8 * c + 0], f.x, c0); c1 = fmaf(qv[8 * c + 1], f.y, c1);
-                    f = unpack_bf16x2(u.y); c0 = fmaf(qv[8 * c + 2], f.x, c0); c1 = fmaf(qv[8 * c + 3], f.y, c1);
-                    f = unpack_bf16x2(u.z); c0 = fmaf(qv[8 * c + 4], f.x, c0); c1 = fmaf(qv[8 * c + 5], f.y, c1);
-                    f = unpack_bf16x2(u.w); c0 = fmaf(qv[8 * c + 6], f.x, c0); c1 = fmaf(qv[8 * c + 7], f.y, c1);
-                }
-                sc2 = c0 + c1;
+                for (int c = 0; c < 8; ++c) c0 = dot8(*reinterpret_cast<const uint4*>(k2 + (c << 4)), qv + 8 * c, c0);
+                a2 = c0;
             }
-            float lmax = fmaxf(fmaxf(sc0, sc1), sc2);
+            float lmax = fmaxf(fmaxf(a0, a1), a2);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
             if (lane == 0) red[q] = lmax;
             named_bar_sync(1, 128);
             const float mb = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * LOG2E;
-            const float p0 = ex2_approx(fmaf(sc0, LOG2E, -mb));
-            const float p1 = ex2_approx(fmaf(sc1, LOG2E, -mb));
+            const float p0 = ex2_approx(fmaf(a0, LOG2E, -mb));
+            const float p1 = ex2_approx(fmaf(a1, LOG2E, -mb));
             float lsum = p0 + p1;
             pbuf[te] = p0;
             pbuf[te + 128] = p1;
-            if (te == 0) { const float p2 = ex2_approx(fmaf(sc2, LOG2E, -mb)); pbuf[256] = p2; lsum += p2; }
+            if (te == 0) { const float p2 = ex2_approx(fmaf(a2, LOG2E, -mb)); pbuf[256] = p2; lsum += p2; }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
             if (lane == 0) red[4 + q] = lsum;
             named_bar_sync(1, 128);
             const float inv_cls = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
-            {   // o[d] = sum_j p_j v[j][d]: lane -> dims 2*lane, 2*lane+1; warp q -> keys j = q (mod 4)
+            {   // o[d] = sum_j p_j v[j][d]: lane -> dims 2*lane, 2*lane+1; warp q -> patch keys j = q (mod 4); CLS key by warp 0
                 const uint8_t* vbase = sV + (lane & 3) * 4;
                 const int dc = lane >> 2;
                 float x0 = 0.f, y0 = 0.f, x1 = 0.f, y1 = 0.f;
-                int j = q;
 #pragma unroll 4
-                for (; j + 4 < N_TOK; j += 8) {
+                for (int j = q; j < 256; j += 8) {
                     const float2 va = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + j * 128 + ((dc ^ (j & 7)) << 4)));
                     const float2 vb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + (j + 4) * 128 + ((dc ^ ((j + 4) & 7)) << 4)));
                     const float pa = pbuf[j], pb = pbuf[j + 4];
                     x0 = fmaf(pa, va.x, x0); y0 = fmaf(pa, va.y, y0);
                     x1 = fmaf(pb, vb.x, x1); y1 = fmaf(pb, vb.y, y1);
                 }
-                for (; j < N_TOK; j += 4) {
-                    const float2 va = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + j * 128 + ((dc ^ (j & 7)) << 4)));
-                    const float pa = pbuf[j];
-                    x0 = fmaf(pa, va.x, x0); y0 = fmaf(pa, va.y, y0);
+                if (q == 0) {
+                    const float2 vc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(smem + st * STAGE_BYTES + OFF_V0 + lane * 4));
+                    const float pc = pbuf[256];
+                    x0 = fmaf(pc, vc.x, x0); y0 = fmaf(pc, vc.y, y0);
                 }
                 part[q * 64 + 2 * lane] = x0 + x1;
                 part[q * 64 + 2 * lane + 1] = y0 + y1;
