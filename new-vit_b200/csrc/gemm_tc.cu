@@ -16,6 +16,7 @@
 // the L2->SM traffic per 128x192x384 tile from 240 KB to 96 KB, which is what bounds a K=384 GEMM here
 // (DESIGN.md "GEMM roofline").  Streaming mode (KCH == 0) rings both operands (fc2, K = 1536).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -84,14 +85,18 @@ int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, u
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
+// epilogue warps: 4 lane quadrants x (BN/64) column groups of 64 (two 32-column chunks per warp and tile)
+constexpr int epi_warps(int BN) { return 4 * (BN / 64); }
+constexpr int gemm_threads(int BN) { return 128 + epi_warps(BN) * 32; }
 constexpr int STG_TILE = 32 * 32 * 2;   // staging tile: 32 rows x 32 bf16
 
 
 template <int BN, int KCH, int STAGES, int NSTG>
 struct GemmSmem {
-    static constexpr int STG_BYTES = NSTG * STG_TILE;  // per warp; NSTG == 2: one TMA store in flight while the next tile fills
+    // per-warp staging: NSTG 1/2 = that many 32x32 tiles (one TMA store per 32-column chunk; 2: one store in flight while
+    // the next tile fills); NSTG 3 = the warp's whole 32 x BN/2 region (ONE async-proxy fence + ONE TMA store per tile)
+    static constexpr int EPI_WARPS = epi_warps(BN);
+    static constexpr int STG_BYTES = NSTG == 3 ? 32 * 64 * 2 : NSTG * STG_TILE;
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int B_BUFS = KCH > 0 ? KCH : STAGES;
     static constexpr int BIAS_FLOATS = KCH > 0 ? BN : 2048;  // resident: this CTA's n-block; streaming: the whole vector
@@ -195,14 +200,16 @@ __device__ __forceinline__ void store_block_32x32(uint8_t* stg, const uint32_t (
 }
 
 template <int BN, int KCH, int STAGES, int NSTG>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads(BN), 1)
 gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, const __grid_constant__ TmaDesc tmC,
-               int M, int N, int K, int mode, EpiParams ep) {
+               int M, int N, int K, int mode_flags, EpiParams ep) {
     using L = GemmSmem<BN, KCH, STAGES, NSTG>;
+    const int mode = mode_flags & 0xff;
     constexpr bool kResident = KCH > 0;
     constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
-    constexpr int CHUNKS_PER_WARP = BN / 64;  // each epilogue warp covers BN/2 columns in 32-column chunks
-    static_assert(2 * BN <= 512 && (CHUNKS_PER_WARP == 2 || CHUNKS_PER_WARP == 3), "tile shape");
+    constexpr int EPI_WARPS = L::EPI_WARPS;
+    constexpr int CHUNKS_PER_WARP = 2;  // each epilogue warp covers 64 columns in two 32-column chunks
+    static_assert(2 * BN <= 512 && BN % 64 == 0, "tile shape");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -323,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         // ===================== epilogue =====================
         const int e = warp - 4;
         const int q = e & 3;    // == warp % 4: the TMEM lane quadrant this warp may access
-        const int hf = e >> 2;  // column half
+        const int hf = e >> 2;  // column group (64 columns)
         uint8_t* stg = smem + L::STG_OFF + e * L::STG_BYTES;
         int stg_sel = 0;
         int acc = 0; uint32_t acc_phase = 0;
@@ -334,7 +341,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             const int row0 = m_blk * BM + q * 32;
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < M;
-            const int col0 = hf * (BN / 2);                       // first column of this warp inside the tile
+            const int col0 = hf * 64;                             // first column of this warp inside the tile
             const int nbase = n_blk * BN + col0;                  // ... and in the output
             const float* bias0 = bias_cached ? sBias + (kResident ? col0 : nbase) : (mode == EPI_PATCH ? nullptr : ep.bias + nbase);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
@@ -358,11 +365,30 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
 #pragma unroll
                         for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     }
+                } else if (NSTG == 3) {
+                    // whole-region staging: rows of BN bytes; the previous tile's store must have read the buffer
+                    if (c == 0) {
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        *reinterpret_cast<uint4*>(stg + lane * 128 + (((c * 4 + i) ^ (lane & 7)) << 4)) =
+                            make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    if (c == CHUNKS_PER_WARP - 1) {
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && !(mode_flags & 0x200)) {
+                            if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, stg, nbase, row0);
+                            else tma_store_2d(&tmC, stg, nbase, row0);
+                            tma_store_commit();
+                        }
+                    }
                 } else {
                     // the tile written two stores ago must no longer be read by its TMA store
                     uint8_t* tile = stg + stg_sel * STG_TILE;
                     if (NSTG == 2) stg_sel ^= 1;
-                    if (lane == 0) tma_store_wait_read<NSTG - 1>();
+                    if (lane == 0) tma_store_wait_read<(NSTG == 2 ? 1 : 0)>();
                     __syncwarp();
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -385,22 +411,18 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after_sync();
+            if (mode_flags & 0x100) {  // experiment: mainloop ceiling (no epilogue work at all)
+                release_tmem();
+                acc ^= 1; if (acc == 0) acc_phase ^= 1;
+                continue;
+            }
             uint32_t ra[32], rb[32];
             tmem_ld_32x32b_x32(taddr, ra);
+            tmem_ld_32x32b_x32(taddr + 32, rb);
             tmem_ld_wait();
-            tmem_ld_32x32b_x32(taddr + 32, rb);  // in flight while chunk 0 is processed
+            release_tmem();  // the accumulator stage goes back to the MMA warp before any epilogue math
             process(ra, 0);
-            tmem_ld_wait();
-            if (CHUNKS_PER_WARP == 2) {
-                release_tmem();
-                process(rb, 1);
-            } else {
-                tmem_ld_32x32b_x32(taddr + 64, ra);
-                process(rb, 1);
-                tmem_ld_wait();
-                release_tmem();
-                process(ra, 2);
-            }
+            process(rb, 1);
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
         if (lane == 0) tma_store_wait_all<0>();  // all output bytes are in global memory before the CTA retires
@@ -439,7 +461,7 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     } else {
         grid = m_tiles * n_tiles < num_sms ? m_tiles * n_tiles : num_sms;
     }
-    kern<<<grid, GEMM_THREADS, L::DYN_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, mode, ep);
+    kern<<<grid, gemm_threads(BN), L::DYN_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, mode, ep);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -454,19 +476,25 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) mode = EPI_BIAS_ACCUM;
     TmaDesc tmA, tmB, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
-    // output map (unused by EPI_PATCH, whose rows are re-mapped): 32x32 boxes, 64B swizzle (conflict-free staging writes)
+    // output maps (unused by EPI_PATCH, whose rows are re-mapped)
     const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1) : static_cast<uint64_t>(M);
-    MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
-    if (N % 192 == 0) {
+    static const int force_bn = getenv("MST_GEMM_BN") ? atoi(getenv("MST_GEMM_BN")) : 0;  // experiments only
+    static const int skip_epi = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;
+    if (skip_epi) mode |= skip_epi << 8;  // 1: no epilogue at all, 2: epilogue without the final store
+    if (N % 192 == 0 && force_bn != 128) {
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
-        // GELU epilogue (fc1) is the longest: give it two staging tiles per warp and a 3-deep A ring instead
-        if (K == 384 && mode == EPI_BIAS_GELU) return launch_cfg<192, 6, 3, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-        if (K == 384) return launch_cfg<192, 6, 4, 1>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-        if (K == 256) return launch_cfg<192, 4, 4, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-        return launch_cfg<192, 0, 5, 1>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        if (K == 256) {  // patch embedding: weight-resident, chunk staging (its epilogue stores rows directly)
+            MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+            return launch_cfg<192, 4, 4, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        }
+        // both operands stream through a 4-stage ring; the shared memory a resident weight slab would take goes to
+        // whole-region epilogue staging (one fence + one 32x96 TMA store per warp and tile)
+        MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 64, 32, true, false));
+        return launch_cfg<192, 0, 4, 3>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
     }
     MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 128));
-    return launch_cfg<128, 0, 5, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+    MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 64, 32, true, false));
+    return launch_cfg<128, 0, 5, 3>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
 }
 
 }  // namespace mst
