@@ -30,13 +30,23 @@ class _Mlp(nn.Module):
         self.fc2 = nn.Linear(4 * E, E)
 
 
-class _Block(nn.Module):
+class _LayerScale(nn.Module):
     def __init__(self, E):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(E))
+
+
+class _Block(nn.Module):
+    def __init__(self, E, layerscale=False):
         super().__init__()
         self.norm1 = nn.LayerNorm(E, eps=1e-6)
         self.attn = _Attn(E)
+        if layerscale:
+            self.ls1 = _LayerScale(E)
         self.norm2 = nn.LayerNorm(E, eps=1e-6)
         self.mlp = _Mlp(E)
+        if layerscale:
+            self.ls2 = _LayerScale(E)
 
 
 class _PatchEmbed(nn.Module):
@@ -46,9 +56,10 @@ class _PatchEmbed(nn.Module):
 
 
 class _Encoder(nn.Module):
-    """Key layout of DinoVisionTransformer built by vit_small/base (block_chunks=1 => blocks.0.<i>)."""
+    """Key layout of DinoVisionTransformer: local factory (block_chunks=1 => blocks.0.<i>, no LayerScale) or, with
+    hub_layout, the torch.hub checkpoints' (blocks.<i>, ls1/ls2.gamma)."""
 
-    def __init__(self, E, depth, heads, pos_tokens):
+    def __init__(self, E, depth, heads, pos_tokens, hub_layout=False):
         super().__init__()
         self.num_features = self.embed_dim = E
         self.num_heads = heads
@@ -56,7 +67,11 @@ class _Encoder(nn.Module):
         self.pos_embed = nn.Parameter(torch.zeros(1, pos_tokens, E))
         self.mask_token = nn.Parameter(torch.zeros(1, E))
         self.patch_embed = _PatchEmbed(E)
-        self.blocks = nn.ModuleList([nn.ModuleList([_Block(E) for _ in range(depth)])])
+        self.depth = depth
+        if hub_layout:
+            self.blocks = nn.ModuleList([_Block(E, layerscale=True) for _ in range(depth)])
+        else:
+            self.blocks = nn.ModuleList([nn.ModuleList([_Block(E) for _ in range(depth)])])
         self.norm = nn.LayerNorm(E, eps=1e-6)
 
 
@@ -84,7 +99,7 @@ class DinoV2ClassifierSlice(nn.Module):
                  rotary_positional_encoding=None, optimizer_kwargs={'lr': 1e-6, 'weight_decay': 1e-2},
                  model_size='s', use_registers=False, use_bottleneck=False, use_slice_pos_emb=False,
                  enable_linear=True, enable_trans=True, slice_fusion='transformer', freeze=False,
-                 precision='bf16', img_size=224, **kwargs):
+                 precision='bf16', img_size=224, hub_layout=False, **kwargs):
         super().__init__()
         if pretrained:
             raise NotImplementedError(
@@ -111,14 +126,14 @@ class DinoV2ClassifierSlice(nn.Module):
         self.precision = precision
         self.model_size = model_size
         pos_tokens = 1 + (img_size // 14) ** 2
-        self.encoder = _Encoder(E, depth, heads, pos_tokens)
+        self.encoder = _Encoder(E, depth, heads, pos_tokens, hub_layout=hub_layout)
         self.emb_ch = E
         self.slice_fusion = _SliceFusion(E, synth.SLICE_HEADS)
         self.cls_token = nn.Parameter(torch.zeros(1, 1, E))
         self.linear = nn.Linear(E, out_ch)
         # reference init distributions, drawn from the global torch RNG
         sd = synth.make_state_dict(model_size, out_ch, seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()),
-                                   img_size=img_size)
+                                   img_size=img_size, layerscale=hub_layout, chunked_names=not hub_layout)
         nn.Module.load_state_dict(self, sd, strict=True)
         if freeze:
             for p in self.encoder.parameters():
@@ -165,7 +180,7 @@ class DinoV2ClassifierSlice(nn.Module):
         key = (dev.index or 0, self.precision, self.encoder.pos_embed.shape[1])
         if self._handle is None or self._handle_key != key:
             self._release()
-            cfg = _cabi.MstConfig(E, len(self.encoder.blocks[0]), self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
+            cfg = _cabi.MstConfig(E, self.encoder.depth, self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
                                   self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0])
             h = _cabi.ctypes.c_void_p()
             _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))

@@ -229,3 +229,31 @@ def bilinear14_reference(coarse, H, W):
     v10 = coarse[..., y1, :][..., x0]; v11 = coarse[..., y1, :][..., x1]
     out = (1 - ly) * ((1 - lx) * v00 + lx * v01) + ly * ((1 - lx) * v10 + lx * v11)
     return out
+
+
+def run_pred(sd, source, src_key_padding_mask=None, use_softmax=True, use_tta=False):
+    """scripts/main_predict.py:133-164 (`run_pred` with `_pred_trans`, save_attn=True), generalised to a batch:
+    softmax of the logits, head-mean saliency map reshaped to [B,1,D,g,g], slice weights broadcast to the source
+    shape, optional 8-flip TTA (the un-flipped padding mask is passed to every flip, as the script does), and the
+    trilinear upsample AFTER the TTA average (:161-162).  Returns (pred, weight [B,1,D,H,W], weight_slice)."""
+    B, _, D, H, W = source.shape
+
+    def pred_trans(x):
+        r = forward(sd, x, src_key_padding_mask)
+        pred = torch.softmax(r["logits"], dim=-1) if use_softmax else r["logits"]
+        w = get_attention_maps(r["plane_cls"], r["slice_cls"]).mean(dim=1)
+        g = int(w.shape[-1] ** 0.5)
+        w = w.reshape(B, 1, D, g, g)
+        ws = get_slice_attention(r["slice_cls"]).mean(dim=1).reshape(B, 1, D, 1, 1) * torch.ones_like(x)
+        return pred, w, ws
+
+    pred, weight, weight_slice = pred_trans(source)
+    if use_tta:
+        for flip_dim in [(2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)]:
+            p_i, w_i, ws_i = pred_trans(torch.flip(source, flip_dim))
+            pred = pred + p_i
+            weight = weight + torch.flip(w_i, flip_dim)
+            weight_slice = weight_slice + torch.flip(ws_i, flip_dim)
+        pred, weight, weight_slice = pred / 8, weight / 8, weight_slice / 8
+    weight = F.interpolate(weight, size=(D, H, W), mode="trilinear")
+    return pred, weight, weight_slice

@@ -102,9 +102,16 @@ def load_reference_class():
     return DinoV2ClassifierSlice
 
 
-def build_reference_model(state_dict=None, out_ch=2, model_size="s", **kw):
+def build_reference_model(state_dict=None, out_ch=2, model_size="s", hub_layout=False, **kw):
+    """`hub_layout=True` swaps in the encoder configuration of the torch.hub DINOv2 checkpoints that
+    `pretrained=True` would download (dino.py:59-63): LayerScale (init_values=1.0) and un-chunked block names
+    (block_chunks=0), built from the reference's own vendored factory (vision_transformer.py:340-352)."""
     Cls = load_reference_class()
     model = Cls(in_ch=1, out_ch=out_ch, pretrained=False, model_size=model_size, **kw).eval()
+    if hub_layout:
+        from mst.models.extern.dinov2 import vision_transformer as vits
+        factory = {"s": vits.vit_small, "b": vits.vit_base, "l": vits.vit_large}[model_size]
+        model.encoder = factory(patch_size=14, img_size=224, init_values=1.0, block_chunks=0, num_register_tokens=0).eval()
     if state_dict is not None:
         pe = state_dict["encoder.pos_embed"]
         if tuple(pe.shape) != tuple(model.encoder.pos_embed.shape):

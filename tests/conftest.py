@@ -24,8 +24,9 @@ def load_golden(name):
 
 def case_inputs(meta, out_ch=2):
     from new_vit_b200 import synth
+    hub = bool(meta.get("hub_layout", False))
     sd = synth.make_state_dict(meta["size"], out_ch=out_ch, seed=meta["wseed"], variant=meta["variant"],
-                               img_size=meta["H"])
+                               img_size=meta["H"], layerscale=hub, chunked_names=not hub)
     x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
     mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"]) if meta["masked"] else None
     return sd, x, mask

@@ -34,13 +34,17 @@ CASES = {
     "s_peaky_small_mask_b3": ("s", "peaky", 3, 7, 112, 112, True, 3, 3),
     # config 4 of BASELINE.json: ViT-B/14 encoder at 252x252 (256x256 is rejected by the reference, patch_embed.py:72-73)
     "b_peaky_252_mask_b2": ("b", "peaky", 2, 3, 252, 252, True, 4, 4),
+    # hub-checkpoint layout: LayerScale gammas + "encoder.blocks.<i>" key names
+    "s_hub_layerscale_b1": ("s", "peaky", 1, 4, 224, 224, False, 5, 5, {"hub_layout": True}),
 }
 
 
 def run_case(name):
-    size, variant, B, D, H, W, masked, wseed, vseed = CASES[name]
-    sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=H)
-    model = build_reference_model(sd, out_ch=2, model_size=size)
+    size, variant, B, D, H, W, masked, wseed, vseed = CASES[name][:9]
+    flags = CASES[name][9] if len(CASES[name]) > 9 else {}
+    hub = bool(flags.get("hub_layout", False))
+    sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=H, layerscale=hub, chunked_names=not hub)
+    model = build_reference_model(sd, out_ch=2, model_size=size, hub_layout=hub)
     x = synth.make_volume(B, D, H, W, seed=vseed)
     mask = synth.make_padding_mask(B, D, seed=vseed) if masked else None
     out = {}
@@ -70,7 +74,7 @@ def run_case(name):
             if b == 0:
                 out["sal_sum_b0"] = w.double().sum().float().reshape(1)
         out["sal_sub"] = torch.stack(subs)
-    meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed)
+    meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed, hub_layout=hub)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
                         meta=np.array(repr(meta)), **{k: v.numpy() for k, v in out.items()})
     print(name, "logits", out["logits"].tolist())

@@ -12,12 +12,14 @@ from conftest import case_inputs, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2"]
+GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2",
+           "s_hub_layerscale_b1"]
 
 
-def _model(sd, precision, img_size, size="s"):
+def _model(sd, precision, img_size, size="s", hub_layout=False):
     from new_vit_b200 import DinoV2ClassifierSlice
-    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=precision, img_size=img_size, model_size=size).cuda().eval()
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=precision, img_size=img_size, model_size=size,
+                              hub_layout=hub_layout).cuda().eval()
     m.load_state_dict(sd)
     return m
 
@@ -45,7 +47,7 @@ def _run(m, x, mask):
 def test_fp32_matches_reference_golden(name):
     meta, g = load_golden(name)
     sd, x, mask = case_inputs(meta)
-    r = _run(_model(sd, "fp32", meta["H"], meta["size"]), x, mask)
+    r = _run(_model(sd, "fp32", meta["H"], meta["size"], meta.get("hub_layout", False)), x, mask)
     B = meta["B"]
     scale = g["logits"].abs().max().item()
     assert (r["logits"] - g["logits"]).abs().max().item() <= 1e-4 * max(scale, 1.0), (r["logits"], g["logits"])
@@ -68,7 +70,7 @@ def test_fp32_matches_reference_golden(name):
 def test_bf16_matches_reference_golden(name):
     meta, g = load_golden(name)
     sd, x, mask = case_inputs(meta)
-    r = _run(_model(sd, "bf16", meta["H"], meta["size"]), x, mask)
+    r = _run(_model(sd, "bf16", meta["H"], meta["size"], meta.get("hub_layout", False)), x, mask)
     B = meta["B"]
     err = (r["logits"] - g["logits"]).abs().max().item()
     assert err <= 2e-2, f"bf16 logits differ by {err}: {r['logits']} vs {g['logits']}"
@@ -148,6 +150,27 @@ def test_pipelined_host_input_is_bit_identical():
         y2 = m(x, save_attn=True, src_key_padding_mask=mask).cpu()  # buffers reused on the second call
     assert torch.equal(y0, y1) and torch.equal(y0, y2)
     assert torch.equal(maps0, maps1)
+
+
+@pytest.mark.parametrize("use_tta", [False, True])
+def test_run_pred_matches_script_semantics(use_tta):
+    """run_pred (scripts/main_predict.py:133-164): softmax, saliency volume, slice weights, 8-flip TTA.  Our version
+    upsamples each flip before averaging (the x14 bilinear upsample commutes with flips and averaging)."""
+    from new_vit_b200 import synth
+    from new_vit_b200.model import run_pred
+    from oracle import mst_oracle as O
+    B, D, H, W = 2, 4, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=31, variant="peaky")
+    x = synth.make_volume(B, D, H, W, seed=32)
+    mask = synth.make_padding_mask(B, D, seed=0)
+    rp, rw, rws = O.run_pred(sd, x, mask, use_tta=use_tta)
+    m = _model(sd, "fp32", H)
+    p, w, ws = run_pred(m, {"source": x, "src_key_padding_mask": mask}, save_attn=True, use_tta=use_tta)
+    torch.testing.assert_close(p.cpu(), rp, rtol=1e-4, atol=1e-5)
+    assert w.shape == rw.shape == (B, 1, D, H, W) and ws.shape == rws.shape
+    torch.testing.assert_close(w.cpu(), rw, rtol=5e-4, atol=float(rw.max()) * 1e-5)
+    torch.testing.assert_close(ws.cpu(), rws, rtol=5e-4, atol=1e-8)
+    assert torch.equal(w.cpu().reshape(B, -1).argmax(-1), rw.reshape(B, -1).argmax(-1))
 
 
 def test_errors_mirror_reference():

@@ -7,7 +7,7 @@ from conftest import case_inputs, load_golden
 from oracle import mst_oracle as O
 from oracle import ref_harness
 
-SMALL = ["s_init_small", "s_peaky_small_mask_b3"]
+SMALL = ["s_init_small", "s_peaky_small_mask_b3", "s_hub_layerscale_b1"]
 FULL = ["s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2"]
 
 
