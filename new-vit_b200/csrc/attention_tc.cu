@@ -119,8 +119,8 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 13);
-            mbar_init(&s_full[i], 1); mbar_init(&sp_done[i], 8);
-            mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 8);
+            mbar_init(&s_full[i], 1); mbar_init(&sp_done[i], 4);
+            mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
         }
         fence_barrier_init();
     }
@@ -159,14 +159,14 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
         constexpr uint32_t kDescHiV = (1024u >> 4) | (1u << 14) | (2u << 29);                  // MN-major SW128: same fields
         constexpr uint32_t kLboV = (static_cast<uint32_t>(KV_BYTES) >> 4) << 16;               // LBO (unused: N == 64)
         const uint32_t smem_lo = (smem_u32(smem) & 0x3FFFF) >> 4;
-        auto issue_pv = [&](int g) {  // O(g) = P(g) . V(item of g), into columns [64,128) of buffer g&1
+        auto issue_pv = [&](int g) {  // O(g) = P(g) . V(item of g): P in columns [0,128), O into [128,192) of buffer g&1
             const int it = g >> 1;
             const uint32_t buf = tmem_base + static_cast<uint32_t>((g & 1) * 256);
             const uint32_t v_lo = smem_lo + (((it & 1) * STAGE_BYTES + OFF_V) >> 4);
             if (elect_one_sync()) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
-                    umma_bf16_ts(buf + 64, buf + (j < 8 ? 8 * j : 128 + 8 * (j - 8)),
+                    umma_bf16_ts(buf + 128, buf + 8 * j,
                                  make_desc((v_lo + j * (2048 >> 4)) | kLboV, kDescHiV), idesc_pv, j != 0 ? 1u : 0u);
                 umma_commit(&o_full[g & 1]);
                 if (g & 1) umma_commit(&kv_empty[it & 1]);  // last tensor-core read of this stage
@@ -202,118 +202,103 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
             issue_pv(g - 1);
         }
     } else if (warp >= 4 && warp < 12) {
-        // ===================== softmax + O epilogue =====================
-        const int e = warp - 4, q = e & 3, hf = e >> 2;
+        // ===================== softmax + O epilogue: two teams of four warps =====================
+        // Team tm owns the tiles g = tm (mod 2), i.e. TMEM buffer tm; warp (q, tm) owns rows q*32.. of its tile, all 256
+        // score columns.  The two warps that share an SM sub-partition belong to different teams and are half a period
+        // out of phase, so the MUFU-heavy pass 2 of one overlaps the ALU / wait phases of the other.
+        const int e = warp - 4, q = e & 3, tm = e >> 2;
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+        const uint32_t buf = tmem_base + lane_base + static_cast<uint32_t>(tm * 256);
         const int row = q * 32 + lane;
-        uint8_t* ostg = smem + OSTG_OFF + e * 2048;  // 32 rows x 32 dims bf16
-        uint4* ostg_row = reinterpret_cast<uint4*>(ostg + lane * 64);
-
-        // O(g) + p0 * v_cls -> 1/l -> bf16 -> staging tile -> TMA store   (runs once PV(g) has completed)
-        auto epilogue = [&](int g) {
-            const int b = g & 1, it = g >> 1;
-            mbar_wait(&o_full[b], (g >> 1) & 1);
-            tc_fence_after_sync();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_base + static_cast<uint32_t>(b * 256 + 64 + hf * 32), r);
-            tmem_ld_wait();
-            tc_fence_before_sync();
-            const float* st = stats + b * STATS_KINDS * 128;
-            const float inv = 1.0f / (st[2 * 128 + row] + st[3 * 128 + row]);
-            const float p0 = st[6 * 128 + row];
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&o_free[b]); tma_store_wait_read<0>(); }
-            __syncwarp();
-            const uint8_t* v0 = smem + (it & 1) * STAGE_BYTES + OFF_V0 + hf * 64;  // V of the CLS token, dims hf*32..+31
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 vv = *reinterpret_cast<const uint4*>(v0 + c * 16);  // token 0 -> row 0: chunks unswizzled
-                float2 f;
-                uint4 u;
-                f = unpack_bf16x2(vv.x);
-                u.x = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 0])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 1])) * inv);
-                f = unpack_bf16x2(vv.y);
-                u.y = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 2])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 3])) * inv);
-                f = unpack_bf16x2(vv.z);
-                u.z = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 4])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 5])) * inv);
-                f = unpack_bf16x2(vv.w);
-                u.w = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[8 * c + 6])) * inv, fmaf(p0, f.y, __uint_as_float(r[8 * c + 7])) * inv);
-                ostg_row[c] = u;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-                if (g & 1) mbar_arrive(&kv_empty[it & 1]);  // V_cls of this stage is no longer needed by this warp
-                const int item = blockIdx.x + it * gridDim.x;
-                tma_store_3d(&mapO, ostg, (item % heads) * 64 + hf * 32, 1 + (g & 1) * 128 + q * 32, item / heads);
-                tma_store_commit();
-            }
-        };
-
-        for (int g = 0; g < n_tiles; ++g) {
-            const int b = g & 1, it = g >> 1, t = g & 1, stg = it & 1;
-            float* st = stats + b * STATS_KINDS * 128;
-            const uint32_t ts = tmem_base + lane_base + static_cast<uint32_t>(b * 256 + hf * 128);  // S columns of this warp
-            const uint32_t tp = ts;                                                                  // P overwrites them in place
-            mbar_wait(&s_full[b], (g >> 1) & 1);
+        for (int g = tm; g < n_tiles; g += 2) {
+            const int it = g >> 1, stg = it & 1;
+            const uint32_t par = static_cast<uint32_t>(it & 1);
+            mbar_wait(&s_full[tm], par);
             tc_fence_after_sync();
             uint32_t ra[32], rb[32];
-            tmem_ld_32x32b_x32(ts, ra);
-            // ---- CLS key: partial dot q_row . k_cls over dims hf*32..+31 (CUDA cores, from the smem tiles) ----
-            float dot = 0.f;
+            tmem_ld_32x32b_x32(buf, ra);
+            // ---- CLS key: s0 = q_row . k_cls (CUDA cores, from the smem tiles) ----
+            float s0 = 0.f;
             {
-                const uint8_t* qrow = smem + stg * STAGE_BYTES + t * Q_TILE_BYTES + row * 128;
-                const uint8_t* k0 = smem + stg * STAGE_BYTES + OFF_K0 + hf * 64;
+                const uint8_t* qrow = smem + stg * STAGE_BYTES + tm * Q_TILE_BYTES + row * 128;
+                const uint8_t* k0 = smem + stg * STAGE_BYTES + OFF_K0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < 8; ++c) {
                     const uint4 kk = *reinterpret_cast<const uint4*>(k0 + c * 16);
-                    const uint4 qq = *reinterpret_cast<const uint4*>(qrow + (((hf * 4 + c) ^ (row & 7)) << 4));
+                    const uint4 qq = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
                     float kf[8];
                     float2 f;
                     f = unpack_bf16x2(kk.x); kf[0] = f.x; kf[1] = f.y;
                     f = unpack_bf16x2(kk.y); kf[2] = f.x; kf[3] = f.y;
                     f = unpack_bf16x2(kk.z); kf[4] = f.x; kf[5] = f.y;
                     f = unpack_bf16x2(kk.w); kf[6] = f.x; kf[7] = f.y;
-                    dot = dot8(qq, kf, dot);
+                    s0 = dot8(qq, kf, s0);
                 }
             }
-            // ---- pass 1: row max over this warp's 128 columns; the next TMEM load is in flight while reducing ----
-            float m = -CUDART_INF_F;
+            // ---- pass 1: row max over 256 columns; the next TMEM load is in flight while reducing ----
+            float m = s0;
             tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 32, rb); m = max32(ra, m); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 64, ra); m = max32(rb, m); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 96, rb); m = max32(ra, m); tmem_ld_wait();
-            m = max32(rb, m);
-            st[hf * 128 + row] = m;
-            st[(4 + hf) * 128 + row] = dot;
-            named_bar_sync(2 + q, 64);  // the two column halves of this lane quadrant
-            const float s0 = dot + st[(4 + (hf ^ 1)) * 128 + row];  // score against the CLS key
-            m = fmaxf(fmaxf(m, st[(hf ^ 1) * 128 + row]), s0);
-            const float mb = m * LOG2E;
-            // ---- previous tile: PV(g-1) has finished -> store O(g-1), hand its buffer back to the MMA warp ----
-            if (g > 0) epilogue(g - 1);
-            // ---- pass 2: P in place over S ----
-            float sum = 0.f;
-            uint32_t o[16];
-            tmem_ld_32x32b_x32(ts, ra); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 32, rb); sum += softmax_math32(ra, o, mb); tmem_st_32x32b_x16(tp, o); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 64, ra); sum += softmax_math32(rb, o, mb); tmem_st_32x32b_x16(tp + 16, o); tmem_ld_wait();
-            tmem_ld_32x32b_x32(ts + 96, rb); sum += softmax_math32(ra, o, mb); tmem_st_32x32b_x16(tp + 32, o); tmem_ld_wait();
-            sum += softmax_math32(rb, o, mb); tmem_st_32x32b_x16(tp + 48, o);
-            if (hf == 0) {
-                const float p0 = ex2_approx(fmaf(s0, LOG2E, -mb));
-                st[6 * 128 + row] = p0;  // rank-1 term of the epilogue
-                sum += p0;
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_32x32b_x32(buf + (c + 1) * 32, rb); m = max32(ra, m); tmem_ld_wait();
+                if (c + 2 < 8) tmem_ld_32x32b_x32(buf + (c + 2) * 32, ra);
+                m = max32(rb, m);
+                if (c + 2 < 8) tmem_ld_wait();
             }
-            st[(2 + hf) * 128 + row] = sum;
+            const float mb = m * LOG2E;
+            // ---- pass 2: P (bf16 pairs) in place over S: chunk c (columns 32c..) -> columns 16c.. ----
+            float sum = ex2_approx(fmaf(s0, LOG2E, -mb));
+            const float p0 = sum;  // probability of the CLS key: rank-1 term of the epilogue
+            uint32_t o[16];
+            tmem_ld_32x32b_x32(buf, ra); tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                tmem_ld_32x32b_x32(buf + (c + 1) * 32, rb);
+                sum += softmax_math32(ra, o, mb); tmem_st_32x32b_x16(buf + c * 16, o);
+                tmem_ld_wait();
+                if (c + 2 < 8) tmem_ld_32x32b_x32(buf + (c + 2) * 32, ra);
+                sum += softmax_math32(rb, o, mb); tmem_st_32x32b_x16(buf + (c + 1) * 16, o);
+                if (c + 2 < 8) tmem_ld_wait();
+            }
             tmem_st_wait();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sp_done[b]);
+            if (lane == 0) mbar_arrive(&sp_done[tm]);
+            // ---- epilogue of the same tile: O (columns 128..191) + p0 * v_cls, 1/l, bf16, 128-byte row stores ----
+            const float inv = 1.0f / sum;
+            mbar_wait(&o_full[tm], par);
+            tc_fence_after_sync();
+            tmem_ld_32x32b_x32(buf + 128, ra);
+            tmem_ld_32x32b_x32(buf + 160, rb);
+            tmem_ld_wait();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&o_free[tm]);
+            {
+                const int item = blockIdx.x + it * gridDim.x;
+                const int s = item / heads, h = item % heads;
+                const uint8_t* v0 = smem + stg * STAGE_BYTES + OFF_V0;  // V of the CLS token: row 0, chunks unswizzled
+                uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(s) * N_TOK + 1 + tm * 128 + row) * E + h * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* r = c < 4 ? &ra[8 * c] : &rb[8 * (c - 4)];
+                    const uint4 vv = *reinterpret_cast<const uint4*>(v0 + c * 16);
+                    float2 f;
+                    uint4 u;
+                    f = unpack_bf16x2(vv.x);
+                    u.x = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[0])) * inv, fmaf(p0, f.y, __uint_as_float(r[1])) * inv);
+                    f = unpack_bf16x2(vv.y);
+                    u.y = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[2])) * inv, fmaf(p0, f.y, __uint_as_float(r[3])) * inv);
+                    f = unpack_bf16x2(vv.z);
+                    u.z = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[4])) * inv, fmaf(p0, f.y, __uint_as_float(r[5])) * inv);
+                    f = unpack_bf16x2(vv.w);
+                    u.w = pack_bf16x2(fmaf(p0, f.x, __uint_as_float(r[6])) * inv, fmaf(p0, f.y, __uint_as_float(r[7])) * inv);
+                    dst[c] = u;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&kv_empty[stg]);  // Q rows / K_cls / V_cls of this stage are no longer needed
         }
-        if (n_tiles > 0) epilogue(n_tiles - 1);
-        if (lane == 0) tma_store_wait_all<0>();
-        __syncwarp();
     } else if (warp >= 12) {
         // ===================== CLS query (token 0) on CUDA cores, decoupled from the tensor pipeline =====================
         const int q = warp - 12;
