@@ -103,6 +103,9 @@ MST_API int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32
  * warp-MMA kernel otherwise; _bf16_warp_mma always runs the latter. */
 MST_API int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_attention_bf16_warp_mma(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
+/* profiling aid: cycles one softmax warp of CTA 0 spends per phase (7 x int64: wait S, pass 1, pair barrier, pass 2,
+ * wait O, epilogue, tiles) */
+MST_API int mst_debug_attention_timing(const void* qkv, void* out, int32_t BD, int32_t heads, long long* dbg_dev, void* stream);
 MST_API int mst_kernel_attention_f32(const float* qkv, float* out, int32_t BD, int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t E,
                               float eps, void* stream);

@@ -56,6 +56,7 @@ def lib():
     L.mst_kernel_gemm_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_attention_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_attention_bf16_warp_mma.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.mst_debug_attention_timing.argtypes = [vp, vp, i32, i32, vp, vp]
     L.mst_kernel_attention_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_layernorm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
     L.mst_profile_begin.argtypes = [vp]

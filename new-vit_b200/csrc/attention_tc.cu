@@ -10,14 +10,20 @@
 // overwritten in place by P (bf16 pairs, columns [0,64) and [128,192)) and receives O in the columns [64,128) that
 // P does not use.  While the softmax warps work on tile g the tensor pipe computes S(g+1) and O(g-1).
 //
-//   warp 0      TMA producer: per item Q0,Q1 (128x64), K, V (tokens 1..256) and 16-row boxes holding K/V of token 0,
-//               2-stage ring (100 KB per stage, 128B swizzle)
-//   warp 1      MMA issuer (warp-convergent, one elected lane):
-//                 S = Q K^T   SS, M128 N256 K16 x 4        O = P V   TS (A = P from TMEM), V MN-major, N64 K16 x 16
-//   warp 2      TMEM allocator
-//   warps 4-11  softmax + O epilogue: warp (quadrant q = w%4, half hf) owns 32 rows x 128 score columns
-//   warps 12-15 CLS query on CUDA cores
-// The kernel is bound by the exponentials (MUFU: 2*128*256 per item at 16/clk/SM), not by the tensor pipe.
+//   warp 0       TMA producer: per item Q0,Q1 (128x64), K, V (tokens 1..256) and 16-row boxes holding K/V of token 0,
+//                2-stage ring (100 KB per stage, 128B swizzle)
+//   warp 1       MMA issuer (warp-convergent, one elected lane):
+//                  S = Q K^T   SS, M128 N256 K16 x 4        O = P V   TS (A = P from TMEM), V MN-major, N64 K16 x 16
+//   warps 4-11   softmax + O epilogue in two teams of four (team = tile parity = TMEM buffer); warp (q, team) owns rows
+//                q*32.. of its tile and all 256 score columns: pass 1 row max, pass 2 p = 2^(s*log2e - m*log2e) written
+//                as bf16 pairs IN PLACE over S (columns [0,128)), O lands in columns [128,192); row statistics stay in
+//                registers; the epilogue adds p_cls * v_cls, scales by 1/l and stores 128-byte rows.  The two warps that
+//                share an SM sub-partition belong to different teams and run half a period out of phase.
+//   warps 2,3,12-15  CLS query with warp-level MMA (mma.sync) from the same smem tiles, two groups of three warps on
+//                alternate items, partial (max, sum, O) merged through smem.  (A single warp needed 21k cycles per
+//                item -- long mma.sync dependency chains on a busy sub-partition -- and gated the stage release.)
+// Measured (profiles/attn_timing.py, clock64 per phase of one softmax warp, config-2 shape): wait S 0.5k, CLS-key dot +
+// pass 1 1.4k, pass 2 4.0k (MUFU, shared with the other team), wait O 1.7k, epilogue 2.0k cycles per tile.
 #include <math_constants.h>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -90,15 +96,16 @@ __device__ __forceinline__ float dot8(const uint4& u, const float* q, float a) {
     return a;
 }
 
+// phase timing of one softmax warp of block 0 (dbg != nullptr only in profiles/attn_timing.py)
+#define ATT_T(i) do { if (dbg_on) { const long long _t = clock64(); dbg_acc[i] += _t - dbg_t; dbg_t = _t; } } while (0)
+
 __global__ void __launch_bounds__(atc::THREADS, 1)
 attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_constant__ TmaDesc map16,
                        const __grid_constant__ TmaDesc mapO, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                       int num_items, int heads) {
+                       int num_items, int heads, long long* __restrict__ dbg) {
     using namespace atc;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    float* stats = reinterpret_cast<float*>(smem + STATS_OFF);
-    float* clsbuf = reinterpret_cast<float*>(smem + CLS_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
     uint64_t* kv_full = bars;        // [2] TMA -> everyone
     uint64_t* kv_empty = bars + 2;   // [2] 1 (MMA commit) + 4 (CLS-query warps) + 8 (softmax warps, after their last epilogue)
@@ -118,7 +125,7 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 13);
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 12);  // MMA commit + 8 softmax warps + 3 CLS warps
             mbar_init(&s_full[i], 1); mbar_init(&sp_done[i], 4);
             mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
         }
@@ -210,10 +217,14 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
         const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
         const uint32_t buf = tmem_base + lane_base + static_cast<uint32_t>(tm * 256);
         const int row = q * 32 + lane;
+        const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
+        long long dbg_acc[6] = {0, 0, 0, 0, 0, 0};
+        long long dbg_t = clock64();
         for (int g = tm; g < n_tiles; g += 2) {
             const int it = g >> 1, stg = it & 1;
             const uint32_t par = static_cast<uint32_t>(it & 1);
             mbar_wait(&s_full[tm], par);
+            ATT_T(0);  // waiting for S
             tc_fence_after_sync();
             uint32_t ra[32], rb[32];
             tmem_ld_32x32b_x32(buf, ra);
@@ -246,6 +257,7 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
                 if (c + 2 < 8) tmem_ld_wait();
             }
             const float mb = m * LOG2E;
+            ATT_T(1);  // CLS-key dot + pass 1
             // ---- pass 2: P (bf16 pairs) in place over S: chunk c (columns 32c..) -> columns 16c.. ----
             float sum = ex2_approx(fmaf(s0, LOG2E, -mb));
             const float p0 = sum;  // probability of the CLS key: rank-1 term of the epilogue
@@ -264,9 +276,11 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sp_done[tm]);
+            ATT_T(3);  // pass 2
             // ---- epilogue of the same tile: O (columns 128..191) + p0 * v_cls, 1/l, bf16, 128-byte row stores ----
             const float inv = 1.0f / sum;
             mbar_wait(&o_full[tm], par);
+            ATT_T(4);  // waiting for O
             tc_fence_after_sync();
             tmem_ld_32x32b_x32(buf + 128, ra);
             tmem_ld_32x32b_x32(buf + 160, rb);
@@ -298,99 +312,133 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&kv_empty[stg]);  // Q rows / K_cls / V_cls of this stage are no longer needed
+            ATT_T(5);  // epilogue
         }
-    } else if (warp >= 12) {
-        // ===================== CLS query (token 0) on CUDA cores, decoupled from the tensor pipeline =====================
-        const int q = warp - 12;
-        const int te = threadIdx.x - 384;   // 0..127
-        float* pbuf = clsbuf;               // [272]: p for keys token 1..256 at [0,256), CLS key at [256]
-        float* red = clsbuf + 272;          // [16]
-        float* part = clsbuf + 288;         // [4 key quarters][64 dims]
-        for (int it = 0; it < my_items; ++it) {
+        if (dbg_on) { for (int i = 0; i < 6; ++i) dbg[i] = dbg_acc[i]; dbg[6] = n_tiles; }
+    } else {
+        // ===================== CLS query (token 0): warp-level MMA from the same smem tiles =====================
+        // Six warps in two groups of three (group A = warps 2,12,13 takes even items, group B = 3,14,15 odd items).  The
+        // CLS query is the only valid row of a 16-row mma.sync block; keys = 8 chunks of 32 patch keys + one chunk holding
+        // the CLS key (row 0 of the K0/V0 boxes).  Member i of a group runs the chunks i, i+3, i+6 with an online softmax
+        // in registers; the three partial (max, sum, O) triples are merged through shared memory.  A single warp needs
+        // ~21k cycles per item (long mma.sync dependency chains on a busy sub-partition) and was the kernel's bottleneck.
+        const int grp = (warp == 2 || warp == 12 || warp == 13) ? 0 : 1;
+        const int mem = (warp == 2 || warp == 3) ? 0 : ((warp == 12 || warp == 14) ? 1 : 2);
+        const int gq = lane >> 2, tq = lane & 3;
+        float* merge = reinterpret_cast<float*>(smem + CLS_OFF) + grp * 3 * 68;  // per member: m, l, pad, pad, o[64]
+        for (int it = grp; it < my_items; it += 2) {
             const int item = blockIdx.x + it * gridDim.x;
             const int s = item / heads, h = item % heads;
             const int st = it & 1;
-            const uint8_t* sK = smem + st * STAGE_BYTES + OFF_K;
-            const uint8_t* sV = smem + st * STAGE_BYTES + OFF_V;
-            float qv[64];
+            const uint32_t sK_u = smem_u32(smem + st * STAGE_BYTES + OFF_K), sV_u = smem_u32(smem + st * STAGE_BYTES + OFF_V);
+            const uint32_t sK0_u = smem_u32(smem + st * STAGE_BYTES + OFF_K0), sV0_u = smem_u32(smem + st * STAGE_BYTES + OFF_V0);
+            uint32_t qa[4][4];
             {
-                const uint4* qp = reinterpret_cast<const uint4*>(qkv + (static_cast<int64_t>(s) * N_TOK) * 3 * E + h * 64);
+                const uint32_t* q0 = reinterpret_cast<const uint32_t*>(qkv + (static_cast<int64_t>(s) * N_TOK) * 3 * E + h * 64);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint4 u = __ldg(qp + i);
-                    float2 f;
-                    f = unpack_bf16x2(u.x); qv[8 * i + 0] = f.x; qv[8 * i + 1] = f.y;
-                    f = unpack_bf16x2(u.y); qv[8 * i + 2] = f.x; qv[8 * i + 3] = f.y;
-                    f = unpack_bf16x2(u.z); qv[8 * i + 4] = f.x; qv[8 * i + 5] = f.y;
-                    f = unpack_bf16x2(u.w); qv[8 * i + 6] = f.x; qv[8 * i + 7] = f.y;
+                for (int ks = 0; ks < 4; ++ks) {
+                    qa[ks][0] = gq == 0 ? __ldg(q0 + ks * 8 + tq) : 0u;
+                    qa[ks][1] = 0u;
+                    qa[ks][2] = gq == 0 ? __ldg(q0 + ks * 8 + 4 + tq) : 0u;
+                    qa[ks][3] = 0u;
                 }
             }
+            float oacc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f; }
+            float m0 = -CUDART_INF_F, l0 = 0.f;
             mbar_wait(&kv_full[st], (it >> 1) & 1);
-            // scores: patch keys te and te+128 together (independent chains); the CLS key by thread 0
-            float a0 = 0.f, a1 = 0.f;
-            {
-                const int j0 = te, j1 = te + 128;
-                const uint8_t* k0 = sK + j0 * 128;
-                const uint8_t* k1 = sK + j1 * 128;
+#pragma unroll 1
+            for (int ci = mem; ci < 9; ci += 3) {  // chunks 0..7: 32 patch keys each; chunk 8: the CLS key block
+                const bool cls_chunk = ci == 8;
+                const uint32_t kb = cls_chunk ? sK0_u : sK_u + ci * 32 * 128;
+                const uint32_t vb = cls_chunk ? sV0_u : sV_u + ci * 32 * 128;
+                const int nblk = cls_chunk ? 1 : 4;
+                float sacc[4][4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(k0 + ((c ^ (j0 & 7)) << 4));
-                    const uint4 w = *reinterpret_cast<const uint4*>(k1 + ((c ^ (j1 & 7)) << 4));
-                    a0 = dot8(u, qv + 8 * c, a0);
-                    a1 = dot8(w, qv + 8 * c, a1);
+                for (int nb = 0; nb < 4; ++nb) {
+                    sacc[nb][0] = sacc[nb][1] = sacc[nb][2] = sacc[nb][3] = 0.f;
+                    if (nb < nblk) {
+                        const int key = nb * 8 + (lane & 7);  // row inside the chunk's tile; (row & 7) == (key & 7)
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int c = half * 4 + (lane >> 3);
+                            uint32_t bfr[4];
+                            ldmatrix_x4(bfr, kb + key * 128 + ((c ^ (key & 7)) << 4));
+                            mma_bf16_16816(sacc[nb], qa[2 * half], bfr[0], bfr[1]);
+                            mma_bf16_16816(sacc[nb], qa[2 * half + 1], bfr[2], bfr[3]);
+                        }
+                    }
                 }
-            }
-            float a2 = -CUDART_INF_F;
-            if (te == 0) {
-                const uint8_t* k2 = smem + st * STAGE_BYTES + OFF_K0;  // row 0: chunks unswizzled
-                float c0 = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) c0 = dot8(*reinterpret_cast<const uint4*>(k2 + (c << 4)), qv + 8 * c, c0);
-                a2 = c0;
-            }
-            float lmax = fmaxf(fmaxf(a0, a1), a2);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
-            if (lane == 0) red[q] = lmax;
-            named_bar_sync(1, 128);
-            const float mb = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) * LOG2E;
-            const float p0 = ex2_approx(fmaf(a0, LOG2E, -mb));
-            const float p1 = ex2_approx(fmaf(a1, LOG2E, -mb));
-            float lsum = p0 + p1;
-            pbuf[te] = p0;
-            pbuf[te + 128] = p1;
-            if (te == 0) { const float p2 = ex2_approx(fmaf(a2, LOG2E, -mb)); pbuf[256] = p2; lsum += p2; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-            if (lane == 0) red[4 + q] = lsum;
-            named_bar_sync(1, 128);
-            const float inv_cls = 1.0f / ((red[4] + red[5]) + (red[6] + red[7]));
-            {   // o[d] = sum_j p_j v[j][d]: lane -> dims 2*lane, 2*lane+1; warp q -> patch keys j = q (mod 4); CLS key by warp 0
-                const uint8_t* vbase = sV + (lane & 3) * 4;
-                const int dc = lane >> 2;
-                float x0 = 0.f, y0 = 0.f, x1 = 0.f, y1 = 0.f;
-#pragma unroll 4
-                for (int j = q; j < 256; j += 8) {
-                    const float2 va = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + j * 128 + ((dc ^ (j & 7)) << 4)));
-                    const float2 vb = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vbase + (j + 4) * 128 + ((dc ^ ((j + 4) & 7)) << 4)));
-                    const float pa = pbuf[j], pb = pbuf[j + 4];
-                    x0 = fmaf(pa, va.x, x0); y0 = fmaf(pa, va.y, y0);
-                    x1 = fmaf(pb, vb.x, x1); y1 = fmaf(pb, vb.y, y1);
+                if (cls_chunk) {  // only key 0 of the box is the CLS token; rows 1..7 are other tokens
+                    if (tq != 0) sacc[0][0] = -CUDART_INF_F;
+                    sacc[0][1] = -CUDART_INF_F;
                 }
-                if (q == 0) {
-                    const float2 vc = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(smem + st * STAGE_BYTES + OFF_V0 + lane * 4));
-                    const float pc = pbuf[256];
-                    x0 = fmaf(pc, vc.x, x0); y0 = fmaf(pc, vc.y, y0);
+                float cm = -CUDART_INF_F;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb)
+                    if (nb < nblk) cm = fmaxf(cm, fmaxf(sacc[nb][0], sacc[nb][1]));
+                cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+                cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+                const float mn = fmaxf(m0, cm);
+                const float sc = ex2_approx((m0 - mn) * LOG2E);
+                m0 = mn;
+                const float ms = mn * LOG2E;
+                float rs = 0.f;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    if (nb < nblk) {
+                        sacc[nb][0] = ex2_approx(fmaf(sacc[nb][0], LOG2E, -ms));
+                        sacc[nb][1] = ex2_approx(fmaf(sacc[nb][1], LOG2E, -ms));
+                        rs += sacc[nb][0] + sacc[nb][1];
+                    }
+                    sacc[nb][2] = 0.f; sacc[nb][3] = 0.f;  // rows 8..15 of the block do not exist
                 }
-                part[q * 64 + 2 * lane] = x0 + x1;
-                part[q * 64 + 2 * lane + 1] = y0 + y1;
+                l0 = fmaf(l0, sc, rs);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { oacc[i][0] *= sc; oacc[i][1] *= sc; }
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    if (2 * kk < nblk) {
+                        uint32_t pa[4];
+                        pa[0] = pack_bf16x2(sacc[2 * kk][0], sacc[2 * kk][1]);
+                        pa[1] = 0u;
+                        pa[2] = pack_bf16x2(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1]);
+                        pa[3] = 0u;
+                        const int key = kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                        for (int dn = 0; dn < 8; dn += 2) {
+                            const int c = dn + (lane >> 4);
+                            uint32_t bfr[4];
+                            ldmatrix_x4_trans(bfr, vb + key * 128 + ((c ^ (key & 7)) << 4));
+                            mma_bf16_16816(oacc[dn], pa, bfr[0], bfr[1]);
+                            mma_bf16_16816(oacc[dn + 1], pa, bfr[2], bfr[3]);
+                        }
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&kv_empty[st]);  // this warp no longer reads the stage
-            named_bar_sync(1, 128);
-            if (te < 64)
-                out[(static_cast<int64_t>(s) * N_TOK) * E + h * 64 + te] =
-                    __float2bfloat16_rn(((part[te] + part[64 + te]) + (part[128 + te] + part[192 + te])) * inv_cls);
+            // ---- merge the three members' partials (row 0 lives in lanes 0..3: dims dn*8 + 2*tq, +1) ----
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            float* mine = merge + mem * 68;
+            if (gq == 0) {
+                if (tq == 0) { mine[0] = m0; mine[1] = l0; }
+#pragma unroll
+                for (int dn = 0; dn < 8; ++dn) { mine[4 + dn * 8 + 2 * tq] = oacc[dn][0]; mine[4 + dn * 8 + 2 * tq + 1] = oacc[dn][1]; }
+            }
+            named_bar_sync(1 + grp, 96);
+            if (mem == 0) {
+                const float ma = merge[0], mb2 = merge[68], mc = merge[136];
+                const float mm = fmaxf(ma, fmaxf(mb2, mc));
+                const float wa = ex2_approx((ma - mm) * LOG2E), wb = ex2_approx((mb2 - mm) * LOG2E), wc = ex2_approx((mc - mm) * LOG2E);
+                const float inv = 1.0f / (merge[1] * wa + merge[69] * wb + merge[137] * wc);
+                const float o0 = (merge[4 + 2 * lane] * wa + merge[72 + 2 * lane] * wb + merge[140 + 2 * lane] * wc) * inv;
+                const float o1 = (merge[5 + 2 * lane] * wa + merge[73 + 2 * lane] * wb + merge[141 + 2 * lane] * wc) * inv;
+                reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(s) * N_TOK) * E + h * 64)[lane] = pack_bf16x2(o0, o1);
+            }
+            named_bar_sync(1 + grp, 96);  // the merge buffer may be overwritten by the next item
         }
     }
 
@@ -402,7 +450,7 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
     }
 }
 
-int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream) {
+int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream, long long* dbg) {
     using namespace atc;
     const int E = heads * 64;
     TmaDesc m128, m16, mO;
@@ -416,7 +464,7 @@ int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int nu
     }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
-    attention_tc257_kernel<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads);
+    attention_tc257_kernel<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -102,7 +102,8 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t ro
 int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                      uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128);
 // tcgen05 attention for N == 257 tokens (ViT-S/B @224); other N use the warp-MMA kernel
-int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream);
+int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
+                           long long* dbg = nullptr);
 
 // bf16 tensor-core GEMM (tcgen05 + TMA + TMEM). A: [M,K] bf16 row-major (lda=K), W: [N,K] bf16 row-major.
 int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
