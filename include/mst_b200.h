@@ -97,6 +97,10 @@ MST_API int mst_profile_end(mst_handle h, double* ms, int64_t* launches, int32_t
  * mode: 0 bias, 1 bias+GELU(erf), 2 bias+residual.  A [M,K], W [N,K] (nn.Linear layout), out/res [M,N]. */
 MST_API int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode,
                          const float* bias, const void* res, void* out, void* stream);
+/* profiling aid: same as mst_kernel_gemm_bf16, plus cycle counters of CTA 0 (8 x int64: MMA warp wait-for-accumulator,
+ * wait-for-operands, total, tiles; epilogue warp 0 wait-for-MMA, TMEM read, math+store) */
+MST_API int mst_debug_gemm_timing(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode,
+                          const float* bias, const void* res, void* out, long long* dbg_dev, void* stream);
 MST_API int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, int32_t K, int32_t mode,
                         const float* bias, const float* res, float* out, void* stream);
 /* qkv [BD*N, 3*heads*64] (q pre-scaled) -> out [BD*N, heads*64].  _bf16 picks the tcgen05 kernel for N == 257 and the

@@ -53,6 +53,7 @@ def lib():
     L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     L.mst_saliency.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mst_kernel_gemm_bf16.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.mst_debug_gemm_timing.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mst_kernel_gemm_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_attention_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_attention_bf16_warp_mma.argtypes = [vp, vp, i32, i32, i32, vp]

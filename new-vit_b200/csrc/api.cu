@@ -539,6 +539,14 @@ int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_t N, int
     return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, num_sms_current(),
                         static_cast<cudaStream_t>(stream));
 }
+int mst_debug_gemm_timing(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode, const float* bias,
+                          const void* res, void* out, long long* dbg_dev, void* stream) {
+    MST_REQUIRE(A && W && out && bias && dbg_dev && mode >= 0 && mode <= 2, "mst_debug_gemm_timing: bad argument");
+    EpiParams ep{};
+    ep.bias = bias; ep.res = res; ep.ldr = N; ep.out = out; ep.ldo = N; ep.dbg = dbg_dev;
+    return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, num_sms_current(),
+                        static_cast<cudaStream_t>(stream));
+}
 int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, int32_t K, int32_t mode, const float* bias,
                         const float* res, float* out, void* stream) {
     MST_REQUIRE(A && W && out && bias && mode >= 0 && mode <= 2, "mst_kernel_gemm_f32: bad argument");

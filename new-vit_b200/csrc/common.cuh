@@ -52,6 +52,7 @@ struct EpiParams {
     int P;               // patches per slice (EPI_PATCH)
     void* out;           // output, dtype T
     int64_t ldo;         // output row stride in elements
+    long long* dbg;      // nullable: phase cycle counters of CTA 0 (profiles/gemm_timing.py)
 };
 
 // erf via the rational minimax on [-4,4] (max abs error 3.8e-7 in fp32; checked against math.erf).

@@ -304,12 +304,18 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         if (kResident && t_count > 0) { mbar_wait(bfull_bar, 0); tc_fence_after_sync(); }
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
+        long long gd[2] = {0, 0};
+        const long long gstart = clock64();
         for (int it = 0; it < t_count; ++it) {
+            const long long g0 = clock64();
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            gd[0] += clock64() - g0;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
             for (int kc = 0; kc < kchunks; ++kc) {
+                const long long g1 = clock64();
                 mbar_wait(&full_bar[stage], phase);
+                gd[1] += clock64() - g1;
                 tc_fence_after_sync();
                 const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
                 const uint32_t b_lo = b_lo0 + (kResident ? kc : stage) * (L::B_TILE_BYTES >> 4);
@@ -325,6 +331,9 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
+        }
+        if (ep.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+            ep.dbg[0] = gd[0]; ep.dbg[1] = gd[1]; ep.dbg[2] = clock64() - gstart; ep.dbg[3] = t_count;
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -409,7 +418,9 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             };
 
+            const long long e0 = clock64();
             mbar_wait(&tfull_bar[acc], acc_phase);
+            const long long e1 = clock64();
             tc_fence_after_sync();
             if (mode_flags & 0x100) {  // experiment: mainloop ceiling (no epilogue work at all)
                 release_tmem();
@@ -421,8 +432,13 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             tmem_ld_32x32b_x32(taddr + 32, rb);
             tmem_ld_wait();
             release_tmem();  // the accumulator stage goes back to the MMA warp before any epilogue math
+            const long long e2 = clock64();
             process(ra, 0);
             process(rb, 1);
+            if (ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0) {
+                const long long e3 = clock64();
+                ep.dbg[4] += e1 - e0; ep.dbg[5] += e2 - e1; ep.dbg[6] += e3 - e2;
+            }
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
         if (lane == 0) tma_store_wait_all<0>();  // all output bytes are in global memory before the CTA retires
