@@ -85,17 +85,17 @@ int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, u
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-// epilogue warps: 4 lane quadrants x (BN/64) column groups of 64 (two 32-column chunks per warp and tile)
-constexpr int epi_warps(int BN) { return 4 * (BN / 64); }
-constexpr int gemm_threads(int BN) { return 128 + epi_warps(BN) * 32; }
+// epilogue warps EW (8 or 12): 4 lane quadrants x EW/4 column groups of BN/(EW/4) columns each
+constexpr int gemm_threads(int EW) { return 128 + EW * 32; }
 constexpr int STG_TILE = 32 * 32 * 2;   // staging tile: 32 rows x 32 bf16
 
 
-template <int BN, int KCH, int STAGES, int NSTG>
+template <int BN, int KCH, int STAGES, int NSTG, int EW>
 struct GemmSmem {
     // per-warp staging: NSTG 1/2 = that many 32x32 tiles (one TMA store per 32-column chunk; 2: one store in flight while
     // the next tile fills); NSTG 3 = the warp's whole 32 x BN/2 region (ONE async-proxy fence + ONE TMA store per tile)
-    static constexpr int EPI_WARPS = epi_warps(BN);
+    static constexpr int EPI_WARPS = EW;
+    static_assert(NSTG != 3 || BN / (EW / 4) == 64, "whole-region staging needs 64-column groups");
     static constexpr int STG_BYTES = NSTG == 3 ? 32 * 64 * 2 : NSTG * STG_TILE;
     static constexpr int B_TILE_BYTES = BN * BK * 2;
     static constexpr int B_BUFS = KCH > 0 ? KCH : STAGES;
@@ -199,17 +199,23 @@ __device__ __forceinline__ void store_block_32x32(uint8_t* stg, const uint32_t (
     __syncwarp();
 }
 
-template <int BN, int KCH, int STAGES, int NSTG>
-__global__ void __launch_bounds__(gemm_threads(BN), 1)
+template <int BN, int KCH, int STAGES, int NSTG, int EW, bool MCAST>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, const __grid_constant__ TmaDesc tmC,
                int M, int N, int K, int mode_flags, EpiParams ep) {
-    using L = GemmSmem<BN, KCH, STAGES, NSTG>;
+    using L = GemmSmem<BN, KCH, STAGES, NSTG, EW>;
     const int mode = mode_flags & 0xff;
     constexpr bool kResident = KCH > 0;
     constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
     constexpr int EPI_WARPS = L::EPI_WARPS;
-    constexpr int CHUNKS_PER_WARP = 2;  // each epilogue warp covers 64 columns in two 32-column chunks
-    static_assert(2 * BN <= 512 && BN % 64 == 0, "tile shape");
+    constexpr int COLS_PER_WARP = BN / (EW / 4);
+    constexpr int CHUNKS_PER_WARP = COLS_PER_WARP / 32;  // 32-column chunks per epilogue warp and tile
+    static_assert(2 * BN <= 512 && (CHUNKS_PER_WARP == 2 || CHUNKS_PER_WARP == 3), "tile shape");
+    static_assert(!MCAST || KCH > 0, "multicast is wired for the weight-resident schedule");
+    // MCAST: the CTA pair (2j, 2j+1) of a cluster walks the same m-blocks with adjacent n-blocks; each CTA fetches half
+    // of every A stage and TMA-multicasts it to both, halving the bytes each SM must keep in flight per tile.
+    const uint32_t cta_rank = MCAST ? cluster_ctarank() : 0;
+    constexpr int kPrefetchTiles = 2;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -250,7 +256,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], MCAST ? 2 : 1); }
         mbar_init(bfull_bar, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
         fence_barrier_init();
@@ -264,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         for (int i = threadIdx.x - 128; i < cnt; i += EPI_WARPS * 32) sBias[i] = __ldg(src + i);
     }
     tc_fence_before_sync();
-    __syncthreads();
+    if (MCAST) cluster_sync_all(); else __syncthreads();  // peers' barriers must be initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -281,10 +287,23 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 const int t = t_first + it * t_step;
                 const int m_blk = kResident ? t : t / n_tiles;
                 const int n_blk = kResident ? n_fixed : t % n_tiles;
+                // (streaming mode: prefetching there made fc2 13 % slower -- every CTA of an m-block row would issue the same
+                //  prefetches -- so it is limited to the resident schedule, where one cluster per m-group issues them)
+                if (kResident && n_fixed < (MCAST ? 2 : 1) && it + kPrefetchTiles < t_count) {
+                    // pull the A rows of a later tile into L2 now: under load a TMA load that misses L2 takes ~3000 clk,
+                    // far more than the 4 x 384 clk of MMA work the operand ring can cover (profiles/gemm_timing.py)
+                    const int m_pf = t + kPrefetchTiles * t_step;
+                    for (int kc = 0; kc < kchunks; ++kc)
+                        tma_prefetch_l2_2d(&tmA, kc * BK, m_pf * BM + (MCAST ? static_cast<int>(cta_rank) * (BM / 2) : 0));
+                }
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + (kResident ? 0 : L::B_TILE_BYTES));
-                    tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, m_blk * BM);
+                    if (MCAST)
+                        tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + cta_rank * (A_STAGE_BYTES / 2), &tmA, &full_bar[stage],
+                                              kc * BK, m_blk * BM + static_cast<int>(cta_rank) * (BM / 2), 0x3);
+                    else
+                        tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, m_blk * BM);
                     if (!kResident)
                         tma_load_2d(sB + stage * L::B_TILE_BYTES, &tmB, &full_bar[stage], kc * BK, n_blk * BN);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -324,7 +343,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     for (int k = 0; k < BK / 16; ++k)
                         umma_bf16_ss(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
                                      (kc | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (MCAST) umma_commit_multicast(&empty_bar[stage], 0x3);  // both CTAs refill this slot
+                    else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                     if (kc == kchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                 }
                 __syncwarp();
@@ -350,7 +370,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             const int row0 = m_blk * BM + q * 32;
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < M;
-            const int col0 = hf * 64;                             // first column of this warp inside the tile
+            const int col0 = hf * COLS_PER_WARP;                  // first column of this warp inside the tile
             const int nbase = n_blk * BN + col0;                  // ... and in the output
             const float* bias0 = bias_cached ? sBias + (kResident ? col0 : nbase) : (mode == EPI_PATCH ? nullptr : ep.bias + nbase);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
@@ -427,14 +447,16 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
                 continue;
             }
-            uint32_t ra[32], rb[32];
+            uint32_t ra[32], rb[32], rc[CHUNKS_PER_WARP == 3 ? 32 : 1];
             tmem_ld_32x32b_x32(taddr, ra);
             tmem_ld_32x32b_x32(taddr + 32, rb);
+            if constexpr (CHUNKS_PER_WARP == 3) tmem_ld_32x32b_x32(taddr + 64, rc);
             tmem_ld_wait();
             release_tmem();  // the accumulator stage goes back to the MMA warp before any epilogue math
             const long long e2 = clock64();
             process(ra, 0);
             process(rb, 1);
+            if constexpr (CHUNKS_PER_WARP == 3) process(rc, 2);
             if (ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0) {
                 const long long e3 = clock64();
                 ep.dbg[4] += e1 - e0; ep.dbg[5] += e2 - e1; ep.dbg[6] += e3 - e2;
@@ -446,7 +468,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     }
 
     tc_fence_before_sync();
-    __syncthreads();
+    if (MCAST) cluster_sync_all(); else __syncthreads();  // the peer may still multicast into / arrive on this CTA's smem
     if (warp == 2) {
         tc_fence_after_sync();
         tmem_dealloc<kTmemCols>(tmem_base);
@@ -456,11 +478,11 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
 // ---------------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int KCH, int STAGES, int NSTG>
+template <int BN, int KCH, int STAGES, int NSTG, int EW, bool MCAST = false>
 static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC, int M, int N, int K, int mode,
                       const EpiParams& ep, int num_sms, cudaStream_t stream) {
-    using L = GemmSmem<BN, KCH, STAGES, NSTG>;
-    auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG>;
+    using L = GemmSmem<BN, KCH, STAGES, NSTG, EW>;
+    auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG, EW, MCAST>;
     static bool attr_set = false;
     if (!attr_set) {
         MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
@@ -477,7 +499,17 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     } else {
         grid = m_tiles * n_tiles < num_sms ? m_tiles * n_tiles : num_sms;
     }
-    kern<<<grid, gemm_threads(BN), L::DYN_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, mode, ep);
+    if (MCAST) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gemm_threads(EW)); cfg.dynamicSmemBytes = L::DYN_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, mode, ep));
+    } else {
+        kern<<<grid, gemm_threads(EW), L::DYN_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, mode, ep);
+    }
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -497,20 +529,31 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     static const int force_bn = getenv("MST_GEMM_BN") ? atoi(getenv("MST_GEMM_BN")) : 0;  // experiments only
     static const int skip_epi = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;
     if (skip_epi) mode |= skip_epi << 8;  // 1: no epilogue at all, 2: epilogue without the final store
+    static const int no_mcast = getenv("MST_GEMM_NO_MCAST") ? atoi(getenv("MST_GEMM_NO_MCAST")) : 0;  // experiments only
     if (N % 192 == 0 && force_bn != 128) {
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
         if (K == 256) {  // patch embedding: weight-resident, chunk staging (its epilogue stores rows directly)
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
-            return launch_cfg<192, 4, 4, 2>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+            return launch_cfg<192, 4, 4, 2, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
         }
-        // both operands stream through a 4-stage ring; the shared memory a resident weight slab would take goes to
-        // whole-region epilogue staging (one fence + one 32x96 TMA store per warp and tile)
-        MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 64, 32, true, false));
-        return launch_cfg<192, 0, 4, 3>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        if (K == 384 && (N / 192) % 2 == 0 && !no_mcast) {
+            // weight slab resident (144 KB), A stages fetched half-and-half by a CTA pair and TMA-multicast to both
+            TmaDesc tmAh;
+            MST_PROPAGATE(make_tma_2d_bf16(&tmAh, A, K, M, K, BK, BM / 2));
+            MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+            // GELU epilogue (fc1) is the longest: two staging tiles per warp (a TMA store stays in flight while the next
+            // chunk is computed) paid for with a 3-deep A ring; the L2 prefetch keeps the shorter ring fed
+            if ((mode & 0xff) == EPI_BIAS_GELU)
+                return launch_cfg<192, 6, 3, 1, 12, true>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+            return launch_cfg<192, 6, 4, 1, 8, true>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        }
+        // K too large for a resident weight slab (fc2): both operands stream through a 5-stage ring
+        MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+        return launch_cfg<192, 0, 5, 1, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
     }
     MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 128));
     MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 64, 32, true, false));
-    return launch_cfg<128, 0, 5, 3>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+    return launch_cfg<128, 0, 5, 3, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
 }
 
 }  // namespace mst
