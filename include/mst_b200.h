@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MST_ABI_VERSION 1
+#define MST_ABI_VERSION 2
 #if defined(__GNUC__)
 #define MST_API __attribute__((visibility("default")))
 #else
@@ -27,6 +27,8 @@ extern "C" {
 #endif
 
 enum { MST_PRECISION_FP32 = 0, MST_PRECISION_BF16 = 1 };
+/* slice_fusion constructor argument (reference dino.py:80-101,144-157) */
+enum { MST_FUSION_TRANSFORMER = 0, MST_FUSION_LINEAR = 1, MST_FUSION_AVERAGE = 2 };
 
 /* Architecture of one DinoV2ClassifierSlice instance.  Replaces the constructor arguments of
  * reference dino.py:33-103 (model_size -> embed_dim/depth/enc_heads per vision_transformer.py:340-396). */
@@ -36,9 +38,16 @@ typedef struct mst_config {
     int32_t enc_heads;   /* embed_dim / 64 */
     int32_t slice_heads; /* 12 (dino.py:87) */
     int32_t out_ch;      /* classes (dino.py:103) */
-    int32_t pos_tokens;  /* rows of encoder.pos_embed = 1 + (img/14)^2 the weights were built for (257 @224) */
+    int32_t pos_tokens;  /* rows of encoder.pos_embed = 1 + M*M the weights were built for (257 for the local factory
+                            @224, 1370 for the hub checkpoints @518); other patch grids are bicubically resampled
+                            (vision_transformer.py:179-211) */
     int32_t precision;   /* MST_PRECISION_FP32: CUDA-core parity mode; MST_PRECISION_BF16: tcgen05 tensor cores */
     int32_t device;      /* CUDA device ordinal */
+    int32_t num_registers;     /* use_registers: 4 for the dinov2_vit*14_reg hub checkpoints (dino.py:60-61), else 0 */
+    int32_t use_bottleneck;    /* dino.py:75-77: Linear(embed_dim -> embed_dim/4) on the per-slice features */
+    int32_t use_slice_pos_emb; /* dino.py:81-82,140-142: nn.Embedding(256, emb) added to the slice tokens */
+    int32_t slice_fusion;      /* MST_FUSION_* (dino.py:80-101) */
+    int32_t enable_linear;     /* dino.py:103: 0 = nn.Identity head (forward returns the feature) */
 } mst_config;
 
 typedef struct mst_handle_s* mst_handle;
@@ -67,23 +76,43 @@ MST_API int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, i
 /* DinoV2ClassifierSlice.forward (dino.py:110-167).
  *   src        [B,1,D,H,W] fp32 (H, W multiples of 14; (H/14)*(W/14)+1 == pos_tokens; else error)
  *   pad_mask   nullable [B,D] uint8, non-zero = ignore slice (dino.py:147-150)
- *   logits     [B,out_ch] fp32                         feat       nullable [B,embed_dim] (without_linear, dino.py:164)
+ *   src        [B,1,D,H,W] fp32 (H, W multiples of 14)
+ *   logits     [B,out_ch] fp32 (nullable iff enable_linear == 0)
+ *   feat       nullable [B,F] (without_linear, dino.py:164): F = emb for 'transformer'/'average', emb*D for 'linear',
+ *              emb = embed_dim or embed_dim/4 behind the bottleneck
  *   enc_cls    nullable [B*D,embed_dim]: encoder output per slice (dino.py:131)
- *   plane_cls  nullable [B*D,enc_heads,pos_tokens]: row 0 of the LAST encoder block's attention -- the only part
- *              of attention_maps the getters read (dino.py:190-192)
- *   slice_cls  nullable [B,slice_heads,D+1]: row 0 of the slice attention (dino.py:174-175) */
+ *   plane_cls  nullable [B*D,enc_heads,NT], NT = 1 + num_registers + (H/14)*(W/14): row 0 of the LAST encoder block's
+ *              attention -- the only part of attention_maps the getters read (dino.py:190-192)
+ *   slice_cls  nullable [B,slice_heads,D+1]: row 0 of the slice attention (dino.py:174-175); 'transformer' only
+ *   full_maps  nullable [depth,B*D,enc_heads,NT,NT] fp32: every block's full attention, as the reference's hook stores
+ *              them (dino.py:241); only get_attention_cls needs them (mst_rollout) */
 MST_API int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
-                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, void* workspace,
-                size_t workspace_bytes, void* stream);
+                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, float* full_maps,
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* get_plane_attention / get_slice_attention / get_attention_maps (dino.py:173-202) and the caller's
  * head-mean + reshape + trilinear upsample (scripts/main_predict.py:73-74,100,161-162), batched.
  *   attn_maps  nullable [B*D,enc_heads,P] (get_attention_maps)   plane_attn nullable [B*D,enc_heads,P] (get_plane_attention)
  *   slice_attn nullable [B*D] (get_slice_attention)
- *   coarse     nullable [B,1,D,gh,gw] (required when full != NULL)   full nullable [B,1,D,H,W] */
+ *   coarse     nullable [B,1,D,gh,gw] (required when full != NULL)   full nullable [B,1,D,H,W]
+ *   skip_tokens  tokens in front of the patches in plane_cls: 1, or 5 with registers (dino.py:191) */
 MST_API int mst_saliency(const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
-                 int32_t slice_heads, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
+                 int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
                  float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream);
+
+/* get_attention_cls (dino.py:204-212), attention rollout: out = maps[0] @ maps[1] @ ... @ maps[depth-1] evaluated right to
+ * left.  maps [depth,nmat,N,N] fp32 (mst_forward's full_maps with nmat = B*D*enc_heads); out, scratch [nmat,N,N]. */
+MST_API int mst_rollout(const float* maps, int32_t depth, int32_t nmat, int32_t N, float* out, float* scratch, void* stream);
+
+/* interpolate_pos_encoding (vision_transformer.py:179-211) for an H x W input: out [1 + (H/14)*(W/14), embed_dim] fp32,
+ * row 0 the class position.  (mst_forward applies the same table internally; exposed for parity tests.) */
+MST_API int mst_pos_embed(mst_handle h, int32_t H, int32_t W, float* out, void* stream);
+
+/* np.quantile(x, q) per item, numpy's default 'linear' method (scripts/main_predict.py:243-245,296 on the upsampled saliency
+ * volume).  data [items,n] fp32, q_dev [nq] fp64 on the device (nq <= 8), out [items,nq] fp64. */
+MST_API int mst_quantile_workspace_bytes(int32_t items, int32_t nq, size_t* bytes);
+MST_API int mst_quantile(const float* data, int64_t n, int32_t items, const double* q_dev, int32_t nq, double* out,
+                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Instrumentation: kernels launched by this handle so far; per-category device time (CUDA events recorded on the
  * caller's stream around every launch between begin and end; end synchronises the device).  `ms`/`launches` must

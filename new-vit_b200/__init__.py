@@ -4,11 +4,11 @@ Host-side mirror of the reference's `mst.models` surface over a C-ABI CUDA libra
 (`include/mst_b200.h`, built from `new-vit_b200/csrc/`).  No CPU fallback: every compute entry
 point raises if the CUDA library or a GPU is missing.
 """
-__all__ = ["DinoV2ClassifierSlice", "run_pred", "synth"]
+__all__ = ["DinoV2ClassifierSlice", "run_pred", "quantile", "synth"]
 
 
 def __getattr__(name):  # lazy: `import new_vit_b200.synth` must not need the CUDA library
-    if name in ("DinoV2ClassifierSlice", "run_pred", "MSTError"):
+    if name in ("DinoV2ClassifierSlice", "run_pred", "quantile", "MSTError"):
         from new_vit_b200 import model as _m
         return getattr(_m, name)
     if name == "synth":

@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libmst_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mst_b200.h")
 
 PRECISION = {"fp32": 0, "bf16": 1}
+FUSION = {"transformer": 0, "linear": 1, "average": 2}
+ABI_VERSION = 2
 
 
 class MSTError(RuntimeError):
@@ -21,7 +23,8 @@ class MSTError(RuntimeError):
 
 class MstConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("embed_dim", "depth", "enc_heads", "slice_heads", "out_ch", "pos_tokens", "precision", "device")]
+                ("embed_dim", "depth", "enc_heads", "slice_heads", "out_ch", "pos_tokens", "precision", "device",
+                 "num_registers", "use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear")]
 
 
 def declared_symbols():
@@ -50,8 +53,12 @@ def lib():
     L.mst_set_weight.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]
     L.mst_finalize_weights.argtypes = [vp, vp]
     L.mst_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(sz)]
-    L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    L.mst_saliency.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.mst_saliency.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.mst_rollout.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    L.mst_pos_embed.argtypes = [vp, i32, i32, vp, vp]
+    L.mst_quantile_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
+    L.mst_quantile.argtypes = [vp, i64, i32, vp, i32, vp, vp, sz, vp]
     L.mst_kernel_gemm_bf16.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_debug_gemm_timing.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mst_kernel_gemm_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
@@ -69,7 +76,7 @@ def lib():
             fn.restype = ctypes.c_int
     L.mst_profile_categories.restype = ctypes.c_char_p
     L.mst_launch_count.restype = ctypes.c_ulonglong
-    if L.mst_abi_version() != 1:
+    if L.mst_abi_version() != ABI_VERSION:
         raise ImportError("libmst_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -58,7 +58,7 @@ __global__ void pack_pos_kernel(const float* __restrict__ pos, const float* __re
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int t = i / E, n = i % E;
         if (t == 0) cls_pos0[n] = cls[n] + pos[n];
-        else posb[(t - 1) * E + n] = pos[i] + cbias[n];
+        else posb[(t - 1) * E + n] = pos[i] + (cbias ? cbias[n] : 0.f);
     }
 }
 __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict__ Wt, int N, int K) {  // W[N,K] -> Wt[K,N]
@@ -82,8 +82,8 @@ struct Layer {
 
 namespace mst {
 enum Cat { CAT_IM2COL = 0, CAT_GEMM_PATCH, CAT_LAYERNORM, CAT_GEMM_QKV, CAT_ATTENTION, CAT_GEMM_PROJ, CAT_GEMM_FC1,
-           CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, NUM_CAT };
-static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion";
+           CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, CAT_FULL_MAPS, NUM_CAT };
+static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps";
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> pool;
@@ -110,7 +110,10 @@ struct mst_handle_s {
     std::vector<mst::Layer> layers;
     void* wpatch = nullptr;
     float *posb = nullptr, *cls_pos0 = nullptr;
+    std::map<int, float*> pos_cache;            // (gh << 16 | gw) -> interpolated patch position table (+ conv bias), owned
     mst::SliceWeights sw{};
+    int slice_emb() const { return cfg.use_bottleneck ? cfg.embed_dim / 4 : cfg.embed_dim; }
+    int feat_dim(int D) const { return cfg.slice_fusion == mst::SLICE_FUSION_LINEAR ? slice_emb() * D : slice_emb(); }
 };
 
 namespace mst {
@@ -118,10 +121,10 @@ namespace mst {
 static size_t elem_size(const mst_config& c) { return c.precision == MST_PRECISION_BF16 ? 2 : 4; }
 
 static void expected_names(mst_handle h) {
-    const int E = h->cfg.embed_dim, C = h->cfg.out_ch;
+    const int E = h->cfg.embed_dim, C = h->cfg.out_ch, Es = h->slice_emb();
     auto& x = h->expected;
-    x["cls_token"] = E;
     x["encoder.cls_token"] = E;
+    if (h->cfg.num_registers > 0) x["encoder.register_tokens"] = static_cast<int64_t>(h->cfg.num_registers) * E;
     x["encoder.pos_embed"] = static_cast<int64_t>(h->cfg.pos_tokens) * E;
     x["encoder.patch_embed.proj.weight"] = static_cast<int64_t>(E) * 3 * 196;
     x["encoder.patch_embed.proj.bias"] = E;
@@ -135,15 +138,23 @@ static void expected_names(mst_handle h) {
         x[p + "mlp.fc2.weight"] = 4LL * E * E; x[p + "mlp.fc2.bias"] = E;
     }
     x["encoder.norm.weight"] = E; x["encoder.norm.bias"] = E;
-    const std::string q = "slice_fusion.layers.0.";
-    x[q + "self_attn.in_proj_weight"] = 3LL * E * E; x[q + "self_attn.in_proj_bias"] = 3 * E;
-    x[q + "self_attn.out_proj.weight"] = 1LL * E * E; x[q + "self_attn.out_proj.bias"] = E;
-    x[q + "linear1.weight"] = 1LL * E * E; x[q + "linear1.bias"] = E;
-    x[q + "linear2.weight"] = 1LL * E * E; x[q + "linear2.bias"] = E;
-    x[q + "norm1.weight"] = E; x[q + "norm1.bias"] = E;
-    x[q + "norm2.weight"] = E; x[q + "norm2.bias"] = E;
-    x["slice_fusion.norm.weight"] = E; x["slice_fusion.norm.bias"] = E;
-    x["linear.weight"] = 1LL * C * E; x["linear.bias"] = C;
+    if (h->cfg.use_bottleneck) { x["bottleneck.weight"] = 1LL * Es * E; x["bottleneck.bias"] = Es; }  // dino.py:75-77
+    if (h->cfg.slice_fusion == SLICE_FUSION_TRANSFORMER) {                                             // dino.py:80-97
+        if (h->cfg.use_slice_pos_emb) x["slice_pos_emb.weight"] = 256LL * Es;
+        x["cls_token"] = Es;
+        const std::string q = "slice_fusion.layers.0.";
+        x[q + "self_attn.in_proj_weight"] = 3LL * Es * Es; x[q + "self_attn.in_proj_bias"] = 3 * Es;
+        x[q + "self_attn.out_proj.weight"] = 1LL * Es * Es; x[q + "self_attn.out_proj.bias"] = Es;
+        x[q + "linear1.weight"] = 1LL * Es * Es; x[q + "linear1.bias"] = Es;
+        x[q + "linear2.weight"] = 1LL * Es * Es; x[q + "linear2.bias"] = Es;
+        x[q + "norm1.weight"] = Es; x[q + "norm1.bias"] = Es;
+        x[q + "norm2.weight"] = Es; x[q + "norm2.bias"] = Es;
+        x["slice_fusion.norm.weight"] = Es; x["slice_fusion.norm.bias"] = Es;
+    }
+    if (h->cfg.enable_linear) {                                                                        // dino.py:98-103
+        const int64_t in = h->cfg.slice_fusion == SLICE_FUSION_LINEAR ? 32LL * Es : Es;
+        x["linear.weight"] = C * in; x["linear.bias"] = C;
+    }
 }
 
 // "encoder.blocks.0.7.x" (BlockChunk naming, vision_transformer.py:153-160) -> "encoder.blocks.7.x"
@@ -194,6 +205,8 @@ static int transposed(mst_handle h, const std::string& name, int N, int K, const
 template <typename T>
 static int finalize_t(mst_handle h, cudaStream_t st) {
     const int E = h->cfg.embed_dim, P = h->cfg.pos_tokens - 1;
+    for (auto& kv : h->pos_cache) cudaFree(kv.second);
+    h->pos_cache.clear();
     h->layers.assign(h->cfg.depth, Layer());
     for (int i = 0; i < h->cfg.depth; ++i) {
         const std::string p = "encoder.blocks." + std::to_string(i) + ".";
@@ -220,17 +233,54 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
     MST_CHECK_CUDA(cudaGetLastError());
     const std::string q = "slice_fusion.layers.0.";
     SliceWeights& s = h->sw;
-    s.cls_token = h->master["cls_token"];
-    s.n1w = h->master[q + "norm1.weight"]; s.n1b = h->master[q + "norm1.bias"];
-    s.n2w = h->master[q + "norm2.weight"]; s.n2b = h->master[q + "norm2.bias"];
-    s.nfw = h->master["slice_fusion.norm.weight"]; s.nfb = h->master["slice_fusion.norm.bias"];
-    s.in_b = h->master[q + "self_attn.in_proj_bias"]; s.out_b = h->master[q + "self_attn.out_proj.bias"];
-    s.l1_b = h->master[q + "linear1.bias"]; s.l2_b = h->master[q + "linear2.bias"]; s.head_b = h->master["linear.bias"];
-    MST_PROPAGATE(transposed(h, q + "self_attn.in_proj_weight", 3 * E, E, &s.in_wt, st));
-    MST_PROPAGATE(transposed(h, q + "self_attn.out_proj.weight", E, E, &s.out_wt, st));
-    MST_PROPAGATE(transposed(h, q + "linear1.weight", E, E, &s.l1_wt, st));
-    MST_PROPAGATE(transposed(h, q + "linear2.weight", E, E, &s.l2_wt, st));
-    MST_PROPAGATE(transposed(h, "linear.weight", h->cfg.out_ch, E, &s.head_wt, st));
+    s = SliceWeights{};
+    const int Es = h->slice_emb();
+    if (h->cfg.use_bottleneck) {
+        MST_PROPAGATE(transposed(h, "bottleneck.weight", Es, E, &s.bott_wt, st));
+        s.bott_b = h->master["bottleneck.bias"];
+    }
+    if (h->cfg.slice_fusion == SLICE_FUSION_TRANSFORMER) {
+        if (h->cfg.use_slice_pos_emb) s.pos_emb = h->master["slice_pos_emb.weight"];
+        s.cls_token = h->master["cls_token"];
+        s.n1w = h->master[q + "norm1.weight"]; s.n1b = h->master[q + "norm1.bias"];
+        s.n2w = h->master[q + "norm2.weight"]; s.n2b = h->master[q + "norm2.bias"];
+        s.nfw = h->master["slice_fusion.norm.weight"]; s.nfb = h->master["slice_fusion.norm.bias"];
+        s.in_b = h->master[q + "self_attn.in_proj_bias"]; s.out_b = h->master[q + "self_attn.out_proj.bias"];
+        s.l1_b = h->master[q + "linear1.bias"]; s.l2_b = h->master[q + "linear2.bias"];
+        MST_PROPAGATE(transposed(h, q + "self_attn.in_proj_weight", 3 * Es, Es, &s.in_wt, st));
+        MST_PROPAGATE(transposed(h, q + "self_attn.out_proj.weight", Es, Es, &s.out_wt, st));
+        MST_PROPAGATE(transposed(h, q + "linear1.weight", Es, Es, &s.l1_wt, st));
+        MST_PROPAGATE(transposed(h, q + "linear2.weight", Es, Es, &s.l2_wt, st));
+    }
+    if (h->cfg.enable_linear) {
+        s.head_b = h->master["linear.bias"];
+        const int in = h->cfg.slice_fusion == SLICE_FUSION_LINEAR ? 32 * Es : Es;
+        MST_PROPAGATE(transposed(h, "linear.weight", h->cfg.out_ch, in, &s.head_wt, st));
+    }
+    return 0;
+}
+
+// Patch position table (+ conv bias) for a gh x gw patch grid: the checkpoint's own rows when the grid matches
+// (vision_transformer.py:183-184), else bicubic resampling (:185-211), cached per grid for the handle's lifetime.
+static int pos_for_grid(mst_handle h, int gh, int gw, const float** out, cudaStream_t st) {
+    const int E = h->cfg.embed_dim, Pn = h->cfg.pos_tokens - 1;
+    int M = 1;
+    while ((M + 1) * (M + 1) <= Pn) ++M;
+    if (gh == M && gw == M && M * M == Pn) { *out = h->posb; return 0; }
+    MST_REQUIRE(M * M == Pn, "pos_embed has %d patch rows, not a square grid: cannot interpolate (vision_transformer.py:193)", Pn);
+    const int key = (gh << 16) | gw;
+    auto it = h->pos_cache.find(key);
+    if (it == h->pos_cache.end()) {
+        float* t = nullptr;
+        MST_CHECK_CUDA(cudaMalloc(&t, static_cast<size_t>(gh) * gw * E * sizeof(float)));
+        // scale_factor = (g + 0.1) / M (interpolate_offset, :199-200); ATen maps coordinates with 1/scale_factor
+        const float sy = static_cast<float>(1.0 / ((gh + 0.1) / static_cast<double>(M)));
+        const float sx = static_cast<float>(1.0 / ((gw + 0.1) / static_cast<double>(M)));
+        MST_PROPAGATE(launch_pos_bicubic(h->master["encoder.pos_embed"], h->master["encoder.patch_embed.proj.bias"], t, M, gh, gw, E,
+                                         sy, sx, st));
+        it = h->pos_cache.emplace(key, t).first;
+    }
+    *out = it->second;
     return 0;
 }
 
@@ -244,7 +294,7 @@ struct Workspace {
 };
 static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t* base) {
     const size_t es = elem_size(c);
-    const int64_t E = c.embed_dim, BD = static_cast<int64_t>(B) * D, P = static_cast<int64_t>(H / 14) * (W / 14), N = P + 1, M = BD * N;
+    const int64_t E = c.embed_dim, BD = static_cast<int64_t>(B) * D, P = static_cast<int64_t>(H / 14) * (W / 14), N = P + 1 + c.num_registers, M = BD * N;
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~static_cast<size_t>(255); return p; };
     Workspace w;
@@ -296,9 +346,12 @@ template <> struct Ops<float> {
 
 template <typename T>
 static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W, const uint8_t* pad_mask, float* logits,
-                     float* feat, float* enc_cls_out, float* plane_cls, float* slice_cls, const Workspace& ws, cudaStream_t st) {
+                     float* feat, float* enc_cls_out, float* plane_cls, float* slice_cls, float* full_maps, const Workspace& ws,
+                     cudaStream_t st) {
     const mst_config& c = h->cfg;
-    const int E = c.embed_dim, BD = B * D, P = (H / 14) * (W / 14), N = P + 1;
+    const int E = c.embed_dim, BD = B * D, P = (H / 14) * (W / 14), R = c.num_registers, N = P + 1 + R;
+    const float* posb = nullptr;
+    MST_PROPAGATE(pos_for_grid(h, H / 14, W / 14, &posb, st));
     const int64_t M64 = static_cast<int64_t>(BD) * N;
     MST_REQUIRE(M64 * 4 * E < (1LL << 40) && M64 < (1LL << 31) - 256, "batch too large: %lld tokens", (long long)M64);
     const int M = static_cast<int>(M64);
@@ -306,10 +359,11 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
     T* xn = static_cast<T*>(ws.xn);
 
     // patch embedding + CLS/pos (K1-K3)
-    MST_LAUNCH(CAT_IM2COL, launch_im2col<T>(src, static_cast<T*>(ws.A0), x, h->cls_pos0, BD, H, W, KP, E, st));
+    MST_LAUNCH(CAT_IM2COL, launch_im2col<T>(src, static_cast<T*>(ws.A0), x, h->cls_pos0,
+                                            R > 0 ? h->master["encoder.register_tokens"] : nullptr, R, BD, H, W, KP, E, st));
     {
         EpiParams ep{};
-        ep.posb = h->posb; ep.P = P; ep.out = x; ep.ldo = E;
+        ep.posb = posb; ep.P = P; ep.R = R; ep.out = x; ep.ldo = E;
         MST_LAUNCH(CAT_GEMM_PATCH, Ops<T>::gemm(h, ws.A0, KP, h->wpatch, BD * P, E, KP, EPI_PATCH, ep, st));
     }
     for (int l = 0; l < c.depth; ++l) {
@@ -322,6 +376,10 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
             ep.bias = L.bqkv; ep.out = ws.qkv; ep.ldo = 3 * E;
             MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, xn, E, L.wqkv, M, 3 * E, E, EPI_BIAS, ep, st));
         }
+        if (full_maps)  // what the reference's hook appends for every block (dino.py:241): [BD, heads, N, N] fp32
+            MST_LAUNCH(CAT_FULL_MAPS, launch_attention_probs<T>(static_cast<const T*>(ws.qkv),
+                                                                full_maps + static_cast<int64_t>(l) * BD * c.enc_heads * N * N, BD, N,
+                                                                c.enc_heads, st));
         if (!last) {
             MST_LAUNCH(CAT_ATTENTION, Ops<T>::attention(h, ws.qkv, xn, BD, N, c.enc_heads, st));  // xn is dead: reuse as attention output
             {
@@ -368,8 +426,9 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
             float* enc = enc_cls_out ? enc_cls_out : ws.enc_cls;
             MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, float>(xc, E, enc, E, h->master["encoder.norm.weight"],
                                                                  h->master["encoder.norm.bias"], BD, E, 1e-6f, st)));
-            MST_LAUNCH(CAT_SLICE_FUSION, launch_slice_fusion(enc, pad_mask, h->sw, ws.hs, logits, feat, slice_cls, B, D, E,
-                                                         c.slice_heads, c.out_ch, st));
+            MST_LAUNCH(CAT_SLICE_FUSION, launch_slice_fusion(enc, pad_mask, h->sw, ws.hs, c.enable_linear ? logits : nullptr, feat,
+                                                         slice_cls, B, D, E, h->slice_emb(), c.slice_heads, c.out_ch,
+                                                         c.slice_fusion, st));
         }
     }
     return 0;
@@ -395,6 +454,11 @@ int mst_create(const mst_config* cfg, mst_handle* out) {
     MST_REQUIRE(cfg->depth >= 1 && cfg->out_ch >= 1 && cfg->pos_tokens >= 2, "mst_create: bad depth/out_ch/pos_tokens");
     MST_REQUIRE(cfg->slice_heads >= 1 && cfg->slice_heads <= 16 && cfg->embed_dim % cfg->slice_heads == 0, "mst_create: bad slice_heads");
     MST_REQUIRE(cfg->precision == MST_PRECISION_FP32 || cfg->precision == MST_PRECISION_BF16, "mst_create: bad precision");
+    MST_REQUIRE(cfg->num_registers >= 0 && cfg->num_registers <= 16, "mst_create: bad num_registers %d", cfg->num_registers);
+    MST_REQUIRE(cfg->slice_fusion >= MST_FUSION_TRANSFORMER && cfg->slice_fusion <= MST_FUSION_AVERAGE, "mst_create: bad slice_fusion %d",
+                cfg->slice_fusion);
+    MST_REQUIRE(!cfg->use_bottleneck || (cfg->embed_dim / 4) % cfg->slice_heads == 0, "mst_create: bottleneck width %d not divisible by %d heads",
+                cfg->embed_dim / 4, cfg->slice_heads);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     MST_REQUIRE(e == cudaSuccess && ndev > 0, "mst_create: no CUDA device (%s); this library has no CPU fallback",
@@ -418,6 +482,7 @@ int mst_destroy(mst_handle h) {
     cudaDeviceSynchronize();
     for (auto& kv : h->master) cudaFree(kv.second);
     for (void* p : h->owned) cudaFree(p);
+    for (auto& kv : h->pos_cache) cudaFree(kv.second);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     delete h;
     return 0;
@@ -465,9 +530,9 @@ static int check_shape(mst_handle h, int B, int D, int H, int W) {
     MST_REQUIRE(B >= 1 && D >= 1, "empty batch: B=%d D=%d", B, D);
     MST_REQUIRE(H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0,
                 "Input image height/width (%d, %d) is not a multiple of patch size 14", H, W);  // patch_embed.py:72-73
-    MST_REQUIRE((H / 14) * (W / 14) + 1 == h->cfg.pos_tokens,
-                "input %dx%d gives %d tokens but pos_embed has %d: set an interpolated pos_embed for this size first",
-                H, W, (H / 14) * (W / 14) + 1, h->cfg.pos_tokens);
+    MST_REQUIRE(h->cfg.slice_fusion != MST_FUSION_LINEAR || D == 32,
+                "slice_fusion='linear' is built for 32 slices (dino.py:99), got D=%d", D);
+    MST_REQUIRE(!h->cfg.use_slice_pos_emb || D <= 256, "slice position embedding holds 256 slices (dino.py:82), got D=%d", D);
     return 0;
 }
 
@@ -479,9 +544,11 @@ int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W
 }
 
 int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
-                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, void* workspace,
-                size_t workspace_bytes, void* stream) {
-    MST_REQUIRE(h && src && logits && workspace, "mst_forward: null argument");
+                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, float* full_maps,
+                void* workspace, size_t workspace_bytes, void* stream) {
+    MST_REQUIRE(h && src && workspace && (logits || !h->cfg.enable_linear), "mst_forward: null argument");
+    MST_REQUIRE(h->cfg.slice_fusion == MST_FUSION_TRANSFORMER || slice_cls == nullptr,
+                "mst_forward: slice attention exists only for slice_fusion='transformer' (dino.py:257-260)");
     MST_REQUIRE(h->finalized, "mst_forward: weights not finalized");
     MST_PROPAGATE(check_shape(h, B, D, H, W));
     MST_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mst_forward: workspace must be 256-byte aligned");
@@ -490,17 +557,57 @@ int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H,
     MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (h->cfg.precision == MST_PRECISION_BF16)
-        return forward_t<bf16>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, ws, st);
-    return forward_t<float>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, ws, st);
+        return forward_t<bf16>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+    return forward_t<float>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
 }
 
 int mst_saliency(const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
-                 int32_t slice_heads, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
+                 int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
                  float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream) {
     MST_REQUIRE(plane_cls && slice_cls, "mst_saliency: null argument");
-    MST_REQUIRE(B >= 1 && D >= 1 && gh >= 1 && gw >= 1, "mst_saliency: empty input");
-    return launch_saliency(plane_cls, slice_cls, B, D, enc_heads, slice_heads, gh, gw, H, W, attn_maps, plane_attn, slice_attn, coarse, full,
-                           static_cast<cudaStream_t>(stream));
+    MST_REQUIRE(B >= 1 && D >= 1 && gh >= 1 && gw >= 1 && skip_tokens >= 1, "mst_saliency: empty input");
+    return launch_saliency(plane_cls, slice_cls, B, D, enc_heads, slice_heads, skip_tokens, gh, gw, H, W, attn_maps, plane_attn, slice_attn,
+                           coarse, full, static_cast<cudaStream_t>(stream));
+}
+
+int mst_rollout(const float* maps, int32_t depth, int32_t nmat, int32_t N, float* out, float* scratch, void* stream) {
+    MST_REQUIRE(maps && out && scratch && depth >= 1 && nmat >= 1 && N >= 1, "mst_rollout: bad argument");
+    return launch_rollout(maps, depth, nmat, N, out, scratch, static_cast<cudaStream_t>(stream));
+}
+
+int mst_pos_embed(mst_handle h, int32_t H, int32_t W, float* out, void* stream) {
+    MST_REQUIRE(h && out && h->finalized, "mst_pos_embed: null argument or weights not finalized");
+    MST_REQUIRE(H > 0 && W > 0 && H % 14 == 0 && W % 14 == 0, "mst_pos_embed: %dx%d is not a multiple of 14", H, W);
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int E = h->cfg.embed_dim, gh = H / 14, gw = W / 14;
+    int M = 1;
+    while ((M + 1) * (M + 1) <= h->cfg.pos_tokens - 1) ++M;
+    const float* pos = h->master["encoder.pos_embed"];
+    MST_CHECK_CUDA(cudaMemcpyAsync(out, pos, E * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (gh == M && gw == M && M * M == h->cfg.pos_tokens - 1) {
+        MST_CHECK_CUDA(cudaMemcpyAsync(out + E, pos + E, static_cast<size_t>(M) * M * E * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    MST_REQUIRE(M * M == h->cfg.pos_tokens - 1, "mst_pos_embed: pos_embed is not a square grid");
+    const float sy = static_cast<float>(1.0 / ((gh + 0.1) / static_cast<double>(M)));
+    const float sx = static_cast<float>(1.0 / ((gw + 0.1) / static_cast<double>(M)));
+    return launch_pos_bicubic(pos, nullptr, out + E, M, gh, gw, E, sy, sx, st);
+}
+
+int mst_quantile_workspace_bytes(int32_t items, int32_t nq, size_t* bytes) {
+    MST_REQUIRE(bytes && items >= 1 && nq >= 1, "mst_quantile_workspace_bytes: bad argument");
+    *bytes = quantile_workspace_bytes(items, nq);
+    return 0;
+}
+int mst_quantile(const float* data, int64_t n, int32_t items, const double* q_dev, int32_t nq, double* out, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    MST_REQUIRE(data && q_dev && out && workspace, "mst_quantile: null argument");
+    MST_REQUIRE(workspace_bytes >= quantile_workspace_bytes(items, nq), "mst_quantile: workspace too small");
+    int dev = 0, sms = 0;
+    MST_CHECK_CUDA(cudaGetDevice(&dev));
+    MST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_quantile(data, n, items, q_dev, nq, out, workspace, sms, static_cast<cudaStream_t>(stream));
 }
 
 const char* mst_profile_categories(void) { return kCatNames; }

@@ -39,7 +39,7 @@ enum EpiMode : int {
     EPI_BIAS = 0,       // out = acc + bias[n]
     EPI_BIAS_GELU = 1,  // out = gelu_erf(acc + bias[n])                (reference mlp.py:35-36)
     EPI_BIAS_RES = 2,   // out = res[row*ldr + n] + acc + bias[n]       (block.py:112-113; LayerScale folded in W,b)
-    EPI_PATCH = 3,      // out[(row/P)*(P+1) + 1 + row%P, n] = acc + posb[(row%P)*N + n]   (patch_embed.py:75-77 +
+    EPI_PATCH = 3,      // out[(row/P)*(P+1+R) + 1 + R + row%P, n] = acc + posb[(row%P)*N + n]   (patch_embed.py:75-77 +
                         //                                      vision_transformer.py:219-220; bias folded in posb)
     EPI_BIAS_ACCUM = 4  // out[row, n] += acc + bias[n]   (in-place residual update; bf16 path: TMA reduce-add)
 };
@@ -50,6 +50,7 @@ struct EpiParams {
     int64_t ldr;         // residual row stride in elements
     const float* posb;   // [P, N] fp32 (EPI_PATCH)
     int P;               // patches per slice (EPI_PATCH)
+    int R;               // register tokens between the CLS row and the patch rows (EPI_PATCH)
     void* out;           // output, dtype T
     int64_t ldo;         // output row stride in elements
     long long* dbg;      // nullable: phase cycle counters of CTA 0 (profiles/gemm_timing.py)
@@ -114,8 +115,8 @@ int gemm_f32_simt(const float* A, int64_t lda, const float* W, int M, int N, int
                   cudaStream_t stream);
 
 template <typename T>
-int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, int BD, int H, int W, int KP, int E,
-                  cudaStream_t stream);
+int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, const float* regs, int R, int BD, int H, int W,
+                  int KP, int E, cudaStream_t stream);
 template <typename TIn, typename TOut>
 int launch_layernorm(const TIn* x, int64_t ldx, TOut* y, int64_t ldy, const float* gamma, const float* beta, int rows,
                      int E, float eps, cudaStream_t stream);
@@ -124,15 +125,28 @@ int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads,
 template <typename T>
 int launch_cls_attention(const T* qkv, T* out_cls, float* plane_cls, int BD, int N, int heads, cudaStream_t stream);
 
-struct SliceWeights {  // fp32, linear weights pre-transposed to [in][out]
+enum SliceFusionMode : int { SLICE_FUSION_TRANSFORMER = 0, SLICE_FUSION_LINEAR = 1, SLICE_FUSION_AVERAGE = 2 };  // dino.py:80-101
+struct SliceWeights {  // fp32, linear weights pre-transposed to [in][out]; bott_* / pos_emb nullable (dino.py:75-82)
     const float *cls_token, *n1w, *n1b, *in_wt, *in_b, *out_wt, *out_b, *n2w, *n2b, *l1_wt, *l1_b, *l2_wt, *l2_b, *nfw,
-        *nfb, *head_wt, *head_b;
+        *nfb, *head_wt, *head_b, *bott_wt, *bott_b, *pos_emb;
 };
+// enc_cls [B*D, Eenc]; E = slice embedding (Eenc, or Eenc/4 behind the bottleneck); logits/feat nullable
 int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,
-                        float* logits, float* feat, float* slice_cls, int B, int D, int E, int heads, int out_ch,
-                        cudaStream_t stream);
-int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int gh,
+                        float* logits, float* feat, float* slice_cls, int B, int D, int Eenc, int E, int heads, int out_ch,
+                        int mode, cudaStream_t stream);
+int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int skip, int gh,
                     int gw, int H, int W, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full,
                     cudaStream_t stream);
+
+
+// ---- kernels either side of the main path (extras.cu) ---------------------------------------------
+int launch_pos_bicubic(const float* pos, const float* cbias, float* posb, int M, int gh, int gw, int E, float scale_y,
+                       float scale_x, cudaStream_t stream);
+template <typename T>
+int launch_attention_probs(const T* qkv, float* probs, int BD, int N, int heads, cudaStream_t stream);
+int launch_rollout(const float* maps, int depth, int nmat, int N, float* out, float* scratch, cudaStream_t stream);
+size_t quantile_workspace_bytes(int items, int nq);
+int launch_quantile(const float* data, int64_t n, int items, const double* q_dev, int nq, double* out, void* workspace,
+                    int num_sms, cudaStream_t stream);
 
 }  // namespace mst

@@ -190,7 +190,7 @@ __device__ __forceinline__ void store_block_32x32(uint8_t* stg, const uint32_t (
         const int64_t row = static_cast<int64_t>(row0) + r;
         if (row < M) {
             int64_t orow = row;
-            if (mode == EPI_PATCH) orow = (row / ep.P) * (ep.P + 1) + 1 + (row % ep.P);
+            if (mode == EPI_PATCH) orow = (row / ep.P) * (ep.P + 1 + ep.R) + 1 + ep.R + (row % ep.P);
             bf16* dst = static_cast<bf16*>(ep.out) + orow * ep.ldo + n0 + pc * 8;
             if (mode == EPI_BIAS_ACCUM) red_add_bf16x8(dst, u);
             else *reinterpret_cast<uint4*>(dst) = u;
@@ -389,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 if (mode == EPI_PATCH) {
                     // rows are re-mapped (one CLS row inserted per slice): direct 64-byte row stores
                     if (row_ok) {
-                        const int64_t orow = (row / ep.P) * (ep.P + 1) + 1 + (row % ep.P);
+                        const int64_t orow = (row / ep.P) * (ep.P + 1 + ep.R) + 1 + ep.R + (row % ep.P);
                         uint4* po = reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) po[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);

@@ -84,13 +84,15 @@ template <> struct Vec4<bf16> {
 
 // ---------------------------------------------------------------------------------------------------
 // im2col: src [BD,H,W] fp32 -> A0 [BD*P, KP] (column ky*14+kx, zero padded to KP), plus the CLS token
-// row of every slice: x[s*(P+1)] = cls_token + pos_embed[0].  Replaces the rearrange + 3x repeat +
+// row of every slice: x[s*NT] = cls_token + pos_embed[0], followed by the R register tokens (no position
+// embedding, vision_transformer.py:222-230); NT = 1 + R + P.  Replaces the rearrange + 3x repeat +
 // conv unfold of reference dino.py:125-127 / patch_embed.py:75-77 (the RGB copies are never
 // materialised: the conv weight is channel-summed at pack time).
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ src, T* __restrict__ A0, T* __restrict__ x,
-                                                      const float* __restrict__ cls_pos0, int H, int W, int KP, int E) {
+                                                      const float* __restrict__ cls_pos0, const float* __restrict__ regs, int R,
+                                                      int H, int W, int KP, int E) {
     extern __shared__ float tile[];  // [14][W]
     const int gh = H / 14, gw = W / 14, P = gh * gw;
     const int s = blockIdx.x / gh, py = blockIdx.x % gh;
@@ -106,21 +108,22 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ s
         }
     }
     if (py == 0) {
-        T* xrow = x + static_cast<int64_t>(s) * (P + 1) * E;
+        T* xrow = x + static_cast<int64_t>(s) * (P + 1 + R) * E;
         for (int e = threadIdx.x; e < E; e += blockDim.x) xrow[e] = from_f<T>(cls_pos0[e]);
+        for (int e = threadIdx.x; e < R * E; e += blockDim.x) xrow[E + e] = from_f<T>(regs[e]);
     }
 }
 
 template <typename T>
-int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, int BD, int H, int W, int KP, int E,
-                  cudaStream_t stream) {
+int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, const float* regs, int R, int BD, int H, int W,
+                  int KP, int E, cudaStream_t stream) {
     const int gh = H / 14;
-    im2col_kernel<T><<<BD * gh, 256, 14 * W * sizeof(float), stream>>>(src, A0, x, cls_pos0, H, W, KP, E);
+    im2col_kernel<T><<<BD * gh, 256, 14 * W * sizeof(float), stream>>>(src, A0, x, cls_pos0, regs, R, H, W, KP, E);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_im2col<float>(const float*, float*, float*, const float*, int, int, int, int, int, cudaStream_t);
-template int launch_im2col<bf16>(const float*, bf16*, bf16*, const float*, int, int, int, int, int, cudaStream_t);
+template int launch_im2col<float>(const float*, float*, float*, const float*, const float*, int, int, int, int, int, int, cudaStream_t);
+template int launch_im2col<bf16>(const float*, bf16*, bf16*, const float*, const float*, int, int, int, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm over rows of E (E % 128 == 0): one warp per row, two-pass in registers, fp32 statistics.
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
         int64_t orow = row;
         if (mode == EPI_PATCH) {
             const int p = static_cast<int>(row % ep.P);
-            orow = (row / ep.P) * (ep.P + 1) + 1 + p;
+            orow = (row / ep.P) * (ep.P + 1 + ep.R) + 1 + ep.R + p;
             const float4 b = *reinterpret_cast<const float4*>(ep.posb + static_cast<int64_t>(p) * N + n);
             v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
         } else {
@@ -449,10 +452,10 @@ __device__ __forceinline__ void block_matvec(const float* in, const float* __res
 
 __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restrict__ enc_cls, const uint8_t* __restrict__ pad_mask,
                                                             SliceWeights w, float* __restrict__ hs_all, float* __restrict__ logits,
-                                                            float* __restrict__ feat, float* __restrict__ slice_cls, int D, int E,
-                                                            int heads, int out_ch) {
+                                                            float* __restrict__ feat, float* __restrict__ slice_cls, int D, int Eenc,
+                                                            int E, int heads, int out_ch, int mode) {
     extern __shared__ float sm[];
-    const int L = D + 1, hd = E / heads;
+    const int L = mode == SLICE_FUSION_TRANSFORMER ? D + 1 : D, l0 = L - D, hd = E / heads;
     float* x0 = sm;                 // [E]  raw CLS token (residual)
     float* n0 = x0 + E;             // [E]  LN1(token 0)
     float* q = n0 + E;              // [E]
@@ -466,11 +469,63 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     float* p = red + 40;            // [heads][L]
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    float* hs = hs_all + static_cast<int64_t>(b) * L * E;
+    float* hs = hs_all + static_cast<int64_t>(b) * (D + 1) * E;
 
-    // 1. tokens = [cls_token, enc_cls[b, 0..D-1]]; hs[l] = LN1(token l)   (dino.py:145; transformer_blocks.py:566)
+    // 0. slice tokens: optional bottleneck Linear(Eenc -> E) (dino.py:134-135), optional slice position embedding
+    //    (dino.py:140-142), the slice-CLS token in front for the transformer (dino.py:145)
     for (int l = warp; l < L; l += nwarps) {
-        const float* src = l == 0 ? w.cls_token : enc_cls + (static_cast<int64_t>(b) * D + l - 1) * E;
+        float* dst = hs + static_cast<int64_t>(l) * E;
+        if (l < l0) {
+            for (int i = lane; i < E; i += 32) dst[i] = w.cls_token[i];
+            continue;
+        }
+        const int d = l - l0;
+        const float* src = enc_cls + (static_cast<int64_t>(b) * D + d) * Eenc;
+        for (int i = lane; i < E; i += 32) {
+            float v;
+            if (w.bott_wt) {
+                float a0 = 0.f, a1 = 0.f;
+                for (int k = 0; k < Eenc; k += 2) {
+                    a0 = fmaf(src[k], __ldg(w.bott_wt + static_cast<int64_t>(k) * E + i), a0);
+                    a1 = fmaf(src[k + 1], __ldg(w.bott_wt + static_cast<int64_t>(k + 1) * E + i), a1);
+                }
+                v = (a0 + a1) + w.bott_b[i];
+            } else {
+                v = src[i];
+            }
+            if (w.pos_emb) v += w.pos_emb[static_cast<int64_t>(d) * E + i];
+            dst[i] = v;
+        }
+    }
+    __syncthreads();
+
+    if (mode != SLICE_FUSION_TRANSFORMER) {
+        // 'linear': flatten [D*E] (dino.py:154-155); 'average': mean over slices (dino.py:156-157); the padding mask is
+        // not consulted by either (same as the reference)
+        const int F = mode == SLICE_FUSION_LINEAR ? D * E : E;
+        if (mode == SLICE_FUSION_AVERAGE) {
+            for (int i = threadIdx.x; i < E; i += blockDim.x) {
+                float a = 0.f;
+                for (int d = 0; d < D; ++d) a += hs[static_cast<int64_t>(d) * E + i];
+                hs[i] = a / D;  // row 0 is only read by this thread at column i
+            }
+            __syncthreads();
+        }
+        if (feat)
+            for (int i = threadIdx.x; i < F; i += blockDim.x) feat[static_cast<int64_t>(b) * F + i] = hs[i];
+        if (logits)
+            for (int c = warp; c < out_ch; c += nwarps) {
+                float a = 0.f;
+                for (int k = lane; k < F; k += 32) a = fmaf(hs[k], w.head_wt[static_cast<int64_t>(k) * out_ch + c], a);
+                a = warp_sum(a);
+                if (lane == 0) logits[static_cast<int64_t>(b) * out_ch + c] = a + w.head_b[c];
+            }
+        return;
+    }
+
+    // 1. hs[l] = LN1(token l), in place                                 (transformer_blocks.py:566)
+    for (int l = warp; l < L; l += nwarps) {
+        float* src = hs + static_cast<int64_t>(l) * E;
         float s = 0.f;
         for (int i = lane; i < E; i += 32) s += src[i];
         const float mean = warp_sum(s) / E;
@@ -478,9 +533,10 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
         for (int i = lane; i < E; i += 32) { const float d = src[i] - mean; v = fmaf(d, d, v); }
         const float rstd = rsqrtf(warp_sum(v) / E + 1e-5f);
         for (int i = lane; i < E; i += 32) {
-            const float o = fmaf((src[i] - mean) * rstd, w.n1w[i], w.n1b[i]);
-            hs[static_cast<int64_t>(l) * E + i] = o;
-            if (l == 0) { n0[i] = o; x0[i] = src[i]; }
+            const float raw = src[i];
+            const float o = fmaf((raw - mean) * rstd, w.n1w[i], w.n1b[i]);
+            src[i] = o;
+            if (l == 0) { n0[i] = o; x0[i] = raw; }
         }
     }
     __syncthreads();
@@ -556,22 +612,23 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     block_layernorm(t1, t0, w.n2w, w.n2b, E, 1e-5f, red);
     block_matvec(t0, w.l1_wt, E, w.l1_b, nullptr, t2, E, E, true, 1.0f);
     block_matvec(t2, w.l2_wt, E, w.l2_b, t1, t0, E, E, false, 1.0f);
-    // 10. final LayerNorm (dino.py:95), feature = row 0 (dino.py:153), logits (dino.py:166)
+    // 10. final LayerNorm (dino.py:95), feature = row 0 (dino.py:153), logits (dino.py:166; nn.Identity if !enable_linear)
     block_layernorm(t0, t1, w.nfw, w.nfb, E, 1e-5f, red);
     if (feat)
         for (int i = threadIdx.x; i < E; i += blockDim.x) feat[static_cast<int64_t>(b) * E + i] = t1[i];
-    for (int c = warp; c < out_ch; c += nwarps) {
-        float a = 0.f;
-        for (int k = lane; k < E; k += 32) a = fmaf(t1[k], w.head_wt[static_cast<int64_t>(k) * out_ch + c], a);
-        a = warp_sum(a);
-        if (lane == 0) logits[static_cast<int64_t>(b) * out_ch + c] = a + w.head_b[c];
-    }
+    if (logits)
+        for (int c = warp; c < out_ch; c += nwarps) {
+            float a = 0.f;
+            for (int k = lane; k < E; k += 32) a = fmaf(t1[k], w.head_wt[static_cast<int64_t>(k) * out_ch + c], a);
+            a = warp_sum(a);
+            if (lane == 0) logits[static_cast<int64_t>(b) * out_ch + c] = a + w.head_b[c];
+        }
 }
 
 int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,
-                        float* logits, float* feat, float* slice_cls, int B, int D, int E, int heads, int out_ch,
-                        cudaStream_t stream) {
-    MST_REQUIRE(heads <= 16 && E % heads == 0, "slice transformer: heads=%d E=%d unsupported", heads, E);
+                        float* logits, float* feat, float* slice_cls, int B, int D, int Eenc, int E, int heads, int out_ch,
+                        int mode, cudaStream_t stream) {
+    MST_REQUIRE(heads <= 16 && E % heads == 0 && Eenc % 2 == 0, "slice fusion: heads=%d E=%d unsupported", heads, E);
     const int L = D + 1;
     const size_t smem = (static_cast<size_t>(6) * E + 2 * heads * E + 32 + 40 + heads * L) * sizeof(float);
     MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
@@ -580,7 +637,8 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
         MST_CHECK_CUDA(cudaFuncSetAttribute(slice_fusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr = true;
     }
-    slice_fusion_kernel<<<B, 384, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, E, heads, out_ch);
+    slice_fusion_kernel<<<B, 384, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,
+                                                  out_ch, mode);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -590,14 +648,14 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
 // (main_predict.py:161-162: trilinear with depth scale 1 == per-slice bilinear, align_corners=False).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __restrict__ plane_cls, const float* __restrict__ slice_cls,
-                                                                int D, int heads, int sheads, int P,
+                                                                int D, int heads, int sheads, int P, int skip,
                                                                 float* __restrict__ attn_maps, float* __restrict__ plane_attn,
                                                                 float* __restrict__ slice_attn, float* __restrict__ coarse) {
     extern __shared__ float sm[];  // acc[P] | red[40] | wsl[1]
     float* acc = sm;
     float* red = sm + P;
     float* wsl = red + 40;
-    const int s = blockIdx.x, b = s / D, d = s % D, L = D + 1, N = P + 1;
+    const int s = blockIdx.x, b = s / D, d = s % D, L = D + 1, N = P + skip;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     // slice weight: mean over heads of S[b,h,1+d] / sum_j S[b,h,1+j]          (dino.py:174-181)
     if (warp == 0) {
@@ -616,7 +674,7 @@ __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __re
     const float wslice = *wsl;
     (void)nwarps;
     for (int h = 0; h < heads; ++h) {
-        const float* pr = plane_cls + (static_cast<int64_t>(s) * heads + h) * N + 1;  // drop the CLS column (dino.py:192)
+        const float* pr = plane_cls + (static_cast<int64_t>(s) * heads + h) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
         float t = 0.f;
         for (int i = threadIdx.x; i < P; i += blockDim.x) t += (i == 0) ? 0.f : pr[i];  // patch 0 := 0 (dino.py:193)
         const float tot = block_sum(t, red);
@@ -674,12 +732,12 @@ __global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __r
     }
 }
 
-int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int gh,
+int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int skip, int gh,
                     int gw, int H, int W, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full,
                     cudaStream_t stream) {
     const int P = gh * gw, BD = B * D;
     MST_REQUIRE(coarse != nullptr || full == nullptr, "saliency: the full-resolution map needs the coarse buffer");
-    saliency_combine_kernel<<<BD, 256, (P + 48) * sizeof(float), stream>>>(plane_cls, slice_cls, D, heads, slice_heads, P,
+    saliency_combine_kernel<<<BD, 256, (P + 48) * sizeof(float), stream>>>(plane_cls, slice_cls, D, heads, slice_heads, P, skip,
                                                                           attn_maps, plane_attn, slice_attn, coarse);
     MST_CHECK_CUDA(cudaGetLastError());
     if (full) {

@@ -4,9 +4,12 @@ library.  Same constructor arguments, same `state_dict` key layout, same forward
 signatures and error behaviour; the arithmetic runs in libmst_b200.so (hand-written sm_100a
 kernels).  PyTorch is used for device memory, streams and parameter bookkeeping only.
 
-Not mirrored yet (raise NotImplementedError): pretrained hub weights
-(no network), registers, bottleneck, slice position embedding, rotary encodings,
-slice_fusion in {'linear','average'}, get_attention_cls (needs all 12 full maps).
+Constructor variants of dino.py:56-103 are mirrored: use_registers (hub "_reg" architecture, 4 register
+tokens), use_bottleneck, use_slice_pos_emb, slice_fusion in {'transformer','linear','average'},
+enable_linear; `img_size` is the input size `encoder.pos_embed` is built for (224 local factory, 518 hub
+checkpoints) -- other input sizes get the bicubically resampled table (vision_transformer.py:179-211).
+Not mirrored (raise NotImplementedError): pretrained=True (downloads hub weights; offline) and
+rotary_positional_encoding (RoPE / LieRE on the slice tokens, transformer_blocks.py:262-264,333-358).
 """
 import torch
 import torch.nn as nn
@@ -59,12 +62,15 @@ class _Encoder(nn.Module):
     """Key layout of DinoVisionTransformer: local factory (block_chunks=1 => blocks.0.<i>, no LayerScale) or, with
     hub_layout, the torch.hub checkpoints' (blocks.<i>, ls1/ls2.gamma)."""
 
-    def __init__(self, E, depth, heads, pos_tokens, hub_layout=False):
+    def __init__(self, E, depth, heads, pos_tokens, hub_layout=False, num_registers=0):
         super().__init__()
         self.num_features = self.embed_dim = E
         self.num_heads = heads
+        self.num_register_tokens = num_registers
         self.cls_token = nn.Parameter(torch.zeros(1, 1, E))
         self.pos_embed = nn.Parameter(torch.zeros(1, pos_tokens, E))
+        if num_registers:
+            self.register_tokens = nn.Parameter(torch.zeros(1, num_registers, E))
         self.mask_token = nn.Parameter(torch.zeros(1, E))
         self.patch_embed = _PatchEmbed(E)
         self.depth = depth
@@ -105,12 +111,10 @@ class DinoV2ClassifierSlice(nn.Module):
             raise NotImplementedError(
                 "pretrained=True downloads hub weights (dino.py:59-63); this machine is offline. "
                 "Construct with pretrained=False and load a checkpoint with load_state_dict().")
-        for flag, val in (("rotary_positional_encoding", rotary_positional_encoding), ("use_registers", use_registers),
-                          ("use_bottleneck", use_bottleneck), ("use_slice_pos_emb", use_slice_pos_emb)):
-            if val:
-                raise NotImplementedError(f"{flag} is not built yet (SURVEY.md 8f)")
-        if slice_fusion != 'transformer' or not enable_linear:
-            raise NotImplementedError("only slice_fusion='transformer' with the linear head is built (SURVEY.md 8f)")
+        if rotary_positional_encoding is not None:
+            raise NotImplementedError("rotary_positional_encoding (RoPE / LieRE on the slice tokens) is not built (SURVEY.md 8f.3)")
+        if slice_fusion not in _cabi.FUSION:
+            raise ValueError(f"slice_fusion {slice_fusion!r} unsupported")
         if model_size not in synth.VIT_CFG:
             raise ValueError(f"model_size {model_size!r} unsupported")
         if precision not in _cabi.PRECISION:
@@ -126,14 +130,27 @@ class DinoV2ClassifierSlice(nn.Module):
         self.precision = precision
         self.model_size = model_size
         pos_tokens = 1 + (img_size // 14) ** 2
-        self.encoder = _Encoder(E, depth, heads, pos_tokens, hub_layout=hub_layout)
-        self.emb_ch = E
-        self.slice_fusion = _SliceFusion(E, synth.SLICE_HEADS)
-        self.cls_token = nn.Parameter(torch.zeros(1, 1, E))
-        self.linear = nn.Linear(E, out_ch)
+        self.num_registers = 4 if use_registers else 0     # dinov2_vit*14_reg (dino.py:60-61)
+        self.encoder = _Encoder(E, depth, heads, pos_tokens, hub_layout=hub_layout, num_registers=self.num_registers)
+        emb = E
+        if use_bottleneck:                                  # dino.py:75-77
+            self.bottleneck = nn.Linear(E, E // 4)
+            emb = E // 4
+        self.emb_ch = emb
+        self.enable_linear = bool(enable_linear)
+        if slice_fusion == 'transformer':                   # dino.py:80-97
+            if use_slice_pos_emb:
+                self.slice_pos_emb = nn.Embedding(256, emb)
+            self.slice_fusion = _SliceFusion(emb, synth.SLICE_HEADS)
+            self.cls_token = nn.Parameter(torch.zeros(1, 1, emb))
+        head_in = emb * 32 if slice_fusion == 'linear' else emb   # dino.py:98-99
+        self.linear = nn.Linear(head_in, out_ch) if enable_linear else nn.Identity()
         # reference init distributions, drawn from the global torch RNG
         sd = synth.make_state_dict(model_size, out_ch, seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()),
-                                   img_size=img_size, layerscale=hub_layout, chunked_names=not hub_layout)
+                                   img_size=img_size, layerscale=hub_layout, chunked_names=not hub_layout,
+                                   num_registers=self.num_registers, use_bottleneck=use_bottleneck,
+                                   use_slice_pos_emb=use_slice_pos_emb and slice_fusion == 'transformer',
+                                   slice_fusion=slice_fusion, enable_linear=enable_linear)
         nn.Module.load_state_dict(self, sd, strict=True)
         if freeze:
             for p in self.encoder.parameters():
@@ -146,12 +163,13 @@ class DinoV2ClassifierSlice(nn.Module):
         self._copy_stream = None
         self.h2d_chunk_volumes = 8   # host batches larger than this are pipelined H2D || compute
         self._last = None
+        self._last_inputs = None
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_dirty", True))
 
     # -- Lightning-style conveniences the callers use (base_model.py) --------------------------------
     @property
     def device(self):
-        return self.cls_token.device
+        return self.encoder.cls_token.device
 
     def _apply(self, fn, *a, **k):
         r = super()._apply(fn, *a, **k)
@@ -176,12 +194,14 @@ class DinoV2ClassifierSlice(nn.Module):
         if dev.type != "cuda":
             raise MSTError("DinoV2ClassifierSlice runs on a CUDA device only (no CPU fallback): call .cuda() first")
         L = _cabi.lib()
-        E = self.emb_ch
+        E = self.encoder.embed_dim
         key = (dev.index or 0, self.precision, self.encoder.pos_embed.shape[1])
         if self._handle is None or self._handle_key != key:
             self._release()
             cfg = _cabi.MstConfig(E, self.encoder.depth, self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
-                                  self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0])
+                                  self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0],
+                                  self.num_registers, int(hasattr(self, "bottleneck")), int(hasattr(self, "slice_pos_emb")),
+                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear))
             h = _cabi.ctypes.c_void_p()
             _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))
             self._handle, self._handle_key = h, key
@@ -207,8 +227,14 @@ class DinoV2ClassifierSlice(nn.Module):
         assert H % 14 == 0 and W % 14 == 0, \
             f"Input image height {H} / width {W} is not a multiple of patch size 14"   # patch_embed.py:72-73
         L = _cabi.lib()
-        E, heads = self.emb_ch, self.encoder.num_heads
-        N = (H // 14) * (W // 14) + 1
+        E, heads = self.encoder.embed_dim, self.encoder.num_heads
+        N = (H // 14) * (W // 14) + 1 + self.num_registers
+        transformer = self.slice_fusion_type == 'transformer'
+        if save_attn and not transformer:
+            # the reference's register_hooks walks self.slice_fusion.named_modules() (dino.py:257), which does not exist
+            raise AttributeError(f"'{type(self).__name__}' object has no attribute 'slice_fusion'")
+        full_maps = kwargs.get("_full_maps", None)
+        feat_dim = self.emb_ch * D if self.slice_fusion_type == 'linear' else self.emb_ch
         mask = None
         if src_key_padding_mask is not None:               # dino.py:147-150
             mask = src_key_padding_mask.to(dev).to(torch.uint8).contiguous()
@@ -221,10 +247,12 @@ class DinoV2ClassifierSlice(nn.Module):
         if source.device.type == "cpu" and self.h2d_chunk_volumes and B > self.h2d_chunk_volumes:
             chunk = self.h2d_chunk_volumes
         with torch.cuda.device(dev):
-            logits = torch.empty((B, self.out_ch), device=dev, dtype=torch.float32)
-            feat = torch.empty((B, E), device=dev, dtype=torch.float32)
+            logits = torch.empty((B, self.out_ch), device=dev, dtype=torch.float32) if self.enable_linear else None
+            feat = torch.empty((B, feat_dim), device=dev, dtype=torch.float32)
             plane = torch.empty((B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None
             slc = torch.empty((B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
+            if full_maps is not None:
+                chunk = B   # full maps are written for the whole batch in one call
             enc = torch.empty((B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
             need = _cabi.ctypes.c_size_t()
             _cabi.check(L.mst_workspace_bytes(self._handle, chunk, D, H, W, _cabi.ctypes.byref(need)))
@@ -238,7 +266,7 @@ class DinoV2ClassifierSlice(nn.Module):
                 sl = lambda t, per: None if t is None else t[b0 * per:(b0 + nb) * per]
                 _cabi.check(L.mst_forward(self._handle, _cabi.ptr(xc), nb, D, H, W, _cabi.ptr(sl(mask, 1)),
                                           _cabi.ptr(sl(logits, 1)), _cabi.ptr(sl(feat, 1)), _cabi.ptr(sl(enc, D)),
-                                          _cabi.ptr(sl(plane, D)), _cabi.ptr(sl(slc, 1)),
+                                          _cabi.ptr(sl(plane, D)), _cabi.ptr(sl(slc, 1)), _cabi.ptr(full_maps),
                                           _cabi.ptr(self._workspace), self._workspace.numel(), stream))
 
             if chunk == B:
@@ -269,8 +297,10 @@ class DinoV2ClassifierSlice(nn.Module):
             self.attention_maps = [plane.unsqueeze(2)]
             self.attention_maps_slice = [slc.unsqueeze(2)]
             self._last = (B, D, H, W)
+            # get_attention_cls needs every block's full map: recomputed on demand from these (caller-owned) inputs
+            self._last_inputs = (source, src_key_padding_mask)
         self._enc_cls = enc
-        if kwargs.get('without_linear', False):             # dino.py:164-165
+        if kwargs.get('without_linear', False) or not self.enable_linear:   # dino.py:164-165; nn.Identity head (:103)
             return feat
         return logits
 
@@ -302,7 +332,8 @@ class DinoV2ClassifierSlice(nn.Module):
         BD, heads, N = plane.shape
         B, sheads, L = slc.shape
         D = L - 1
-        P = N - 1
+        skip = 1 + self.num_registers                      # dino.py:191
+        P = N - skip
         if self._last is not None and self._last[0] * self._last[1] == BD:
             H, W = self._last[2], self._last[3]
         else:
@@ -318,7 +349,7 @@ class DinoV2ClassifierSlice(nn.Module):
             coarse = torch.empty((B, 1, D, gh, gw), device=dev, dtype=torch.float32) if (want_coarse or want_full) else None
             full = torch.empty((B, 1, D, H, W), device=dev, dtype=torch.float32) if want_full else None
             stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _cabi.check(_cabi.lib().mst_saliency(_cabi.ptr(plane), _cabi.ptr(slc), B, D, heads, sheads, gh, gw, H, W,
+            _cabi.check(_cabi.lib().mst_saliency(_cabi.ptr(plane), _cabi.ptr(slc), B, D, heads, sheads, skip, gh, gw, H, W,
                                                  _cabi.ptr(maps), _cabi.ptr(pl), _cabi.ptr(sl), _cabi.ptr(coarse), _cabi.ptr(full), stream))
         return maps, pl, sl, coarse, full
 
@@ -335,7 +366,43 @@ class DinoV2ClassifierSlice(nn.Module):
         return self._saliency(want_maps=True)[0]
 
     def get_attention_cls(self):
-        raise NotImplementedError("attention rollout needs all 12 full maps (dino.py:204-212); SURVEY.md 8f.3")
+        """Attention rollout over all encoder blocks (dino.py:204-212) -> [B*D, heads, N, N].
+
+        The reference keeps every block's [B*D,heads,N,N] map from the save_attn forward (dino.py:241; 39 GB at
+        256 volumes); here only row 0 of the last one is kept, and the full maps are recomputed on demand from the
+        inputs of the last save_attn forward, then multiplied right to left on the device."""
+        if not self.attention_maps or getattr(self, "_last_inputs", None) is None:
+            raise IndexError("list index out of range")
+        source, mask = self._last_inputs
+        B, D, H, W = self._last
+        heads, depth = self.encoder.num_heads, self.encoder.depth
+        N = (H // 14) * (W // 14) + 1 + self.num_registers
+        dev = self.device
+        need = (depth + 2) * B * D * heads * N * N * 4
+        free = torch.cuda.mem_get_info(dev)[0]
+        if need > free:
+            raise MSTError(f"get_attention_cls needs {need / 2**30:.1f} GiB for {depth} full maps of {B * D} slices "
+                           f"({free / 2**30:.1f} GiB free): call it on a smaller batch")
+        with torch.cuda.device(dev):
+            maps = torch.empty((depth, B * D, heads, N, N), device=dev, dtype=torch.float32)
+            with torch.no_grad():
+                self.forward(source, save_attn=False, src_key_padding_mask=mask, _full_maps=maps)
+            out = torch.empty((B * D, heads, N, N), device=dev, dtype=torch.float32)
+            scratch = torch.empty_like(out)
+            stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _cabi.check(_cabi.lib().mst_rollout(_cabi.ptr(maps), depth, B * D * heads, N, _cabi.ptr(out), _cabi.ptr(scratch), stream))
+        return out
+
+    def interpolated_pos_embed(self, H, W):
+        """`encoder.interpolate_pos_encoding` (vision_transformer.py:179-211) for an H x W input -> [1, 1+P, E]."""
+        if self._dirty or self._handle is None:
+            self.sync_weights()
+        dev = self.device
+        with torch.cuda.device(dev):
+            out = torch.empty((1, 1 + (H // 14) * (W // 14), self.encoder.embed_dim), device=dev, dtype=torch.float32)
+            stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _cabi.check(_cabi.lib().mst_pos_embed(self._handle, H, W, _cabi.ptr(out), stream))
+        return out
 
     def saliency_volume(self, size=None):
         """Batched form of main_predict.py:73-74,93-105,161-162: returns
@@ -343,6 +410,29 @@ class DinoV2ClassifierSlice(nn.Module):
         _, _, sl, coarse, full = self._saliency(want_slice=True, want_full=True, size=size)
         B, _, D = coarse.shape[:3]
         return full, sl.view(B, 1, D, 1, 1)
+
+
+def quantile(x, q):
+    """np.quantile(x[i], q) for every item i of a CUDA fp32 tensor [items, ...] (numpy 'linear' method), on the device:
+    the 0.995/0.999 clip and 0.999 threshold of scripts/main_predict.py:243-245,296.  Returns float64 [items, len(q)]."""
+    if x.device.type != "cuda":
+        raise MSTError("quantile runs on a CUDA tensor only (no CPU fallback)")
+    qs = [float(v) for v in (q if isinstance(q, (list, tuple)) else [q])]
+    if not all(0.0 <= v <= 1.0 for v in qs):
+        raise ValueError("Quantiles must be in the range [0, 1]")   # numpy's message
+    x = x.detach().to(torch.float32).contiguous()
+    items = x.shape[0]
+    n = x.numel() // items
+    L = _cabi.lib()
+    with torch.cuda.device(x.device):
+        qd = torch.tensor(qs, dtype=torch.float64, device=x.device)
+        out = torch.empty((items, len(qs)), dtype=torch.float64, device=x.device)
+        need = _cabi.ctypes.c_size_t()
+        _cabi.check(L.mst_quantile_workspace_bytes(items, len(qs), _cabi.ctypes.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=x.device)
+        stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _cabi.check(L.mst_quantile(_cabi.ptr(x), n, items, _cabi.ptr(qd), len(qs), _cabi.ptr(out), _cabi.ptr(ws), need.value, stream))
+    return out
 
 
 def _pred_trans(model, source, src_key_padding_mask, save_attn=False, use_softmax=True):

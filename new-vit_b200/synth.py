@@ -43,20 +43,33 @@ def _u(g, shape, bound):
 
 
 def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=224,
-                    layerscale=False, chunked_names=True):
+                    layerscale=False, chunked_names=True, num_registers=0, use_bottleneck=False,
+                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True):
     """Return an OrderedDict with the reference's state_dict key layout.
 
     variant: "init"  -- reference-like init distributions
              "peaky" -- same, attention projections scaled up (sharp attention maps)
+    img_size: the input size `encoder.pos_embed` is built for (224 local factory, 518 hub checkpoints).
+    The constructor variants of reference dino.py:56-103 (registers, bottleneck, slice position embedding,
+    slice_fusion, enable_linear) add / drop / resize the corresponding tensors; their values come from a second
+    generator so that the default layout is unchanged by them.
     """
     assert variant in ("init", "peaky")
+    assert slice_fusion in ("transformer", "linear", "average")
     E, depth, _heads = VIT_CFG[model_size]
     g = torch.Generator(device="cpu")
     g.manual_seed(1000003 * seed + {"s": 1, "b": 2, "l": 3}[model_size] + (17 if variant == "peaky" else 0))
+    g2 = torch.Generator(device="cpu")
+    g2.manual_seed(7 + 1000003 * seed)
     npatch = (img_size // PATCH) ** 2
     sd = OrderedDict()
-    sd["cls_token"] = _n(g, (1, 1, E), 1.0)
+    Es = E // 4 if use_bottleneck else E
+    cls_slice = _n(g, (1, 1, E), 1.0)[..., :Es].contiguous()
+    if slice_fusion == "transformer":
+        sd["cls_token"] = cls_slice
     sd["encoder.cls_token"] = _n(g, (1, 1, E), 0.02)
+    if num_registers:
+        sd["encoder.register_tokens"] = _n(g2, (1, num_registers, E), 0.02)
     sd["encoder.pos_embed"] = _tn(g, (1, 1 + npatch, E), 0.02)
     sd["encoder.mask_token"] = torch.zeros(1, E)
     fan_in = 3 * PATCH * PATCH
@@ -85,6 +98,18 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
             sd[p + "ls2.gamma"] = 1.0 + _n(g, (E,), 0.1)
     sd["encoder.norm.weight"] = 1.0 + _n(g, (E,), 0.05)
     sd["encoder.norm.bias"] = _n(g, (E,), 0.02)
+    if use_bottleneck:
+        sd["bottleneck.weight"] = _u(g2, (Es, E), (1.0 / E) ** 0.5)
+        sd["bottleneck.bias"] = _u(g2, (Es,), (1.0 / E) ** 0.5)
+    enc_E, E = E, Es   # everything below lives in the slice embedding
+    if slice_fusion != "transformer":
+        if enable_linear:
+            fin = E * 32 if slice_fusion == "linear" else E
+            sd["linear.weight"] = _u(g2, (out_ch, fin), (1.0 / fin) ** 0.5)
+            sd["linear.bias"] = _u(g2, (out_ch,), (1.0 / fin) ** 0.5)
+        return sd
+    if use_slice_pos_emb:
+        sd["slice_pos_emb.weight"] = _n(g2, (256, E), 1.0)
     q = "slice_fusion.layers.0."
     xav = (6.0 / (E + 3 * E)) ** 0.5
     w = _u(g, (3 * E, E), xav)
@@ -105,8 +130,9 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
     sd[q + "norm2.bias"] = _n(g, (E,), 0.02)
     sd["slice_fusion.norm.weight"] = 1.0 + _n(g, (E,), 0.05)
     sd["slice_fusion.norm.bias"] = _n(g, (E,), 0.02)
-    sd["linear.weight"] = _u(g, (out_ch, E), lin)
-    sd["linear.bias"] = _u(g, (out_ch,), lin)
+    if enable_linear:
+        sd["linear.weight"] = _u(g, (out_ch, E), lin)
+        sd["linear.bias"] = _u(g, (out_ch,), lin)
     return sd
 
 

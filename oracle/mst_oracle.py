@@ -87,7 +87,10 @@ def encoder_forward(sd, img, heads, keep_all_maps=False):
     x = x.flatten(2).transpose(1, 2)
     # vision_transformer.py:219-220
     x = torch.cat((sd["encoder.cls_token"].expand(BD, -1, -1), x), dim=1)
-    x = x + interpolate_pos_encoding(sd["encoder.pos_embed"], x.shape[1] - 1, W, H)
+    # (the reference names the image dims "w, h = x.shape[2:]": its w is the height)
+    x = x + interpolate_pos_encoding(sd["encoder.pos_embed"], x.shape[1] - 1, H, W)
+    if "encoder.register_tokens" in sd:  # vision_transformer.py:222-230: registers go in AFTER the position add
+        x = torch.cat((x[:, :1], sd["encoder.register_tokens"].expand(BD, -1, -1), x[:, 1:]), dim=1)
     maps = []
     depth = encoder_depth(sd)
     for i in range(depth):
@@ -110,7 +113,7 @@ def encoder_forward(sd, img, heads, keep_all_maps=False):
     return x[:, 0], maps
 
 
-def slice_transformer(sd, x, key_padding_mask, heads=12):
+def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
     """nn.TransformerEncoder(num_layers=1, norm) over the custom pre-LN layer
     (utils/transformer_blocks.py:524-573, 29-318; dino.py:84-96).  Explicit bmm/softmax path
     (`:266-295`), which the reference takes when save_attn=True; the SDPA path differs by ~2e-7.
@@ -141,12 +144,13 @@ def slice_transformer(sd, x, key_padding_mask, heads=12):
 
 
 @torch.no_grad()
-def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps=False):
-    """DinoV2ClassifierSlice.forward (dino.py:110-167), default configuration
-    (slice_fusion='transformer', no bottleneck, no slice pos-emb, no rotary).
+def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps=False, slice_fusion="transformer"):
+    """DinoV2ClassifierSlice.forward (dino.py:110-167).  The constructor variants are read off the state_dict
+    (bottleneck.*, slice_pos_emb.weight, encoder.register_tokens, linear.* present or not); `slice_fusion`
+    selects dino.py:144-157.  Rotary encodings are not restated.
 
-    Returns a dict: logits [B,out], feat [B,E], enc_cls [BD,E], plane_cls [BD,heads,N] (row 0 of
-    the last encoder block's attention), slice_cls [B,12,L] (row 0 of slice attention), and the
+    Returns a dict: logits [B,out] (None without the linear head), feat, enc_cls [BD,E], plane_cls [BD,heads,N]
+    (row 0 of the last encoder block's attention), slice_cls [B,12,L] (row 0 of slice attention), and the
     full maps under 'maps' / 'maps_slice' as the reference stores them (dino.py:241,249)."""
     sd = {k: v.float() for k, v in sd.items()}
     B, C, D, H, W = source.shape
@@ -157,14 +161,24 @@ def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps
     x = source.float().permute(0, 2, 1, 3, 4).reshape(B * D * C, H, W)  # dino.py:125
     x = x[:, None].repeat(1, 3, 1, 1)                                    # dino.py:126-127
     enc_cls, maps = encoder_forward(sd, x, enc_heads, keep_all_maps)     # dino.py:131
-    x = enc_cls.reshape(B, D, E)                                         # dino.py:138
+    x = enc_cls
+    if "bottleneck.weight" in sd:                                        # dino.py:134-135
+        x = F.linear(x, sd["bottleneck.weight"], sd["bottleneck.bias"])
+    x = x.reshape(B, D, -1)                                              # dino.py:138
+    if "slice_pos_emb.weight" in sd:                                     # dino.py:140-142
+        x = x + sd["slice_pos_emb.weight"][:D]
+    if slice_fusion != "transformer":
+        feat = x.reshape(B, -1) if slice_fusion == "linear" else x.mean(dim=1)   # dino.py:154-157
+        logits = F.linear(feat, sd["linear.weight"], sd["linear.bias"]) if "linear.weight" in sd else None
+        return {"logits": logits, "feat": feat, "enc_cls": enc_cls, "plane_cls": maps[-1][:, :, 0, :].clone(),
+                "slice_cls": None, "maps": maps, "maps_slice": []}
     x = torch.cat([sd["cls_token"].repeat(B, 1, 1), x], dim=1)           # dino.py:145
     kpm = None
     if src_key_padding_mask is not None:                                 # dino.py:147-150
         kpm = torch.cat([torch.zeros((B, 1), dtype=torch.bool), src_key_padding_mask.bool()], dim=1)
     x, w = slice_transformer(sd, x, kpm)                                 # dino.py:152
     feat = x[:, 0]                                                       # dino.py:153
-    logits = F.linear(feat, sd["linear.weight"], sd["linear.bias"])      # dino.py:166
+    logits = F.linear(feat, sd["linear.weight"], sd["linear.bias"]) if "linear.weight" in sd else None  # dino.py:166,103
     return {
         "logits": logits, "feat": feat, "enc_cls": enc_cls,
         "plane_cls": maps[-1][:, :, 0, :].clone(), "slice_cls": w[:, :, 0, :].clone(),
@@ -172,9 +186,9 @@ def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps
     }
 
 
-def get_plane_attention(plane_cls):
-    """dino.py:189-195 on the CLS row [BD,heads,N]: drop CLS column, zero patch 0, renormalise."""
-    a = plane_cls[:, :, 1:].clone()
+def get_plane_attention(plane_cls, num_registers=0):
+    """dino.py:189-195 on the CLS row [BD,heads,N]: drop CLS (+ register) columns, zero patch 0, renormalise."""
+    a = plane_cls[:, :, 1 + num_registers:].clone()
     a[:, :, 0] = 0
     a = a / a.sum(dim=-1, keepdim=True)
     return a
@@ -188,9 +202,16 @@ def get_slice_attention(slice_cls):
     return s.reshape(-1)[:, None, None]
 
 
-def get_attention_maps(plane_cls, slice_cls):
+def get_attention_maps(plane_cls, slice_cls, num_registers=0):
     """dino.py:197-202 -> [BD,heads,P]."""
-    return get_slice_attention(slice_cls) * get_plane_attention(plane_cls)
+    return get_slice_attention(slice_cls) * get_plane_attention(plane_cls, num_registers)
+
+
+def quantile(x, q):
+    """np.quantile as scripts/main_predict.py:243-245,296 calls it (default 'linear' method), per item of [items, ...]."""
+    import numpy as np
+    a = x.detach().cpu().numpy().reshape(x.shape[0], -1)
+    return torch.from_numpy(np.stack([np.quantile(r, list(q)) for r in a]))
 
 
 def get_attention_cls(maps):
@@ -201,13 +222,16 @@ def get_attention_cls(maps):
     return a
 
 
-def saliency(plane_cls, slice_cls, B, D, H, W):
+def saliency(plane_cls, slice_cls, B, D, H, W, num_registers=0):
     """scripts/main_predict.py:70-105,161-162 generalised from B=1 to a batch:
     head-mean of get_attention_maps -> [B,1,D,g,g] -> trilinear upsample to [B,1,D,H,W];
     slice weights broadcast to the source shape.  Returns (coarse, full, weight_slice)."""
-    w = get_attention_maps(plane_cls, slice_cls).mean(dim=1)  # main_predict.py:73-74
-    g = int(w.shape[-1] ** 0.5)                                # main_predict.py:93-94
-    coarse = w.reshape(B, 1, D, g, g)                          # main_predict.py:100 (B=1 there)
+    w = get_attention_maps(plane_cls, slice_cls, num_registers).mean(dim=1)  # main_predict.py:73-74
+    if H == W:
+        g = int(w.shape[-1] ** 0.5)                            # main_predict.py:93-94 (assumes a square patch grid)
+        coarse = w.reshape(B, 1, D, g, g)                      # main_predict.py:100 (B=1 there)
+    else:
+        coarse = w.reshape(B, 1, D, H // PATCH, W // PATCH)
     full = F.interpolate(coarse, size=(D, H, W), mode="trilinear")  # main_predict.py:161-162
     ws = get_slice_attention(slice_cls).mean(dim=1)            # main_predict.py:103-104
     ws = ws.reshape(B, 1, D, 1, 1).expand(B, 1, D, H, W)
@@ -217,13 +241,12 @@ def saliency(plane_cls, slice_cls, B, D, H, W):
 def bilinear14_reference(coarse, H, W):
     """with depth scale 1 the trilinear upsample equals per-slice bilinear with
     align_corners=False; plain-loop restatement used to pin the CUDA kernel's index math."""
-    B, _, D, g, _ = coarse.shape
-    out = torch.empty(B, 1, D, H, W, dtype=coarse.dtype)
-    sy_scale, sx_scale = g / H, g / W
+    B, _, D, gh, gw = coarse.shape
+    sy_scale, sx_scale = gh / H, gw / W
     ys = ((torch.arange(H, dtype=torch.float32) + 0.5) * sy_scale - 0.5).clamp(min=0)
     xs = ((torch.arange(W, dtype=torch.float32) + 0.5) * sx_scale - 0.5).clamp(min=0)
     y0 = ys.floor().long(); x0 = xs.floor().long()
-    y1 = (y0 + 1).clamp(max=g - 1); x1 = (x0 + 1).clamp(max=g - 1)
+    y1 = (y0 + 1).clamp(max=gh - 1); x1 = (x0 + 1).clamp(max=gw - 1)
     ly = (ys - y0).view(1, 1, 1, H, 1); lx = (xs - x0).view(1, 1, 1, 1, W)
     v00 = coarse[..., y0, :][..., x0]; v01 = coarse[..., y0, :][..., x1]
     v10 = coarse[..., y1, :][..., x0]; v11 = coarse[..., y1, :][..., x1]

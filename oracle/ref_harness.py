@@ -102,16 +102,21 @@ def load_reference_class():
     return DinoV2ClassifierSlice
 
 
-def build_reference_model(state_dict=None, out_ch=2, model_size="s", hub_layout=False, **kw):
+def build_reference_model(state_dict=None, out_ch=2, model_size="s", hub_layout=False, num_registers=0,
+                          pos_img_size=None, **kw):
     """`hub_layout=True` swaps in the encoder configuration of the torch.hub DINOv2 checkpoints that
     `pretrained=True` would download (dino.py:59-63): LayerScale (init_values=1.0) and un-chunked block names
-    (block_chunks=0), built from the reference's own vendored factory (vision_transformer.py:340-352)."""
+    (block_chunks=0), built from the reference's own vendored factory (vision_transformer.py:340-352);
+    `num_registers=4` is the "_reg" hub architecture (dino.py:60-61) and `pos_img_size=518` the hub checkpoints'
+    position-embedding size.  Other keyword arguments go to the reference constructor unchanged
+    (use_bottleneck, use_slice_pos_emb, slice_fusion, enable_linear)."""
     Cls = load_reference_class()
-    model = Cls(in_ch=1, out_ch=out_ch, pretrained=False, model_size=model_size, **kw).eval()
-    if hub_layout:
+    model = Cls(in_ch=1, out_ch=out_ch, pretrained=False, model_size=model_size, use_registers=num_registers > 0, **kw).eval()
+    if hub_layout or num_registers or pos_img_size:
         from mst.models.extern.dinov2 import vision_transformer as vits
         factory = {"s": vits.vit_small, "b": vits.vit_base, "l": vits.vit_large}[model_size]
-        model.encoder = factory(patch_size=14, img_size=224, init_values=1.0, block_chunks=0, num_register_tokens=0).eval()
+        extra = dict(init_values=1.0, block_chunks=0) if hub_layout else {}
+        model.encoder = factory(patch_size=14, img_size=pos_img_size or 224, num_register_tokens=num_registers, **extra).eval()
     if state_dict is not None:
         pe = state_dict["encoder.pos_embed"]
         if tuple(pe.shape) != tuple(model.encoder.pos_embed.shape):

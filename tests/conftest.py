@@ -22,14 +22,27 @@ def load_golden(name):
     return meta, {k: torch.from_numpy(z[k]) for k in z.files if k != "meta"}
 
 
+CTOR_KEYS = ("use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear")
+
+
 def case_inputs(meta, out_ch=2):
     from new_vit_b200 import synth
     hub = bool(meta.get("hub_layout", False))
+    ctor = {k: meta[k] for k in CTOR_KEYS if k in meta}
     sd = synth.make_state_dict(meta["size"], out_ch=out_ch, seed=meta["wseed"], variant=meta["variant"],
-                               img_size=meta["H"], layerscale=hub, chunked_names=not hub)
+                               img_size=meta.get("pos_img", meta["H"]), layerscale=hub, chunked_names=not hub,
+                               num_registers=meta.get("num_registers", 0), **ctor)
     x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
     mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"]) if meta["masked"] else None
     return sd, x, mask
+
+
+def model_kwargs(meta):
+    """Constructor arguments of new_vit_b200.DinoV2ClassifierSlice for a golden case."""
+    kw = {k: meta[k] for k in CTOR_KEYS if k in meta}
+    kw.update(model_size=meta["size"], img_size=meta.get("pos_img", meta["H"]), hub_layout=bool(meta.get("hub_layout", False)),
+              use_registers=meta.get("num_registers", 0) > 0)
+    return kw
 
 
 @pytest.fixture(scope="session")

@@ -36,6 +36,14 @@ CASES = {
     "b_peaky_252_mask_b2": ("b", "peaky", 2, 3, 252, 252, True, 4, 4),
     # hub-checkpoint layout: LayerScale gammas + "encoder.blocks.<i>" key names
     "s_hub_layerscale_b1": ("s", "peaky", 1, 4, 224, 224, False, 5, 5, {"hub_layout": True}),
+    # ---- SURVEY 8f.2/8f.3 rows (flags: see run_case) ----
+    # the hub "_reg" architecture: 4 register tokens, LayerScale, pos_embed built for 518 (37x37) resampled to 16x16
+    "s_hub_reg518_b1": ("s", "peaky", 1, 3, 224, 224, False, 6, 6, {"hub_layout": True, "num_registers": 4, "pos_img": 518}),
+    # local factory (pos_embed 16x16) on a non-square 126x168 input: bicubic resampling to 9x12
+    "s_interp_126x168_b2": ("s", "peaky", 2, 3, 126, 168, True, 7, 7, {"pos_img": 224}),
+    "s_bottleneck_posemb_b2": ("s", "peaky", 2, 5, 112, 112, True, 8, 8, {"use_bottleneck": True, "use_slice_pos_emb": True}),
+    "s_fusion_linear_b2": ("s", "init", 2, 32, 56, 56, False, 9, 9, {"slice_fusion": "linear"}),
+    "s_fusion_average_nolinear_b2": ("s", "init", 2, 6, 56, 56, False, 10, 10, {"slice_fusion": "average", "enable_linear": False}),
 }
 
 
@@ -43,41 +51,56 @@ def run_case(name):
     size, variant, B, D, H, W, masked, wseed, vseed = CASES[name][:9]
     flags = CASES[name][9] if len(CASES[name]) > 9 else {}
     hub = bool(flags.get("hub_layout", False))
-    sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=H, layerscale=hub, chunked_names=not hub)
-    model = build_reference_model(sd, out_ch=2, model_size=size, hub_layout=hub)
+    nreg = int(flags.get("num_registers", 0))
+    pos_img = int(flags.get("pos_img", H))
+    fusion = flags.get("slice_fusion", "transformer")
+    ctor = {k: flags[k] for k in ("use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear") if k in flags}
+    sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=pos_img, layerscale=hub,
+                               chunked_names=not hub, num_registers=nreg, **ctor)
+    model = build_reference_model(sd, out_ch=2, model_size=size, hub_layout=hub, num_registers=nreg,
+                                  pos_img_size=pos_img if pos_img != H or nreg else None, **ctor)
     x = synth.make_volume(B, D, H, W, seed=vseed)
     mask = synth.make_padding_mask(B, D, seed=vseed) if masked else None
     out = {}
     with torch.no_grad():
         out["logits_nosave"] = model(x, src_key_padding_mask=mask, save_attn=False)
         out["feat"] = model(x, src_key_padding_mask=mask, save_attn=False, without_linear=True)
-        out["logits"] = model(x, src_key_padding_mask=mask, save_attn=True)
-        out["plane_cls"] = model.attention_maps[-1][:, :, 0, :].clone()
-        out["slice_cls"] = model.attention_maps_slice[-1][:, :, 0, :].clone()
-        out["attn_maps"] = model.get_attention_maps().clone()
-        out["slice_attn"] = model.get_slice_attention().clone()
-        # encoder CLS features: run the encoder alone
         xs = x.permute(0, 2, 1, 3, 4).reshape(B * D, H, W)[:, None].repeat(1, 3, 1, 1)
         out["enc_cls"] = model.encoder(xs)
-        # saliency exactly as scripts/main_predict.py does it, one volume at a time
-        subs = []
-        for b in range(B):
-            xb = x[b:b + 1]
-            mb = None if mask is None else mask[b:b + 1]
-            model(xb, src_key_padding_mask=mb, save_attn=True)
-            w = model.get_attention_maps()
-            w = w.mean(dim=1)
-            g = int(w.shape[-1] ** 0.5)
-            w = w.view(1, 1, D, g, g)
-            w = F.interpolate(w, size=xb.shape[2:], mode="trilinear")
-            subs.append(w[0, 0, :, ::7, ::7].clone())
-            if b == 0:
-                out["sal_sum_b0"] = w.double().sum().float().reshape(1)
-        out["sal_sub"] = torch.stack(subs)
-    meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed, hub_layout=hub)
+        if pos_img != H or H != W:
+            out["pos_embed"] = model.encoder.interpolate_pos_encoding(torch.zeros(1, 1 + (H // 14) * (W // 14), sd["encoder.pos_embed"].shape[-1]), H, W)
+        if fusion == "transformer":
+            out["logits"] = model(x, src_key_padding_mask=mask, save_attn=True)
+            out["plane_cls"] = model.attention_maps[-1][:, :, 0, :].clone()
+            out["slice_cls"] = model.attention_maps_slice[-1][:, :, 0, :].clone()
+            if "rollout" in flags or nreg or name == "s_init_small":
+                out["rollout_cls"] = model.get_attention_cls()[:, :, 0, :].clone()   # row 0 of the rollout product
+            out["attn_maps"] = model.get_attention_maps().clone()
+            out["slice_attn"] = model.get_slice_attention().clone()
+            # saliency exactly as scripts/main_predict.py does it, one volume at a time
+            subs = []
+            for b in range(B):
+                xb = x[b:b + 1]
+                mb = None if mask is None else mask[b:b + 1]
+                model(xb, src_key_padding_mask=mb, save_attn=True)
+                w = model.get_attention_maps()
+                w = w.mean(dim=1)
+                if H == W:
+                    g = int(w.shape[-1] ** 0.5)           # main_predict.py:93-94 assumes a square grid
+                    w = w.view(1, 1, D, g, g)
+                else:
+                    w = w.view(1, 1, D, H // 14, W // 14)
+                w = F.interpolate(w, size=xb.shape[2:], mode="trilinear")
+                subs.append(w[0, 0, :, ::7, ::7].clone())
+                if b == 0:
+                    out["sal_sum_b0"] = w.double().sum().float().reshape(1)
+                    out["sal_quantiles_b0"] = torch.from_numpy(np.quantile(w.numpy(), [0.5, 0.995, 0.999]))
+            out["sal_sub"] = torch.stack(subs)
+    meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed, hub_layout=hub,
+                num_registers=nreg, pos_img=pos_img, **ctor)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
                         meta=np.array(repr(meta)), **{k: v.numpy() for k, v in out.items()})
-    print(name, "logits", out["logits"].tolist())
+    print(name, "logits", out["logits_nosave"].tolist()[:2])
 
 
 if __name__ == "__main__":

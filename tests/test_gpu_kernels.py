@@ -156,7 +156,7 @@ def test_saliency_upsample_matches_trilinear():
     sl = torch.empty(B * D, device="cuda")
     coarse = torch.empty(B, 1, D, g, g, device="cuda")
     full = torch.empty(B, 1, D, H, W, device="cuda")
-    cabi.check(L.mst_saliency(cabi.ptr(plane), cabi.ptr(slc), B, D, heads, sheads, g, g, H, W, cabi.ptr(maps), cabi.ptr(pl),
+    cabi.check(L.mst_saliency(cabi.ptr(plane), cabi.ptr(slc), B, D, heads, sheads, 1, g, g, H, W, cabi.ptr(maps), cabi.ptr(pl),
                               cabi.ptr(sl), cabi.ptr(coarse), cabi.ptr(full), _stream()))
     torch.cuda.synchronize()
     from oracle import mst_oracle as O
@@ -169,3 +169,36 @@ def test_saliency_upsample_matches_trilinear():
     torch.testing.assert_close(full.cpu(), rf, rtol=1e-5, atol=float(rf.max()) * 1e-6)
     # indexing is bit-exact: same argmax voxel
     assert torch.equal(full.cpu().reshape(B, -1).argmax(-1), rf.reshape(B, -1).argmax(-1))
+
+
+@pytest.mark.parametrize("n,items", [(1, 1), (2, 3), (1000, 2), (224 * 224 * 8 + 3, 2)])
+def test_quantile_matches_numpy_bit_exact(n, items):
+    """np.quantile (numpy 'linear' method; scripts/main_predict.py:243-245,296): radix select + numpy's own lerp arithmetic.
+    Ties, negatives, zeros of both signs and the q = 0 / 1 ends included."""
+    import numpy as np
+    from new_vit_b200.model import quantile
+    g = torch.Generator().manual_seed(n)
+    x = torch.randn(items, n, generator=g)
+    x[:, ::7] = x[:, :1]            # ties
+    if n > 4:
+        x[0, 1], x[0, 2] = 0.0, -0.0
+    qs = [0.0, 0.25, 0.5, 0.995, 0.999, 1.0]
+    got = quantile(x.cuda(), qs).cpu().numpy()
+    want = np.stack([np.quantile(r, qs) for r in x.numpy()])
+    assert got.shape == want.shape and np.array_equal(got, want), (got, want)
+
+
+def test_rollout_matches_matmul_chain():
+    """get_attention_cls (dino.py:204-212): R = maps[-1]; for attn in reversed(maps[:-1]): R = attn @ R."""
+    cabi, L = _lib()
+    depth, nmat, N = 5, 7, 67   # N not a multiple of the 64-wide tile
+    maps = torch.rand(depth, nmat, N, N, device="cuda")
+    maps = maps / maps.sum(-1, keepdim=True)
+    out, scratch = torch.empty(nmat, N, N, device="cuda"), torch.empty(nmat, N, N, device="cuda")
+    for d in (depth, 2, 1):
+        cabi.check(L.mst_rollout(cabi.ptr(maps), d, nmat, N, cabi.ptr(out), cabi.ptr(scratch), _stream()))
+        torch.cuda.synchronize()
+        ref = maps[d - 1].double().cpu()
+        for l in range(d - 2, -1, -1):
+            ref = maps[l].double().cpu() @ ref
+        torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-8)

@@ -8,20 +8,29 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import case_inputs, load_golden
+from conftest import case_inputs, load_golden, model_kwargs
 
 pytestmark = pytest.mark.gpu
 
 GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2",
-           "s_hub_layerscale_b1"]
+           "s_hub_layerscale_b1",
+           # hub "_reg" architecture (registers + 518 pos_embed resampled), non-square input through the
+           # bicubic pos_embed path, bottleneck + slice position embedding
+           "s_hub_reg518_b1", "s_interp_126x168_b2", "s_bottleneck_posemb_b2"]
+OTHER_FUSIONS = ["s_fusion_linear_b2", "s_fusion_average_nolinear_b2"]
 
 
-def _model(sd, precision, img_size, size="s", hub_layout=False):
+def _model(sd, precision, img_size, size="s", hub_layout=False, **kw):
     from new_vit_b200 import DinoV2ClassifierSlice
-    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=precision, img_size=img_size, model_size=size,
-                              hub_layout=hub_layout).cuda().eval()
+    args = dict(pretrained=False, precision=precision, img_size=img_size, model_size=size, hub_layout=hub_layout)
+    args.update(kw)
+    m = DinoV2ClassifierSlice(1, 2, **args).cuda().eval()
     m.load_state_dict(sd)
     return m
+
+
+def _model_for(meta, sd, precision):
+    return _model(sd, precision, **{("size" if k == "model_size" else k): v for k, v in model_kwargs(meta).items()})
 
 
 def _cos(a, b):
@@ -47,7 +56,8 @@ def _run(m, x, mask):
 def test_fp32_matches_reference_golden(name):
     meta, g = load_golden(name)
     sd, x, mask = case_inputs(meta)
-    r = _run(_model(sd, "fp32", meta["H"], meta["size"], meta.get("hub_layout", False)), x, mask)
+    m = _model_for(meta, sd, "fp32")
+    r = _run(m, x, mask)
     B = meta["B"]
     scale = g["logits"].abs().max().item()
     assert (r["logits"] - g["logits"]).abs().max().item() <= 1e-4 * max(scale, 1.0), (r["logits"], g["logits"])
@@ -64,13 +74,55 @@ def test_fp32_matches_reference_golden(name):
     torch.testing.assert_close(r["full"][:, 0, :, ::7, ::7], g["sal_sub"], rtol=3e-4, atol=float(g["sal_sub"].max()) * 1e-5)
     if meta["masked"]:
         assert (r["slice_attn"].reshape(B, -1)[mask] == 0).all()  # masked slices get exactly zero attention
+    H, W = meta["H"], meta["W"]
+    if "pos_embed" in g:       # interpolate_pos_encoding: bicubic resampling of the checkpoint's table
+        torch.testing.assert_close(m.interpolated_pos_embed(H, W).cpu(), g["pos_embed"], rtol=1e-5, atol=2e-6)
+    if "rollout_cls" in g:     # get_attention_cls (dino.py:204-212): row 0 of the 12-map product
+        with torch.no_grad():
+            m(x, save_attn=True, src_key_padding_mask=mask)
+            roll = m.get_attention_cls()
+        N = g["rollout_cls"].shape[-1]
+        assert tuple(roll.shape) == (B * meta["D"], g["rollout_cls"].shape[1], N, N)
+        torch.testing.assert_close(roll[:, :, 0, :].cpu(), g["rollout_cls"], rtol=5e-4, atol=1e-8)
+        torch.testing.assert_close(roll.sum(-1).cpu(), torch.ones(roll.shape[:3]), rtol=1e-4, atol=1e-4)  # rows stay stochastic
+    if "sal_quantiles_b0" in g:  # np.quantile(weight, [..]) of the upsampled volume (main_predict.py:243-245,296)
+        from new_vit_b200.model import quantile
+        with torch.no_grad():
+            m(x[:1], save_attn=True, src_key_padding_mask=None if mask is None else mask[:1])
+            w0, _ = m.saliency_volume()
+        qv = quantile(w0, [0.5, 0.995, 0.999]).cpu()[0]
+        torch.testing.assert_close(qv, g["sal_quantiles_b0"], rtol=3e-4, atol=0)
+        # against numpy on OUR volume the selection is exact and the blend follows numpy's own arithmetic: bit-equal
+        import numpy as np
+        assert np.array_equal(qv.numpy(), np.quantile(w0.cpu().numpy(), [0.5, 0.995, 0.999]))
+
+
+@pytest.mark.parametrize("name", OTHER_FUSIONS)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_other_slice_fusions_match_reference_golden(name, precision):
+    """slice_fusion='linear' / 'average' (dino.py:154-157) and the nn.Identity head (enable_linear=False, dino.py:103)."""
+    meta, g = load_golden(name)
+    sd, x, mask = case_inputs(meta)
+    m = _model_for(meta, sd, precision)
+    with torch.no_grad():
+        y = m(x, src_key_padding_mask=mask).cpu()
+        feat = m(x, src_key_padding_mask=mask, without_linear=True).cpu()
+    assert y.shape == g["logits_nosave"].shape and feat.shape == g["feat"].shape
+    if precision == "fp32":
+        torch.testing.assert_close(y, g["logits_nosave"], rtol=1e-4, atol=2e-4)
+        torch.testing.assert_close(feat, g["feat"], rtol=1e-4, atol=2e-4)
+    else:
+        assert (y - g["logits_nosave"]).abs().max().item() <= 2e-2
+        assert (feat - g["feat"]).abs().max().item() <= 3e-2
+    with pytest.raises(AttributeError):   # the reference's register_hooks needs self.slice_fusion (dino.py:257)
+        m(x, save_attn=True)
 
 
 @pytest.mark.parametrize("name", GOLDENS)
 def test_bf16_matches_reference_golden(name):
     meta, g = load_golden(name)
     sd, x, mask = case_inputs(meta)
-    r = _run(_model(sd, "bf16", meta["H"], meta["size"], meta.get("hub_layout", False)), x, mask)
+    r = _run(_model_for(meta, sd, "bf16"), x, mask)
     B = meta["B"]
     err = (r["logits"] - g["logits"]).abs().max().item()
     assert err <= 2e-2, f"bf16 logits differ by {err}: {r['logits']} vs {g['logits']}"

@@ -14,7 +14,7 @@ def test_library_loads_and_exports_all_declared_symbols():
     assert len(names) >= 14 and "mst_forward" in names and "mst_saliency" in names
     for n in names:
         assert hasattr(L, n), n
-    assert L.mst_abi_version() == 1
+    assert L.mst_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -22,7 +22,7 @@ def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     L = _cabi.lib()
-    cfg = _cabi.MstConfig(384, 12, 6, 12, 2, 257, 1, 0)
+    cfg = _cabi.MstConfig(384, 12, 6, 12, 2, 257, 1, 0, 0, 0, 0, 0, 1)
     h = ctypes.c_void_p()
     assert L.mst_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
     assert b"no CUDA device" in L.mst_last_error()
@@ -53,12 +53,41 @@ def test_state_dict_layout_matches_reference():
 
 def test_unbuilt_options_raise():
     from new_vit_b200 import DinoV2ClassifierSlice
-    for kw in (dict(pretrained=True), dict(use_bottleneck=True), dict(slice_fusion="average"),
-               dict(rotary_positional_encoding="RoPE"), dict(use_slice_pos_emb=True), dict(use_registers=True)):
+    for kw in (dict(pretrained=True), dict(rotary_positional_encoding="RoPE")):
         args = dict(in_ch=1, out_ch=2, pretrained=False)
         args.update(kw)
         with pytest.raises(NotImplementedError):
             DinoV2ClassifierSlice(**args)
+    with pytest.raises(ValueError):
+        DinoV2ClassifierSlice(1, 2, pretrained=False, slice_fusion="max")
+
+
+@pytest.mark.parametrize("kw", [dict(use_bottleneck=True), dict(use_slice_pos_emb=True), dict(slice_fusion="linear"),
+                                dict(slice_fusion="average", enable_linear=False), dict(use_bottleneck=True, slice_fusion="linear")])
+def test_constructor_variants_keep_the_reference_state_dict_layout(kw):
+    """dino.py:75-103: bottleneck, slice position embedding, slice_fusion, enable_linear add / drop / resize tensors."""
+    from new_vit_b200 import DinoV2ClassifierSlice
+    from oracle import ref_harness
+    m = DinoV2ClassifierSlice(in_ch=1, out_ch=3, pretrained=False, **kw)
+    sd = m.state_dict()
+    syn = synth.make_state_dict("s", 3, seed=1, **kw)
+    assert sorted(sd.keys()) == sorted(syn.keys())
+    assert all(tuple(sd[k].shape) == tuple(syn[k].shape) for k in sd)
+    if ref_harness.reference_available():
+        real = ref_harness.build_reference_model(out_ch=3, **kw)
+        rsd = real.state_dict()
+        assert sorted(rsd.keys()) == sorted(sd.keys())
+        assert all(tuple(rsd[k].shape) == tuple(sd[k].shape) for k in sd)
+        assert real.emb_ch == m.emb_ch
+
+
+def test_register_architecture_layout():
+    from new_vit_b200 import DinoV2ClassifierSlice
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, use_registers=True, hub_layout=True, img_size=518)
+    sd = m.state_dict()
+    assert tuple(sd["encoder.register_tokens"].shape) == (1, 4, 384)
+    assert tuple(sd["encoder.pos_embed"].shape) == (1, 1370, 384)      # hub checkpoints: 37 x 37 grid @518
+    assert "encoder.blocks.11.ls2.gamma" in sd and "encoder.blocks.0.0.norm1.weight" not in sd
 
 
 def test_synth_is_deterministic():
