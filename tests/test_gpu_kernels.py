@@ -179,7 +179,7 @@ def test_quantile_matches_numpy_bit_exact(n, items):
     from new_vit_b200.model import quantile
     g = torch.Generator().manual_seed(n)
     x = torch.randn(items, n, generator=g)
-    x[:, ::7] = x[:, :1]            # ties
+    x[:, ::7] = x[:, :1].clone()    # ties
     if n > 4:
         x[0, 1], x[0, 2] = 0.0, -0.0
     qs = [0.0, 0.25, 0.5, 0.995, 0.999, 1.0]
