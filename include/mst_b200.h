@@ -126,6 +126,13 @@ MST_API int mst_profile_end(mst_handle h, double* ms, int64_t* launches, int32_t
  * mode: 0 bias, 1 bias+GELU(erf), 2 bias+residual.  A [M,K], W [N,K] (nn.Linear layout), out/res [M,N]. */
 MST_API int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode,
                          const float* bias, const void* res, void* out, void* stream);
+/* LayerNorm folded into the GEMM that consumes it (bf16 path; norm1 -> qkv, norm2 -> fc1; block.py:112-113):
+ * A holds RAW rows; W rows are gamma-scaled and CENTRED, W[n,k] = bf16(gamma[k] W0[n,k] - mean_k(gamma W0[n,:])), so the
+ * row mean cancels inside the MMA; bias[n] = b[n] + sum_k beta[k] W0[n,k]; rowstat [M] = rstd from
+ * mst_kernel_row_stats_bf16:  out = act(rstd * acc + bias[n]). */
+MST_API int mst_kernel_gemm_bf16_ln(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t gelu,
+                            const float* bias, const float* rowstat, void* out, void* stream);
+MST_API int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream);
 /* profiling aid: same as mst_kernel_gemm_bf16, plus cycle counters of CTA 0 (8 x int64: MMA warp wait-for-accumulator,
  * wait-for-operands, total, tiles; epilogue warp 0 wait-for-MMA, TMEM read, math+store) */
 MST_API int mst_debug_gemm_timing(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode,

@@ -60,6 +60,8 @@ def lib():
     L.mst_quantile_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
     L.mst_quantile.argtypes = [vp, i64, i32, vp, i32, vp, vp, sz, vp]
     L.mst_kernel_gemm_bf16.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.mst_kernel_gemm_bf16_ln.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.mst_kernel_row_stats_bf16.argtypes = [vp, vp, i32, i32, ctypes.c_float, vp]
     L.mst_debug_gemm_timing.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mst_kernel_gemm_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_attention_bf16.argtypes = [vp, vp, i32, i32, i32, vp]

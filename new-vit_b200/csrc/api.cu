@@ -1,6 +1,7 @@
 // C ABI (include/mst_b200.h): handle, weight store + packing, forward orchestration, saliency.
 #include <stdarg.h>
 #include <map>
+#include <type_traits>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,30 @@ __global__ void pack_linear_kernel(const float* __restrict__ W, const float* __r
         if (i % K == 0) bd[n] = b[n] * f;
     }
 }
+// LayerNorm folded into the consuming Linear (EPI_LN_*): one CTA per output row n.
+//   g[k] = W[n,k] * f_n * gamma[k];  Wd[n,k] = bf16(g[k] - mean_k g)  (centred row: x . Wd[n,:] = (x - mean x) . g);
+//   bd[n] = b[n]*f_n + sum_k beta[k] * W[n,k] * f_n
+__global__ void __launch_bounds__(128) pack_linear_ln_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             int nscaled, float s, bf16* __restrict__ Wd, float* __restrict__ bd,
+                                                             int K) {
+    __shared__ float red[2][4];
+    const int n = blockIdx.x;
+    const float f = n < nscaled ? s : 1.0f;
+    float cs = 0.f, ds = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = W[static_cast<int64_t>(n) * K + k] * f;
+        cs = fmaf(w, gamma[k], cs);
+        ds = fmaf(beta[k], w, ds);
+    }
+    for (int o = 16; o > 0; o >>= 1) { cs += __shfl_xor_sync(0xffffffffu, cs, o); ds += __shfl_xor_sync(0xffffffffu, ds, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cs; red[1][threadIdx.x >> 5] = ds; }
+    __syncthreads();
+    const float mean = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / K;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        Wd[static_cast<int64_t>(n) * K + k] = __float2bfloat16_rn(W[static_cast<int64_t>(n) * K + k] * f * gamma[k] - mean);
+    if (threadIdx.x == 0) bd[n] = b[n] * f + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+}
 // conv weight [E,3,14,14] -> [E,KP]: sum over the 3 identical input channels (dino.py:127 repeats gray -> RGB)
 template <typename T>
 __global__ void pack_patch_kernel(const float* __restrict__ W, T* __restrict__ Wd, int E) {
@@ -75,6 +100,7 @@ __global__ void transpose_kernel(const float* __restrict__ W, float* __restrict_
 struct Layer {
     void *wqkv = nullptr, *wproj = nullptr, *wfc1 = nullptr, *wfc2 = nullptr;
     float *bqkv = nullptr, *bproj = nullptr, *bfc1 = nullptr, *bfc2 = nullptr;
+    bool fold_qkv = false, fold_fc1 = false;  // bf16 path: norm1 / norm2 folded into the qkv / fc1 weights (EPI_LN_*)
     const float *n1w = nullptr, *n1b = nullptr, *n2w = nullptr, *n2b = nullptr;
 };
 
@@ -193,6 +219,18 @@ static int pack_linear(mst_handle h, const std::string& wname, const std::string
     return 0;
 }
 
+// bf16 path: Linear with the preceding LayerNorm (gamma, beta) folded in (EPI_LN_*)
+static int pack_linear_ln(mst_handle h, const std::string& wname, const std::string& bname, const float* gamma, const float* beta,
+                          int nscaled, float s, int N, int K, void** Wd, float** bd, cudaStream_t st) {
+    bf16* w;
+    MST_PROPAGATE(alloc_dev<bf16>(h, &w, static_cast<size_t>(N) * K));
+    MST_PROPAGATE(alloc_dev<float>(h, bd, N));
+    pack_linear_ln_kernel<<<N, 128, 0, st>>>(h->master[wname], h->master[bname], gamma, beta, nscaled, s, w, *bd, K);
+    MST_CHECK_CUDA(cudaGetLastError());
+    *Wd = w;
+    return 0;
+}
+
 static int transposed(mst_handle h, const std::string& name, int N, int K, const float** out, cudaStream_t st) {
     float* t;
     MST_PROPAGATE(alloc_dev<float>(h, &t, static_cast<size_t>(N) * K));
@@ -213,13 +251,26 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
         Layer& L = h->layers[i];
         const float* g1 = h->have.count(p + "ls1.gamma") ? h->master[p + "ls1.gamma"] : nullptr;
         const float* g2 = h->have.count(p + "ls2.gamma") ? h->master[p + "ls2.gamma"] : nullptr;
-        // q rows (first E outputs) carry the 1/sqrt(64) attention scale (attention.py:60): exact power of two
-        MST_PROPAGATE(pack_linear<T>(h, p + "attn.qkv.weight", p + "attn.qkv.bias", nullptr, E, 0.125f, 3 * E, E, &L.wqkv, &L.bqkv, st));
-        MST_PROPAGATE(pack_linear<T>(h, p + "attn.proj.weight", p + "attn.proj.bias", g1, 0, 1.f, E, E, &L.wproj, &L.bproj, st));
-        MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc1.weight", p + "mlp.fc1.bias", nullptr, 0, 1.f, 4 * E, E, &L.wfc1, &L.bfc1, st));
-        MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc2.weight", p + "mlp.fc2.bias", g2, 0, 1.f, E, 4 * E, &L.wfc2, &L.bfc2, st));
         L.n1w = h->master[p + "norm1.weight"]; L.n1b = h->master[p + "norm1.bias"];
         L.n2w = h->master[p + "norm2.weight"]; L.n2b = h->master[p + "norm2.bias"];
+        // q rows (first E outputs) carry the 1/sqrt(64) attention scale (attention.py:60): exact power of two.
+        // bf16 path: norm1 is folded into qkv and norm2 into fc1 (the last block's fc1 runs on CLS rows behind a real
+        // LayerNorm kernel, so it stays unfolded).
+        static const bool no_fold = getenv("MST_NO_LN_FOLD") != nullptr;  // experiments only: separate LayerNorm kernels
+        const bool kFold = std::is_same<T, bf16>::value && !no_fold;
+        L.fold_qkv = kFold;
+        L.fold_fc1 = kFold && i != h->cfg.depth - 1;
+        if (L.fold_qkv)
+            MST_PROPAGATE(pack_linear_ln(h, p + "attn.qkv.weight", p + "attn.qkv.bias", L.n1w, L.n1b, E, 0.125f, 3 * E, E, &L.wqkv,
+                                         &L.bqkv, st));
+        else
+            MST_PROPAGATE(pack_linear<T>(h, p + "attn.qkv.weight", p + "attn.qkv.bias", nullptr, E, 0.125f, 3 * E, E, &L.wqkv, &L.bqkv, st));
+        MST_PROPAGATE(pack_linear<T>(h, p + "attn.proj.weight", p + "attn.proj.bias", g1, 0, 1.f, E, E, &L.wproj, &L.bproj, st));
+        if (L.fold_fc1)
+            MST_PROPAGATE(pack_linear_ln(h, p + "mlp.fc1.weight", p + "mlp.fc1.bias", L.n2w, L.n2b, 0, 1.f, 4 * E, E, &L.wfc1, &L.bfc1, st));
+        else
+            MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc1.weight", p + "mlp.fc1.bias", nullptr, 0, 1.f, 4 * E, E, &L.wfc1, &L.bfc1, st));
+        MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc2.weight", p + "mlp.fc2.bias", g2, 0, 1.f, E, 4 * E, &L.wfc2, &L.bfc2, st));
     }
     T* wp;
     MST_PROPAGATE(alloc_dev<T>(h, &wp, static_cast<size_t>(E) * KP));
@@ -245,6 +296,7 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
         s.n1w = h->master[q + "norm1.weight"]; s.n1b = h->master[q + "norm1.bias"];
         s.n2w = h->master[q + "norm2.weight"]; s.n2b = h->master[q + "norm2.bias"];
         s.nfw = h->master["slice_fusion.norm.weight"]; s.nfb = h->master["slice_fusion.norm.bias"];
+        s.in_w = h->master[q + "self_attn.in_proj_weight"];
         s.in_b = h->master[q + "self_attn.in_proj_bias"]; s.out_b = h->master[q + "self_attn.out_proj.bias"];
         s.l1_b = h->master[q + "linear1.bias"]; s.l2_b = h->master[q + "linear2.bias"];
         MST_PROPAGATE(transposed(h, q + "self_attn.in_proj_weight", 3 * Es, Es, &s.in_wt, st));
@@ -290,6 +342,7 @@ static int pos_for_grid(mst_handle h, int gh, int gw, const float** out, cudaStr
 struct Workspace {
     void *A0, *x, *xn, *qkv, *hid, *ao_cls, *xc, *xcn, *hc;
     float *enc_cls, *hs;
+    float* rowstat;
     size_t total;
 };
 static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t* base) {
@@ -309,6 +362,7 @@ static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t*
     w.hc = take(BD * 4 * E * es);
     w.enc_cls = static_cast<float*>(take(BD * E * 4));
     w.hs = static_cast<float*>(take(static_cast<size_t>(B) * (D + 1) * E * 4));
+    w.rowstat = static_cast<float*>(take(M * sizeof(float)));
     w.total = off;
     return w;
 }
@@ -370,8 +424,13 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
         const Layer& L = h->layers[l];
         const bool last = (l == c.depth - 1);
         // x = x + ls1(attn(norm1(x)))                                   (block.py:112)
-        MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n1w, L.n1b, M, E, 1e-6f, st)));
-        {
+        if (L.fold_qkv) {  // bf16: only the row statistics are materialised; norm1 itself rides in the qkv epilogue
+            MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
+            EpiParams ep{};
+            ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = ws.qkv; ep.ldo = 3 * E;
+            MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
+        } else {
+            MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n1w, L.n1b, M, E, 1e-6f, st)));
             EpiParams ep{};
             ep.bias = L.bqkv; ep.out = ws.qkv; ep.ldo = 3 * E;
             MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, xn, E, L.wqkv, M, 3 * E, E, EPI_BIAS, ep, st));
@@ -388,8 +447,13 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
                 MST_LAUNCH(CAT_GEMM_PROJ, Ops<T>::gemm(h, xn, E, L.wproj, M, E, E, EPI_BIAS_RES, ep, st));
             }
             // x = x + ls2(mlp(norm2(x)))                                  (block.py:113)
-            MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n2w, L.n2b, M, E, 1e-6f, st)));
-            {
+            if (L.fold_fc1) {
+                MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
+                EpiParams ep{};
+                ep.bias = L.bfc1; ep.rowstat = ws.rowstat; ep.out = ws.hid; ep.ldo = 4 * E;
+                MST_LAUNCH(CAT_GEMM_FC1, Ops<T>::gemm(h, x, E, L.wfc1, M, 4 * E, E, EPI_LN_BIAS_GELU, ep, st));
+            } else {
+                MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n2w, L.n2b, M, E, 1e-6f, st)));
                 EpiParams ep{};
                 ep.bias = L.bfc1; ep.out = ws.hid; ep.ldo = 4 * E;
                 MST_LAUNCH(CAT_GEMM_FC1, Ops<T>::gemm(h, xn, E, L.wfc1, M, 4 * E, E, EPI_BIAS_GELU, ep, st));
@@ -645,6 +709,18 @@ int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_t N, int
     ep.bias = bias; ep.res = res; ep.ldr = N; ep.out = out; ep.ldo = N;
     return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, num_sms_current(),
                         static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_gemm_bf16_ln(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t gelu, const float* bias,
+                            const float* rowstat, void* out, void* stream) {
+    MST_REQUIRE(A && W && out && bias && rowstat, "mst_kernel_gemm_bf16_ln: null argument");
+    EpiParams ep{};
+    ep.bias = bias; ep.rowstat = rowstat; ep.out = out; ep.ldo = N;
+    return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, gelu ? EPI_LN_BIAS_GELU : EPI_LN_BIAS, ep,
+                        num_sms_current(), static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream) {
+    MST_REQUIRE(x && rowstat, "mst_kernel_row_stats_bf16: null argument");
+    return launch_row_stats(static_cast<const bf16*>(x), rowstat, rows, E, eps, static_cast<cudaStream_t>(stream));
 }
 int mst_debug_gemm_timing(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode, const float* bias,
                           const void* res, void* out, long long* dbg_dev, void* stream) {

@@ -41,7 +41,13 @@ enum EpiMode : int {
     EPI_BIAS_RES = 2,   // out = res[row*ldr + n] + acc + bias[n]       (block.py:112-113; LayerScale folded in W,b)
     EPI_PATCH = 3,      // out[(row/P)*(P+1+R) + 1 + R + row%P, n] = acc + posb[(row%P)*N + n]   (patch_embed.py:75-77 +
                         //                                      vision_transformer.py:219-220; bias folded in posb)
-    EPI_BIAS_ACCUM = 4  // out[row, n] += acc + bias[n]   (in-place residual update; bf16 path: TMA reduce-add)
+    EPI_BIAS_ACCUM = 4, // out[row, n] += acc + bias[n]   (in-place residual update; bf16 path: TMA reduce-add)
+    // LayerNorm folded into the GEMM that consumes it (bf16 path): A holds the RAW residual rows; the weight is scaled by the
+    // LayerNorm weight and every row is CENTRED, Wc[n,k] = gamma[k] W[n,k] - mean_k(gamma W[n,:]), so that x . Wc[n,:] =
+    // (x - mean(x)) . (gamma W[n,:]) -- the mean subtraction happens inside the MMA; bias[n] = b[n] + sum_k beta[k] W[n,k];
+    // rowstat[row] = rstd:   LN(x) W^T + b  =  rstd * acc + bias[n]
+    EPI_LN_BIAS = 5,
+    EPI_LN_BIAS_GELU = 6
 };
 
 struct EpiParams {
@@ -54,6 +60,7 @@ struct EpiParams {
     void* out;           // output, dtype T
     int64_t ldo;         // output row stride in elements
     long long* dbg;      // nullable: phase cycle counters of CTA 0 (profiles/gemm_timing.py)
+    const float* rowstat;   // [M] rstd of every A row (EPI_LN_*)
 };
 
 // erf via the rational minimax on [-4,4] (max abs error 3.8e-7 in fp32; checked against math.erf).
@@ -85,6 +92,29 @@ __device__ __forceinline__ float gelu_tanh_fit(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x * p));
     const float hx = 0.5f * x;
     return fmaf(hx, t, hx);
+}
+// the same function on a packed pair: 4 packed FP32 ops + 2 FMNMX + 2 MUFU per two elements
+__device__ __forceinline__ unsigned long long gelu_tanh_fit2(unsigned long long x) {
+    unsigned long long x2, p, u, hx, t, y;
+    float a, b;
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(x2) : "l"(x));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x2));
+    a = fminf(a, 64.0f); b = fminf(b, 64.0f);
+    asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(a), "f"(b));
+    constexpr unsigned long long C2 = 0xB9B84BC9B9B84BC9ULL;  // -3.51516788e-04f twice
+    constexpr unsigned long long C1 = 0x3D17933B3D17933BULL;  //  3.70056460e-02f
+    constexpr unsigned long long C0 = 0x3F4C297A3F4C297AULL;  //  7.97507884e-01f
+    constexpr unsigned long long HALF = 0x3F0000003F000000ULL;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(C2), "l"(x2), "l"(C1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(p) : "l"(p), "l"(x2), "l"(C0));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(x), "l"(p));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(u));
+    asm("tanh.approx.f32 %0, %0;" : "+f"(a));
+    asm("tanh.approx.f32 %0, %0;" : "+f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(a), "f"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(hx) : "l"(x), "l"(HALF));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(y) : "l"(hx), "l"(t), "l"(hx));
+    return y;
 }
 template <bool kExact>
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -120,6 +150,8 @@ int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, const fl
 template <typename TIn, typename TOut>
 int launch_layernorm(const TIn* x, int64_t ldx, TOut* y, int64_t ldy, const float* gamma, const float* beta, int rows,
                      int E, float eps, cudaStream_t stream);
+// rowstat[row] = rstd of x[row, 0..E) (fp32 statistics, two-pass), the per-row part of a folded LayerNorm
+int launch_row_stats(const bf16* x, float* rowstat, int rows, int E, float eps, cudaStream_t stream);
 int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, cudaStream_t stream);
 int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads, cudaStream_t stream);
 template <typename T>
@@ -128,7 +160,7 @@ int launch_cls_attention(const T* qkv, T* out_cls, float* plane_cls, int BD, int
 enum SliceFusionMode : int { SLICE_FUSION_TRANSFORMER = 0, SLICE_FUSION_LINEAR = 1, SLICE_FUSION_AVERAGE = 2 };  // dino.py:80-101
 struct SliceWeights {  // fp32, linear weights pre-transposed to [in][out]; bott_* / pos_emb nullable (dino.py:75-82)
     const float *cls_token, *n1w, *n1b, *in_wt, *in_b, *out_wt, *out_b, *n2w, *n2b, *l1_wt, *l1_b, *l2_wt, *l2_b, *nfw,
-        *nfb, *head_wt, *head_b, *bott_wt, *bott_b, *pos_emb;
+        *nfb, *head_wt, *head_b, *bott_wt, *bott_b, *pos_emb, *in_w /* in_proj_weight as stored, [3E][E] */;
 };
 // enc_cls [B*D, Eenc]; E = slice embedding (Eenc, or Eenc/4 behind the bottleneck); logits/feat nullable
 int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,

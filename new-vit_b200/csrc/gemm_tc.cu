@@ -90,14 +90,17 @@ constexpr int gemm_threads(int EW) { return 128 + EW * 32; }
 constexpr int STG_TILE = 32 * 32 * 2;   // staging tile: 32 rows x 32 bf16
 
 
-template <int BN, int KCH, int STAGES, int NSTG, int EW>
+// PAIR: 0 = one CTA per tile; 1 = CTA pair sharing A by TMA multicast (adjacent n-blocks); 2 = CTA pair driving ONE
+// 256 x BN tcgen05.mma.cta_group::2 (each CTA holds its 128 rows of A and BN/2 rows of the weight tile)
+template <int BN, int KCH, int STAGES, int NSTG, int EW, int PAIR = 0>
 struct GemmSmem {
+    static constexpr int BNL = PAIR == 2 ? BN / 2 : BN;  // weight rows held in THIS CTA's shared memory
     // per-warp staging: NSTG 1/2 = that many 32x32 tiles (one TMA store per 32-column chunk; 2: one store in flight while
     // the next tile fills); NSTG 3 = the warp's whole 32 x BN/2 region (ONE async-proxy fence + ONE TMA store per tile)
     static constexpr int EPI_WARPS = EW;
     static_assert(NSTG != 3 || BN / (EW / 4) == 64, "whole-region staging needs 64-column groups");
     static constexpr int STG_BYTES = NSTG == 3 ? 32 * 64 * 2 : NSTG * STG_TILE;
-    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int B_TILE_BYTES = BNL * BK * 2;
     static constexpr int B_BUFS = KCH > 0 ? KCH : STAGES;
     static constexpr int BIAS_FLOATS = KCH > 0 ? BN : 2048;  // resident: this CTA's n-block; streaming: the whole vector
     static constexpr int A_OFF = 0;
@@ -115,39 +118,61 @@ struct GemmSmem {
 // `bias` points to the 32 bias values of this chunk (shared memory cache or global).
 template <int MODE>
 __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t (&o)[16], const EpiParams& ep,
-                                              const float* bias, bool bias_smem, int64_t row, bool row_ok, int N, int n0) {
-    float v[32];
+                                              const float* bias, bool bias_smem, int64_t row, bool row_ok, int N, int n0,
+                                              float rstat) {
+    constexpr bool LNF = MODE == EPI_LN_BIAS || MODE == EPI_LN_BIAS_GELU;
+    // packed fp32 pairs throughout: one FADD2 / FFMA2 / FMUL2 per two columns (the GELU epilogue was issue-bound)
+    f32x2 v[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    for (int i = 0; i < 16; ++i) v[i] = f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
     if (MODE == EPI_PATCH) {
         const int p = static_cast<int>(row % ep.P);
         const float4* pb = reinterpret_cast<const float4*>(ep.posb + static_cast<int64_t>(p) * N + n0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float4 b = __ldg(pb + i);
-            v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+            v[2 * i] = f2_add(v[2 * i], f2_pack(b.x, b.y));
+            v[2 * i + 1] = f2_add(v[2 * i + 1], f2_pack(b.z, b.w));
+        }
+    } else if (LNF) {
+        // LN(x) W^T + b = rstd * (x . Wc^T) + bias'[n]: the weight rows are centred (sum_k Wc[n,k] = 0), which subtracts the
+        // row mean inside the MMA; one FFMA2 per column pair, same issue count as the plain bias add
+        const f32x2 rs = f2_pack(rstat, rstat);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            f32x2 b0, b1;
+            if (bias_smem) {
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(smem_u32(bias) + i * 16));
+            } else {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
+                b0 = f2_pack(b.x, b.y); b1 = f2_pack(b.z, b.w);
+            }
+            v[2 * i] = f2_fma(v[2 * i], rs, b0);
+            v[2 * i + 1] = f2_fma(v[2 * i + 1], rs, b1);
         }
     } else {
         if (bias_smem) {
             const uint32_t sb = smem_u32(bias);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                float4 b;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(sb + i * 16));
-                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                f32x2 b0, b1;
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(sb + i * 16));
+                v[2 * i] = f2_add(v[2 * i], b0);
+                v[2 * i + 1] = f2_add(v[2 * i + 1], b1);
             }
         } else {
             const float4* pb = reinterpret_cast<const float4*>(bias);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float4 b = __ldg(pb + i);
-                v[4 * i + 0] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
+                v[2 * i] = f2_add(v[2 * i], f2_pack(b.x, b.y));
+                v[2 * i + 1] = f2_add(v[2 * i + 1], f2_pack(b.z, b.w));
             }
         }
     }
-    if (MODE == EPI_BIAS_GELU) {
+    if (MODE == EPI_BIAS_GELU || MODE == EPI_LN_BIAS_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fit(v[i]);
+        for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_fit2(v[i]);
     }
     if (MODE == EPI_BIAS_RES) {
         if (row_ok) {
@@ -156,15 +181,19 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
             for (int i = 0; i < 4; ++i) {
                 const uint4 u = __ldg(pr + i);
                 float2 f;
-                f = unpack_bf16x2(u.x); v[8 * i + 0] += f.x; v[8 * i + 1] += f.y;
-                f = unpack_bf16x2(u.y); v[8 * i + 2] += f.x; v[8 * i + 3] += f.y;
-                f = unpack_bf16x2(u.z); v[8 * i + 4] += f.x; v[8 * i + 5] += f.y;
-                f = unpack_bf16x2(u.w); v[8 * i + 6] += f.x; v[8 * i + 7] += f.y;
+                f = unpack_bf16x2(u.x); v[4 * i + 0] = f2_add(v[4 * i + 0], f2_pack(f.x, f.y));
+                f = unpack_bf16x2(u.y); v[4 * i + 1] = f2_add(v[4 * i + 1], f2_pack(f.x, f.y));
+                f = unpack_bf16x2(u.z); v[4 * i + 2] = f2_add(v[4 * i + 2], f2_pack(f.x, f.y));
+                f = unpack_bf16x2(u.w); v[4 * i + 3] = f2_add(v[4 * i + 3], f2_pack(f.x, f.y));
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    for (int i = 0; i < 16; ++i) {
+        float lo, hi;
+        f2_unpack(v[i], lo, hi);
+        o[i] = pack_bf16x2(lo, hi);
+    }
 }
 
 __device__ __forceinline__ void red_add_bf16x8(void* gptr, const uint4& v) {
@@ -199,11 +228,14 @@ __device__ __forceinline__ void store_block_32x32(uint8_t* stg, const uint32_t (
     __syncwarp();
 }
 
-template <int BN, int KCH, int STAGES, int NSTG, int EW, bool MCAST>
+template <int BN, int KCH, int STAGES, int NSTG, int EW, int PAIR>
 __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, const __grid_constant__ TmaDesc tmC,
                int M, int N, int K, int mode_flags, EpiParams ep) {
-    using L = GemmSmem<BN, KCH, STAGES, NSTG, EW>;
+    using L = GemmSmem<BN, KCH, STAGES, NSTG, EW, PAIR>;
+    constexpr bool MCAST = PAIR == 1;
+    constexpr bool TWO = PAIR == 2;
+    constexpr int BMT = TWO ? 2 * BM : BM;  // rows of one tile (the pair's 256-row tile in cta_group::2 mode)
     const int mode = mode_flags & 0xff;
     constexpr bool kResident = KCH > 0;
     constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
@@ -214,7 +246,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     static_assert(!MCAST || KCH > 0, "multicast is wired for the weight-resident schedule");
     // MCAST: the CTA pair (2j, 2j+1) of a cluster walks the same m-blocks with adjacent n-blocks; each CTA fetches half
     // of every A stage and TMA-multicasts it to both, halving the bytes each SM must keep in flight per tile.
-    const uint32_t cta_rank = MCAST ? cluster_ctarank() : 0;
+    const uint32_t cta_rank = PAIR != 0 ? cluster_ctarank() : 0;
+    const bool leader = cta_rank == 0;
     constexpr int kPrefetchTiles = 2;
 
     extern __shared__ uint8_t smem_raw[];
@@ -233,22 +266,25 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int n_tiles = N / BN;
-    const int m_tiles = (M + BM - 1) / BM;
+    const int m_tiles = (M + BMT - 1) / BMT;
     const int kchunks = K / BK;
 
-    // tile sequence of this CTA
+    // tile sequence of this CTA (cta_group::2: of this CTA pair -- both CTAs walk the same tiles, 128 rows each)
+    const int unit = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int units = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int row_off = TWO ? static_cast<int>(cta_rank) * BM : 0;  // this CTA's rows inside a tile
     int t_first, t_step, t_count;
     if (kResident) {  // one n-block per CTA; m-blocks strided by the group size
-        const int gs = gridDim.x / n_tiles;
-        const int m0 = blockIdx.x / n_tiles;
+        const int gs = units / n_tiles;
+        const int m0 = unit / n_tiles;
         t_first = m0; t_step = gs;
         t_count = m0 < m_tiles ? (m_tiles - m0 + gs - 1) / gs : 0;
     } else {
         const int total = m_tiles * n_tiles;
-        t_first = blockIdx.x; t_step = gridDim.x;
+        t_first = unit; t_step = units;
         t_count = t_first < total ? (total - t_first + t_step - 1) / t_step : 0;
     }
-    const int n_fixed = blockIdx.x % n_tiles;
+    const int n_fixed = unit % n_tiles;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -258,11 +294,15 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], MCAST ? 2 : 1); }
         mbar_init(bfull_bar, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
+        // cta_group::2: the leader's accumulator-free barrier collects the epilogue warps of BOTH CTAs
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 2 * EPI_WARPS : EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    if (warp == 2) {
+        if (TWO) tmem_alloc_pair<kTmemCols>(tmem_ptr_smem); else tmem_alloc<kTmemCols>(tmem_ptr_smem);
+    }
     // bias cache (EPI_PATCH has no bias vector)
+    const bool ln_fold = mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU;
     const bool bias_cached = mode != EPI_PATCH && (kResident || N <= L::BIAS_FLOATS);
     if (bias_cached && warp >= 4) {
         const int cnt = kResident ? BN : N;
@@ -270,17 +310,24 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         for (int i = threadIdx.x - 128; i < cnt; i += EPI_WARPS * 32) sBias[i] = __ldg(src + i);
     }
     tc_fence_before_sync();
-    if (MCAST) cluster_sync_all(); else __syncthreads();  // peers' barriers must be initialised before any remote arrive
+    if (PAIR != 0) cluster_sync_all(); else __syncthreads();  // peers' barriers must be initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
+            // cta_group::2: every operand byte of BOTH CTAs completes on the LEADER's barriers (its MMA warp consumes them)
+            const uint32_t bfull_leader = TWO ? mapa_u32(bfull_bar, 0) : 0;
             if (kResident && t_count > 0) {
-                mbar_arrive_expect_tx(bfull_bar, KCH * L::B_TILE_BYTES);
-                for (int kc = 0; kc < KCH; ++kc)
-                    tma_load_2d(sB + kc * L::B_TILE_BYTES, &tmB, bfull_bar, kc * BK, n_fixed * BN);
+                if (!TWO || leader) mbar_arrive_expect_tx(bfull_bar, (TWO ? 2 : 1) * KCH * L::B_TILE_BYTES);
+                for (int kc = 0; kc < KCH; ++kc) {
+                    if (TWO)
+                        tma_load_2d_pair(sB + kc * L::B_TILE_BYTES, &tmB, bfull_leader, kc * BK,
+                                         n_fixed * BN + static_cast<int>(cta_rank) * L::BNL);
+                    else
+                        tma_load_2d(sB + kc * L::B_TILE_BYTES, &tmB, bfull_bar, kc * BK, n_fixed * BN);
+                }
             }
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < t_count; ++it) {
@@ -294,10 +341,20 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     // far more than the 4 x 384 clk of MMA work the operand ring can cover (profiles/gemm_timing.py)
                     const int m_pf = t + kPrefetchTiles * t_step;
                     for (int kc = 0; kc < kchunks; ++kc)
-                        tma_prefetch_l2_2d(&tmA, kc * BK, m_pf * BM + (MCAST ? static_cast<int>(cta_rank) * (BM / 2) : 0));
+                        tma_prefetch_l2_2d(&tmA, kc * BK, m_pf * BMT + row_off + (MCAST ? static_cast<int>(cta_rank) * (BM / 2) : 0));
                 }
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (TWO) {
+                        const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
+                        if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + (kResident ? 0 : L::B_TILE_BYTES)));
+                        tma_load_2d_pair(sA + stage * A_STAGE_BYTES, &tmA, full_leader, kc * BK, m_blk * BMT + row_off);
+                        if (!kResident)
+                            tma_load_2d_pair(sB + stage * L::B_TILE_BYTES, &tmB, full_leader, kc * BK,
+                                             n_blk * BN + static_cast<int>(cta_rank) * L::BNL);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + (kResident ? 0 : L::B_TILE_BYTES));
                     if (MCAST)
                         tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + cta_rank * (A_STAGE_BYTES / 2), &tmA, &full_bar[stage],
@@ -311,12 +368,12 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && (!TWO || leader)) {
+        // ===================== MMA issuer (cta_group::2: the leader CTA's warp drives both SMs) =====================
         // The whole warp runs this loop convergently (operands stay in uniform registers; a single-lane loop made
         // ptxas route every descriptor through ELECT/R2UR and the issue loop, not the tensor pipe, set the pace);
         // one elected lane issues.  Descriptors are a constant high word + (smem address >> 4) in the low word.
-        constexpr uint32_t idesc = umma_idesc_bf16_f32(BM, BN);
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(BMT, BN);
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B | version 1 | SWIZZLE_128B
         const uint32_t a_lo0 = (smem_u32(sA) & 0x3FFFF) >> 4;
         const uint32_t b_lo0 = (smem_u32(sB) & 0x3FFFF) >> 4;
@@ -340,12 +397,22 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 const uint32_t b_lo = b_lo0 + (kResident ? kc : stage) * (L::B_TILE_BYTES >> 4);
                 if (elect_one_sync()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16_ss(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
-                                     (kc | k) != 0 ? 1u : 0u);
-                    if (MCAST) umma_commit_multicast(&empty_bar[stage], 0x3);  // both CTAs refill this slot
-                    else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                    if (kc == kchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if (TWO)
+                            umma_bf16_ss_pair(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
+                                              (kc | k) != 0 ? 1u : 0u);
+                        else
+                            umma_bf16_ss(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
+                                         (kc | k) != 0 ? 1u : 0u);
+                    }
+                    if (TWO) {
+                        umma_commit_pair(&empty_bar[stage], 0x3);                          // both CTAs refill their slot
+                        if (kc == kchunks - 1) umma_commit_pair(&tfull_bar[acc], 0x3);      // both epilogues read their half
+                    } else {
+                        if (MCAST) umma_commit_multicast(&empty_bar[stage], 0x3);  // both CTAs refill this slot
+                        else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                        if (kc == kchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                    }
                 }
                 __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -367,12 +434,14 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             const int t = t_first + it * t_step;
             const int m_blk = kResident ? t : t / n_tiles;
             const int n_blk = kResident ? n_fixed : t % n_tiles;
-            const int row0 = m_blk * BM + q * 32;
+            const int row0 = m_blk * BMT + row_off + q * 32;
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < M;
             const int col0 = hf * COLS_PER_WARP;                  // first column of this warp inside the tile
             const int nbase = n_blk * BN + col0;                  // ... and in the output
             const float* bias0 = bias_cached ? sBias + (kResident ? col0 : nbase) : (mode == EPI_PATCH ? nullptr : ep.bias + nbase);
+            float rstat = 0.f;
+            if (ln_fold && row_ok) rstat = __ldg(ep.rowstat + row);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
 
             auto process = [&](const uint32_t (&r)[32], int c) {
@@ -381,10 +450,12 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 const float* b = bias0 + c * 32;
                 switch (mode) {
                     case EPI_BIAS:
-                    case EPI_BIAS_ACCUM: epilogue_math<EPI_BIAS>(r, o, ep, b, bias_cached, row, row_ok, N, n0); break;
-                    case EPI_BIAS_GELU: epilogue_math<EPI_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0); break;
-                    case EPI_BIAS_RES: epilogue_math<EPI_BIAS_RES>(r, o, ep, b, bias_cached, row, row_ok, N, n0); break;
-                    default: epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0); break;
+                    case EPI_BIAS_ACCUM: epilogue_math<EPI_BIAS>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
+                    case EPI_BIAS_GELU: epilogue_math<EPI_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
+                    case EPI_BIAS_RES: epilogue_math<EPI_BIAS_RES>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
+                    case EPI_LN_BIAS: epilogue_math<EPI_LN_BIAS>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
+                    case EPI_LN_BIAS_GELU: epilogue_math<EPI_LN_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
+                    default: epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0, rstat); break;
                 }
                 if (mode == EPI_PATCH) {
                     // rows are re-mapped (one CLS row inserted per slice): direct 64-byte row stores
@@ -435,7 +506,10 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             auto release_tmem = [&]() {  // every tcgen05.ld of this tile has completed
                 tc_fence_before_sync();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) {
+                    if (TWO && !leader) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
             };
 
             const long long e0 = clock64();
@@ -468,36 +542,39 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     }
 
     tc_fence_before_sync();
-    if (MCAST) cluster_sync_all(); else __syncthreads();  // the peer may still multicast into / arrive on this CTA's smem
+    if (PAIR != 0) cluster_sync_all(); else __syncthreads();  // the peer may still multicast into / arrive on this CTA's smem
     if (warp == 2) {
         tc_fence_after_sync();
-        tmem_dealloc<kTmemCols>(tmem_base);
+        if (TWO) tmem_dealloc_pair<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // host launcher
 // ---------------------------------------------------------------------------------------------------
-template <int BN, int KCH, int STAGES, int NSTG, int EW, bool MCAST = false>
+template <int BN, int KCH, int STAGES, int NSTG, int EW, int PAIR = 0>
 static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC, int M, int N, int K, int mode,
                       const EpiParams& ep, int num_sms, cudaStream_t stream) {
-    using L = GemmSmem<BN, KCH, STAGES, NSTG, EW>;
-    auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG, EW, MCAST>;
+    using L = GemmSmem<BN, KCH, STAGES, NSTG, EW, PAIR>;
+    constexpr bool MCAST = PAIR != 0;  // launched as clusters of two
+    auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG, EW, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
         MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
         attr_set = true;
     }
+    constexpr int CPU_ = PAIR == 2 ? 2 : 1;               // CTAs per scheduling unit (a cta_group::2 pair shares its tiles)
     const int n_tiles = N / BN;
-    const int m_tiles = (M + BM - 1) / BM;
+    const int m_tiles = (M + BM * CPU_ - 1) / (BM * CPU_);
+    const int units = num_sms / CPU_;
     int grid;
     if (KCH > 0) {
-        int gs = num_sms / n_tiles;
+        int gs = units / n_tiles;
         if (gs < 1) gs = 1;
         if (gs > m_tiles) gs = m_tiles;
-        grid = gs * n_tiles;
+        grid = gs * n_tiles * CPU_;
     } else {
-        grid = m_tiles * n_tiles < num_sms ? m_tiles * n_tiles : num_sms;
+        grid = (m_tiles * n_tiles < units ? m_tiles * n_tiles : units) * CPU_;
     }
     if (MCAST) {
         cudaLaunchConfig_t cfg{};
@@ -525,16 +602,29 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     TmaDesc tmA, tmB, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
     // output maps (unused by EPI_PATCH, whose rows are re-mapped)
-    const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1) : static_cast<uint64_t>(M);
+    const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1 + ep.R) : static_cast<uint64_t>(M);
     static const int force_bn = getenv("MST_GEMM_BN") ? atoi(getenv("MST_GEMM_BN")) : 0;  // experiments only
     static const int skip_epi = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;
     if (skip_epi) mode |= skip_epi << 8;  // 1: no epilogue at all, 2: epilogue without the final store
     static const int no_mcast = getenv("MST_GEMM_NO_MCAST") ? atoi(getenv("MST_GEMM_NO_MCAST")) : 0;  // experiments only
+    static const int use_two = getenv("MST_GEMM_TWO") ? atoi(getenv("MST_GEMM_TWO")) : 1;             // experiments only
     if (N % 192 == 0 && force_bn != 128) {
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
         if (K == 256) {  // patch embedding: weight-resident, chunk staging (its epilogue stores rows directly)
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
             return launch_cfg<192, 4, 4, 2, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+        }
+        if (K == 384 && use_two == 2) {  // measured slower than the multicast pair below (0.512 vs 0.428 ms for qkv): every CTA
+                                         // streams all of its own A again, and A supply is what bounds the resident schedule
+            // cta_group::2: one 256 x 192 MMA per CTA pair; each CTA keeps HALF of the resident weight slab (72 KB) and
+            // streams its own 128 rows of A, so the tensor core reads 7 KB instead of 10 KB of shared memory per k-step
+            // (the shared-memory port, shared with the TMA fills and the epilogue staging, is what bounds this kernel)
+            TmaDesc tmBh;
+            MST_PROPAGATE(make_tma_2d_bf16(&tmBh, W, K, N, K, BK, 96));
+            MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+            if ((mode & 0xff) == EPI_BIAS_GELU || (mode & 0xff) == EPI_LN_BIAS_GELU)
+                return launch_cfg<192, 6, 6, 2, 12, 2>(tmA, tmBh, tmC, M, N, K, mode, ep, num_sms, stream);
+            return launch_cfg<192, 6, 6, 2, 8, 2>(tmA, tmBh, tmC, M, N, K, mode, ep, num_sms, stream);
         }
         if (K == 384 && (N / 192) % 2 == 0 && !no_mcast) {
             // weight slab resident (144 KB), A stages fetched half-and-half by a CTA pair and TMA-multicast to both
@@ -543,12 +633,17 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
             // GELU epilogue (fc1) is the longest: two staging tiles per warp (a TMA store stays in flight while the next
             // chunk is computed) paid for with a 3-deep A ring; the L2 prefetch keeps the shorter ring fed
-            if ((mode & 0xff) == EPI_BIAS_GELU)
+            if ((mode & 0xff) == EPI_BIAS_GELU || (mode & 0xff) == EPI_LN_BIAS_GELU)
                 return launch_cfg<192, 6, 3, 1, 12, true>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
             return launch_cfg<192, 6, 4, 1, 8, true>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
         }
-        // K too large for a resident weight slab (fc2): both operands stream through a 5-stage ring
+        // K too large for a resident weight slab (fc2): both operands stream through the ring
         MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+        if (use_two) {  // cta_group::2: 16 KB of A + 12 KB (half) of the weight tile per CTA and stage
+            TmaDesc tmBh;
+            MST_PROPAGATE(make_tma_2d_bf16(&tmBh, W, K, N, K, BK, 96));
+            return launch_cfg<192, 0, 7, 1, 8, 2>(tmA, tmBh, tmC, M, N, K, mode, ep, num_sms, stream);
+        }
         return launch_cfg<192, 0, 5, 1, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
     }
     MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 128));

@@ -186,6 +186,47 @@ template int launch_layernorm<float, float>(const float*, int64_t, float*, int64
 template int launch_layernorm<bf16, bf16>(const bf16*, int64_t, bf16*, int64_t, const float*, const float*, int, int, float, cudaStream_t);
 template int launch_layernorm<bf16, float>(const bf16*, int64_t, float*, int64_t, const float*, const float*, int, int, float, cudaStream_t);
 
+// Row statistics for the LayerNorm that is folded into the consuming GEMM (bf16 path): reads x once, writes 4 bytes
+// per row instead of a normalised copy.  Same two-pass fp32 arithmetic as layernorm_kernel.
+template <int E>
+__global__ void __launch_bounds__(256) row_stats_kernel(const bf16* __restrict__ x, float* __restrict__ rowstat, int rows,
+                                                         float eps) {
+    constexpr int V = E / 128;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const bf16* xr = x + static_cast<int64_t>(row) * E;
+    float v[V][4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        Vec4<bf16>::load(xr + i * 128 + lane * 4, v[i]);
+        s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+    }
+    const float mean = warp_sum(s) * (1.0f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float d = v[i][j] - mean;
+            q = fmaf(d, d, q);
+        }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
+    if (lane == 0) rowstat[row] = rstd;
+}
+
+int launch_row_stats(const bf16* x, float* rowstat, int rows, int E, float eps, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    const int grid = (rows + 7) / 8;
+    if (E == 384) row_stats_kernel<384><<<grid, 256, 0, stream>>>(x, rowstat, rows, eps);
+    else if (E == 768) row_stats_kernel<768><<<grid, 256, 0, stream>>>(x, rowstat, rows, eps);
+    else if (E == 1024) row_stats_kernel<1024><<<grid, 256, 0, stream>>>(x, rowstat, rows, eps);
+    else MST_REQUIRE(false, "row stats: unsupported embed dim %d", E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // CLS-row attention of one encoder block (head_dim 64): for (slice, head) the CLS query against all N
 // keys.  Used for the LAST block, whose other query rows are dead (only x[:,0] is consumed,
@@ -543,11 +584,12 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     // 2. q = (Wq n0 + bq) / sqrt(hd)                                    (transformer_blocks.py:166,268)
     block_matvec(n0, w.in_wt, 3 * E, w.in_b, nullptr, q, E, E, false, rsqrtf(static_cast<float>(hd)));
     // 3. qk[h][k] = sum_d q[h,d] Wk[h*hd+d][k];  cterm[h] = q_h . bk_h
+    //    (reads the UN-transposed in_proj_weight [3E][E]: consecutive threads -> consecutive k -> coalesced)
     for (int idx = threadIdx.x; idx < heads * E; idx += blockDim.x) {
         const int h = idx / E, k = idx % E;
-        const float* wr = w.in_wt + static_cast<int64_t>(k) * 3 * E + E + h * hd;
+        const float* wr = w.in_w + (static_cast<int64_t>(E) + h * hd) * E + k;
         float a = 0.f;
-        for (int d = 0; d < hd; ++d) a = fmaf(q[h * hd + d], __ldg(wr + d), a);
+        for (int d = 0; d < hd; ++d) a = fmaf(q[h * hd + d], __ldg(wr + static_cast<int64_t>(d) * E), a);
         qk[idx] = a;
     }
     if (threadIdx.x < heads) {

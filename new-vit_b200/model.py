@@ -161,7 +161,10 @@ class DinoV2ClassifierSlice(nn.Module):
         self._workspace = None
         self._h2d = None
         self._copy_stream = None
-        self.h2d_chunk_volumes = 8   # host batches larger than this are pipelined H2D || compute
+        # Host batches are moved in chunks of whole volumes, H2D of chunk k+1 overlapped with the kernels of chunk k.
+        # Only the first chunk's copy is exposed, so it is small; later chunks grow so that the GEMM grids keep full
+        # waves (8 volumes = 514 m-tiles = 3.5 waves of 148 SMs cost 13 % in wave quantisation; 32 volumes cost 1.5 %).
+        self.h2d_chunk_volumes = (4, 12, 16, 32)   # then the last size repeats; an int = fixed chunk size; 0/None = off
         self._last = None
         self._last_inputs = None
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_dirty", True))
@@ -243,16 +246,25 @@ class DinoV2ClassifierSlice(nn.Module):
         # `source.to(self.device)` (dino.py:121).  A host batch is moved in chunks of whole volumes on a copy stream so
         # that the H2D transfer of chunk k+1 overlaps the kernels of chunk k (volumes are independent: results are
         # bit-identical to a single call, tests/test_gpu_parity.py::test_batch_composition...).
-        chunk = B
-        if source.device.type == "cpu" and self.h2d_chunk_volumes and B > self.h2d_chunk_volumes:
-            chunk = self.h2d_chunk_volumes
+        sched = self.h2d_chunk_volumes
+        if isinstance(sched, int):
+            sched = (sched,)
+        chunks = [B]
+        if source.device.type == "cpu" and sched and B > sched[0]:
+            chunks, left, i = [], B, 0
+            while left > 0:
+                c = min(left, sched[min(i, len(sched) - 1)])
+                chunks.append(c)
+                left -= c
+                i += 1
+        chunk = max(chunks)
         with torch.cuda.device(dev):
             logits = torch.empty((B, self.out_ch), device=dev, dtype=torch.float32) if self.enable_linear else None
             feat = torch.empty((B, feat_dim), device=dev, dtype=torch.float32)
             plane = torch.empty((B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None
             slc = torch.empty((B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
             if full_maps is not None:
-                chunk = B   # full maps are written for the whole batch in one call
+                chunks, chunk = [B], B   # full maps are written for the whole batch in one call
             enc = torch.empty((B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
             need = _cabi.ctypes.c_size_t()
             _cabi.check(L.mst_workspace_bytes(self._handle, chunk, D, H, W, _cabi.ctypes.byref(need)))
@@ -269,20 +281,22 @@ class DinoV2ClassifierSlice(nn.Module):
                                           _cabi.ptr(sl(plane, D)), _cabi.ptr(sl(slc, 1)), _cabi.ptr(full_maps),
                                           _cabi.ptr(self._workspace), self._workspace.numel(), stream))
 
-            if chunk == B:
+            if len(chunks) == 1:
                 x = source.to(dev).to(torch.float32).contiguous()
                 run(x, 0, B)
             else:
                 src = source if source.dtype == torch.float32 else source.float()
-                if self._h2d is None or self._h2d[0].shape[1:] != (1, D, H, W) or self._h2d[0].device != dev:
+                if (self._h2d is None or self._h2d[0].shape[1:] != (1, D, H, W) or self._h2d[0].device != dev
+                        or self._h2d[0].shape[0] < chunk):
+                    self._h2d = None
                     self._h2d = [torch.empty((chunk, 1, D, H, W), device=dev, dtype=torch.float32) for _ in range(2)]
                     self._copy_stream = torch.cuda.Stream(device=dev)
                 copied = [torch.cuda.Event() for _ in range(2)]
                 freed = [torch.cuda.Event() for _ in range(2)]
-                nchunks = (B + chunk - 1) // chunk
                 self._copy_stream.wait_stream(cur)   # buffers may still be read by a previous forward
-                for k in range(nchunks):
-                    b0, nb, buf = k * chunk, min(chunk, B - k * chunk), self._h2d[k & 1]
+                b0 = 0
+                for k, nb in enumerate(chunks):
+                    buf = self._h2d[k & 1]
                     with torch.cuda.stream(self._copy_stream):
                         if k >= 2:
                             self._copy_stream.wait_event(freed[k & 1])
@@ -291,6 +305,7 @@ class DinoV2ClassifierSlice(nn.Module):
                     cur.wait_event(copied[k & 1])
                     run(buf, b0, nb)
                     freed[k & 1].record(cur)
+                    b0 += nb
         if save_attn:
             # The reference keeps 12 x [BD,heads,N,N] (dino.py:241); its getters only ever read row 0 of the last
             # one.  We keep that row, shaped [BD,heads,1,N] so that `attention_maps[-1][:, :, 0, 1:]` still works.

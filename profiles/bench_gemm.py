@@ -23,4 +23,20 @@ for name, N, K, mode in shapes:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     print(f"{name:5s} M={M} N={N} K={K} mode={mode}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.0f} TFLOP/s  BN={os.environ.get('MST_GEMM_BN','192')}")
+    if mode in (0, 1):   # the same GEMM with the LayerNorm folded into its epilogue (EPI_LN_*)
+        stat = torch.empty(M, device="cuda")
+        _cabi.check(L.mst_kernel_row_stats_bf16(_cabi.ptr(A), _cabi.ptr(stat), M, K, 1e-6, st))
+        for _ in range(3):
+            _cabi.check(L.mst_kernel_gemm_bf16_ln(_cabi.ptr(A), _cabi.ptr(W), M, N, K, mode, _cabi.ptr(b), _cabi.ptr(stat), _cabi.ptr(out), st))
+        e0.record()
+        for _ in range(n):
+            _cabi.check(L.mst_kernel_gemm_bf16_ln(_cabi.ptr(A), _cabi.ptr(W), M, N, K, mode, _cabi.ptr(b), _cabi.ptr(stat), _cabi.ptr(out), st))
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        print(f"{name:5s} +LN fold: {ms:.3f} ms  {2*M*N*K/ms/1e9:.0f} TFLOP/s")
+        e0.record()
+        for _ in range(n):
+            _cabi.check(L.mst_kernel_row_stats_bf16(_cabi.ptr(A), _cabi.ptr(stat), M, K, 1e-6, st))
+        e1.record(); torch.cuda.synchronize()
+        print(f"      row stats: {e0.elapsed_time(e1) / n:.3f} ms")
     del A, W, out

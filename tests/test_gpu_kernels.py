@@ -202,3 +202,34 @@ def test_rollout_matches_matmul_chain():
         for l in range(d - 2, -1, -1):
             ref = maps[l].double().cpu() @ ref
         torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 1152, 384), (4112, 1536, 384), (333, 2304, 768), (300, 3072, 768)])
+@pytest.mark.parametrize("gelu", [0, 1])
+def test_gemm_bf16_layernorm_folded(M, N, K, gelu):
+    """norm1 -> qkv and norm2 -> fc1 with the LayerNorm folded into the GEMM (block.py:112-113): raw rows through the tensor
+    cores against gamma-scaled, row-centred weights, per-row rstd applied in the epilogue.  Reference: LN in fp32, then the Linear."""
+    cabi, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K + gelu)
+    x = (torch.randn(M, K, device="cuda", generator=g) * 1.7 + 0.9).bfloat16()   # non-zero mean: the -mean*csum term matters
+    x[:, 5] += 20.0                                                               # an outlier channel, as real ViTs have
+    W0 = torch.randn(N, K, device="cuda", generator=g) * (K ** -0.5)
+    b0 = torch.randn(N, device="cuda", generator=g)
+    gamma = 1.0 + 0.2 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(K, device="cuda", generator=g)
+    Wg = W0 * gamma
+    Wf = (Wg - Wg.mean(-1, keepdim=True)).bfloat16()     # centred rows: the row mean of x cancels inside the MMA
+    bias = (b0 + W0 @ beta).contiguous()
+    stat = torch.empty(M, device="cuda")
+    out = torch.full((M, N), float("nan"), device="cuda").bfloat16()
+    cabi.check(L.mst_kernel_row_stats_bf16(cabi.ptr(x), cabi.ptr(stat), M, K, 1e-6, _stream()))
+    cabi.check(L.mst_kernel_gemm_bf16_ln(cabi.ptr(x), cabi.ptr(Wf), M, N, K, gelu, cabi.ptr(bias), cabi.ptr(stat), cabi.ptr(out),
+                                         _stream()))
+    torch.cuda.synchronize()
+    xf = x.float()
+    var, mean = torch.var_mean(xf, dim=-1, unbiased=False, keepdim=True)
+    torch.testing.assert_close(stat[:, None], torch.rsqrt(var + 1e-6), rtol=1e-5, atol=0)
+    ref = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, 1e-6) @ W0.t() + b0
+    if gelu:
+        ref = _gelu(ref)
+    torch.testing.assert_close(out.float(), ref, rtol=1.2e-2, atol=1.2e-2)
