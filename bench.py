@@ -37,6 +37,20 @@ def gemm_flops_executed(BD, N=257, E=384, depth=12, KP=256):
     return 2 * BD * (N - 1) * KP * E + (depth - 1) * per_layer_full + last
 
 
+def kernel_models(BD, N=257, E=384, heads=6):
+    """Algorithmic FLOPs and HBM bytes PER LAUNCH of the kernels of one full encoder block:
+    bf16 activations read/written once, the in-place residual update counted as read + write, weights negligible."""
+    M = BD * N
+    return {
+        "gemm_qkv": (2 * M * 3 * E * E, M * E * 2 + M * 3 * E * 2 + M * 4),
+        "gemm_proj": (2 * M * E * E, M * E * 2 + 2 * M * E * 2),
+        "gemm_fc1": (2 * M * 4 * E * E, M * E * 2 + M * 4 * E * 2 + M * 4),
+        "gemm_fc2": (2 * M * 4 * E * E, M * 4 * E * 2 + 2 * M * E * 2),
+        "attention": (4 * BD * heads * N * N * 64, M * 3 * E * 2 + M * E * 2),
+        "layernorm": (0, M * E * 2 + M * 4),   # bf16 path: row statistics only (the normalisation rides in the next GEMM)
+    }
+
+
 class ClockSampler(threading.Thread):
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -206,6 +220,12 @@ def main():
             pass
         roof = None
         kernels = {}
+        traffic = {}
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload (profiles/)
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+                traffic = json.load(f)
+        except Exception:
+            pass
         if prof:
             gemm_cats = ["gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_cls_rows"]
             gemm_ms = sum(prof[c][0] for c in gemm_cats) / args.steps
@@ -218,9 +238,31 @@ def main():
                     "peak_kind": f"{peaks['_src']} sustained (kernel timed inside a long step); burst {peaks['bf16_tflops']}",
                     "frac_of_burst": ach / peaks["bf16_tflops"], "flops_per_step": fl, "ms_per_step": gemm_ms, "traffic": None}
             tot = sum(v[0] for v in prof.values()) / args.steps
+            models = kernel_models(B * D)
             for k, (m_, n_) in prof.items():
                 kernels[k] = {"ms_per_step": m_ / args.steps, "launches_per_step": n_ / args.steps, "share": (m_ / args.steps) / tot if tot else 0}
+                if k in models and n_ and args.precision == "bf16":
+                    fl, by = models[k]
+                    ms_launch = m_ / n_   # (the last block's shorter launches are included in the average: < 1 % effect)
+                    t_tensor, t_hbm = fl / (peaks["bf16_tflops_sustained"] * 1e12), by / (peaks["hbm_gbs"] * 1e9)
+                    kernels[k].update({"ms_per_launch": ms_launch, "tflops": fl / ms_launch / 1e9, "gbs": by / ms_launch / 1e6,
+                                       "bound": "tensor" if t_tensor >= t_hbm else "hbm",
+                                       "frac_of_roofline": max(t_tensor, t_hbm) * 1e3 / ms_launch})
             kernels["_sum_ms_per_step"] = tot
+            # the dominant single kernel (largest share of the step) against the roofline that bounds it
+            top = max((k for k in kernels if k in models and "bound" in kernels[k]), key=lambda k: kernels[k]["share"], default=None)
+            if top:
+                kt = kernels[top]
+                fl, by = models[top]
+                tensor = kt["bound"] == "tensor"
+                roof_top = {"kernel": top, "bound": kt["bound"], "achieved": kt["tflops"] if tensor else kt["gbs"],
+                            "peak": peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"],
+                            "unit": "TFLOP/s" if tensor else "GB/s", "ms_per_launch": kt["ms_per_launch"],
+                            "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": by,
+                            "traffic": traffic.get(top), "share_of_step": kt["share"],
+                            "peak_kind": f"{peaks['_src']} sustained (kernel timed inside a long step)"}
+                roof_top["frac"] = roof_top["achieved"] / roof_top["peak"]
+                roof = dict(roof_top, family=roof)
         base = None
         if not args.no_cpu_baseline and world == 1:
             base, _ = cpu_baseline(3, 1)

@@ -64,17 +64,52 @@ __device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_
                  : "memory");
 }
 
-// pass-2 math for 32 score columns already in registers: p = 2^(s*log2e - mb) -> 16 packed bf16 pairs; returns sum(p)
+// 2^t for a packed pair on the FMA/ALU pipes (no MUFU): t = n + f with n = round(t) (magic-number add), f in [-0.5, 0.5],
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, far below the bf16 rounding of P), 2^n by adding n
+// to the exponent field.  t is clamped at -126 (the result underflows to ~1e-38 there).
+__device__ __forceinline__ void ex2_poly_pair(f32x2 t, float& p0, float& p1) {
+    float t0, t1;
+    f2_unpack(t, t0, t1);
+    t = f2_pack(fmaxf(t0, -126.0f), fmaxf(t1, -126.0f));
+    const f32x2 magic = f2_pack(12582912.0f, 12582912.0f), nmagic = f2_pack(-12582912.0f, -12582912.0f);
+    const f32x2 r = f2_add(t, magic);                 // low mantissa bits of r = round(t)
+    const f32x2 n = f2_add(r, nmagic);
+    const f32x2 f = f2_fma(n, f2_pack(-1.0f, -1.0f), t);
+    f32x2 q = f2_fma(f2_pack(0.05517145f, 0.05517145f), f, f2_pack(0.24261084f, 0.24261084f));
+    q = f2_fma(q, f, f2_pack(0.69326097f, 0.69326097f));
+    q = f2_fma(q, f, f2_pack(0.9999281f, 0.9999281f));
+    float q0, q1, r0, r1;
+    f2_unpack(q, q0, q1);
+    f2_unpack(r, r0, r1);
+    p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(r0) << 23));
+    p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
+}
+
+// pass-2 math for 32 score columns already in registers: p = 2^(s*log2e - mb) -> 16 packed bf16 pairs; returns sum(p).
+// The exponentials are what bounds this kernel (16 MUFU results per clock and SM): kPolyPairs of every 16 column pairs
+// take the polynomial path instead, which balances the MUFU pipe against the issue slots of the sub-partition.
+template <int kPolyPairs>
 __device__ __forceinline__ float softmax_math32(const uint32_t (&r)[32], uint32_t (&o)[16], float mb) {
-    float s0 = 0.f, s1 = 0.f;
+    const f32x2 l2 = f2_pack(atc::LOG2E, atc::LOG2E), nmb = f2_pack(-mb, -mb);
+    f32x2 acc = f2_pack(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), atc::LOG2E, -mb));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), atc::LOG2E, -mb));
-        o[i >> 1] = pack_bf16x2(p0, p1);
-        s0 += p0;
-        s1 += p1;
+    for (int i = 0; i < 16; ++i) {
+        const f32x2 t = f2_fma(f2_pack(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), l2, nmb);
+        float p0, p1;
+        // interleave the two kinds so that MUFU latency hides behind polynomial work
+        if ((i * kPolyPairs) % 16 < kPolyPairs) {
+            ex2_poly_pair(t, p0, p1);
+        } else {
+            float t0, t1;
+            f2_unpack(t, t0, t1);
+            p0 = ex2_approx(t0);
+            p1 = ex2_approx(t1);
+        }
+        o[i] = pack_bf16x2(p0, p1);
+        acc = f2_add(acc, f2_pack(p0, p1));
     }
+    float s0, s1;
+    f2_unpack(acc, s0, s1);
     return s0 + s1;
 }
 __device__ __forceinline__ float max32(const uint32_t (&r)[32], float m) {
@@ -99,6 +134,7 @@ __device__ __forceinline__ float dot8(const uint4& u, const float* q, float a) {
 // phase timing of one softmax warp of block 0 (dbg != nullptr only in profiles/attn_timing.py)
 #define ATT_T(i) do { if (dbg_on) { const long long _t = clock64(); dbg_acc[i] += _t - dbg_t; dbg_t = _t; } } while (0)
 
+template <int kPolyPairs>
 __global__ void __launch_bounds__(atc::THREADS, 1)
 attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_constant__ TmaDesc map16,
                        const __grid_constant__ TmaDesc mapO, const bf16* __restrict__ qkv, bf16* __restrict__ out,
@@ -266,10 +302,10 @@ attention_tc257_kernel(const __grid_constant__ TmaDesc map128, const __grid_cons
 #pragma unroll
             for (int c = 0; c < 8; c += 2) {
                 tmem_ld_32x32b_x32(buf + (c + 1) * 32, rb);
-                sum += softmax_math32(ra, o, mb); tmem_st_32x32b_x16(buf + c * 16, o);
+                sum += softmax_math32<kPolyPairs>(ra, o, mb); tmem_st_32x32b_x16(buf + c * 16, o);
                 tmem_ld_wait();
                 if (c + 2 < 8) tmem_ld_32x32b_x32(buf + (c + 2) * 32, ra);
-                sum += softmax_math32(rb, o, mb); tmem_st_32x32b_x16(buf + (c + 1) * 16, o);
+                sum += softmax_math32<kPolyPairs>(rb, o, mb); tmem_st_32x32b_x16(buf + (c + 1) * 16, o);
                 if (c + 2 < 8) tmem_ld_wait();
             }
             tmem_st_wait();
@@ -457,14 +493,18 @@ int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int nu
     MST_PROPAGATE(make_tma_3d_bf16(&m128, qkv, 3 * E, N_TOK, BD, 3 * E, static_cast<uint64_t>(N_TOK) * 3 * E, 64, 128, true));
     MST_PROPAGATE(make_tma_3d_bf16(&m16, qkv, 3 * E, N_TOK, BD, 3 * E, static_cast<uint64_t>(N_TOK) * 3 * E, 64, 16, true));
     MST_PROPAGATE(make_tma_3d_bf16(&mO, out, E, N_TOK, BD, E, static_cast<uint64_t>(N_TOK) * E, 32, 32, false));
+    static const int poly = getenv("MST_ATTN_POLY") ? atoi(getenv("MST_ATTN_POLY")) : 7;  // experiments: 0 = all exponentials on MUFU
+    // 7 of 16 pairs on the polynomial: measured optimum (kernel 0.547 ms with 0, 0.495 / 0.469 / 0.510 / 0.499 / 0.569 ms with
+    // 6 / 7 / 8 / 10 / 12 of 16, config-2 shape, profiles/attn_timing.py)
+    auto kern = poly == 0 ? attention_tc257_kernel<0> : attention_tc257_kernel<7>;
     static bool attr = false;
     if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(attention_tc257_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
+        MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
         attr = true;
     }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
-    attention_tc257_kernel<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg);
+    kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaDesc tmB, const __grid_constant__ TmaDesc tmC,
                int M, int N, int K, int mode_flags, EpiParams ep) {
     using L = GemmSmem<BN, KCH, STAGES, NSTG, EW, PAIR>;
-    constexpr bool MCAST = PAIR == 1;
+    constexpr int MC = PAIR == 1 ? 2 : (PAIR == 4 ? 4 : 1);  // CTAs sharing one A stage by TMA multicast
+    constexpr bool MCAST = MC > 1;
     constexpr bool TWO = PAIR == 2;
     constexpr int BMT = TWO ? 2 * BM : BM;  // rows of one tile (the pair's 256-row tile in cta_group::2 mode)
     const int mode = mode_flags & 0xff;
@@ -292,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         tma_prefetch_desc(&tmC);
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], MCAST ? 2 : 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], MC); }
         mbar_init(bfull_bar, 1);
         // cta_group::2: the leader's accumulator-free barrier collects the epilogue warps of BOTH CTAs
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], TWO ? 2 * EPI_WARPS : EPI_WARPS); }
@@ -336,12 +337,12 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 const int n_blk = kResident ? n_fixed : t % n_tiles;
                 // (streaming mode: prefetching there made fc2 13 % slower -- every CTA of an m-block row would issue the same
                 //  prefetches -- so it is limited to the resident schedule, where one cluster per m-group issues them)
-                if (kResident && n_fixed < (MCAST ? 2 : 1) && it + kPrefetchTiles < t_count) {
+                if (kResident && n_fixed < MC && it + kPrefetchTiles < t_count) {
                     // pull the A rows of a later tile into L2 now: under load a TMA load that misses L2 takes ~3000 clk,
                     // far more than the 4 x 384 clk of MMA work the operand ring can cover (profiles/gemm_timing.py)
                     const int m_pf = t + kPrefetchTiles * t_step;
                     for (int kc = 0; kc < kchunks; ++kc)
-                        tma_prefetch_l2_2d(&tmA, kc * BK, m_pf * BMT + row_off + (MCAST ? static_cast<int>(cta_rank) * (BM / 2) : 0));
+                        tma_prefetch_l2_2d(&tmA, kc * BK, m_pf * BMT + row_off + (MCAST ? static_cast<int>(cta_rank) * (BM / MC) : 0));
                 }
                 for (int kc = 0; kc < kchunks; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -357,8 +358,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     }
                     mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + (kResident ? 0 : L::B_TILE_BYTES));
                     if (MCAST)
-                        tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + cta_rank * (A_STAGE_BYTES / 2), &tmA, &full_bar[stage],
-                                              kc * BK, m_blk * BM + static_cast<int>(cta_rank) * (BM / 2), 0x3);
+                        tma_load_2d_multicast(sA + stage * A_STAGE_BYTES + cta_rank * (A_STAGE_BYTES / MC), &tmA, &full_bar[stage],
+                                              kc * BK, m_blk * BM + static_cast<int>(cta_rank) * (BM / MC), (1u << MC) - 1);
                     else
                         tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], kc * BK, m_blk * BM);
                     if (!kResident)
@@ -409,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                         umma_commit_pair(&empty_bar[stage], 0x3);                          // both CTAs refill their slot
                         if (kc == kchunks - 1) umma_commit_pair(&tfull_bar[acc], 0x3);      // both epilogues read their half
                     } else {
-                        if (MCAST) umma_commit_multicast(&empty_bar[stage], 0x3);  // both CTAs refill this slot
+                        if (MCAST) umma_commit_multicast(&empty_bar[stage], (1u << MC) - 1);  // every CTA of the cluster refills this slot
                         else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
                         if (kc == kchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                     }
@@ -556,7 +557,8 @@ template <int BN, int KCH, int STAGES, int NSTG, int EW, int PAIR = 0>
 static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC, int M, int N, int K, int mode,
                       const EpiParams& ep, int num_sms, cudaStream_t stream) {
     using L = GemmSmem<BN, KCH, STAGES, NSTG, EW, PAIR>;
-    constexpr bool MCAST = PAIR != 0;  // launched as clusters of two
+    constexpr bool MCAST = PAIR != 0;  // launched as clusters
+    constexpr int CLUSTER = PAIR == 4 ? 4 : 2;
     auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG, EW, PAIR>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -581,7 +583,7 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gemm_threads(EW)); cfg.dynamicSmemBytes = L::DYN_BYTES; cfg.stream = stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, mode, ep));
     } else {
@@ -633,9 +635,17 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
             // GELU epilogue (fc1) is the longest: two staging tiles per warp (a TMA store stays in flight while the next
             // chunk is computed) paid for with a 3-deep A ring; the L2 prefetch keeps the shorter ring fed
+            static const int mc4 = getenv("MST_GEMM_MC4") ? atoi(getenv("MST_GEMM_MC4")) : 0;  // experiments only
+            if (mc4 && (N / 192) % 4 == 0) {  // four adjacent n-blocks share every A stage: each CTA fetches 32 rows
+                TmaDesc tmAq;
+                MST_PROPAGATE(make_tma_2d_bf16(&tmAq, A, K, M, K, BK, BM / 4));
+                if ((mode & 0xff) == EPI_BIAS_GELU || (mode & 0xff) == EPI_LN_BIAS_GELU)
+                    return launch_cfg<192, 6, 3, 1, 12, 4>(tmAq, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+                return launch_cfg<192, 6, 4, 1, 8, 4>(tmAq, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+            }
             if ((mode & 0xff) == EPI_BIAS_GELU || (mode & 0xff) == EPI_LN_BIAS_GELU)
-                return launch_cfg<192, 6, 3, 1, 12, true>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-            return launch_cfg<192, 6, 4, 1, 8, true>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+                return launch_cfg<192, 6, 3, 1, 12, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+            return launch_cfg<192, 6, 4, 1, 8, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
         }
         // K too large for a resident weight slab (fc2): both operands stream through the ring
         MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));

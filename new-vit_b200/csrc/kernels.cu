@@ -191,34 +191,43 @@ template int launch_layernorm<bf16, float>(const bf16*, int64_t, float*, int64_t
 template <int E>
 __global__ void __launch_bounds__(256) row_stats_kernel(const bf16* __restrict__ x, float* __restrict__ rowstat, int rows,
                                                          float eps) {
+    // half a warp per row, 16-byte loads: lane l of the half-warp owns the chunks l, l+16, ... of the row
     constexpr int V = E / 128;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    const bf16* xr = x + static_cast<int64_t>(row) * E;
-    float v[V][4];
+    const int row = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+    const int hl = threadIdx.x & 15;
+    const bool ok = row < rows;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(ok ? row : 0) * E);
+    float v[V][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-        Vec4<bf16>::load(xr + i * 128 + lane * 4, v[i]);
-        s += (v[i][0] + v[i][1]) + (v[i][2] + v[i][3]);
+        const uint4 u = __ldg(xr + i * 16 + hl);
+        float2 f;
+        f = unpack_bf16x2(u.x); v[i][0] = f.x; v[i][1] = f.y;
+        f = unpack_bf16x2(u.y); v[i][2] = f.x; v[i][3] = f.y;
+        f = unpack_bf16x2(u.z); v[i][4] = f.x; v[i][5] = f.y;
+        f = unpack_bf16x2(u.w); v[i][6] = f.x; v[i][7] = f.y;
+        s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
     }
-    const float mean = warp_sum(s) * (1.0f / E);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / E);
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
             const float d = v[i][j] - mean;
             q = fmaf(d, d, q);
         }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / E) + eps);
-    if (lane == 0) rowstat[row] = rstd;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (ok && hl == 0) rowstat[row] = rsqrtf(q * (1.0f / E) + eps);
 }
 
 int launch_row_stats(const bf16* x, float* rowstat, int rows, int E, float eps, cudaStream_t stream) {
     if (rows <= 0) return 0;
-    const int grid = (rows + 7) / 8;
+    const int grid = (rows + 15) / 16;
     if (E == 384) row_stats_kernel<384><<<grid, 256, 0, stream>>>(x, rowstat, rows, eps);
     else if (E == 768) row_stats_kernel<768><<<grid, 256, 0, stream>>>(x, rowstat, rows, eps);
     else if (E == 1024) row_stats_kernel<1024><<<grid, 256, 0, stream>>>(x, rowstat, rows, eps);
