@@ -568,7 +568,20 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     constexpr int CPU_ = PAIR == 2 ? 2 : 1;               // CTAs per scheduling unit (a cta_group::2 pair shares its tiles)
     const int n_tiles = N / BN;
     const int m_tiles = (M + BM * CPU_ - 1) / (BM * CPU_);
-    const int units = num_sms / CPU_;
+    int units = num_sms / CPU_;
+    if (CLUSTER == 4 && MCAST) {  // clusters of 4 do not tile every GPC: size the grid to what is co-resident
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(num_sms / 4 * 4); q.blockDim = dim3(gemm_threads(EW)); q.dynamicSmemBytes = L::DYN_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 4; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            q.attrs = qa; q.numAttrs = 1;
+            MST_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &q));
+        }
+        if (max_clusters * 4 < units) units = max_clusters * 4;
+    }
     int grid;
     if (KCH > 0) {
         int gs = units / n_tiles;
