@@ -133,6 +133,11 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t inner, uint64_t ro
 
 int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
                      uint64_t stride2_elems, uint32_t box0, uint32_t box1, bool swizzle128);
+// weights-in-TMEM transposed-accumulator GEMM for K = 384, N >= 1024 (qkv, fc1): gemm_wt.cu
+struct EpiParams;
+bool gemm_wt_supported(int M, int N, int K, int mode, const EpiParams& ep);
+int gemm_bf16_wt(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
+                 cudaStream_t stream);
 // tcgen05 attention for N == 257 tokens (ViT-S/B @224); other N use the warp-MMA kernel
 int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
                            long long* dbg = nullptr);

@@ -445,8 +445,10 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             if (ln_fold && row_ok) rstat = __ldg(ep.rowstat + row);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
 
+            const bool dbg_w = ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
             auto process = [&](const uint32_t (&r)[32], int c) {
                 uint32_t o[16];
+                const long long p0 = dbg_w ? clock64() : 0;
                 const int n0 = nbase + c * 32;
                 const float* b = bias0 + c * 32;
                 switch (mode) {
@@ -489,26 +491,30 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     // the tile written two stores ago must no longer be read by its TMA store
                     uint8_t* tile = stg + stg_sel * STG_TILE;
                     if (NSTG == 2) stg_sel ^= 1;
+                    const long long p1 = dbg_w ? clock64() : 0;
                     if (lane == 0) tma_store_wait_read<(NSTG == 2 ? 1 : 0)>();
                     __syncwarp();
+                    const long long p2 = dbg_w ? clock64() : 0;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<uint4*>(tile + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
                             make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
+                    const long long p3 = dbg_w ? clock64() : 0;
                     if (lane == 0) {
                         if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, tile, n0, row0);
                         else tma_store_2d(&tmC, tile, n0, row0);
                         tma_store_commit();
                     }
+                    if (dbg_w) { const long long p4 = clock64(); ep.dbg[8] += p1 - p0; ep.dbg[9] += p2 - p1; ep.dbg[10] += p3 - p2; ep.dbg[11] += p4 - p3; }
                 }
             };
             auto release_tmem = [&]() {  // every tcgen05.ld of this tile has completed
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) {
-                    if (TWO && !leader) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+                    if (TWO && !leader) mbar_arrive_cluster_relaxed(mapa_u32(&tempty_bar[acc], 0));
                     else mbar_arrive(&tempty_bar[acc]);
                 }
             };
@@ -614,6 +620,13 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
     // in-place residual update: `out += acc + bias` as 16-byte vector reductions (no residual read by the SM)
     if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) mode = EPI_BIAS_ACCUM;
+    static const int use_wt = getenv("MST_GEMM_WT") ? atoi(getenv("MST_GEMM_WT")) : 1;  // 0: experiments / A-B comparisons
+    if (use_wt && gemm_wt_supported(M, N, K, mode, ep)) {
+        static const int wt_skip = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;  // experiments only
+        EpiParams e2 = ep;
+        e2.P = wt_skip;
+        return gemm_bf16_wt(A, W, M, N, K, mode, e2, num_sms, stream);  // weights in TMEM, 16 epilogue warps (gemm_wt.cu)
+    }
     TmaDesc tmA, tmB, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
     // output maps (unused by EPI_PATCH, whose rows are re-mapped)

@@ -1,0 +1,388 @@
+// bf16 GEMM with the WEIGHTS resident in tensor memory, for the K = 384 projections with a wide output (qkv, fc1):
+//     out[t, f] = epi( sum_k x[t, k] W[f, k] )          (nn.Linear; attention.py:57, mlp.py:35-36 of the reference)
+//
+// The tensor core computes the TRANSPOSED product  D^T[f, t] = W[f, :] . x[t, :]  with tcgen05.mma in its TS form: the
+// "A" operand (128 features x 384 k of this CTA's weight block = 192 TMEM columns of bf16 pairs) is written into tensor
+// memory once per CTA, the "B" operand (a 128-token tile of x) streams through shared memory.  A CTA pair drives one
+// cta_group::2 MMA (256 features x 128 tokens): each CTA holds its own 128 features and fetches HALF of every token tile.
+//
+// Why (profiles/gemm_timing.py on the weight-in-shared-memory kernel, gemm_tc.cu): with the 144 KB weight slab in shared
+// memory only a 3-4 stage operand ring and ONE 2 KB staging tile per epilogue warp fit, 12 epilogue warps were the most
+// that could be fed, all of them ran their MUFU-heavy GELU phase at the same time and their store phase at the same time,
+// and the epilogue (3200-3600 cycles per 128x192 tile) -- not the MMA (2000) -- set the pace.  With the weights in TMEM the
+// shared memory holds a 16-stage ring of 8 KB token half-tiles (128 KB in flight per SM) and two staging tiles for each
+// of SIXTEEN epilogue warps, which work in two teams on alternate accumulator stages: the tanh phase of one team overlaps
+// the TMEM-read / staging / TMA-store phase of the other.  Shared-memory port load per MMA drops from 10 KB (A 4 KB + W 6 KB
+// per 128x192x16) to 2 KB per CTA (its half of the token tile, 256x128x16 per pair).
+//
+//   warp 0 (1 lane)   TMA producer: token half-tiles (64 tokens x 64 k, 128B swizzle), both CTAs' bytes complete on the
+//                     leader's barriers
+//   warp 1            MMA issuer (leader CTA): 24 x tcgen05.mma.cta_group::2 (M256 N128 K16) per tile, A from TMEM
+//   warp 2            TMEM allocator (512 columns: 192 weights + 2 x 128 accumulator)
+//   warps 4..19       epilogue: warp e -> TMEM lane quadrant e%4 (32 features), team (e/4)%2 = accumulator stage = tile
+//                     parity, token half e/8 (2 chunks of 32 tokens).  lane = feature, register j = token: rstd[token] and
+//                     bias[feature] applied, GELU, bf16, transposed through a [32 tokens][32 features] staging tile
+//                     (st.shared.b16, conflict-free) and written with one TMA store per chunk.
+#include <stdlib.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mst {
+
+namespace wt {
+constexpr int K = 384;
+constexpr int KCH = K / 64;                       // 64-wide k chunks (one ring stage each)
+constexpr int NT = 128;                           // tokens per tile (MMA N)
+constexpr int NTH = NT / 2;                       // tokens fetched by each CTA of the pair
+constexpr int STAGE_BYTES = NTH * 128;            // 8 KB
+constexpr int STAGES = 16;
+constexpr int EW = 16;                            // epilogue warps
+constexpr int THREADS = 128 + EW * 32;            // 640
+constexpr int STG_TILE = 32 * 64;                 // [32 tokens][32 features] bf16
+constexpr int kPrefetchTiles = 5;                // L2 prefetch distance (the ring itself covers 2.7 tiles)
+constexpr int W_COLS = K / 2;                     // 192 TMEM columns of bf16 pairs
+constexpr int RING_OFF = 0;
+constexpr int STG_OFF = STAGES * STAGE_BYTES;     // 2 staging tiles per epilogue warp
+constexpr int RS_OFF = STG_OFF + EW * 2 * STG_TILE;   // 64 rstd floats per epilogue warp
+constexpr int BAR_OFF = RS_OFF + EW * 64 * 4;
+constexpr int NUM_BARS = 2 * STAGES + 4;          // full[S], empty[S], tfull[2], tempty[2]
+constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
+constexpr int DYN_BYTES = TOTAL + 1024;
+static_assert(DYN_BYTES <= 232448, "shared memory budget");
+static_assert(W_COLS + 2 * NT <= 512, "TMEM budget");
+}  // namespace wt
+
+__device__ __forceinline__ void umma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the two bf16 halves of `u` go to [addr] and [addr + 64] (rows j and j+1 of the staging tile)
+__device__ __forceinline__ void sts_bf16_pair_rows(uint32_t addr, uint32_t u) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b16 l, h;\n\t"
+        "mov.b32 {l, h}, %1;\n\t"
+        "st.shared.b16 [%0], l;\n\t"
+        "st.shared.b16 [%0+64], h;\n\t"
+        "}\n" ::"r"(addr),
+        "r"(u)
+        : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(wt::THREADS, 1)
+gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaDesc tmC, const bf16* __restrict__ W,
+               int M, int N, int n_pairs, EpiParams ep) {
+    using namespace wt;
+    constexpr bool LNF = MODE == EPI_LN_BIAS || MODE == EPI_LN_BIAS_GELU;
+    constexpr bool GELU = MODE == EPI_BIAS_GELU || MODE == EPI_LN_BIAS_GELU;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + STAGES;
+    uint64_t* tfull_bar = bars + 2 * STAGES;
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    // schedule: pair `unit` owns the feature pair unit % n_pairs (256 features) and walks the token tiles
+    // unit / n_pairs, + groups, + 2 groups ... (pairs of one group read the same token tiles at about the same time)
+    const int unit = static_cast<int>(blockIdx.x >> 1);
+    const int units = static_cast<int>(gridDim.x >> 1);
+    const int groups = units / n_pairs;
+    const int m_tiles = (M + NT - 1) / NT;
+    const int t_first = unit / n_pairs;
+    const int t_count = t_first < m_tiles ? (m_tiles - t_first + groups - 1) / groups : 0;
+    const int f0 = (unit % n_pairs) * 256 + static_cast<int>(cta_rank) * 128;   // first feature of this CTA
+
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmC); }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        // each accumulator stage is drained by ONE team (8 warps) in each CTA of the pair
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * (EW / 2)); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_pair<512>(tmem_ptr_smem);
+    tc_fence_before_sync();
+    cluster_sync_all();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // ---- this CTA's 128 x 384 weight block -> TMEM columns [0, 192): lane = feature, column c = (W[f][2c], W[f][2c+1]) ----
+    if (warp >= 4 && warp < 8) {
+        const int q = warp & 3;
+        const int f = f0 + q * 32 + lane;
+        const uint4* src = reinterpret_cast<const uint4*>(W + static_cast<int64_t>(f < N ? f : 0) * K);
+        const uint32_t dst = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 2
+        for (int c = 0; c < W_COLS / 16; ++c) {
+            uint32_t r[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 u = __ldg(src + c * 4 + i);
+                if (f >= N) u = make_uint4(0u, 0u, 0u, 0u);   // padded feature block (N not a multiple of 256)
+                r[4 * i] = u.x; r[4 * i + 1] = u.y; r[4 * i + 2] = u.z; r[4 * i + 3] = u.w;
+            }
+            tmem_st_32x32b_x16(dst + c * 16, r);
+        }
+        tmem_st_wait();
+    }
+    tc_fence_before_sync();
+    cluster_sync_all();   // the leader's MMAs read the weight block of BOTH CTAs
+    tc_fence_after_sync();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < ((ep.P & 4) ? 0 : t_count); ++it) {   // (experiment 4: no operand traffic at all)
+                const int tok0 = (t_first + it * groups) * NT + static_cast<int>(cta_rank) * NTH;
+                // One pair per group pulls a later token tile into L2 (the other pairs of the group read the same rows):
+                // under load an HBM miss costs more than the ring covers, an L2 hit does not.
+                if (unit % n_pairs == 0 && it + kPrefetchTiles < t_count) {
+                    for (int kc = 0; kc < KCH; ++kc) tma_prefetch_l2_2d(&tmX, kc * 64, tok0 + kPrefetchTiles * groups * NT);
+                }
+                for (int kc = 0; kc < KCH; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+                    tma_load_2d_pair(smem + RING_OFF + stage * STAGE_BYTES, &tmX, full_leader, kc * 64, tok0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1 && leader) {
+        // ===================== MMA issuer (whole warp convergent, one elected lane issues) =====================
+        constexpr uint32_t idesc = umma_idesc_bf16_f32(256, NT);
+        constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B | version 1 | SWIZZLE_128B
+        const uint32_t b_lo0 = (smem_u32(smem + RING_OFF) & 0x3FFFF) >> 4;
+        int stage = 0; uint32_t phase = 0;
+        long long gd[2] = {0, 0};
+        const long long gstart = clock64();
+        for (int it = 0; it < t_count; ++it) {
+            const int acc = it & 1;
+            const long long g0 = clock64();
+            mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+            gd[0] += clock64() - g0;
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(W_COLS + acc * NT);
+            for (int kc = 0; kc < KCH; ++kc) {
+                const long long g1 = clock64();
+                if (!(ep.P & 4)) mbar_wait(&full_bar[stage], phase);
+                gd[1] += clock64() - g1;
+                tc_fence_after_sync();
+                const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ts_pair(d_tmem, tmem_base + static_cast<uint32_t>((kc * 4 + k) * 8), make_desc(b_lo + 2 * k, kDescHi),
+                                          idesc, (kc | k) != 0 ? 1u : 0u);
+                    if (!(ep.P & 4)) umma_commit_pair(&empty_bar[stage], 0x3);      // both CTAs refill their slot
+                    if (kc == KCH - 1) umma_commit_pair(&tfull_bar[acc], 0x3);      // both CTAs' teams read their half
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        if (ep.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+            ep.dbg[0] = gd[0]; ep.dbg[1] = gd[1]; ep.dbg[2] = clock64() - gstart; ep.dbg[3] = t_count;
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: two teams on alternate tiles =====================
+        const int e = warp - 4;
+        const int q = e & 3, team = (e >> 2) & 1, half = e >> 3;
+        const int feat0 = f0 + q * 32;                      // first feature of this warp's 32 TMEM lanes
+        const int f = feat0 + lane;
+        const float bias = f < N ? __ldg(ep.bias + f) : 0.f;
+        const f32x2 bias2 = f2_pack(bias, bias);
+        uint8_t* stg = smem + STG_OFF + e * 2 * STG_TILE;
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(W_COLS + team * NT + half * 64);
+        const bool store_ok = feat0 < N;
+        const bool skip_epi = (ep.P & 1) != 0;   // experiment: mainloop ceiling (accumulators are read and dropped)
+        const bool dbg_all = ep.dbg != nullptr && blockIdx.x < 2 && lane == 0;
+        long long busy = 0, waitt = 0;
+        float* rsb = reinterpret_cast<float*>(smem + RS_OFF) + e * 64;   // this warp's 64 rstd values of the current tile
+        bf16* const outp = static_cast<bf16*>(ep.out);
+        for (int it = team; it < t_count; it += 2) {
+            const int tok_tile = (t_first + it * groups) * NT + half * 64;
+            // rstd of this warp's 64 tokens: requested BEFORE the wait on the accumulator, so the L2 round trip hides behind it
+            float rs0 = 0.f, rs1 = 0.f;
+            if (LNF) {
+                if (tok_tile + lane < M) rs0 = __ldg(ep.rowstat + tok_tile + lane);
+                if (tok_tile + 32 + lane < M) rs1 = __ldg(ep.rowstat + tok_tile + 32 + lane);
+            }
+            const long long w0 = dbg_all ? clock64() : 0;
+            mbar_wait(&tfull_bar[team], (it >> 1) & 1);
+            const long long w1 = dbg_all ? clock64() : 0;
+            waitt += w1 - w0;
+            tc_fence_after_sync();
+            if (LNF) { rsb[lane] = rs0; rsb[32 + lane] = rs1; }
+            __syncwarp();
+            auto release = [&]() {   // every tcgen05.ld of this tile has completed: the stage goes back to the MMA warp
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader) mbar_arrive(&tempty_bar[team]);
+                    else mbar_arrive_cluster_relaxed(mapa_u32(&tempty_bar[team], 0));
+                }
+            };
+            if (skip_epi) {
+                if (!(ep.P & 2)) {   // (experiment 2: not even the TMEM reads)
+                    uint32_t r0[16];
+                    for (int g = 0; g < 4; ++g) { tmem_ld_32x32b_x16(taddr0 + g * 16, r0); tmem_ld_wait(); }
+                }
+                release();
+                continue;
+            }
+            // 16 tokens (8 packed pairs) at a time, double-buffered: 32 accumulator registers live instead of 64, which is what
+            // lets ptxas interleave the eight independent GELU chains (with 64 live it serialised them: one chain at a time,
+            // ~100 cycles of dependent latency per pair -- the ncu source page showed every chain in the same two registers)
+            auto process16 = [&](const uint32_t (&r)[16], int g) {   // g: 16-token group 0..3 of this warp's 64 tokens
+                uint8_t* tile = stg + (g >> 1) * STG_TILE;
+                const uint32_t tile_u = smem_u32(tile) + lane * 2 + (g & 1) * 16 * 64;
+                f32x2 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = f2_pack(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                if (LNF) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f32x2 r01, r23;   // (rstd[t], rstd[t+1]), (rstd[t+2], rstd[t+3]): one broadcast 16-byte shared load
+                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r01), "=l"(r23) : "r"(smem_u32(rsb + g * 16 + 4 * j)));
+                        v[2 * j] = f2_fma(v[2 * j], r01, bias2);
+                        v[2 * j + 1] = f2_fma(v[2 * j + 1], r23, bias2);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = f2_add(v[j], bias2);
+                }
+                if (GELU) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = gelu_tanh_fit2(v[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float a, b;
+                    f2_unpack(v[j], a, b);
+                    sts_bf16_pair_rows(tile_u + (2 * j) * 64, pack_bf16x2(a, b));
+                }
+            };
+            auto write_out = [&](int c) {   // the finished [32 tokens][32 features] tile c -> global
+                uint8_t* tile = stg + c * STG_TILE;
+                const int tok0 = tok_tile + c * 32;
+                if (ep.P & 16) {   // (experiment 16: vector stores instead of the TMA store)
+                    __syncwarp();
+                    if (store_ok) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr = k * 8 + (lane >> 2);
+                            const uint4 u = *reinterpret_cast<const uint4*>(tile + rr * 64 + (lane & 3) * 16);
+                            const int tok = tok0 + rr;
+                            if (tok < M) *reinterpret_cast<uint4*>(outp + static_cast<int64_t>(tok) * ep.ldo + feat0 + (lane & 3) * 8) = u;
+                        }
+                    }
+                    return;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0 && store_ok && !(ep.P & 8)) {   // (experiment 8: everything but the store itself)
+                    tma_store_2d(&tmC, tile, feat0, tok0);   // rows >= M are clipped by the tensor map
+                    tma_store_commit();
+                }
+            };
+            uint32_t r0[16], r1[16];
+            tmem_ld_32x32b_x16(taddr0, r0);
+            if (lane == 0) tma_store_wait_read<0>();   // last tile's two stores have drained the staging tiles
+            tmem_ld_wait();
+            tmem_ld_32x32b_x16(taddr0 + 16, r1);
+            __syncwarp();
+            process16(r0, 0);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x16(taddr0 + 32, r0);
+            process16(r1, 1);
+            write_out(0);
+            tmem_ld_wait();
+            tmem_ld_32x32b_x16(taddr0 + 48, r1);
+            process16(r0, 2);
+            tmem_ld_wait();
+            release();
+            process16(r1, 3);
+            write_out(1);
+            __syncwarp();   // both staging tiles have been read before the next tile overwrites them
+            if (dbg_all) busy += clock64() - w1;
+        }
+        if (dbg_all) { ep.dbg[16 + blockIdx.x * 32 + e] = busy; ep.dbg[32 + blockIdx.x * 32 + e] = waitt; }
+    }
+
+    tc_fence_before_sync();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc_pair<512>(tmem_base);
+    }
+}
+
+template <int MODE>
+static int launch_wt(const TmaDesc& tmX, const TmaDesc& tmC, const bf16* W, int M, int N, const EpiParams& ep, int num_sms,
+                     cudaStream_t stream) {
+    using namespace wt;
+    auto kern = gemm_wt_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
+        attr_set = true;
+    }
+    const int n_pairs = (N + 255) / 256;
+    const int m_tiles = (M + NT - 1) / NT;
+    int groups = (num_sms / 2) / n_pairs;
+    if (groups < 1) groups = 1;
+    if (groups > m_tiles) groups = m_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * groups * n_pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = DYN_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmX, tmC, W, M, N, n_pairs, ep));
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool gemm_wt_supported(int M, int N, int K, int mode, const EpiParams& ep) {
+    (void)M;
+    // N % 256 == 128 (qkv, 1152) also runs correctly (the last pair's second CTA is padding) but wastes a tenth of the MMAs
+    // and 8 SMs: measured 0.445 ms against 0.433 ms for the weight-in-shared-memory kernel, so only whole pairs come here.
+    static const int allow_pad = getenv("MST_GEMM_WT_PAD") ? atoi(getenv("MST_GEMM_WT_PAD")) : 0;
+    return K == wt::K && N >= 1024 && (N % 256 == 0 || (allow_pad && N % 128 == 0)) && ep.ldo % 8 == 0 &&
+           (mode == EPI_BIAS || mode == EPI_BIAS_GELU || mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU);
+}
+
+int gemm_bf16_wt(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
+                 cudaStream_t stream) {
+    using namespace wt;
+    MST_REQUIRE(gemm_wt_supported(M, N, K, mode, ep), "gemm_wt: unsupported problem M=%d N=%d K=%d mode=%d", M, N, K, mode);
+    MST_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm_wt: weight pointer must be 16-byte aligned");
+    MST_REQUIRE(!(mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU) || (reinterpret_cast<uintptr_t>(ep.rowstat) & 15) == 0,
+                "gemm_wt: rowstat must be 16-byte aligned");
+    TmaDesc tmX, tmC;
+    MST_PROPAGATE(make_tma_2d_bf16(&tmX, A, K, M, K, 64, NTH));
+    MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, M, ep.ldo, 32, 32, false, false));
+    switch (mode) {
+        case EPI_BIAS: return launch_wt<EPI_BIAS>(tmX, tmC, W, M, N, ep, num_sms, stream);
+        case EPI_BIAS_GELU: return launch_wt<EPI_BIAS_GELU>(tmX, tmC, W, M, N, ep, num_sms, stream);
+        case EPI_LN_BIAS: return launch_wt<EPI_LN_BIAS>(tmX, tmC, W, M, N, ep, num_sms, stream);
+        default: return launch_wt<EPI_LN_BIAS_GELU>(tmX, tmC, W, M, N, ep, num_sms, stream);
+    }
+}
+
+}  // namespace mst

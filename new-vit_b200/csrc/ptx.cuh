@@ -250,6 +250,13 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same arrive without the cluster-scope RELEASE: a release makes the issuing thread wait until its earlier global / shared
+// stores are visible cluster-wide (hundreds of cycles in an epilogue that streams stores; profiles/gemm_timing.py showed the
+// non-leader CTA's epilogue warps at twice the leader's time per tile).  Safe where the arrive only hands back TMEM that
+// this warp has finished READING (tcgen05.wait::ld has returned): no memory write of this thread is published by it.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load into THIS CTA's shared memory whose bytes complete on an mbarrier that may live in the peer CTA (the leader's)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint32_t bar_cluster_addr, int c0, int c1) {
     asm volatile(
@@ -277,6 +284,15 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                      smem_u32(bar)),
                  "h"(cta_mask)
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
