@@ -458,11 +458,42 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     case EPI_BIAS_RES: epilogue_math<EPI_BIAS_RES>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
                     case EPI_LN_BIAS: epilogue_math<EPI_LN_BIAS>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
                     case EPI_LN_BIAS_GELU: epilogue_math<EPI_LN_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
-                    default: epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0, rstat); break;
+                    default: if (NSTG != 2) epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0, rstat); break;
                 }
                 if (mode == EPI_PATCH) {
-                    // rows are re-mapped (one CLS row inserted per slice): direct 64-byte row stores
-                    if (row_ok) {
+                    if (NSTG == 2) {
+                        // The fp32 accumulators are transposed through this warp's 4 KB staging area so that BOTH the position
+                        // table read (fp32 [P, N]) and the re-mapped row store (one CLS row inserted per slice) are coalesced:
+                        // 4 lanes cover 32 consecutive columns of one row, 8 rows per instruction.  (Per-lane row access -- 32
+                        // scattered 16-byte pieces per instruction -- made this GEMM epilogue-bound at 12 % tensor activity.)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + ((i ^ (lane & 7)) << 4)) = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+                        __syncwarp();
+                        const int cc = lane & 3;
+                        // slice / patch index of the block's first row, once (32-bit; M < 2^31): rows of a 32-row block span at
+                        // most two slices, so the per-row indices follow without a division
+                        const int s_blk = row0 / ep.P, p_blk = row0 - s_blk * ep.P;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr = k * 8 + (lane >> 2);
+                            const int grow = row0 + rr;
+                            const float4 a0 = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * cc) ^ (rr & 7)) << 4));
+                            const float4 a1 = *reinterpret_cast<const float4*>(stg + rr * 128 + (((2 * cc + 1) ^ (rr & 7)) << 4));
+                            if (grow < M) {
+                                int p = p_blk + rr, sl = s_blk;
+                                while (p >= ep.P) { p -= ep.P; ++sl; }
+                                const float4* pb = reinterpret_cast<const float4*>(ep.posb + static_cast<int64_t>(p) * N + n0 + cc * 8);
+                                const float4 b0 = __ldg(pb), b1 = __ldg(pb + 1);
+                                const int64_t orow = static_cast<int64_t>(sl) * (ep.P + 1 + ep.R) + 1 + ep.R + p;
+                                *reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + orow * ep.ldo + n0 + cc * 8) =
+                                    make_uint4(pack_bf16x2(a0.x + b0.x, a0.y + b0.y), pack_bf16x2(a0.z + b0.z, a0.w + b0.w),
+                                               pack_bf16x2(a1.x + b1.x, a1.y + b1.y), pack_bf16x2(a1.z + b1.z, a1.w + b1.w));
+                            }
+                        }
+                        __syncwarp();
+                    } else if (row_ok) {
+                        // rows are re-mapped (one CLS row inserted per slice): direct 64-byte row stores
                         const int64_t orow = (row / ep.P) * (ep.P + 1 + ep.R) + 1 + ep.R + (row % ep.P);
                         uint4* po = reinterpret_cast<uint4*>(static_cast<bf16*>(ep.out) + orow * ep.ldo + n0);
 #pragma unroll

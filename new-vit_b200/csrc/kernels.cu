@@ -97,14 +97,38 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ s
     const int gh = H / 14, gw = W / 14, P = gh * gw;
     const int s = blockIdx.x / gh, py = blockIdx.x % gh;
     const float* base = src + (static_cast<int64_t>(s) * H + py * 14) * W;
-    for (int i = threadIdx.x; i < 14 * W; i += blockDim.x) tile[i] = __ldg(base + i);
+    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // 16-byte loads (the 14-row band starts on a 16-byte boundary when W % 4 == 0)
+        const float4* b4 = reinterpret_cast<const float4*>(base);
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        for (int i = threadIdx.x; i < 14 * W / 4; i += blockDim.x) t4[i] = __ldg(b4 + i);
+    } else {
+        for (int i = threadIdx.x; i < 14 * W; i += blockDim.x) tile[i] = __ldg(base + i);
+    }
     __syncthreads();
-    for (int px = 0; px < gw; ++px) {
-        T* orow = A0 + (static_cast<int64_t>(s) * P + py * gw + px) * KP;
-        for (int c = threadIdx.x; c < KP; c += blockDim.x) {
-            float v = 0.f;
-            if (c < 196) v = tile[(c / 14) * W + px * 14 + (c % 14)];
-            orow[c] = from_f<T>(v);
+    // thread -> 8 consecutive columns (taps) of a patch row, written as ONE 16-byte (bf16) / two 16-byte (fp32) stores;
+    // the tap -> pixel offsets depend only on the thread's column chunk and are computed once
+    const int chunks = KP >> 3;                       // 8-column chunks per patch row (KP % 8 == 0)
+    const int ch = threadIdx.x % chunks, pp = threadIdx.x / chunks, pstep = blockDim.x / chunks;
+    int offs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = ch * 8 + j;
+        offs[j] = c < 196 ? (c / 14) * W + (c % 14) : -1;
+    }
+    if (pp < pstep) {
+        for (int px = pp; px < gw; px += pstep) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = offs[j] >= 0 ? tile[offs[j] + px * 14] : 0.f;
+            T* o = A0 + (static_cast<int64_t>(s) * P + py * gw + px) * KP + ch * 8;
+            if constexpr (sizeof(T) == 2) {
+                *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                                          pack_bf16x2(v[6], v[7]));
+            } else {
+                float lo[4] = {v[0], v[1], v[2], v[3]}, hi[4] = {v[4], v[5], v[6], v[7]};
+                Vec4<T>::store(o, lo);
+                Vec4<T>::store(o + 4, hi);
+            }
         }
     }
     if (py == 0) {
