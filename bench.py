@@ -24,8 +24,20 @@ FLOP_PER_SLICE_S = 12_247_123_968
 FLOP_SLICE_TRANSFORMER_S = 60_066_816
 
 
-def flops_per_volume(D=32):
-    return FLOP_PER_SLICE_S * D + FLOP_SLICE_TRANSFORMER_S
+def flops_per_volume(D=32, model="s", img=224):
+    """Algorithmic matmul FLOPs of one volume (2*M*N*K, matmuls only)."""
+    if model == "s" and img == 224:
+        return FLOP_PER_SLICE_S * D + (FLOP_SLICE_TRANSFORMER_S if D == 32 else slice_transformer_flops(384, D))
+    E = {"s": 384, "b": 768}[model]
+    P = (img // 14) ** 2
+    N = P + 1
+    per_block = 2 * N * E * (3 * E + E + 4 * E + 4 * E) + 4 * (E // 64) * N * N * 64
+    return (2 * P * 588 * E + 12 * per_block) * D + slice_transformer_flops(E, D)
+
+
+def slice_transformer_flops(E, D):
+    L = D + 1   # in-proj, QK^T, PV, out-proj, two FFN matrices (dim_feedforward = E), head
+    return 2 * L * E * 3 * E + 4 * L * L * E + 2 * L * E * E + 4 * L * E * E + 2 * E * 2
 
 
 def gemm_flops_executed(BD, N=257, E=384, depth=12, KP=256):
@@ -107,6 +119,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="volumes per GPU per step")
     ap.add_argument("--slices", type=int, default=32)
+    ap.add_argument("--model", default="s", choices=["s", "b"], help="encoder size (config 4: b)")
+    ap.add_argument("--img", type=int, default=224, help="slice height = width (config 4: 252; 256 is rejected by the reference)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--saliency", action="store_true", help="config 3: save_attn + full-resolution saliency volume")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -115,10 +129,10 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
-    cfg = {"workload": f"MST-DINOv2 (DinoV2ClassifierSlice, random-init ViT-S/14) {args.precision} inference, "
-                       f"{args.batch} volumes x {args.slices} slices x 224x224 per GPU"
+    cfg = {"workload": f"MST-DINOv2 (DinoV2ClassifierSlice, random-init ViT-{args.model.upper()}/14) {args.precision} inference, "
+                       f"{args.batch} volumes x {args.slices} slices x {args.img}x{args.img} per GPU"
                        + (" + --get_attention saliency maps" if args.saliency else ""),
-           "volumes_per_gpu": args.batch, "slices": args.slices, "img": 224, "parallelism": f"volume-sharded dp{world}",
+           "volumes_per_gpu": args.batch, "slices": args.slices, "img": args.img, "parallelism": f"volume-sharded dp{world}",
            "l2_policy": "inputs larger than L2 (411 MB fp32 per step; 0.4-1.6 GB activations per kernel)"}
 
     if args.impl == "reference":
@@ -147,9 +161,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, D = args.batch, args.slices
     torch.manual_seed(0)
-    model = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=args.precision).to(dev).eval()
-    model.load_state_dict(synth.make_state_dict("s", 2, seed=0))
-    x_host = synth.make_volume(B, D, 224, 224, seed=rank).pin_memory()
+    model = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=args.precision, model_size=args.model, img_size=args.img).to(dev).eval()
+    model.load_state_dict(synth.make_state_dict(args.model, 2, seed=0, img_size=args.img))
+    x_host = synth.make_volume(B, D, args.img, args.img, seed=rank).pin_memory()
     x_dev = x_host.to(dev)
 
     def step(src):
@@ -230,7 +244,7 @@ def main():
             gemm_cats = ["gemm_patch", "gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_cls_rows"]
             gemm_ms = sum(prof[c][0] for c in gemm_cats) / args.steps
             gemm_n = sum(prof[c][1] for c in gemm_cats) // args.steps
-            fl = gemm_flops_executed(B * D)
+            fl = gemm_flops_executed(B * D, N=1 + (args.img // 14) ** 2, E={'s': 384, 'b': 768}[args.model])
             ach = fl / (gemm_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"]
             roof = {"kernel": "gemm_tc_kernel (tcgen05/TMA/TMEM bf16 GEMM family, %d launches/step)" % gemm_n, "bound": "tensor",
@@ -238,7 +252,7 @@ def main():
                     "peak_kind": f"{peaks['_src']} sustained (kernel timed inside a long step); burst {peaks['bf16_tflops']}",
                     "frac_of_burst": ach / peaks["bf16_tflops"], "flops_per_step": fl, "ms_per_step": gemm_ms, "traffic": None}
             tot = sum(v[0] for v in prof.values()) / args.steps
-            models = kernel_models(B * D)
+            models = kernel_models(B * D, N=1 + (args.img // 14) ** 2, E={'s': 384, 'b': 768}[args.model], heads={'s': 6, 'b': 12}[args.model])
             for k, (m_, n_) in prof.items():
                 kernels[k] = {"ms_per_step": m_ / args.steps, "launches_per_step": n_ / args.steps, "share": (m_ / args.steps) / tot if tot else 0}
                 if k in models and n_ and args.precision == "bf16":
@@ -266,7 +280,7 @@ def main():
         base = None
         if not args.no_cpu_baseline and world == 1:
             base, _ = cpu_baseline(3, 1)
-        model_tflops = value * flops_per_volume(D) / 1e12
+        model_tflops = value * flops_per_volume(D, args.model, args.img) / 1e12
         out = {"metric": "volumes_per_sec", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,

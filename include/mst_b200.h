@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MST_ABI_VERSION 2
+#define MST_ABI_VERSION 3
 #if defined(__GNUC__)
 #define MST_API __attribute__((visibility("default")))
 #else
@@ -29,6 +29,7 @@ extern "C" {
 enum { MST_PRECISION_FP32 = 0, MST_PRECISION_BF16 = 1 };
 /* slice_fusion constructor argument (reference dino.py:80-101,144-157) */
 enum { MST_FUSION_TRANSFORMER = 0, MST_FUSION_LINEAR = 1, MST_FUSION_AVERAGE = 2 };
+enum { MST_ROTARY_NONE = 0, MST_ROTARY_ROPE = 1 };
 
 /* Architecture of one DinoV2ClassifierSlice instance.  Replaces the constructor arguments of
  * reference dino.py:33-103 (model_size -> embed_dim/depth/enc_heads per vision_transformer.py:340-396). */
@@ -48,6 +49,9 @@ typedef struct mst_config {
     int32_t use_slice_pos_emb; /* dino.py:81-82,140-142: nn.Embedding(256, emb) added to the slice tokens */
     int32_t slice_fusion;      /* MST_FUSION_* (dino.py:80-101) */
     int32_t enable_linear;     /* dino.py:103: 0 = nn.Identity head (forward returns the feature) */
+    int32_t rotary;            /* rotary_positional_encoding (dino.py:40,92; utils/transformer_blocks.py:335-351):
+                                  MST_ROTARY_NONE, or MST_ROTARY_ROPE = RoPE on the slice-token queries and keys; the
+                                  checkpoint then carries slice_fusion.layers.0.self_attn.rotary_positional_encoding.freqs */
 } mst_config;
 
 typedef struct mst_handle_s* mst_handle;

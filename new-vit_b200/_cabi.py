@@ -14,7 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mst_b200.h")
 
 PRECISION = {"fp32": 0, "bf16": 1}
 FUSION = {"transformer": 0, "linear": 1, "average": 2}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class MSTError(RuntimeError):
@@ -24,7 +24,7 @@ class MSTError(RuntimeError):
 class MstConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("embed_dim", "depth", "enc_heads", "slice_heads", "out_ch", "pos_tokens", "precision", "device",
-                 "num_registers", "use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear")]
+                 "num_registers", "use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear", "rotary")]
 
 
 def declared_symbols():

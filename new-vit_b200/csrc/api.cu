@@ -176,6 +176,8 @@ static void expected_names(mst_handle h) {
         x[q + "norm1.weight"] = Es; x[q + "norm1.bias"] = Es;
         x[q + "norm2.weight"] = Es; x[q + "norm2.bias"] = Es;
         x["slice_fusion.norm.weight"] = Es; x["slice_fusion.norm.bias"] = Es;
+        if (h->cfg.rotary == MST_ROTARY_ROPE)   // RotaryEmbedding(dim = head_dim).freqs (rotary_embedding_torch.py:104,117)
+            x[q + "self_attn.rotary_positional_encoding.freqs"] = Es / h->cfg.slice_heads / 2;
     }
     if (h->cfg.enable_linear) {                                                                        // dino.py:98-103
         const int64_t in = h->cfg.slice_fusion == SLICE_FUSION_LINEAR ? 32LL * Es : Es;
@@ -297,6 +299,7 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
         s.n2w = h->master[q + "norm2.weight"]; s.n2b = h->master[q + "norm2.bias"];
         s.nfw = h->master["slice_fusion.norm.weight"]; s.nfb = h->master["slice_fusion.norm.bias"];
         s.in_w = h->master[q + "self_attn.in_proj_weight"];
+        if (h->cfg.rotary == MST_ROTARY_ROPE) s.rope_freqs = h->master[q + "self_attn.rotary_positional_encoding.freqs"];
         s.in_b = h->master[q + "self_attn.in_proj_bias"]; s.out_b = h->master[q + "self_attn.out_proj.bias"];
         s.l1_b = h->master[q + "linear1.bias"]; s.l2_b = h->master[q + "linear2.bias"];
         MST_PROPAGATE(transposed(h, q + "self_attn.in_proj_weight", 3 * Es, Es, &s.in_wt, st));
@@ -521,6 +524,8 @@ int mst_create(const mst_config* cfg, mst_handle* out) {
     MST_REQUIRE(cfg->num_registers >= 0 && cfg->num_registers <= 16, "mst_create: bad num_registers %d", cfg->num_registers);
     MST_REQUIRE(cfg->slice_fusion >= MST_FUSION_TRANSFORMER && cfg->slice_fusion <= MST_FUSION_AVERAGE, "mst_create: bad slice_fusion %d",
                 cfg->slice_fusion);
+    MST_REQUIRE(cfg->rotary == MST_ROTARY_NONE || (cfg->rotary == MST_ROTARY_ROPE && cfg->slice_fusion == MST_FUSION_TRANSFORMER),
+                "mst_create: rotary=%d unsupported (RoPE needs slice_fusion='transformer'; LiRE is not built)", cfg->rotary);
     MST_REQUIRE(!cfg->use_bottleneck || (cfg->embed_dim / 4) % cfg->slice_heads == 0, "mst_create: bottleneck width %d not divisible by %d heads",
                 cfg->embed_dim / 4, cfg->slice_heads);
     int ndev = 0;

@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     float* cterm = t2 + E;          // [heads] (padded to 32)
     float* red = cterm + 32;        // [40]
     float* p = red + 40;            // [heads][L]
+    float* kmat = p + ((heads * L + 3) & ~3);   // [L][E] projected keys, RoPE only
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float* hs = hs_all + static_cast<int64_t>(b) * (D + 1) * E;
@@ -616,6 +617,47 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     __syncthreads();
     // 2. q = (Wq n0 + bq) / sqrt(hd)                                    (transformer_blocks.py:166,268)
     block_matvec(n0, w.in_wt, 3 * E, w.in_b, nullptr, q, E, E, false, rsqrtf(static_cast<float>(hd)));
+    if (w.rope_freqs) {
+        // RoPE (transformer_blocks.py:262-264; rotary_embedding_torch.py:159-173,45-62): the key of sequence position j is
+        // rotated by j*freqs[i] in each feature pair (2i, 2i+1) of its head before the dot product, so the keys are
+        // materialised here (the W_k^T q re-association below needs position-independent keys).  The slice-CLS query sits
+        // at position 0, where the rotation is the identity.
+        // 3'. K[j][n] = hs[j] . Wk[n] + bk[n]
+        for (int n = threadIdx.x; n < E; n += blockDim.x) {
+            for (int j0 = 0; j0 < L; j0 += 11) {
+                float acc[11];
+#pragma unroll
+                for (int jj = 0; jj < 11; ++jj) acc[jj] = 0.f;
+                for (int k = 0; k < E; ++k) {
+                    const float wv = __ldg(w.in_wt + static_cast<int64_t>(k) * 3 * E + E + n);
+#pragma unroll
+                    for (int jj = 0; jj < 11; ++jj)
+                        if (j0 + jj < L) acc[jj] = fmaf(hs[static_cast<int64_t>(j0 + jj) * E + k], wv, acc[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 11; ++jj)
+                    if (j0 + jj < L) kmat[(j0 + jj) * E + n] = acc[jj] + w.in_b[E + n];
+            }
+        }
+        __syncthreads();
+        // 4'. s[h][j] = q_h . R_j k_{h,j}; key-padding mask -> -inf
+        for (int task = warp; task < heads * L; task += nwarps) {
+            const int h = task / L, j = task % L;
+            const float* kr = kmat + j * E + h * hd;
+            float a = 0.f;
+            for (int d = lane; d < hd; d += 32) {
+                const float kd = kr[d], kp = kr[d ^ 1];
+                float sn, cs;
+                sincosf(static_cast<float>(j) * w.rope_freqs[d >> 1], &sn, &cs);
+                const float rot = (d & 1) ? kp : -kp;                // rotate_half: (x1, x2) -> (-x2, x1)
+                a = fmaf(q[h * hd + d], kd * cs + rot * sn, a);
+            }
+            a = warp_sum(a);
+            if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(b) * D + j - 1]) a = -CUDART_INF_F;
+            if (lane == 0) p[h * L + j] = a;
+        }
+        __syncthreads();
+    } else {
     // 3. qk[h][k] = sum_d q[h,d] Wk[h*hd+d][k];  cterm[h] = q_h . bk_h
     //    (reads the UN-transposed in_proj_weight [3E][E]: consecutive threads -> consecutive k -> coalesced)
     for (int idx = threadIdx.x; idx < heads * E; idx += blockDim.x) {
@@ -642,6 +684,7 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
         if (lane == 0) p[h * L + j] = a;
     }
     __syncthreads();
+    }
     // 5. softmax per head
     for (int h = warp; h < heads; h += nwarps) {
         float m = -CUDART_INF_F;
@@ -705,7 +748,8 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
                         int mode, cudaStream_t stream) {
     MST_REQUIRE(heads <= 16 && E % heads == 0 && Eenc % 2 == 0, "slice fusion: heads=%d E=%d unsupported", heads, E);
     const int L = D + 1;
-    const size_t smem = (static_cast<size_t>(6) * E + 2 * heads * E + 32 + 40 + heads * L) * sizeof(float);
+    const size_t smem = (static_cast<size_t>(6) * E + 2 * heads * E + 32 + 40 + ((heads * L + 3) & ~3) +
+                         (w.rope_freqs ? static_cast<size_t>(L) * E : 0)) * sizeof(float);
     MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
     static bool attr = false;
     if (!attr) {

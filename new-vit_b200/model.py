@@ -8,8 +8,9 @@ Constructor variants of dino.py:56-103 are mirrored: use_registers (hub "_reg" a
 tokens), use_bottleneck, use_slice_pos_emb, slice_fusion in {'transformer','linear','average'},
 enable_linear; `img_size` is the input size `encoder.pos_embed` is built for (224 local factory, 518 hub
 checkpoints) -- other input sizes get the bicubically resampled table (vision_transformer.py:179-211).
+rotary_positional_encoding='RoPE' rotates the slice-token queries and keys (transformer_blocks.py:262-264,335-351).
 Not mirrored (raise NotImplementedError): pretrained=True (downloads hub weights; offline) and
-rotary_positional_encoding (RoPE / LieRE on the slice tokens, transformer_blocks.py:262-264,333-358).
+rotary_positional_encoding='LiRE' (transformer_blocks.py:352-358; see DESIGN.md for what the reference's version does).
 """
 import torch
 import torch.nn as nn
@@ -81,10 +82,20 @@ class _Encoder(nn.Module):
         self.norm = nn.LayerNorm(E, eps=1e-6)
 
 
+class _Rotary(nn.Module):
+    # RotaryEmbedding(dim=head_dim, theta=256, freqs_for='lang') keeps its frequencies as a (frozen) parameter
+    # (rotary_embedding_torch.py:104,117; transformer_blocks.py:335-351)
+    def __init__(self, hd):
+        super().__init__()
+        self.freqs = nn.Parameter(torch.zeros(hd // 2), requires_grad=False)
+
+
 class _SliceLayer(nn.Module):
-    def __init__(self, E, heads):
+    def __init__(self, E, heads, rope=False):
         super().__init__()
         self.self_attn = nn.MultiheadAttention(E, heads, dropout=0.0, batch_first=True)
+        if rope:
+            self.self_attn.rotary_positional_encoding = _Rotary(E // heads)
         self.linear1 = nn.Linear(E, E)
         self.linear2 = nn.Linear(E, E)
         self.norm1 = nn.LayerNorm(E)
@@ -92,9 +103,9 @@ class _SliceLayer(nn.Module):
 
 
 class _SliceFusion(nn.Module):
-    def __init__(self, E, heads):
+    def __init__(self, E, heads, rope=False):
         super().__init__()
-        self.layers = nn.ModuleList([_SliceLayer(E, heads)])
+        self.layers = nn.ModuleList([_SliceLayer(E, heads, rope)])
         self.norm = nn.LayerNorm(E)
 
 
@@ -111,8 +122,14 @@ class DinoV2ClassifierSlice(nn.Module):
             raise NotImplementedError(
                 "pretrained=True downloads hub weights (dino.py:59-63); this machine is offline. "
                 "Construct with pretrained=False and load a checkpoint with load_state_dict().")
-        if rotary_positional_encoding is not None:
-            raise NotImplementedError("rotary_positional_encoding (RoPE / LieRE on the slice tokens) is not built (SURVEY.md 8f.3)")
+        if rotary_positional_encoding not in (None, 'RoPE', 'LiRE'):
+            raise ValueError(f"Unkown parameter {rotary_positional_encoding} for rotary_positional_encoding")  # transformer_blocks.py:358
+        if rotary_positional_encoding == 'LiRE':
+            raise NotImplementedError(
+                "rotary_positional_encoding='LiRE' is not built: the reference applies ONE position-independent orthogonal matrix "
+                "and then reinterprets [B,L,heads,hd] as [B*heads,L,hd] (rotary_embedding_torch.py:338-396), see DESIGN.md")
+        if rotary_positional_encoding == 'RoPE' and slice_fusion != 'transformer':
+            rotary_positional_encoding = None               # only the transformer fusion has attention (dino.py:84-96)
         if slice_fusion not in _cabi.FUSION:
             raise ValueError(f"slice_fusion {slice_fusion!r} unsupported")
         if model_size not in synth.VIT_CFG:
@@ -127,6 +144,7 @@ class DinoV2ClassifierSlice(nn.Module):
         self.attention_maps_slice = []
         self.use_registers = use_registers
         self.slice_fusion_type = slice_fusion
+        self.rotary = rotary_positional_encoding
         self.precision = precision
         self.model_size = model_size
         pos_tokens = 1 + (img_size // 14) ** 2
@@ -141,7 +159,7 @@ class DinoV2ClassifierSlice(nn.Module):
         if slice_fusion == 'transformer':                   # dino.py:80-97
             if use_slice_pos_emb:
                 self.slice_pos_emb = nn.Embedding(256, emb)
-            self.slice_fusion = _SliceFusion(emb, synth.SLICE_HEADS)
+            self.slice_fusion = _SliceFusion(emb, synth.SLICE_HEADS, rope=rotary_positional_encoding == 'RoPE')
             self.cls_token = nn.Parameter(torch.zeros(1, 1, emb))
         head_in = emb * 32 if slice_fusion == 'linear' else emb   # dino.py:98-99
         self.linear = nn.Linear(head_in, out_ch) if enable_linear else nn.Identity()
@@ -150,7 +168,8 @@ class DinoV2ClassifierSlice(nn.Module):
                                    img_size=img_size, layerscale=hub_layout, chunked_names=not hub_layout,
                                    num_registers=self.num_registers, use_bottleneck=use_bottleneck,
                                    use_slice_pos_emb=use_slice_pos_emb and slice_fusion == 'transformer',
-                                   slice_fusion=slice_fusion, enable_linear=enable_linear)
+                                   slice_fusion=slice_fusion, enable_linear=enable_linear,
+                                   rope=rotary_positional_encoding == 'RoPE')
         nn.Module.load_state_dict(self, sd, strict=True)
         if freeze:
             for p in self.encoder.parameters():
@@ -204,7 +223,7 @@ class DinoV2ClassifierSlice(nn.Module):
             cfg = _cabi.MstConfig(E, self.encoder.depth, self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
                                   self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0],
                                   self.num_registers, int(hasattr(self, "bottleneck")), int(hasattr(self, "slice_pos_emb")),
-                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear))
+                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear), int(self.rotary == 'RoPE'))
             h = _cabi.ctypes.c_void_p()
             _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))
             self._handle, self._handle_key = h, key

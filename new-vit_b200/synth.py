@@ -44,7 +44,7 @@ def _u(g, shape, bound):
 
 def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=224,
                     layerscale=False, chunked_names=True, num_registers=0, use_bottleneck=False,
-                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True):
+                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True, rope=False):
     """Return an OrderedDict with the reference's state_dict key layout.
 
     variant: "init"  -- reference-like init distributions
@@ -130,6 +130,9 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
     sd[q + "norm2.bias"] = _n(g, (E,), 0.02)
     sd["slice_fusion.norm.weight"] = 1.0 + _n(g, (E,), 0.05)
     sd["slice_fusion.norm.bias"] = _n(g, (E,), 0.02)
+    if rope:  # RotaryEmbedding(dim=head_dim, theta=256, 'lang'): 1/theta^(2i/dim) (rotary_embedding_torch.py:104; transformer_blocks.py:339)
+        hd = E // SLICE_HEADS
+        sd[q + "self_attn.rotary_positional_encoding.freqs"] = 1.0 / (256.0 ** (torch.arange(0, hd, 2)[: hd // 2].float() / hd))
     if enable_linear:
         sd["linear.weight"] = _u(g, (out_ch, E), lin)
         sd["linear.bias"] = _u(g, (out_ch,), lin)

@@ -113,6 +113,19 @@ def encoder_forward(sd, img, heads, keep_all_maps=False):
     return x[:, 0], maps
 
 
+def rope_rotate(t, freqs):
+    """RotaryEmbedding.rotate_queries_or_keys (utils/rotary_embedding_torch.py:159-173,45-62,38-42,272-300) for the
+    configuration the slice transformer builds (transformer_blocks.py:335-351: dim = head_dim, theta = 256, 'lang' frequencies
+    1/theta^(2i/dim), no xpos, interpolate_factor 1): token at sequence position j (0 = the slice-CLS token), feature pair
+    (2i, 2i+1) rotated by the angle j*freqs[i].  t: [B, heads, L, hd]."""
+    L = t.shape[-2]
+    ang = torch.arange(L, dtype=t.dtype)[:, None] * freqs[None, :]          # einsum('..., f -> ... f', seq, freqs)
+    ang = ang.repeat_interleave(2, dim=-1)                                   # repeat '... n -> ... (n r)', r = 2
+    t1, t2 = t[..., 0::2], t[..., 1::2]
+    rot = torch.stack((-t2, t1), dim=-1).reshape(t.shape)                    # rotate_half
+    return t * ang.cos() + rot * ang.sin()
+
+
 def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
     """nn.TransformerEncoder(num_layers=1, norm) over the custom pre-LN layer
     (utils/transformer_blocks.py:524-573, 29-318; dino.py:84-96).  Explicit bmm/softmax path
@@ -128,6 +141,9 @@ def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
     q = q.reshape(B, L, heads, hd).transpose(1, 2) * math.sqrt(1.0 / hd)  # transformer_blocks.py:268
     k = k.reshape(B, L, heads, hd).transpose(1, 2)
     v = v.reshape(B, L, heads, hd).transpose(1, 2)
+    rope = q_ + "self_attn.rotary_positional_encoding.freqs"
+    if rope in sd:  # rotary_positional_encoding='RoPE' (transformer_blocks.py:262-264,335-351): q and k rotated by position
+        q, k = rope_rotate(q, sd[rope]), rope_rotate(k, sd[rope])
     s = q @ k.transpose(-2, -1)
     if key_padding_mask is not None:  # additive -inf on key columns (transformer_blocks.py:244-252)
         s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
@@ -147,7 +163,8 @@ def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
 def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps=False, slice_fusion="transformer"):
     """DinoV2ClassifierSlice.forward (dino.py:110-167).  The constructor variants are read off the state_dict
     (bottleneck.*, slice_pos_emb.weight, encoder.register_tokens, linear.* present or not); `slice_fusion`
-    selects dino.py:144-157.  Rotary encodings are not restated.
+    selects dino.py:144-157; RoPE on the slice tokens is applied when its `freqs` tensor is in the state_dict
+    (LiRE is not restated).
 
     Returns a dict: logits [B,out] (None without the linear head), feat, enc_cls [BD,E], plane_cls [BD,heads,N]
     (row 0 of the last encoder block's attention), slice_cls [B,12,L] (row 0 of slice attention), and the

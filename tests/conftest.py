@@ -31,7 +31,7 @@ def case_inputs(meta, out_ch=2):
     ctor = {k: meta[k] for k in CTOR_KEYS if k in meta}
     sd = synth.make_state_dict(meta["size"], out_ch=out_ch, seed=meta["wseed"], variant=meta["variant"],
                                img_size=meta.get("pos_img", meta["H"]), layerscale=hub, chunked_names=not hub,
-                               num_registers=meta.get("num_registers", 0), **ctor)
+                               num_registers=meta.get("num_registers", 0), rope=bool(meta.get("rope", False)), **ctor)
     x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
     mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"]) if meta["masked"] else None
     return sd, x, mask
@@ -42,6 +42,8 @@ def model_kwargs(meta):
     kw = {k: meta[k] for k in CTOR_KEYS if k in meta}
     kw.update(model_size=meta["size"], img_size=meta.get("pos_img", meta["H"]), hub_layout=bool(meta.get("hub_layout", False)),
               use_registers=meta.get("num_registers", 0) > 0)
+    if meta.get("rope"):
+        kw["rotary_positional_encoding"] = "RoPE"
     return kw
 
 

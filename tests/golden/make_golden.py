@@ -42,6 +42,10 @@ CASES = {
     # local factory (pos_embed 16x16) on a non-square 126x168 input: bicubic resampling to 9x12
     "s_interp_126x168_b2": ("s", "peaky", 2, 3, 126, 168, True, 7, 7, {"pos_img": 224}),
     "s_bottleneck_posemb_b2": ("s", "peaky", 2, 5, 112, 112, True, 8, 8, {"use_bottleneck": True, "use_slice_pos_emb": True}),
+    # rotary_positional_encoding='RoPE' on the slice tokens, with the bottleneck (the combination the reference's own
+    # tests/models/test_dinoslice.py constructs) and a padding mask
+    "s_rope_bottleneck_mask_b2": ("s", "peaky", 2, 9, 112, 112, True, 11, 11, {"use_bottleneck": True, "rope": True}),
+    "s_rope_b2": ("s", "init", 2, 32, 112, 112, False, 12, 12, {"rope": True}),
     "s_fusion_linear_b2": ("s", "init", 2, 32, 56, 56, False, 9, 9, {"slice_fusion": "linear"}),
     "s_fusion_average_nolinear_b2": ("s", "init", 2, 6, 56, 56, False, 10, 10, {"slice_fusion": "average", "enable_linear": False}),
 }
@@ -55,10 +59,12 @@ def run_case(name):
     pos_img = int(flags.get("pos_img", H))
     fusion = flags.get("slice_fusion", "transformer")
     ctor = {k: flags[k] for k in ("use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear") if k in flags}
+    rope = bool(flags.get("rope", False))
     sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=pos_img, layerscale=hub,
-                               chunked_names=not hub, num_registers=nreg, **ctor)
+                               chunked_names=not hub, num_registers=nreg, rope=rope, **ctor)
+    ref_kw = dict(ctor, rotary_positional_encoding="RoPE") if rope else ctor
     model = build_reference_model(sd, out_ch=2, model_size=size, hub_layout=hub, num_registers=nreg,
-                                  pos_img_size=pos_img if pos_img != H or nreg else None, **ctor)
+                                  pos_img_size=pos_img if pos_img != H or nreg else None, **ref_kw)
     x = synth.make_volume(B, D, H, W, seed=vseed)
     mask = synth.make_padding_mask(B, D, seed=vseed) if masked else None
     out = {}
@@ -97,7 +103,7 @@ def run_case(name):
                     out["sal_quantiles_b0"] = torch.from_numpy(np.quantile(w.numpy(), [0.5, 0.995, 0.999]))
             out["sal_sub"] = torch.stack(subs)
     meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed, hub_layout=hub,
-                num_registers=nreg, pos_img=pos_img, **ctor)
+                num_registers=nreg, pos_img=pos_img, **(dict(ctor, rope=True) if rope else ctor))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
                         meta=np.array(repr(meta)), **{k: v.numpy() for k, v in out.items()})
     print(name, "logits", out["logits_nosave"].tolist()[:2])

@@ -14,7 +14,7 @@ def test_library_loads_and_exports_all_declared_symbols():
     assert len(names) >= 14 and "mst_forward" in names and "mst_saliency" in names
     for n in names:
         assert hasattr(L, n), n
-    assert L.mst_abi_version() == 2
+    assert L.mst_abi_version() == 3
 
 
 def test_no_cpu_fallback():
@@ -53,24 +53,28 @@ def test_state_dict_layout_matches_reference():
 
 def test_unbuilt_options_raise():
     from new_vit_b200 import DinoV2ClassifierSlice
-    for kw in (dict(pretrained=True), dict(rotary_positional_encoding="RoPE")):
+    for kw in (dict(pretrained=True), dict(rotary_positional_encoding="LiRE")):
         args = dict(in_ch=1, out_ch=2, pretrained=False)
         args.update(kw)
         with pytest.raises(NotImplementedError):
             DinoV2ClassifierSlice(**args)
     with pytest.raises(ValueError):
         DinoV2ClassifierSlice(1, 2, pretrained=False, slice_fusion="max")
+    with pytest.raises(ValueError):   # transformer_blocks.py:358
+        DinoV2ClassifierSlice(1, 2, pretrained=False, rotary_positional_encoding="xpos")
 
 
 @pytest.mark.parametrize("kw", [dict(use_bottleneck=True), dict(use_slice_pos_emb=True), dict(slice_fusion="linear"),
-                                dict(slice_fusion="average", enable_linear=False), dict(use_bottleneck=True, slice_fusion="linear")])
+                                dict(slice_fusion="average", enable_linear=False), dict(use_bottleneck=True, slice_fusion="linear"),
+                                dict(rotary_positional_encoding="RoPE", use_bottleneck=True)])
 def test_constructor_variants_keep_the_reference_state_dict_layout(kw):
     """dino.py:75-103: bottleneck, slice position embedding, slice_fusion, enable_linear add / drop / resize tensors."""
     from new_vit_b200 import DinoV2ClassifierSlice
     from oracle import ref_harness
     m = DinoV2ClassifierSlice(in_ch=1, out_ch=3, pretrained=False, **kw)
     sd = m.state_dict()
-    syn = synth.make_state_dict("s", 3, seed=1, **kw)
+    skw = {k: v for k, v in kw.items() if k != "rotary_positional_encoding"}
+    syn = synth.make_state_dict("s", 3, seed=1, rope=kw.get("rotary_positional_encoding") == "RoPE", **skw)
     assert sorted(sd.keys()) == sorted(syn.keys())
     assert all(tuple(sd[k].shape) == tuple(syn[k].shape) for k in sd)
     if ref_harness.reference_available():
