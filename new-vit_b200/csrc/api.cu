@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../include/mst_b200.h"
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mst {
@@ -379,6 +380,9 @@ template <> struct Ops<bf16> {
     static int attention(mst_handle h, const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
         if (N == 257)  // ViT @224: tcgen05 kernel; other token counts: warp-MMA kernel
             return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
+        static const int use_tcg = getenv("MST_ATTN_TCG") ? atoi(getenv("MST_ATTN_TCG")) : 1;   // 0: A-B comparisons
+        if (use_tcg && attention_tcg_supported(N))
+            return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, h->num_sms, st);
         return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, st);
     }
 };
@@ -747,6 +751,9 @@ int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N,
     if (N == 257)
         return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
                                       static_cast<cudaStream_t>(stream));
+    if (attention_tcg_supported(N))
+        return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, num_sms_current(),
+                                    static_cast<cudaStream_t>(stream));
     return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, static_cast<cudaStream_t>(stream));
 }
 int mst_debug_attention_timing(const void* qkv, void* out, int32_t BD, int32_t heads, long long* dbg_dev, void* stream) {
