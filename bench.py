@@ -129,6 +129,14 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on the first
+    # communicator), so file descriptor 1 is pointed at stderr for the run and the result goes to the saved descriptor.
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(result_fd, (json.dumps(obj) + "\n").encode())
     cfg = {"workload": f"MST-DINOv2 (DinoV2ClassifierSlice, random-init ViT-{args.model.upper()}/14) {args.precision} inference, "
                        f"{args.batch} volumes x {args.slices} slices x {args.img}x{args.img} per GPU"
                        + (" + --get_attention saliency maps" if args.saliency else ""),
@@ -142,10 +150,10 @@ def main():
             return
         base, ts = cpu_baseline(max(1, args.steps), max(1, args.warmup))
         v = base["value"]
-        print(json.dumps({"impl": "reference", "metric": "volumes_per_sec", "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": "volumes_per_sec", "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.median(ts),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "slices_per_sec": v * 32, "config": dict(cfg, workload=cfg["workload"] + " [CPU: 1 volume per step]"),
+                          "slices_per_sec": v * 32, "config": cfg,
                           "cpu_baseline": base,
                           "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -289,7 +297,7 @@ def main():
                "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_step_e2e,
                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": base, "kernels": kernels}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
