@@ -371,6 +371,11 @@ static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t*
     return w;
 }
 
+static int attn257_warps() {
+    static const int w = getenv("MST_ATTN_WARPS") ? atoi(getenv("MST_ATTN_WARPS")) : 16;
+    return w == 8 ? 8 : 16;
+}
+
 template <typename T> struct Ops;
 template <> struct Ops<bf16> {
     static int gemm(mst_handle h, const void* A, int64_t lda, const void* W, int M, int N, int K, int mode, const EpiParams& ep, cudaStream_t st) {
@@ -378,8 +383,11 @@ template <> struct Ops<bf16> {
         return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, h->num_sms, st);
     }
     static int attention(mst_handle h, const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
-        if (N == 257)  // ViT @224: tcgen05 kernel; other token counts: warp-MMA kernel
+        if (N == 257) {  // ViT @224: the specialised tcgen05 kernels (16 softmax warps by default, MST_ATTN_WARPS=8: the older one)
+            if (attn257_warps() == 16)
+                return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
             return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
+        }
         static const int use_tcg = getenv("MST_ATTN_TCG") ? atoi(getenv("MST_ATTN_TCG")) : 1;   // 0: A-B comparisons
         if (use_tcg && attention_tcg_supported(N))
             return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, h->num_sms, st);
@@ -748,6 +756,9 @@ int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, in
 }
 int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
     MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16: null argument");
+    if (N == 257 && mst::attn257_warps() == 16)
+        return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
+                                         static_cast<cudaStream_t>(stream));
     if (N == 257)
         return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
                                       static_cast<cudaStream_t>(stream));

@@ -158,7 +158,10 @@ int launch_layernorm(const TIn* x, int64_t ldx, TOut* y, int64_t ldy, const floa
 // rowstat[row] = rstd of x[row, 0..E) (fp32 statistics, two-pass), the per-row part of a folded LayerNorm
 int launch_row_stats(const bf16* x, float* rowstat, int rows, int E, float eps, cudaStream_t stream);
 int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, cudaStream_t stream);
-// tcgen05 attention for any token count 17 <= N <= 448 (attention_tcg.cu); N == 257 keeps its specialised kernel
+// the same with sixteen softmax warps (two per TMEM lane quadrant and tile, splitting the key columns): attention_tc16.cu
+int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
+                              long long* dbg = nullptr);
+// tcgen05 attention for any token count 17 <= N <= 360 (attention_tcg.cu); N == 257 keeps its specialised kernels
 bool attention_tcg_supported(int N);
 int launch_attention_tcg(const bf16* qkv, bf16* out, int BD, int N, int heads, int num_sms, cudaStream_t stream);
 int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads, cudaStream_t stream);
