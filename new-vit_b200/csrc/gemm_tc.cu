@@ -142,7 +142,9 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
         for (int i = 0; i < 8; ++i) {
             f32x2 b0, b1;
             if (bias_smem) {
-                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(smem_u32(bias) + i * 16));
+                // NOT `asm volatile`: volatile statements keep their order, which chained eight 30-cycle
+                // shared-memory round trips in front of the FMAs of every 32-column chunk (profiles/gemm_timing.py: 360 cycles)
+                asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(smem_u32(bias) + i * 16));  // the bias cache is read-only
             } else {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
                 b0 = f2_pack(b.x, b.y); b1 = f2_pack(b.z, b.w);
@@ -152,11 +154,10 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
         }
     } else {
         if (bias_smem) {
-            const uint32_t sb = smem_u32(bias);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 f32x2 b0, b1;
-                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(sb + i * 16));
+                asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(smem_u32(bias) + i * 16));  // the bias cache is read-only
                 v[2 * i] = f2_add(v[2 * i], b0);
                 v[2 * i + 1] = f2_add(v[2 * i + 1], b1);
             }
@@ -701,6 +702,11 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
                 return launch_cfg<192, 6, 4, 1, 8, 4>(tmAq, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
             }
             if ((mode & 0xff) == EPI_BIAS_GELU || (mode & 0xff) == EPI_LN_BIAS_GELU)
+                return launch_cfg<192, 6, 3, 1, 12, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+            static const int alt = getenv("MST_GEMM_ALT") ? atoi(getenv("MST_GEMM_ALT")) : 0;  // experiments only
+            if (alt == 1)   // two staging tiles per epilogue warp (no wait for the previous chunk's TMA store), 3-stage A ring
+                return launch_cfg<192, 6, 3, 2, 8, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
+            if (alt == 2)   // 12 epilogue warps (2 chunks each), 3-stage A ring
                 return launch_cfg<192, 6, 3, 1, 12, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
             return launch_cfg<192, 6, 4, 1, 8, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
         }

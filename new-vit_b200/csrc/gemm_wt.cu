@@ -266,8 +266,10 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
                 if (LNF) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        f32x2 r01, r23;   // (rstd[t], rstd[t+1]), (rstd[t+2], rstd[t+3]): one broadcast 16-byte shared load
-                        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(r01), "=l"(r23) : "r"(smem_u32(rsb + g * 16 + 4 * j)));
+                        // (rstd[t], rstd[t+1]), (rstd[t+2], rstd[t+3]): one broadcast 16-byte shared load (a plain load, so the
+                        // four of a group are issued together instead of in `asm volatile` order)
+                        const float4 rr = *reinterpret_cast<const float4*>(rsb + g * 16 + 4 * j);
+                        const f32x2 r01 = f2_pack(rr.x, rr.y), r23 = f2_pack(rr.z, rr.w);
                         v[2 * j] = f2_fma(v[2 * j], r01, bias2);
                         v[2 * j + 1] = f2_fma(v[2 * j + 1], r23, bias2);
                     }
