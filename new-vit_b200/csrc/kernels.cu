@@ -284,13 +284,26 @@ __global__ void __launch_bounds__(128) cls_attention_kernel(const T* __restrict_
     float lmax = -CUDART_INF_F;
     for (int j = threadIdx.x; j < N; j += blockDim.x) {
         const T* kr = base + j * ld + E + h * 64;
-        float acc = 0.f;
+        float acc = 0.f, acc2 = 0.f;
+        if constexpr (sizeof(T) == 2) {   // 16-byte loads, two accumulation chains
 #pragma unroll
-        for (int d = 0; d < 64; d += 4) {
-            float kv[4];
-            Vec4<T>::load(kr + d, kv);
-            acc = fmaf(q[d], kv[0], acc); acc = fmaf(q[d + 1], kv[1], acc);
-            acc = fmaf(q[d + 2], kv[2], acc); acc = fmaf(q[d + 3], kv[3], acc);
+            for (int d = 0; d < 64; d += 8) {
+                const uint4 u = *reinterpret_cast<const uint4*>(kr + d);
+                float2 f;
+                f = unpack_bf16x2(u.x); acc = fmaf(q[d], f.x, acc); acc2 = fmaf(q[d + 1], f.y, acc2);
+                f = unpack_bf16x2(u.y); acc = fmaf(q[d + 2], f.x, acc); acc2 = fmaf(q[d + 3], f.y, acc2);
+                f = unpack_bf16x2(u.z); acc = fmaf(q[d + 4], f.x, acc); acc2 = fmaf(q[d + 5], f.y, acc2);
+                f = unpack_bf16x2(u.w); acc = fmaf(q[d + 6], f.x, acc); acc2 = fmaf(q[d + 7], f.y, acc2);
+            }
+            acc += acc2;
+        } else {
+#pragma unroll
+            for (int d = 0; d < 64; d += 4) {
+                float kv[4];
+                Vec4<T>::load(kr + d, kv);
+                acc = fmaf(q[d], kv[0], acc); acc = fmaf(q[d + 1], kv[1], acc);
+                acc = fmaf(q[d + 2], kv[2], acc); acc = fmaf(q[d + 3], kv[3], acc);
+            }
         }
         p[j] = acc;
         lmax = fmaxf(lmax, acc);
@@ -311,7 +324,19 @@ __global__ void __launch_bounds__(128) cls_attention_kernel(const T* __restrict_
     __syncthreads();
     const int d = threadIdx.x & 63, half = threadIdx.x >> 6;
     float acc = 0.f;
-    for (int j = half; j < N; j += 2) acc = fmaf(p[j], to_f<T>(base[j * ld + 2 * E + h * 64 + d]), acc);
+    {
+        const T* vp = base + 2 * E + h * 64 + d;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four independent chains: the loop is latency-bound otherwise
+        int j = half;
+        for (; j + 6 < N; j += 8) {
+            a0 = fmaf(p[j], to_f<T>(vp[static_cast<int64_t>(j) * ld]), a0);
+            a1 = fmaf(p[j + 2], to_f<T>(vp[static_cast<int64_t>(j + 2) * ld]), a1);
+            a2 = fmaf(p[j + 4], to_f<T>(vp[static_cast<int64_t>(j + 4) * ld]), a2);
+            a3 = fmaf(p[j + 6], to_f<T>(vp[static_cast<int64_t>(j + 6) * ld]), a3);
+        }
+        for (; j < N; j += 2) a0 = fmaf(p[j], to_f<T>(vp[static_cast<int64_t>(j) * ld]), a0);
+        acc = (a0 + a1) + (a2 + a3);
+    }
     part[threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.x < 64) out_cls[static_cast<int64_t>(s) * E + h * 64 + d] = from_f<T>(part[d] + part[64 + d]);
@@ -509,14 +534,17 @@ __device__ __forceinline__ void block_layernorm(const float* in, float* out, con
 __device__ __forceinline__ void block_matvec(const float* in, const float* __restrict__ Wt, int ldw, const float* __restrict__ bias,
                                              const float* res, float* out, int K, int Nout, bool relu, float scale) {
     for (int n = threadIdx.x; n < Nout; n += blockDim.x) {
-        float a0 = 0.f, a1 = 0.f;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four chains, eight loads in flight: the loop is L2-latency-bound
         int k = 0;
-        for (; k + 1 < K; k += 2) {
+#pragma unroll 2
+        for (; k + 3 < K; k += 4) {
             a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
             a1 = fmaf(in[k + 1], __ldg(Wt + static_cast<int64_t>(k + 1) * ldw + n), a1);
+            a2 = fmaf(in[k + 2], __ldg(Wt + static_cast<int64_t>(k + 2) * ldw + n), a2);
+            a3 = fmaf(in[k + 3], __ldg(Wt + static_cast<int64_t>(k + 3) * ldw + n), a3);
         }
-        if (k < K) a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
-        float v = (a0 + a1 + bias[n]) * scale;
+        for (; k < K; ++k) a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
+        float v = ((a0 + a1) + (a2 + a3) + bias[n]) * scale;
         if (relu) v = fmaxf(v, 0.f);
         if (res) v += res[n];
         out[n] = v;
@@ -719,9 +747,16 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     // 7. o[n] = Wv[n,:] . hbar[head(n)] + bv[n]
     for (int n = threadIdx.x; n < E; n += blockDim.x) {
         const float* hb = hbar + (n / hd) * E;
-        float a = 0.f;
-        for (int k = 0; k < E; ++k) a = fmaf(hb[k], __ldg(w.in_wt + static_cast<int64_t>(k) * 3 * E + 2 * E + n), a);
-        t0[n] = a + w.in_b[2 * E + n];
+        const float* wv = w.in_wt + 2 * E + n;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+        for (int k = 0; k < E; k += 4) {   // E % 4 == 0
+            a0 = fmaf(hb[k], __ldg(wv + static_cast<int64_t>(k) * 3 * E), a0);
+            a1 = fmaf(hb[k + 1], __ldg(wv + static_cast<int64_t>(k + 1) * 3 * E), a1);
+            a2 = fmaf(hb[k + 2], __ldg(wv + static_cast<int64_t>(k + 2) * 3 * E), a2);
+            a3 = fmaf(hb[k + 3], __ldg(wv + static_cast<int64_t>(k + 3) * 3 * E), a3);
+        }
+        t0[n] = ((a0 + a1) + (a2 + a3)) + w.in_b[2 * E + n];
     }
     __syncthreads();
     // 8. x1 = x0 + out_proj(o)                                           (transformer_blocks.py:566)
