@@ -183,7 +183,8 @@ class DinoV2ClassifierSlice(nn.Module):
         # Host batches are moved in chunks of whole volumes, H2D of chunk k+1 overlapped with the kernels of chunk k.
         # Only the first chunk's copy is exposed, so it is small; later chunks grow so that the GEMM grids keep full
         # waves (8 volumes = 514 m-tiles = 3.5 waves of 148 SMs cost 13 % in wave quantisation; 32 volumes cost 1.5 %).
-        self.h2d_chunk_volumes = (4, 12, 16, 32)   # then the last size repeats; an int = fixed chunk size; 0/None = off
+        # (profiles/e2e_schedule.py, 64 volumes: (4,12,48) 31.6 ms, (4,12,16,32) 32.6, (8,24,32) 31.9, device-resident 28.7)
+        self.h2d_chunk_volumes = (4, 12, 48)   # then the last size repeats; an int = fixed chunk size; 0/None = off
         self._last = None
         self._last_inputs = None
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_dirty", True))
