@@ -23,7 +23,10 @@ def _gelu(x):
 
 @pytest.mark.parametrize("M,N,K", [(128, 192, 64), (1000, 384, 384), (647, 1152, 384), (300, 1536, 384),
                                    (520, 384, 1536), (64, 384, 256), (4112, 1152, 384), (40000, 384, 384),
-                                   (257, 256, 128), (20000, 384, 1536)])
+                                   (257, 256, 128), (20000, 384, 1536),
+                                   # gemm_wt (weights in TMEM; K = 384, N % 256 == 0): one token, a ragged second tile, and enough
+                                   # tiles per CTA pair for the operand ring and both accumulator stages to wrap many times
+                                   (1, 1536, 384), (129, 1024, 384), (70000, 1536, 384)])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_bf16_tcgen05(M, N, K, mode):
     cabi, L = _lib()
@@ -207,7 +210,8 @@ def test_rollout_matches_matmul_chain():
         torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-8)
 
 
-@pytest.mark.parametrize("M,N,K", [(1000, 1152, 384), (4112, 1536, 384), (333, 2304, 768), (300, 3072, 768)])
+@pytest.mark.parametrize("M,N,K", [(1000, 1152, 384), (4112, 1536, 384), (333, 2304, 768), (300, 3072, 768), (33, 1536, 384),
+                                   (50001, 1536, 384)])
 @pytest.mark.parametrize("gelu", [0, 1])
 def test_gemm_bf16_layernorm_folded(M, N, K, gelu):
     """norm1 -> qkv and norm2 -> fc1 with the LayerNorm folded into the GEMM (block.py:112-113): raw rows through the tensor
