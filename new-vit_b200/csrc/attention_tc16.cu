@@ -308,7 +308,10 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             auto max16 = [&](const uint32_t (&r)[16]) {
                 float a = m, b2 = -CUDART_INF_F;
 #pragma unroll
-                for (int i = 0; i < 16; i += 2) { a = fmaxf(a, __uint_as_float(r[i])); b2 = fmaxf(b2, __uint_as_float(r[i + 1])); }
+                for (int i = 0; i < 16; i += 4) {
+                    a = fmax3(a, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                    b2 = fmax3(b2, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
                 m = fmaxf(a, b2);
             };
 #pragma unroll
@@ -528,7 +531,12 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     static const int poly = getenv("MST_ATTN_POLY") ? atoi(getenv("MST_ATTN_POLY")) : 7;  // experiments: 0 = all exponentials on MUFU
     // 7 of 16 pairs on the polynomial: measured optimum (kernel 0.547 ms with 0, 0.495 / 0.469 / 0.510 / 0.499 / 0.569 ms with
     // 6 / 7 / 8 / 10 / 12 of 16, config-2 shape, profiles/attn_timing.py)
-    auto kern = poly == 0 ? attention_tc257x16_kernel<0> : attention_tc257x16_kernel<7>;
+    auto kern = poly == 0 ? attention_tc257x16_kernel<0>
+              : poly == 4 ? attention_tc257x16_kernel<4>
+              : poly == 5 ? attention_tc257x16_kernel<5>
+              : poly == 6 ? attention_tc257x16_kernel<6>
+              : poly == 8 ? attention_tc257x16_kernel<8>
+                          : attention_tc257x16_kernel<7>;
     static bool attr = false;
     if (!attr) {
         MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
