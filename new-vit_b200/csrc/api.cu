@@ -435,12 +435,15 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
         ep.posb = posb; ep.P = P; ep.R = R; ep.out = x; ep.ldo = E;
         MST_LAUNCH(CAT_GEMM_PATCH, Ops<T>::gemm(h, ws.A0, KP, h->wpatch, BD * P, E, KP, EPI_PATCH, ep, st));
     }
+    bool stats_from_fc2 = false;
     for (int l = 0; l < c.depth; ++l) {
         const Layer& L = h->layers[l];
         const bool last = (l == c.depth - 1);
         // x = x + ls1(attn(norm1(x)))                                   (block.py:112)
         if (L.fold_qkv) {  // bf16: only the row statistics are materialised; norm1 itself rides in the qkv epilogue
-            MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
+            if (!stats_from_fc2)   // (blocks >= 1: the previous block's fc2 epilogue has already written them)
+                MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
+            stats_from_fc2 = false;
             EpiParams ep{};
             ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = ws.qkv; ep.ldo = 3 * E;
             MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
@@ -476,6 +479,13 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
             {
                 EpiParams ep{};
                 ep.bias = L.bfc2; ep.res = x; ep.ldr = E; ep.out = x; ep.ldo = E;
+                // The next block's norm1 statistics come out of this GEMM's epilogue (it then adds the residual itself instead
+                // of a TMA reduce-add, and one CTA pair walks both n-blocks of its rows): one pass over x less per block.
+                static const int fuse = getenv("MST_NO_STAT_FUSE") ? 0 : 1;
+                if (fuse && sizeof(T) == 2 && E == 384 && h->layers[l + 1].fold_qkv) {
+                    ep.rowstat_out = ws.rowstat; ep.stat_eps = 1e-6f;
+                    stats_from_fc2 = true;
+                }
                 MST_LAUNCH(CAT_GEMM_FC2, Ops<T>::gemm(h, ws.hid, 4 * E, L.wfc2, M, E, 4 * E, EPI_BIAS_RES, ep, st));
             }
         } else {

@@ -61,6 +61,9 @@ struct EpiParams {
     int64_t ldo;         // output row stride in elements
     long long* dbg;      // nullable: phase cycle counters of CTA 0 (profiles/gemm_timing.py)
     const float* rowstat;   // [M] rstd of every A row (EPI_LN_*)
+    float* rowstat_out;     // nullable, EPI_BIAS_RES on the streaming pair GEMM: rstd of every OUTPUT row (the LayerNorm statistics
+                            // the next GEMM needs), computed in the epilogue from the bf16-rounded rows it writes
+    float stat_eps;         // LayerNorm eps for rowstat_out
 };
 
 // erf via the rational minimax on [-4,4] (max abs error 3.8e-7 in fp32; checked against math.erf).

@@ -107,7 +107,11 @@ struct GemmSmem {
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
     static constexpr int STG_OFF = B_OFF + B_BUFS * B_TILE_BYTES;
     static constexpr int BIAS_OFF = STG_OFF + EPI_WARPS * STG_BYTES;
-    static constexpr int BAR_OFF = BIAS_OFF + BIAS_FLOATS * 4;
+    // row-statistics exchange of the fused residual + LayerNorm-statistics epilogue (streaming pair mode only):
+    // [2 parities][2 column groups][128 rows] x (sum, sum of squares)
+    static constexpr int STAT_BYTES = (KCH == 0 && PAIR == 2 && EW == 8) ? 2 * 2 * 128 * 2 * 4 : 0;
+    static constexpr int STAT_OFF = BIAS_OFF + BIAS_FLOATS * 4;
+    static constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 1 + 4;
     static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-byte alignment
@@ -180,7 +184,7 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
             const uint4* pr = reinterpret_cast<const uint4*>(static_cast<const bf16*>(ep.res) + row * ep.ldr + n0);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint4 u = __ldg(pr + i);
+                const uint4 u = pr[i];   // plain load: with the fused statistics the same buffer is written later in this kernel
                 float2 f;
                 f = unpack_bf16x2(u.x); v[4 * i + 0] = f2_add(v[4 * i + 0], f2_pack(f.x, f.y));
                 f = unpack_bf16x2(u.y); v[4 * i + 1] = f2_add(v[4 * i + 1], f2_pack(f.x, f.y));
@@ -281,11 +285,16 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         const int m0 = unit / n_tiles;
         t_first = m0; t_step = gs;
         t_count = m0 < m_tiles ? (m_tiles - m0 + gs - 1) / gs : 0;
+    } else if (mode_flags & 0x400) {
+        // fused row statistics: a unit takes WHOLE m-blocks, its n-blocks back to back, so one CTA sees every column of its rows
+        t_first = unit; t_step = units;
+        t_count = unit < m_tiles ? ((m_tiles - unit + units - 1) / units) * n_tiles : 0;
     } else {
         const int total = m_tiles * n_tiles;
         t_first = unit; t_step = units;
         t_count = t_first < total ? (total - t_first + t_step - 1) / t_step : 0;
     }
+    const bool seqn = !kResident && (mode_flags & 0x400) != 0;
     const int n_fixed = unit % n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -334,8 +343,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < t_count; ++it) {
                 const int t = t_first + it * t_step;
-                const int m_blk = kResident ? t : t / n_tiles;
-                const int n_blk = kResident ? n_fixed : t % n_tiles;
+                const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : t / n_tiles);
+                const int n_blk = kResident ? n_fixed : (seqn ? it % n_tiles : t % n_tiles);
                 // (streaming mode: prefetching there made fc2 13 % slower -- every CTA of an m-block row would issue the same
                 //  prefetches -- so it is limited to the resident schedule, where one cluster per m-group issues them)
                 if (kResident && n_fixed < MC && it + kPrefetchTiles < t_count) {
@@ -432,10 +441,11 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         uint8_t* stg = smem + L::STG_OFF + e * L::STG_BYTES;
         int stg_sel = 0;
         int acc = 0; uint32_t acc_phase = 0;
+        float st1 = 0.f, st2 = 0.f;   // fused row statistics: sum and sum of squares of this lane's row over this warp's columns
         for (int it = 0; it < t_count; ++it) {
             const int t = t_first + it * t_step;
-            const int m_blk = kResident ? t : t / n_tiles;
-            const int n_blk = kResident ? n_fixed : t % n_tiles;
+            const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : t / n_tiles);
+            const int n_blk = kResident ? n_fixed : (seqn ? it % n_tiles : t % n_tiles);
             const int row0 = m_blk * BMT + row_off + q * 32;
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < M;
@@ -460,6 +470,15 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     case EPI_LN_BIAS: epilogue_math<EPI_LN_BIAS>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
                     case EPI_LN_BIAS_GELU: epilogue_math<EPI_LN_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
                     default: if (NSTG != 2) epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0, rstat); break;
+                }
+                if (L::STAT_BYTES > 0 && seqn && row_ok) {   // statistics of the bf16 values that are written
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 f = unpack_bf16x2(o[i]);
+                        st1 += f.x + f.y;
+                        st2 = fmaf(f.x, f.x, st2);
+                        st2 = fmaf(f.y, f.y, st2);
+                    }
                 }
                 if (mode == EPI_PATCH) {
                     if (NSTG == 2) {
@@ -570,6 +589,22 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             process(ra, 0);
             process(rb, 1);
             if constexpr (CHUNKS_PER_WARP == 3) process(rc, 2);
+            if constexpr (L::STAT_BYTES > 0) {
+                if (seqn && n_blk == n_tiles - 1) {
+                    // both column groups of a row quadrant meet in shared memory; group 0 turns the totals into rstd
+                    float* sst = reinterpret_cast<float*>(smem + L::STAT_OFF) + ((it / n_tiles) & 1) * 512;
+                    const int r = q * 32 + lane;
+                    sst[(hf * 128 + r) * 2] = st1;
+                    sst[(hf * 128 + r) * 2 + 1] = st2;
+                    named_bar_sync(1 + q, 64);
+                    if (hf == 0 && row_ok) {
+                        const float t1 = st1 + sst[(128 + r) * 2], t2 = st2 + sst[(128 + r) * 2 + 1];
+                        const float mean = t1 / N;
+                        ep.rowstat_out[row] = rsqrtf(fmaxf(t2 / N - mean * mean, 0.f) + ep.stat_eps);
+                    }
+                    st1 = 0.f; st2 = 0.f;
+                }
+            }
             if (ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0) {
                 const long long e3 = clock64();
                 ep.dbg[4] += e1 - e0; ep.dbg[5] += e2 - e1; ep.dbg[6] += e3 - e2;
@@ -651,7 +686,14 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(N % 192 == 0 || N % 128 == 0, "gemm: N=%d must be a multiple of 192 or 128", N);
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
     // in-place residual update: `out += acc + bias` as 16-byte vector reductions (no residual read by the SM)
-    if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) mode = EPI_BIAS_ACCUM;
+    const bool want_stats = ep.rowstat_out != nullptr;
+    if (want_stats) {
+        MST_REQUIRE(mode == EPI_BIAS_RES && N % 192 == 0 && N / 192 == 2 && K > 384,
+                    "gemm: fused row statistics need EPI_BIAS_RES, N = 384 and the streaming pair schedule (K > 384); got N=%d K=%d mode=%d",
+                    N, K, mode);
+    } else if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) {
+        mode = EPI_BIAS_ACCUM;
+    }
     static const int use_wt = getenv("MST_GEMM_WT") ? atoi(getenv("MST_GEMM_WT")) : 1;  // 0: experiments / A-B comparisons
     if (use_wt && gemm_wt_supported(M, N, K, mode, ep)) {
         static const int wt_skip = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;  // experiments only
@@ -665,7 +707,7 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1 + ep.R) : static_cast<uint64_t>(M);
     static const int force_bn = getenv("MST_GEMM_BN") ? atoi(getenv("MST_GEMM_BN")) : 0;  // experiments only
     static const int skip_epi = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;
-    if (skip_epi) mode |= skip_epi << 8;  // 1: no epilogue at all, 2: epilogue without the final store
+    if (skip_epi) mode |= (skip_epi & 3) << 8;  // 1: no epilogue at all, 2: epilogue without the final store
     static const int no_mcast = getenv("MST_GEMM_NO_MCAST") ? atoi(getenv("MST_GEMM_NO_MCAST")) : 0;  // experiments only
     static const int use_two = getenv("MST_GEMM_TWO") ? atoi(getenv("MST_GEMM_TWO")) : 1;             // experiments only
     if (N % 192 == 0 && force_bn != 128) {
@@ -712,6 +754,8 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
         }
         // K too large for a resident weight slab (fc2): both operands stream through the ring
         MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+        if (want_stats) mode |= 0x400;
+        MST_REQUIRE(!want_stats || use_two, "gemm: fused row statistics need the cta_group::2 streaming schedule");
         if (use_two) {  // cta_group::2: 16 KB of A + 12 KB (half) of the weight tile per CTA and stage
             TmaDesc tmBh;
             MST_PROPAGATE(make_tma_2d_bf16(&tmBh, W, K, N, K, BK, 96));
