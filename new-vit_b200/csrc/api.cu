@@ -347,6 +347,7 @@ struct Workspace {
     void *A0, *x, *xn, *qkv, *hid, *ao_cls, *xc, *xcn, *hc;
     float *enc_cls, *hs;
     float* rowstat;
+    float* rowpart;   // [M][4][2] row partials written by the proj epilogue, read by fc1 (bf16 ViT-S path)
     size_t total;
 };
 static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t* base) {
@@ -367,6 +368,7 @@ static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t*
     w.enc_cls = static_cast<float*>(take(BD * E * 4));
     w.hs = static_cast<float*>(take(static_cast<size_t>(B) * (D + 1) * E * 4));
     w.rowstat = static_cast<float*>(take(M * sizeof(float)));
+    w.rowpart = static_cast<float*>(take(M * 8 * sizeof(float)));
     w.total = off;
     return w;
 }
@@ -459,16 +461,24 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
                                                                 c.enc_heads, st));
         if (!last) {
             MST_LAUNCH(CAT_ATTENTION, Ops<T>::attention(h, ws.qkv, xn, BD, N, c.enc_heads, st));  // xn is dead: reuse as attention output
+            // norm2 statistics as row partials out of proj's epilogue, consumed by fc1: measured SLOWER (proj 0.21 -> 0.40 ms with
+            // the explicit per-lane residual loads instead of the TMA reduce-add, fc1 0.68 -> 0.78 ms with 32 bytes of partials
+            // per token instead of 4 bytes of rstd: step 31.3 -> 32.1 ms), so it is off unless MST_PROJ_STAT_FUSE=1
+            static const int fuse_stats = getenv("MST_PROJ_STAT_FUSE") ? atoi(getenv("MST_PROJ_STAT_FUSE")) : 0;
+            const bool part_fc1 = fuse_stats && sizeof(T) == 2 && E == 384 && L.fold_fc1 && gemm_wt_enabled();
             {
                 EpiParams ep{};
                 ep.bias = L.bproj; ep.res = x; ep.ldr = E; ep.out = x; ep.ldo = E;
+                if (part_fc1) ep.rowpart_out = ws.rowpart;
                 MST_LAUNCH(CAT_GEMM_PROJ, Ops<T>::gemm(h, xn, E, L.wproj, M, E, E, EPI_BIAS_RES, ep, st));
             }
             // x = x + ls2(mlp(norm2(x)))                                  (block.py:113)
             if (L.fold_fc1) {
-                MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
+                if (!part_fc1)
+                    MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
                 EpiParams ep{};
                 ep.bias = L.bfc1; ep.rowstat = ws.rowstat; ep.out = ws.hid; ep.ldo = 4 * E;
+                if (part_fc1) { ep.rowpart = ws.rowpart; ep.stat_eps = 1e-6f; }
                 MST_LAUNCH(CAT_GEMM_FC1, Ops<T>::gemm(h, x, E, L.wfc1, M, 4 * E, E, EPI_LN_BIAS_GELU, ep, st));
             } else {
                 MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n2w, L.n2b, M, E, 1e-6f, st)));

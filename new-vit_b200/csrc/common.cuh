@@ -63,7 +63,10 @@ struct EpiParams {
     const float* rowstat;   // [M] rstd of every A row (EPI_LN_*)
     float* rowstat_out;     // nullable, EPI_BIAS_RES on the streaming pair GEMM: rstd of every OUTPUT row (the LayerNorm statistics
                             // the next GEMM needs), computed in the epilogue from the bf16-rounded rows it writes
-    float stat_eps;         // LayerNorm eps for rowstat_out
+    float stat_eps;         // LayerNorm eps for rowstat_out / rowpart
+    float* rowpart_out;     // nullable, EPI_BIAS_RES on the weight-resident GEMM with N = 384: [M][4][2] partial (sum, sum of squares)
+                            // of every output row, slot = 2 * n_block + column group (plain stores, fixed slots: deterministic)
+    const float* rowpart;   // gemm_wt, EPI_LN_*: the same partials as INPUT (instead of rowstat); rstd is formed on the fly
 };
 
 // erf via the rational minimax on [-4,4] (max abs error 3.8e-7 in fp32; checked against math.erf).
@@ -139,6 +142,7 @@ int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, u
 // weights-in-TMEM transposed-accumulator GEMM for K = 384, N >= 1024 (qkv, fc1): gemm_wt.cu
 struct EpiParams;
 bool gemm_wt_supported(int M, int N, int K, int mode, const EpiParams& ep);
+bool gemm_wt_enabled();   // MST_GEMM_WT != 0
 int gemm_bf16_wt(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
                  cudaStream_t stream);
 // tcgen05 attention for N == 257 tokens (ViT-S/B @224); other N use the warp-MMA kernel

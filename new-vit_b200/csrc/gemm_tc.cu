@@ -442,6 +442,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         int stg_sel = 0;
         int acc = 0; uint32_t acc_phase = 0;
         float st1 = 0.f, st2 = 0.f;   // fused row statistics: sum and sum of squares of this lane's row over this warp's columns
+        const bool stats_on = (L::STAT_BYTES > 0 && seqn) || (kResident && ep.rowpart_out != nullptr);
         for (int it = 0; it < t_count; ++it) {
             const int t = t_first + it * t_step;
             const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : t / n_tiles);
@@ -471,7 +472,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     case EPI_LN_BIAS_GELU: epilogue_math<EPI_LN_BIAS_GELU>(r, o, ep, b, bias_cached, row, row_ok, N, n0, rstat); break;
                     default: if (NSTG != 2) epilogue_math<EPI_PATCH>(r, o, ep, b, false, row, row_ok, N, n0, rstat); break;
                 }
-                if (L::STAT_BYTES > 0 && seqn && row_ok) {   // statistics of the bf16 values that are written
+                if (stats_on && row_ok) {   // statistics of the bf16 values that are written
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const float2 f = unpack_bf16x2(o[i]);
@@ -589,6 +590,10 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             process(ra, 0);
             process(rb, 1);
             if constexpr (CHUNKS_PER_WARP == 3) process(rc, 2);
+            if (kResident && ep.rowpart_out != nullptr) {   // this warp's partial for its rows: slot 2 * n_block + column group
+                if (row_ok) *reinterpret_cast<float2*>(ep.rowpart_out + (row * 4 + n_blk * 2 + hf) * 2) = make_float2(st1, st2);
+                st1 = 0.f; st2 = 0.f;
+            }
             if constexpr (L::STAT_BYTES > 0) {
                 if (seqn && n_blk == n_tiles - 1) {
                     // both column groups of a row quadrant meet in shared memory; group 0 turns the totals into rstd
@@ -679,6 +684,11 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     return 0;
 }
 
+bool gemm_wt_enabled() {
+    static const int use_wt = getenv("MST_GEMM_WT") ? atoi(getenv("MST_GEMM_WT")) : 1;  // 0: experiments / A-B comparisons
+    return use_wt != 0;
+}
+
 int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
                  cudaStream_t stream) {
     MST_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
@@ -687,20 +697,24 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
     // in-place residual update: `out += acc + bias` as 16-byte vector reductions (no residual read by the SM)
     const bool want_stats = ep.rowstat_out != nullptr;
-    if (want_stats) {
+    if (ep.rowpart_out != nullptr) {
+        MST_REQUIRE(mode == EPI_BIAS_RES && N == 384 && K == 384 && !want_stats,
+                    "gemm: row partials need EPI_BIAS_RES on the weight-resident N = K = 384 GEMM; got N=%d K=%d mode=%d", N, K, mode);
+    } else if (want_stats) {
         MST_REQUIRE(mode == EPI_BIAS_RES && N % 192 == 0 && N / 192 == 2 && K > 384,
                     "gemm: fused row statistics need EPI_BIAS_RES, N = 384 and the streaming pair schedule (K > 384); got N=%d K=%d mode=%d",
                     N, K, mode);
     } else if (mode == EPI_BIAS_RES && ep.res == ep.out && ep.ldr == ep.ldo) {
         mode = EPI_BIAS_ACCUM;
     }
-    static const int use_wt = getenv("MST_GEMM_WT") ? atoi(getenv("MST_GEMM_WT")) : 1;  // 0: experiments / A-B comparisons
+    const int use_wt = gemm_wt_enabled();
     if (use_wt && gemm_wt_supported(M, N, K, mode, ep)) {
         static const int wt_skip = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;  // experiments only
         EpiParams e2 = ep;
         e2.P = wt_skip;
         return gemm_bf16_wt(A, W, M, N, K, mode, e2, num_sms, stream);  // weights in TMEM, 16 epilogue warps (gemm_wt.cu)
     }
+    MST_REQUIRE(ep.rowpart == nullptr, "gemm: row partials (rowpart) are consumed by gemm_wt only");
     TmaDesc tmA, tmB, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
     // output maps (unused by EPI_PATCH, whose rows are re-mapped)

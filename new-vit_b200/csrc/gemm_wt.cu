@@ -228,8 +228,21 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
             // rstd of this warp's 64 tokens: requested BEFORE the wait on the accumulator, so the L2 round trip hides behind it
             float rs0 = 0.f, rs1 = 0.f;
             if (LNF) {
-                if (tok_tile + lane < M) rs0 = __ldg(ep.rowstat + tok_tile + lane);
-                if (tok_tile + 32 + lane < M) rs1 = __ldg(ep.rowstat + tok_tile + 32 + lane);
+                if (ep.rowpart != nullptr) {
+                    // rstd from the four (sum, sum of squares) partials the producing GEMM's epilogue left for every row
+                    auto rstd_of = [&](int tok) {
+                        const float4* pp = reinterpret_cast<const float4*>(ep.rowpart + static_cast<int64_t>(tok) * 8);
+                        const float4 a = __ldg(pp), b = __ldg(pp + 1);
+                        const float t1 = (a.x + a.z) + (b.x + b.z), t2 = (a.y + a.w) + (b.y + b.w);
+                        const float mean = t1 * (1.0f / K);
+                        return rsqrtf(fmaxf(t2 * (1.0f / K) - mean * mean, 0.f) + ep.stat_eps);
+                    };
+                    if (tok_tile + lane < M) rs0 = rstd_of(tok_tile + lane);
+                    if (tok_tile + 32 + lane < M) rs1 = rstd_of(tok_tile + 32 + lane);
+                } else {
+                    if (tok_tile + lane < M) rs0 = __ldg(ep.rowstat + tok_tile + lane);
+                    if (tok_tile + 32 + lane < M) rs1 = __ldg(ep.rowstat + tok_tile + 32 + lane);
+                }
             }
             const long long w0 = dbg_all ? clock64() : 0;
             mbar_wait(&tfull_bar[team], (it >> 1) & 1);
@@ -383,8 +396,9 @@ int gemm_bf16_wt(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     using namespace wt;
     MST_REQUIRE(gemm_wt_supported(M, N, K, mode, ep), "gemm_wt: unsupported problem M=%d N=%d K=%d mode=%d", M, N, K, mode);
     MST_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, "gemm_wt: weight pointer must be 16-byte aligned");
-    MST_REQUIRE(!(mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU) || (reinterpret_cast<uintptr_t>(ep.rowstat) & 15) == 0,
-                "gemm_wt: rowstat must be 16-byte aligned");
+    MST_REQUIRE(!(mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU) || ep.rowpart != nullptr || ep.rowstat != nullptr,
+                "gemm_wt: LayerNorm-folded modes need rowstat or rowpart");
+    MST_REQUIRE((reinterpret_cast<uintptr_t>(ep.rowpart) & 15) == 0, "gemm_wt: rowpart must be 16-byte aligned");
     TmaDesc tmX, tmC;
     MST_PROPAGATE(make_tma_2d_bf16(&tmX, A, K, M, K, 64, NTH));
     MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, M, ep.ldo, 32, 32, false, false));
