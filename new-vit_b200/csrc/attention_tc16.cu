@@ -31,7 +31,7 @@ constexpr int OFF_K = 2 * Q_TILE_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_K0 = OFF_V
 constexpr int NUM_STAGES = 2;
 constexpr int OSTG_OFF = NUM_STAGES * STAGE_BYTES;            // 8 x 2 KB O staging tiles
 constexpr int STATS_OFF = OSTG_OFF + 8 * 2048;                // [2 parity][6 kinds][128] floats
-constexpr int STATS_KINDS = 7;                                // per team: max[2 halves], sum[2 halves], p0 (CLS key), 2 spare
+constexpr int STATS_KINDS = 7;                                // per team: max[2 halves], sum[2 halves], p0 (CLS key), CLS-key dot[2 halves]
 constexpr int CLS_OFF = STATS_OFF + 2 * STATS_KINDS * 128 * 4;  // pbuf[272] + red[16] + part[256] floats
 constexpr int BAR_OFF = CLS_OFF + (272 + 16 + 256) * 4;
 constexpr int NUM_BARS = 2 * NUM_STAGES + 2 + 2 + 2 + 2;      // kv_full[2], kv_empty[2], s_full[2], sp_done[2], o_full[2], o_free[2]
@@ -160,7 +160,7 @@ template <int kPolyPairs>
 __global__ void __launch_bounds__(atc16::THREADS, 1)
 attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_constant__ TmaDesc map16,
                        const __grid_constant__ TmaDesc mapO, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                       int num_items, int heads, long long* __restrict__ dbg) {
+                       int num_items, int heads, long long* __restrict__ dbg, int split_dot) {
     using namespace atc16;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -277,21 +277,28 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
         const int row = q * 32 + lane;
         float* st = reinterpret_cast<float*>(smem + STATS_OFF) + tm * STATS_KINDS * 128;   // max[2][128] sum[2][128] p0[128]
         const uint32_t bar_id = 1 + tm * 4 + q;                           // named barrier of the (team, quadrant) warp pair
+        const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
+        long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long dbg_t = dbg_on ? clock64() : 0;
         for (int g = tm; g < n_tiles; g += 2) {
             const int it = g >> 1, stg = it & 1;
             const uint32_t par = static_cast<uint32_t>(it & 1);
             mbar_wait(&s_full[tm], par);
+            ATT_T(0);  // waiting for S
             tc_fence_after_sync();
             uint32_t ra[16], rb[16];
             tmem_ld_32x32b_x16(sbase, ra);
-            // ---- CLS key: s0 = q_row . k_cls (CUDA cores, from the smem tiles); key half 0 owns it ----
-            float s0 = -CUDART_INF_F;
-            if (ch == 0) {
-                s0 = 0.f;
+            // ---- CLS key: s0 = q_row . k_cls (CUDA cores, from the smem tiles).  The two warps of a row quadrant take 32 of
+            //      the 64 dims each (the whole dot on one of them was 2300 cycles of its 10400-cycle chain, attn_timing.py);
+            //      the halves meet in the same exchange as the row maxima ----
+            float s0 = 0.f;
+            {
                 const uint8_t* qrow = smem + stg * STAGE_BYTES + tm * Q_TILE_BYTES + row * 128;
                 const uint8_t* k0 = smem + stg * STAGE_BYTES + OFF_K0;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    if (split_dot ? c4 >= 4 : ch != 0) break;       // whole dot on key half 0, or 32 dims on each warp
+                    const int c = split_dot ? ch * 4 + c4 : c4;
                     const uint4 kk = *reinterpret_cast<const uint4*>(k0 + c * 16);
                     const uint4 qq = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
                     float kf[8];
@@ -303,8 +310,9 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                     s0 = dot8_16(qq, kf, s0);
                 }
             }
+            ATT_T(1);  // CLS-key dot
             // ---- pass 1: row max over this warp's 128 columns; the next TMEM load is in flight while reducing ----
-            float m = s0;
+            float m = -CUDART_INF_F;
             auto max16 = [&](const uint32_t (&r)[16]) {
                 float a = m, b2 = -CUDART_INF_F;
 #pragma unroll
@@ -323,10 +331,14 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                 if (c + 2 < 8) tmem_ld_32x32b_x16(sbase + (c + 2) * 16, ra);
                 max16(rb);
             }
+            ATT_T(2);  // pass 1
             st[ch * 128 + row] = m;
+            st[(5 + ch) * 128 + row] = s0;             // this warp's half of the CLS-key dot
             tmem_ld_32x32b_x16(sbase, ra);            // first chunk of pass 2 rides over the exchange
             named_bar_sync(bar_id, 64);
-            m = fmaxf(m, st[(ch ^ 1) * 128 + row]);
+            s0 = st[5 * 128 + row] + st[6 * 128 + row];   // same order in both warps: bit-identical
+            m = fmax3(m, st[(ch ^ 1) * 128 + row], s0);
+            ATT_T(3);  // max exchange
             const float mb = m * LOG2E;
             // ---- pass 2: P (bf16 pairs) in place at the start of this warp's half: chunk c (16 columns) -> 8 columns ----
             float sum = 0.f;
@@ -344,6 +356,7 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                 if (c + 2 < 8) tmem_ld_32x32b_x16(sbase + (c + 2) * 16, ra);
                 sum += softmax_math16<kPolyPairs, 8>(rb, o, mb); tmem_st_32x32b_x8_16(sbase + (c + 1) * 8, o);
             }
+            ATT_T(4);  // pass 2
             tmem_st_wait();
             tc_fence_before_sync();
             st[(2 + ch) * 128 + row] = sum;
@@ -352,8 +365,10 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             named_bar_sync(bar_id, 64);
             const float inv = 1.0f / (sum + st[(2 + (ch ^ 1)) * 128 + row]);
             const float p0 = st[4 * 128 + row];
+            ATT_T(5);  // sum exchange
             // ---- epilogue: O columns [64 + 32 ch, +32) of this warp's rows + p0 * v_cls, 1/l, bf16, 64-byte row pieces ----
             mbar_wait(&o_full[tm], par);
+            ATT_T(6);  // waiting for O
             tc_fence_after_sync();
             uint32_t ro[32];
             tmem_ld_32x32b_x32(buf + 64 + ch * 32, ro);
@@ -385,7 +400,9 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&kv_empty[stg]);  // Q rows / K_cls / V_cls of this stage are no longer needed
+            ATT_T(7);  // epilogue
         }
+        if (dbg_on) { for (int i = 0; i < 8; ++i) dbg[i] = dbg_acc[i]; dbg[8] = n_tiles; }
     } else {
         // ===================== CLS query (token 0): warp-level MMA from the same smem tiles =====================
         // Six warps in two groups of three (group A = warps 2,12,13 takes even items, group B = 3,14,15 odd items).  The
@@ -544,7 +561,8 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
-    kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg);
+    static const int split_dot = getenv("MST_ATTN_SPLITDOT") ? atoi(getenv("MST_ATTN_SPLITDOT")) : 1;  // A-B switch
+    kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg, split_dot);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
