@@ -238,22 +238,47 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             }
             __syncwarp();
         };
+        auto issue_s = [&](int g) {   // S(g) = Q(tile g) . K^T into buffer g&1
+            const int it = g >> 1, t = g & 1, st = it & 1, b = g & 1;
+            const uint32_t q_lo = smem_lo + ((st * STAGE_BYTES + t * Q_TILE_BYTES) >> 4);
+            const uint32_t k_lo = smem_lo + ((st * STAGE_BYTES + OFF_K) >> 4);
+            if (elect_one_sync()) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16_ss(tmem_base + static_cast<uint32_t>(b * 256), make_desc(q_lo + 2 * k, kDescHiK),
+                                 make_desc(k_lo + 2 * k, kDescHiK), idesc_s, k != 0 ? 1u : 0u);
+                umma_commit(&s_full[b]);
+            }
+            __syncwarp();
+        };
+        if (split_dot & 2) {
+            // Event-driven issue: S(g) needs its item's K/V/Q and the buffer's previous O read out, P.V(g) needs P(g); whichever
+            // is ready goes first (in program order S(g+1) waited for the OTHER team's epilogue before this team's P.V could go).
+            int gs = 0, gp = 0;
+            uint32_t idle = 0;
+            while (gp < n_tiles) {
+                bool did = false;
+                if (gs < n_tiles) {
+                    const int it = gs >> 1, st = it & 1, b = gs & 1;
+                    bool ready = (gs & 1) != 0 || mbar_test(&kv_full[st], (it >> 1) & 1);
+                    if (ready && gs >= 2) ready = mbar_test(&o_free[b], ((gs - 2) >> 1) & 1);
+                    if (ready) { tc_fence_after_sync(); issue_s(gs); ++gs; did = true; }
+                }
+                if (gp < gs && mbar_test(&sp_done[gp & 1], (gp >> 1) & 1)) {
+                    tc_fence_after_sync();
+                    issue_pv(gp);
+                    ++gp;
+                    did = true;
+                }
+                if (did) idle = 0;
+                else if (++idle > (1u << 26)) asm volatile("trap;");   // a protocol bug becomes an error, not a hang
+            }
+        } else {
         for (int g = 0; g < n_tiles; ++g) {
             const int it = g >> 1, t = g & 1, st = it & 1, b = g & 1;
             if (t == 0) { mbar_wait(&kv_full[st], (it >> 1) & 1); tc_fence_after_sync(); }
             if (g >= 2) { mbar_wait(&o_free[b], ((g - 2) >> 1) & 1); tc_fence_after_sync(); }   // O(g-2) read out
-            {
-                const uint32_t q_lo = smem_lo + ((st * STAGE_BYTES + t * Q_TILE_BYTES) >> 4);
-                const uint32_t k_lo = smem_lo + ((st * STAGE_BYTES + OFF_K) >> 4);
-                if (elect_one_sync()) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_base + static_cast<uint32_t>(b * 256), make_desc(q_lo + 2 * k, kDescHiK),
-                                     make_desc(k_lo + 2 * k, kDescHiK), idesc_s, k != 0 ? 1u : 0u);
-                    umma_commit(&s_full[b]);
-                }
-                __syncwarp();
-            }
+            issue_s(g);
             if (g > 0) {  // P(g-1) complete
                 mbar_wait(&sp_done[b ^ 1], ((g - 1) >> 1) & 1);
                 tc_fence_after_sync();
@@ -265,6 +290,7 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             mbar_wait(&sp_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
             tc_fence_after_sync();
             issue_pv(g - 1);
+        }
         }
     } else if (warp >= 4 && warp < 20) {
         // ===================== softmax + O epilogue: two teams of eight warps =====================
@@ -297,8 +323,8 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                 const uint8_t* k0 = smem + stg * STAGE_BYTES + OFF_K0;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    if (split_dot ? c4 >= 4 : ch != 0) break;       // whole dot on key half 0, or 32 dims on each warp
-                    const int c = split_dot ? ch * 4 + c4 : c4;
+                    if ((split_dot & 1) ? c4 >= 4 : ch != 0) break;       // whole dot on key half 0, or 32 dims on each warp
+                    const int c = (split_dot & 1) ? ch * 4 + c4 : c4;
                     const uint4 kk = *reinterpret_cast<const uint4*>(k0 + c * 16);
                     const uint4 qq = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
                     float kf[8];
@@ -561,7 +587,7 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
-    static const int split_dot = getenv("MST_ATTN_SPLITDOT") ? atoi(getenv("MST_ATTN_SPLITDOT")) : 1;  // A-B switch
+    static const int split_dot = getenv("MST_ATTN_SPLITDOT") ? atoi(getenv("MST_ATTN_SPLITDOT")) : 1;  // A-B switches: bit 0 split the CLS-key dot, bit 1 event-driven MMA issue
     kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg, split_dot);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;

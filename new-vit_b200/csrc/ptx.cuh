@@ -83,6 +83,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded spin: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
 #ifndef MST_MBAR_TIMEOUT_NS
 #define MST_MBAR_TIMEOUT_NS 4000000000ull
