@@ -63,7 +63,6 @@ attention_tcg_kernel(const __grid_constant__ TmaDesc mapKV, const __grid_constan
     const int E = heads * 64;
     const int tiles_per_item = (N + 127) >> 7;
     const int my_items = static_cast<int>(blockIdx.x) < num_items ? (num_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int n_tiles = my_items * tiles_per_item;
 
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&mapKV); tma_prefetch_desc(&mapQ); }
     if (warp == 1 && lane == 0) {
