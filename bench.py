@@ -92,6 +92,38 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """One process per GPU: run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned input buffer is
+    allocated (first touch puts the pages there), so the per-step host-to-device copies of 8 ranks do not all cross the
+    socket interconnect.  Best effort: returns the node, or None when sysfs does not say."""
+    try:
+        import torch
+        bdf = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
+        if bdf is None:
+            o = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                               capture_output=True, text=True, timeout=10).stdout.strip()
+            bdf = o
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:      # nvidia-smi prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline(steps, warmup, threads=None):
     """Time the oracle (CPU port of the reference path) on one synthetic volume per step."""
     import torch
@@ -163,6 +195,7 @@ def main():
     from new_vit_b200 import DinoV2ClassifierSlice, synth
     from new_vit_b200.dist import gather_volumes
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -296,7 +329,8 @@ def main():
                "model_tflops": model_tflops, "model_frac_of_bf16_burst_peak": model_tflops / (peaks["bf16_tflops"] * world),
                "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_step_e2e,
                        "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
-               "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": base, "kernels": kernels}
+               "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": base, "kernels": kernels,
+               "numa_node_rank0": numa}
         emit(out)
     if world > 1:
         dist.barrier()
