@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmst_b200.so")
+LIB_PATH = os.environ.get("MST_LIB_PATH") or os.path.join(_HERE, "libmst_b200.so")   # MST_LIB_PATH: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mst_b200.h")
 
 PRECISION = {"fp32": 0, "bf16": 1}

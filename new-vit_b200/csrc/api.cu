@@ -789,11 +789,8 @@ int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N,
 }
 int mst_debug_attention_timing(const void* qkv, void* out, int32_t BD, int32_t heads, long long* dbg_dev, void* stream) {
     MST_REQUIRE(qkv && out && dbg_dev, "mst_debug_attention_timing: null argument");
-    if (mst::attn257_warps() == 16)
-        return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
-                                         static_cast<cudaStream_t>(stream), dbg_dev);
     return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
-                                  static_cast<cudaStream_t>(stream), dbg_dev);
+                                  static_cast<cudaStream_t>(stream), dbg_dev);   // the 8-warp kernel carries the phase counters
 }
 int mst_kernel_attention_bf16_warp_mma(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
     MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16_warp_mma: null argument");

@@ -115,9 +115,9 @@ __device__ __forceinline__ float softmax_math32(const uint32_t (&r)[32], uint32_
 __device__ __forceinline__ float max32(const uint32_t (&r)[32], float m) {
     float a = m, b = -CUDART_INF_F;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-        a = fmax3(a, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-        b = fmax3(b, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+    for (int i = 0; i < 32; i += 2) {
+        a = fmaxf(a, __uint_as_float(r[i]));
+        b = fmaxf(b, __uint_as_float(r[i + 1]));
     }
     return fmaxf(a, b);
 }

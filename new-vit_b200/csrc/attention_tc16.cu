@@ -31,7 +31,7 @@ constexpr int OFF_K = 2 * Q_TILE_BYTES, OFF_V = OFF_K + KV_BYTES, OFF_K0 = OFF_V
 constexpr int NUM_STAGES = 2;
 constexpr int OSTG_OFF = NUM_STAGES * STAGE_BYTES;            // 8 x 2 KB O staging tiles
 constexpr int STATS_OFF = OSTG_OFF + 8 * 2048;                // [2 parity][6 kinds][128] floats
-constexpr int STATS_KINDS = 7;                                // per team: max[2 halves], sum[2 halves], p0 (CLS key), CLS-key dot[2 halves]
+constexpr int STATS_KINDS = 7;                                // per team: max[2 halves], sum[2 halves], p0 (CLS key), 2 spare
 constexpr int CLS_OFF = STATS_OFF + 2 * STATS_KINDS * 128 * 4;  // pbuf[272] + red[16] + part[256] floats
 constexpr int BAR_OFF = CLS_OFF + (272 + 16 + 256) * 4;
 constexpr int NUM_BARS = 2 * NUM_STAGES + 2 + 2 + 2 + 2;      // kv_full[2], kv_empty[2], s_full[2], sp_done[2], o_full[2], o_free[2]
@@ -160,7 +160,7 @@ template <int kPolyPairs>
 __global__ void __launch_bounds__(atc16::THREADS, 1)
 attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_constant__ TmaDesc map16,
                        const __grid_constant__ TmaDesc mapO, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                       int num_items, int heads, long long* __restrict__ dbg, int split_dot) {
+                       int num_items, int heads, long long* __restrict__ dbg) {
     using namespace atc16;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -238,47 +238,22 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             }
             __syncwarp();
         };
-        auto issue_s = [&](int g) {   // S(g) = Q(tile g) . K^T into buffer g&1
-            const int it = g >> 1, t = g & 1, st = it & 1, b = g & 1;
-            const uint32_t q_lo = smem_lo + ((st * STAGE_BYTES + t * Q_TILE_BYTES) >> 4);
-            const uint32_t k_lo = smem_lo + ((st * STAGE_BYTES + OFF_K) >> 4);
-            if (elect_one_sync()) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(tmem_base + static_cast<uint32_t>(b * 256), make_desc(q_lo + 2 * k, kDescHiK),
-                                 make_desc(k_lo + 2 * k, kDescHiK), idesc_s, k != 0 ? 1u : 0u);
-                umma_commit(&s_full[b]);
-            }
-            __syncwarp();
-        };
-        if (split_dot & 2) {
-            // Event-driven issue: S(g) needs its item's K/V/Q and the buffer's previous O read out, P.V(g) needs P(g); whichever
-            // is ready goes first (in program order S(g+1) waited for the OTHER team's epilogue before this team's P.V could go).
-            int gs = 0, gp = 0;
-            uint32_t idle = 0;
-            while (gp < n_tiles) {
-                bool did = false;
-                if (gs < n_tiles) {
-                    const int it = gs >> 1, st = it & 1, b = gs & 1;
-                    bool ready = (gs & 1) != 0 || mbar_test(&kv_full[st], (it >> 1) & 1);
-                    if (ready && gs >= 2) ready = mbar_test(&o_free[b], ((gs - 2) >> 1) & 1);
-                    if (ready) { tc_fence_after_sync(); issue_s(gs); ++gs; did = true; }
-                }
-                if (gp < gs && mbar_test(&sp_done[gp & 1], (gp >> 1) & 1)) {
-                    tc_fence_after_sync();
-                    issue_pv(gp);
-                    ++gp;
-                    did = true;
-                }
-                if (did) idle = 0;
-                else if (++idle > (1u << 26)) asm volatile("trap;");   // a protocol bug becomes an error, not a hang
-            }
-        } else {
         for (int g = 0; g < n_tiles; ++g) {
             const int it = g >> 1, t = g & 1, st = it & 1, b = g & 1;
             if (t == 0) { mbar_wait(&kv_full[st], (it >> 1) & 1); tc_fence_after_sync(); }
             if (g >= 2) { mbar_wait(&o_free[b], ((g - 2) >> 1) & 1); tc_fence_after_sync(); }   // O(g-2) read out
-            issue_s(g);
+            {
+                const uint32_t q_lo = smem_lo + ((st * STAGE_BYTES + t * Q_TILE_BYTES) >> 4);
+                const uint32_t k_lo = smem_lo + ((st * STAGE_BYTES + OFF_K) >> 4);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem_base + static_cast<uint32_t>(b * 256), make_desc(q_lo + 2 * k, kDescHiK),
+                                     make_desc(k_lo + 2 * k, kDescHiK), idesc_s, k != 0 ? 1u : 0u);
+                    umma_commit(&s_full[b]);
+                }
+                __syncwarp();
+            }
             if (g > 0) {  // P(g-1) complete
                 mbar_wait(&sp_done[b ^ 1], ((g - 1) >> 1) & 1);
                 tc_fence_after_sync();
@@ -291,7 +266,6 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             tc_fence_after_sync();
             issue_pv(g - 1);
         }
-        }
     } else if (warp >= 4 && warp < 20) {
         // ===================== softmax + O epilogue: two teams of eight warps =====================
         // Team tm owns the tiles g = tm (mod 2), i.e. TMEM buffer tm; warp (q, tm, ch) owns rows q*32.. of its tile and the
@@ -303,28 +277,21 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
         const int row = q * 32 + lane;
         float* st = reinterpret_cast<float*>(smem + STATS_OFF) + tm * STATS_KINDS * 128;   // max[2][128] sum[2][128] p0[128]
         const uint32_t bar_id = 1 + tm * 4 + q;                           // named barrier of the (team, quadrant) warp pair
-        const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
-        long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        long long dbg_t = dbg_on ? clock64() : 0;
         for (int g = tm; g < n_tiles; g += 2) {
             const int it = g >> 1, stg = it & 1;
             const uint32_t par = static_cast<uint32_t>(it & 1);
             mbar_wait(&s_full[tm], par);
-            ATT_T(0);  // waiting for S
             tc_fence_after_sync();
             uint32_t ra[16], rb[16];
             tmem_ld_32x32b_x16(sbase, ra);
-            // ---- CLS key: s0 = q_row . k_cls (CUDA cores, from the smem tiles).  The two warps of a row quadrant take 32 of
-            //      the 64 dims each (the whole dot on one of them was 2300 cycles of its 10400-cycle chain, attn_timing.py);
-            //      the halves meet in the same exchange as the row maxima ----
-            float s0 = 0.f;
-            {
+            // ---- CLS key: s0 = q_row . k_cls (CUDA cores, from the smem tiles); key half 0 owns it ----
+            float s0 = -CUDART_INF_F;
+            if (ch == 0) {
+                s0 = 0.f;
                 const uint8_t* qrow = smem + stg * STAGE_BYTES + tm * Q_TILE_BYTES + row * 128;
                 const uint8_t* k0 = smem + stg * STAGE_BYTES + OFF_K0;
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    if ((split_dot & 1) ? c4 >= 4 : ch != 0) break;       // whole dot on key half 0, or 32 dims on each warp
-                    const int c = (split_dot & 1) ? ch * 4 + c4 : c4;
+                for (int c = 0; c < 8; ++c) {
                     const uint4 kk = *reinterpret_cast<const uint4*>(k0 + c * 16);
                     const uint4 qq = *reinterpret_cast<const uint4*>(qrow + ((c ^ (row & 7)) << 4));
                     float kf[8];
@@ -336,16 +303,12 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                     s0 = dot8_16(qq, kf, s0);
                 }
             }
-            ATT_T(1);  // CLS-key dot
             // ---- pass 1: row max over this warp's 128 columns; the next TMEM load is in flight while reducing ----
-            float m = -CUDART_INF_F;
+            float m = s0;
             auto max16 = [&](const uint32_t (&r)[16]) {
                 float a = m, b2 = -CUDART_INF_F;
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    a = fmax3(a, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-                    b2 = fmax3(b2, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                }
+                for (int i = 0; i < 16; i += 2) { a = fmaxf(a, __uint_as_float(r[i])); b2 = fmaxf(b2, __uint_as_float(r[i + 1])); }
                 m = fmaxf(a, b2);
             };
 #pragma unroll
@@ -357,14 +320,10 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                 if (c + 2 < 8) tmem_ld_32x32b_x16(sbase + (c + 2) * 16, ra);
                 max16(rb);
             }
-            ATT_T(2);  // pass 1
             st[ch * 128 + row] = m;
-            st[(5 + ch) * 128 + row] = s0;             // this warp's half of the CLS-key dot
             tmem_ld_32x32b_x16(sbase, ra);            // first chunk of pass 2 rides over the exchange
             named_bar_sync(bar_id, 64);
-            s0 = st[5 * 128 + row] + st[6 * 128 + row];   // same order in both warps: bit-identical
-            m = fmax3(m, st[(ch ^ 1) * 128 + row], s0);
-            ATT_T(3);  // max exchange
+            m = fmaxf(m, st[(ch ^ 1) * 128 + row]);
             const float mb = m * LOG2E;
             // ---- pass 2: P (bf16 pairs) in place at the start of this warp's half: chunk c (16 columns) -> 8 columns ----
             float sum = 0.f;
@@ -382,7 +341,6 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                 if (c + 2 < 8) tmem_ld_32x32b_x16(sbase + (c + 2) * 16, ra);
                 sum += softmax_math16<kPolyPairs, 8>(rb, o, mb); tmem_st_32x32b_x8_16(sbase + (c + 1) * 8, o);
             }
-            ATT_T(4);  // pass 2
             tmem_st_wait();
             tc_fence_before_sync();
             st[(2 + ch) * 128 + row] = sum;
@@ -391,10 +349,8 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             named_bar_sync(bar_id, 64);
             const float inv = 1.0f / (sum + st[(2 + (ch ^ 1)) * 128 + row]);
             const float p0 = st[4 * 128 + row];
-            ATT_T(5);  // sum exchange
             // ---- epilogue: O columns [64 + 32 ch, +32) of this warp's rows + p0 * v_cls, 1/l, bf16, 64-byte row pieces ----
             mbar_wait(&o_full[tm], par);
-            ATT_T(6);  // waiting for O
             tc_fence_after_sync();
             uint32_t ro[32];
             tmem_ld_32x32b_x32(buf + 64 + ch * 32, ro);
@@ -426,9 +382,7 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&kv_empty[stg]);  // Q rows / K_cls / V_cls of this stage are no longer needed
-            ATT_T(7);  // epilogue
         }
-        if (dbg_on) { for (int i = 0; i < 8; ++i) dbg[i] = dbg_acc[i]; dbg[8] = n_tiles; }
     } else {
         // ===================== CLS query (token 0): warp-level MMA from the same smem tiles =====================
         // Six warps in two groups of three (group A = warps 2,12,13 takes even items, group B = 3,14,15 odd items).  The
@@ -574,12 +528,7 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     static const int poly = getenv("MST_ATTN_POLY") ? atoi(getenv("MST_ATTN_POLY")) : 7;  // experiments: 0 = all exponentials on MUFU
     // 7 of 16 pairs on the polynomial: measured optimum (kernel 0.547 ms with 0, 0.495 / 0.469 / 0.510 / 0.499 / 0.569 ms with
     // 6 / 7 / 8 / 10 / 12 of 16, config-2 shape, profiles/attn_timing.py)
-    auto kern = poly == 0 ? attention_tc257x16_kernel<0>
-              : poly == 4 ? attention_tc257x16_kernel<4>
-              : poly == 5 ? attention_tc257x16_kernel<5>
-              : poly == 6 ? attention_tc257x16_kernel<6>
-              : poly == 8 ? attention_tc257x16_kernel<8>
-                          : attention_tc257x16_kernel<7>;
+    auto kern = poly == 0 ? attention_tc257x16_kernel<0> : attention_tc257x16_kernel<7>;
     static bool attr = false;
     if (!attr) {
         MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
@@ -587,8 +536,7 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
-    static const int split_dot = getenv("MST_ATTN_SPLITDOT") ? atoi(getenv("MST_ATTN_SPLITDOT")) : 1;  // A-B switches: bit 0 split the CLS-key dot, bit 1 event-driven MMA issue
-    kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg, split_dot);
+    kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -178,10 +178,7 @@ attention_tcg_kernel(const __grid_constant__ TmaDesc mapKV, const __grid_constan
                     if (16 * c + 16 <= N) {
                         float a = m, b2 = -CUDART_INF_F;
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            a = fmax3(a, __uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-                            b2 = fmax3(b2, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                        }
+                        for (int i = 0; i < 16; i += 2) { a = fmaxf(a, __uint_as_float(r[i])); b2 = fmaxf(b2, __uint_as_float(r[i + 1])); }
                         m = fmaxf(a, b2);
                     } else {
 #pragma unroll
