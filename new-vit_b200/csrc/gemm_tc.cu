@@ -728,6 +728,10 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
         if (K == 256) {  // patch embedding: weight-resident, chunk staging (its epilogue stores rows directly)
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
+            // 12 epilogue warps (two 32-column chunks each instead of three): the epilogue, not the 16 MMAs, paces this GEMM
+            // (0.47 -> 0.38 ms per launch in-step); MST_PATCH_EW12=0 keeps the 8-warp configuration for A-B runs
+            static const int ew12 = getenv("MST_PATCH_EW12") ? atoi(getenv("MST_PATCH_EW12")) : 1;
+            if (ew12) return launch_cfg<192, 4, 4, 2, 12>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
             return launch_cfg<192, 4, 4, 2, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
         }
         if (K == 384 && use_two == 2) {  // measured slower than the multicast pair below (0.512 vs 0.428 ms for qkv): every CTA
