@@ -50,3 +50,15 @@ def model_kwargs(meta):
 @pytest.fixture(scope="session")
 def golden_names():
     return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+@pytest.fixture(autouse=True)
+def _seed_everything():
+    """Every test starts from the same RNG state (some draw inputs from the global generator): a test either passes or fails,
+    it does not do so one run in ten."""
+    import torch
+    torch.manual_seed(1234)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(1234)
+    yield
+

@@ -49,16 +49,25 @@ def test_gemm_bf16_tcgen05(M, N, K, mode):
 
 
 def test_gemm_bf16_inplace_residual():
+    """x += A W^T + b in place: the update is a TMA reduce-add, i.e. the UPDATE is rounded to bf16 before the memory system adds it
+    to the bf16 residual (two roundings).  The bound therefore carries half an ulp of the larger operand next to the usual output
+    rounding: where x and the update nearly cancel, the error is set by their magnitude, not by the result's.  (Unseeded and with a
+    flat 8e-3 this test failed about one run in ten on exactly such an element.)"""
     cabi, L = _lib()
     M, N, K = 777, 384, 384
-    A = torch.randn(M, K, device="cuda").bfloat16()
-    W = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
-    bias = torch.randn(N, device="cuda")
-    x = torch.randn(M, N, device="cuda").bfloat16()
-    ref = x.float() + A.float() @ W.float().t() + bias
+    g = torch.Generator(device="cuda").manual_seed(777)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    x0 = x.float()
+    delta = A.float() @ W.float().t() + bias
+    ref = x0 + delta
     cabi.check(L.mst_kernel_gemm_bf16(cabi.ptr(A), cabi.ptr(W), M, N, K, 2, cabi.ptr(bias), cabi.ptr(x), cabi.ptr(x), _stream()))
     torch.cuda.synchronize()
-    torch.testing.assert_close(x.float(), ref, rtol=8e-3, atol=8e-3)
+    bound = 8e-3 * (1.0 + ref.abs()) + 2.0 ** -8 * torch.maximum(x0.abs(), delta.abs())
+    err = (x.float() - ref).abs()
+    assert bool((err <= bound).all()), f"max excess {(err - bound).max().item():.3e}"
 
 
 @pytest.mark.parametrize("M,N,K", [(130, 384, 384), (257, 1152, 384), (100, 384, 1536), (65, 384, 256)])
