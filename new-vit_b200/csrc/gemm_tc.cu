@@ -146,12 +146,10 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
         for (int i = 0; i < 8; ++i) {
             f32x2 b0, b1;
             if (bias_smem) {
-                // A plain load: the compiler keeps it behind the barrier that follows the bias-cache fill.  (`asm volatile`
-                // chained eight dependent 30-cycle round trips per chunk; a non-volatile asm without a memory clobber is a pure
-                // function to the compiler, which hoisted it above that barrier -- an intermittent wrong bias, caught by
-                // test_gemm_bf16_inplace_residual failing one run in six.)
-                const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * i);
-                b0 = f2_pack(bb.x, bb.y); b1 = f2_pack(bb.z, bb.w);
+                // `asm volatile`: an explicit LDS that stays behind the barrier after the bias-cache fill (a NON-volatile asm load
+                // is a pure function to the compiler and may be hoisted above it; a plain C++ load through the generic pointer
+                // cost qkv 12 % in-step)
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(smem_u32(bias) + i * 16));
             } else {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + i);
                 b0 = f2_pack(b.x, b.y); b1 = f2_pack(b.z, b.w);
@@ -164,8 +162,7 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&r)[32], uint32_t 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 f32x2 b0, b1;
-                const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * i);
-                b0 = f2_pack(bb.x, bb.y); b1 = f2_pack(bb.z, bb.w);
+                asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(smem_u32(bias) + i * 16));
                 v[2 * i] = f2_add(v[2 * i], b0);
                 v[2 * i + 1] = f2_add(v[2 * i + 1], b1);
             }
