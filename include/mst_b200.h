@@ -118,6 +118,20 @@ MST_API int mst_quantile_workspace_bytes(int32_t items, int32_t nq, size_t* byte
 MST_API int mst_quantile(const float* data, int64_t n, int32_t items, const double* q_dev, int32_t nq, double* out,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Input pipeline in front of mst_forward: DUKE_Dataset3D's default transform chain for one batch of equally shaped volumes
+ * (mst/data/datasets/dataset_3d_duke.py:36-47 with image_resize / resample None and the random augmentations off):
+ * tio.Flip(1) -> CropOrPad((W,H,D), padding_mode='minimum') (augmentations/augmentations_3d.py:144-195) ->
+ * ZNormalization(percentiles, mask = (x > min) & (x < max)) (:41-86) -> ImageOrSubjectToTensor swapaxes(1,-1) (:23-29).
+ *   src   [items, W0, H0, D0] fp32 (torchio's [C=1, W, H, D] per item)      out [items, 1, D, H, W] fp32 (the model's `source`)
+ *   q_lo, q_hi  percentiles / 100 (0.005, 0.995), clamped before the statistics; flip_h = 1 for tio.Flip(1)
+ *   stats nullable [items, 8] fp64: min, max, cutoff_lo, cutoff_hi, mean, std, masked voxels, status
+ *         (status 0 ok; 1 std == 0 and 2 empty mask: the reference raises RuntimeError, augmentations_3d.py:75-84)
+ * W*H*D must be a multiple of 4. */
+MST_API int mst_prepare_volume_workspace_bytes(int32_t items, int32_t W0, int32_t H0, int32_t D0, size_t* bytes);
+MST_API int mst_prepare_volume(const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H,
+                       int32_t D, int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Instrumentation: kernels launched by this handle so far; per-category device time (CUDA events recorded on the
  * caller's stream around every launch between begin and end; end synchronises the device).  `ms`/`launches` must
  * hold at least 16 entries; mst_profile_categories() names them, comma separated, in order. */

@@ -711,6 +711,25 @@ int mst_quantile(const float* data, int64_t n, int32_t items, const double* q_de
     return launch_quantile(data, n, items, q_dev, nq, out, workspace, sms, static_cast<cudaStream_t>(stream));
 }
 
+int mst_prepare_volume_workspace_bytes(int32_t items, int32_t W0, int32_t H0, int32_t D0, size_t* bytes) {
+    MST_REQUIRE(bytes && items >= 1 && W0 >= 1 && H0 >= 1 && D0 >= 1, "mst_prepare_volume_workspace_bytes: bad argument");
+    *bytes = prepare_volume_workspace_bytes(items, W0, H0, D0);
+    return 0;
+}
+int mst_prepare_volume(const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H, int32_t D,
+                       int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+    MST_REQUIRE(src && out && workspace, "mst_prepare_volume: null argument");
+    MST_REQUIRE(items >= 1 && W0 >= 1 && H0 >= 1 && D0 >= 1 && W >= 1 && H >= 1 && D >= 1, "mst_prepare_volume: bad shape");
+    MST_REQUIRE(q_lo >= 0.f && q_lo <= q_hi && q_hi <= 1.f, "mst_prepare_volume: quantiles must satisfy 0 <= q_lo <= q_hi <= 1");
+    MST_REQUIRE(workspace_bytes >= prepare_volume_workspace_bytes(items, W0, H0, D0), "mst_prepare_volume: workspace too small");
+    int dev = 0, sms = 0;
+    MST_CHECK_CUDA(cudaGetDevice(&dev));
+    MST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return launch_prepare_volume(src, items, W0, H0, D0, W, H, D, flip_h, q_lo, q_hi, out, stats, workspace, sms,
+                                 static_cast<cudaStream_t>(stream));
+}
+
 const char* mst_profile_categories(void) { return kCatNames; }
 unsigned long long mst_launch_count(mst_handle h) { return h ? h->launches : 0; }
 int mst_profile_begin(mst_handle h) {

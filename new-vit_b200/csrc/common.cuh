@@ -200,4 +200,9 @@ size_t quantile_workspace_bytes(int items, int nq);
 int launch_quantile(const float* data, int64_t n, int items, const double* q_dev, int nq, double* out, void* workspace,
                     int num_sms, cudaStream_t stream);
 
+// ---- input pipeline in front of the forward (prep.cu) -----------------------
+size_t prepare_volume_workspace_bytes(int items, int W0, int H0, int D0);
+int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, int W, int H, int D, int flip_h, float q_lo,
+                          float q_hi, float* out, double* stats, void* workspace, int num_sms, cudaStream_t stream);
+
 }  // namespace mst
