@@ -7,7 +7,7 @@
 //   ZNormalization(percentiles=(0.5, 99.5), masking_method = (x > x.min()) & (x < x.max()))   augmentations_3d.py:41-86
 //   ImageOrSubjectToTensor                                   swapaxes(1, -1): [C, W, H, D] -> [C, D, H, W]  (:23-29)
 // All of it is HBM-bound element work: one gather pass (flip, crop, pad and the axis swap through a shared-memory tile, so
-// that both the reads along D and the writes along W are coalesced), a masked 4-pass radix select for the two cutoffs, one
+// that both the reads along D and the writes along W are coalesced), a masked 3-pass radix select (12 + 10 + 10 key bits) for the two cutoffs, one
 // moments pass and one normalise pass; the passes after the gather read the 6.4 MB output volume, which stays in L2.
 #include <math_constants.h>
 #include "common.cuh"
@@ -24,7 +24,26 @@ __device__ __forceinline__ float pkey2f(uint32_t k) {
     return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
+// f(float4) over a volume, four independent 16-byte loads in flight per thread (a loop with shared-memory atomics or branches
+// in its body is not unrolled by the compiler: one load per round trip ran at 2.4 TB/s, this form at the copy rate).
+template <typename F>
+__device__ __forceinline__ void for_each_vec4(const float4* __restrict__ v4, int64_t n4, F f) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = __ldg(v4 + i), b = __ldg(v4 + i + stride), c = __ldg(v4 + i + 2 * stride), d = __ldg(v4 + i + 3 * stride);
+        f(a); f(b); f(c); f(d);
+    }
+    for (; i < n4; i += stride) f(__ldg(v4 + i));
+}
+
 constexpr int PSEL = 4;  // order statistics per item: below / above rank of the low and of the high percentile
+// Radix digits of the 32-bit key, most significant first: 12 + 10 + 10 bits = three passes.  (8-bit digits took four, and the first
+// one discriminates badly: sign + seven exponent bits put 68 % of an MRI-like volume into one bin, so the second pass still
+// counted most voxels with atomics.)
+__device__ __forceinline__ int radix_shift(int pass) { return pass == 0 ? 20 : (pass == 1 ? 10 : 0); }
+__device__ __forceinline__ int radix_bins(int pass) { return pass == 0 ? 4096 : 1024; }
+constexpr int RADIX_PASSES = 3;
 
 struct PrepState {  // per item, in the workspace
     uint32_t kmin, kmax;            // keys of the volume's min / max (after crop / pad)
@@ -35,7 +54,7 @@ struct PrepState {  // per item, in the workspace
     float lo, hi;                   // cutoffs
     float mean, stdv;
     double sum, sumsq;              // of (clamped - lo) over the mask
-    unsigned int hist[PSEL * 256];
+    unsigned int hist[4096];        // first pass: 4096 shared bins; later passes: 4 x 1024
 };
 
 // np.pad(mode='minimum') with the default stat_length pads axis by axis with the minimum of each 1-D line over the ORIGINAL
@@ -75,51 +94,84 @@ struct PrepMargins {    // per-item tables, nullptr when no axis is padded
     int64_t item;       // floats per item in the margin block
 };
 
-__device__ __forceinline__ float prep_fetch(const float* __restrict__ s, const PrepGeom& g, const PrepMargins& pm, int64_t moff,
-                                            int w, int h, int d) {
+// Address of the voxel (or of the marginal minimum) that target voxel (w, h, d) takes: address arithmetic only, so that the
+// caller can issue all its loads back to back.
+__device__ __forceinline__ const float* prep_addr(const float* __restrict__ s, const PrepGeom& g, const PrepMargins& pm,
+                                                  int64_t moff, int w, int h, int d) {
     const int sw = w + g.ow, sd = d + g.od;
     int sh = h + g.oh;
     const bool iw = sw >= 0 && sw < g.W0, ih = sh >= 0 && sh < g.H0, id = sd >= 0 && sd < g.D0;
     if (g.flip_h) sh = g.H0 - 1 - sh;   // tio.Flip(1) runs before the pad; minima along H do not see it
-    if (iw && ih && id) return s[(static_cast<int64_t>(sw) * g.H0 + sh) * g.D0 + sd];
-    if (!iw && ih && id) return pm.m_w[moff + static_cast<int64_t>(sh) * g.D0 + sd];
-    if (iw && !ih && id) return pm.m_h[moff + static_cast<int64_t>(sw) * g.D0 + sd];
-    if (iw && ih && !id) return pm.m_d[moff + static_cast<int64_t>(sw) * g.H0 + sh];
-    if (!iw && !ih && id) return pm.m_wh[moff + sd];
-    if (!iw && ih && !id) return pm.m_wd[moff + sh];
-    if (iw && !ih && !id) return pm.m_hd[moff + sw];
-    return pm.m_whd[moff];
+    if (iw && ih && id) return s + (static_cast<int64_t>(sw) * g.H0 + sh) * g.D0 + sd;
+    if (!iw && ih && id) return pm.m_w + moff + static_cast<int64_t>(sh) * g.D0 + sd;
+    if (iw && !ih && id) return pm.m_h + moff + static_cast<int64_t>(sw) * g.D0 + sd;
+    if (iw && ih && !id) return pm.m_d + moff + static_cast<int64_t>(sw) * g.H0 + sh;
+    if (!iw && !ih && id) return pm.m_wh + moff + sd;
+    if (!iw && ih && !id) return pm.m_wd + moff + sh;
+    if (iw && !ih && !id) return pm.m_hd + moff + sw;
+    return pm.m_whd + moff;
 }
 
 // out[item, d, h, w] = padded / cropped / flipped src[item, w, h, d]; per-item min / max keys by atomics.
-// grid (ceil(W/32), H, items), block (32, 8): 32(w) x 32(d) tiles through shared memory.
-__global__ void __launch_bounds__(256) prep_gather_kernel(const float* __restrict__ src, PrepGeom g, PrepMargins pm,
+// grid (ceil(W/32), ceil(H/GATHER_HB), items), block (32, 8): GATHER_HB tiles of 32(w) x 32(d) through shared memory per step,
+// so that every thread has 4 * GATHER_HB independent loads in flight (one tile per block and step: 1.0 TB/s, latency-bound).
+constexpr int GATHER_HB = 4;
+__global__ void __launch_bounds__(256, 4) prep_gather_kernel(const float* __restrict__ src, PrepGeom g, PrepMargins pm,
                                                            float* __restrict__ out, PrepState* __restrict__ st) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[GATHER_HB][32][33];
     __shared__ uint32_t smin[8], smax[8];
-    const int item = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * 32;
+    const int item = blockIdx.z, h0 = blockIdx.y * GATHER_HB, w0 = blockIdx.x * 32;
     const float* s = src + static_cast<int64_t>(item) * g.W0 * g.H0 * g.D0;
     float* o = out + static_cast<int64_t>(item) * g.W * g.H * g.D;
     const int64_t moff = static_cast<int64_t>(item) * pm.item;
     uint32_t kmin = 0xffffffffu, kmax = 0u;
+    const int w1 = min(w0 + 32, g.W) - 1, h1 = min(h0 + GATHER_HB, g.H) - 1;
+    const bool in_wh = w0 + g.ow >= 0 && w1 + g.ow < g.W0 && h0 + g.oh >= 0 && h1 + g.oh < g.H0;
     for (int d0 = 0; d0 < g.D; d0 += 32) {
+        const bool interior = in_wh && d0 + g.od >= 0 && min(d0 + 32, g.D) - 1 + g.od < g.D0;
+        float v[GATHER_HB][4];
+        if (interior) {
+            // every voxel of the tile lies inside the source: the address is affine in (k, hb), no table lookups, few registers
+            const int sh0 = g.flip_h ? g.H0 - 1 - (h0 + g.oh) : h0 + g.oh;
+            const float* base = s + (static_cast<int64_t>(w0 + threadIdx.y + g.ow) * g.H0 + sh0) * g.D0 + (d0 + threadIdx.x + g.od);
+            const int64_t sk = static_cast<int64_t>(8) * g.H0 * g.D0;
+            const int shs = g.flip_h ? -g.D0 : g.D0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int wl = threadIdx.y + 8 * k, w = w0 + wl, d = d0 + threadIdx.x;
-            if (w < g.W && d < g.D) {
-                const float v = prep_fetch(s, g, pm, moff, w, h, d);
-                tile[wl][threadIdx.x] = v;
-                const uint32_t key = pf2key(v);
-                kmin = min(kmin, key);
-                kmax = max(kmax, key);
-            }
+            for (int hb = 0; hb < GATHER_HB; ++hb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool ok = w0 + threadIdx.y + 8 * k < g.W && d0 + threadIdx.x < g.D && h0 + hb < g.H;
+                    v[hb][k] = ok ? __ldg(base + k * sk + hb * shs) : CUDART_NAN_F;
+                }
+        } else {
+#pragma unroll
+            for (int hb = 0; hb < GATHER_HB; ++hb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int w = w0 + threadIdx.y + 8 * k, d = d0 + threadIdx.x, h = h0 + hb;
+                    v[hb][k] = (w < g.W && d < g.D && h < g.H) ? __ldg(prep_addr(s, g, pm, moff, w, h, d)) : CUDART_NAN_F;
+                }
         }
+#pragma unroll
+        for (int hb = 0; hb < GATHER_HB; ++hb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int wl = threadIdx.y + 8 * k;
+                tile[hb][wl][threadIdx.x] = v[hb][k];
+                if (w0 + wl < g.W && d0 + threadIdx.x < g.D && h0 + hb < g.H) {
+                    const uint32_t key = pf2key(v[hb][k]);
+                    kmin = min(kmin, key);
+                    kmax = max(kmax, key);
+                }
+            }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int dl = threadIdx.y + 8 * k, d = d0 + dl, w = w0 + threadIdx.x;
-            if (w < g.W && d < g.D) o[(static_cast<int64_t>(d) * g.H + h) * g.W + w] = tile[threadIdx.x][dl];
-        }
+        for (int hb = 0; hb < GATHER_HB; ++hb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int dl = threadIdx.y + 8 * k, d = d0 + dl, w = w0 + threadIdx.x, h = h0 + hb;
+                if (w < g.W && d < g.D && h < g.H) o[(static_cast<int64_t>(d) * g.H + h) * g.W + w] = tile[hb][threadIdx.x][dl];
+            }
         __syncthreads();
     }
     for (int off = 16; off > 0; off >>= 1) {
@@ -137,7 +189,7 @@ __global__ void __launch_bounds__(256) prep_gather_kernel(const float* __restric
 
 __global__ void prep_init_kernel(PrepState* __restrict__ st) {
     PrepState& q = st[blockIdx.x];
-    for (int i = threadIdx.x; i < PSEL * 256; i += blockDim.x) q.hist[i] = 0;
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) q.hist[i] = 0;
     if (threadIdx.x == 0) {
         q.kmin = 0xffffffffu; q.kmax = 0u; q.count = 0; q.sum = 0.0; q.sumsq = 0.0;
         for (int s = 0; s < PSEL; ++s) { q.prefix[s] = 0; q.rank[s] = 0; }
@@ -147,69 +199,133 @@ __global__ void prep_init_kernel(PrepState* __restrict__ st) {
 // One radix pass over the masked voxels (min < x < max, augmentations_3d.py:75 masked_select with dataset_3d_duke.py:43's mask).
 __global__ void __launch_bounds__(256) prep_hist_kernel(const float* __restrict__ vol, int64_t n, int pass,
                                                          PrepState* __restrict__ st) {
-    __shared__ unsigned int sh[PSEL * 256];
-    __shared__ uint32_t spre[PSEL];
+    __shared__ unsigned int sh[4096];
     const int item = blockIdx.y;
     PrepState& q = st[item];
-    for (int i = threadIdx.x; i < PSEL * 256; i += blockDim.x) sh[i] = 0;
-    if (threadIdx.x < PSEL) spre[threadIdx.x] = q.prefix[threadIdx.x];
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x) sh[i] = 0;
     const uint32_t kmin = q.kmin, kmax = q.kmax;
+    // in registers: read from shared memory inside the loop they would be re-loaded after every atomic (possible alias)
+    const uint32_t p0 = q.prefix[0], p1 = q.prefix[1], p2 = q.prefix[2], p3 = q.prefix[3];
+    const bool d1 = p1 != p0, d3 = p3 != p2;
     __syncthreads();
-    const int shift = 24 - 8 * pass;
-    const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    const int shift = radix_shift(pass);
+    const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << radix_shift(pass - 1));
     const float4* v4 = reinterpret_cast<const float4*>(vol + static_cast<int64_t>(item) * n);  // n % 4 == 0 (checked by the host)
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n / 4;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float4 v = v4[i];
-        const float e[4] = {v.x, v.y, v.z, v.w};
+    if (pass == 0) {
+        for_each_vec4(v4, n / 4, [&](const float4 v) {   // all four selections share the first histogram
+            const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t k = pf2key(e[j]);
-            if (k > kmin && k < kmax) {
-                const uint32_t bin = (k >> shift) & 0xffu;
-                if (pass == 0) atomicAdd(&sh[bin], 1u);  // all four selections share the first histogram
-                else
-#pragma unroll
-                    for (int s = 0; s < PSEL; ++s)
-                        if ((k & himask) == spre[s]) atomicAdd(&sh[s * 256 + bin], 1u);
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t k = pf2key(e[j]);
+                if (k > kmin && k < kmax) atomicAdd(&sh[k >> 20], 1u);
             }
-        }
+        });
+    } else {
+        // Later passes: the four voxels of a 16-byte load share ONE branch (a branch per voxel and selection made these passes
+        // instruction-bound).  The below / above ranks of a percentile are adjacent and nearly always share their prefix; then
+        // the even selection's histogram serves both.
+        for_each_vec4(v4, n / 4, [&](const float4 v) {
+            const float e[4] = {v.x, v.y, v.z, v.w};
+            uint32_t k[4];
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                k[j] = pf2key(e[j]);
+                const uint32_t kp = k[j] & himask;
+                any |= (kp == p0) | (kp == p2) | (d1 & (kp == p1)) | (d3 & (kp == p3));
+            }
+            if (any) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (k[j] > kmin && k[j] < kmax) {
+                        const uint32_t kp = k[j] & himask, bin = (k[j] >> shift) & 0x3ffu;
+                        if (kp == p0) atomicAdd(&sh[bin], 1u);
+                        if (d1 && kp == p1) atomicAdd(&sh[1024 + bin], 1u);
+                        if (kp == p2) atomicAdd(&sh[2048 + bin], 1u);
+                        if (d3 && kp == p3) atomicAdd(&sh[3072 + bin], 1u);
+                    }
+                }
+            }
+        });
     }
     __syncthreads();
-    const int lim = pass == 0 ? 256 : PSEL * 256;
-    for (int i = threadIdx.x; i < lim; i += blockDim.x)
+    for (int i = threadIdx.x; i < 4096; i += blockDim.x)
         if (sh[i]) atomicAdd(&q.hist[i], sh[i]);
 }
 
 // torch.quantile(values, tensor(percentiles) / 100) (augmentations_3d.py:75), 'linear': ranks = q * (n - 1) in fp32,
 // below = trunc, above = ceil, weight = ranks - below.
-__global__ void prep_pick_kernel(int pass, float q_lo, float q_hi, PrepState* __restrict__ st) {
+__global__ void __launch_bounds__(256) prep_pick_kernel(int pass, float q_lo, float q_hi, PrepState* __restrict__ st) {
+    __shared__ unsigned long long excl[PSEL][256];   // voxels in the bins before thread t's group, per selection
+    __shared__ unsigned long long wsum[PSEL][8];
+    __shared__ unsigned long long total0;
     PrepState& q = st[blockIdx.x];
-    const int s = threadIdx.x;
-    if (s < PSEL) {
-        unsigned int* h = q.hist + (pass == 0 ? 0 : s * 256);
-        if (pass == 0) {
-            unsigned long long total = 0;
-            for (int i = 0; i < 256; ++i) total += h[i];
-            const float last = static_cast<float>(total > 0 ? total - 1 : 0);
-            const float r = (s < 2 ? q_lo : q_hi) * last;
-            const long long below = static_cast<long long>(r);
-            const long long above = static_cast<long long>(ceilf(r));
-            q.rank[s] = static_cast<unsigned long long>((s & 1) ? above : below);
-            if (!(s & 1)) q.w[s >> 1] = r - static_cast<float>(below);
-            if (s == 0) q.count = total;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int nb = radix_bins(pass), per = nb / 256;   // consecutive bins per thread: 16, then 4
+    int src[PSEL];
+#pragma unroll
+    for (int s = 0; s < PSEL; ++s) {
+        // histogram of selection s: shared in the first pass; later an odd selection with its neighbour's prefix reads the neighbour's
+        src[s] = pass == 0 ? 0 : s * 1024;
+        if (pass != 0 && (s & 1) && q.prefix[s] == q.prefix[s - 1]) src[s] = (s - 1) * 1024;
+        unsigned long long mine = 0;
+        for (int i = 0; i < per; ++i) mine += q.hist[src[s] + t * per + i];
+        unsigned long long v = mine;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long u = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= off) v += u;
         }
-        unsigned long long r = q.rank[s];
-        int bin = 0;
-        for (; bin < 255; ++bin) {
-            if (r < h[bin]) break;
-            r -= h[bin];
-        }
-        q.rank[s] = r;
-        q.prefix[s] |= static_cast<uint32_t>(bin) << (24 - 8 * pass);
+        excl[s][t] = v - mine;
+        if (lane == 31) wsum[s][warp] = v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < PSEL * 256; i += blockDim.x) q.hist[i] = 0;
+#pragma unroll
+    for (int s = 0; s < PSEL; ++s) {
+        unsigned long long base = 0;
+        for (int i = 0; i < warp; ++i) base += wsum[s][i];
+        excl[s][t] += base;
+    }
+    if (t == 0) {
+        unsigned long long tot = 0;
+        for (int i = 0; i < 8; ++i) tot += wsum[0][i];
+        total0 = tot;
+    }
+    __syncthreads();
+    if (pass == 0 && t < PSEL) {
+        const unsigned long long total = total0;
+        const float last = static_cast<float>(total > 0 ? total - 1 : 0);
+        const float r = (t < 2 ? q_lo : q_hi) * last;
+        const long long below = static_cast<long long>(r);
+        const long long above = static_cast<long long>(ceilf(r));
+        q.rank[t] = static_cast<unsigned long long>((t & 1) ? above : below);
+        if (!(t & 1)) q.w[t >> 1] = r - static_cast<float>(below);
+        if (t == 0) q.count = total;
+    }
+    __syncthreads();
+    // thread t owns the rank when excl[t] <= rank < excl[t+1]; a rank past the end (empty mask) falls into the last bin
+#pragma unroll
+    for (int s = 0; s < PSEL; ++s) {
+        const unsigned long long r = q.rank[s];
+        const unsigned long long lo = excl[s][t];
+        const bool last_t = t == 255;
+        const unsigned long long hi = last_t ? ~0ull : excl[s][t + 1];
+        __syncthreads();
+        if (r >= lo && r < hi) {
+            unsigned long long rem = r - lo;
+            int bin = t * per;
+            for (int i = 0; i < per - 1; ++i) {
+                const unsigned long long c = q.hist[src[s] + bin];
+                if (rem < c) break;
+                rem -= c;
+                ++bin;
+            }
+            const unsigned long long c = q.hist[src[s] + bin];
+            q.rank[s] = rem < c ? rem : 0ull;
+            q.prefix[s] |= static_cast<uint32_t>(bin) << radix_shift(pass);
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < 4096; i += blockDim.x) q.hist[i] = 0;
 }
 
 // ATen lerp (values_below.lerp_(values_above, weights)): w < 0.5 ? a + w (b - a) : b - (b - a)(1 - w), fused multiply-add
@@ -235,9 +351,7 @@ __global__ void __launch_bounds__(256) prep_moments_kernel(const float* __restri
     const float lo = q.lo, hi = q.hi;
     double sum = 0.0, sq = 0.0;
     const float4* v4 = reinterpret_cast<const float4*>(vol + static_cast<int64_t>(item) * n);
-    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n / 4;
-         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float4 v = v4[i];
+    for_each_vec4(v4, n / 4, [&](const float4 v) {
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -248,7 +362,7 @@ __global__ void __launch_bounds__(256) prep_moments_kernel(const float* __restri
                 sq += static_cast<double>(c) * static_cast<double>(c);
             }
         }
-    }
+    });
     for (int off = 16; off > 0; off >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, off);
         sq += __shfl_xor_sync(0xffffffffu, sq, off);
@@ -369,13 +483,13 @@ int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, i
         pm = PrepMargins{m_w, m_h, m_d, m_wh, m_wd, m_hd, m_whd, per};
     }
 
-    prep_gather_kernel<<<dim3((W + 31) / 32, H, items), dim3(32, 8), 0, stream>>>(src, g, pm, out, st);
+    prep_gather_kernel<<<dim3((W + 31) / 32, (H + GATHER_HB - 1) / GATHER_HB, items), dim3(32, 8), 0, stream>>>(src, g, pm, out, st);
     MST_CHECK_CUDA(cudaGetLastError());
 
     int gx = static_cast<int>((n / 4 + 256 * 8 - 1) / (256 * 8));
     const int cap = (4 * num_sms + items - 1) / items;
     gx = gx < 1 ? 1 : (gx > cap ? cap : gx);
-    for (int pass = 0; pass < 4; ++pass) {
+    for (int pass = 0; pass < RADIX_PASSES; ++pass) {
         prep_hist_kernel<<<dim3(gx, items), 256, 0, stream>>>(out, n, pass, st);
         MST_CHECK_CUDA(cudaGetLastError());
         prep_pick_kernel<<<items, 256, 0, stream>>>(pass, q_lo, q_hi, st);
