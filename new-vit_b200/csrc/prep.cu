@@ -88,6 +88,7 @@ struct PrepGeom {
     int W, H, D;        // target extents
     int ow, oh, od;     // source coordinate = target coordinate + offset (crop_ini - pad_ini)
     int flip_h;
+    int vec_ok;         // 16-byte loads along D and stores along W are aligned (pointers included)
 };
 struct PrepMargins {    // per-item tables, nullptr when no axis is padded
     const float *m_w, *m_h, *m_d, *m_wh, *m_wd, *m_hd, *m_whd;
@@ -127,9 +128,47 @@ __global__ void __launch_bounds__(256, 4) prep_gather_kernel(const float* __rest
     uint32_t kmin = 0xffffffffu, kmax = 0u;
     const int w1 = min(w0 + 32, g.W) - 1, h1 = min(h0 + GATHER_HB, g.H) - 1;
     const bool in_wh = w0 + g.ow >= 0 && w1 + g.ow < g.W0 && h0 + g.oh >= 0 && h1 + g.oh < g.H0;
+    const bool vec_ok = g.vec_ok && w0 + 32 <= g.W;
     for (int d0 = 0; d0 < g.D; d0 += 32) {
         const bool interior = in_wh && d0 + g.od >= 0 && min(d0 + 32, g.D) - 1 + g.od < g.D0;
+        const bool vec = vec_ok && d0 + 32 <= g.D;
         float v[GATHER_HB][4];
+        if (interior && vec) {
+            // 16-byte path (D0, the D offset and W multiples of 4, full 32 x 32 tiles): one LDG.128 along D and one STG.128
+            // along W per thread and tile, the 4 x 4 transposition through scalar shared-memory accesses (row stride 33:
+            // conflict-free both ways).  The scalar path was issue-bound (ncu: issue slots 76 %, DRAM 50 %).
+            const int t = threadIdx.y * 32 + threadIdx.x;
+            const int lw = t >> 3, ld4 = (t & 7) * 4;          // load: tile row (w) and first of four d
+            const int sw4 = (t & 7) * 4, sd = t >> 3;           // store: first of four w, d
+            float4 r[GATHER_HB];
+#pragma unroll
+            for (int hb = 0; hb < GATHER_HB; ++hb) {
+                const int sh = g.flip_h ? g.H0 - 1 - (h0 + hb + g.oh) : h0 + hb + g.oh;
+                r[hb] = h0 + hb < g.H ? __ldg(reinterpret_cast<const float4*>(
+                                            s + (static_cast<int64_t>(w0 + lw + g.ow) * g.H0 + sh) * g.D0 + (d0 + ld4 + g.od)))
+                                      : make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+            }
+#pragma unroll
+            for (int hb = 0; hb < GATHER_HB; ++hb) {
+                tile[hb][lw][ld4 + 0] = r[hb].x; tile[hb][lw][ld4 + 1] = r[hb].y;
+                tile[hb][lw][ld4 + 2] = r[hb].z; tile[hb][lw][ld4 + 3] = r[hb].w;
+                if (h0 + hb < g.H) {
+                    const uint32_t k0 = pf2key(r[hb].x), k1 = pf2key(r[hb].y), k2 = pf2key(r[hb].z), k3 = pf2key(r[hb].w);
+                    kmin = min(min(kmin, min(k0, k1)), min(k2, k3));
+                    kmax = max(max(kmax, max(k0, k1)), max(k2, k3));
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int hb = 0; hb < GATHER_HB; ++hb) {
+                if (h0 + hb < g.H) {
+                    const float4 w4 = make_float4(tile[hb][sw4 + 0][sd], tile[hb][sw4 + 1][sd], tile[hb][sw4 + 2][sd], tile[hb][sw4 + 3][sd]);
+                    *reinterpret_cast<float4*>(o + (static_cast<int64_t>(d0 + sd) * g.H + (h0 + hb)) * g.W + (w0 + sw4)) = w4;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         if (interior) {
             // every voxel of the tile lies inside the source: the address is affine in (k, hb), no table lookups, few registers
             const int sh0 = g.flip_h ? g.H0 - 1 - (h0 + g.oh) : h0 + g.oh;
@@ -206,7 +245,8 @@ __global__ void __launch_bounds__(256) prep_hist_kernel(const float* __restrict_
     const uint32_t kmin = q.kmin, kmax = q.kmax;
     // in registers: read from shared memory inside the loop they would be re-loaded after every atomic (possible alias)
     const uint32_t p0 = q.prefix[0], p1 = q.prefix[1], p2 = q.prefix[2], p3 = q.prefix[3];
-    const bool d1 = p1 != p0, d3 = p3 != p2;
+    // a selection counts only under a prefix no earlier selection has (prep_pick_kernel reads the first equal one's histogram)
+    const bool u1 = p1 != p0, u2 = p2 != p0 && p2 != p1, u3 = p3 != p0 && p3 != p1 && p3 != p2;
     __syncthreads();
     const int shift = radix_shift(pass);
     const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << radix_shift(pass - 1));
@@ -222,8 +262,10 @@ __global__ void __launch_bounds__(256) prep_hist_kernel(const float* __restrict_
         });
     } else {
         // Later passes: the four voxels of a 16-byte load share ONE branch (a branch per voxel and selection made these passes
-        // instruction-bound).  The below / above ranks of a percentile are adjacent and nearly always share their prefix; then
-        // the even selection's histogram serves both.
+        // instruction-bound).  The below / above ranks of a percentile are adjacent and nearly always share their prefix (u1 and
+        // u3 false): then a voxel counts under p0 or under p2, one predicated atomic.  Some lane of nearly every warp takes the
+        // counting path in the second pass (about 4 % of an MRI-like volume shares the upper cutoff's 12-bit prefix), so its
+        // instruction count is what that pass costs.
         for_each_vec4(v4, n / 4, [&](const float4 v) {
             const float e[4] = {v.x, v.y, v.z, v.w};
             uint32_t k[4];
@@ -232,17 +274,26 @@ __global__ void __launch_bounds__(256) prep_hist_kernel(const float* __restrict_
             for (int j = 0; j < 4; ++j) {
                 k[j] = pf2key(e[j]);
                 const uint32_t kp = k[j] & himask;
-                any |= (kp == p0) | (kp == p2) | (d1 & (kp == p1)) | (d3 & (kp == p3));
+                any |= (kp == p0) | (kp == p2) | (u1 & (kp == p1)) | (u3 & (kp == p3));
             }
             if (any) {
+                if (!u1 && !u3) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (k[j] > kmin && k[j] < kmax) {
+                    for (int j = 0; j < 4; ++j) {
                         const uint32_t kp = k[j] & himask, bin = (k[j] >> shift) & 0x3ffu;
-                        if (kp == p0) atomicAdd(&sh[bin], 1u);
-                        if (d1 && kp == p1) atomicAdd(&sh[1024 + bin], 1u);
-                        if (kp == p2) atomicAdd(&sh[2048 + bin], 1u);
-                        if (d3 && kp == p3) atomicAdd(&sh[3072 + bin], 1u);
+                        const bool m0 = kp == p0, m2 = u2 && kp == p2;
+                        if ((m0 || m2) && k[j] > kmin && k[j] < kmax) atomicAdd(&sh[(m0 ? 0u : 2048u) + bin], 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (k[j] > kmin && k[j] < kmax) {
+                            const uint32_t kp = k[j] & himask, bin = (k[j] >> shift) & 0x3ffu;
+                            if (kp == p0) atomicAdd(&sh[bin], 1u);
+                            if (u1 && kp == p1) atomicAdd(&sh[1024 + bin], 1u);
+                            if (u2 && kp == p2) atomicAdd(&sh[2048 + bin], 1u);
+                            if (u3 && kp == p3) atomicAdd(&sh[3072 + bin], 1u);
+                        }
                     }
                 }
             }
@@ -265,9 +316,11 @@ __global__ void __launch_bounds__(256) prep_pick_kernel(int pass, float q_lo, fl
     int src[PSEL];
 #pragma unroll
     for (int s = 0; s < PSEL; ++s) {
-        // histogram of selection s: shared in the first pass; later an odd selection with its neighbour's prefix reads the neighbour's
+        // histogram of selection s: shared in the first pass; later the one of the FIRST selection with the same prefix
         src[s] = pass == 0 ? 0 : s * 1024;
-        if (pass != 0 && (s & 1) && q.prefix[s] == q.prefix[s - 1]) src[s] = (s - 1) * 1024;
+        if (pass != 0)
+            for (int e = s - 1; e >= 0; --e)
+                if (q.prefix[e] == q.prefix[s]) src[s] = e * 1024;
         unsigned long long mine = 0;
         for (int i = 0; i < per; ++i) mine += q.hist[src[s] + t * per + i];
         unsigned long long v = mine;
@@ -440,7 +493,7 @@ int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, i
 
     // CropOrPad._get_six_bounds_parameters (augmentations_3d.py:166-175): ini = ceil(n / 2), fin = n - ini, for the padding and
     // for the cropping alike; tio.Pad then tio.Crop (:190-194).  An axis is padded or cropped, never both.
-    PrepGeom g{W0, H0, D0, W, H, D, 0, 0, 0, flip_h};
+    PrepGeom g{W0, H0, D0, W, H, D, 0, 0, 0, flip_h, 0};
     const int src_n[3] = {W0, H0, D0}, dst_n[3] = {W, H, D};
     int off[3];
     bool any_pad = false;
@@ -450,6 +503,8 @@ int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, i
         else off[a] = ((-diff) + 1) / 2;                                 // crop_ini removed in front
     }
     g.ow = off[0]; g.oh = off[1]; g.od = off[2];
+    g.vec_ok = D0 % 4 == 0 && ((g.od % 4) + 4) % 4 == 0 && W % 4 == 0 && reinterpret_cast<uintptr_t>(src) % 16 == 0 &&
+               reinterpret_cast<uintptr_t>(out) % 16 == 0;
 
     prep_init_kernel<<<items, 256, 0, stream>>>(st);
     MST_CHECK_CUDA(cudaGetLastError());

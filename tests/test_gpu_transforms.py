@@ -17,6 +17,9 @@ def _volume(shape, seed, kind="gamma"):
         v = rng.normal(0.0, 300.0, size=shape).astype(np.float32)
         v[rng.random(shape) < 0.3] = -1024.0
         return v
+    if kind == "geom":       # all values distinct and a factor 2^(1/8) apart: adjacent order statistics never share a 12-bit key
+        n = int(np.prod(shape))   # prefix, so the below / above ranks of a percentile walk different radix buckets
+        return (2.0 ** (rng.permutation(n) / 8.0 - 60.0)).astype(np.float32).reshape(shape)
     return np.round(rng.normal(0, 3, size=shape)).astype(np.float32)    # heavy ties everywhere
 
 
@@ -29,6 +32,8 @@ CASES = [
     ((250, 224, 27), (224, 224, 32), "ties"),      # crop W, pad D by an odd amount
     ((61, 45, 9), (56, 56, 8), "gamma"),           # small ragged tiles (W, D not multiples of 32)
     ((33, 70, 50), (40, 64, 36), "ct"),            # pad W, crop H and D, D > 32 (two d-tiles)
+    ((72, 60, 48), (56, 56, 40), "gamma"),         # 16-byte path on the full tiles, scalar path on the ragged ones (W, D)
+    ((8, 8, 12), (8, 8, 12), "geom"),              # every selection under its own radix prefix
 ]
 
 
