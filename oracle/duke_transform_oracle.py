@@ -3,13 +3,17 @@
 CPU restatement (numpy + torch CPU) of what DUKE_Dataset3D's default transform chain does to one volume between the
 HDF5 read and the model's `source` tensor.  Only `tests/` may import it.
 
-PARITY UNPINNED against torchio: the chain is built from torchio 0.19.9 classes (pinned in the reference's
-`environment.yaml:25`) and torchio is NOT in this image (no network), so the reference's transform objects cannot be run
-here.  What IS the reference's own code is restated line by line:
+PARITY PARTIALLY PINNED.  The chain is built from torchio 0.19.9 classes (pinned in the reference's
+`environment.yaml:25`) and torchio is NOT in this image (no network), so the torchio base classes cannot be run here.
+The reference's OWN code can: `oracle/ref_transform_harness.py` executes augmentations_3d.py from /root/reference over
+minimal stand-ins for those base classes, `tests/golden/duke_transform_ref.npz` holds its outputs (5 seeded volumes; script
+`tests/golden/make_transform_golden.py`), and this oracle is bit-equal to them (tests/test_transform_oracle.py).  That pins
+the reference's own lines, restated here one by one:
   * `CropOrPad._get_six_bounds_parameters` / `apply_transform` (mst/data/datasets/augmentations/augmentations_3d.py:166-195),
-  * `ZNormalization._znorm` (augmentations_3d.py:74-86: torch.quantile of the masked values, torch.clamp, znorm),
+  * `ZNormalization.apply_normalization` / `_znorm` (augmentations_3d.py:55-86: torch.quantile of the masked values, torch.clamp, znorm),
   * `ImageOrSubjectToTensor` (augmentations_3d.py:23-29: swapaxes(1, -1)),
   * the chain and its arguments (mst/data/datasets/dataset_3d_duke.py:36-47).
+UNPINNED remainder: what torchio itself does around them, below.
 The torchio 0.19.9 parts are restated from its published source and call the SAME library routines torchio calls
 (so the arithmetic is the library's, not a re-derivation):
   * `tio.Flip(axes=1)`: `torch.flip(data, dims=[axis + 1])` on the [C, W, H, D] tensor,

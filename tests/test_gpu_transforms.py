@@ -52,6 +52,18 @@ def test_duke_transform_matches_oracle(shape, crop, kind):
     torch.testing.assert_close(got[0].cpu(), want, rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("case", range(5))
+def test_duke_transform_matches_reference_golden(case):
+    """Against the output of the reference's own transform classes (tests/golden/duke_transform_ref.npz, see
+    tests/golden/make_transform_golden.py), not the oracle: same tolerance as above."""
+    import os
+    from new_vit_b200 import duke_transform
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "duke_transform_ref.npz"))
+    v, crop = g[f"in{case}"], tuple(int(c) for c in g[f"crop{case}"])
+    got = duke_transform(torch.from_numpy(v).cuda(), image_crop=crop)
+    torch.testing.assert_close(got[0].cpu(), torch.from_numpy(g[f"out{case}"]), rtol=0, atol=2e-5)
+
+
 def test_duke_transform_batch_items_are_independent_and_bit_identical():
     from new_vit_b200 import duke_transform
     vols = np.stack([_volume((240, 200, 30), seed=10 + i, kind=k) for i, k in enumerate(["gamma", "ct", "ties"])])

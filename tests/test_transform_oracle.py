@@ -89,3 +89,38 @@ def test_duke_transform_layout():
     raw = (v[4 + 3, 30 - 1 - (1 + 5), 2] - st["mean"]) / st["std"]
     raw = (min(max(v[4 + 3, 30 - 1 - (1 + 5), 2], st["lo"]), st["hi"]) - st["mean"]) / st["std"]
     assert float(src[0, 1 + 2, 5, 3]) == pytest.approx(raw, rel=1e-5, abs=1e-6)
+
+
+# ---- pinned against the reference's own code (tests/golden/duke_transform_ref.npz, made by make_transform_golden.py) ----
+def _golden_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "duke_transform_ref.npz"))
+    return [(g[f"in{i}"], tuple(int(c) for c in g[f"crop{i}"]), torch.from_numpy(g[f"out{i}"])) for i in range(int(g["n"]))]
+
+
+@pytest.mark.parametrize("case", range(5))
+def test_oracle_matches_reference_golden(case):
+    """The fixture is the output of the reference's OWN CropOrPad / ZNormalization / ImageOrSubjectToTensor objects
+    (augmentations_3d.py run in place over torchio stand-ins, oracle/ref_transform_harness.py).  Same ATen ops on both sides:
+    bit-equal in the container that made it; 1e-6 leaves room for another CPU's reduction order in mean / std."""
+    v, crop, want = _golden_cases()[case]
+    got, _ = O.duke_transform(v, image_crop=crop)
+    assert got.shape == want.shape
+    torch.testing.assert_close(got, want, rtol=0, atol=1e-6)
+
+
+def test_reference_code_reproduces_the_fixture():
+    """Container only: run the reference's classes again and compare with the committed fixture and with the oracle, bit for bit."""
+    from oracle import ref_transform_harness as R
+    if not R.reference_available():
+        pytest.skip("/root/reference is not present (GPU box)")
+    import sys
+    for v, crop, want in _golden_cases():
+        ref = R.reference_duke_transform(v, image_crop=crop)
+        assert torch.equal(ref, want)
+        assert torch.equal(O.duke_transform(v, image_crop=crop)[0], ref)
+    assert "torchio" not in sys.modules or hasattr(sys.modules["torchio"], "__version__")   # the stand-ins are gone again
+    A = R.load_reference_augmentations()
+    c = A.CropOrPad((8, 8, 8), random_center=False)
+    for n in ([0, 1, 2], [5, 24, 7]):       # the oracle's bounds rule against the reference's own method (:166-175)
+        assert tuple(int(b) for b in c._get_six_bounds_parameters(np.array(n))) == O.six_bounds(n)
