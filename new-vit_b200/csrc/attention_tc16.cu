@@ -178,6 +178,7 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
     const int my_items = blockIdx.x < num_items ? (num_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int n_tiles = 2 * my_items;
 
+    griddep_launch_dependents();
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map128); tma_prefetch_desc(&map16); tma_prefetch_desc(&mapO);
     }
@@ -194,6 +195,7 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    griddep_wait();   // qkv comes from the kernel in front
 
     if (warp == 0) {
         if (lane == 0) {
@@ -536,7 +538,13 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
-    kern<<<grid, THREADS, DYN_BYTES, stream>>>(m128, m16, mO, qkv, out, items, heads, dbg);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = DYN_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute pattr[1];
+    pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pattr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pattr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, m128, m16, mO, qkv, out, items, heads, dbg));
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -298,6 +298,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     const bool seqn = !kResident && (mode_flags & 0x400) != 0;
     const int n_fixed = unit % n_tiles;
 
+    griddep_launch_dependents();   // the next kernel's prologue may overlap this one's tail (it waits before touching data)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -325,6 +326,9 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     if (PAIR != 0) cluster_sync_all(); else __syncthreads();  // peers' barriers must be initialised before any remote arrive
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // Everything above reads weights only.  The producer lane also fetches its resident weight block before it waits for
+    // the kernel in front (whose output is A, the row statistics and, in place, the residual).
+    if (warp != 0 || lane != 0) griddep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -341,6 +345,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                         tma_load_2d(sB + kc * L::B_TILE_BYTES, &tmB, bfull_bar, kc * BK, n_fixed * BN);
                 }
             }
+            griddep_wait();
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < t_count; ++it) {
                 const int t = t_first + it * t_step;
@@ -673,16 +678,29 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     if (MCAST) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gemm_threads(EW)); cfg.dynamicSmemBytes = L::DYN_BYTES; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
         MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, mode, ep));
     } else {
-        kern<<<grid, gemm_threads(EW), L::DYN_BYTES, stream>>>(tmA, tmB, tmC, M, N, K, mode, ep);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(gemm_threads(EW)); cfg.dynamicSmemBytes = L::DYN_BYTES; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, M, N, K, mode, ep));
     }
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+bool pdl_enabled() {
+    static const int pdl = getenv("MST_PDL") ? atoi(getenv("MST_PDL")) : 0;
+    return pdl != 0;
 }
 
 bool gemm_wt_enabled() {

@@ -108,6 +108,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
     const int t_count = t_first < m_tiles ? (m_tiles - t_first + groups - 1) / groups : 0;
     const int f0 = (unit % n_pairs) * 256 + static_cast<int>(cta_rank) * 128;   // first feature of this CTA
 
+    griddep_launch_dependents();
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmC); }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -143,6 +144,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
     tc_fence_before_sync();
     cluster_sync_all();   // the leader's MMAs read the weight block of BOTH CTAs
     tc_fence_after_sync();
+    griddep_wait();       // the weight block above is constant; the tokens and their statistics come from the kernel in front
 
     if (warp == 0) {
         if (lane == 0) {
@@ -373,10 +375,12 @@ static int launch_wt(const TmaDesc& tmX, const TmaDesc& tmC, const bf16* W, int 
     if (groups > m_tiles) groups = m_tiles;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * groups * n_pairs); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = DYN_BYTES; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmX, tmC, W, M, N, n_pairs, ep));
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -94,6 +94,7 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ s
                                                       const float* __restrict__ cls_pos0, const float* __restrict__ regs, int R,
                                                       int H, int W, int KP, int E) {
     extern __shared__ float tile[];  // [14][W]
+    griddep_launch_dependents();
     const int gh = H / 14, gw = W / 14, P = gh * gw;
     const int s = blockIdx.x / gh, py = blockIdx.x % gh;
     const float* base = src + (static_cast<int64_t>(s) * H + py * 14) * W;
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const TIn* __restrict__ 
                                                          int64_t ldy, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int rows, float eps) {
     constexpr int V = E / 128;
+    griddep_launch_dependents();   // a GEMM launched as a programmatic dependent loads its weights while this kernel drains
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const bf16* __restrict__
                                                          float eps) {
     // half a warp per row, 16-byte loads: lane l of the half-warp owns the chunks l, l+16, ... of the row
     constexpr int V = E / 128;
+    griddep_launch_dependents();
     const int row = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
     const int hl = threadIdx.x & 15;
     const bool ok = row < rows;

@@ -119,6 +119,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (MST_PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while the kernel before it in the stream drains; nothing the earlier kernel wrote may be touched (and nothing it
+// reads may be overwritten) before griddep_wait().  Both are no-ops in a kernel launched the ordinary way.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
