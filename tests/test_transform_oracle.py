@@ -1,7 +1,8 @@
 """CPU checks of oracle/duke_transform_oracle.py (the input-pipeline oracle).  torchio is not in this
-image, so the oracle cannot be pinned against the reference's transform objects ("parity unpinned", see its header); what can
-be pinned is checked here: the reference's own bounds rule, the closed form the CUDA gather uses for np.pad's 'minimum' mode
-against np.pad itself, and the statistics contract of the z-normalisation."""
+image; the reference's OWN transform code (augmentations_3d.py) is run in place over torchio stand-ins by
+oracle/ref_transform_harness.py and its outputs are the fixture tests/golden/duke_transform_ref.npz, to which the oracle must be
+equal (last two tests).  The rest pins what torchio does around it: the closed form the CUDA gather uses for np.pad's 'minimum'
+mode against np.pad itself, the bounds rule, and the statistics contract of the z-normalisation."""
 import numpy as np
 import pytest
 import torch
