@@ -12,6 +12,9 @@ rotary_positional_encoding='RoPE' rotates the slice-token queries and keys (tran
 Not mirrored (raise NotImplementedError): pretrained=True (downloads hub weights; offline) and
 rotary_positional_encoding='LiRE' (transformer_blocks.py:352-358; see DESIGN.md for what the reference's version does).
 """
+import json
+from pathlib import Path
+
 import torch
 import torch.nn as nn
 
@@ -198,6 +201,59 @@ class DinoV2ClassifierSlice(nn.Module):
         r = super()._apply(fn, *a, **k)
         self._dirty = True
         return r
+
+    # -- checkpoints (base_model.py:50-81; main_predict.py:215 calls load_best_checkpoint) -------------
+    @classmethod
+    def save_best_checkpoint(cls, path_checkpoint_dir, best_model_path):
+        with open(Path(path_checkpoint_dir) / 'best_checkpoint.json', 'w') as f:          # base_model.py:51-54
+            json.dump({'best_model_epoch': Path(best_model_path).name}, f)
+
+    @classmethod
+    def _get_best_checkpoint_path(cls, path_checkpoint_dir, **kwargs):
+        with open(Path(path_checkpoint_dir) / 'best_checkpoint.json', 'r') as f:          # base_model.py:56-60
+            return Path(path_checkpoint_dir) / Path(json.load(f)['best_model_epoch'])
+
+    @classmethod
+    def load_best_checkpoint(cls, path_checkpoint_dir, **kwargs):
+        return cls.load_from_checkpoint(cls._get_best_checkpoint_path(path_checkpoint_dir), **kwargs)   # base_model.py:62-65
+
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
+        """What `LightningModule.load_from_checkpoint` does for the reference class: constructor arguments from the
+        checkpoint's 'hyper_parameters' (written by `save_hyperparameters()`, base_model.py:13-14), overridden by **kwargs,
+        then its 'state_dict'.  A checkpoint trained with `pretrained=True` was built on the torch.hub encoder
+        (dino.py:59-63: LayerScale, `blocks.<i>` names, a 518-pixel position table, optional registers); nothing is
+        downloaded here -- that architecture is read off the checkpoint's own tensors and every weight comes from it."""
+        checkpoint = torch.load(checkpoint_path, map_location=map_location or 'cpu', weights_only=False)
+        state = checkpoint['state_dict']
+        hparams = dict(checkpoint.get('hyper_parameters', {}))
+        hparams.update(kwargs)
+        hparams['pretrained'] = False
+        pos = state['encoder.pos_embed']
+        hparams.setdefault('img_size', 14 * int(round((pos.shape[1] - 1) ** 0.5)))
+        hparams.setdefault('hub_layout', 'encoder.blocks.0.ls1.gamma' in state)
+        hparams['use_registers'] = 'encoder.register_tokens' in state
+        size = {v[0]: k for k, v in synth.VIT_CFG.items()}.get(pos.shape[-1])
+        if size is not None:
+            hparams['model_size'] = size
+        model = cls(**hparams)
+        model.load_state_dict(state, strict=strict)
+        return model
+
+    def load_pretrained(self, checkpoint_path, map_location=None, **kwargs):
+        checkpoint_path = Path(checkpoint_path)
+        if checkpoint_path.is_dir():                                                        # base_model.py:67-73
+            checkpoint_path = self._get_best_checkpoint_path(checkpoint_path, **kwargs)
+        checkpoint = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
+        return self.load_weights(checkpoint["state_dict"], **kwargs)
+
+    def load_weights(self, pretrained_weights, strict=True, **kwargs):
+        filter = kwargs.get('filter', lambda key: key in pretrained_weights)                # base_model.py:75-81
+        init_weights = self.state_dict()
+        pretrained_weights = {key: value for key, value in pretrained_weights.items() if filter(key)}
+        init_weights.update(pretrained_weights)
+        self.load_state_dict(init_weights, strict=strict)
+        return self
 
     # -- weights -> C handle --------------------------------------------------------------------------
     def _release(self):

@@ -241,3 +241,16 @@ def test_errors_mirror_reference():
         m.get_attention_maps()
     y = m(torch.zeros(1, 1, 2, 224, 224), target=torch.zeros(1), uid=["a"])  # extra kwargs swallowed (base_model.py:155)
     assert y.shape == (1, 2)
+
+
+def test_checkpoint_round_trip_runs_the_same_forward(tmp_path):
+    """main_predict.py:215: `load_best_checkpoint(path_run)` then forward -- bit-identical to the model the weights came from."""
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    sd = synth.make_state_dict("s", 2, seed=11, variant="peaky")
+    x = synth.make_volume(2, 4, 224, 224, seed=11)
+    want = _model(sd, "fp32", 224)(x)
+    torch.save({"state_dict": sd, "hyper_parameters": dict(in_ch=1, out_ch=2, pretrained=False, precision="fp32")},
+               tmp_path / "last.ckpt")
+    DinoV2ClassifierSlice.save_best_checkpoint(tmp_path, tmp_path / "last.ckpt")
+    m = DinoV2ClassifierSlice.load_best_checkpoint(tmp_path).cuda().eval()
+    assert torch.equal(m(x), want)

@@ -100,3 +100,42 @@ def test_synth_is_deterministic():
     assert torch.equal(synth.make_volume(1, 3, 28, 28, seed=9), synth.make_volume(1, 3, 28, 28, seed=9))
     m = synth.make_padding_mask(4, 32, seed=1)
     assert m.shape == (4, 32) and not m[0].any() and m[1:].any()
+
+
+def test_checkpoint_loading_api_mirrors_base_model(tmp_path):
+    """base_model.py:50-81 + LightningModule.load_from_checkpoint, as main_predict.py:215 uses them: a Lightning-style
+    checkpoint ('hyper_parameters' + 'state_dict') and best_checkpoint.json."""
+    from new_vit_b200 import DinoV2ClassifierSlice
+    sd = synth.make_state_dict("s", 2, seed=3)
+    hp = dict(in_ch=1, out_ch=2, spatial_dims=2, pretrained=False, model_size="s", slice_fusion="transformer",
+              loss_kwargs={}, aucroc_kwargs={"task": "binary"})                    # BasicClassifier's extra arguments are swallowed
+    torch.save({"state_dict": sd, "hyper_parameters": hp, "epoch": 7}, tmp_path / "epoch=7.ckpt")
+    DinoV2ClassifierSlice.save_best_checkpoint(tmp_path, tmp_path / "epoch=7.ckpt")
+    assert DinoV2ClassifierSlice._get_best_checkpoint_path(tmp_path) == tmp_path / "epoch=7.ckpt"
+    m = DinoV2ClassifierSlice.load_best_checkpoint(tmp_path)
+    got = m.state_dict()
+    assert list(got.keys()) == list(sd.keys()) and all(torch.equal(got[k], sd[k]) for k in sd)
+    assert m._dirty                                                                # the next forward re-packs the weights
+
+    # load_pretrained on a directory, and load_weights with a filter (only the encoder is taken)
+    fresh = DinoV2ClassifierSlice(1, 2, pretrained=False)
+    before = {k: v.clone() for k, v in fresh.state_dict().items()}
+    fresh.load_weights(sd, filter=lambda key: key.startswith("encoder."))
+    after = fresh.state_dict()
+    assert torch.equal(after["encoder.pos_embed"], sd["encoder.pos_embed"])
+    assert torch.equal(after["linear.weight"], before["linear.weight"])
+    assert fresh.load_pretrained(tmp_path) is fresh
+    assert torch.equal(fresh.state_dict()["linear.weight"], sd["linear.weight"])
+
+
+def test_checkpoint_of_a_hub_trained_model_needs_no_download(tmp_path):
+    """A checkpoint trained with pretrained=True (hub encoder: LayerScale, blocks.<i>, 518-pixel position table, registers)
+    carries every weight; the architecture is read off its tensors."""
+    from new_vit_b200 import DinoV2ClassifierSlice
+    sd = synth.make_state_dict("s", 2, seed=4, img_size=518, layerscale=True, chunked_names=False, num_registers=4)
+    torch.save({"state_dict": sd, "hyper_parameters": dict(in_ch=1, out_ch=2, pretrained=True, use_registers=True)},
+               tmp_path / "hub.ckpt")
+    m = DinoV2ClassifierSlice.load_from_checkpoint(tmp_path / "hub.ckpt", precision="fp32")
+    assert m.num_registers == 4 and m.encoder.pos_embed.shape[1] == 1370 and m.precision == "fp32"
+    assert "encoder.blocks.11.ls2.gamma" in m.state_dict()
+    assert all(torch.equal(m.state_dict()[k], sd[k]) for k in sd)
