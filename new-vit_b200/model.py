@@ -203,19 +203,21 @@ class DinoV2ClassifierSlice(nn.Module):
         return r
 
     # -- checkpoints (base_model.py:50-81; main_predict.py:215 calls load_best_checkpoint) -------------
+    _BEST = 'best_checkpoint.json'          # {'best_model_epoch': <file name>} next to the checkpoints (base_model.py:51-60)
+
     @classmethod
     def save_best_checkpoint(cls, path_checkpoint_dir, best_model_path):
-        with open(Path(path_checkpoint_dir) / 'best_checkpoint.json', 'w') as f:          # base_model.py:51-54
-            json.dump({'best_model_epoch': Path(best_model_path).name}, f)
+        (Path(path_checkpoint_dir) / cls._BEST).write_text(json.dumps({'best_model_epoch': Path(best_model_path).name}))
 
     @classmethod
     def _get_best_checkpoint_path(cls, path_checkpoint_dir, **kwargs):
-        with open(Path(path_checkpoint_dir) / 'best_checkpoint.json', 'r') as f:          # base_model.py:56-60
-            return Path(path_checkpoint_dir) / Path(json.load(f)['best_model_epoch'])
+        run = Path(path_checkpoint_dir)
+        return run / json.loads((run / cls._BEST).read_text())['best_model_epoch']
 
     @classmethod
     def load_best_checkpoint(cls, path_checkpoint_dir, **kwargs):
-        return cls.load_from_checkpoint(cls._get_best_checkpoint_path(path_checkpoint_dir), **kwargs)   # base_model.py:62-65
+        """base_model.py:62-65: the checkpoint best_checkpoint.json names, through load_from_checkpoint."""
+        return cls.load_from_checkpoint(cls._get_best_checkpoint_path(path_checkpoint_dir), **kwargs)
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **kwargs):
@@ -241,18 +243,19 @@ class DinoV2ClassifierSlice(nn.Module):
         return model
 
     def load_pretrained(self, checkpoint_path, map_location=None, **kwargs):
-        checkpoint_path = Path(checkpoint_path)
-        if checkpoint_path.is_dir():                                                        # base_model.py:67-73
-            checkpoint_path = self._get_best_checkpoint_path(checkpoint_path, **kwargs)
-        checkpoint = torch.load(checkpoint_path, map_location=map_location, weights_only=False)
-        return self.load_weights(checkpoint["state_dict"], **kwargs)
+        """base_model.py:67-73: a checkpoint file, or a run directory (then its best checkpoint), into THIS model."""
+        path = Path(checkpoint_path)
+        if path.is_dir():
+            path = self._get_best_checkpoint_path(path, **kwargs)
+        return self.load_weights(torch.load(path, map_location=map_location, weights_only=False)["state_dict"], **kwargs)
 
     def load_weights(self, pretrained_weights, strict=True, **kwargs):
-        filter = kwargs.get('filter', lambda key: key in pretrained_weights)                # base_model.py:75-81
-        init_weights = self.state_dict()
-        pretrained_weights = {key: value for key, value in pretrained_weights.items() if filter(key)}
-        init_weights.update(pretrained_weights)
-        self.load_state_dict(init_weights, strict=strict)
+        """base_model.py:75-81: overlay the tensors `filter(key)` keeps (default: all of them) on the current state_dict
+        and load the result, so keys the filter drops keep their present values."""
+        keep = kwargs.get('filter') or (lambda key: True)
+        merged = self.state_dict()
+        merged.update({k: v for k, v in pretrained_weights.items() if keep(k)})
+        self.load_state_dict(merged, strict=strict)
         return self
 
     # -- weights -> C handle --------------------------------------------------------------------------
