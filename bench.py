@@ -124,14 +124,19 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+CPU_SAMPLE_VOLUMES = 4   # volumes per CPU step: batching helps ATen's threading a little (about +15 % over one volume here)
+
+
 def cpu_baseline(steps, warmup, threads=None):
-    """Time the oracle (CPU port of the reference path) on one synthetic volume per step."""
+    """Time the oracle (CPU port of the reference path) on a bounded sample of the workload: CPU_SAMPLE_VOLUMES synthetic
+    volumes per step, all host threads."""
     import torch
     from new_vit_b200 import synth
     from oracle import mst_oracle as O
     torch.set_num_threads(threads or os.cpu_count())
     sd = synth.make_state_dict("s", 2, seed=0)
-    x = synth.make_volume(1, 32, 224, 224, seed=0)
+    nv = CPU_SAMPLE_VOLUMES
+    x = synth.make_volume(nv, 32, 224, 224, seed=0)
     for _ in range(warmup):
         O.forward(sd, x)
     ts = []
@@ -139,8 +144,8 @@ def cpu_baseline(steps, warmup, threads=None):
         t0 = time.perf_counter()
         O.forward(sd, x)
         ts.append(time.perf_counter() - t0)
-    return {"value": 1.0 / statistics.median(ts), "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} x 1 volume 32x224x224 fp32 (oracle/mst_oracle.py, torch CPU), median; min {min(ts):.3f}s"}, ts
+    return {"value": nv / statistics.median(ts), "unit": "volumes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} x {nv} volumes 32x224x224 fp32 (oracle/mst_oracle.py, torch CPU), median; min {min(ts):.3f}s per step"}, ts
 
 
 def main():
@@ -177,7 +182,7 @@ def main():
 
     if args.impl == "reference":
         # The reference is a Python/PyTorch package that cannot travel to the GPU box; its path is timed through
-        # the oracle port on the host cores (bounded sample: one volume per step).
+        # the oracle port on the host cores (bounded sample: CPU_SAMPLE_VOLUMES volumes per step).
         if rank != 0:
             return
         base, ts = cpu_baseline(max(1, args.steps), max(1, args.warmup))
