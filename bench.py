@@ -63,6 +63,17 @@ def kernel_models(BD, N=257, E=384, heads=6):
     }
 
 
+def map_kernel_models(B, D, heads, N, H, W, sheads=12):
+    """Algorithmic HBM bytes per launch of the saliency kernels: the combiner reads the CLS rows
+    [BD, heads, N] + [B, 12, D+1] fp32 and writes the coarse map; the upsampler reads the coarse map and writes
+    6 422 528 B per 32x224x224 volume ([B,1,D,H,W] fp32)."""
+    P = N - 1
+    return {
+        "saliency_combine": (0, B * D * heads * N * 4 + B * sheads * (D + 1) * 4 + B * D * P * 4),
+        "saliency_upsample": (0, B * D * P * 4 + B * D * H * W * 4),
+    }
+
+
 class ClockSampler(threading.Thread):
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -148,6 +159,95 @@ def cpu_baseline(steps, warmup, threads=None):
             "sample": f"{steps} x {nv} volumes 32x224x224 fp32 (oracle/mst_oracle.py, torch CPU), median; min {min(ts):.3f}s per step"}, ts
 
 
+def load_peaks():
+    peaks = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "_src": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks.update(json.load(f)); peaks["_src"] = "measured"
+    except Exception:
+        pass
+    return peaks
+
+
+def run_extras(model_s, dev, rank, world, timed, peaks):
+    """Short runs of the other configurations on the same box, every rank (values are whole-job, max time over ranks):
+    config 3 (save_attn + full-resolution saliency volume, 256 volumes sharded over the ranks, at least 32 per GPU), config 4
+    (ViT-B/14, 64 slices x 252 x 252, 16 volumes per GPU), the reference's own predict loop (batch 1, with and without the 8-flip
+    TTA, main_predict.py:208,288) as a latency, and the input pipeline (mst_prepare_volume)."""
+    import torch
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    from new_vit_b200.model import run_pred
+    from new_vit_b200.transforms import duke_transform
+    out = {}
+    hbm = (peaks or {}).get("hbm_gbs", 1.0)
+    # ---- config 3 ----
+    B3, D, H = max(32, 256 // world), 32, 224
+    x3 = synth.make_volume(B3, D, H, H, seed=100 + rank).to(dev)
+
+    def sal():
+        with torch.no_grad():
+            model_s(x3, save_attn=True)
+            model_s.saliency_volume()
+    for _ in range(3):
+        sal()
+    ms = timed(sal, 5)
+    model_s.profile_begin()
+    for _ in range(5):
+        sal()
+    prof = model_s.profile_end()
+    mk = map_kernel_models(B3, D, 6, 257, H, H)
+    c3 = {"workload": f"config 3: save_attn forward + saliency volume [B,1,32,224,224] fp32, {B3} volumes per GPU x {world} GPU",
+          "value": B3 * world / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms}
+    for k in ("saliency_combine", "saliency_upsample"):
+        t, n = prof[k]
+        if n:
+            c3[k] = {"ms_per_launch": t / n, "algorithmic_bytes_per_launch": mk[k][1], "gbs": mk[k][1] / (t / n) / 1e6,
+                     "frac_of_hbm_peak": mk[k][1] / (t / n) / 1e6 / hbm}
+    out["config3_saliency"] = c3
+    del x3
+    # ---- the reference's predict loop: one volume per call (main_predict.py:208), device time per call ----
+    x1 = synth.make_volume(1, D, H, H, seed=7).to(dev)
+    with torch.no_grad():
+        for _ in range(5):
+            model_s(x1)
+        lat = timed(lambda: model_s(x1), 50)
+        batch = {"source": x1}
+        for _ in range(3):
+            run_pred(model_s, batch, save_attn=True, use_tta=True)
+        lat_tta = timed(lambda: run_pred(model_s, batch, save_attn=True, use_tta=True), 20)
+        lat_sal = timed(lambda: run_pred(model_s, batch, save_attn=True, use_tta=False), 20)
+    out["latency_batch1"] = {"workload": "1 volume 32x224x224 per call, device-resident (scripts/main_predict.py:208,288)",
+                             "forward_ms": lat, "run_pred_saliency_ms": lat_sal, "run_pred_saliency_tta8_ms": lat_tta,
+                             "forward_model_tflops": flops_per_volume(32) / lat / 1e9}
+    # ---- input pipeline (SURVEY 8 f4): 64 x (256x256x40 -> 224x224x32), mst_prepare_volume ----
+    raw = torch.randn(64, 256, 256, 40, device=dev) * 300 + 500
+    for _ in range(3):
+        duke_transform(raw, (224, 224, 32), check=False)
+    ms = timed(lambda: duke_transform(raw, (224, 224, 32), check=False), 10)
+    by = 64 * (224 * 224 * 32) * 4 * 2    # one read of the kept region + one write of the result
+    out["prepare_volume"] = {"workload": "64 x (256x256x40 fp32 -> crop 224x224x32, percentile-clamped z-norm, axis swap)",
+                             "ms_per_step": ms, "volumes_per_sec": 64 / (ms * 1e-3), "algorithmic_bytes": by,
+                             "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / hbm}
+    del raw
+    # ---- config 4 ----
+    torch.cuda.empty_cache()
+    mb = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", model_size="b", img_size=252).to(dev).eval()
+    mb.load_state_dict(synth.make_state_dict("b", 2, seed=0, img_size=252))
+    x4 = synth.make_volume(16, 64, 252, 252, seed=200 + rank).to(dev)
+    with torch.no_grad():
+        for _ in range(3):
+            mb(x4)
+        ms = timed(lambda: mb(x4), 5)
+    v4 = 16 * world / (ms * 1e-3)
+    tf = v4 * flops_per_volume(64, "b", 252) / 1e12
+    out["config4_vitb"] = {"workload": f"config 4: ViT-B/14, 16 volumes x 64 slices x 252x252 per GPU x {world} GPU (256x256 is rejected by "
+                                       "the reference, patch_embed.py:72-73)", "value": v4, "unit": "volumes/s", "ms_per_step": ms,
+                           "model_tflops": tf, "model_frac_of_bf16_burst_peak": tf / ((peaks or {}).get("bf16_tflops", 1.0) * world) if peaks else None}
+    del mb, x4
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -162,6 +262,7 @@ def main():
     ap.add_argument("--saliency", action="store_true", help="config 3: save_attn + full-resolution saliency volume")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short config-3 / config-4 / batch-1 / input-pipeline runs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -187,10 +288,14 @@ def main():
             return
         base, ts = cpu_baseline(max(1, args.steps), max(1, args.warmup))
         v = base["value"]
+        # `config` stays the GPU arm's (the driver matches the two arms on it); what THIS arm runs per step is a bounded sample of
+        # that workload, stated in `reference_arm_sample` and in cpu_baseline.sample
+        sample_note = (f"{CPU_SAMPLE_VOLUMES} volumes x 32 x 224 x 224 fp32 per step on the host cores (CPU port of the reference "
+                       "path, kind 'port'); the GPU-over-CPU ratio is a GPU-versus-CPU-port figure, not a same-device comparison")
         emit(({"impl": "reference", "metric": "volumes_per_sec", "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * statistics.median(ts),
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "slices_per_sec": v * 32, "config": cfg,
+                          "slices_per_sec": v * 32, "config": cfg, "reference_arm_sample": sample_note,
                           "cpu_baseline": base,
                           "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -209,8 +314,11 @@ def main():
     torch.manual_seed(0)
     model = DinoV2ClassifierSlice(1, 2, pretrained=False, precision=args.precision, model_size=args.model, img_size=args.img).to(dev).eval()
     model.load_state_dict(synth.make_state_dict(args.model, 2, seed=0, img_size=args.img))
-    x_host = synth.make_volume(B, D, args.img, args.img, seed=rank).pin_memory()
-    x_dev = x_host.to(dev)
+    x_host32 = synth.make_volume(B, D, args.img, args.img, seed=rank).pin_memory()
+    # what travels host -> device end to end: the bf16 path rounds every voxel to bf16 before the patch GEMM anyway, so the
+    # loader hands over bf16 volumes (bit-identical results, half the bytes); fp32 mode keeps fp32
+    x_host = x_host32.to(torch.bfloat16).pin_memory() if args.precision == "bf16" else x_host32
+    x_dev = x_host32.to(dev)
 
     def step(src):
         with torch.no_grad():
@@ -226,6 +334,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, steps):
+        """device time of `steps` calls of fn (CUDA events on the launching stream), max over ranks, in ms per call"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+
     for _ in range(max(3, args.warmup)):
         step(x_dev)
     barrier()
@@ -233,31 +355,20 @@ def main():
     sampler.start()
     # ---- device-resident timing ----
     l0 = model.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(x_dev)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    launches = (model.launch_count() - l0) + (2 * args.steps if args.saliency else 0)
+    ms_step = timed(lambda: step(x_dev), args.steps)
+    launches = model.launch_count() - l0
     # ---- end-to-end timing: pinned host input -> H2D -> forward -> logits D2H, every step ----
-    step(x_host).cpu()
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        y = step(x_host)
-        y_host = y.cpu()
-    e1.record()
-    barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    y_host = step(x_host).cpu()
+
+    def e2e_step(src):
+        nonlocal y_host
+        y_host = step(src).cpu()
+    ms_step_e2e = timed(lambda: e2e_step(x_host), args.steps)
+    ms_step_e2e32 = None
+    if x_host is not x_host32:
+        e2e_step(x_host32)
+        ms_step_e2e32 = timed(lambda: e2e_step(x_host32), args.steps)
     sampler.stop_flag = True
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms_step = ms.item() / args.steps
-    ms_step_e2e = ms_e2e.item() / args.steps
     vols = B * world
     value = vols / (ms_step * 1e-3)
     e2e = vols / (ms_step_e2e * 1e-3)
@@ -269,15 +380,12 @@ def main():
         for _ in range(args.steps):
             with torch.no_grad():
                 model(x_dev, save_attn=args.saliency)
+                if args.saliency:
+                    model.saliency_volume()
         prof = model.profile_end()
     out = None
+    peaks = load_peaks()
     if rank == 0:
-        peaks = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "_src": "fallback"}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks.update(json.load(f)); peaks["_src"] = "measured"
-        except Exception:
-            pass
         roof = None
         kernels = {}
         traffic = {}
@@ -299,6 +407,7 @@ def main():
                     "frac_of_burst": ach / peaks["bf16_tflops"], "flops_per_step": fl, "ms_per_step": gemm_ms, "traffic": None}
             tot = sum(v[0] for v in prof.values()) / args.steps
             models = kernel_models(B * D, N=1 + (args.img // 14) ** 2, E={'s': 384, 'b': 768}[args.model], heads={'s': 6, 'b': 12}[args.model])
+            models.update(map_kernel_models(B, D, {'s': 6, 'b': 12}[args.model], 1 + (args.img // 14) ** 2, args.img, args.img))
             for k, (m_, n_) in prof.items():
                 kernels[k] = {"ms_per_step": m_ / args.steps, "launches_per_step": n_ / args.steps, "share": (m_ / args.steps) / tot if tot else 0}
                 if k in models and n_ and args.precision == "bf16":
@@ -319,23 +428,31 @@ def main():
                             "peak": peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"],
                             "unit": "TFLOP/s" if tensor else "GB/s", "ms_per_launch": kt["ms_per_launch"],
                             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": by,
-                            "traffic": traffic.get(top), "share_of_step": kt["share"],
+                            "traffic": traffic.get(top), "traffic_src": "static: profiles/r01_ncu_traffic.json (one ncu --set full capture of this "
+                            "workload; refreshed by profiles/ncu_traffic.py, not measured in this run)", "share_of_step": kt["share"],
                             "peak_kind": f"{peaks['_src']} sustained (kernel timed inside a long step)"}
                 roof_top["frac"] = roof_top["achieved"] / roof_top["peak"]
                 roof = dict(roof_top, family=roof)
         base = None
         if not args.no_cpu_baseline and world == 1:
             base, _ = cpu_baseline(3, 1)
+    # ---- the other BASELINE.json configs and the reference's own predict loop, short runs on the same box (extra keys) ----
+    extras = None
+    if not args.no_extras and not args.saliency and args.model == "s" and args.precision == "bf16":
+        extras = run_extras(model, dev, rank, world, timed, peaks if rank == 0 else None)
+    if rank == 0:
         model_tflops = value * flops_per_volume(D, args.model, args.img) / 1e12
         out = {"metric": "volumes_per_sec", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
                "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": cfg,
                "slices_per_sec": value * D,
                "model_tflops": model_tflops, "model_frac_of_bf16_burst_peak": model_tflops / (peaks["bf16_tflops"] * world),
-               "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_step_e2e,
-                       "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+               "e2e": {"value": e2e, "unit": "volumes/s", "ms_per_step": ms_step_e2e, "source_dtype": str(x_host.dtype),
+                       "h2d_bytes_per_step": x_host.numel() * x_host.element_size(), "d2h_bytes_per_step": y_host.numel() * 4,
+                       "fp32_source": None if ms_step_e2e32 is None else
+                       {"value": vols / (ms_step_e2e32 * 1e-3), "ms_per_step": ms_step_e2e32, "h2d_bytes_per_step": x_host32.numel() * 4}},
                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": base, "kernels": kernels,
-               "numa_node_rank0": numa}
+               "numa_node_rank0": numa, "extras": extras}
         emit(out)
     if world > 1:
         dist.barrier()

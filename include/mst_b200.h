@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MST_ABI_VERSION 3
+#define MST_ABI_VERSION 4
 #if defined(__GNUC__)
 #define MST_API __attribute__((visibility("default")))
 #else
@@ -30,6 +30,9 @@ enum { MST_PRECISION_FP32 = 0, MST_PRECISION_BF16 = 1 };
 /* slice_fusion constructor argument (reference dino.py:80-101,144-157) */
 enum { MST_FUSION_TRANSFORMER = 0, MST_FUSION_LINEAR = 1, MST_FUSION_AVERAGE = 2 };
 enum { MST_ROTARY_NONE = 0, MST_ROTARY_ROPE = 1 };
+/* element type of the `source` volume handed to mst_forward.  The bf16 path rounds every voxel to bf16 before the patch GEMM
+ * anyway, so a bf16 upload is bit-identical to an fp32 one at half the host-to-device bytes. */
+enum { MST_SRC_F32 = 0, MST_SRC_BF16 = 1, MST_SRC_F16 = 2 };
 
 /* Architecture of one DinoV2ClassifierSlice instance.  Replaces the constructor arguments of
  * reference dino.py:33-103 (model_size -> embed_dim/depth/enc_heads per vision_transformer.py:340-396). */
@@ -52,6 +55,10 @@ typedef struct mst_config {
     int32_t rotary;            /* rotary_positional_encoding (dino.py:40,92; utils/transformer_blocks.py:335-351):
                                   MST_ROTARY_NONE, or MST_ROTARY_ROPE = RoPE on the slice-token queries and keys; the
                                   checkpoint then carries slice_fusion.layers.0.self_attn.rotary_positional_encoding.freqs */
+    int32_t interpolate_antialias; /* DinoVisionTransformer(interpolate_antialias=, interpolate_offset=) (vision_transformer.py:66-67,
+                                      198-210): 0 / 0.1 for the vendored factory and the plain hub checkpoints; 1 / 0.0 for the hub
+                                      "_reg" checkpoints (use_registers, dino.py:60-61) */
+    float interpolate_offset;
 } mst_config;
 
 typedef struct mst_handle_s* mst_handle;
@@ -78,9 +85,13 @@ MST_API int mst_finalize_weights(mst_handle h, void* stream);
 MST_API int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W, size_t* bytes);
 
 /* DinoV2ClassifierSlice.forward (dino.py:110-167).
- *   src        [B,1,D,H,W] fp32 (H, W multiples of 14; (H/14)*(W/14)+1 == pos_tokens; else error)
+ *   src        [B,1,D,H,W] of src_dtype (MST_SRC_*; H, W multiples of 14; the fp32 parity mode takes fp32 only)
  *   pad_mask   nullable [B,D] uint8, non-zero = ignore slice (dino.py:147-150)
- *   src        [B,1,D,H,W] fp32 (H, W multiples of 14)
+ *   tta        0, or 1 = run_pred's test-time augmentation (scripts/main_predict.py:147-149) as ONE batch: the encoder sees the 8
+ *              flipped variants torch.flip(source, dims), dims in [(), (2,), (3,), (4,), (2,3), (2,4), (3,4), (2,3,4)], of every
+ *              volume (flips are index arithmetic on the load; every variant gets the volume's un-flipped pad_mask, as the script
+ *              passes it).  Every output below then holds 8*B volumes, variant-major (volume v*B + b), and workspace must be
+ *              sized with mst_workspace_bytes(h, 8*B, ...).  mst_saliency(tta=1) un-flips and averages.
  *   logits     [B,out_ch] fp32 (nullable iff enable_linear == 0)
  *   feat       nullable [B,F] (without_linear, dino.py:164): F = emb for 'transformer'/'average', emb*D for 'linear',
  *              emb = embed_dim or embed_dim/4 behind the bottleneck
@@ -90,19 +101,23 @@ MST_API int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, i
  *   slice_cls  nullable [B,slice_heads,D+1]: row 0 of the slice attention (dino.py:174-175); 'transformer' only
  *   full_maps  nullable [depth,B*D,enc_heads,NT,NT] fp32: every block's full attention, as the reference's hook stores
  *              them (dino.py:241); only get_attention_cls needs them (mst_rollout) */
-MST_API int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
-                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, float* full_maps,
-                void* workspace, size_t workspace_bytes, void* stream);
+MST_API int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int32_t D, int32_t H, int32_t W,
+                const uint8_t* pad_mask, int32_t tta, float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls,
+                float* full_maps, void* workspace, size_t workspace_bytes, void* stream);
 
 /* get_plane_attention / get_slice_attention / get_attention_maps (dino.py:173-202) and the caller's
  * head-mean + reshape + trilinear upsample (scripts/main_predict.py:73-74,100,161-162), batched.
  *   attn_maps  nullable [B*D,enc_heads,P] (get_attention_maps)   plane_attn nullable [B*D,enc_heads,P] (get_plane_attention)
  *   slice_attn nullable [B*D] (get_slice_attention)
  *   coarse     nullable [B,1,D,gh,gw] (required when full != NULL)   full nullable [B,1,D,H,W]
- *   skip_tokens  tokens in front of the patches in plane_cls: 1, or 5 with registers (dino.py:191) */
-MST_API int mst_saliency(const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
-                 int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
-                 float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream);
+ *   skip_tokens  tokens in front of the patches in plane_cls: 1, or 5 with registers (dino.py:191)
+ *   tta        1: plane_cls / slice_cls come from mst_forward(tta=1) (8*B volumes, variant-major); coarse and slice_attn are
+ *              the un-flipped averages over the 8 variants in the script's summation order (main_predict.py:147-158), upsampled
+ *              ONCE (:161-162); attn_maps / plane_attn must be NULL (they are per variant)
+ *   h          nullable: the handle whose launch counter / profiler categories record the two kernels */
+MST_API int mst_saliency(mst_handle h, const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
+                 int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, int32_t tta,
+                 float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream);
 
 /* get_attention_cls (dino.py:204-212), attention rollout: out = maps[0] @ maps[1] @ ... @ maps[depth-1] evaluated right to
  * left.  maps [depth,nmat,N,N] fp32 (mst_forward's full_maps with nmat = B*D*enc_heads); out, scratch [nmat,N,N]. */
@@ -128,7 +143,7 @@ MST_API int mst_quantile(const float* data, int64_t n, int32_t items, const doub
  *         (status 0 ok; 1 std == 0 and 2 empty mask: the reference raises RuntimeError, augmentations_3d.py:75-84)
  * W*H*D must be a multiple of 4. */
 MST_API int mst_prepare_volume_workspace_bytes(int32_t items, int32_t W0, int32_t H0, int32_t D0, size_t* bytes);
-MST_API int mst_prepare_volume(const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H,
+MST_API int mst_prepare_volume(mst_handle h /* nullable: instrumentation only */, const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H,
                        int32_t D, int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
                        size_t workspace_bytes, void* stream);
 
@@ -150,6 +165,14 @@ MST_API int mst_kernel_gemm_bf16(const void* A, const void* W, int32_t M, int32_
  * mst_kernel_row_stats_bf16:  out = act(rstd * acc + bias[n]). */
 MST_API int mst_kernel_gemm_bf16_ln(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t gelu,
                             const float* bias, const float* rowstat, void* out, void* stream);
+/* The weight packing behind mst_kernel_gemm_bf16_ln, as mst_finalize_weights applies it to qkv / fc1: W [N,K], b [N], gamma / beta [K]
+ * fp32 -> Wd [N,K] bf16 (gamma-scaled, centred, rounded so that every row still sums to ~0) and bd [N] fp32. */
+MST_API int mst_kernel_pack_linear_ln(const float* W, const float* b, const float* gamma, const float* beta, int32_t N, int32_t K,
+                              void* Wd_bf16, float* bd, void* stream);
+/* fc2 as the forward runs it between two blocks (block.py:113 -> :112 of the next block): x[M,N] += A[M,K] W[N,K]^T + bias in place,
+ * and rowstat_out[M] = rstd of every UPDATED row (the next block's norm1 statistics) out of the same epilogue.  N = 384, K > 384. */
+MST_API int mst_kernel_gemm_bf16_res_stats(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, void* x,
+                                   float* rowstat_out, float eps, void* stream);
 MST_API int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream);
 /* profiling aid: same as mst_kernel_gemm_bf16, plus cycle counters of CTA 0 (8 x int64: MMA warp wait-for-accumulator,
  * wait-for-operands, total, tiles; epilogue warp 0 wait-for-MMA, TMEM read, math+store) */
@@ -161,9 +184,6 @@ MST_API int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32
  * warp-MMA kernel otherwise; _bf16_warp_mma always runs the latter. */
 MST_API int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_attention_bf16_warp_mma(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream);
-/* profiling aid: cycles one softmax warp of CTA 0 spends per phase (7 x int64: wait S, pass 1, pair barrier, pass 2,
- * wait O, epilogue, tiles) */
-MST_API int mst_debug_attention_timing(const void* qkv, void* out, int32_t BD, int32_t heads, long long* dbg_dev, void* stream);
 MST_API int mst_kernel_attention_f32(const float* qkv, float* out, int32_t BD, int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_layernorm_bf16(const void* x, void* y, const float* gamma, const float* beta, int32_t rows, int32_t E,
                               float eps, void* stream);

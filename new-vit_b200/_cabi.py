@@ -14,7 +14,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mst_b200.h")
 
 PRECISION = {"fp32": 0, "bf16": 1}
 FUSION = {"transformer": 0, "linear": 1, "average": 2}
-ABI_VERSION = 3
+SRC_DTYPE = {"torch.float32": 0, "torch.bfloat16": 1, "torch.float16": 2}
+ABI_VERSION = 4
 
 
 class MSTError(RuntimeError):
@@ -24,7 +25,8 @@ class MSTError(RuntimeError):
 class MstConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("embed_dim", "depth", "enc_heads", "slice_heads", "out_ch", "pos_tokens", "precision", "device",
-                 "num_registers", "use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear", "rotary")]
+                 "num_registers", "use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear", "rotary",
+                 "interpolate_antialias")] + [("interpolate_offset", ctypes.c_float)]
 
 
 def declared_symbols():
@@ -53,22 +55,23 @@ def lib():
     L.mst_set_weight.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]
     L.mst_finalize_weights.argtypes = [vp, vp]
     L.mst_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(sz)]
-    L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    L.mst_saliency.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.mst_saliency.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mst_rollout.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     L.mst_pos_embed.argtypes = [vp, i32, i32, vp, vp]
     L.mst_quantile_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
     L.mst_quantile.argtypes = [vp, i64, i32, vp, i32, vp, vp, sz, vp]
     L.mst_prepare_volume_workspace_bytes.argtypes = [i32, i32, i32, i32, ctypes.POINTER(sz)]
-    L.mst_prepare_volume.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, ctypes.c_float, ctypes.c_float, vp, vp, vp, sz, vp]
+    L.mst_prepare_volume.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, ctypes.c_float, ctypes.c_float, vp, vp, vp, sz, vp]
     L.mst_kernel_gemm_bf16.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_gemm_bf16_ln.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    L.mst_kernel_pack_linear_ln.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
+    L.mst_kernel_gemm_bf16_res_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, ctypes.c_float, vp]
     L.mst_kernel_row_stats_bf16.argtypes = [vp, vp, i32, i32, ctypes.c_float, vp]
     L.mst_debug_gemm_timing.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mst_kernel_gemm_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_attention_bf16.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_attention_bf16_warp_mma.argtypes = [vp, vp, i32, i32, i32, vp]
-    L.mst_debug_attention_timing.argtypes = [vp, vp, i32, i32, vp, vp]
     L.mst_kernel_attention_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_layernorm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
     L.mst_profile_begin.argtypes = [vp]

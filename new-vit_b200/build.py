@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmst_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_wt.cu", "attention_tc.cu", "attention_tc16.cu", "attention_tcg.cu", "attention_mma.cu", "kernels.cu", "extras.cu", "prep.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_wt.cu", "attention_tc16.cu", "attention_tcg.cu", "attention_mma.cu", "kernels.cu", "extras.cu", "prep.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -22,7 +22,9 @@ def _newest(paths):
     return max(os.path.getmtime(p) for p in paths)
 
 
-def build_library(force=False, verbose=False):
+def build_library(force=False, verbose=False, experiments=False):
+    """experiments=True adds -DMST_EXPERIMENTS: the MST_* environment switches (alternative tilings, A/B toggles) and the
+    clock64() phase counters behind mst_debug_gemm_timing.  The product build has neither."""
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "mst_b200.h"))
@@ -35,7 +37,7 @@ def build_library(force=False, verbose=False):
     for s in srcs:
         o = os.path.join(HERE, "build", os.path.basename(s) + ".o")
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [nvcc] + NVCC_FLAGS + (["-DMST_EXPERIMENTS"] if experiments else []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()
@@ -49,4 +51,5 @@ def build_library(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv or "--experiments" in sys.argv, verbose="-v" in sys.argv,
+                        experiments="--experiments" in sys.argv))

@@ -45,11 +45,21 @@ __global__ void pack_linear_kernel(const float* __restrict__ W, const float* __r
 // LayerNorm folded into the consuming Linear (EPI_LN_*): one CTA per output row n.
 //   g[k] = W[n,k] * f_n * gamma[k];  Wd[n,k] = bf16(g[k] - mean_k g)  (centred row: x . Wd[n,:] = (x - mean x) . g);
 //   bd[n] = b[n]*f_n + sum_k beta[k] * W[n,k] * f_n
+// The centring must survive the bf16 rounding: x . Wd[n,:] carries mean(x) * sum_k Wd[n,k], and independent roundings leave
+// sum_k Wd[n,k] ~ sqrt(K) * ulp/sqrt(12) (7e-4 for K = 384, |W| ~ 0.02), which a row with mean(x) * rstd ~ 20 (real DINOv2
+// residual streams have such rows) turns into a 1.4e-2 error on every output.  So after rounding, single elements are moved
+// by one bf16 step -- the ones whose new rounding error is smallest -- until no step brings the row sum closer to zero:
+// |sum_k Wd[n,k]| ends below half the smallest step available in the row (~1e-7), at the cost of a handful of elements per
+// row carrying up to one ulp of rounding error instead of half.
+constexpr int kPackLnMaxK = 1024;
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
 __global__ void __launch_bounds__(128) pack_linear_ln_kernel(const float* __restrict__ W, const float* __restrict__ b,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              int nscaled, float s, bf16* __restrict__ Wd, float* __restrict__ bd,
                                                              int K) {
     __shared__ float red[2][4];
+    __shared__ float tk[kPackLnMaxK];       // exact centred values
+    __shared__ uint16_t qb[kPackLnMaxK];    // their bf16 roundings (bits)
     const int n = blockIdx.x;
     const float f = n < nscaled ? s : 1.0f;
     float cs = 0.f, ds = 0.f;
@@ -62,9 +72,41 @@ __global__ void __launch_bounds__(128) pack_linear_ln_kernel(const float* __rest
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = cs; red[1][threadIdx.x >> 5] = ds; }
     __syncthreads();
     const float mean = ((red[0][0] + red[0][1]) + (red[0][2] + red[0][3])) / K;
-    for (int k = threadIdx.x; k < K; k += blockDim.x)
-        Wd[static_cast<int64_t>(n) * K + k] = __float2bfloat16_rn(W[static_cast<int64_t>(n) * K + k] * f * gamma[k] - mean);
-    if (threadIdx.x == 0) bd[n] = b[n] * f + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float t = W[static_cast<int64_t>(n) * K + k] * f * gamma[k] - mean;
+        tk[k] = t;
+        qb[k] = __bfloat16_as_ushort(__float2bfloat16_rn(t));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double r = 0.0;
+        for (int k = 0; k < K; ++k) r += static_cast<double>(bf16_bits_to_float(qb[k]));
+        for (int iter = 0; iter < 256; ++iter) {
+            int best = -1;
+            uint16_t best_bits = 0;
+            float best_cost = 3.0e38f;
+            double best_d = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const uint16_t bits = qb[k];
+                if ((bits & 0x7f80) == 0) continue;                       // zero / subnormal: leave alone
+                const float qv = bf16_bits_to_float(bits);
+                const bool up = r < 0.0;                                   // the row sum must grow
+                const uint16_t nb = (up == (qv > 0.f)) ? bits + 1 : bits - 1;
+                if ((nb & 0x7f80) == 0x7f80 || (nb & 0x7f80) == 0) continue;
+                const float nv = bf16_bits_to_float(nb);
+                const double d = static_cast<double>(nv) - static_cast<double>(qv);
+                if (fabs(r + d) >= fabs(r)) continue;                      // this step would not bring the sum closer to zero
+                const float cost = fabsf(nv - tk[k]);                      // the element's rounding error after the step
+                if (cost < best_cost) { best_cost = cost; best = k; best_bits = nb; best_d = d; }
+            }
+            if (best < 0) break;
+            qb[best] = best_bits;
+            r += best_d;
+        }
+        bd[n] = b[n] * f + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) Wd[static_cast<int64_t>(n) * K + k] = __ushort_as_bfloat16(qb[k]);
 }
 // conv weight [E,3,14,14] -> [E,KP]: sum over the 3 identical input channels (dino.py:127 repeats gray -> RGB)
 template <typename T>
@@ -109,8 +151,9 @@ struct Layer {
 
 namespace mst {
 enum Cat { CAT_IM2COL = 0, CAT_GEMM_PATCH, CAT_LAYERNORM, CAT_GEMM_QKV, CAT_ATTENTION, CAT_GEMM_PROJ, CAT_GEMM_FC1,
-           CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, CAT_FULL_MAPS, NUM_CAT };
-static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps";
+           CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, CAT_FULL_MAPS, CAT_SALIENCY_COMBINE,
+           CAT_SALIENCY_UPSAMPLE, CAT_PREPARE_VOLUME, NUM_CAT };
+static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps,saliency_combine,saliency_upsample,prepare_volume";
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> pool;
@@ -226,6 +269,7 @@ static int pack_linear(mst_handle h, const std::string& wname, const std::string
 static int pack_linear_ln(mst_handle h, const std::string& wname, const std::string& bname, const float* gamma, const float* beta,
                           int nscaled, float s, int N, int K, void** Wd, float** bd, cudaStream_t st) {
     bf16* w;
+    MST_REQUIRE(K <= kPackLnMaxK, "pack_linear_ln: K=%d exceeds %d", K, kPackLnMaxK);
     MST_PROPAGATE(alloc_dev<bf16>(h, &w, static_cast<size_t>(N) * K));
     MST_PROPAGATE(alloc_dev<float>(h, bd, N));
     pack_linear_ln_kernel<<<N, 128, 0, st>>>(h->master[wname], h->master[bname], gamma, beta, nscaled, s, w, *bd, K);
@@ -259,7 +303,7 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
         // q rows (first E outputs) carry the 1/sqrt(64) attention scale (attention.py:60): exact power of two.
         // bf16 path: norm1 is folded into qkv and norm2 into fc1 (the last block's fc1 runs on CLS rows behind a real
         // LayerNorm kernel, so it stays unfolded).
-        static const bool no_fold = getenv("MST_NO_LN_FOLD") != nullptr;  // experiments only: separate LayerNorm kernels
+        static const bool no_fold = exp_env("MST_NO_LN_FOLD", 0) != 0;  // experiments only: separate LayerNorm kernels
         const bool kFold = std::is_same<T, bf16>::value && !no_fold;
         L.fold_qkv = kFold;
         L.fold_fc1 = kFold && i != h->cfg.depth - 1;
@@ -316,6 +360,22 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
     return 0;
 }
 
+// interpolate_pos_encoding's resampling step (vision_transformer.py:194-208) for the handle's interpolate_* configuration
+static int resample_pos(mst_handle h, const float* cbias, float* dst, int M, int gh, int gw, cudaStream_t st) {
+    const int E = h->cfg.embed_dim;
+    const float* pos = h->master["encoder.pos_embed"];
+    if (h->cfg.interpolate_antialias) {
+        MST_REQUIRE(h->cfg.interpolate_offset == 0.0f, "interpolate_antialias is built for interpolate_offset = 0 (the hub _reg configuration)");
+        return launch_pos_bicubic_aa(pos, cbias, dst, M, gh, gw, E, st);
+    }
+    // scale_factor = (g + offset) / M (:199-200); ATen maps coordinates with 1/scale_factor.  offset == 0: size=(gh, gw) and the
+    // coordinate scale is in/out (:203-204)
+    const double off = h->cfg.interpolate_offset;
+    const float sy = static_cast<float>(1.0 / ((gh + off) / static_cast<double>(M)));
+    const float sx = static_cast<float>(1.0 / ((gw + off) / static_cast<double>(M)));
+    return launch_pos_bicubic(pos, cbias, dst, M, gh, gw, E, sy, sx, st);
+}
+
 // Patch position table (+ conv bias) for a gh x gw patch grid: the checkpoint's own rows when the grid matches
 // (vision_transformer.py:183-184), else bicubic resampling (:185-211), cached per grid for the handle's lifetime.
 static int pos_for_grid(mst_handle h, int gh, int gw, const float** out, cudaStream_t st) {
@@ -329,11 +389,7 @@ static int pos_for_grid(mst_handle h, int gh, int gw, const float** out, cudaStr
     if (it == h->pos_cache.end()) {
         float* t = nullptr;
         MST_CHECK_CUDA(cudaMalloc(&t, static_cast<size_t>(gh) * gw * E * sizeof(float)));
-        // scale_factor = (g + 0.1) / M (interpolate_offset, :199-200); ATen maps coordinates with 1/scale_factor
-        const float sy = static_cast<float>(1.0 / ((gh + 0.1) / static_cast<double>(M)));
-        const float sx = static_cast<float>(1.0 / ((gw + 0.1) / static_cast<double>(M)));
-        MST_PROPAGATE(launch_pos_bicubic(h->master["encoder.pos_embed"], h->master["encoder.patch_embed.proj.bias"], t, M, gh, gw, E,
-                                         sy, sx, st));
+        MST_PROPAGATE(resample_pos(h, h->master["encoder.patch_embed.proj.bias"], t, M, gh, gw, st));
         it = h->pos_cache.emplace(key, t).first;
     }
     *out = it->second;
@@ -373,11 +429,6 @@ static Workspace carve(const mst_config& c, int B, int D, int H, int W, uint8_t*
     return w;
 }
 
-static int attn257_warps() {
-    static const int w = getenv("MST_ATTN_WARPS") ? atoi(getenv("MST_ATTN_WARPS")) : 16;
-    return w == 8 ? 8 : 16;
-}
-
 template <typename T> struct Ops;
 template <> struct Ops<bf16> {
     static int gemm(mst_handle h, const void* A, int64_t lda, const void* W, int M, int N, int K, int mode, const EpiParams& ep, cudaStream_t st) {
@@ -385,12 +436,9 @@ template <> struct Ops<bf16> {
         return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, h->num_sms, st);
     }
     static int attention(mst_handle h, const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
-        if (N == 257) {  // ViT @224: the specialised tcgen05 kernels (16 softmax warps by default, MST_ATTN_WARPS=8: the older one)
-            if (attn257_warps() == 16)
-                return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
-            return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
-        }
-        static const int use_tcg = getenv("MST_ATTN_TCG") ? atoi(getenv("MST_ATTN_TCG")) : 1;   // 0: A-B comparisons
+        if (N == 257)   // ViT @224: the specialised tcgen05 kernel (16 softmax warps)
+            return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
+        static const int use_tcg = exp_env("MST_ATTN_TCG", 1);   // 0: A-B comparisons
         if (use_tcg && attention_tcg_supported(N))
             return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, h->num_sms, st);
         return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, st);
@@ -416,9 +464,10 @@ template <> struct Ops<float> {
     } while (0)
 
 template <typename T>
-static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W, const uint8_t* pad_mask, float* logits,
-                     float* feat, float* enc_cls_out, float* plane_cls, float* slice_cls, float* full_maps, const Workspace& ws,
-                     cudaStream_t st) {
+static int forward_t(mst_handle h, const void* src, int src_dtype, int B, int D, int H, int W, const uint8_t* pad_mask, int tta,
+                     float* logits, float* feat, float* enc_cls_out, float* plane_cls, float* slice_cls, float* full_maps,
+                     const Workspace& ws, cudaStream_t st) {
+    // B counts the volumes that run through the encoder: with tta, 8 flipped variants of each of the B / 8 source volumes
     const mst_config& c = h->cfg;
     const int E = c.embed_dim, BD = B * D, P = (H / 14) * (W / 14), R = c.num_registers, N = P + 1 + R;
     const float* posb = nullptr;
@@ -430,8 +479,9 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
     T* xn = static_cast<T*>(ws.xn);
 
     // patch embedding + CLS/pos (K1-K3)
-    MST_LAUNCH(CAT_IM2COL, launch_im2col<T>(src, static_cast<T*>(ws.A0), x, h->cls_pos0,
-                                            R > 0 ? h->master["encoder.register_tokens"] : nullptr, R, BD, H, W, KP, E, st));
+    MST_LAUNCH(CAT_IM2COL, launch_im2col<T>(src, src_dtype, static_cast<T*>(ws.A0), x, h->cls_pos0,
+                                            R > 0 ? h->master["encoder.register_tokens"] : nullptr, R, BD, H, W, KP, E,
+                                            tta ? BD / 8 : 0, D, st));
     {
         EpiParams ep{};
         ep.posb = posb; ep.P = P; ep.R = R; ep.out = x; ep.ldo = E;
@@ -464,7 +514,7 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
             // norm2 statistics as row partials out of proj's epilogue, consumed by fc1: measured SLOWER (proj 0.21 -> 0.40 ms with
             // the explicit per-lane residual loads instead of the TMA reduce-add, fc1 0.68 -> 0.78 ms with 32 bytes of partials
             // per token instead of 4 bytes of rstd: step 31.3 -> 32.1 ms), so it is off unless MST_PROJ_STAT_FUSE=1
-            static const int fuse_stats = getenv("MST_PROJ_STAT_FUSE") ? atoi(getenv("MST_PROJ_STAT_FUSE")) : 0;
+            static const int fuse_stats = exp_env("MST_PROJ_STAT_FUSE", 0);
             const bool part_fc1 = fuse_stats && sizeof(T) == 2 && E == 384 && L.fold_fc1 && gemm_wt_enabled();
             {
                 EpiParams ep{};
@@ -491,7 +541,7 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
                 ep.bias = L.bfc2; ep.res = x; ep.ldr = E; ep.out = x; ep.ldo = E;
                 // The next block's norm1 statistics come out of this GEMM's epilogue (it then adds the residual itself instead
                 // of a TMA reduce-add, and one CTA pair walks both n-blocks of its rows): one pass over x less per block.
-                static const int fuse = getenv("MST_NO_STAT_FUSE") ? 0 : 1;
+                static const int fuse = exp_env("MST_NO_STAT_FUSE", 0) ? 0 : 1;
                 if (fuse && sizeof(T) == 2 && E == 384 && h->layers[l + 1].fold_qkv) {
                     ep.rowstat_out = ws.rowstat; ep.stat_eps = 1e-6f;
                     stats_from_fc2 = true;
@@ -527,7 +577,7 @@ static int forward_t(mst_handle h, const float* src, int B, int D, int H, int W,
                                                                  h->master["encoder.norm.bias"], BD, E, 1e-6f, st)));
             MST_LAUNCH(CAT_SLICE_FUSION, launch_slice_fusion(enc, pad_mask, h->sw, ws.hs, c.enable_linear ? logits : nullptr, feat,
                                                          slice_cls, B, D, E, h->slice_emb(), c.slice_heads, c.out_ch,
-                                                         c.slice_fusion, st));
+                                                         c.slice_fusion, tta ? B / 8 : 0, st));
         }
     }
     return 0;
@@ -558,6 +608,7 @@ int mst_create(const mst_config* cfg, mst_handle* out) {
                 cfg->slice_fusion);
     MST_REQUIRE(cfg->rotary == MST_ROTARY_NONE || (cfg->rotary == MST_ROTARY_ROPE && cfg->slice_fusion == MST_FUSION_TRANSFORMER),
                 "mst_create: rotary=%d unsupported (RoPE needs slice_fusion='transformer'; LiRE is not built)", cfg->rotary);
+    MST_REQUIRE(cfg->interpolate_offset >= 0.0f && cfg->interpolate_offset < 1.0f, "mst_create: bad interpolate_offset %f", (double)cfg->interpolate_offset);
     MST_REQUIRE(!cfg->use_bottleneck || (cfg->embed_dim / 4) % cfg->slice_heads == 0, "mst_create: bottleneck width %d not divisible by %d heads",
                 cfg->embed_dim / 4, cfg->slice_heads);
     int ndev = 0;
@@ -644,10 +695,15 @@ int mst_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W
     return 0;
 }
 
-int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
-                float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, float* full_maps,
+int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int32_t D, int32_t H, int32_t W, const uint8_t* pad_mask,
+                int32_t tta, float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls, float* full_maps,
                 void* workspace, size_t workspace_bytes, void* stream) {
     MST_REQUIRE(h && src && workspace && (logits || !h->cfg.enable_linear), "mst_forward: null argument");
+    MST_REQUIRE(src_dtype == MST_SRC_F32 || src_dtype == MST_SRC_BF16 || src_dtype == MST_SRC_F16, "mst_forward: bad src_dtype %d", src_dtype);
+    MST_REQUIRE(src_dtype == MST_SRC_F32 || h->cfg.precision == MST_PRECISION_BF16,
+                "mst_forward: the fp32 parity mode takes fp32 volumes (a 16-bit source would be the only rounding on the path)");
+    MST_REQUIRE(!tta || full_maps == nullptr, "mst_forward: full_maps and tta are exclusive");
+    if (tta) B *= 8;   // the encoder sees 8 flipped variants of every volume (variant-major); outputs are sized for them
     MST_REQUIRE(h->cfg.slice_fusion == MST_FUSION_TRANSFORMER || slice_cls == nullptr,
                 "mst_forward: slice attention exists only for slice_fusion='transformer' (dino.py:257-260)");
     MST_REQUIRE(h->finalized, "mst_forward: weights not finalized");
@@ -658,17 +714,23 @@ int mst_forward(mst_handle h, const float* src, int32_t B, int32_t D, int32_t H,
     MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (h->cfg.precision == MST_PRECISION_BF16)
-        return forward_t<bf16>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
-    return forward_t<float>(h, src, B, D, H, W, pad_mask, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+        return forward_t<bf16>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+    return forward_t<float>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
 }
 
-int mst_saliency(const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
-                 int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, float* attn_maps,
+int mst_saliency(mst_handle h, const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
+                 int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, int32_t tta, float* attn_maps,
                  float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream) {
     MST_REQUIRE(plane_cls && slice_cls, "mst_saliency: null argument");
     MST_REQUIRE(B >= 1 && D >= 1 && gh >= 1 && gw >= 1 && skip_tokens >= 1, "mst_saliency: empty input");
-    return launch_saliency(plane_cls, slice_cls, B, D, enc_heads, slice_heads, skip_tokens, gh, gw, H, W, attn_maps, plane_attn, slice_attn,
-                           coarse, full, static_cast<cudaStream_t>(stream));
+    MST_REQUIRE(coarse != nullptr || full == nullptr, "mst_saliency: the full-resolution map needs the coarse buffer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    mst_handle_s none;   // instrumentation is optional: without a handle the launches are not counted
+    if (!h) h = &none;
+    MST_LAUNCH(CAT_SALIENCY_COMBINE, launch_saliency_combine(plane_cls, slice_cls, B, D, enc_heads, slice_heads, skip_tokens, gh, gw, tta,
+                                                             attn_maps, plane_attn, slice_attn, coarse, st));
+    if (full) MST_LAUNCH(CAT_SALIENCY_UPSAMPLE, launch_saliency_upsample(coarse, full, B, D, gh, gw, H, W, st));
+    return 0;
 }
 
 int mst_rollout(const float* maps, int32_t depth, int32_t nmat, int32_t N, float* out, float* scratch, void* stream) {
@@ -691,9 +753,7 @@ int mst_pos_embed(mst_handle h, int32_t H, int32_t W, float* out, void* stream) 
         return 0;
     }
     MST_REQUIRE(M * M == h->cfg.pos_tokens - 1, "mst_pos_embed: pos_embed is not a square grid");
-    const float sy = static_cast<float>(1.0 / ((gh + 0.1) / static_cast<double>(M)));
-    const float sx = static_cast<float>(1.0 / ((gw + 0.1) / static_cast<double>(M)));
-    return launch_pos_bicubic(pos, nullptr, out + E, M, gh, gw, E, sy, sx, st);
+    return resample_pos(h, nullptr, out + E, M, gh, gw, st);
 }
 
 int mst_quantile_workspace_bytes(int32_t items, int32_t nq, size_t* bytes) {
@@ -716,7 +776,7 @@ int mst_prepare_volume_workspace_bytes(int32_t items, int32_t W0, int32_t H0, in
     *bytes = prepare_volume_workspace_bytes(items, W0, H0, D0);
     return 0;
 }
-int mst_prepare_volume(const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H, int32_t D,
+int mst_prepare_volume(mst_handle h, const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H, int32_t D,
                        int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
                        size_t workspace_bytes, void* stream) {
     MST_REQUIRE(src && out && workspace, "mst_prepare_volume: null argument");
@@ -726,8 +786,12 @@ int mst_prepare_volume(const float* src, int32_t items, int32_t W0, int32_t H0, 
     int dev = 0, sms = 0;
     MST_CHECK_CUDA(cudaGetDevice(&dev));
     MST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    return launch_prepare_volume(src, items, W0, H0, D0, W, H, D, flip_h, q_lo, q_hi, out, stats, workspace, sms,
-                                 static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    mst_handle_s none;
+    if (!h) h = &none;
+    MST_LAUNCH(CAT_PREPARE_VOLUME, launch_prepare_volume(src, items, W0, H0, D0, W, H, D, flip_h, q_lo, q_hi, out, stats, workspace, sms, st));
+    h->launches += launch_prepare_volume_count(W0, H0, D0, W, H, D) - 1;   // the chain is several kernels, timed as one category
+    return 0;
 }
 
 const char* mst_profile_categories(void) { return kCatNames; }
@@ -774,6 +838,21 @@ int mst_kernel_gemm_bf16_ln(const void* A, const void* W, int32_t M, int32_t N, 
     return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, gelu ? EPI_LN_BIAS_GELU : EPI_LN_BIAS, ep,
                         num_sms_current(), static_cast<cudaStream_t>(stream));
 }
+int mst_kernel_pack_linear_ln(const float* W, const float* b, const float* gamma, const float* beta, int32_t N, int32_t K,
+                              void* Wd_bf16, float* bd, void* stream) {
+    MST_REQUIRE(W && b && gamma && beta && Wd_bf16 && bd && N >= 1 && K >= 1 && K <= kPackLnMaxK, "mst_kernel_pack_linear_ln: bad argument");
+    pack_linear_ln_kernel<<<N, 128, 0, static_cast<cudaStream_t>(stream)>>>(W, b, gamma, beta, 0, 1.f, static_cast<bf16*>(Wd_bf16), bd, K);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int mst_kernel_gemm_bf16_res_stats(const void* A, const void* W, int32_t M, int32_t N, int32_t K, const float* bias, void* x,
+                                   float* rowstat_out, float eps, void* stream) {
+    MST_REQUIRE(A && W && bias && x && rowstat_out, "mst_kernel_gemm_bf16_res_stats: null argument");
+    EpiParams ep{};
+    ep.bias = bias; ep.res = x; ep.ldr = N; ep.out = x; ep.ldo = N; ep.rowstat_out = rowstat_out; ep.stat_eps = eps;
+    return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, EPI_BIAS_RES, ep, num_sms_current(),
+                        static_cast<cudaStream_t>(stream));
+}
 int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream) {
     MST_REQUIRE(x && rowstat, "mst_kernel_row_stats_bf16: null argument");
     return launch_row_stats(static_cast<const bf16*>(x), rowstat, rows, E, eps, static_cast<cudaStream_t>(stream));
@@ -781,6 +860,7 @@ int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32
 int mst_debug_gemm_timing(const void* A, const void* W, int32_t M, int32_t N, int32_t K, int32_t mode, const float* bias,
                           const void* res, void* out, long long* dbg_dev, void* stream) {
     MST_REQUIRE(A && W && out && bias && dbg_dev && mode >= 0 && mode <= 2, "mst_debug_gemm_timing: bad argument");
+    MST_REQUIRE(kDbgTiming, "mst_debug_gemm_timing: the phase counters are compiled in only with -DMST_EXPERIMENTS (build.py --experiments)");
     EpiParams ep{};
     ep.bias = bias; ep.res = res; ep.ldr = N; ep.out = out; ep.ldo = N; ep.dbg = dbg_dev;
     return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, num_sms_current(),
@@ -795,21 +875,13 @@ int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, in
 }
 int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
     MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16: null argument");
-    if (N == 257 && mst::attn257_warps() == 16)
+    if (N == 257)
         return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
                                          static_cast<cudaStream_t>(stream));
-    if (N == 257)
-        return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
-                                      static_cast<cudaStream_t>(stream));
     if (attention_tcg_supported(N))
         return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, num_sms_current(),
                                     static_cast<cudaStream_t>(stream));
     return launch_attention_bf16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, static_cast<cudaStream_t>(stream));
-}
-int mst_debug_attention_timing(const void* qkv, void* out, int32_t BD, int32_t heads, long long* dbg_dev, void* stream) {
-    MST_REQUIRE(qkv && out && dbg_dev, "mst_debug_attention_timing: null argument");
-    return launch_attention_tc257(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
-                                  static_cast<cudaStream_t>(stream), dbg_dev);   // the 8-warp kernel carries the phase counters
 }
 int mst_kernel_attention_bf16_warp_mma(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
     MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16_warp_mma: null argument");

@@ -166,11 +166,7 @@ int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, 
     const int NKP = ((N + 31) / 32) * 32;  // a 32-key chunk may touch rows up to the next multiple of 16; keep 32
     const size_t smem = static_cast<size_t>(NKP) * 256;
     MST_REQUIRE(smem <= 227 * 1024, "attention: N=%d tokens do not fit shared memory", N);
-    static bool attr = false;
-    if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(attention_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    MST_SET_DYN_SMEM(attention_bf16_kernel, 227 * 1024);
     attention_bf16_kernel<<<BD * heads, ATT_THREADS, smem, stream>>>(qkv, out, N, heads, NKP);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;

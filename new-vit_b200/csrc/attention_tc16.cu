@@ -1,8 +1,8 @@
-// Encoder attention on tcgen05 for N = 257 tokens, head_dim 64 -- SIXTEEN softmax warps (attention_tc.cu has eight).
+// Encoder attention on tcgen05 for N = 257 tokens, head_dim 64 -- SIXTEEN softmax warps (a TMEM lane quadrant is readable by warps with warp % 4 == q only).
 //     out[s, i, h*64:(h+1)*64] = softmax(q_i . K^T) V      per (slice, head), q pre-scaled
 // (reference layers/attention.py:56-69).  Persistent, one CTA per SM, 768 threads; items = (slice, head).
 //
-// Same data flow as attention_tc.cu (two 128-query tiles per item against the 256 patch keys on the tensor cores, two
+// Data flow: (two 128-query tiles per item against the 256 patch keys on the tensor cores, two
 // 256-column TMEM buffers = two tiles in flight, the CLS token as a key on CUDA cores and as a query on warp-level MMA),
 // but each tile is now worked on by EIGHT warps instead of four: a TMEM lane quadrant (32 query rows) can only be read
 // by warps with warp % 4 == quadrant, so the two warps of a quadrant split the 256 KEY columns, exchange row max and row
@@ -10,7 +10,7 @@
 // each team's serial chain  S -> max -> exp -> P -> (P.V) -> O  (issue slots 48 %, MUFU 26 %, tensor pipe 26 % busy, ncu);
 // halving the per-warp work of every phase shortens that chain and puts four softmax warps on every SM sub-partition.
 //
-//   warp 0        TMA producer (as attention_tc.cu)
+//   warp 0        TMA producer
 //   warp 1        MMA issuer:  S = Q K^T (SS, M128 N256 K16 x 4);  O = P V (TS, N64 K16 x 16), P of key half 0 in columns
 //                 [0,64), of key half 1 in [128,192) (each in place at the start of its own half of S), O in [64,128)
 //   warps 4-19    softmax + epilogue: warp e -> quadrant e%4, team (e/4)%2 = tile parity = TMEM buffer, key half e/8
@@ -527,15 +527,12 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     MST_PROPAGATE(make_tma_3d_bf16(&m128, qkv, 3 * E, N_TOK, BD, 3 * E, static_cast<uint64_t>(N_TOK) * 3 * E, 64, 128, true));
     MST_PROPAGATE(make_tma_3d_bf16(&m16, qkv, 3 * E, N_TOK, BD, 3 * E, static_cast<uint64_t>(N_TOK) * 3 * E, 64, 16, true));
     MST_PROPAGATE(make_tma_3d_bf16(&mO, out, E, N_TOK, BD, E, static_cast<uint64_t>(N_TOK) * E, 32, 32, false));
-    static const int poly = getenv("MST_ATTN_POLY") ? atoi(getenv("MST_ATTN_POLY")) : 7;  // experiments: 0 = all exponentials on MUFU
+    static const int poly = exp_env("MST_ATTN_POLY", 7);  // experiments: 0 = all exponentials on MUFU
     // 7 of 16 pairs on the polynomial: measured optimum (kernel 0.547 ms with 0, 0.495 / 0.469 / 0.510 / 0.499 / 0.569 ms with
     // 6 / 7 / 8 / 10 / 12 of 16, config-2 shape, profiles/attn_timing.py)
     auto kern = poly == 0 ? attention_tc257x16_kernel<0> : attention_tc257x16_kernel<7>;
-    static bool attr = false;
-    if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
-        attr = true;
-    }
+    MST_SET_DYN_SMEM(attention_tc257x16_kernel<0>, DYN_BYTES);
+    MST_SET_DYN_SMEM(attention_tc257x16_kernel<7>, DYN_BYTES);
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
     cudaLaunchConfig_t cfg{};

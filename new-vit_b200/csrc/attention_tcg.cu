@@ -1,6 +1,6 @@
 // Encoder attention on tcgen05 for ANY token count N <= 448 (head_dim 64):  config 4 of BASELINE.json runs ViT-B/14 at
 // 252x252 = 325 tokens, registers add 4, other input sizes give other N; N == 257 has its own specialised kernel
-// (attention_tc.cu).        out[s, i, h*64:(h+1)*64] = softmax(q_i . K^T) V        (reference layers/attention.py:56-69)
+// (attention_tc16.cu).        out[s, i, h*64:(h+1)*64] = softmax(q_i . K^T) V        (reference layers/attention.py:56-69)
 //
 // Persistent, one CTA per SM, 384 threads; items = (slice, head).  K and V of the item (all N tokens, zero-padded by TMA
 // to KPAD = N rounded up to 16) are loaded once into a 2-stage shared-memory ring; the queries run in tiles of 128 rows:
@@ -303,11 +303,7 @@ int launch_attention_tcg(const bf16* qkv, bf16* out, int BD, int N, int heads, i
     TmaDesc mKV, mQ;
     MST_PROPAGATE(make_tma_3d_bf16(&mKV, qkv, 3 * E, N, BD, 3 * E, static_cast<uint64_t>(N) * 3 * E, 64, kv_box, true));
     MST_PROPAGATE(make_tma_3d_bf16(&mQ, qkv, 3 * E, N, BD, 3 * E, static_cast<uint64_t>(N) * 3 * E, 64, 128, true));
-    static bool attr = false;
-    if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(attention_tcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-        attr = true;
-    }
+    MST_SET_DYN_SMEM(attention_tcg_kernel, 232448);
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
     attention_tcg_kernel<<<grid, THREADS, smem, stream>>>(mKV, mQ, out, items, heads, N, KPAD, kv_box, kv_boxes);

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 namespace mst {
@@ -31,6 +32,31 @@ void set_error(const char* fmt, ...);
     do {                           \
         int _s = (expr);           \
         if (_s != 0) return _s;    \
+    } while (0)
+
+// ---- experiment switches and profiling counters: compiled in only with -DMST_EXPERIMENTS (new-vit_b200/build.py --experiments);
+// the product library reads no environment variable and carries no clock64() on its hot paths.
+#ifdef MST_EXPERIMENTS
+inline int exp_env(const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; }
+constexpr bool kDbgTiming = true;
+#else
+inline int exp_env(const char*, int dflt) { return dflt; }
+constexpr bool kDbgTiming = false;
+#endif
+#define MST_DBG_CLOCK() (mst::kDbgTiming ? clock64() : 0LL)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: set it once per (kernel, device), so a
+// second GPU used by the same process (a model on cuda:1 after one on cuda:0, one thread per GPU) gets it too.
+constexpr int kMaxDevices = 64;
+#define MST_SET_DYN_SMEM(kern, bytes)                                                                                   \
+    do {                                                                                                                \
+        static bool _done[mst::kMaxDevices] = {};                                                                       \
+        int _dev = 0;                                                                                                   \
+        MST_CHECK_CUDA(cudaGetDevice(&_dev));                                                                           \
+        if (_dev < 0 || _dev >= mst::kMaxDevices || !_done[_dev]) {                                                     \
+            MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));             \
+            if (_dev >= 0 && _dev < mst::kMaxDevices) _done[_dev] = true;                                               \
+        }                                                                                                               \
     } while (0)
 
 // ---- GEMM epilogues --------------------------------------------------------------------------------
@@ -146,9 +172,6 @@ bool gemm_wt_enabled();   // MST_GEMM_WT != 0
 bool pdl_enabled();       // MST_PDL != 0: GEMM / attention kernels are launched as programmatic dependents (ptx.cuh)
 int gemm_bf16_wt(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
                  cudaStream_t stream);
-// tcgen05 attention for N == 257 tokens (ViT-S/B @224); other N use the warp-MMA kernel
-int launch_attention_tc257(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
-                           long long* dbg = nullptr);
 
 // bf16 tensor-core GEMM (tcgen05 + TMA + TMEM). A: [M,K] bf16 row-major (lda=K), W: [N,K] bf16 row-major.
 int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
@@ -158,15 +181,16 @@ int gemm_f32_simt(const float* A, int64_t lda, const float* W, int M, int N, int
                   cudaStream_t stream);
 
 template <typename T>
-int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, const float* regs, int R, int BD, int H, int W,
-                  int KP, int E, cudaStream_t stream);
+int launch_im2col(const void* src, int src_dtype, T* A0, T* x, const float* cls_pos0, const float* regs, int R, int BD, int H, int W,
+                  int KP, int E, int tta_BD, int D, cudaStream_t stream);
 template <typename TIn, typename TOut>
 int launch_layernorm(const TIn* x, int64_t ldx, TOut* y, int64_t ldy, const float* gamma, const float* beta, int rows,
                      int E, float eps, cudaStream_t stream);
 // rowstat[row] = rstd of x[row, 0..E) (fp32 statistics, two-pass), the per-row part of a folded LayerNorm
 int launch_row_stats(const bf16* x, float* rowstat, int rows, int E, float eps, cudaStream_t stream);
 int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, cudaStream_t stream);
-// the same with sixteen softmax warps (two per TMEM lane quadrant and tile, splitting the key columns): attention_tc16.cu
+// tcgen05 attention for N == 257 tokens (ViT @224), sixteen softmax warps (two per TMEM lane quadrant and tile, splitting the key
+// columns): attention_tc16.cu
 int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
                               long long* dbg = nullptr);
 // tcgen05 attention for any token count 17 <= N <= 360 (attention_tcg.cu); N == 257 keeps its specialised kernels
@@ -185,15 +209,18 @@ struct SliceWeights {  // fp32, linear weights pre-transposed to [in][out]; bott
 // enc_cls [B*D, Eenc]; E = slice embedding (Eenc, or Eenc/4 behind the bottleneck); logits/feat nullable
 int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,
                         float* logits, float* feat, float* slice_cls, int B, int D, int Eenc, int E, int heads, int out_ch,
-                        int mode, cudaStream_t stream);
-int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int skip, int gh,
-                    int gw, int H, int W, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full,
-                    cudaStream_t stream);
+                        int mode, int mask_period, cudaStream_t stream);
+// tta: plane_cls / slice_cls hold 8 flipped variants per volume (variant-major); coarse / slice_attn are the un-flipped averages
+int launch_saliency_combine(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int skip, int gh,
+                            int gw, int tta, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, cudaStream_t stream);
+int launch_saliency_upsample(const float* coarse, float* full, int B, int D, int gh, int gw, int H, int W, cudaStream_t stream);
 
 
 // ---- kernels either side of the main path (extras.cu) ---------------------------------------------
 int launch_pos_bicubic(const float* pos, const float* cbias, float* posb, int M, int gh, int gw, int E, float scale_y,
                        float scale_x, cudaStream_t stream);
+// anti-aliased variant with an exact output size (hub "_reg" encoders: interpolate_antialias=True, interpolate_offset=0.0)
+int launch_pos_bicubic_aa(const float* pos, const float* cbias, float* posb, int M, int gh, int gw, int E, cudaStream_t stream);
 template <typename T>
 int launch_attention_probs(const T* qkv, float* probs, int BD, int N, int heads, cudaStream_t stream);
 int launch_rollout(const float* maps, int depth, int nmat, int N, float* out, float* scratch, cudaStream_t stream);
@@ -203,6 +230,7 @@ int launch_quantile(const float* data, int64_t n, int items, const double* q_dev
 
 // ---- input pipeline in front of the forward (prep.cu) -----------------------
 size_t prepare_volume_workspace_bytes(int items, int W0, int H0, int D0);
+int launch_prepare_volume_count(int W0, int H0, int D0, int W, int H, int D);
 int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, int W, int H, int D, int flip_h, float q_lo,
                           float q_hi, float* out, double* stats, void* workspace, int num_sms, cudaStream_t stream);
 

@@ -59,6 +59,65 @@ int launch_pos_bicubic(const float* pos, const float* cbias, float* posb, int M,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// The same table for the torch.hub "_reg" encoders (dinov2_vit*14_reg, dino.py:60-61), which are built with
+// interpolate_antialias=True, interpolate_offset=0.0 (vision_transformer.py:66-67,198-210):
+// F.interpolate(size=(gh, gw), mode="bicubic", antialias=True).  ATen's separable anti-aliased resampling
+// (UpSampleKernel.cpp, _compute_indices_min_size_weights_aa): per output index i, scale = in/out,
+// support = 2*max(scale,1), center = scale*(i+0.5), taps xmin = max(int(center-support+0.5), 0) ..
+// min(int(center+support+0.5), in), weight = keys_{a=-0.5}((j+xmin-center+0.5)/max(scale,1)), normalised to sum 1;
+// width pass first, then height, fp32 throughout.
+// ---------------------------------------------------------------------------------------------------
+constexpr int AA_MAX_TAPS = 64;
+__device__ __forceinline__ float aa_keys(float x) {
+    const float a = -0.5f;
+    x = fabsf(x);
+    if (x < 1.0f) return ((a + 2.0f) * x - (a + 3.0f)) * x * x + 1.0f;
+    if (x < 2.0f) return (((x - 5.0f) * x + 8.0f) * x - 4.0f) * a;
+    return 0.0f;
+}
+__device__ __forceinline__ void aa_taps(int i, int in_size, int out_size, int& xmin, int& xsize, float* w) {
+    const float scale = static_cast<float>(in_size) / static_cast<float>(out_size);
+    const float support = scale >= 1.0f ? 2.0f * scale : 2.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const float center = scale * (i + 0.5f);
+    xmin = max(static_cast<int>(center - support + 0.5f), 0);
+    xsize = min(static_cast<int>(center + support + 0.5f), in_size) - xmin;
+    xsize = min(max(xsize, 0), AA_MAX_TAPS);
+    float total = 0.f;
+    for (int j = 0; j < xsize; ++j) { w[j] = aa_keys((j + xmin - center + 0.5f) * invscale); total += w[j]; }
+    if (total != 0.f)
+        for (int j = 0; j < xsize; ++j) w[j] /= total;
+}
+__global__ void __launch_bounds__(128) pos_bicubic_aa_kernel(const float* __restrict__ pos, const float* __restrict__ cbias,
+                                                              float* __restrict__ posb, int M, int gh, int gw, int E) {
+    __shared__ float wy[AA_MAX_TAPS], wx[AA_MAX_TAPS];
+    __shared__ int lim[4];
+    const int p = blockIdx.x, oy = p / gw, ox = p % gw;
+    if (threadIdx.x == 0) aa_taps(oy, M, gh, lim[0], lim[1], wy);
+    if (threadIdx.x == 32) aa_taps(ox, M, gw, lim[2], lim[3], wx);
+    __syncthreads();
+    const int y0 = lim[0], ny = lim[1], x0 = lim[2], nx = lim[3];
+    const float* grid = pos + E;  // skip the class row
+    for (int n = threadIdx.x; n < E; n += blockDim.x) {
+        float acc = 0.f;
+        for (int i = 0; i < ny; ++i) {
+            float row = 0.f;   // the width pass of ATen's separable scheme for source row y0 + i
+            for (int j = 0; j < nx; ++j) row += wx[j] * grid[(static_cast<int64_t>(y0 + i) * M + x0 + j) * E + n];
+            acc += wy[i] * row;
+        }
+        posb[static_cast<int64_t>(p) * E + n] = acc + (cbias ? cbias[n] : 0.f);
+    }
+}
+int launch_pos_bicubic_aa(const float* pos, const float* cbias, float* posb, int M, int gh, int gw, int E, cudaStream_t stream) {
+    const float smax = fmaxf(static_cast<float>(M) / gh, static_cast<float>(M) / gw);
+    MST_REQUIRE(2.0f * fmaxf(smax, 1.0f) * 2.0f + 2.0f <= AA_MAX_TAPS, "anti-aliased position resampling %d -> %dx%d needs more than %d taps",
+                M, gh, gw, AA_MAX_TAPS);
+    pos_bicubic_aa_kernel<<<gh * gw, 128, 0, stream>>>(pos, cbias, posb, M, gh, gw, E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Full attention probabilities of one encoder block: probs[s, h, i, j] = softmax_j(q_i . k_j), q pre-scaled.
 // This is what the reference's hook stores for every block when save_attn=True (dino.py:229-241); only
 // get_attention_cls (dino.py:204-212) reads more than row 0 of the last one, so it is produced on request.
@@ -131,11 +190,7 @@ template <typename T>
 int launch_attention_probs(const T* qkv, float* probs, int BD, int N, int heads, cudaStream_t stream) {
     MST_REQUIRE(N <= PROBS_MAXJ * 32, "full attention maps support at most %d tokens per slice (got %d)", PROBS_MAXJ * 32, N);
     const size_t smem = (static_cast<size_t>(N) * 65 + PROBS_WARPS * 64) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(attention_probs_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    MST_SET_DYN_SMEM(attention_probs_kernel<T>, 227 * 1024);
     attention_probs_kernel<T><<<BD * heads, PROBS_WARPS * 32, smem, stream>>>(qkv, probs, N, heads);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;

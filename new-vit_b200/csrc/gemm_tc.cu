@@ -398,17 +398,17 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         long long gd[2] = {0, 0};
-        const long long gstart = clock64();
+        const long long gstart = MST_DBG_CLOCK();
         for (int it = 0; it < t_count; ++it) {
-            const long long g0 = clock64();
+            const long long g0 = MST_DBG_CLOCK();
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            gd[0] += clock64() - g0;
+            gd[0] += MST_DBG_CLOCK() - g0;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
             for (int kc = 0; kc < kchunks; ++kc) {
-                const long long g1 = clock64();
+                const long long g1 = MST_DBG_CLOCK();
                 mbar_wait(&full_bar[stage], phase);
-                gd[1] += clock64() - g1;
+                gd[1] += MST_DBG_CLOCK() - g1;
                 tc_fence_after_sync();
                 const uint32_t a_lo = a_lo0 + stage * (A_STAGE_BYTES >> 4);
                 const uint32_t b_lo = b_lo0 + (kResident ? kc : stage) * (L::B_TILE_BYTES >> 4);
@@ -436,8 +436,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             }
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
         }
-        if (ep.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
-            ep.dbg[0] = gd[0]; ep.dbg[1] = gd[1]; ep.dbg[2] = clock64() - gstart; ep.dbg[3] = t_count;
+        if (kDbgTiming && ep.dbg != nullptr && blockIdx.x == 0 && lane == 0) {
+            ep.dbg[0] = gd[0]; ep.dbg[1] = gd[1]; ep.dbg[2] = MST_DBG_CLOCK() - gstart; ep.dbg[3] = t_count;
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -463,10 +463,10 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             if (ln_fold && row_ok) rstat = __ldg(ep.rowstat + row);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
 
-            const bool dbg_w = ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
+            const bool dbg_w = kDbgTiming && ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
             auto process = [&](const uint32_t (&r)[32], int c) {
                 uint32_t o[16];
-                const long long p0 = dbg_w ? clock64() : 0;
+                const long long p0 = MST_DBG_CLOCK();
                 const int n0 = nbase + c * 32;
                 const float* b = bias0 + c * 32;
                 switch (mode) {
@@ -549,23 +549,23 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     // the tile written two stores ago must no longer be read by its TMA store
                     uint8_t* tile = stg + stg_sel * STG_TILE;
                     if (NSTG == 2) stg_sel ^= 1;
-                    const long long p1 = dbg_w ? clock64() : 0;
+                    const long long p1 = MST_DBG_CLOCK();
                     if (lane == 0) tma_store_wait_read<(NSTG == 2 ? 1 : 0)>();
                     __syncwarp();
-                    const long long p2 = dbg_w ? clock64() : 0;
+                    const long long p2 = MST_DBG_CLOCK();
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         *reinterpret_cast<uint4*>(tile + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) =
                             make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     fence_proxy_async_smem();
                     __syncwarp();
-                    const long long p3 = dbg_w ? clock64() : 0;
+                    const long long p3 = MST_DBG_CLOCK();
                     if (lane == 0) {
                         if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, tile, n0, row0);
                         else tma_store_2d(&tmC, tile, n0, row0);
                         tma_store_commit();
                     }
-                    if (dbg_w) { const long long p4 = clock64(); ep.dbg[8] += p1 - p0; ep.dbg[9] += p2 - p1; ep.dbg[10] += p3 - p2; ep.dbg[11] += p4 - p3; }
+                    if (dbg_w) { const long long p4 = MST_DBG_CLOCK(); ep.dbg[8] += p1 - p0; ep.dbg[9] += p2 - p1; ep.dbg[10] += p3 - p2; ep.dbg[11] += p4 - p3; }
                 }
             };
             auto release_tmem = [&]() {  // every tcgen05.ld of this tile has completed
@@ -577,9 +577,9 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                 }
             };
 
-            const long long e0 = clock64();
+            const long long e0 = MST_DBG_CLOCK();
             mbar_wait(&tfull_bar[acc], acc_phase);
-            const long long e1 = clock64();
+            const long long e1 = MST_DBG_CLOCK();
             tc_fence_after_sync();
             if (mode_flags & 0x100) {  // experiment: mainloop ceiling (no epilogue work at all)
                 release_tmem();
@@ -592,7 +592,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             if constexpr (CHUNKS_PER_WARP == 3) tmem_ld_32x32b_x32(taddr + 64, rc);
             tmem_ld_wait();
             release_tmem();  // the accumulator stage goes back to the MMA warp before any epilogue math
-            const long long e2 = clock64();
+            const long long e2 = MST_DBG_CLOCK();
             process(ra, 0);
             process(rb, 1);
             if constexpr (CHUNKS_PER_WARP == 3) process(rc, 2);
@@ -616,8 +616,8 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     st1 = 0.f; st2 = 0.f;
                 }
             }
-            if (ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0) {
-                const long long e3 = clock64();
+            if (kDbgTiming && ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0) {
+                const long long e3 = MST_DBG_CLOCK();
                 ep.dbg[4] += e1 - e0; ep.dbg[5] += e2 - e1; ep.dbg[6] += e3 - e2;
             }
             acc ^= 1; if (acc == 0) acc_phase ^= 1;
@@ -644,18 +644,20 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     constexpr bool MCAST = PAIR != 0;  // launched as clusters
     constexpr int CLUSTER = PAIR == 4 ? 4 : 2;
     auto kern = gemm_tc_kernel<BN, KCH, STAGES, NSTG, EW, PAIR>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DYN_BYTES));
-        attr_set = true;
-    }
+    MST_SET_DYN_SMEM(kern, L::DYN_BYTES);
     constexpr int CPU_ = PAIR == 2 ? 2 : 1;               // CTAs per scheduling unit (a cta_group::2 pair shares its tiles)
     const int n_tiles = N / BN;
     const int m_tiles = (M + BM * CPU_ - 1) / (BM * CPU_);
     int units = num_sms / CPU_;
     if (CLUSTER == 4 && MCAST) {  // clusters of 4 do not tile every GPC: size the grid to what is co-resident
-        static int max_clusters = -1;
-        if (max_clusters < 0) {
+        static int max_clusters_dev[kMaxDevices];
+        static bool max_clusters_set[kMaxDevices] = {};
+        int dev = 0;
+        MST_CHECK_CUDA(cudaGetDevice(&dev));
+        MST_REQUIRE(dev >= 0 && dev < kMaxDevices, "device ordinal %d out of range", dev);
+        int& max_clusters = max_clusters_dev[dev];
+        if (!max_clusters_set[dev]) {
+            max_clusters_set[dev] = true;
             cudaLaunchConfig_t q{};
             q.gridDim = dim3(num_sms / 4 * 4); q.blockDim = dim3(gemm_threads(EW)); q.dynamicSmemBytes = L::DYN_BYTES;
             cudaLaunchAttribute qa[1];
@@ -699,12 +701,12 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
 }
 
 bool pdl_enabled() {
-    static const int pdl = getenv("MST_PDL") ? atoi(getenv("MST_PDL")) : 0;
+    static const int pdl = exp_env("MST_PDL", 0);
     return pdl != 0;
 }
 
 bool gemm_wt_enabled() {
-    static const int use_wt = getenv("MST_GEMM_WT") ? atoi(getenv("MST_GEMM_WT")) : 1;  // 0: experiments / A-B comparisons
+    static const int use_wt = exp_env("MST_GEMM_WT", 1);  // 0: experiments / A-B comparisons
     return use_wt != 0;
 }
 
@@ -728,7 +730,7 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     }
     const int use_wt = gemm_wt_enabled();
     if (use_wt && gemm_wt_supported(M, N, K, mode, ep)) {
-        static const int wt_skip = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;  // experiments only
+        static const int wt_skip = exp_env("MST_GEMM_SKIP_EPI", 0);  // experiments only
         EpiParams e2 = ep;
         e2.P = wt_skip;
         return gemm_bf16_wt(A, W, M, N, K, mode, e2, num_sms, stream);  // weights in TMEM, 16 epilogue warps (gemm_wt.cu)
@@ -738,18 +740,18 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_PROPAGATE(make_tma_2d_bf16(&tmA, A, K, M, K, BK, BM));
     // output maps (unused by EPI_PATCH, whose rows are re-mapped)
     const uint64_t out_rows = mode == EPI_PATCH ? static_cast<uint64_t>(M / ep.P) * (ep.P + 1 + ep.R) : static_cast<uint64_t>(M);
-    static const int force_bn = getenv("MST_GEMM_BN") ? atoi(getenv("MST_GEMM_BN")) : 0;  // experiments only
-    static const int skip_epi = getenv("MST_GEMM_SKIP_EPI") ? atoi(getenv("MST_GEMM_SKIP_EPI")) : 0;
+    static const int force_bn = exp_env("MST_GEMM_BN", 0);  // experiments only
+    static const int skip_epi = exp_env("MST_GEMM_SKIP_EPI", 0);
     if (skip_epi) mode |= (skip_epi & 3) << 8;  // 1: no epilogue at all, 2: epilogue without the final store
-    static const int no_mcast = getenv("MST_GEMM_NO_MCAST") ? atoi(getenv("MST_GEMM_NO_MCAST")) : 0;  // experiments only
-    static const int use_two = getenv("MST_GEMM_TWO") ? atoi(getenv("MST_GEMM_TWO")) : 1;             // experiments only
+    static const int no_mcast = exp_env("MST_GEMM_NO_MCAST", 0);  // experiments only
+    static const int use_two = exp_env("MST_GEMM_TWO", 1);             // experiments only
     if (N % 192 == 0 && force_bn != 128) {
         MST_PROPAGATE(make_tma_2d_bf16(&tmB, W, K, N, K, BK, 192));
         if (K == 256) {  // patch embedding: weight-resident, chunk staging (its epilogue stores rows directly)
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
             // 12 epilogue warps (two 32-column chunks each instead of three): the epilogue, not the 16 MMAs, paces this GEMM
             // (0.47 -> 0.38 ms per launch in-step); MST_PATCH_EW12=0 keeps the 8-warp configuration for A-B runs
-            static const int ew12 = getenv("MST_PATCH_EW12") ? atoi(getenv("MST_PATCH_EW12")) : 1;
+            static const int ew12 = exp_env("MST_PATCH_EW12", 1);
             if (ew12) return launch_cfg<192, 4, 4, 2, 12>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
             return launch_cfg<192, 4, 4, 2, 8>(tmA, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
         }
@@ -772,7 +774,7 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
             MST_PROPAGATE(make_tma_2d_bf16(&tmC, ep.out, N, out_rows, ep.ldo, 32, 32, false, true));
             // GELU epilogue (fc1) is the longest: two staging tiles per warp (a TMA store stays in flight while the next
             // chunk is computed) paid for with a 3-deep A ring; the L2 prefetch keeps the shorter ring fed
-            static const int mc4 = getenv("MST_GEMM_MC4") ? atoi(getenv("MST_GEMM_MC4")) : 0;  // experiments only
+            static const int mc4 = exp_env("MST_GEMM_MC4", 0);  // experiments only
             if (mc4 && (N / 192) % 4 == 0) {  // four adjacent n-blocks share every A stage: each CTA fetches 32 rows
                 TmaDesc tmAq;
                 MST_PROPAGATE(make_tma_2d_bf16(&tmAq, A, K, M, K, BK, BM / 4));
@@ -782,7 +784,7 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
             }
             if ((mode & 0xff) == EPI_BIAS_GELU || (mode & 0xff) == EPI_LN_BIAS_GELU)
                 return launch_cfg<192, 6, 3, 1, 12, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
-            static const int alt = getenv("MST_GEMM_ALT") ? atoi(getenv("MST_GEMM_ALT")) : 0;  // experiments only
+            static const int alt = exp_env("MST_GEMM_ALT", 0);  // experiments only
             if (alt == 1)   // two staging tiles per epilogue warp (no wait for the previous chunk's TMA store), 3-stage A ring
                 return launch_cfg<192, 6, 3, 2, 8, 1>(tmAh, tmB, tmC, M, N, K, mode, ep, num_sms, stream);
             if (alt == 2)   // 12 epilogue warps (2 chunks each), 3-stage A ring

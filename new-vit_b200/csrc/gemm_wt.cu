@@ -176,21 +176,21 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
         constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B | version 1 | SWIZZLE_128B
         const uint32_t b_lo0 = (smem_u32(smem + RING_OFF) & 0x3FFFF) >> 4;
         int stage = 0; uint32_t phase = 0;
-        const bool dbg = ep.dbg != nullptr && blockIdx.x == 0;   // phase counters only in profiles/gemm_timing.py
+        const bool dbg = kDbgTiming && ep.dbg != nullptr && blockIdx.x == 0;   // phase counters only in profiles/gemm_timing.py
         long long gd[2] = {0, 0};
-        const long long gstart = dbg ? clock64() : 0;
+        const long long gstart = MST_DBG_CLOCK();
         for (int it = 0; it < t_count; ++it) {
             const int acc = it & 1;
-            const long long g0 = dbg ? clock64() : 0;
+            const long long g0 = MST_DBG_CLOCK();
             mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
-            if (dbg) gd[0] += clock64() - g0;
+            if (dbg) gd[0] += MST_DBG_CLOCK() - g0;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(W_COLS + acc * NT);
 #pragma unroll
             for (int s2 = 0; s2 < SPT; ++s2) {   // unrolled: the weight (A) addresses in TMEM are compile-time offsets
-                const long long g1 = dbg ? clock64() : 0;
+                const long long g1 = MST_DBG_CLOCK();
                 if (!(ep.P & 4)) mbar_wait(&full_bar[stage], phase);
-                if (dbg) gd[1] += clock64() - g1;
+                if (dbg) gd[1] += MST_DBG_CLOCK() - g1;
                 tc_fence_after_sync();
                 const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
                 if (elect_one_sync()) {
@@ -207,7 +207,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
             }
         }
         if (dbg && lane == 0) {
-            ep.dbg[0] = gd[0]; ep.dbg[1] = gd[1]; ep.dbg[2] = clock64() - gstart; ep.dbg[3] = t_count;
+            ep.dbg[0] = gd[0]; ep.dbg[1] = gd[1]; ep.dbg[2] = MST_DBG_CLOCK() - gstart; ep.dbg[3] = t_count;
         }
     } else if (warp >= 4) {
         // ===================== epilogue: two teams on alternate tiles =====================
@@ -221,7 +221,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(W_COLS + team * NT + half * 64);
         const bool store_ok = feat0 < N;
         const bool skip_epi = (ep.P & 1) != 0;   // experiment: mainloop ceiling (accumulators are read and dropped)
-        const bool dbg_all = ep.dbg != nullptr && blockIdx.x < 2 && lane == 0;
+        const bool dbg_all = kDbgTiming && ep.dbg != nullptr && blockIdx.x < 2 && lane == 0;
         long long busy = 0, waitt = 0;
         float* rsb = reinterpret_cast<float*>(smem + RS_OFF) + e * 64;   // this warp's 64 rstd values of the current tile
         bf16* const outp = static_cast<bf16*>(ep.out);
@@ -246,9 +246,9 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
                     if (tok_tile + 32 + lane < M) rs1 = __ldg(ep.rowstat + tok_tile + 32 + lane);
                 }
             }
-            const long long w0 = dbg_all ? clock64() : 0;
+            const long long w0 = MST_DBG_CLOCK();
             mbar_wait(&tfull_bar[team], (it >> 1) & 1);
-            const long long w1 = dbg_all ? clock64() : 0;
+            const long long w1 = MST_DBG_CLOCK();
             waitt += w1 - w0;
             tc_fence_after_sync();
             if (LNF) { rsb[lane] = rs0; rsb[32 + lane] = rs1; }
@@ -345,7 +345,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
             process16(r0, 3);
             write_out(1);
             __syncwarp();   // both staging tiles have been read before the next tile overwrites them
-            if (dbg_all) busy += clock64() - w1;
+            if (dbg_all) busy += MST_DBG_CLOCK() - w1;
         }
         if (dbg_all) { ep.dbg[16 + blockIdx.x * 32 + e] = busy; ep.dbg[32 + blockIdx.x * 32 + e] = waitt; }
     }
@@ -363,11 +363,7 @@ static int launch_wt(const TmaDesc& tmX, const TmaDesc& tmC, const bf16* W, int 
                      cudaStream_t stream) {
     using namespace wt;
     auto kern = gemm_wt_kernel<MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES));
-        attr_set = true;
-    }
+    MST_SET_DYN_SMEM(kern, DYN_BYTES);
     const int n_pairs = (N + 255) / 256;
     const int m_tiles = (M + NT - 1) / NT;
     int groups = (num_sms / 2) / n_pairs;
@@ -390,7 +386,7 @@ bool gemm_wt_supported(int M, int N, int K, int mode, const EpiParams& ep) {
     (void)M;
     // N % 256 == 128 (qkv, 1152) also runs correctly (the last pair's second CTA is padding) but wastes a tenth of the MMAs
     // and 8 SMs: measured 0.445 ms against 0.433 ms for the weight-in-shared-memory kernel, so only whole pairs come here.
-    static const int allow_pad = getenv("MST_GEMM_WT_PAD") ? atoi(getenv("MST_GEMM_WT_PAD")) : 0;
+    static const int allow_pad = exp_env("MST_GEMM_WT_PAD", 0);
     return K == wt::K && N >= 1024 && (N % 256 == 0 || (allow_pad && N % 128 == 0)) && ep.ldo % 8 == 0 &&
            (mode == EPI_BIAS || mode == EPI_BIAS_GELU || mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU);
 }

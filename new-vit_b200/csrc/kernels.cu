@@ -3,6 +3,7 @@
 // combiner + upsampler.  All arithmetic that the reference does in fp32 statistics (LN mean/var,
 // softmax) is fp32 here too.
 #include <math_constants.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -83,27 +84,65 @@ template <> struct Vec4<bf16> {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// im2col: src [BD,H,W] fp32 -> A0 [BD*P, KP] (column ky*14+kx, zero padded to KP), plus the CLS token
+// im2col: src [BD,H,W] (fp32, bf16 or fp16) -> A0 [BD*P, KP] (column ky*14+kx, zero padded to KP), plus the CLS token
 // row of every slice: x[s*NT] = cls_token + pos_embed[0], followed by the R register tokens (no position
 // embedding, vision_transformer.py:222-230); NT = 1 + R + P.  Replaces the rearrange + 3x repeat +
 // conv unfold of reference dino.py:125-127 / patch_embed.py:75-77 (the RGB copies are never
 // materialised: the conv weight is channel-summed at pack time).
+// Test-time augmentation (scripts/main_predict.py:147-149): with tta_BD = B*D > 0 the grid covers 8*B*D VIRTUAL slices,
+// variant v = s / (B*D) of torch.flip(source, dims) for dims in [(), (2,), (3,), (4,), (2,3), (2,4), (3,4), (2,3,4)];
+// the flips are index arithmetic on the load, the flipped volumes are never materialised.
 // ---------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ src, T* __restrict__ A0, T* __restrict__ x,
+template <typename TS> __device__ __forceinline__ float src_to_f(TS v);
+template <> __device__ __forceinline__ float src_to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float src_to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float src_to_f<__half>(__half v) { return __half2float(v); }
+
+template <typename TS, typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const TS* __restrict__ src, T* __restrict__ A0, T* __restrict__ x,
                                                       const float* __restrict__ cls_pos0, const float* __restrict__ regs, int R,
-                                                      int H, int W, int KP, int E) {
+                                                      int H, int W, int KP, int E, int tta_BD, int D) {
     extern __shared__ float tile[];  // [14][W]
     griddep_launch_dependents();
     const int gh = H / 14, gw = W / 14, P = gh * gw;
     const int s = blockIdx.x / gh, py = blockIdx.x % gh;
-    const float* base = src + (static_cast<int64_t>(s) * H + py * 14) * W;
-    if ((W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // 16-byte loads (the 14-row band starts on a 16-byte boundary when W % 4 == 0)
-        const float4* b4 = reinterpret_cast<const float4*>(base);
-        float4* t4 = reinterpret_cast<float4*>(tile);
-        for (int i = threadIdx.x; i < 14 * W / 4; i += blockDim.x) t4[i] = __ldg(b4 + i);
+    int ss = s;
+    bool flip_h = false, flip_w = false;
+    if (tta_BD > 0) {
+        const int v = s / tta_BD, rem = s - v * tta_BD, b = rem / D, d = rem - b * D;
+        const bool flip_d = (0xB2 >> v) & 1;   // variants 1, 4, 5, 7 flip dim 2 (depth)
+        flip_h = (0xD4 >> v) & 1;              // variants 2, 4, 6, 7 flip dim 3 (height)
+        flip_w = (0xE8 >> v) & 1;              // variants 3, 5, 6, 7 flip dim 4 (width)
+        ss = b * D + (flip_d ? D - 1 - d : d);
+    }
+    if (flip_h || flip_w) {
+        const TS* sl = src + static_cast<int64_t>(ss) * H * W;
+        for (int i = threadIdx.x; i < 14 * W; i += blockDim.x) {
+            const int r = i / W, xc = i - r * W;
+            const int yy = flip_h ? H - 1 - (py * 14 + r) : py * 14 + r;
+            const int xx = flip_w ? W - 1 - xc : xc;
+            tile[i] = src_to_f<TS>(sl[static_cast<int64_t>(yy) * W + xx]);
+        }
     } else {
-        for (int i = threadIdx.x; i < 14 * W; i += blockDim.x) tile[i] = __ldg(base + i);
+        const TS* base = src + (static_cast<int64_t>(ss) * H + py * 14) * W;
+        if (sizeof(TS) == 4 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            // 16-byte loads (the 14-row band starts on a 16-byte boundary when W % 4 == 0)
+            const float4* b4 = reinterpret_cast<const float4*>(base);
+            float4* t4 = reinterpret_cast<float4*>(tile);
+            for (int i = threadIdx.x; i < 14 * W / 4; i += blockDim.x) t4[i] = __ldg(b4 + i);
+        } else if (sizeof(TS) == 2 && (W & 7) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const uint4* b8 = reinterpret_cast<const uint4*>(base);   // 8 two-byte voxels per load
+            for (int i = threadIdx.x; i < 14 * W / 8; i += blockDim.x) {
+                const uint4 u = __ldg(b8 + i);
+                const TS* e8 = reinterpret_cast<const TS*>(&u);
+                float4 lo = make_float4(src_to_f<TS>(e8[0]), src_to_f<TS>(e8[1]), src_to_f<TS>(e8[2]), src_to_f<TS>(e8[3]));
+                float4 hi = make_float4(src_to_f<TS>(e8[4]), src_to_f<TS>(e8[5]), src_to_f<TS>(e8[6]), src_to_f<TS>(e8[7]));
+                reinterpret_cast<float4*>(tile)[2 * i] = lo;
+                reinterpret_cast<float4*>(tile)[2 * i + 1] = hi;
+            }
+        } else {
+            for (int i = threadIdx.x; i < 14 * W; i += blockDim.x) tile[i] = src_to_f<TS>(base[i]);
+        }
     }
     __syncthreads();
     // thread -> 8 consecutive columns (taps) of a patch row, written as ONE 16-byte (bf16) / two 16-byte (fp32) stores;
@@ -139,16 +178,26 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ s
     }
 }
 
+// src_dtype: 0 fp32, 1 bf16, 2 fp16 (MST_SRC_*).  BD counts the slices the grid covers (8x the real count with TTA).
 template <typename T>
-int launch_im2col(const float* src, T* A0, T* x, const float* cls_pos0, const float* regs, int R, int BD, int H, int W,
-                  int KP, int E, cudaStream_t stream) {
+int launch_im2col(const void* src, int src_dtype, T* A0, T* x, const float* cls_pos0, const float* regs, int R, int BD, int H, int W,
+                  int KP, int E, int tta_BD, int D, cudaStream_t stream) {
     const int gh = H / 14;
-    im2col_kernel<T><<<BD * gh, 256, 14 * W * sizeof(float), stream>>>(src, A0, x, cls_pos0, regs, R, H, W, KP, E);
+    const size_t smem = 14 * W * sizeof(float);
+    const dim3 grid(BD * gh);
+    if (src_dtype == 0)
+        im2col_kernel<float, T><<<grid, 256, smem, stream>>>(static_cast<const float*>(src), A0, x, cls_pos0, regs, R, H, W, KP, E, tta_BD, D);
+    else if (src_dtype == 1)
+        im2col_kernel<bf16, T><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(src), A0, x, cls_pos0, regs, R, H, W, KP, E, tta_BD, D);
+    else if (src_dtype == 2)
+        im2col_kernel<__half, T><<<grid, 256, smem, stream>>>(static_cast<const __half*>(src), A0, x, cls_pos0, regs, R, H, W, KP, E, tta_BD, D);
+    else
+        MST_REQUIRE(false, "im2col: unknown source dtype %d", src_dtype);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
-template int launch_im2col<float>(const float*, float*, float*, const float*, const float*, int, int, int, int, int, int, cudaStream_t);
-template int launch_im2col<bf16>(const float*, bf16*, bf16*, const float*, const float*, int, int, int, int, int, int, cudaStream_t);
+template int launch_im2col<float>(const void*, int, float*, float*, const float*, const float*, int, int, int, int, int, int, int, int, cudaStream_t);
+template int launch_im2col<bf16>(const void*, int, bf16*, bf16*, const float*, const float*, int, int, int, int, int, int, int, int, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------------
 // LayerNorm over rows of E (E % 128 == 0): one warp per row, two-pass in registers, fp32 statistics.
@@ -433,11 +482,7 @@ int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads,
     MST_REQUIRE(N <= ATT32_MAXJ * 32, "fp32 attention supports at most %d tokens per slice (got %d)", ATT32_MAXJ * 32, N);
     const size_t smem = (static_cast<size_t>(N) * 65 + N * 64 + ATT32_WARPS * 64 + ATT32_WARPS * N) * sizeof(float);
     MST_REQUIRE(smem <= 227 * 1024, "fp32 attention: %zu bytes of shared memory needed", smem);
-    static bool attr = false;
-    if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    MST_SET_DYN_SMEM(attention_f32_kernel, 227 * 1024);
     attention_f32_kernel<<<BD * heads, ATT32_WARPS * 32, smem, stream>>>(qkv, out, N, heads);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -558,7 +603,7 @@ __device__ __forceinline__ void block_matvec(const float* in, const float* __res
 __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restrict__ enc_cls, const uint8_t* __restrict__ pad_mask,
                                                             SliceWeights w, float* __restrict__ hs_all, float* __restrict__ logits,
                                                             float* __restrict__ feat, float* __restrict__ slice_cls, int D, int Eenc,
-                                                            int E, int heads, int out_ch, int mode) {
+                                                            int E, int heads, int out_ch, int mode, int mask_period) {
     extern __shared__ float sm[];
     const int L = mode == SLICE_FUSION_TRANSFORMER ? D + 1 : D, l0 = L - D, hd = E / heads;
     float* x0 = sm;                 // [E]  raw CLS token (residual)
@@ -574,6 +619,8 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
     float* p = red + 40;            // [heads][L]
     float* kmat = p + ((heads * L + 3) & ~3);   // [L][E] projected keys, RoPE only
     const int b = blockIdx.x;
+    // TTA: the 8 flipped variants of a volume all get the volume's UN-flipped padding mask (main_predict.py:149)
+    const int bm = mask_period > 0 ? b % mask_period : b;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float* hs = hs_all + static_cast<int64_t>(b) * (D + 1) * E;
 
@@ -684,7 +731,7 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
                 a = fmaf(q[h * hd + d], kd * cs + rot * sn, a);
             }
             a = warp_sum(a);
-            if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(b) * D + j - 1]) a = -CUDART_INF_F;
+            if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(bm) * D + j - 1]) a = -CUDART_INF_F;
             if (lane == 0) p[h * L + j] = a;
         }
         __syncthreads();
@@ -711,7 +758,7 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
         float a = 0.f;
         for (int k = lane; k < E; k += 32) a = fmaf(qk[h * E + k], hr[k], a);
         a = warp_sum(a) + cterm[h];
-        if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(b) * D + j - 1]) a = -CUDART_INF_F;
+        if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(bm) * D + j - 1]) a = -CUDART_INF_F;
         if (lane == 0) p[h * L + j] = a;
     }
     __syncthreads();
@@ -783,19 +830,15 @@ __global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restri
 
 int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,
                         float* logits, float* feat, float* slice_cls, int B, int D, int Eenc, int E, int heads, int out_ch,
-                        int mode, cudaStream_t stream) {
+                        int mode, int mask_period, cudaStream_t stream) {
     MST_REQUIRE(heads <= 16 && E % heads == 0 && Eenc % 2 == 0, "slice fusion: heads=%d E=%d unsupported", heads, E);
     const int L = D + 1;
     const size_t smem = (static_cast<size_t>(6) * E + 2 * heads * E + 32 + 40 + ((heads * L + 3) & ~3) +
                          (w.rope_freqs ? static_cast<size_t>(L) * E : 0)) * sizeof(float);
     MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
-    static bool attr = false;
-    if (!attr) {
-        MST_CHECK_CUDA(cudaFuncSetAttribute(slice_fusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr = true;
-    }
+    MST_SET_DYN_SMEM(slice_fusion_kernel, 227 * 1024);
     slice_fusion_kernel<<<B, 384, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,
-                                                  out_ch, mode);
+                                                  out_ch, mode, mask_period);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -804,48 +847,71 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
 // Saliency combiner (reference dino.py:173-202 + scripts/main_predict.py:73-74,100) and the x14 upsampler
 // (main_predict.py:161-162: trilinear with depth scale 1 == per-slice bilinear, align_corners=False).
 // ---------------------------------------------------------------------------------------------------
+// nvar = 1: one CTA per slice.  nvar = 8 (test-time augmentation, main_predict.py:147-158): plane_cls / slice_cls hold the 8 flipped
+// variants of every volume, variant-major ([8*B*D, ...] / [8*B, ...]); the CTA of output slice (b, d) walks the variants in the
+// script's order, un-flips each variant's coarse map (flip of dims 2/3/4 = depth / grid rows / grid columns) and averages, so the
+// x14 upsample runs ONCE on the averaged coarse map as the script does (:161-162).
 __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __restrict__ plane_cls, const float* __restrict__ slice_cls,
-                                                                int D, int heads, int sheads, int P, int skip,
+                                                                int B, int D, int heads, int sheads, int gh, int gw, int skip, int nvar,
                                                                 float* __restrict__ attn_maps, float* __restrict__ plane_attn,
                                                                 float* __restrict__ slice_attn, float* __restrict__ coarse) {
-    extern __shared__ float sm[];  // acc[P] | red[40] | wsl[1]
+    extern __shared__ float sm[];  // acc[P] | tot[P] | red[40] | wsl[1]
+    const int P = gh * gw;
     float* acc = sm;
-    float* red = sm + P;
+    float* tot = sm + P;
+    float* red = tot + P;
     float* wsl = red + 40;
     const int s = blockIdx.x, b = s / D, d = s % D, L = D + 1, N = P + skip;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    // slice weight: mean over heads of S[b,h,1+d] / sum_j S[b,h,1+j]          (dino.py:174-181)
-    if (warp == 0) {
-        float wacc = 0.f;
-        for (int h = 0; h < sheads; ++h) {
-            const float* sr = slice_cls + (static_cast<int64_t>(b) * sheads + h) * L + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float wtot = 0.f;
+    for (int v = 0; v < nvar; ++v) {
+        const bool flip_d = (0xB2 >> v) & 1, flip_h = (0xD4 >> v) & 1, flip_w = (0xE8 >> v) & 1;
+        const int bv = v * B + b, dv = flip_d ? D - 1 - d : d;
+        const int64_t sv = static_cast<int64_t>(bv) * D + dv;
+        __syncthreads();   // acc / wsl of the previous variant have been consumed
+        // slice weight: mean over heads of S[b,h,1+d] / sum_j S[b,h,1+j]          (dino.py:174-181)
+        if (warp == 0) {
+            float wacc = 0.f;
+            for (int h = 0; h < sheads; ++h) {
+                const float* sr = slice_cls + (static_cast<int64_t>(bv) * sheads + h) * L + 1;
+                float t = 0.f;
+                for (int j = lane; j < D; j += 32) t += sr[j];
+                t = warp_sum(t);
+                wacc += sr[dv] / t;
+            }
+            if (lane == 0) *wsl = wacc / sheads;
+        }
+        for (int i = threadIdx.x; i < P; i += blockDim.x) acc[i] = 0.f;
+        __syncthreads();
+        const float wslice = *wsl;
+        for (int h = 0; h < heads; ++h) {
+            const float* pr = plane_cls + (sv * heads + h) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
             float t = 0.f;
-            for (int j = lane; j < D; j += 32) t += sr[j];
-            t = warp_sum(t);
-            wacc += sr[d] / t;
+            for (int i = threadIdx.x; i < P; i += blockDim.x) t += (i == 0) ? 0.f : pr[i];  // patch 0 := 0 (dino.py:193)
+            const float tsum = block_sum(t, red);
+            for (int i = threadIdx.x; i < P; i += blockDim.x) {
+                const float a = (i == 0) ? 0.f : pr[i] / tsum;                          // dino.py:194
+                const float m = wslice * a;                                             // dino.py:201
+                if (attn_maps) attn_maps[(sv * heads + h) * P + i] = m;
+                if (plane_attn) plane_attn[(sv * heads + h) * P + i] = a;
+                acc[i] += m;
+            }
         }
-        if (lane == 0) *wsl = wacc / sheads;
-    }
-    for (int i = threadIdx.x; i < P; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
-    const float wslice = *wsl;
-    (void)nwarps;
-    for (int h = 0; h < heads; ++h) {
-        const float* pr = plane_cls + (static_cast<int64_t>(s) * heads + h) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
-        float t = 0.f;
-        for (int i = threadIdx.x; i < P; i += blockDim.x) t += (i == 0) ? 0.f : pr[i];  // patch 0 := 0 (dino.py:193)
-        const float tot = block_sum(t, red);
+        __syncthreads();
+        // head mean (main_predict.py:73-74), un-flipped into the output orientation, summed in the script's order (:157)
         for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            const float a = (i == 0) ? 0.f : pr[i] / tot;                           // dino.py:194
-            const float m = wslice * a;                                             // dino.py:201
-            if (attn_maps) attn_maps[(static_cast<int64_t>(s) * heads + h) * P + i] = m;
-            if (plane_attn) plane_attn[(static_cast<int64_t>(s) * heads + h) * P + i] = a;
-            acc[i] += m;
+            const int y = i / gw, x = i - y * gw;
+            const int src_i = (flip_h ? gh - 1 - y : y) * gw + (flip_w ? gw - 1 - x : x);
+            const float m = acc[src_i] / heads;
+            tot[i] = v == 0 ? m : tot[i] + m;
         }
+        wtot = v == 0 ? wslice : wtot + wslice;
     }
+    __syncthreads();
+    const float inv = 1.0f / nvar;   // exact (1 or 1/8)
     if (coarse)
-        for (int i = threadIdx.x; i < P; i += blockDim.x) coarse[static_cast<int64_t>(s) * P + i] = acc[i] / heads;  // main_predict.py:73-74
-    if (slice_attn && threadIdx.x == 0) slice_attn[s] = wslice;
+        for (int i = threadIdx.x; i < P; i += blockDim.x) coarse[static_cast<int64_t>(s) * P + i] = tot[i] * inv;
+    if (slice_attn && threadIdx.x == 0) slice_attn[s] = wtot * inv;
 }
 
 __global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __restrict__ coarse, float* __restrict__ full,
@@ -889,15 +955,18 @@ __global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __r
     }
 }
 
-int launch_saliency(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int skip, int gh,
-                    int gw, int H, int W, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, float* full,
-                    cudaStream_t stream) {
+int launch_saliency_combine(const float* plane_cls, const float* slice_cls, int B, int D, int heads, int slice_heads, int skip, int gh,
+                            int gw, int tta, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, cudaStream_t stream) {
     const int P = gh * gw, BD = B * D;
-    MST_REQUIRE(coarse != nullptr || full == nullptr, "saliency: the full-resolution map needs the coarse buffer");
-    saliency_combine_kernel<<<BD, 256, (P + 48) * sizeof(float), stream>>>(plane_cls, slice_cls, D, heads, slice_heads, P, skip,
-                                                                          attn_maps, plane_attn, slice_attn, coarse);
+    MST_REQUIRE(!tta || (attn_maps == nullptr && plane_attn == nullptr), "saliency: the per-head maps are per variant; with tta only coarse / slice_attn");
+    saliency_combine_kernel<<<BD, 256, (2 * P + 48) * sizeof(float), stream>>>(plane_cls, slice_cls, B, D, heads, slice_heads, gh, gw, skip,
+                                                                              tta ? 8 : 1, attn_maps, plane_attn, slice_attn, coarse);
     MST_CHECK_CUDA(cudaGetLastError());
-    if (full) {
+    return 0;
+}
+int launch_saliency_upsample(const float* coarse, float* full, int B, int D, int gh, int gw, int H, int W, cudaStream_t stream) {
+    const int P = gh * gw, BD = B * D;
+    {
         const int rows_per_cta = 32;
         dim3 grid(BD, (H + rows_per_cta - 1) / rows_per_cta);
         saliency_upsample_kernel<<<grid, 256, P * sizeof(float), stream>>>(coarse, full, gh, gw, H, W, rows_per_cta);

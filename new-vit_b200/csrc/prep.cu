@@ -483,6 +483,13 @@ size_t prepare_volume_workspace_bytes(int items, int W0, int H0, int D0) {
            align256(static_cast<size_t>(items) * margin_floats(W0, H0, D0) * sizeof(float));
 }
 
+// kernels one launch_prepare_volume call issues: init, (7 marginal-minimum tables when an axis is padded), gather,
+// RADIX_PASSES x (histogram, pick), cutoff, moments, finalize, normalize
+int launch_prepare_volume_count(int W0, int H0, int D0, int W, int H, int D) {
+    const bool any_pad = W > W0 || H > H0 || D > D0;
+    return 1 + (any_pad ? 7 : 0) + 1 + 2 * RADIX_PASSES + 4;
+}
+
 int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, int W, int H, int D, int flip_h, float q_lo,
                           float q_hi, float* out, double* stats, void* workspace, int num_sms, cudaStream_t stream) {
     const int64_t n = static_cast<int64_t>(W) * H * D;

@@ -41,6 +41,10 @@ def predict_sharded(model, source_all, src_key_padding_mask=None, save_attn=Fals
     total = source_all.shape[0]
     start, count = shard_volumes(total, rank, world)
     mask = None if src_key_padding_mask is None else src_key_padding_mask[start:start + count]
-    with torch.no_grad():
-        local = model(source_all[start:start + count], save_attn=save_attn, src_key_padding_mask=mask)
+    if count == 0:   # more ranks than volumes: this rank contributes an empty block (the forward rejects an empty batch)
+        out_ch = getattr(model, "out_ch", None) or getattr(model, "emb_ch")
+        local = torch.empty((0, out_ch), dtype=torch.float32, device=getattr(model, "device", source_all.device))
+    else:
+        with torch.no_grad():
+            local = model(source_all[start:start + count], save_attn=save_attn, src_key_padding_mask=mask)
     return gather_volumes(local, total, group), (start, count)

@@ -166,14 +166,20 @@ class DinoV2ClassifierSlice(nn.Module):
             self.cls_token = nn.Parameter(torch.zeros(1, 1, emb))
         head_in = emb * 32 if slice_fusion == 'linear' else emb   # dino.py:98-99
         self.linear = nn.Linear(head_in, out_ch) if enable_linear else nn.Identity()
-        # reference init distributions, drawn from the global torch RNG
+        # the reference's init (zero encoder biases, unit LayerNorm, default-initialised conv / slice layers), seeded
+        # from the global torch RNG
         sd = synth.make_state_dict(model_size, out_ch, seed=int(torch.randint(0, 2 ** 31 - 1, (1,)).item()),
                                    img_size=img_size, layerscale=hub_layout, chunked_names=not hub_layout,
                                    num_registers=self.num_registers, use_bottleneck=use_bottleneck,
                                    use_slice_pos_emb=use_slice_pos_emb and slice_fusion == 'transformer',
                                    slice_fusion=slice_fusion, enable_linear=enable_linear,
-                                   rope=rotary_positional_encoding == 'RoPE')
+                                   rope=rotary_positional_encoding == 'RoPE', strict_init=True)
         nn.Module.load_state_dict(self, sd, strict=True)
+        # DinoVisionTransformer(interpolate_antialias, interpolate_offset): the vendored factory and the plain hub checkpoints
+        # resample with (False, 0.1) (vision_transformer.py:66-67); the hub "_reg" models use_registers loads (dino.py:60-61) are
+        # built with (True, 0.0).  Constructor keywords override, as they do on the reference's own factory.
+        self.interpolate_antialias = bool(kwargs.get("interpolate_antialias", use_registers))
+        self.interpolate_offset = float(kwargs.get("interpolate_offset", 0.0 if use_registers else 0.1))
         if freeze:
             for p in self.encoder.parameters():
                 p.requires_grad = False
@@ -283,7 +289,8 @@ class DinoV2ClassifierSlice(nn.Module):
             cfg = _cabi.MstConfig(E, self.encoder.depth, self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
                                   self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0],
                                   self.num_registers, int(hasattr(self, "bottleneck")), int(hasattr(self, "slice_pos_emb")),
-                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear), int(self.rotary == 'RoPE'))
+                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear), int(self.rotary == 'RoPE'),
+                                  int(self.interpolate_antialias), self.interpolate_offset)
             h = _cabi.ctypes.c_void_p()
             _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))
             self._handle, self._handle_key = h, key
@@ -316,12 +323,21 @@ class DinoV2ClassifierSlice(nn.Module):
             # the reference's register_hooks walks self.slice_fusion.named_modules() (dino.py:257), which does not exist
             raise AttributeError(f"'{type(self).__name__}' object has no attribute 'slice_fusion'")
         full_maps = kwargs.get("_full_maps", None)
+        tta = bool(kwargs.get("_tta", False))      # run_pred(use_tta=True): the 8 flipped variants as one batch (C ABI: tta)
+        V = 8 if tta else 1
         feat_dim = self.emb_ch * D if self.slice_fusion_type == 'linear' else self.emb_ch
         mask = None
         if src_key_padding_mask is not None:               # dino.py:147-150
             mask = src_key_padding_mask.to(dev).to(torch.uint8).contiguous()
             if tuple(mask.shape) != (B, D):
                 raise ValueError(f"src_key_padding_mask must be [B, D] = {(B, D)}, got {tuple(mask.shape)}")
+        # Volume element type on the wire: the bf16 path rounds every voxel to bf16 before the patch GEMM, so a bf16 (or fp16)
+        # `source` is taken as it is -- half the host-to-device bytes, bit-identical results for bf16; fp32 mode takes fp32.
+        if self.precision == 'bf16' and source.dtype in (torch.bfloat16, torch.float16):
+            src_dt = source.dtype
+        else:
+            src_dt = torch.float32
+        src_code = _cabi.SRC_DTYPE[str(src_dt)]
         # `source.to(self.device)` (dino.py:121).  A host batch is moved in chunks of whole volumes on a copy stream so
         # that the H2D transfer of chunk k+1 overlaps the kernels of chunk k (volumes are independent: results are
         # bit-identical to a single call, tests/test_gpu_parity.py::test_batch_composition...).
@@ -329,7 +345,7 @@ class DinoV2ClassifierSlice(nn.Module):
         if isinstance(sched, int):
             sched = (sched,)
         chunks = [B]
-        if source.device.type == "cpu" and sched and B > sched[0]:
+        if source.device.type == "cpu" and sched and B > sched[0] and not tta:
             chunks, left, i = [], B, 0
             while left > 0:
                 c = min(left, sched[min(i, len(sched) - 1)])
@@ -338,15 +354,15 @@ class DinoV2ClassifierSlice(nn.Module):
                 i += 1
         chunk = max(chunks)
         with torch.cuda.device(dev):
-            logits = torch.empty((B, self.out_ch), device=dev, dtype=torch.float32) if self.enable_linear else None
-            feat = torch.empty((B, feat_dim), device=dev, dtype=torch.float32)
-            plane = torch.empty((B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None
-            slc = torch.empty((B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
+            logits = torch.empty((V * B, self.out_ch), device=dev, dtype=torch.float32) if self.enable_linear else None
+            feat = torch.empty((V * B, feat_dim), device=dev, dtype=torch.float32)
+            plane = torch.empty((V * B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None
+            slc = torch.empty((V * B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
             if full_maps is not None:
                 chunks, chunk = [B], B   # full maps are written for the whole batch in one call
-            enc = torch.empty((B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
+            enc = torch.empty((V * B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
             need = _cabi.ctypes.c_size_t()
-            _cabi.check(L.mst_workspace_bytes(self._handle, chunk, D, H, W, _cabi.ctypes.byref(need)))
+            _cabi.check(L.mst_workspace_bytes(self._handle, V * chunk, D, H, W, _cabi.ctypes.byref(need)))
             if self._workspace is None or self._workspace.numel() < need.value or self._workspace.device != dev:
                 self._workspace = None
                 self._workspace = torch.empty(need.value, device=dev, dtype=torch.uint8)
@@ -355,20 +371,22 @@ class DinoV2ClassifierSlice(nn.Module):
 
             def run(xc, b0, nb):
                 sl = lambda t, per: None if t is None else t[b0 * per:(b0 + nb) * per]
-                _cabi.check(L.mst_forward(self._handle, _cabi.ptr(xc), nb, D, H, W, _cabi.ptr(sl(mask, 1)),
+                if tta:
+                    sl = lambda t, per: t          # one call covers the batch; outputs are variant-major over all of it
+                _cabi.check(L.mst_forward(self._handle, _cabi.ptr(xc), src_code, nb, D, H, W, _cabi.ptr(sl(mask, 1)), int(tta),
                                           _cabi.ptr(sl(logits, 1)), _cabi.ptr(sl(feat, 1)), _cabi.ptr(sl(enc, D)),
                                           _cabi.ptr(sl(plane, D)), _cabi.ptr(sl(slc, 1)), _cabi.ptr(full_maps),
                                           _cabi.ptr(self._workspace), self._workspace.numel(), stream))
 
             if len(chunks) == 1:
-                x = source.to(dev).to(torch.float32).contiguous()
+                x = source.to(dev).to(src_dt).contiguous()
                 run(x, 0, B)
             else:
-                src = source if source.dtype == torch.float32 else source.float()
+                src = source if source.dtype == src_dt else source.to(src_dt)
                 if (self._h2d is None or self._h2d[0].shape[1:] != (1, D, H, W) or self._h2d[0].device != dev
-                        or self._h2d[0].shape[0] < chunk):
+                        or self._h2d[0].shape[0] < chunk or self._h2d[0].dtype != src_dt):
                     self._h2d = None
-                    self._h2d = [torch.empty((chunk, 1, D, H, W), device=dev, dtype=torch.float32) for _ in range(2)]
+                    self._h2d = [torch.empty((chunk, 1, D, H, W), device=dev, dtype=src_dt) for _ in range(2)]
                     self._copy_stream = torch.cuda.Stream(device=dev)
                 copied = [torch.cuda.Event() for _ in range(2)]
                 freed = [torch.cuda.Event() for _ in range(2)]
@@ -391,6 +409,7 @@ class DinoV2ClassifierSlice(nn.Module):
             self.attention_maps = [plane.unsqueeze(2)]
             self.attention_maps_slice = [slc.unsqueeze(2)]
             self._last = (B, D, H, W)
+            self._last_tta = tta
             # get_attention_cls needs every block's full map: recomputed on demand from these (caller-owned) inputs
             self._last_inputs = (source, src_key_padding_mask)
         self._enc_cls = enc
@@ -426,6 +445,11 @@ class DinoV2ClassifierSlice(nn.Module):
         BD, heads, N = plane.shape
         B, sheads, L = slc.shape
         D = L - 1
+        tta = bool(getattr(self, "_last_tta", False))
+        if tta:                                            # the stored rows hold 8 flipped variants per volume
+            if want_maps or want_plane:
+                raise MSTError("get_attention_maps / get_plane_attention are per variant; after a TTA forward use saliency_volume()")
+            B, BD = B // 8, BD // 8
         skip = 1 + self.num_registers                      # dino.py:191
         P = N - skip
         if self._last is not None and self._last[0] * self._last[1] == BD:
@@ -443,8 +467,9 @@ class DinoV2ClassifierSlice(nn.Module):
             coarse = torch.empty((B, 1, D, gh, gw), device=dev, dtype=torch.float32) if (want_coarse or want_full) else None
             full = torch.empty((B, 1, D, H, W), device=dev, dtype=torch.float32) if want_full else None
             stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            _cabi.check(_cabi.lib().mst_saliency(_cabi.ptr(plane), _cabi.ptr(slc), B, D, heads, sheads, skip, gh, gw, H, W,
-                                                 _cabi.ptr(maps), _cabi.ptr(pl), _cabi.ptr(sl), _cabi.ptr(coarse), _cabi.ptr(full), stream))
+            _cabi.check(_cabi.lib().mst_saliency(self._handle, _cabi.ptr(plane), _cabi.ptr(slc), B, D, heads, sheads, skip, gh, gw,
+                                                 H, W, int(tta), _cabi.ptr(maps), _cabi.ptr(pl), _cabi.ptr(sl), _cabi.ptr(coarse),
+                                                 _cabi.ptr(full), stream))
         return maps, pl, sl, coarse, full
 
     def get_slice_attention(self):
@@ -529,12 +554,15 @@ def quantile(x, q):
     return out
 
 
-def _pred_trans(model, source, src_key_padding_mask, save_attn=False, use_softmax=True):
-    """scripts/main_predict.py:55-106, generalised from batch 1 to batch B."""
+def _pred_trans(model, source, src_key_padding_mask, save_attn=False, use_softmax=True, _tta=False):
+    """scripts/main_predict.py:55-106, generalised from batch 1 to batch B.  With _tta the forward covers the 8 flipped
+    variants as one batch (predictions come back [8, B, out_ch]) and the saliency kernels un-flip and average them."""
     with torch.no_grad():
-        pred = model(source, src_key_padding_mask=src_key_padding_mask, save_attn=save_attn)
+        pred = model(source, src_key_padding_mask=src_key_padding_mask, save_attn=save_attn, _tta=_tta)
     if use_softmax:
         pred = torch.softmax(pred, dim=-1)
+    if _tta:
+        pred = pred.view(8, source.shape[0], -1)
     if not save_attn:
         return pred, None, None
     weight, weight_slice = model.saliency_volume(size=tuple(source.shape[3:]))
@@ -543,21 +571,15 @@ def _pred_trans(model, source, src_key_padding_mask, save_attn=False, use_softma
 
 
 def run_pred(model, batch, save_attn=False, use_softmax=True, use_tta=False):
-    """scripts/main_predict.py:133-164.  The x14 upsample (F.interpolate trilinear, :161-162) is linear and
-    commutes with the flips/average of TTA, so it is applied inside `_pred_trans` by the fused kernel."""
+    """scripts/main_predict.py:133-164.  use_tta: the script's eight forwards (:147-158) run as ONE forward over the 8 flipped
+    variants (flips are index arithmetic on the patch load), the coarse maps are un-flipped and averaged in the script's
+    summation order inside the combine kernel, and the x14 upsample (F.interpolate trilinear, :161-162) runs once on the
+    average: one forward + two map launches.  The un-flipped padding mask goes to every variant, as the script passes it (:149)."""
     source, mask = batch['source'], batch.get('src_key_padding_mask', None)
-    pred, weight, weight_slice = _pred_trans(model, source, mask, save_attn, use_softmax)
+    pred, weight, weight_slice = _pred_trans(model, source, mask, save_attn, use_softmax, _tta=use_tta)
     if use_tta:
-        weight_slice = weight_slice.clone() if weight_slice is not None else None
-        for flip_dim in [(2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)]:
-            # the reference passes the un-flipped padding mask to the flipped volume (main_predict.py:149): mirrored
-            p_i, w_i, ws_i = _pred_trans(model, torch.flip(source, flip_dim), mask, save_attn, use_softmax)
-            pred = pred + p_i
-            if save_attn:
-                weight = weight + torch.flip(w_i, flip_dim)
-                weight_slice = weight_slice + torch.flip(ws_i, flip_dim)
-        pred = pred / 8
-        if save_attn:
-            weight = weight / 8
-            weight_slice = weight_slice / 8
+        p = pred[0]
+        for i in range(1, 8):      # the script's own order of additions (:151), on [B, out_ch] values
+            p = p + pred[i]
+        pred = p / 8
     return pred, weight, weight_slice

@@ -44,7 +44,7 @@ def _u(g, shape, bound):
 
 def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=224,
                     layerscale=False, chunked_names=True, num_registers=0, use_bottleneck=False,
-                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True, rope=False):
+                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True, rope=False, strict_init=False):
     """Return an OrderedDict with the reference's state_dict key layout.
 
     variant: "init"  -- reference-like init distributions
@@ -56,6 +56,10 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
     """
     assert variant in ("init", "peaky")
     assert slice_fusion in ("transformer", "linear", "average")
+    if strict_init:
+        sd = make_state_dict(model_size, out_ch, seed, "init", img_size, layerscale, chunked_names, num_registers, use_bottleneck,
+                             use_slice_pos_emb, slice_fusion, enable_linear, rope)
+        return _reference_init(sd)
     E, depth, _heads = VIT_CFG[model_size]
     g = torch.Generator(device="cpu")
     g.manual_seed(1000003 * seed + {"s": 1, "b": 2, "l": 3}[model_size] + (17 if variant == "peaky" else 0))
@@ -136,6 +140,27 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
     if enable_linear:
         sd["linear.weight"] = _u(g, (out_ch, E), lin)
         sd["linear.bias"] = _u(g, (out_ch,), lin)
+    return sd
+
+
+def _reference_init(sd):
+    """What a freshly constructed reference model holds, on top of the weight matrices drawn above:
+    every encoder Linear bias 0 and LayerNorm 1 / 0 (init_weights_vit_timm, vision_transformer.py:332-337, and nn.LayerNorm's
+    default), encoder cls_token / register tokens ~ N(0, 1e-6) (:174-176), LayerScale gamma = init_values (1.0 for the hub
+    configuration), MultiheadAttention in_proj / out_proj biases 0 (torch's _reset_parameters).  The conv / slice Linear / head
+    keep PyTorch's default uniform init, as in the reference."""
+    for k, v in sd.items():
+        enc = k.startswith("encoder.")
+        if k.endswith((".norm1.weight", ".norm2.weight", "norm.weight")) or k.endswith(("ls1.gamma", "ls2.gamma")):
+            v.fill_(1.0)
+        elif k.endswith((".norm1.bias", ".norm2.bias", "norm.bias")):
+            v.zero_()
+        elif enc and k.endswith(("qkv.bias", "proj.bias", "fc1.bias", "fc2.bias")) and "patch_embed" not in k:
+            v.zero_()
+        elif k in ("encoder.cls_token", "encoder.register_tokens"):
+            v.mul_(1e-6 / 0.02)
+        elif k.endswith(("self_attn.in_proj_bias", "self_attn.out_proj.bias")):
+            v.zero_()
     return sd
 
 

@@ -44,7 +44,7 @@ def duke_transform(data, image_crop=(224, 224, 32), percentiles=(0.5, 99.5), fli
         _cabi.check(L.mst_prepare_volume_workspace_bytes(items, W0, H0, D0, ct.byref(need)))
         ws = torch.empty(need.value, dtype=torch.uint8, device=data.device)
         stream = ct.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _cabi.check(L.mst_prepare_volume(_cabi.ptr(data), items, W0, H0, D0, W, H, D, 1 if flip else 0,
+        _cabi.check(L.mst_prepare_volume(None, _cabi.ptr(data), items, W0, H0, D0, W, H, D, 1 if flip else 0,
                                          ct.c_float(percentiles[0] / 100.0), ct.c_float(percentiles[1] / 100.0),
                                          _cabi.ptr(out), _cabi.ptr(stats), _cabi.ptr(ws), need.value, stream))
         if check:

@@ -38,8 +38,9 @@ def encoder_depth(sd):
     return d
 
 
-def interpolate_pos_encoding(pos_embed, npatch, w, h, interpolate_offset=0.1):
-    """vision_transformer.py:179-211."""
+def interpolate_pos_encoding(pos_embed, npatch, w, h, interpolate_offset=0.1, interpolate_antialias=False):
+    """vision_transformer.py:179-211.  (interpolate_offset, interpolate_antialias) = (0.1, False) for the vendored factory
+    and the plain hub checkpoints, (0.0, True) for the hub "_reg" checkpoints (dino.py:60-61)."""
     N = pos_embed.shape[1] - 1
     if npatch == N and w == h:
         return pos_embed
@@ -56,7 +57,7 @@ def interpolate_pos_encoding(pos_embed, npatch, w, h, interpolate_offset=0.1):
     else:
         kwargs["size"] = (w0, h0)
     patch_pos = F.interpolate(patch_pos.reshape(1, M, M, dim).permute(0, 3, 1, 2), mode="bicubic",
-                              antialias=False, **kwargs)
+                              antialias=interpolate_antialias, **kwargs)
     assert (w0, h0) == patch_pos.shape[-2:]
     patch_pos = patch_pos.permute(0, 2, 3, 1).reshape(1, -1, dim)
     return torch.cat((class_pos.unsqueeze(0), patch_pos), dim=1)
@@ -88,7 +89,8 @@ def encoder_forward(sd, img, heads, keep_all_maps=False):
     # vision_transformer.py:219-220
     x = torch.cat((sd["encoder.cls_token"].expand(BD, -1, -1), x), dim=1)
     # (the reference names the image dims "w, h = x.shape[2:]": its w is the height)
-    x = x + interpolate_pos_encoding(sd["encoder.pos_embed"], x.shape[1] - 1, H, W)
+    reg = "encoder.register_tokens" in sd   # the "_reg" hub architecture resamples anti-aliased, without the 0.1 offset
+    x = x + interpolate_pos_encoding(sd["encoder.pos_embed"], x.shape[1] - 1, H, W, 0.0 if reg else 0.1, reg)
     if "encoder.register_tokens" in sd:  # vision_transformer.py:222-230: registers go in AFTER the position add
         x = torch.cat((x[:, :1], sd["encoder.register_tokens"].expand(BD, -1, -1), x[:, 1:]), dim=1)
     maps = []

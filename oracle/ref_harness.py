@@ -116,6 +116,8 @@ def build_reference_model(state_dict=None, out_ch=2, model_size="s", hub_layout=
         from mst.models.extern.dinov2 import vision_transformer as vits
         factory = {"s": vits.vit_small, "b": vits.vit_base, "l": vits.vit_large}[model_size]
         extra = dict(init_values=1.0, block_chunks=0) if hub_layout else {}
+        if num_registers:   # torch.hub's dinov2_vit*14_reg entry points (what dino.py:60-61 loads) pass these two
+            extra.update(interpolate_antialias=True, interpolate_offset=0.0)
         model.encoder = factory(patch_size=14, img_size=pos_img_size or 224, num_register_tokens=num_registers, **extra).eval()
     if state_dict is not None:
         pe = state_dict["encoder.pos_embed"]

@@ -34,6 +34,8 @@ CASES = {
     "s_peaky_small_mask_b3": ("s", "peaky", 3, 7, 112, 112, True, 3, 3),
     # config 4 of BASELINE.json: ViT-B/14 encoder at 252x252 (256x256 is rejected by the reference, patch_embed.py:72-73)
     "b_peaky_252_mask_b2": ("b", "peaky", 2, 3, 252, 252, True, 4, 4),
+    # ... and at config 4's full slice count: D = 64 => slice-transformer L = 65 with 12 heads x 64 (E = 768)
+    "b_peaky_252_d64_mask_b1": ("b", "peaky", 1, 64, 252, 252, True, 13, 13),
     # hub-checkpoint layout: LayerScale gammas + "encoder.blocks.<i>" key names
     "s_hub_layerscale_b1": ("s", "peaky", 1, 4, 224, 224, False, 5, 5, {"hub_layout": True}),
     # ---- SURVEY 8f.2/8f.3 rows (flags: see run_case) ----

@@ -171,7 +171,7 @@ def test_saliency_upsample_matches_trilinear():
     sl = torch.empty(B * D, device="cuda")
     coarse = torch.empty(B, 1, D, g, g, device="cuda")
     full = torch.empty(B, 1, D, H, W, device="cuda")
-    cabi.check(L.mst_saliency(cabi.ptr(plane), cabi.ptr(slc), B, D, heads, sheads, 1, g, g, H, W, cabi.ptr(maps), cabi.ptr(pl),
+    cabi.check(L.mst_saliency(None, cabi.ptr(plane), cabi.ptr(slc), B, D, heads, sheads, 1, g, g, H, W, 0, cabi.ptr(maps), cabi.ptr(pl),
                               cabi.ptr(sl), cabi.ptr(coarse), cabi.ptr(full), _stream()))
     torch.cuda.synchronize()
     from oracle import mst_oracle as O
@@ -249,3 +249,73 @@ def test_gemm_bf16_layernorm_folded(M, N, K, gelu):
     if gelu:
         ref = _gelu(ref)
     torch.testing.assert_close(out.float(), ref, rtol=1.2e-2, atol=1.2e-2)
+
+
+@pytest.mark.parametrize("M", [777, 4112, 70000])
+@pytest.mark.parametrize("case", ["plain", "large_mean", "outlier_channel"])
+def test_gemm_fc2_fused_row_statistics(M, case):
+    """fc2 between two blocks (block.py:113 -> the next block's norm1, :112): x += A W^T + b in place and rstd of the UPDATED rows
+    out of the same epilogue (one-pass sum / sum of squares of the bf16 values it writes).  Against two-pass fp32 statistics of
+    the rows the kernel wrote, on rows with |mean| = 20 std and with a 100x outlier channel (massive activations)."""
+    cabi, L = _lib()
+    N, K = 384, 1536
+    g = torch.Generator(device="cuda").manual_seed(M + len(case))
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    x = torch.randn(M, N, device="cuda", generator=g)
+    if case == "large_mean":
+        x = x + 20.0 * (1.0 + torch.rand(M, 1, device="cuda", generator=g))     # row mean 20..40 x the row std
+    if case == "outlier_channel":
+        x[:, 7] += 100.0
+        x[:, 300] -= 60.0
+    x = x.bfloat16()
+    ref = x.float() + A.float() @ W.float().t() + bias
+    stat = torch.full((M,), float("nan"), device="cuda")
+    cabi.check(L.mst_kernel_gemm_bf16_res_stats(cabi.ptr(A), cabi.ptr(W), M, N, K, cabi.ptr(bias), cabi.ptr(x), cabi.ptr(stat),
+                                                1e-6, _stream()))
+    torch.cuda.synchronize()
+    bound = 8e-3 * (1.0 + ref.abs())
+    assert bool(((x.float() - ref).abs() <= bound).all())
+    var, _ = torch.var_mean(x.float(), dim=-1, unbiased=False)       # two-pass fp32 on what was written
+    want = torch.rsqrt(var + 1e-6)
+    # half a bf16 ulp (2^-9 = 2e-3) is what the consuming GEMM's output rounding costs anyway; hold the statistics to 1e-3
+    torch.testing.assert_close(stat, want, rtol=1e-3, atol=0)
+
+
+@pytest.mark.parametrize("N,K", [(1152, 384), (1536, 384), (2304, 768)])
+def test_ln_fold_packing_keeps_rows_centred_after_bf16_rounding(N, K):
+    """norm1 -> qkv / norm2 -> fc1 folding (api.cu pack_linear_ln_kernel): the bf16 weight rows must still sum to ~0, otherwise
+    mean(x) * rstd * sum_k Wc[n,k] leaks into every output.  Rows with mean = 20 std through the packed weights + folded GEMM
+    against LayerNorm-then-Linear in fp32."""
+    cabi, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(N + K)
+    W0 = torch.randn(N, K, device="cuda", generator=g).clamp(-2, 2) * 0.02          # trunc_normal(std 0.02)
+    b0 = 0.1 * torch.randn(N, device="cuda", generator=g)
+    gamma = 1.0 + 0.3 * torch.randn(K, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(K, device="cuda", generator=g)
+    Wd = torch.empty(N, K, device="cuda", dtype=torch.bfloat16)
+    bd = torch.empty(N, device="cuda")
+    cabi.check(L.mst_kernel_pack_linear_ln(cabi.ptr(W0), cabi.ptr(b0), cabi.ptr(gamma), cabi.ptr(beta), N, K, cabi.ptr(Wd), cabi.ptr(bd),
+                                           _stream()))
+    torch.cuda.synchronize()
+    Wg = W0 * gamma
+    Wc = Wg - Wg.mean(-1, keepdim=True)
+    ulp = 2.0 ** (torch.floor(torch.log2(Wc.abs().clamp_min(1e-30))) - 7)
+    assert bool(((Wd.float() - Wc).abs() <= 1.01 * ulp).all())                       # at most one bf16 step from the exact value
+    assert ((Wd.float() - Wc).abs() > 0.51 * ulp).float().mean().item() < 0.08        # ... and that only for a few elements per row
+    rowsum = Wd.double().sum(-1).abs()
+    plain = Wc.bfloat16().double().sum(-1).abs()
+    assert rowsum.max().item() <= 2e-6, rowsum.max().item()                          # independent roundings leave ~7e-4 (K = 384)
+    assert plain.max().item() > 50 * rowsum.max().item()
+    torch.testing.assert_close(bd, b0 + W0 @ beta, rtol=1e-5, atol=1e-6)
+    M = 2000
+    x = (torch.randn(M, K, device="cuda", generator=g) + 20.0).bfloat16()            # row mean = 20 std
+    stat = torch.empty(M, device="cuda")
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cabi.check(L.mst_kernel_row_stats_bf16(cabi.ptr(x), cabi.ptr(stat), M, K, 1e-6, _stream()))
+    cabi.check(L.mst_kernel_gemm_bf16_ln(cabi.ptr(x), cabi.ptr(Wd), M, N, K, 0, cabi.ptr(bd), cabi.ptr(stat), cabi.ptr(out), _stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, 1e-6) @ W0.t() + b0
+    # the error budget is the bf16 weight rounding (|LN(x)| ~ 1 over K terms of 2^-9 relative error) + the output rounding
+    torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=4e-3)

@@ -13,6 +13,7 @@ from conftest import case_inputs, load_golden, model_kwargs
 pytestmark = pytest.mark.gpu
 
 GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2",
+           "b_peaky_252_d64_mask_b1",     # config 4 at its full slice count: slice transformer L = 65, 12 heads x 64
            "s_hub_layerscale_b1",
            # hub "_reg" architecture (registers + 518 pos_embed resampled), non-square input through the
            # bicubic pos_embed path, bottleneck + slice position embedding
@@ -254,3 +255,118 @@ def test_checkpoint_round_trip_runs_the_same_forward(tmp_path):
     DinoV2ClassifierSlice.save_best_checkpoint(tmp_path, tmp_path / "last.ckpt")
     m = DinoV2ClassifierSlice.load_best_checkpoint(tmp_path).cuda().eval()
     assert torch.equal(m(x), want)
+
+
+def _assert_volume_matches_oracle(r_logits, r_maps, sd, xb, mb, variant):
+    from oracle import mst_oracle as O
+    ref = O.forward(sd, xb, mb)
+    err = (r_logits - ref["logits"]).abs().max().item()
+    assert err <= 2e-2, f"bf16 logits differ from the oracle by {err}"
+    assert _cos(r_maps, O.get_attention_maps(ref["plane_cls"], ref["slice_cls"])) >= 0.999
+    return ref
+
+
+@pytest.mark.parametrize("size,B,D,HW,probe", [("s", 64, 32, 224, (0, 31, 63)),      # BASELINE config 2 (the benchmarked shape)
+                                               ("b", 16, 64, 252, (0, 15))])         # BASELINE config 4 per GPU (ViT-B/14)
+def test_benchmarked_shapes_parity(size, B, D, HW, probe):
+    """The launch geometry bench.py times (M = 526 336 token rows on ViT-S: every persistent CTA wraps its operand rings and
+    accumulator stages hundreds of times; 16 x 64 x 325 tokens on ViT-B) is parity-checked end to end: selected volumes of the
+    full batch are bit-identical to single-volume calls, and one of them is within the bf16 tolerance of the oracle."""
+    from new_vit_b200 import synth
+    sd = synth.make_state_dict(size, 2, seed=41, variant="peaky", img_size=HW)
+    x = synth.make_volume(B, D, HW, HW, seed=42)
+    mask = synth.make_padding_mask(B, D, seed=3)
+    m = _model(sd, "bf16", HW, size=size)
+    with torch.no_grad():
+        y = m(x.cuda(), save_attn=True, src_key_padding_mask=mask).cpu()
+        maps = m.get_attention_maps().cpu()
+        sl = m.get_slice_attention().cpu().reshape(B, D)
+        assert torch.isfinite(y).all() and torch.isfinite(maps).all()
+        for b in probe:
+            yb = m(x[b:b + 1], save_attn=True, src_key_padding_mask=mask[b:b + 1]).cpu()
+            mb = m.get_attention_maps().cpu()
+            assert torch.equal(yb[0], y[b]), (b, yb, y[b])
+            assert torch.equal(mb, maps[b * D:(b + 1) * D])
+    torch.testing.assert_close(maps.mean(1).reshape(B, -1).sum(-1), torch.ones(B), rtol=1e-5, atol=1e-5)
+    assert (sl[mask] == 0).all()
+    b = probe[-1]
+    _assert_volume_matches_oracle(y[b:b + 1], maps[b * D:(b + 1) * D], sd, x[b:b + 1], mask[b:b + 1], "peaky")
+
+
+def test_bf16_source_is_bit_identical_and_fp16_close():
+    """The bf16 path rounds every voxel to bf16 before the patch GEMM, so a bf16 `source` (half the host-to-device bytes) gives
+    bit-identical results, device-resident and through the pipelined host path; fp16 voxels differ only by their own rounding."""
+    from new_vit_b200 import synth
+    B, D, H, W = 5, 4, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=21, variant="peaky")
+    x = synth.make_volume(B, D, H, W, seed=23)
+    mask = synth.make_padding_mask(B, D, seed=1)
+    m = _model(sd, "bf16", H)
+    with torch.no_grad():
+        y0 = m(x.cuda(), save_attn=True, src_key_padding_mask=mask).cpu()
+        maps0 = m.get_attention_maps().cpu()
+        y1 = m(x.bfloat16().cuda(), save_attn=True, src_key_padding_mask=mask).cpu()
+        maps1 = m.get_attention_maps().cpu()
+        m.h2d_chunk_volumes = 2
+        y2 = m(x.bfloat16().pin_memory(), save_attn=True, src_key_padding_mask=mask).cpu()
+        y3 = m(x.half().cuda(), src_key_padding_mask=mask).cpu()
+    assert torch.equal(y0, y1) and torch.equal(y0, y2) and torch.equal(maps0, maps1)
+    assert (y3 - y0).abs().max().item() <= 2e-2
+    m32 = _model(sd, "fp32", H)
+    with torch.no_grad():   # fp32 parity mode: a 16-bit source is converted up front (the C ABI takes fp32 only there)
+        assert torch.equal(m32(x.bfloat16().cuda()), m32(x.bfloat16().float().cuda()))
+
+
+def test_tta_runs_as_one_forward_and_two_map_launches():
+    """run_pred(use_tta=True) (main_predict.py:147-162): ONE forward over the 8 flipped variants, un-flip + average of the
+    coarse maps inside the combine kernel, one upsample -- and the same numbers as eight separate flipped forwards."""
+    from new_vit_b200 import synth
+    from new_vit_b200.model import run_pred
+    B, D, H, W = 2, 5, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=31, variant="peaky")
+    x = synth.make_volume(B, D, H, W, seed=33).cuda()
+    mask = synth.make_padding_mask(B, D, seed=0)
+    m = _model(sd, "fp32", H)
+    with torch.no_grad():
+        m(x, save_attn=True, src_key_padding_mask=mask)
+        n0 = m.launch_count()
+        m(x, save_attn=True, src_key_padding_mask=mask)
+        fwd = m.launch_count() - n0
+        n0 = m.launch_count()
+        p, w, ws = run_pred(m, {"source": x, "src_key_padding_mask": mask}, save_attn=True, use_tta=True)
+        assert m.launch_count() - n0 == fwd + 2
+        # the script's own loop, flip by flip, coarse maps averaged before the single upsample
+        flips = [(), (2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)]
+        ps, cs, sls = [], [], []
+        for f in flips:
+            xf = torch.flip(x, f) if f else x
+            ps.append(torch.softmax(m(xf, save_attn=True, src_key_padding_mask=mask), -1))
+            _, _, sl, coarse, _ = m._saliency(want_slice=True, want_coarse=True)
+            cs.append(torch.flip(coarse, f) if f else coarse)
+            s5 = sl.view(B, 1, D, 1, 1)
+            sls.append(torch.flip(s5, [d for d in f if d == 2]) if 2 in f else s5)
+        pr, cr, sr = ps[0], cs[0], sls[0]
+        for i in range(1, 8):
+            pr, cr, sr = pr + ps[i], cr + cs[i], sr + sls[i]
+        wr = F.interpolate(cr / 8, size=(D, H, W), mode="trilinear")
+    assert torch.equal(p, pr / 8)
+    torch.testing.assert_close(w, wr, rtol=1e-5, atol=float(wr.max()) * 1e-6)
+    torch.testing.assert_close(ws[:, :, :, 0, 0], (sr / 8)[:, :, :, 0, 0], rtol=1e-6, atol=0)
+    assert torch.equal(w.reshape(B, -1).argmax(-1), wr.reshape(B, -1).argmax(-1))
+
+
+def test_second_device_in_one_process():
+    """Kernel attributes (opt-in dynamic shared memory) are per device: a model on cuda:1 after one on cuda:0 must launch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU")
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    sd = synth.make_state_dict("s", 2, seed=5, variant="peaky")
+    x = synth.make_volume(2, 4, 224, 224, seed=5)
+    ys = []
+    for d in (0, 1):
+        m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16").to(f"cuda:{d}").eval()
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            ys.append(m(x, save_attn=True).cpu())
+            m.saliency_volume()
+    assert torch.equal(ys[0], ys[1])

@@ -14,7 +14,7 @@ def test_library_loads_and_exports_all_declared_symbols():
     assert len(names) >= 14 and "mst_forward" in names and "mst_saliency" in names
     for n in names:
         assert hasattr(L, n), n
-    assert L.mst_abi_version() == 3
+    assert L.mst_abi_version() == _cabi.ABI_VERSION == 4
 
 
 def test_no_cpu_fallback():
@@ -22,7 +22,7 @@ def test_no_cpu_fallback():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     L = _cabi.lib()
-    cfg = _cabi.MstConfig(384, 12, 6, 12, 2, 257, 1, 0, 0, 0, 0, 0, 1)
+    cfg = _cabi.MstConfig(384, 12, 6, 12, 2, 257, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0.1)
     h = ctypes.c_void_p()
     assert L.mst_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
     assert b"no CUDA device" in L.mst_last_error()

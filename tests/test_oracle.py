@@ -10,7 +10,7 @@ from oracle import ref_harness
 SMALL = ["s_init_small", "s_peaky_small_mask_b3", "s_hub_layerscale_b1", "s_hub_reg518_b1", "s_interp_126x168_b2",
          "s_bottleneck_posemb_b2", "s_rope_bottleneck_mask_b2", "s_rope_b2"]
 NO_TRANSFORMER = ["s_fusion_linear_b2", "s_fusion_average_nolinear_b2"]
-FULL = ["s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2"]
+FULL = ["s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2", "b_peaky_252_d64_mask_b1"]
 
 
 def _check(name):
@@ -20,7 +20,8 @@ def _check(name):
     r = O.forward(sd, x, mask, keep_all_maps="rollout_cls" in g)
     B, D, H, W = meta["B"], meta["D"], meta["H"], meta["W"]
     if "pos_embed" in g:   # interpolate_pos_encoding (vision_transformer.py:179-211), bicubic through ATen
-        torch.testing.assert_close(O.interpolate_pos_encoding(sd["encoder.pos_embed"], (H // 14) * (W // 14), H, W),
+        torch.testing.assert_close(O.interpolate_pos_encoding(sd["encoder.pos_embed"], (H // 14) * (W // 14), H, W,
+                                                              0.0 if nreg else 0.1, nreg > 0),
                                    g["pos_embed"], rtol=1e-5, atol=1e-6)
     if "rollout_cls" in g:
         torch.testing.assert_close(O.get_attention_cls(r["maps"])[:, :, 0, :], g["rollout_cls"], rtol=1e-4, atol=1e-8)
