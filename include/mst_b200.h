@@ -105,6 +105,13 @@ MST_API int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_
                 const uint8_t* pad_mask, int32_t tta, float* logits, float* feat, float* enc_cls, float* plane_cls, float* slice_cls,
                 float* full_maps, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Small batches are launch-bound (one volume: 77 kernels of ~10 us each): forwards of at most `max_tokens` token rows
+ * (B * D * tokens per slice) are captured into a CUDA graph the second time mst_forward sees the exact same argument tuple
+ * (pointers, shapes, stream) and replayed afterwards.  0 switches graphs off (the default).  The caller keeps the buffers of a
+ * captured call alive and unchanged in address; results are identical to the eager path.  mst_graph_replays counts replays. */
+MST_API int mst_set_graph_threshold(mst_handle h, int64_t max_tokens);
+MST_API unsigned long long mst_graph_replays(mst_handle h);
+
 /* get_plane_attention / get_slice_attention / get_attention_maps (dino.py:173-202) and the caller's
  * head-mean + reshape + trilinear upsample (scripts/main_predict.py:73-74,100,161-162), batched.
  *   attn_maps  nullable [B*D,enc_heads,P] (get_attention_maps)   plane_attn nullable [B*D,enc_heads,P] (get_plane_attention)

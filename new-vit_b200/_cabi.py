@@ -77,12 +77,15 @@ def lib():
     L.mst_profile_begin.argtypes = [vp]
     L.mst_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.mst_launch_count.argtypes = [vp]
+    L.mst_set_graph_threshold.argtypes = [vp, i64]
+    L.mst_graph_replays.argtypes = [vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
-        if name not in ("mst_last_error", "mst_profile_categories", "mst_launch_count"):
+        if name not in ("mst_last_error", "mst_profile_categories", "mst_launch_count", "mst_graph_replays"):
             fn.restype = ctypes.c_int
     L.mst_profile_categories.restype = ctypes.c_char_p
     L.mst_launch_count.restype = ctypes.c_ulonglong
+    L.mst_graph_replays.restype = ctypes.c_ulonglong
     if L.mst_abi_version() != ABI_VERSION:
         raise ImportError("libmst_b200.so ABI version mismatch")
     _lib = L

@@ -48,9 +48,9 @@ __global__ void pack_linear_kernel(const float* __restrict__ W, const float* __r
 // The centring must survive the bf16 rounding: x . Wd[n,:] carries mean(x) * sum_k Wd[n,k], and independent roundings leave
 // sum_k Wd[n,k] ~ sqrt(K) * ulp/sqrt(12) (7e-4 for K = 384, |W| ~ 0.02), which a row with mean(x) * rstd ~ 20 (real DINOv2
 // residual streams have such rows) turns into a 1.4e-2 error on every output.  So after rounding, single elements are moved
-// by one bf16 step -- the ones whose new rounding error is smallest -- until no step brings the row sum closer to zero:
-// |sum_k Wd[n,k]| ends below half the smallest step available in the row (~1e-7), at the cost of a handful of elements per
-// row carrying up to one ulp of rounding error instead of half.
+// by ONE bf16 step each -- greedily the move that brings the row sum closest to zero -- until no move helps: |sum_k Wd[n,k]|
+// ends below half the smallest step available in the row (~1e-7), at the cost of about ten elements per row carrying up to
+// 1.5 ulp of rounding error instead of half an ulp.
 constexpr int kPackLnMaxK = 1024;
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
 __global__ void __launch_bounds__(128) pack_linear_ln_kernel(const float* __restrict__ W, const float* __restrict__ b,
@@ -81,26 +81,24 @@ __global__ void __launch_bounds__(128) pack_linear_ln_kernel(const float* __rest
     if (threadIdx.x == 0) {
         double r = 0.0;
         for (int k = 0; k < K; ++k) r += static_cast<double>(bf16_bits_to_float(qb[k]));
-        for (int iter = 0; iter < 256; ++iter) {
+        for (int iter = 0; iter < 64; ++iter) {
+            // the single one-step move (of an element not moved yet) that brings the row sum closest to zero
             int best = -1;
             uint16_t best_bits = 0;
-            float best_cost = 3.0e38f;
-            double best_d = 0.0;
+            double best_abs = fabs(r), best_d = 0.0;
             for (int k = 0; k < K; ++k) {
                 const uint16_t bits = qb[k];
-                if ((bits & 0x7f80) == 0) continue;                       // zero / subnormal: leave alone
+                if ((bits & 0x7f80) == 0 || tk[k] == 3.0e38f) continue;     // zero / subnormal, or already moved
                 const float qv = bf16_bits_to_float(bits);
                 const bool up = r < 0.0;                                   // the row sum must grow
                 const uint16_t nb = (up == (qv > 0.f)) ? bits + 1 : bits - 1;
                 if ((nb & 0x7f80) == 0x7f80 || (nb & 0x7f80) == 0) continue;
-                const float nv = bf16_bits_to_float(nb);
-                const double d = static_cast<double>(nv) - static_cast<double>(qv);
-                if (fabs(r + d) >= fabs(r)) continue;                      // this step would not bring the sum closer to zero
-                const float cost = fabsf(nv - tk[k]);                      // the element's rounding error after the step
-                if (cost < best_cost) { best_cost = cost; best = k; best_bits = nb; best_d = d; }
+                const double d = static_cast<double>(bf16_bits_to_float(nb)) - static_cast<double>(qv);
+                if (fabs(r + d) < best_abs) { best_abs = fabs(r + d); best = k; best_bits = nb; best_d = d; }
             }
             if (best < 0) break;
             qb[best] = best_bits;
+            tk[best] = 3.0e38f;   // marks the element as moved
             r += best_d;
         }
         bd[n] = b[n] * f + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
@@ -167,9 +165,34 @@ struct Profiler {
 };
 }  // namespace mst
 
+namespace mst {
+// One captured forward: every kernel of mst_forward for one exact argument tuple (pointers included -- they are baked into the
+// kernel parameters and TMA descriptors), replayed with a single cudaGraphLaunch.  What it removes is host time: ~150
+// cuTensorMapEncodeTiled calls and ~77 launches per forward, which is what a one-volume forward costs (main_predict.py:208).
+struct GraphKey {
+    const void* src; int src_dtype, B, D, H, W; const void* mask; int tta;
+    void *logits, *feat, *enc, *plane, *slc, *full, *ws; size_t ws_bytes; void* stream;
+    bool operator==(const GraphKey& o) const {
+        return src == o.src && src_dtype == o.src_dtype && B == o.B && D == o.D && H == o.H && W == o.W && mask == o.mask && tta == o.tta &&
+               logits == o.logits && feat == o.feat && enc == o.enc && plane == o.plane && slc == o.slc && full == o.full && ws == o.ws &&
+               ws_bytes == o.ws_bytes && stream == o.stream;
+    }
+};
+struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;   // null until the key has been seen twice (one-off argument tuples are not captured)
+    unsigned long long launches = 0;
+    unsigned long long last_use = 0;
+};
+constexpr int kMaxGraphs = 16;
+}  // namespace mst
+
 struct mst_handle_s {
     mst::Profiler prof;
     unsigned long long launches = 0;
+    std::vector<mst::GraphEntry> graphs;
+    unsigned long long graph_clock = 0, graph_replays = 0;
+    long long graph_max_tokens = 0;             // 0 = CUDA graphs off (mst_set_graph_threshold)
     mst_config cfg;
     int num_sms = 0;
     bool finalized = false;
@@ -628,10 +651,17 @@ int mst_create(const mst_config* cfg, mst_handle* out) {
     return 0;
 }
 
+static void drop_graphs(mst_handle h) {
+    for (auto& g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
 int mst_destroy(mst_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    drop_graphs(h);
     for (auto& kv : h->master) cudaFree(kv.second);
     for (void* p : h->owned) cudaFree(p);
     for (auto& kv : h->pos_cache) cudaFree(kv.second);
@@ -665,6 +695,7 @@ int mst_finalize_weights(mst_handle h, void* stream) {
     MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MST_CHECK_CUDA(cudaStreamSynchronize(st));
+    drop_graphs(h);   // captured forwards hold the old packed-weight pointers
     for (void* p : h->owned) cudaFree(p);
     h->owned.clear();
     if (h->cfg.precision == MST_PRECISION_BF16) {
@@ -713,10 +744,80 @@ int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int
     MST_REQUIRE(ws.total <= workspace_bytes, "mst_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
     MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (h->cfg.precision == MST_PRECISION_BF16)
-        return forward_t<bf16>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
-    return forward_t<float>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+    auto run = [&]() -> int {
+        if (h->cfg.precision == MST_PRECISION_BF16)
+            return forward_t<bf16>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+        return forward_t<float>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+    };
+    // ---- CUDA graph replay for small batches (launch-bound: the kernels of a one-volume forward take less time than issuing them) ----
+    const long long tokens = static_cast<long long>(B) * D * ((H / 14) * (W / 14) + 1 + h->cfg.num_registers);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (h->graph_max_tokens <= 0 || tokens > h->graph_max_tokens || h->prof.on || full_maps != nullptr ||
+        cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
+        return run();
+    const GraphKey key{src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, workspace,
+                       workspace_bytes, stream};
+    GraphEntry* e = nullptr;
+    for (auto& g : h->graphs)
+        if (g.key == key) { e = &g; break; }
+    if (e && e->exec) {
+        MST_CHECK_CUDA(cudaGraphLaunch(e->exec, st));
+        e->last_use = ++h->graph_clock;
+        h->launches += e->launches;
+        h->graph_replays++;
+        return 0;
+    }
+    if (!e) {   // first sight of this argument tuple: run it eagerly, remember it (least recently used entry makes room)
+        if (static_cast<int>(h->graphs.size()) >= kMaxGraphs) {
+            size_t lru = 0;
+            for (size_t i = 1; i < h->graphs.size(); ++i)
+                if (h->graphs[i].last_use < h->graphs[lru].last_use) lru = i;
+            if (h->graphs[lru].exec) cudaGraphExecDestroy(h->graphs[lru].exec);
+            h->graphs.erase(h->graphs.begin() + lru);
+        }
+        GraphEntry ne;
+        ne.key = key;
+        ne.last_use = ++h->graph_clock;
+        h->graphs.push_back(ne);
+        return run();
+    }
+    // second sight: capture.  (The position table of this grid and every per-device kernel attribute were set up by the eager run.)
+    const unsigned long long l0 = h->launches;
+    MST_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rc = run();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->launches = l0;
+        h->graph_max_tokens = 0;   // capture is not possible in this context: stay on the eager path
+        return run();
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || exec == nullptr) {
+        cudaGetLastError();
+        h->launches = l0;
+        h->graph_max_tokens = 0;
+        return run();
+    }
+    e->exec = exec;
+    e->launches = h->launches - l0;
+    e->last_use = ++h->graph_clock;
+    MST_CHECK_CUDA(cudaGraphLaunch(exec, st));
+    h->graph_replays++;
+    return 0;
 }
+
+int mst_set_graph_threshold(mst_handle h, int64_t max_tokens) {
+    MST_REQUIRE(h, "mst_set_graph_threshold: null handle");
+    h->graph_max_tokens = max_tokens;
+    if (max_tokens <= 0) drop_graphs(h);
+    return 0;
+}
+unsigned long long mst_graph_replays(mst_handle h) { return h ? h->graph_replays : 0; }
 
 int mst_saliency(mst_handle h, const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
                  int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, int32_t tta, float* attn_maps,

@@ -855,102 +855,116 @@ __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __re
                                                                 int B, int D, int heads, int sheads, int gh, int gw, int skip, int nvar,
                                                                 float* __restrict__ attn_maps, float* __restrict__ plane_attn,
                                                                 float* __restrict__ slice_attn, float* __restrict__ coarse) {
-    extern __shared__ float sm[];  // acc[P] | tot[P] | red[40] | wsl[1]
+    extern __shared__ float sm[];  // acc[P] | tot[P] | hsum[32] | whd[32]
     const int P = gh * gw;
     float* acc = sm;
     float* tot = sm + P;
-    float* red = tot + P;
-    float* wsl = red + 40;
+    float* hsum = tot + P;     // per encoder head: sum of the CLS->patch probabilities, patch 0 excluded
+    float* whd = hsum + 32;    // per slice head: this slice's renormalised weight
     const int s = blockIdx.x, b = s / D, d = s % D, L = D + 1, N = P + skip;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     float wtot = 0.f;
     for (int v = 0; v < nvar; ++v) {
         const bool flip_d = (0xB2 >> v) & 1, flip_h = (0xD4 >> v) & 1, flip_w = (0xE8 >> v) & 1;
         const int bv = v * B + b, dv = flip_d ? D - 1 - d : d;
         const int64_t sv = static_cast<int64_t>(bv) * D + dv;
-        __syncthreads();   // acc / wsl of the previous variant have been consumed
-        // slice weight: mean over heads of S[b,h,1+d] / sum_j S[b,h,1+j]          (dino.py:174-181)
-        if (warp == 0) {
-            float wacc = 0.f;
-            for (int h = 0; h < sheads; ++h) {
+        __syncthreads();   // acc / hsum / whd of the previous variant have been consumed
+        // one warp per reduction, all of them in flight at once: the encoder heads' renormalisation sums (patch 0 := 0,
+        // dino.py:193-194) and the slice heads' weights S[b,h,1+d] / sum_j S[b,h,1+j] (dino.py:174-176)
+        for (int task = warp; task < heads + sheads; task += nwarps) {
+            if (task < heads) {
+                const float* pr = plane_cls + (sv * heads + task) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
+                float t = 0.f;
+                for (int i = 1 + lane; i < P; i += 32) t += pr[i];
+                t = warp_sum(t);
+                if (lane == 0) hsum[task] = t;
+            } else {
+                const int h = task - heads;
                 const float* sr = slice_cls + (static_cast<int64_t>(bv) * sheads + h) * L + 1;
                 float t = 0.f;
                 for (int j = lane; j < D; j += 32) t += sr[j];
                 t = warp_sum(t);
-                wacc += sr[dv] / t;
+                if (lane == 0) whd[h] = sr[dv] / t;
             }
-            if (lane == 0) *wsl = wacc / sheads;
         }
-        for (int i = threadIdx.x; i < P; i += blockDim.x) acc[i] = 0.f;
         __syncthreads();
-        const float wslice = *wsl;
-        for (int h = 0; h < heads; ++h) {
-            const float* pr = plane_cls + (sv * heads + h) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
-            float t = 0.f;
-            for (int i = threadIdx.x; i < P; i += blockDim.x) t += (i == 0) ? 0.f : pr[i];  // patch 0 := 0 (dino.py:193)
-            const float tsum = block_sum(t, red);
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                const float a = (i == 0) ? 0.f : pr[i] / tsum;                          // dino.py:194
-                const float m = wslice * a;                                             // dino.py:201
+        float wslice = 0.f;
+        for (int h = 0; h < sheads; ++h) wslice += whd[h];
+        wslice /= sheads;                                                           // mean over the slice heads (dino.py:181)
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+            float msum = 0.f;
+            for (int h = 0; h < heads; ++h) {
+                const float* pr = plane_cls + (sv * heads + h) * N + skip;
+                const float a = (i == 0) ? 0.f : pr[i] / hsum[h];                   // dino.py:193-194
+                const float m = wslice * a;                                         // dino.py:201
                 if (attn_maps) attn_maps[(sv * heads + h) * P + i] = m;
                 if (plane_attn) plane_attn[(sv * heads + h) * P + i] = a;
-                acc[i] += m;
+                msum += m;
             }
+            acc[i] = msum / heads;                                                  // head mean (main_predict.py:73-74)
         }
         __syncthreads();
-        // head mean (main_predict.py:73-74), un-flipped into the output orientation, summed in the script's order (:157)
+        // un-flipped into the output orientation, summed in the script's order (main_predict.py:157)
         for (int i = threadIdx.x; i < P; i += blockDim.x) {
             const int y = i / gw, x = i - y * gw;
-            const int src_i = (flip_h ? gh - 1 - y : y) * gw + (flip_w ? gw - 1 - x : x);
-            const float m = acc[src_i] / heads;
+            const float m = acc[(flip_h ? gh - 1 - y : y) * gw + (flip_w ? gw - 1 - x : x)];
             tot[i] = v == 0 ? m : tot[i] + m;
         }
         wtot = v == 0 ? wslice : wtot + wslice;
     }
-    __syncthreads();
     const float inv = 1.0f / nvar;   // exact (1 or 1/8)
     if (coarse)
         for (int i = threadIdx.x; i < P; i += blockDim.x) coarse[static_cast<int64_t>(s) * P + i] = tot[i] * inv;
     if (slice_attn && threadIdx.x == 0) slice_attn[s] = wtot * inv;
 }
 
+// x(H/gh) bilinear upsample, align_corners=False (== F.interpolate 'trilinear' with depth scale 1, main_predict.py:161-162):
+//   out[y, x] = hy * (hx * c[y0, x0] + lx * c[y0, x1]) + ly * (hx * c[y1, x0] + lx * c[y1, x1])
+// One CTA = one slice x UP_ROWS output rows.  The horizontal blends hrow[r][x] = hx * c[r, x0] + lx * c[r, x1] of the few
+// coarse rows the block touches are built once in shared memory; every output is then two shared-memory values and one
+// FMUL + FMA, written as 16-byte streaming stores (this is the bandwidth-bound step of the saliency path: 6.4 MB per volume).
+constexpr int UP_ROWS = 56;
 __global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __restrict__ coarse, float* __restrict__ full,
-                                                                 int gh, int gw, int H, int W, int rows_per_cta) {
-    extern __shared__ float c[];  // [gh*gw]
+                                                                 int gh, int gw, int H, int W, int crow_max) {
+    extern __shared__ float hrow[];  // [crow_max][W]
     const int s = blockIdx.x;
-    const int y_begin = blockIdx.y * rows_per_cta;
-    const int y_end = min(H, y_begin + rows_per_cta);
-    for (int i = threadIdx.x; i < gh * gw; i += blockDim.x) c[i] = coarse[static_cast<int64_t>(s) * gh * gw + i];
-    __syncthreads();
+    const int y_begin = blockIdx.y * UP_ROWS;
+    const int y_end = min(H, y_begin + UP_ROWS);
     const float sy = static_cast<float>(gh) / static_cast<float>(H), sx = static_cast<float>(gw) / static_cast<float>(W);
+    const int r_first = static_cast<int>(fmaxf(sy * (y_begin + 0.5f) - 0.5f, 0.f));   // first coarse row this block reads
+    const float* c = coarse + static_cast<int64_t>(s) * gh * gw;
+    for (int idx = threadIdx.x; idx < crow_max * W; idx += blockDim.x) {
+        const int rr = idx / W, x = idx - rr * W;
+        const int r = min(r_first + rr, gh - 1);
+        const float fx = fmaxf(sx * (x + 0.5f) - 0.5f, 0.f);
+        const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, gw - 1);
+        const float lx = fx - x0, hx = 1.f - lx;
+        hrow[idx] = hx * __ldg(c + r * gw + x0) + lx * __ldg(c + r * gw + x1);
+    }
+    __syncthreads();
     float* out = full + static_cast<int64_t>(s) * H * W;
-    const int W4 = W >> 2;
     if ((W & 3) == 0) {
-        for (int idx = y_begin * W4 + threadIdx.x; idx < y_end * W4; idx += blockDim.x) {
-            const int y = idx / W4, x4 = (idx % W4) * 4;
+        const int W4 = W >> 2;
+        const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 column groups x 4 rows in flight
+        for (int y = y_begin + ty; y < y_end; y += 4) {
             const float fy = fmaxf(sy * (y + 0.5f) - 0.5f, 0.f);
             const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, gh - 1);
             const float ly = fy - y0, hy = 1.f - ly;
-            float o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float fx = fmaxf(sx * (x4 + j + 0.5f) - 0.5f, 0.f);
-                const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, gw - 1);
-                const float lx = fx - x0, hx = 1.f - lx;
-                o[j] = hy * (hx * c[y0 * gw + x0] + lx * c[y0 * gw + x1]) + ly * (hx * c[y1 * gw + x0] + lx * c[y1 * gw + x1]);
+            const float4* r0 = reinterpret_cast<const float4*>(hrow + (y0 - r_first) * W);
+            const float4* r1 = reinterpret_cast<const float4*>(hrow + (y1 - r_first) * W);
+            for (int cg = tx; cg < W4; cg += 64) {
+                const float4 a = r0[cg], bq = r1[cg];
+                __stcs(reinterpret_cast<float4*>(out + static_cast<int64_t>(y) * W) + cg,
+                       make_float4(hy * a.x + ly * bq.x, hy * a.y + ly * bq.y, hy * a.z + ly * bq.z, hy * a.w + ly * bq.w));
             }
-            __stcs(reinterpret_cast<float4*>(out + static_cast<int64_t>(y) * W + x4), make_float4(o[0], o[1], o[2], o[3]));
         }
     } else {
         for (int idx = y_begin * W + threadIdx.x; idx < y_end * W; idx += blockDim.x) {
-            const int y = idx / W, x = idx % W;
+            const int y = idx / W, x = idx - y * W;
             const float fy = fmaxf(sy * (y + 0.5f) - 0.5f, 0.f);
             const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, gh - 1);
             const float ly = fy - y0, hy = 1.f - ly;
-            const float fx = fmaxf(sx * (x + 0.5f) - 0.5f, 0.f);
-            const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, gw - 1);
-            const float lx = fx - x0, hx = 1.f - lx;
-            out[idx] = hy * (hx * c[y0 * gw + x0] + lx * c[y0 * gw + x1]) + ly * (hx * c[y1 * gw + x0] + lx * c[y1 * gw + x1]);
+            out[idx] = hy * hrow[(y0 - r_first) * W + x] + ly * hrow[(y1 - r_first) * W + x];
         }
     }
 }
@@ -959,19 +973,22 @@ int launch_saliency_combine(const float* plane_cls, const float* slice_cls, int 
                             int gw, int tta, float* attn_maps, float* plane_attn, float* slice_attn, float* coarse, cudaStream_t stream) {
     const int P = gh * gw, BD = B * D;
     MST_REQUIRE(!tta || (attn_maps == nullptr && plane_attn == nullptr), "saliency: the per-head maps are per variant; with tta only coarse / slice_attn");
-    saliency_combine_kernel<<<BD, 256, (2 * P + 48) * sizeof(float), stream>>>(plane_cls, slice_cls, B, D, heads, slice_heads, gh, gw, skip,
+    MST_REQUIRE(heads <= 32 && slice_heads <= 32, "saliency: at most 32 heads");
+    saliency_combine_kernel<<<BD, 256, (2 * P + 64) * sizeof(float), stream>>>(plane_cls, slice_cls, B, D, heads, slice_heads, gh, gw, skip,
                                                                               tta ? 8 : 1, attn_maps, plane_attn, slice_attn, coarse);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 int launch_saliency_upsample(const float* coarse, float* full, int B, int D, int gh, int gw, int H, int W, cudaStream_t stream) {
-    const int P = gh * gw, BD = B * D;
-    {
-        const int rows_per_cta = 32;
-        dim3 grid(BD, (H + rows_per_cta - 1) / rows_per_cta);
-        saliency_upsample_kernel<<<grid, 256, P * sizeof(float), stream>>>(coarse, full, gh, gw, H, W, rows_per_cta);
-        MST_CHECK_CUDA(cudaGetLastError());
-    }
+    const int BD = B * D;
+    // coarse rows one block of UP_ROWS output rows can touch: its span in coarse coordinates, plus the y1 = y0 + 1 neighbour
+    const int crow_max = static_cast<int>(static_cast<double>(UP_ROWS) * gh / H) + 3;
+    const size_t smem = static_cast<size_t>(crow_max) * W * sizeof(float);
+    MST_REQUIRE(smem <= 200 * 1024, "saliency upsample: %d x %d output rows need %zu bytes of shared memory", crow_max, W, smem);
+    MST_SET_DYN_SMEM(saliency_upsample_kernel, 200 * 1024);
+    dim3 grid(BD, (H + UP_ROWS - 1) / UP_ROWS);
+    saliency_upsample_kernel<<<grid, 256, smem, stream>>>(coarse, full, gh, gw, H, W, crow_max);
+    MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -194,6 +194,11 @@ class DinoV2ClassifierSlice(nn.Module):
         # waves (8 volumes = 514 m-tiles = 3.5 waves of 148 SMs cost 13 % in wave quantisation; 32 volumes cost 1.5 %).
         # (profiles/e2e_schedule.py, 64 volumes: (4,12,48) 31.6 ms, (4,12,16,32) 32.6, (8,24,32) 31.9, device-resident 28.7)
         self.h2d_chunk_volumes = (4, 12, 48)   # then the last size repeats; an int = fixed chunk size; 0/None = off
+        # Forwards of at most this many slices (B*D, x8 with TTA) are launch-bound (one volume = 77 kernels of ~10 us): they run
+        # from persistent input / output buffers so that the C library can replay them as one CUDA graph
+        # (mst_set_graph_threshold); results are returned as copies.  0 = always launch eagerly.
+        self.graph_max_slices = 256
+        self._static = {}
         self._last = None
         self._last_inputs = None
         self.register_load_state_dict_post_hook(lambda m, k: setattr(m, "_dirty", True))
@@ -294,6 +299,7 @@ class DinoV2ClassifierSlice(nn.Module):
             h = _cabi.ctypes.c_void_p()
             _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))
             self._handle, self._handle_key = h, key
+            self._static = {}
         with torch.cuda.device(dev):
             stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             keep = []
@@ -353,19 +359,41 @@ class DinoV2ClassifierSlice(nn.Module):
                 left -= c
                 i += 1
         chunk = max(chunks)
+        want_enc = bool(kwargs.get("return_enc_cls", False))
+        small = bool(self.graph_max_slices) and V * B * D <= self.graph_max_slices and full_maps is None
         with torch.cuda.device(dev):
-            logits = torch.empty((V * B, self.out_ch), device=dev, dtype=torch.float32) if self.enable_linear else None
-            feat = torch.empty((V * B, feat_dim), device=dev, dtype=torch.float32)
-            plane = torch.empty((V * B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None
-            slc = torch.empty((V * B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None
+            need = _cabi.ctypes.c_size_t()
             if full_maps is not None:
                 chunks, chunk = [B], B   # full maps are written for the whole batch in one call
-            enc = torch.empty((V * B * D, E), device=dev, dtype=torch.float32) if kwargs.get("return_enc_cls", False) else None
-            need = _cabi.ctypes.c_size_t()
             _cabi.check(L.mst_workspace_bytes(self._handle, V * chunk, D, H, W, _cabi.ctypes.byref(need)))
             if self._workspace is None or self._workspace.numel() < need.value or self._workspace.device != dev:
                 self._workspace = None
+                self._static = {}
                 self._workspace = torch.empty(need.value, device=dev, dtype=torch.uint8)
+                _cabi.check(L.mst_set_graph_threshold(self._handle, int(self.graph_max_slices or 0) * 400))
+
+            def outputs():
+                return (torch.empty((V * B, self.out_ch), device=dev, dtype=torch.float32) if self.enable_linear else None,
+                        torch.empty((V * B, feat_dim), device=dev, dtype=torch.float32),
+                        torch.empty((V * B * D, heads, N), device=dev, dtype=torch.float32) if save_attn else None,
+                        torch.empty((V * B, synth.SLICE_HEADS, D + 1), device=dev, dtype=torch.float32) if save_attn else None,
+                        torch.empty((V * B * D, E), device=dev, dtype=torch.float32) if want_enc else None)
+            io = None
+            if small:   # persistent buffers: the same argument tuple every call, so the library replays a captured graph
+                skey = (B, D, H, W, bool(save_attn), src_dt, tta, want_enc, mask is not None)
+                io = self._static.get(skey)
+                if io is None:
+                    if len(self._static) >= 8:
+                        self._static.pop(next(iter(self._static)))
+                    io = {"x": torch.empty((B, 1, D, H, W), device=dev, dtype=src_dt), "out": outputs(),
+                          "mask": torch.empty((B, D), device=dev, dtype=torch.uint8) if mask is not None else None}
+                    self._static[skey] = io
+                logits, feat, plane, slc, enc = io["out"]
+                if mask is not None:
+                    io["mask"].copy_(mask)
+                    mask = io["mask"]
+            else:
+                logits, feat, plane, slc, enc = outputs()
             cur = torch.cuda.current_stream()
             stream = _cabi.ctypes.c_void_p(cur.cuda_stream)
 
@@ -378,7 +406,12 @@ class DinoV2ClassifierSlice(nn.Module):
                                           _cabi.ptr(sl(plane, D)), _cabi.ptr(sl(slc, 1)), _cabi.ptr(full_maps),
                                           _cabi.ptr(self._workspace), self._workspace.numel(), stream))
 
-            if len(chunks) == 1:
+            if io is not None:
+                io["x"].copy_(source.reshape(B, 1, D, H, W), non_blocking=True)   # H2D (or D2D) + dtype conversion in one copy
+                run(io["x"], 0, B)
+                # the persistent buffers are overwritten by the next forward of this shape: hand out copies
+                logits, feat, plane, slc, enc = (None if t is None else t.clone() for t in (logits, feat, plane, slc, enc))
+            elif len(chunks) == 1:
                 x = source.to(dev).to(src_dt).contiguous()
                 run(x, 0, B)
             else:
@@ -419,8 +452,12 @@ class DinoV2ClassifierSlice(nn.Module):
 
     # -- instrumentation ------------------------------------------------------------------------------------
     def launch_count(self):
-        """CUDA kernels launched by this model's handle so far."""
+        """CUDA kernels launched by this model's handle so far (kernels inside a replayed CUDA graph are counted)."""
         return int(_cabi.lib().mst_launch_count(self._handle)) if self._handle is not None else 0
+
+    def graph_replays(self):
+        """Forwards that ran as a replayed CUDA graph (small batches, see graph_max_slices)."""
+        return int(_cabi.lib().mst_graph_replays(self._handle)) if self._handle is not None else 0
 
     def profile_begin(self):
         if self._dirty or self._handle is None:

@@ -301,9 +301,11 @@ def test_ln_fold_packing_keeps_rows_centred_after_bf16_rounding(N, K):
     torch.cuda.synchronize()
     Wg = W0 * gamma
     Wc = Wg - Wg.mean(-1, keepdim=True)
-    ulp = 2.0 ** (torch.floor(torch.log2(Wc.abs().clamp_min(1e-30))) - 7)
-    assert bool(((Wd.float() - Wc).abs() <= 1.01 * ulp).all())                       # at most one bf16 step from the exact value
-    assert ((Wd.float() - Wc).abs() > 0.51 * ulp).float().mean().item() < 0.08        # ... and that only for a few elements per row
+    ulp = 2.0 ** (torch.floor(torch.log2(torch.maximum(Wc.abs(), Wd.float().abs()).clamp_min(1e-30))) - 7)
+    # a moved element sits one bf16 step from its rounding: at most 1.5 of its own steps from the exact value (half a step
+    # of rounding plus the move), and only a few elements per row are moved
+    assert bool(((Wd.float() - Wc).abs() <= 1.51 * ulp).all())
+    assert ((Wd.float() - Wc).abs() > 0.51 * ulp).float().mean().item() < 0.08
     rowsum = Wd.double().sum(-1).abs()
     plain = Wc.bfloat16().double().sum(-1).abs()
     assert rowsum.max().item() <= 2e-6, rowsum.max().item()                          # independent roundings leave ~7e-4 (K = 384)

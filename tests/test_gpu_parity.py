@@ -370,3 +370,34 @@ def test_second_device_in_one_process():
             ys.append(m(x, save_attn=True).cpu())
             m.saliency_volume()
     assert torch.equal(ys[0], ys[1])
+
+
+def test_small_batches_replay_a_cuda_graph_with_identical_results():
+    """One-volume forwards (the reference's predict loop, main_predict.py:208) are launch-bound: from the third call on they run as
+    a replayed CUDA graph out of persistent buffers.  Same bits as the eager path, fresh output tensors every call, inputs and
+    masks picked up call by call."""
+    from new_vit_b200 import synth
+    B, D, H, W = 1, 8, 224, 224
+    sd = synth.make_state_dict("s", 2, seed=51, variant="peaky")
+    xs = [synth.make_volume(B, D, H, W, seed=60 + i) for i in range(4)]
+    mask = torch.zeros(B, D, dtype=torch.bool)
+    mask[0, 6:] = True
+    m = _model(sd, "bf16", H)
+    eager = _model(sd, "bf16", H)
+    eager.graph_max_slices = 0
+    outs = []
+    with torch.no_grad():
+        for i in range(4):
+            y = m(xs[i].cuda(), save_attn=True, src_key_padding_mask=mask if i % 2 else None)
+            outs.append((y, m.attention_maps[-1], m.get_attention_maps()))
+        assert m.graph_replays() >= 1                      # calls with the same mask-ness share a captured graph
+        for i in range(4):
+            ye = eager(xs[i].cuda(), save_attn=True, src_key_padding_mask=mask if i % 2 else None)
+            assert torch.equal(outs[i][0], ye), i          # earlier results were not overwritten by later forwards
+            assert torch.equal(outs[i][1], eager.attention_maps[-1])
+            assert torch.equal(outs[i][2], eager.get_attention_maps())
+        assert eager.graph_replays() == 0
+        # host input through the same persistent buffer
+        for _ in range(3):
+            yh = m(xs[0], src_key_padding_mask=None)
+        assert torch.equal(yh, eager(xs[0].cuda()))
