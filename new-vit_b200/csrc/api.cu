@@ -193,6 +193,8 @@ struct mst_handle_s {
     std::vector<mst::GraphEntry> graphs;
     unsigned long long graph_clock = 0, graph_replays = 0;
     long long graph_max_tokens = 0;             // 0 = CUDA graphs off (mst_set_graph_threshold)
+    cudaStream_t cap_stream = nullptr;          // capture happens here (the caller's stream may be the legacy default stream, which
+                                                // cannot be captured); the instantiated graph is launched into the caller's stream
     mst_config cfg;
     int num_sms = 0;
     bool finalized = false;
@@ -521,7 +523,21 @@ static int forward_t(mst_handle h, const void* src, int src_dtype, int B, int D,
             stats_from_fc2 = false;
             EpiParams ep{};
             ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = ws.qkv; ep.ldo = 3 * E;
-            MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
+            // ViT-S: 1152 features = 4.5 pairs of 128.  The first 1024 run on the weights-in-TMEM kernel (whole cta_group::2 pairs,
+            // sixteen epilogue warps), the last 128 (the tail of V) on the streaming 128-wide tile kernel: two launches, the
+            // second one HBM-bound (it re-reads the rows), together faster than one launch of the weights-in-smem kernel.
+            // (Small batches keep the single launch: below ~150 m-tiles both halves are latency, not throughput.)
+            static const int qkv_split = exp_env("MST_QKV_SPLIT", 1);
+            if (qkv_split && sizeof(T) == 2 && E == 384 && gemm_wt_enabled() && M >= 32768) {
+                MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 1024, E, EPI_LN_BIAS, ep, st));
+                EpiParams ep2 = ep;
+                ep2.bias = L.bqkv + 1024;
+                ep2.out = static_cast<T*>(ws.qkv) + 1024;
+                MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, static_cast<const T*>(L.wqkv) + static_cast<size_t>(1024) * E, M, 128, E,
+                                                      EPI_LN_BIAS, ep2, st));
+            } else {
+                MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
+            }
         } else {
             MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n1w, L.n1b, M, E, 1e-6f, st)));
             EpiParams ep{};
@@ -662,6 +678,7 @@ int mst_destroy(mst_handle h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     drop_graphs(h);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (auto& kv : h->master) cudaFree(kv.second);
     for (void* p : h->owned) cudaFree(p);
     for (auto& kv : h->pos_cache) cudaFree(kv.second);
@@ -744,11 +761,13 @@ int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int
     MST_REQUIRE(ws.total <= workspace_bytes, "mst_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
     MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    auto run = [&]() -> int {
+    auto run_on = [&](cudaStream_t s_) -> int {
         if (h->cfg.precision == MST_PRECISION_BF16)
-            return forward_t<bf16>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
-        return forward_t<float>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, st);
+            return forward_t<bf16>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, s_);
+        return forward_t<float>(h, src, src_dtype, B, D, H, W, pad_mask, tta, logits, feat, enc_cls, plane_cls, slice_cls, full_maps, ws, s_);
     };
+    auto run = [&]() -> int { return run_on(st); };
+    set_pdl(h->graph_max_tokens > 0 && static_cast<long long>(B) * D * ((H / 14) * (W / 14) + 1 + h->cfg.num_registers) <= h->graph_max_tokens);
     // ---- CUDA graph replay for small batches (launch-bound: the kernels of a one-volume forward take less time than issuing them) ----
     const long long tokens = static_cast<long long>(B) * D * ((H / 14) * (W / 14) + 1 + h->cfg.num_registers);
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -783,10 +802,11 @@ int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int
     }
     // second sight: capture.  (The position table of this grid and every per-device kernel attribute were set up by the eager run.)
     const unsigned long long l0 = h->launches;
-    MST_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    const int rc = run();
+    if (!h->cap_stream) MST_CHECK_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    MST_CHECK_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = run_on(h->cap_stream);
     cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
     if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();

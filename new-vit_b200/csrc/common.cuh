@@ -169,7 +169,8 @@ int make_tma_3d_bf16(TmaDesc* out, const void* base, uint64_t d0, uint64_t d1, u
 struct EpiParams;
 bool gemm_wt_supported(int M, int N, int K, int mode, const EpiParams& ep);
 bool gemm_wt_enabled();   // MST_GEMM_WT != 0
-bool pdl_enabled();       // MST_PDL != 0: GEMM / attention kernels are launched as programmatic dependents (ptx.cuh)
+bool pdl_enabled();       // GEMM / attention kernels are launched as programmatic dependents (ptx.cuh): small batches only
+void set_pdl(bool on);
 int gemm_bf16_wt(const bf16* A, const bf16* W, int M, int N, int K, int mode, const EpiParams& ep, int num_sms,
                  cudaStream_t stream);
 

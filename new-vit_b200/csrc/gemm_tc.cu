@@ -700,9 +700,15 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
     return 0;
 }
 
+// Programmatic dependent launch of the tcgen05 kernels (ptx.cuh: every kernel of the encoder calls griddepcontrol.wait before it
+// touches data): on for launch-bound small batches, where a kernel's prologue (barrier init, TMEM allocation, descriptor
+// prefetch, the resident weight block) is a visible share of its ~10 us and can overlap the tail of the kernel in front; off for
+// large batches (measured flat under the power cap).  Set per forward by mst_forward.
+static thread_local bool g_pdl = false;
+void set_pdl(bool on) { g_pdl = on; }
 bool pdl_enabled() {
-    static const int pdl = exp_env("MST_PDL", 0);
-    return pdl != 0;
+    static const int pdl = exp_env("MST_PDL", -1);   // experiments: force on (1) / off (0)
+    return pdl >= 0 ? pdl != 0 : g_pdl;
 }
 
 bool gemm_wt_enabled() {

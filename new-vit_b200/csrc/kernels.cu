@@ -600,7 +600,7 @@ __device__ __forceinline__ void block_matvec(const float* in, const float* __res
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(384) slice_fusion_kernel(const float* __restrict__ enc_cls, const uint8_t* __restrict__ pad_mask,
+__global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restrict__ enc_cls, const uint8_t* __restrict__ pad_mask,
                                                             SliceWeights w, float* __restrict__ hs_all, float* __restrict__ logits,
                                                             float* __restrict__ feat, float* __restrict__ slice_cls, int D, int Eenc,
                                                             int E, int heads, int out_ch, int mode, int mask_period) {
@@ -837,7 +837,10 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
                          (w.rope_freqs ? static_cast<size_t>(L) * E : 0)) * sizeof(float);
     MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
     MST_SET_DYN_SMEM(slice_fusion_kernel, 227 * 1024);
-    slice_fusion_kernel<<<B, 384, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,
+    // one CTA per volume; few volumes (the predict loop's batch of one): twice the threads, every phase of the kernel is a
+    // blockDim-strided loop whose time is load latency over loads in flight
+    const int threads = B <= 74 ? 768 : 384;
+    slice_fusion_kernel<<<B, threads, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,
                                                   out_ch, mode, mask_period);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -920,22 +923,20 @@ __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __re
 
 // x(H/gh) bilinear upsample, align_corners=False (== F.interpolate 'trilinear' with depth scale 1, main_predict.py:161-162):
 //   out[y, x] = hy * (hx * c[y0, x0] + lx * c[y0, x1]) + ly * (hx * c[y1, x0] + lx * c[y1, x1])
-// One CTA = one slice x UP_ROWS output rows.  The horizontal blends hrow[r][x] = hx * c[r, x0] + lx * c[r, x1] of the few
-// coarse rows the block touches are built once in shared memory; every output is then two shared-memory values and one
-// FMUL + FMA, written as 16-byte streaming stores (this is the bandwidth-bound step of the saliency path: 6.4 MB per volume).
-constexpr int UP_ROWS = 56;
+// One CTA = one slice (or one of `chunks` contiguous pieces of it when there are few slices).  The horizontal blends
+// hrow[r][x] = hx * c[r, x0] + lx * c[r, x1] of all coarse rows are built once in shared memory; every output is then two
+// shared-memory values, one FMUL and one FMA, and the slice is written as ONE flat run of 16-byte streaming stores (thread i ->
+// float4 i, i + 256, ...: every warp instruction covers 512 contiguous bytes).  This is the bandwidth-bound step of the saliency
+// path (6.4 MB per volume): 6.8 TB/s on a 256-volume batch, against 7.0-7.3 TB/s for a plain fill / cudaMemset
+// (profiles/micro/upsample_bw.cu; a row-blocked layout with 56 of 64 lanes active reached 4.4 TB/s).
 __global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __restrict__ coarse, float* __restrict__ full,
-                                                                 int gh, int gw, int H, int W, int crow_max) {
-    extern __shared__ float hrow[];  // [crow_max][W]
+                                                                 int gh, int gw, int H, int W, int chunks) {
+    extern __shared__ float hrow[];  // [gh][W]
     const int s = blockIdx.x;
-    const int y_begin = blockIdx.y * UP_ROWS;
-    const int y_end = min(H, y_begin + UP_ROWS);
     const float sy = static_cast<float>(gh) / static_cast<float>(H), sx = static_cast<float>(gw) / static_cast<float>(W);
-    const int r_first = static_cast<int>(fmaxf(sy * (y_begin + 0.5f) - 0.5f, 0.f));   // first coarse row this block reads
     const float* c = coarse + static_cast<int64_t>(s) * gh * gw;
-    for (int idx = threadIdx.x; idx < crow_max * W; idx += blockDim.x) {
-        const int rr = idx / W, x = idx - rr * W;
-        const int r = min(r_first + rr, gh - 1);
+    for (int idx = threadIdx.x; idx < gh * W; idx += blockDim.x) {
+        const int r = idx / W, x = idx - r * W;
         const float fx = fmaxf(sx * (x + 0.5f) - 0.5f, 0.f);
         const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, gw - 1);
         const float lx = fx - x0, hx = 1.f - lx;
@@ -944,27 +945,27 @@ __global__ void __launch_bounds__(256) saliency_upsample_kernel(const float* __r
     __syncthreads();
     float* out = full + static_cast<int64_t>(s) * H * W;
     if ((W & 3) == 0) {
-        const int W4 = W >> 2;
-        const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 column groups x 4 rows in flight
-        for (int y = y_begin + ty; y < y_end; y += 4) {
+        const int W4 = W >> 2, total = H * W4;
+        const int per = (total + chunks - 1) / chunks;
+        const int i_end = min(total, (static_cast<int>(blockIdx.y) + 1) * per);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        for (int i = blockIdx.y * per + threadIdx.x; i < i_end; i += blockDim.x) {
+            const int y = i / W4, cg = i - y * W4;
             const float fy = fmaxf(sy * (y + 0.5f) - 0.5f, 0.f);
             const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, gh - 1);
             const float ly = fy - y0, hy = 1.f - ly;
-            const float4* r0 = reinterpret_cast<const float4*>(hrow + (y0 - r_first) * W);
-            const float4* r1 = reinterpret_cast<const float4*>(hrow + (y1 - r_first) * W);
-            for (int cg = tx; cg < W4; cg += 64) {
-                const float4 a = r0[cg], bq = r1[cg];
-                __stcs(reinterpret_cast<float4*>(out + static_cast<int64_t>(y) * W) + cg,
-                       make_float4(hy * a.x + ly * bq.x, hy * a.y + ly * bq.y, hy * a.z + ly * bq.z, hy * a.w + ly * bq.w));
-            }
+            const float4 a = reinterpret_cast<const float4*>(hrow + y0 * W)[cg], bq = reinterpret_cast<const float4*>(hrow + y1 * W)[cg];
+            __stcs(out4 + i, make_float4(hy * a.x + ly * bq.x, hy * a.y + ly * bq.y, hy * a.z + ly * bq.z, hy * a.w + ly * bq.w));
         }
     } else {
-        for (int idx = y_begin * W + threadIdx.x; idx < y_end * W; idx += blockDim.x) {
-            const int y = idx / W, x = idx - y * W;
+        const int total = H * W, per = (total + chunks - 1) / chunks;
+        const int i_end = min(total, (static_cast<int>(blockIdx.y) + 1) * per);
+        for (int i = blockIdx.y * per + threadIdx.x; i < i_end; i += blockDim.x) {
+            const int y = i / W, x = i - y * W;
             const float fy = fmaxf(sy * (y + 0.5f) - 0.5f, 0.f);
             const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, gh - 1);
             const float ly = fy - y0, hy = 1.f - ly;
-            out[idx] = hy * hrow[(y0 - r_first) * W + x] + ly * hrow[(y1 - r_first) * W + x];
+            out[i] = hy * hrow[y0 * W + x] + ly * hrow[y1 * W + x];
         }
     }
 }
@@ -981,13 +982,13 @@ int launch_saliency_combine(const float* plane_cls, const float* slice_cls, int 
 }
 int launch_saliency_upsample(const float* coarse, float* full, int B, int D, int gh, int gw, int H, int W, cudaStream_t stream) {
     const int BD = B * D;
-    // coarse rows one block of UP_ROWS output rows can touch: its span in coarse coordinates, plus the y1 = y0 + 1 neighbour
-    const int crow_max = static_cast<int>(static_cast<double>(UP_ROWS) * gh / H) + 3;
-    const size_t smem = static_cast<size_t>(crow_max) * W * sizeof(float);
-    MST_REQUIRE(smem <= 200 * 1024, "saliency upsample: %d x %d output rows need %zu bytes of shared memory", crow_max, W, smem);
+    const size_t smem = static_cast<size_t>(gh) * W * sizeof(float);
+    MST_REQUIRE(smem <= 200 * 1024, "saliency upsample: a %d x %d row table needs %zu bytes of shared memory", gh, W, smem);
     MST_SET_DYN_SMEM(saliency_upsample_kernel, 200 * 1024);
-    dim3 grid(BD, (H + UP_ROWS - 1) / UP_ROWS);
-    saliency_upsample_kernel<<<grid, 256, smem, stream>>>(coarse, full, gh, gw, H, W, crow_max);
+    int chunks = 1;   // few slices (one volume): split every slice so that the grid still covers the GPU twice
+    if (BD < 296) chunks = (296 + BD - 1) / BD;
+    if (chunks > 8) chunks = 8;
+    saliency_upsample_kernel<<<dim3(BD, chunks), 256, smem, stream>>>(coarse, full, gh, gw, H, W, chunks);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -304,8 +304,10 @@ def test_ln_fold_packing_keeps_rows_centred_after_bf16_rounding(N, K):
     ulp = 2.0 ** (torch.floor(torch.log2(torch.maximum(Wc.abs(), Wd.float().abs()).clamp_min(1e-30))) - 7)
     # a moved element sits one bf16 step from its rounding: at most 1.5 of its own steps from the exact value (half a step
     # of rounding plus the move), and only a few elements per row are moved
-    assert bool(((Wd.float() - Wc).abs() <= 1.51 * ulp).all())
-    assert ((Wd.float() - Wc).abs() > 0.51 * ulp).float().mean().item() < 0.08
+    # (+ 1e-8: the kernel's own fp32 evaluation of W * gamma - mean differs from this one by a few 1e-9, which is many ulps of an
+    #  element that happens to be ~1e-7)
+    assert bool(((Wd.float() - Wc).abs() <= 1.51 * ulp + 1e-8).all())
+    assert ((Wd.float() - Wc).abs() > 0.51 * ulp + 1e-8).float().mean().item() < 0.08
     rowsum = Wd.double().sum(-1).abs()
     plain = Wc.bfloat16().double().sum(-1).abs()
     assert rowsum.max().item() <= 2e-6, rowsum.max().item()                          # independent roundings leave ~7e-4 (K = 384)
@@ -319,5 +321,7 @@ def test_ln_fold_packing_keeps_rows_centred_after_bf16_rounding(N, K):
     cabi.check(L.mst_kernel_gemm_bf16_ln(cabi.ptr(x), cabi.ptr(Wd), M, N, K, 0, cabi.ptr(bd), cabi.ptr(stat), cabi.ptr(out), _stream()))
     torch.cuda.synchronize()
     ref = torch.nn.functional.layer_norm(x.float(), (K,), gamma, beta, 1e-6) @ W0.t() + b0
-    # the error budget is the bf16 weight rounding (|LN(x)| ~ 1 over K terms of 2^-9 relative error) + the output rounding
-    torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=4e-3)
+    # the error budget is the bf16 weight rounding (|LN(x)| ~ 1 over K terms of 2^-9 relative error: ~3e-3 at 4.5 sigma) + the
+    # output rounding (4e-3 at |y| ~ 2): 8e-3, the tolerance of the plain GEMM tests.  With independently rounded weight rows the
+    # same rows miss it by 5x (mean(x) * rstd * sum_k Wc[n,k] ~ 20 * 1.6e-3).
+    torch.testing.assert_close(out.float(), ref, rtol=8e-3, atol=8e-3)
