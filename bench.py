@@ -217,6 +217,7 @@ def run_extras(model_s, dev, rank, world, timed, peaks):
         lat_tta = timed(lambda: run_pred(model_s, batch, save_attn=True, use_tta=True), 20)
         lat_sal = timed(lambda: run_pred(model_s, batch, save_attn=True, use_tta=False), 20)
     out["latency_batch1"] = {"workload": "1 volume 32x224x224 per call, device-resident (scripts/main_predict.py:208,288)",
+                             "cuda_graph_replays": model_s.graph_replays(),
                              "forward_ms": lat, "run_pred_saliency_ms": lat_sal, "run_pred_saliency_tta8_ms": lat_tta,
                              "forward_model_tflops": flops_per_volume(32) / lat / 1e9}
     # ---- input pipeline: 64 x (256x256x40 -> 224x224x32), mst_prepare_volume ----

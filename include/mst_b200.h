@@ -154,6 +154,28 @@ MST_API int mst_prepare_volume(mst_handle h /* nullable: instrumentation only */
                        int32_t D, int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* Training step on a FROZEN encoder (BASELINE.json config 5, `freeze=True`, reference dino.py:69-71; Lightning's step is
+ * base_model.py:148-170: forward -> CrossEntropyLoss -> backward -> AdamW, base_model.py:103-110 / dino.py:41).  What trains is the
+ * slice transformer + head of dino.py:84-103 (default construction: no bottleneck, no slice position embedding, no rotary).
+ *   enc     [B, D, E] fp32: the encoder's per-slice output (mst_forward's enc_cls), no gradient
+ *   params  HOST array of 17 DEVICE pointers, fp32, nn.Linear layout, in this order: cls_token, slice_fusion.layers.0.norm1.weight,
+ *           .norm1.bias, .self_attn.in_proj_weight, .self_attn.in_proj_bias, .self_attn.out_proj.weight, .self_attn.out_proj.bias,
+ *           .norm2.weight, .norm2.bias, .linear1.weight, .linear1.bias, .linear2.weight, .linear2.bias, slice_fusion.norm.weight,
+ *           slice_fusion.norm.bias, linear.weight, linear.bias
+ *   saved / factors  scratch of mst_slice_train_bytes: activations kept from forward to backward / per-volume backward factors
+ *   logits  [B, C];  dlogits [B, C] = d loss / d logits (the caller's loss);  grads: 17 device pointers shaped like params, overwritten
+ *   denc    nullable [B, D, E]: gradient w.r.t. the encoder outputs (what an un-frozen encoder's backward would consume)
+ * mst_adamw: torch.optim.AdamW's update on one flat buffer (n floats): g is multiplied by grad_scale first (1/world after a summing
+ * all-reduce), step counts from 1. */
+MST_API int mst_slice_train_bytes(int32_t B, int32_t D, int32_t E, int32_t heads, int32_t C, size_t* saved_bytes, size_t* factor_bytes);
+MST_API int mst_slice_train_forward(mst_handle h /* nullable */, const float* enc, const uint8_t* pad_mask, const float* const* params,
+                            int32_t B, int32_t D, int32_t E, int32_t heads, int32_t C, float* saved, float* logits, void* stream);
+MST_API int mst_slice_train_backward(mst_handle h /* nullable */, const float* enc, const float* dlogits, const float* const* params,
+                             const float* saved, float* factors, float* const* grads, float* denc, int32_t B, int32_t D, int32_t E,
+                             int32_t heads, int32_t C, void* stream);
+MST_API int mst_adamw(mst_handle h /* nullable */, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+              float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
+
 /* Instrumentation: kernels launched by this handle so far; per-category device time (CUDA events recorded on the
  * caller's stream around every launch between begin and end; end synchronises the device).  `ms`/`launches` must
  * hold at least 16 entries; mst_profile_categories() names them, comma separated, in order. */

@@ -74,6 +74,11 @@ def lib():
     L.mst_kernel_attention_bf16_warp_mma.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_attention_f32.argtypes = [vp, vp, i32, i32, i32, vp]
     L.mst_kernel_layernorm_bf16.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
+    fl = ctypes.c_float
+    L.mst_slice_train_bytes.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(sz), ctypes.POINTER(sz)]
+    L.mst_slice_train_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.mst_slice_train_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    L.mst_adamw.argtypes = [vp, vp, vp, vp, vp, i64, fl, fl, fl, fl, fl, i32, fl, vp]
     L.mst_profile_begin.argtypes = [vp]
     L.mst_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.mst_launch_count.argtypes = [vp]

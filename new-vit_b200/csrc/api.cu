@@ -150,8 +150,8 @@ struct Layer {
 namespace mst {
 enum Cat { CAT_IM2COL = 0, CAT_GEMM_PATCH, CAT_LAYERNORM, CAT_GEMM_QKV, CAT_ATTENTION, CAT_GEMM_PROJ, CAT_GEMM_FC1,
            CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, CAT_FULL_MAPS, CAT_SALIENCY_COMBINE,
-           CAT_SALIENCY_UPSAMPLE, CAT_PREPARE_VOLUME, NUM_CAT };
-static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps,saliency_combine,saliency_upsample,prepare_volume";
+           CAT_SALIENCY_UPSAMPLE, CAT_PREPARE_VOLUME, CAT_TRAIN_FORWARD, CAT_TRAIN_BACKWARD, CAT_ADAMW, NUM_CAT };
+static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps,saliency_combine,saliency_upsample,prepare_volume,train_slice_forward,train_slice_backward,adamw";
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> pool;
@@ -912,6 +912,47 @@ int mst_prepare_volume(mst_handle h, const float* src, int32_t items, int32_t W0
     if (!h) h = &none;
     MST_LAUNCH(CAT_PREPARE_VOLUME, launch_prepare_volume(src, items, W0, H0, D0, W, H, D, flip_h, q_lo, q_hi, out, stats, workspace, sms, st));
     h->launches += launch_prepare_volume_count(W0, H0, D0, W, H, D) - 1;   // the chain is several kernels, timed as one category
+    return 0;
+}
+
+int mst_slice_train_bytes(int32_t B, int32_t D, int32_t E, int32_t heads, int32_t C, size_t* saved_bytes, size_t* factor_bytes) {
+    MST_REQUIRE(saved_bytes && factor_bytes && B >= 1 && D >= 1 && E >= 1 && heads >= 1 && C >= 1, "mst_slice_train_bytes: bad argument");
+    *saved_bytes = slice_train_saved_bytes(B, D, E, heads);
+    *factor_bytes = slice_train_factor_bytes(B, E, heads, C);
+    return 0;
+}
+int mst_slice_train_forward(mst_handle h, const float* enc, const uint8_t* pad_mask, const float* const* params, int32_t B, int32_t D,
+                            int32_t E, int32_t heads, int32_t C, float* saved, float* logits, void* stream) {
+    MST_REQUIRE(enc && params && saved && logits && B >= 1 && D >= 1, "mst_slice_train_forward: bad argument");
+    for (int i = 0; i < 17; ++i) MST_REQUIRE(params[i] != nullptr, "mst_slice_train_forward: parameter %d is null", i);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    mst_handle_s none;
+    if (!h) h = &none;
+    MST_LAUNCH(CAT_TRAIN_FORWARD, launch_slice_train_forward(enc, pad_mask, params, saved, logits, B, D, E, heads, C, st));
+    return 0;
+}
+int mst_slice_train_backward(mst_handle h, const float* enc, const float* dlogits, const float* const* params, const float* saved,
+                             float* factors, float* const* grads, float* denc, int32_t B, int32_t D, int32_t E, int32_t heads, int32_t C,
+                             void* stream) {
+    MST_REQUIRE(enc && dlogits && params && saved && factors && grads && B >= 1 && D >= 1, "mst_slice_train_backward: bad argument");
+    for (int i = 0; i < 17; ++i) MST_REQUIRE(params[i] != nullptr && grads[i] != nullptr, "mst_slice_train_backward: tensor %d is null", i);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    mst_handle_s none;
+    if (!h) h = &none;
+    MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_slice_train_backward(enc, dlogits, params, saved, factors, grads, denc, B, D, E, heads, C, st));
+    h->launches += 1;   // kernel A (per volume) + kernel B (per weight row)
+    return 0;
+}
+int mst_adamw(mst_handle h, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+              float weight_decay, int32_t step, float grad_scale, void* stream) {
+    MST_REQUIRE(p && g && m && v, "mst_adamw: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    mst_handle_s none;
+    if (!h) h = &none;
+    int dev = 0, sms = 0;
+    MST_CHECK_CUDA(cudaGetDevice(&dev));
+    MST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    MST_LAUNCH(CAT_ADAMW, launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, sms, st));
     return 0;
 }
 

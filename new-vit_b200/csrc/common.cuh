@@ -235,4 +235,17 @@ int launch_prepare_volume_count(int W0, int H0, int D0, int W, int H, int D);
 int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, int W, int H, int D, int flip_h, float q_lo,
                           float q_hi, float* out, double* stats, void* workspace, int num_sms, cudaStream_t stream);
 
+// ---- training step of the slice transformer + head on a frozen encoder (train.cu; BASELINE config 5, frozen-encoder slice) ----
+// params / grads: 17 device pointers in this order: cls_token, norm1.weight, norm1.bias, in_proj_weight, in_proj_bias,
+// out_proj.weight, out_proj.bias, norm2.weight, norm2.bias, linear1.weight, linear1.bias, linear2.weight, linear2.bias,
+// slice_fusion.norm.weight, slice_fusion.norm.bias, linear.weight, linear.bias (nn.Linear layout, fp32)
+size_t slice_train_saved_bytes(int B, int D, int E, int heads);
+size_t slice_train_factor_bytes(int B, int E, int heads, int C);
+int launch_slice_train_forward(const float* enc, const uint8_t* pad_mask, const float* const* params, float* saved, float* logits,
+                               int B, int D, int E, int heads, int C, cudaStream_t stream);
+int launch_slice_train_backward(const float* enc, const float* dlogits, const float* const* params, const float* saved, float* factors,
+                                float* const* grads, float* denc, int B, int D, int E, int heads, int C, cudaStream_t stream);
+int launch_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int step,
+                 float grad_scale, int num_sms, cudaStream_t stream);
+
 }  // namespace mst

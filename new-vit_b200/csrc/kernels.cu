@@ -578,21 +578,48 @@ __device__ __forceinline__ void block_layernorm(const float* in, float* out, con
     for (int i = threadIdx.x; i < E; i += blockDim.x) out[i] = fmaf((in[i] - mean) * rstd, g[i], b[i]);
     __syncthreads();
 }
-// out[n] = act(sum_k in[k] * Wt[k*ldw + n] + bias[n]) (+ res[n]);  in/out in shared memory
-__device__ __forceinline__ void block_matvec(const float* in, const float* __restrict__ Wt, int ldw, const float* __restrict__ bias,
-                                             const float* res, float* out, int K, int Nout, bool relu, float scale) {
-    for (int n = threadIdx.x; n < Nout; n += blockDim.x) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // four chains, eight loads in flight: the loop is L2-latency-bound
+// out[n] = act((sum_k in_n[k] * Wt[k*ldw + n] + bias[n]) * scale) (+ res[n]);  in / out / scr in shared memory.
+// in_n = in + (n / in_group) * in_stride  (in_group = Nout: one input vector; in_group = head_dim: one input row per head).
+// A matrix-vector product on ONE SM is bound by load latency over loads in flight, so the K range is split MV_PARTS ways across
+// the CTA and every thread streams float4 weight columns with eight independent 16-byte loads in flight; the MV_PARTS partials
+// are summed in a fixed order (results do not depend on the launch shape).  Nout % 4 == 0, ldw % 4 == 0, K % MV_PARTS == 0.
+constexpr int MV_PARTS = 8;
+__device__ __forceinline__ void block_matvec(const float* in, int in_group, int in_stride, const float* __restrict__ Wt, int ldw,
+                                             const float* __restrict__ bias, const float* res, float* out, float* scr, int K, int Nout,
+                                             bool relu, float scale) {
+    const int groups = Nout >> 2, kper = K / MV_PARTS;
+    for (int task = threadIdx.x; task < groups * MV_PARTS; task += blockDim.x) {
+        const int g = task % groups, part = task / groups;
+        const int n = g << 2;
+        const float* x = in + (n / in_group) * in_stride + part * kper;
+        const float4* wp = reinterpret_cast<const float4*>(Wt + static_cast<int64_t>(part) * kper * ldw + n);
+        const int64_t step = ldw >> 2;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = 0;
-#pragma unroll 2
-        for (; k + 3 < K; k += 4) {
-            a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
-            a1 = fmaf(in[k + 1], __ldg(Wt + static_cast<int64_t>(k + 1) * ldw + n), a1);
-            a2 = fmaf(in[k + 2], __ldg(Wt + static_cast<int64_t>(k + 2) * ldw + n), a2);
-            a3 = fmaf(in[k + 3], __ldg(Wt + static_cast<int64_t>(k + 3) * ldw + n), a3);
+        for (; k + 7 < kper; k += 8) {
+            float4 wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = __ldg(wp + (k + u) * step);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float xv = x[k + u];
+                acc.x = fmaf(xv, wv[u].x, acc.x); acc.y = fmaf(xv, wv[u].y, acc.y);
+                acc.z = fmaf(xv, wv[u].z, acc.z); acc.w = fmaf(xv, wv[u].w, acc.w);
+            }
         }
-        for (; k < K; ++k) a0 = fmaf(in[k], __ldg(Wt + static_cast<int64_t>(k) * ldw + n), a0);
-        float v = ((a0 + a1) + (a2 + a3) + bias[n]) * scale;
+        for (; k < kper; ++k) {
+            const float4 w1 = __ldg(wp + k * step);
+            const float xv = x[k];
+            acc.x = fmaf(xv, w1.x, acc.x); acc.y = fmaf(xv, w1.y, acc.y); acc.z = fmaf(xv, w1.z, acc.z); acc.w = fmaf(xv, w1.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(scr + part * Nout + n) = acc;
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < Nout; n += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int p = 0; p < MV_PARTS; ++p) a += scr[p * Nout + n];
+        float v = (a + bias[n]) * scale;
         if (relu) v = fmaxf(v, 0.f);
         if (res) v += res[n];
         out[n] = v;
@@ -616,7 +643,8 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
     float* t2 = t1 + E;             // [E]
     float* cterm = t2 + E;          // [heads] (padded to 32)
     float* red = cterm + 32;        // [40]
-    float* p = red + 40;            // [heads][L]
+    float* scr = red + 40;          // [MV_PARTS][E] partial sums of the split-K matrix-vector products
+    float* p = scr + MV_PARTS * E;  // [heads][L]
     float* kmat = p + ((heads * L + 3) & ~3);   // [L][E] projected keys, RoPE only
     const int b = blockIdx.x;
     // TTA: the 8 flipped variants of a volume all get the volume's UN-flipped padding mask (main_predict.py:149)
@@ -694,7 +722,7 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
     }
     __syncthreads();
     // 2. q = (Wq n0 + bq) / sqrt(hd)                                    (transformer_blocks.py:166,268)
-    block_matvec(n0, w.in_wt, 3 * E, w.in_b, nullptr, q, E, E, false, rsqrtf(static_cast<float>(hd)));
+    block_matvec(n0, E, 0, w.in_wt, 3 * E, w.in_b, nullptr, q, scr, E, E, false, rsqrtf(static_cast<float>(hd)));
     if (w.rope_freqs) {
         // RoPE (transformer_blocks.py:262-264; rotary_embedding_torch.py:159-173,45-62): the key of sequence position j is
         // rotated by j*freqs[i] in each feature pair (2i, 2i+1) of its head before the dot product, so the keys are
@@ -742,7 +770,8 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
         const int h = idx / E, k = idx % E;
         const float* wr = w.in_w + (static_cast<int64_t>(E) + h * hd) * E + k;
         float a = 0.f;
-        for (int d = 0; d < hd; ++d) a = fmaf(q[h * hd + d], __ldg(wr + static_cast<int64_t>(d) * E), a);
+#pragma unroll 8
+        for (int d = 0; d < hd; ++d) a = fmaf(q[h * hd + d], __ldg(wr + static_cast<int64_t>(d) * E), a);   // hd % 8 == 0
         qk[idx] = a;
     }
     if (threadIdx.x < heads) {
@@ -795,26 +824,13 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
     }
     __syncthreads();
     // 7. o[n] = Wv[n,:] . hbar[head(n)] + bv[n]
-    for (int n = threadIdx.x; n < E; n += blockDim.x) {
-        const float* hb = hbar + (n / hd) * E;
-        const float* wv = w.in_wt + 2 * E + n;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < E; k += 4) {   // E % 4 == 0
-            a0 = fmaf(hb[k], __ldg(wv + static_cast<int64_t>(k) * 3 * E), a0);
-            a1 = fmaf(hb[k + 1], __ldg(wv + static_cast<int64_t>(k + 1) * 3 * E), a1);
-            a2 = fmaf(hb[k + 2], __ldg(wv + static_cast<int64_t>(k + 2) * 3 * E), a2);
-            a3 = fmaf(hb[k + 3], __ldg(wv + static_cast<int64_t>(k + 3) * 3 * E), a3);
-        }
-        t0[n] = ((a0 + a1) + (a2 + a3)) + w.in_b[2 * E + n];
-    }
-    __syncthreads();
+    block_matvec(hbar, hd, E, w.in_wt + 2 * E, 3 * E, w.in_b + 2 * E, nullptr, t0, scr, E, E, false, 1.0f);
     // 8. x1 = x0 + out_proj(o)                                           (transformer_blocks.py:566)
-    block_matvec(t0, w.out_wt, E, w.out_b, x0, t1, E, E, false, 1.0f);
+    block_matvec(t0, E, 0, w.out_wt, E, w.out_b, x0, t1, scr, E, E, false, 1.0f);
     // 9. x2 = x1 + W2 relu(W1 LN2(x1) + b1) + b2                         (transformer_blocks.py:567,585)
     block_layernorm(t1, t0, w.n2w, w.n2b, E, 1e-5f, red);
-    block_matvec(t0, w.l1_wt, E, w.l1_b, nullptr, t2, E, E, true, 1.0f);
-    block_matvec(t2, w.l2_wt, E, w.l2_b, t1, t0, E, E, false, 1.0f);
+    block_matvec(t0, E, 0, w.l1_wt, E, w.l1_b, nullptr, t2, scr, E, E, true, 1.0f);
+    block_matvec(t2, E, 0, w.l2_wt, E, w.l2_b, t1, t0, scr, E, E, false, 1.0f);
     // 10. final LayerNorm (dino.py:95), feature = row 0 (dino.py:153), logits (dino.py:166; nn.Identity if !enable_linear)
     block_layernorm(t0, t1, w.nfw, w.nfb, E, 1e-5f, red);
     if (feat)
@@ -833,14 +849,12 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
                         int mode, int mask_period, cudaStream_t stream) {
     MST_REQUIRE(heads <= 16 && E % heads == 0 && Eenc % 2 == 0, "slice fusion: heads=%d E=%d unsupported", heads, E);
     const int L = D + 1;
-    const size_t smem = (static_cast<size_t>(6) * E + 2 * heads * E + 32 + 40 + ((heads * L + 3) & ~3) +
+    MST_REQUIRE(E % (4 * MV_PARTS) == 0, "slice fusion: slice embedding %d must be a multiple of %d", E, 4 * MV_PARTS);
+    const size_t smem = (static_cast<size_t>(6 + MV_PARTS) * E + 2 * heads * E + 32 + 40 + ((heads * L + 3) & ~3) +
                          (w.rope_freqs ? static_cast<size_t>(L) * E : 0)) * sizeof(float);
     MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
     MST_SET_DYN_SMEM(slice_fusion_kernel, 227 * 1024);
-    // one CTA per volume; few volumes (the predict loop's batch of one): twice the threads, every phase of the kernel is a
-    // blockDim-strided loop whose time is load latency over loads in flight
-    const int threads = B <= 74 ? 768 : 384;
-    slice_fusion_kernel<<<B, threads, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,
+    slice_fusion_kernel<<<B, 768, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,
                                                   out_ch, mode, mask_period);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from new_vit_b200 import _cabi, synth
 from new_vit_b200._cabi import MSTError  # noqa: F401
+from new_vit_b200.training import SLICE_PARAM_NAMES, LightningSurface, SliceHeadFunction
 
 
 # ---- parameter containers that reproduce the reference's module tree (names only; never called) ----
@@ -93,12 +94,23 @@ class _Rotary(nn.Module):
         self.freqs = nn.Parameter(torch.zeros(hd // 2), requires_grad=False)
 
 
+class _Liere(nn.Module):
+    # AttentionLiereRotator(head_dim, liere_block_size=head_dim//2, spacial_dims=1, axes_length=33, num_heads)
+    # (transformer_blocks.py:352-358; rotary_embedding_torch.py:329-344): head_dim / block = 2 trainable generator tables
+    def __init__(self, hd):
+        super().__init__()
+        blk = hd // 2
+        self.vars = nn.ParameterList([nn.Parameter(torch.randn((blk * blk - blk) // 2, 33, 1)) for _ in range(hd // blk)])
+
+
 class _SliceLayer(nn.Module):
-    def __init__(self, E, heads, rope=False):
+    def __init__(self, E, heads, rope=False, liere=False):
         super().__init__()
         self.self_attn = nn.MultiheadAttention(E, heads, dropout=0.0, batch_first=True)
         if rope:
             self.self_attn.rotary_positional_encoding = _Rotary(E // heads)
+        if liere:
+            self.self_attn.rotary_positional_encoding = _Liere(E // heads)
         self.linear1 = nn.Linear(E, E)
         self.linear2 = nn.Linear(E, E)
         self.norm1 = nn.LayerNorm(E)
@@ -106,14 +118,15 @@ class _SliceLayer(nn.Module):
 
 
 class _SliceFusion(nn.Module):
-    def __init__(self, E, heads, rope=False):
+    def __init__(self, E, heads, rope=False, liere=False):
         super().__init__()
-        self.layers = nn.ModuleList([_SliceLayer(E, heads, rope)])
+        self.layers = nn.ModuleList([_SliceLayer(E, heads, rope, liere)])
         self.norm = nn.LayerNorm(E)
 
 
-class DinoV2ClassifierSlice(nn.Module):
-    """Drop-in for reference `mst.models.DinoV2ClassifierSlice` (dino.py:32)."""
+class DinoV2ClassifierSlice(LightningSurface, nn.Module):
+    """Drop-in for reference `mst.models.DinoV2ClassifierSlice` (dino.py:32), including the Lightning-module methods of its
+    base classes that the training script drives (base_model.py; new_vit_b200/training.py)."""
 
     def __init__(self, in_ch, out_ch, spatial_dims=2, pretrained=True, save_attn=False,
                  rotary_positional_encoding=None, optimizer_kwargs={'lr': 1e-6, 'weight_decay': 1e-2},
@@ -127,11 +140,7 @@ class DinoV2ClassifierSlice(nn.Module):
                 "Construct with pretrained=False and load a checkpoint with load_state_dict().")
         if rotary_positional_encoding not in (None, 'RoPE', 'LiRE'):
             raise ValueError(f"Unkown parameter {rotary_positional_encoding} for rotary_positional_encoding")  # transformer_blocks.py:358
-        if rotary_positional_encoding == 'LiRE':
-            raise NotImplementedError(
-                "rotary_positional_encoding='LiRE' is not built: the reference applies ONE position-independent orthogonal matrix "
-                "and then reinterprets [B,L,heads,hd] as [B*heads,L,hd] (rotary_embedding_torch.py:338-396), see DESIGN.md")
-        if rotary_positional_encoding == 'RoPE' and slice_fusion != 'transformer':
+        if rotary_positional_encoding in ('RoPE', 'LiRE') and slice_fusion != 'transformer':
             rotary_positional_encoding = None               # only the transformer fusion has attention (dino.py:84-96)
         if slice_fusion not in _cabi.FUSION:
             raise ValueError(f"slice_fusion {slice_fusion!r} unsupported")
@@ -141,7 +150,6 @@ class DinoV2ClassifierSlice(nn.Module):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         E, depth, heads = synth.VIT_CFG[model_size]
         self.in_ch, self.out_ch, self.spatial_dims = in_ch, out_ch, spatial_dims
-        self.optimizer_kwargs = optimizer_kwargs
         self.save_attn = save_attn
         self.attention_maps = []
         self.attention_maps_slice = []
@@ -162,7 +170,8 @@ class DinoV2ClassifierSlice(nn.Module):
         if slice_fusion == 'transformer':                   # dino.py:80-97
             if use_slice_pos_emb:
                 self.slice_pos_emb = nn.Embedding(256, emb)
-            self.slice_fusion = _SliceFusion(emb, synth.SLICE_HEADS, rope=rotary_positional_encoding == 'RoPE')
+            self.slice_fusion = _SliceFusion(emb, synth.SLICE_HEADS, rope=rotary_positional_encoding == 'RoPE',
+                                             liere=rotary_positional_encoding == 'LiRE')
             self.cls_token = nn.Parameter(torch.zeros(1, 1, emb))
         head_in = emb * 32 if slice_fusion == 'linear' else emb   # dino.py:98-99
         self.linear = nn.Linear(head_in, out_ch) if enable_linear else nn.Identity()
@@ -174,7 +183,12 @@ class DinoV2ClassifierSlice(nn.Module):
                                    use_slice_pos_emb=use_slice_pos_emb and slice_fusion == 'transformer',
                                    slice_fusion=slice_fusion, enable_linear=enable_linear,
                                    rope=rotary_positional_encoding == 'RoPE', strict_init=True)
+        if rotary_positional_encoding == 'LiRE':            # its generator tables keep their own torch.randn init (:343)
+            sd.update({k: v.detach().clone() for k, v in self.state_dict().items() if ".rotary_positional_encoding.vars." in k})
         nn.Module.load_state_dict(self, sd, strict=True)
+        self._init_lightning_surface(out_ch, optimizer=kwargs.get("optimizer"), optimizer_kwargs=optimizer_kwargs,
+                                     lr_scheduler=kwargs.get("lr_scheduler"), lr_scheduler_kwargs=kwargs.get("lr_scheduler_kwargs"),
+                                     loss=kwargs.get("loss", nn.CrossEntropyLoss), loss_kwargs=kwargs.get("loss_kwargs"))
         # DinoVisionTransformer(interpolate_antialias, interpolate_offset): the vendored factory and the plain hub checkpoints
         # resample with (False, 0.1) (vision_transformer.py:66-67); the hub "_reg" models use_registers loads (dino.py:60-61) are
         # built with (True, 0.0).  Constructor keywords override, as they do on the reference's own factory.
@@ -309,14 +323,37 @@ class DinoV2ClassifierSlice(nn.Module):
                 _cabi.check(L.mst_set_weight(self._handle, name.encode(), _cabi.ptr(t32), t32.numel(), stream))
             _cabi.check(L.mst_finalize_weights(self._handle, stream))
         self._dirty = False
+        self._synced_version = (self._param_version(encoder_only=True), self._param_version())
+        self._params_stepped = False
 
     # -- forward (dino.py:110-167) ---------------------------------------------------------------------
+    def _param_version(self, encoder_only=False):
+        return sum(p._version for p in (self.encoder.parameters() if encoder_only else self.parameters()))
+
     def forward(self, source, save_attn=False, src_key_padding_mask=None, **kwargs):
-        if self._dirty or self._handle is None:
-            self.sync_weights()
-        dev = self.device
         if source.dim() != 5:
             raise ValueError(f"expected source [B, C, D, H, W], got {tuple(source.shape)}")
+        if self.rotary == 'LiRE':
+            # What the reference does with rotary_positional_encoding='LiRE' is raise: AttentionLiereRotator hard-codes 33 tokens
+            # (rotary_embedding_torch.py:350) and returns a permuted [B, L, heads, hd] tensor that the caller cannot .view() as
+            # [B*heads, L, hd] (transformer_blocks.py:263).  Verified against the live reference (tests/test_host.py).
+            B_, L_, hd_ = source.shape[0], source.shape[2] + 1, self.emb_ch // synth.SLICE_HEADS
+            if L_ != 33:
+                raise RuntimeError(f"shape '[{B_}, 33, {synth.SLICE_HEADS}, {hd_}]' is invalid for input of size "
+                                   f"{B_ * synth.SLICE_HEADS * L_ * hd_}")
+            raise RuntimeError("view size is not compatible with input tensor's size and stride (at least one dimension spans "
+                               "across two contiguous subspaces). Use .reshape(...) instead.")
+        # In-place parameter updates (an optimizer step) do not pass through load_state_dict: they are detected by tensor version
+        # (torch optimizers) or by the flag FusedAdamW raises.  The training path reads the slice transformer's live parameters
+        # and needs only the (frozen) encoder packed, so optimizer steps do not trigger a re-pack there.
+        train_path = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        stale = (self._param_version(encoder_only=True) != getattr(self, "_synced_version", (None, None))[0] if train_path else
+                 (self._param_version() != getattr(self, "_synced_version", (None, None))[1] or getattr(self, "_params_stepped", False)))
+        if self._dirty or self._handle is None or stale:
+            self.sync_weights()
+        if train_path:
+            return self._forward_train(source, src_key_padding_mask, **kwargs)
+        dev = self.device
         B, C, D, H, W = source.shape
         assert C == 1, "More than one channel"             # dino.py:14 / the (b d c) flatten at :125
         assert H % 14 == 0 and W % 14 == 0, \
@@ -361,6 +398,8 @@ class DinoV2ClassifierSlice(nn.Module):
         chunk = max(chunks)
         want_enc = bool(kwargs.get("return_enc_cls", False))
         small = bool(self.graph_max_slices) and V * B * D <= self.graph_max_slices and full_maps is None
+        if small:
+            chunks, chunk = [B], B
         with torch.cuda.device(dev):
             need = _cabi.ctypes.c_size_t()
             if full_maps is not None:
@@ -449,6 +488,35 @@ class DinoV2ClassifierSlice(nn.Module):
         if kwargs.get('without_linear', False) or not self.enable_linear:   # dino.py:164-165; nn.Identity head (:103)
             return feat
         return logits
+
+    # -- training step on a frozen encoder (BASELINE config 5, frozen-encoder slice; new_vit_b200/training.py) -----------
+    def _forward_train(self, source, src_key_padding_mask=None, **kwargs):
+        """train()-mode forward with autograd: the encoder runs as in inference (it must be frozen: its backward pass is not
+        built), the slice transformer + head run in the differentiable CUDA path.  Dropouts are 0 and drop_path is 0 in the
+        reference (dino.py:89), so train-mode arithmetic equals eval-mode arithmetic."""
+        if any(p.requires_grad for p in self.encoder.parameters()):
+            raise NotImplementedError(
+                "training the encoder is not built (no encoder backward kernels): construct with freeze=True (dino.py:69-71) "
+                "or call .eval() / torch.no_grad() for inference")
+        if (self.slice_fusion_type != 'transformer' or hasattr(self, "bottleneck") or hasattr(self, "slice_pos_emb")
+                or self.rotary is not None or not self.enable_linear):
+            raise NotImplementedError("the differentiable slice path covers the default construction (dino.py:84-103: transformer "
+                                      "fusion, no bottleneck / slice position embedding / rotary, linear head)")
+        B, C, D, H, W = source.shape
+        was_training = self.training
+        self.training = False                       # (re-enters forward() on the inference path; submodules are parameter holders)
+        try:
+            with torch.no_grad():
+                self.forward(source, src_key_padding_mask=src_key_padding_mask, return_enc_cls=True)
+        finally:
+            self.training = was_training
+        enc = self._enc_cls.view(B, D, -1)
+        mask = None
+        if src_key_padding_mask is not None:
+            mask = src_key_padding_mask.to(self.device).to(torch.uint8).contiguous()
+        sd = dict(self.named_parameters())
+        params = [sd[n] for n in SLICE_PARAM_NAMES]
+        return SliceHeadFunction.apply(self._handle, enc, mask, synth.SLICE_HEADS, False, *params)
 
     # -- instrumentation ------------------------------------------------------------------------------------
     def launch_count(self):

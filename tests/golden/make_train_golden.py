@@ -1,0 +1,65 @@
+"""Golden vectors for the training step (BASELINE.json config 5, frozen-encoder construction) from the REAL reference model:
+
+    python tests/golden/make_train_golden.py          (dev container only: needs /root/reference)
+
+`DinoV2ClassifierSlice(freeze=True)` in train() mode (dino.py:69-71; dropouts are 0, so train == eval arithmetic), one
+`_step`-style pass: pred = model(source, src_key_padding_mask) -> CrossEntropyLoss(pred, target) (base_model.py:155-159,180-181)
+-> loss.backward().  Stored: logits, loss, the gradient of every trainable tensor (the 17 slice-transformer / head tensors), and
+the parameters after ONE torch.optim.AdamW step (base_model.py:103-110).  To keep the fixtures small the [E, E] / [3E, E]
+matrices are stored as every 8th row (SUB); vectors are stored whole."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_harness import build_reference_model  # noqa: E402
+import new_vit_b200.synth as synth  # noqa: E402
+
+SUB = 8
+
+
+def _sub(t):
+    return t[::SUB] if t.dim() == 2 and t.shape[0] >= 64 else t
+
+
+CASES = {
+    # name: (B, D, H, W, masked, weight seed, volume seed, lr)
+    "train_s_frozen_b3": (3, 8, 56, 56, True, 21, 21, 1e-3),
+    "train_s_frozen_d32_b2": (2, 32, 28, 28, False, 22, 22, 1e-6),
+}
+
+
+def run_case(name):
+    B, D, H, W, masked, wseed, vseed, lr = CASES[name]
+    sd = synth.make_state_dict("s", out_ch=2, seed=wseed, variant="peaky", img_size=H)
+    model = build_reference_model(sd, out_ch=2, model_size="s", pos_img_size=H, freeze=True).train()
+    for p in model.encoder.parameters():     # build_reference_model swaps the encoder in after __init__ froze the first one
+        p.requires_grad = False
+    x = synth.make_volume(B, D, H, W, seed=vseed)
+    mask = synth.make_padding_mask(B, D, seed=vseed) if masked else None
+    target = torch.tensor([(i * 7 + vseed) % 2 for i in range(B)])
+    pred = model(x, src_key_padding_mask=mask)
+    loss = torch.nn.CrossEntropyLoss()(pred, target)
+    loss.backward()
+    out = {"logits": pred.detach(), "loss": loss.detach().reshape(1), "target": target}
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    for n in names:
+        out["grad." + n] = _sub(dict(model.named_parameters())[n].grad.detach().clone())
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=lr, weight_decay=1e-2)
+    opt.step()
+    for n in names:
+        out["after." + n] = _sub(dict(model.named_parameters())[n].detach().clone())
+    meta = dict(B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed, lr=lr, trainable=names, sub=SUB)
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"), meta=np.array(repr(meta)),
+                        **{k: v.numpy() for k, v in out.items()})
+    print(name, "loss", float(loss), "trainable tensors", len(names), "logits", pred.detach().tolist())
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(os.cpu_count())
+    for n in (sys.argv[1:] or CASES):
+        run_case(n)

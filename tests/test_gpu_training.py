@@ -1,0 +1,132 @@
+"""Training step on a frozen encoder (BASELINE.json config 5, frozen-encoder construction), GPU: the CUDA forward / backward of
+the slice transformer + head (csrc/train.cu) against (1) gradients the REAL reference produced (tests/golden/train_*.npz),
+(2) the oracle under torch autograd on fresh inputs, and the fused AdamW kernel against torch.optim.AdamW."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _sub(t, sub):
+    return t[::sub] if t.dim() == 2 and t.shape[0] >= 64 else t
+
+
+@pytest.mark.parametrize("name", ["train_s_frozen_b3", "train_s_frozen_d32_b2"])
+def test_training_step_matches_reference_golden(name):
+    """model.train(); loss = model._step(batch) (base_model.py:148-170); loss.backward(); one AdamW step (base_model.py:103-110)."""
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    from new_vit_b200.training import SLICE_PARAM_NAMES, FusedAdamW
+    meta, g = load_golden(name)
+    sd = synth.make_state_dict("s", 2, seed=meta["wseed"], variant="peaky", img_size=meta["H"])
+    x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
+    mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"]) if meta["masked"] else None
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="fp32", img_size=meta["H"], freeze=True,
+                              optimizer_kwargs={'lr': meta["lr"], 'weight_decay': 1e-2}).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    opt = m.configure_optimizers()[0]
+    assert isinstance(opt, FusedAdamW)
+    opt.zero_grad()
+    batch = {"source": x, "target": g["target"].cuda(), "uid": ["a"] * meta["B"]}
+    if mask is not None:
+        batch["src_key_padding_mask"] = mask
+    loss = m.training_step(batch, 0)
+    assert loss.requires_grad
+    torch.testing.assert_close(loss.detach().cpu().reshape(1), g["loss"], rtol=1e-4, atol=1e-5)
+    loss.backward()
+    params = dict(m.named_parameters())
+    for n in SLICE_PARAM_NAMES:
+        got = _sub(params[n].grad.detach().cpu(), meta["sub"])
+        want = g["grad." + n]
+        scale = float(want.abs().max())
+        torch.testing.assert_close(got, want, rtol=2e-3, atol=2e-4 * scale + 1e-9, msg=lambda s, n=n: f"grad {n}: {s}")
+    assert all(p.grad is None for p in m.encoder.parameters())
+    opt.step()
+    for n in SLICE_PARAM_NAMES:
+        got = _sub(params[n].detach().cpu(), meta["sub"])
+        # one AdamW step moves every element by ~lr (|m / sqrt(v)| ~ 1 at step 1): compare the update, not the value
+        before = _sub(sd[n].reshape(params[n].shape), meta["sub"])
+        torch.testing.assert_close(got - before, g["after." + n] - before, rtol=2e-2, atol=0.05 * meta["lr"], msg=lambda s, n=n: f"step {n}: {s}")
+    # eval forward after the step uses the updated weights (the handle is re-packed on demand)
+    m.eval()
+    with torch.no_grad():
+        y = m(x, src_key_padding_mask=mask)
+    m2 = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="fp32", img_size=meta["H"]).cuda().eval()
+    m2.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        assert torch.equal(y, m2(x, src_key_padding_mask=mask))
+
+
+@pytest.mark.parametrize("B,D,masked", [(8, 32, False), (5, 7, True), (1, 64, True)])
+def test_slice_backward_matches_oracle_autograd(B, D, masked):
+    """csrc/train.cu through the autograd.Function on given encoder features, against torch autograd over the oracle's slice
+    transformer (oracle/mst_oracle.py) with the same parameters: logits, every parameter gradient, and d/d enc."""
+    from new_vit_b200 import synth
+    from new_vit_b200.training import SLICE_PARAM_NAMES, SliceHeadFunction
+    from oracle import mst_oracle as O
+    E, heads, C = 384, 12, 2
+    sd = synth.make_state_dict("s", C, seed=61, variant="peaky")
+    g = torch.Generator().manual_seed(B * 100 + D)
+    enc = torch.randn(B, D, E, generator=g)
+    mask = synth.make_padding_mask(B, D, seed=3) if masked else None
+    if masked and B == 1:
+        mask[0, D - 5:] = True
+    target = torch.randint(0, C, (B,), generator=g)
+    # oracle under autograd (CPU)
+    ref_p = {n: sd[n].clone().requires_grad_(True) for n in SLICE_PARAM_NAMES}
+    enc_ref = enc.clone().requires_grad_(True)
+    full = dict(sd)
+    full.update(ref_p)
+    tok = torch.cat([ref_p["cls_token"].repeat(B, 1, 1), enc_ref], dim=1)
+    kpm = None if mask is None else torch.cat([torch.zeros((B, 1), dtype=torch.bool), mask], dim=1)
+    y, _ = O.slice_transformer(full, tok, kpm)
+    logits_ref = F.linear(y[:, 0], ref_p["linear.weight"], ref_p["linear.bias"])
+    F.cross_entropy(logits_ref, target).backward()
+    # CUDA
+    ps = [sd[n].clone().cuda().requires_grad_(True) for n in SLICE_PARAM_NAMES]
+    enc_c = enc.cuda().requires_grad_(True)
+    mk = None if mask is None else mask.to(torch.uint8).cuda()
+    logits = SliceHeadFunction.apply(None, enc_c, mk, heads, True, *ps)
+    torch.testing.assert_close(logits.detach().cpu(), logits_ref.detach(), rtol=1e-4, atol=1e-5)
+    F.cross_entropy(logits, target.cuda()).backward()
+    for n, p in zip(SLICE_PARAM_NAMES, ps):
+        want = ref_p[n].grad
+        torch.testing.assert_close(p.grad.cpu(), want, rtol=1e-3, atol=1e-5 * float(want.abs().max()) + 1e-10, msg=lambda s, n=n: f"{n}: {s}")
+    want = enc_ref.grad
+    torch.testing.assert_close(enc_c.grad.cpu(), want, rtol=1e-3, atol=1e-5 * float(want.abs().max()))
+    if mask is not None:   # masked slices get no gradient through the attention keys/values... and none at all (they only enter there)
+        assert float(enc_c.grad.cpu()[mask].abs().max()) == 0.0
+
+
+def test_fused_adamw_matches_torch():
+    from new_vit_b200.training import FusedAdamW
+    torch.manual_seed(0)
+    shapes = [(384, 384), (1152,), (2, 384), (7,), (1, 1, 384)]
+    ref = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    o_our = FusedAdamW(ours, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    for step in range(5):
+        grads = [torch.randn(s, device="cuda") * (0.1 + step) for s in shapes]
+        o_our.zero_grad()
+        for p, q, gr in zip(ref, ours, grads):
+            p.grad = gr.clone()
+            q.grad.copy_(gr)
+        o_ref.step()
+        o_our.step()
+        for p, q in zip(ref, ours):
+            torch.testing.assert_close(q.detach(), p.detach(), rtol=2e-6, atol=2e-7)
+
+
+def test_unfrozen_encoder_training_is_refused_clearly():
+    from new_vit_b200 import DinoV2ClassifierSlice
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False).cuda().train()
+    with pytest.raises(NotImplementedError, match="freeze=True"):
+        m(torch.zeros(1, 1, 2, 28, 28))
+    m.eval()
+    assert m(torch.zeros(1, 1, 2, 28, 28)).shape == (1, 2)       # inference under grad mode stays the inference path
