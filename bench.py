@@ -230,6 +230,32 @@ def run_extras(model_s, dev, rank, world, timed, peaks):
                              "ms_per_step": ms, "volumes_per_sec": 64 / (ms * 1e-3), "algorithmic_bytes": by,
                              "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / hbm}
     del raw
+    # ---- config 5, frozen-encoder construction (freeze=True, dino.py:69-71): forward + CE loss + backward + gradient all-reduce
+    #      (NCCL, when world > 1) + AdamW, 8 volumes per GPU (the encoder's backward pass is not built: it runs without gradient) ----
+    mt = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", freeze=True).to(dev)
+    mt.load_state_dict(synth.make_state_dict("s", 2, seed=0))
+    mt.train()
+    opt = mt.configure_optimizers()[0]
+    xt = synth.make_volume(8, D, H, H, seed=300 + rank).to(dev)
+    batch = {"source": xt, "target": torch.randint(0, 2, (8,), device=dev), "uid": ["x"] * 8}
+
+    def train_step():
+        opt.zero_grad()
+        loss = mt.training_step(batch, 0)
+        loss.backward()
+        opt.step()
+        return loss
+    for _ in range(3):
+        train_step()
+    ms = timed(train_step, 10)
+    trainable = sum(p.numel() for p in mt.parameters() if p.requires_grad)
+    out["config5_train_frozen_encoder"] = {
+        "workload": f"config 5 (frozen encoder): training step fwd + CrossEntropy + bwd + {'NCCL gradient all-reduce + ' if world > 1 else ''}"
+                    f"AdamW, 8 volumes x 32 x 224x224 per GPU x {world} GPU; trainable = slice transformer + head ({trainable} parameters); "
+                    "the encoder runs forward-only (its backward kernels are not built)",
+        "value": 8 * world / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms, "trainable_parameters": trainable,
+        "grad_allreduce_bytes": trainable * 4 if world > 1 else 0, "loss": float(train_step())}
+    del mt, opt, xt, batch
     # ---- config 4 ----
     torch.cuda.empty_cache()
     mb = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", model_size="b", img_size=252).to(dev).eval()

@@ -29,7 +29,7 @@ extern "C" {
 enum { MST_PRECISION_FP32 = 0, MST_PRECISION_BF16 = 1 };
 /* slice_fusion constructor argument (reference dino.py:80-101,144-157) */
 enum { MST_FUSION_TRANSFORMER = 0, MST_FUSION_LINEAR = 1, MST_FUSION_AVERAGE = 2 };
-enum { MST_ROTARY_NONE = 0, MST_ROTARY_ROPE = 1 };
+enum { MST_ROTARY_NONE = 0, MST_ROTARY_ROPE = 1, MST_ROTARY_LIRE = 2 };
 /* element type of the `source` volume handed to mst_forward.  The bf16 path rounds every voxel to bf16 before the patch GEMM
  * anyway, so a bf16 upload is bit-identical to an fp32 one at half the host-to-device bytes. */
 enum { MST_SRC_F32 = 0, MST_SRC_BF16 = 1, MST_SRC_F16 = 2 };
@@ -54,7 +54,9 @@ typedef struct mst_config {
     int32_t enable_linear;     /* dino.py:103: 0 = nn.Identity head (forward returns the feature) */
     int32_t rotary;            /* rotary_positional_encoding (dino.py:40,92; utils/transformer_blocks.py:335-351):
                                   MST_ROTARY_NONE, or MST_ROTARY_ROPE = RoPE on the slice-token queries and keys; the
-                                  checkpoint then carries slice_fusion.layers.0.self_attn.rotary_positional_encoding.freqs */
+                                  checkpoint then carries slice_fusion.layers.0.self_attn.rotary_positional_encoding.freqs;
+                                  MST_ROTARY_LIRE = 'LiRE' as the reference evaluates it (utils/rotary_embedding_torch.py:328-396):
+                                  batch 1 and 32 slices only, carries ...rotary_positional_encoding.vars.{0,1} */
     int32_t interpolate_antialias; /* DinoVisionTransformer(interpolate_antialias=, interpolate_offset=) (vision_transformer.py:66-67,
                                       198-210): 0 / 0.1 for the vendored factory and the plain hub checkpoints; 1 / 0.0 for the hub
                                       "_reg" checkpoints (use_registers, dino.py:60-61) */
@@ -178,7 +180,7 @@ MST_API int mst_adamw(mst_handle h /* nullable */, float* p, const float* g, flo
 
 /* Instrumentation: kernels launched by this handle so far; per-category device time (CUDA events recorded on the
  * caller's stream around every launch between begin and end; end synchronises the device).  `ms`/`launches` must
- * hold at least 16 entries; mst_profile_categories() names them, comma separated, in order. */
+ * hold at least 32 entries; mst_profile_categories() names them, comma separated, in order. */
 MST_API unsigned long long mst_launch_count(mst_handle h);
 MST_API const char* mst_profile_categories(void);
 MST_API int mst_profile_begin(mst_handle h);

@@ -247,6 +247,11 @@ static void expected_names(mst_handle h) {
         x["slice_fusion.norm.weight"] = Es; x["slice_fusion.norm.bias"] = Es;
         if (h->cfg.rotary == MST_ROTARY_ROPE)   // RotaryEmbedding(dim = head_dim).freqs (rotary_embedding_torch.py:104,117)
             x[q + "self_attn.rotary_positional_encoding.freqs"] = Es / h->cfg.slice_heads / 2;
+        if (h->cfg.rotary == MST_ROTARY_LIRE) {  // AttentionLiereRotator.vars (rotary_embedding_torch.py:342-344): accepted for the
+            const int blk = Es / h->cfg.slice_heads / 2;   // state_dict round trip; the rotation they define cancels in q . k
+            for (int i = 0; i < 2; ++i)
+                x[q + "self_attn.rotary_positional_encoding.vars." + std::to_string(i)] = static_cast<int64_t>((blk * blk - blk) / 2) * 33;
+        }
     }
     if (h->cfg.enable_linear) {                                                                        // dino.py:98-103
         const int64_t in = h->cfg.slice_fusion == SLICE_FUSION_LINEAR ? 32LL * Es : Es;
@@ -370,6 +375,7 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
         s.nfw = h->master["slice_fusion.norm.weight"]; s.nfb = h->master["slice_fusion.norm.bias"];
         s.in_w = h->master[q + "self_attn.in_proj_weight"];
         if (h->cfg.rotary == MST_ROTARY_ROPE) s.rope_freqs = h->master[q + "self_attn.rotary_positional_encoding.freqs"];
+        s.liere = h->cfg.rotary == MST_ROTARY_LIRE ? 1 : 0;
         s.in_b = h->master[q + "self_attn.in_proj_bias"]; s.out_b = h->master[q + "self_attn.out_proj.bias"];
         s.l1_b = h->master[q + "linear1.bias"]; s.l2_b = h->master[q + "linear2.bias"];
         MST_PROPAGATE(transposed(h, q + "self_attn.in_proj_weight", 3 * Es, Es, &s.in_wt, st));
@@ -645,8 +651,11 @@ int mst_create(const mst_config* cfg, mst_handle* out) {
     MST_REQUIRE(cfg->num_registers >= 0 && cfg->num_registers <= 16, "mst_create: bad num_registers %d", cfg->num_registers);
     MST_REQUIRE(cfg->slice_fusion >= MST_FUSION_TRANSFORMER && cfg->slice_fusion <= MST_FUSION_AVERAGE, "mst_create: bad slice_fusion %d",
                 cfg->slice_fusion);
-    MST_REQUIRE(cfg->rotary == MST_ROTARY_NONE || (cfg->rotary == MST_ROTARY_ROPE && cfg->slice_fusion == MST_FUSION_TRANSFORMER),
-                "mst_create: rotary=%d unsupported (RoPE needs slice_fusion='transformer'; LiRE is not built)", cfg->rotary);
+    MST_REQUIRE(cfg->rotary == MST_ROTARY_NONE ||
+                    ((cfg->rotary == MST_ROTARY_ROPE || cfg->rotary == MST_ROTARY_LIRE) && cfg->slice_fusion == MST_FUSION_TRANSFORMER),
+                "mst_create: rotary=%d unsupported (RoPE / LiRE need slice_fusion='transformer')", cfg->rotary);
+    MST_REQUIRE(cfg->rotary != MST_ROTARY_LIRE || (cfg->embed_dim / (cfg->use_bottleneck ? 4 : 1) / cfg->slice_heads) % 2 == 0,
+                "mst_create: LiRE needs an even slice head dimension");
     MST_REQUIRE(cfg->interpolate_offset >= 0.0f && cfg->interpolate_offset < 1.0f, "mst_create: bad interpolate_offset %f", (double)cfg->interpolate_offset);
     MST_REQUIRE(!cfg->use_bottleneck || (cfg->embed_dim / 4) % cfg->slice_heads == 0, "mst_create: bottleneck width %d not divisible by %d heads",
                 cfg->embed_dim / 4, cfg->slice_heads);
@@ -733,6 +742,9 @@ static int check_shape(mst_handle h, int B, int D, int H, int W) {
     MST_REQUIRE(h->cfg.slice_fusion != MST_FUSION_LINEAR || D == 32,
                 "slice_fusion='linear' is built for 32 slices (dino.py:99), got D=%d", D);
     MST_REQUIRE(!h->cfg.use_slice_pos_emb || D <= 256, "slice position embedding holds 256 slices (dino.py:82), got D=%d", D);
+    MST_REQUIRE(h->cfg.rotary != MST_ROTARY_LIRE || (B == 1 && D == 32),
+                "rotary_positional_encoding='LiRE' runs for batch 1 and 32 slices only (rotary_embedding_torch.py:350, transformer_blocks.py:263 "
+                "raise otherwise), got B=%d D=%d", B, D);
     return 0;
 }
 

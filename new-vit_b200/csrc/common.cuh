@@ -206,6 +206,7 @@ struct SliceWeights {  // fp32, linear weights pre-transposed to [in][out]; bott
     const float *cls_token, *n1w, *n1b, *in_wt, *in_b, *out_wt, *out_b, *n2w, *n2b, *l1_wt, *l1_b, *l2_wt, *l2_b, *nfw,
         *nfb, *head_wt, *head_b, *bott_wt, *bott_b, *pos_emb, *in_w /* in_proj_weight as stored, [3E][E] */,
         *rope_freqs /* nullable [head_dim/2]: RoPE on the slice tokens (transformer_blocks.py:262-264) */;
+    int liere;  /* rotary_positional_encoding='LiRE' (batch 1, 33 tokens): q / k slots re-read as the reference's view does */
 };
 // enc_cls [B*D, Eenc]; E = slice embedding (Eenc, or Eenc/4 behind the bottleneck); logits/feat nullable
 int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const SliceWeights& w, float* hs_scratch,

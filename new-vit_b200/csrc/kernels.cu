@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
     __syncthreads();
     // 2. q = (Wq n0 + bq) / sqrt(hd)                                    (transformer_blocks.py:166,268)
     block_matvec(n0, E, 0, w.in_wt, 3 * E, w.in_b, nullptr, q, scr, E, E, false, rsqrtf(static_cast<float>(hd)));
-    if (w.rope_freqs) {
+    if (w.rope_freqs || w.liere) {
         // RoPE (transformer_blocks.py:262-264; rotary_embedding_torch.py:159-173,45-62): the key of sequence position j is
         // rotated by j*freqs[i] in each feature pair (2i, 2i+1) of its head before the dot product, so the keys are
         // materialised here (the W_k^T q re-association below needs position-independent keys).  The slice-CLS query sits
@@ -746,6 +746,35 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
             }
         }
         __syncthreads();
+        if (w.liere) {
+            // LiRE as the reference evaluates it (rotary_embedding_torch.py:346-396 + the caller's view, transformer_blocks.py:263;
+            // batch 1 and L = 33 only, everything else raises there): q and k of every (position, head) are multiplied by ONE
+            // orthogonal matrix -- which cancels in q . k and is therefore not applied -- and the [hd, L, heads] result is re-read
+            // as [heads, L, hd]: slot (head i, position j) holds the vector of position (L i + j) / heads, head (L i + j) % heads.
+            // The slice-CLS query of head i is thus the query of token (L i) / heads in head (L i) % heads.
+            const float scale = rsqrtf(static_cast<float>(hd));
+            for (int n = threadIdx.x; n < E; n += blockDim.x) {
+                const int i = n / hd, d = n - i * hd, m = L * i, l1 = m / heads, h1 = m - l1 * heads, col = h1 * hd + d;
+                const float* x = hs + static_cast<int64_t>(l1) * E;
+                float a0 = 0.f, a1 = 0.f;
+                for (int k = 0; k < E; k += 2) {
+                    a0 = fmaf(x[k], __ldg(w.in_wt + static_cast<int64_t>(k) * 3 * E + col), a0);
+                    a1 = fmaf(x[k + 1], __ldg(w.in_wt + static_cast<int64_t>(k + 1) * 3 * E + col), a1);
+                }
+                q[n] = ((a0 + a1) + w.in_b[col]) * scale;
+            }
+            __syncthreads();
+            for (int task = warp; task < heads * L; task += nwarps) {
+                const int i = task / L, j = task - i * L, m = L * i + j, l2 = m / heads, h2 = m - l2 * heads;
+                const float* kr = kmat + l2 * E + h2 * hd;
+                float a = 0.f;
+                for (int d = lane; d < hd; d += 32) a = fmaf(q[i * hd + d], kr[d], a);
+                a = warp_sum(a);
+                if (j > 0 && pad_mask && pad_mask[static_cast<int64_t>(bm) * D + j - 1]) a = -CUDART_INF_F;
+                if (lane == 0) p[i * L + j] = a;
+            }
+            __syncthreads();
+        } else {
         // 4'. s[h][j] = q_h . R_j k_{h,j}; key-padding mask -> -inf
         for (int task = warp; task < heads * L; task += nwarps) {
             const int h = task / L, j = task % L;
@@ -763,6 +792,7 @@ __global__ void __launch_bounds__(768) slice_fusion_kernel(const float* __restri
             if (lane == 0) p[h * L + j] = a;
         }
         __syncthreads();
+        }
     } else {
     // 3. qk[h][k] = sum_d q[h,d] Wk[h*hd+d][k];  cterm[h] = q_h . bk_h
     //    (reads the UN-transposed in_proj_weight [3E][E]: consecutive threads -> consecutive k -> coalesced)
@@ -851,7 +881,8 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
     const int L = D + 1;
     MST_REQUIRE(E % (4 * MV_PARTS) == 0, "slice fusion: slice embedding %d must be a multiple of %d", E, 4 * MV_PARTS);
     const size_t smem = (static_cast<size_t>(6 + MV_PARTS) * E + 2 * heads * E + 32 + 40 + ((heads * L + 3) & ~3) +
-                         (w.rope_freqs ? static_cast<size_t>(L) * E : 0)) * sizeof(float);
+                         ((w.rope_freqs || w.liere) ? static_cast<size_t>(L) * E : 0)) * sizeof(float);
+    MST_REQUIRE(!w.liere || (B == 1 && L == 33), "rotary_positional_encoding='LiRE' exists for batch 1 and 32 slices only (the reference raises otherwise)");
     MST_REQUIRE(smem <= 227 * 1024, "slice transformer: %zu bytes of shared memory needed (D=%d too large)", smem, D);
     MST_SET_DYN_SMEM(slice_fusion_kernel, 227 * 1024);
     slice_fusion_kernel<<<B, 768, smem, stream>>>(enc_cls, pad_mask, w, hs_scratch, logits, feat, slice_cls, D, Eenc, E, heads,

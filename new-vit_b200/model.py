@@ -308,7 +308,8 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
             cfg = _cabi.MstConfig(E, self.encoder.depth, self.encoder.num_heads, synth.SLICE_HEADS, self.out_ch,
                                   self.encoder.pos_embed.shape[1], _cabi.PRECISION[self.precision], key[0],
                                   self.num_registers, int(hasattr(self, "bottleneck")), int(hasattr(self, "slice_pos_emb")),
-                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear), int(self.rotary == 'RoPE'),
+                                  _cabi.FUSION[self.slice_fusion_type], int(self.enable_linear),
+                                  {None: 0, 'RoPE': 1, 'LiRE': 2}[self.rotary],
                                   int(self.interpolate_antialias), self.interpolate_offset)
             h = _cabi.ctypes.c_void_p()
             _cabi.check(L.mst_create(_cabi.ctypes.byref(cfg), _cabi.ctypes.byref(h)))
@@ -334,15 +335,18 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
         if source.dim() != 5:
             raise ValueError(f"expected source [B, C, D, H, W], got {tuple(source.shape)}")
         if self.rotary == 'LiRE':
-            # What the reference does with rotary_positional_encoding='LiRE' is raise: AttentionLiereRotator hard-codes 33 tokens
-            # (rotary_embedding_torch.py:350) and returns a permuted [B, L, heads, hd] tensor that the caller cannot .view() as
-            # [B*heads, L, hd] (transformer_blocks.py:263).  Verified against the live reference (tests/test_host.py).
+            # rotary_positional_encoding='LiRE' in the reference: AttentionLiereRotator hard-codes 33 tokens
+            # (rotary_embedding_torch.py:350) and returns a permuted [B, L, heads, hd] tensor that the caller can .view() as
+            # [B*heads, L, hd] for batch 1 only (transformer_blocks.py:263).  Everything else raises there, and here, with the same
+            # messages (tests/test_training_cpu.py pins them against the live reference).
             B_, L_, hd_ = source.shape[0], source.shape[2] + 1, self.emb_ch // synth.SLICE_HEADS
             if L_ != 33:
                 raise RuntimeError(f"shape '[{B_}, 33, {synth.SLICE_HEADS}, {hd_}]' is invalid for input of size "
                                    f"{B_ * synth.SLICE_HEADS * L_ * hd_}")
-            raise RuntimeError("view size is not compatible with input tensor's size and stride (at least one dimension spans "
-                               "across two contiguous subspaces). Use .reshape(...) instead.")
+            if B_ != 1:
+                raise RuntimeError("view size is not compatible with input tensor's size and stride (at least one dimension spans "
+                                   "across two contiguous subspaces). Use .reshape(...) instead.")
+            # batch 1, 32 slices: the one case the reference evaluates (csrc/kernels.cu, LiRE branch of slice_fusion_kernel)
         # In-place parameter updates (an optimizer step) do not pass through load_state_dict: they are detected by tensor version
         # (torch optimizers) or by the flag FusedAdamW raises.  The training path reads the slice transformer's live parameters
         # and needs only the (frozen) encoder packed, so optimizer steps do not trigger a re-pack there.
@@ -534,9 +538,9 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
 
     def profile_end(self):
         """{category: (milliseconds, launches)} accumulated since profile_begin (synchronises the device)."""
-        ms = (_cabi.ctypes.c_double * 16)()
-        n = (_cabi.ctypes.c_int64 * 16)()
-        _cabi.check(_cabi.lib().mst_profile_end(self._handle, ms, n, 16))
+        ms = (_cabi.ctypes.c_double * 32)()
+        n = (_cabi.ctypes.c_int64 * 32)()
+        _cabi.check(_cabi.lib().mst_profile_end(self._handle, ms, n, 32))
         names = _cabi.lib().mst_profile_categories().decode().split(",")
         return {k: (ms[i], int(n[i])) for i, k in enumerate(names)}
 

@@ -44,7 +44,7 @@ def _u(g, shape, bound):
 
 def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=224,
                     layerscale=False, chunked_names=True, num_registers=0, use_bottleneck=False,
-                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True, rope=False, strict_init=False):
+                    use_slice_pos_emb=False, slice_fusion="transformer", enable_linear=True, rope=False, strict_init=False, liere=False):
     """Return an OrderedDict with the reference's state_dict key layout.
 
     variant: "init"  -- reference-like init distributions
@@ -58,7 +58,7 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
     assert slice_fusion in ("transformer", "linear", "average")
     if strict_init:
         sd = make_state_dict(model_size, out_ch, seed, "init", img_size, layerscale, chunked_names, num_registers, use_bottleneck,
-                             use_slice_pos_emb, slice_fusion, enable_linear, rope)
+                             use_slice_pos_emb, slice_fusion, enable_linear, rope, liere=liere)
         return _reference_init(sd)
     E, depth, _heads = VIT_CFG[model_size]
     g = torch.Generator(device="cpu")
@@ -137,6 +137,11 @@ def make_state_dict(model_size="s", out_ch=2, seed=0, variant="init", img_size=2
     if rope:  # RotaryEmbedding(dim=head_dim, theta=256, 'lang'): 1/theta^(2i/dim) (rotary_embedding_torch.py:104; transformer_blocks.py:339)
         hd = E // SLICE_HEADS
         sd[q + "self_attn.rotary_positional_encoding.freqs"] = 1.0 / (256.0 ** (torch.arange(0, hd, 2)[: hd // 2].float() / hd))
+    if liere:  # AttentionLiereRotator(head_dim, liere_block_size=head_dim // 2, spacial_dims=1, axes_length=33): two generator
+        hd = E // SLICE_HEADS      # tables of shape [(blk^2 - blk) / 2, 33, 1], torch.randn init (rotary_embedding_torch.py:342-344)
+        blk = hd // 2
+        for i in range(hd // blk):   # (scaled down: exp of sum_p p * A_p with unit-variance entries is far outside any useful range)
+            sd[q + f"self_attn.rotary_positional_encoding.vars.{i}"] = _n(g2, ((blk * blk - blk) // 2, 33, 1), 0.002)
     if enable_linear:
         sd["linear.weight"] = _u(g, (out_ch, E), lin)
         sd["linear.bias"] = _u(g, (out_ch,), lin)

@@ -128,6 +128,33 @@ def rope_rotate(t, freqs):
     return t * ang.cos() + rot * ang.sin()
 
 
+def liere_rotate(t, liere_vars):
+    """rotary_positional_encoding='LiRE' as the reference applies it to q and k (transformer_blocks.py:263-264 ->
+    AttentionLiereRotator.rotate_queries_or_keys / forward, rotary_embedding_torch.py:346-396), operation by operation -- including
+    the two places where it can only raise: the hard-coded 33 tokens (:350) and the caller's .view() of the permuted result
+    (transformer_blocks.py:263), which succeeds for batch 1 only.  t: [B, heads, L, hd] -> [B*heads, L, hd].
+
+    What survives for B = 1, L = 33: ONE position-independent orthogonal matrix R (matrix_exp of a skew matrix built from all 33
+    generator slices) multiplies every vector, and the final view re-reads the [hd, L, heads] result as [heads, L, hd], so slot
+    (head i, position j) receives the vector of position (33 i + j) // heads, head (33 i + j) % heads.  R cancels in q . k."""
+    B, H, L, hd = t.shape
+    blk = hd // len(liere_vars)
+    t = t.permute(0, 2, 1, 3).contiguous()                                    # :392
+    x = t.view(B, 33 * 1, H, hd)                                              # :350 (axes_length = 33, spacial_dims = 1)
+    mats = []
+    for v in liere_vars:                                                      # :359-362, flat_to_skew :320-327
+        A = torch.zeros(blk, blk, 33, 1)
+        i, j = torch.tril_indices(blk, blk, offset=-1)
+        A[i, j, :, 0] = v[:, :, 0]
+        A[j, i, :, 0] = -v[:, :, 0]
+        mats.append(A.view(blk, blk, 33) @ torch.arange(0, 33).to(t.dtype))
+    R = torch.block_diag(*[torch.linalg.matrix_exp(A.float()) for A in mats])  # :365,371
+    x = x.permute(0, 3, 1, 2)                                                 # :381
+    y = torch.bmm(R.unsqueeze(0).repeat(B, 1, 1), x.reshape(B, hd, 33 * H).float())   # :386 (the reference's sparse bmm)
+    y = y.view(B, hd, 33, H).permute(0, 2, 3, 1)                              # :387
+    return y.view(B * H, L, hd)                                               # transformer_blocks.py:263
+
+
 def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
     """nn.TransformerEncoder(num_layers=1, norm) over the custom pre-LN layer
     (utils/transformer_blocks.py:524-573, 29-318; dino.py:84-96).  Explicit bmm/softmax path
@@ -146,6 +173,11 @@ def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
     rope = q_ + "self_attn.rotary_positional_encoding.freqs"
     if rope in sd:  # rotary_positional_encoding='RoPE' (transformer_blocks.py:262-264,335-351): q and k rotated by position
         q, k = rope_rotate(q, sd[rope]), rope_rotate(k, sd[rope])
+    lv = q_ + "self_attn.rotary_positional_encoding.vars."
+    if lv + "0" in sd:   # rotary_positional_encoding='LiRE'
+        liere_vars = [sd[lv + str(i)] for i in range(2)]
+        q = liere_rotate(q, liere_vars).view(B, heads, L, hd)
+        k = liere_rotate(k, liere_vars).view(B, heads, L, hd)
     s = q @ k.transpose(-2, -1)
     if key_padding_mask is not None:  # additive -inf on key columns (transformer_blocks.py:244-252)
         s = s.masked_fill(key_padding_mask[:, None, None, :], float("-inf"))
@@ -165,8 +197,8 @@ def slice_transformer(sd, x, key_padding_mask, heads=12):  # noqa: C901
 def forward(sd, source, src_key_padding_mask=None, enc_heads=None, keep_all_maps=False, slice_fusion="transformer"):
     """DinoV2ClassifierSlice.forward (dino.py:110-167).  The constructor variants are read off the state_dict
     (bottleneck.*, slice_pos_emb.weight, encoder.register_tokens, linear.* present or not); `slice_fusion`
-    selects dino.py:144-157; RoPE on the slice tokens is applied when its `freqs` tensor is in the state_dict
-    (LiRE is not restated).
+    selects dino.py:144-157; RoPE / LiRE on the slice tokens are applied when their `freqs` / `vars.*` tensors are in the
+    state_dict.
 
     Returns a dict: logits [B,out] (None without the linear head), feat, enc_cls [BD,E], plane_cls [BD,heads,N]
     (row 0 of the last encoder block's attention), slice_cls [B,12,L] (row 0 of slice attention), and the

@@ -31,9 +31,14 @@ def case_inputs(meta, out_ch=2):
     ctor = {k: meta[k] for k in CTOR_KEYS if k in meta}
     sd = synth.make_state_dict(meta["size"], out_ch=out_ch, seed=meta["wseed"], variant=meta["variant"],
                                img_size=meta.get("pos_img", meta["H"]), layerscale=hub, chunked_names=not hub,
-                               num_registers=meta.get("num_registers", 0), rope=bool(meta.get("rope", False)), **ctor)
+                               num_registers=meta.get("num_registers", 0), rope=bool(meta.get("rope", False)),
+                               liere=bool(meta.get("liere", False)), **ctor)
     x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
     mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"]) if meta["masked"] else None
+    if meta.get("mask_tail"):
+        import torch
+        mask = torch.zeros(meta["B"], meta["D"], dtype=torch.bool)
+        mask[:, meta["D"] - meta["mask_tail"]:] = True
     return sd, x, mask
 
 
@@ -44,6 +49,8 @@ def model_kwargs(meta):
               use_registers=meta.get("num_registers", 0) > 0)
     if meta.get("rope"):
         kw["rotary_positional_encoding"] = "RoPE"
+    if meta.get("liere"):
+        kw["rotary_positional_encoding"] = "LiRE"
     return kw
 
 

@@ -48,6 +48,8 @@ CASES = {
     # tests/models/test_dinoslice.py constructs) and a padding mask
     "s_rope_bottleneck_mask_b2": ("s", "peaky", 2, 9, 112, 112, True, 11, 11, {"use_bottleneck": True, "rope": True}),
     "s_rope_b2": ("s", "init", 2, 32, 112, 112, False, 12, 12, {"rope": True}),
+    # rotary_positional_encoding='LiRE': runs in the reference for batch 1 and 32 slices only (it raises otherwise)
+    "s_liere_mask_b1": ("s", "peaky", 1, 32, 112, 112, False, 14, 14, {"liere": True, "mask_tail": 5}),
     "s_fusion_linear_b2": ("s", "init", 2, 32, 56, 56, False, 9, 9, {"slice_fusion": "linear"}),
     "s_fusion_average_nolinear_b2": ("s", "init", 2, 6, 56, 56, False, 10, 10, {"slice_fusion": "average", "enable_linear": False}),
 }
@@ -62,13 +64,18 @@ def run_case(name):
     fusion = flags.get("slice_fusion", "transformer")
     ctor = {k: flags[k] for k in ("use_bottleneck", "use_slice_pos_emb", "slice_fusion", "enable_linear") if k in flags}
     rope = bool(flags.get("rope", False))
+    liere = bool(flags.get("liere", False))
     sd = synth.make_state_dict(size, out_ch=2, seed=wseed, variant=variant, img_size=pos_img, layerscale=hub,
-                               chunked_names=not hub, num_registers=nreg, rope=rope, **ctor)
-    ref_kw = dict(ctor, rotary_positional_encoding="RoPE") if rope else ctor
+                               chunked_names=not hub, num_registers=nreg, rope=rope, liere=liere, **ctor)
+    ref_kw = dict(ctor, rotary_positional_encoding="RoPE") if rope else (dict(ctor, rotary_positional_encoding="LiRE") if liere else ctor)
     model = build_reference_model(sd, out_ch=2, model_size=size, hub_layout=hub, num_registers=nreg,
                                   pos_img_size=pos_img if pos_img != H or nreg else None, **ref_kw)
     x = synth.make_volume(B, D, H, W, seed=vseed)
     mask = synth.make_padding_mask(B, D, seed=vseed) if masked else None
+    if flags.get("mask_tail"):   # batch 1: make_padding_mask never masks volume 0
+        mask = torch.zeros(B, D, dtype=torch.bool)
+        mask[:, D - flags["mask_tail"]:] = True
+        masked = True
     out = {}
     with torch.no_grad():
         out["logits_nosave"] = model(x, src_key_padding_mask=mask, save_attn=False)
@@ -105,7 +112,8 @@ def run_case(name):
                     out["sal_quantiles_b0"] = torch.from_numpy(np.quantile(w.numpy(), [0.5, 0.995, 0.999]))
             out["sal_sub"] = torch.stack(subs)
     meta = dict(size=size, variant=variant, B=B, D=D, H=H, W=W, masked=masked, wseed=wseed, vseed=vseed, hub_layout=hub,
-                num_registers=nreg, pos_img=pos_img, **(dict(ctor, rope=True) if rope else ctor))
+                num_registers=nreg, pos_img=pos_img, mask_tail=int(flags.get("mask_tail", 0)),
+                **(dict(ctor, rope=True) if rope else (dict(ctor, liere=True) if liere else ctor)))
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", name + ".npz"),
                         meta=np.array(repr(meta)), **{k: v.numpy() for k, v in out.items()})
     print(name, "logits", out["logits_nosave"].tolist()[:2])

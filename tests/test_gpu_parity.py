@@ -19,7 +19,9 @@ GOLDENS = ["s_init_small", "s_peaky_small_mask_b3", "s_init_b2", "s_peaky_mask_b
            # bicubic pos_embed path, bottleneck + slice position embedding
            "s_hub_reg518_b1", "s_interp_126x168_b2", "s_bottleneck_posemb_b2",
            # rotary_positional_encoding='RoPE' on the slice tokens (with the bottleneck + mask, and at 32 slices)
-           "s_rope_bottleneck_mask_b2", "s_rope_b2"]
+           "s_rope_bottleneck_mask_b2", "s_rope_b2",
+           # rotary_positional_encoding='LiRE' (batch 1, 32 slices: the one shape the reference evaluates it for)
+           "s_liere_mask_b1"]
 OTHER_FUSIONS = ["s_fusion_linear_b2", "s_fusion_average_nolinear_b2"]
 
 

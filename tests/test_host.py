@@ -53,7 +53,7 @@ def test_state_dict_layout_matches_reference():
 
 def test_unbuilt_options_raise():
     from new_vit_b200 import DinoV2ClassifierSlice
-    for kw in (dict(pretrained=True), dict(rotary_positional_encoding="LiRE")):
+    for kw in (dict(pretrained=True),):
         args = dict(in_ch=1, out_ch=2, pretrained=False)
         args.update(kw)
         with pytest.raises(NotImplementedError):

@@ -8,7 +8,7 @@ from oracle import mst_oracle as O
 from oracle import ref_harness
 
 SMALL = ["s_init_small", "s_peaky_small_mask_b3", "s_hub_layerscale_b1", "s_hub_reg518_b1", "s_interp_126x168_b2",
-         "s_bottleneck_posemb_b2", "s_rope_bottleneck_mask_b2", "s_rope_b2"]
+         "s_bottleneck_posemb_b2", "s_rope_bottleneck_mask_b2", "s_rope_b2", "s_liere_mask_b1"]
 NO_TRANSFORMER = ["s_fusion_linear_b2", "s_fusion_average_nolinear_b2"]
 FULL = ["s_init_b2", "s_peaky_mask_b2", "b_peaky_252_mask_b2", "b_peaky_252_d64_mask_b1"]
 

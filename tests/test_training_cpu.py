@@ -76,25 +76,28 @@ def test_unfrozen_training_forward_says_what_is_missing():
 
 
 def test_liere_mirrors_the_reference():
-    """rotary_positional_encoding='LiRE' (transformer_blocks.py:352-358): same extra state_dict tensors, and forward raises the
-    RuntimeError the reference raises (rotary_embedding_torch.py:350 hard-codes 33 tokens; the permuted result cannot be viewed
-    as [B*heads, L, hd], transformer_blocks.py:263)."""
+    """rotary_positional_encoding='LiRE' (transformer_blocks.py:352-358): same extra state_dict tensors; the reference evaluates it
+    for batch 1 and 32 slices only and raises RuntimeError otherwise (rotary_embedding_torch.py:350 hard-codes 33 tokens; the
+    permuted result cannot be viewed as [B*heads, L, hd] for B > 1, transformer_blocks.py:263) -- same errors, same messages here.
+    (What it computes for batch 1 is pinned by the golden s_liere_mask_b1: oracle on the CPU, CUDA kernel in the GPU tests.)"""
     ours = DinoV2ClassifierSlice(in_ch=1, out_ch=2, pretrained=False, rotary_positional_encoding='LiRE')
     keys = [k for k in ours.state_dict() if "rotary" in k]
     assert keys == [f"slice_fusion.layers.0.self_attn.rotary_positional_encoding.vars.{i}" for i in range(2)]
     assert all(tuple(ours.state_dict()[k].shape) == (120, 33, 1) for k in keys) and len(ours.state_dict()) == 170
     errs = {}
-    for D in (32, 5):
+    for B, D in ((2, 32), (1, 5)):
         with pytest.raises(RuntimeError) as e:
-            ours(torch.zeros(1, 1, D, 56, 56))
-        errs[D] = str(e.value)
-    assert "view size is not compatible" in errs[32] and "shape '[1, 33, 12, 32]' is invalid for input of size 2304" in errs[5]
+            ours(torch.zeros(B, 1, D, 56, 56))
+        errs[(B, D)] = str(e.value)
+    assert "view size is not compatible" in errs[(2, 32)] and "shape '[1, 33, 12, 32]' is invalid for input of size 2304" in errs[(1, 5)]
     if ref_harness.reference_available():
         Ref = ref_harness.load_reference_class()
         ref = Ref(in_ch=1, out_ch=2, pretrained=False, rotary_positional_encoding='LiRE').eval()
         assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
         ref.load_state_dict(ours.state_dict())
-        for D in (32, 5):
+        for B, D in ((2, 32), (1, 5)):
             with pytest.raises(RuntimeError) as e:
-                ref(torch.zeros(1, 1, D, 56, 56))
-            assert str(e.value) == errs[D]
+                ref(torch.zeros(B, 1, D, 56, 56))
+            assert str(e.value) == errs[(B, D)]
+        with torch.no_grad():
+            assert ref(torch.zeros(1, 1, 32, 56, 56)).shape == (1, 2)     # the one shape it evaluates
