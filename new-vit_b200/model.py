@@ -351,7 +351,8 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
         # (torch optimizers) or by the flag FusedAdamW raises.  The training path reads the slice transformer's live parameters
         # and needs only the (frozen) encoder packed, so optimizer steps do not trigger a re-pack there.
         train_path = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        stale = (self._param_version(encoder_only=True) != getattr(self, "_synced_version", (None, None))[0] if train_path else
+        encoder_only = train_path or bool(kwargs.get("_encoder_only", False))
+        stale = (self._param_version(encoder_only=True) != getattr(self, "_synced_version", (None, None))[0] if encoder_only else
                  (self._param_version() != getattr(self, "_synced_version", (None, None))[1] or getattr(self, "_params_stepped", False)))
         if self._dirty or self._handle is None or stale:
             self.sync_weights()
@@ -511,7 +512,7 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
         self.training = False                       # (re-enters forward() on the inference path; submodules are parameter holders)
         try:
             with torch.no_grad():
-                self.forward(source, src_key_padding_mask=src_key_padding_mask, return_enc_cls=True)
+                self.forward(source, src_key_padding_mask=src_key_padding_mask, return_enc_cls=True, _encoder_only=True)
         finally:
             self.training = was_training
         enc = self._enc_cls.view(B, D, -1)

@@ -51,7 +51,12 @@ def test_training_step_matches_reference_golden(name):
         got = _sub(params[n].detach().cpu(), meta["sub"])
         # one AdamW step moves every element by ~lr (|m / sqrt(v)| ~ 1 at step 1): compare the update, not the value
         before = _sub(sd[n].reshape(params[n].shape), meta["sub"])
-        torch.testing.assert_close(got - before, g["after." + n] - before, rtol=2e-2, atol=0.05 * meta["lr"], msg=lambda s, n=n: f"step {n}: {s}")
+        # (Adam normalises by sqrt(v): where the gradient is rounding noise -- the key bias, whose exact gradient is 0 because
+        #  softmax rows sum to 1 -- the first step is +-lr with a random sign in the reference too; those elements are skipped)
+        gw = g["grad." + n]
+        live = gw.abs() > 1e-4 * gw.abs().max()
+        torch.testing.assert_close((got - before)[live], (g["after." + n] - before)[live], rtol=2e-2, atol=0.05 * meta["lr"],
+                                   msg=lambda s, n=n: f"step {n}: {s}")
     # eval forward after the step uses the updated weights (the handle is re-packed on demand)
     m.eval()
     with torch.no_grad():
