@@ -1027,6 +1027,40 @@ int mst_kernel_gemm_bf16_res_stats(const void* A, const void* W, int32_t M, int3
     return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, EPI_BIAS_RES, ep, num_sms_current(),
                         static_cast<cudaStream_t>(stream));
 }
+int mst_kernel_gemm_bf16_f32out(const void* A, const void* W, int32_t M, int32_t N, int32_t K, float* out, void* stream) {
+    MST_REQUIRE(A && W && out, "mst_kernel_gemm_bf16_f32out: null argument");
+    EpiParams ep{};
+    ep.out = out; ep.ldo = N;
+    return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, EPI_RAW_F32, ep, num_sms_current(),
+                        static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_ln_bwd_bf16(const void* x, const void* dy, const void* dres, const float* gamma, void* dx, float* dgamma, float* dbeta,
+                           int32_t rows, int32_t E, float eps, void* stream) {
+    MST_REQUIRE(x && dy && gamma && dx && dgamma && dbeta, "mst_kernel_ln_bwd_bf16: null argument");
+    float* ws = nullptr;
+    MST_CHECK_CUDA(cudaMalloc(&ws, ln_bwd_workspace_bytes(E)));
+    const int rc = launch_ln_bwd(static_cast<const bf16*>(x), E, static_cast<const bf16*>(dy), nullptr, static_cast<const bf16*>(dres), gamma,
+                                 static_cast<bf16*>(dx), dgamma, dbeta, rows, E, eps, ws, static_cast<cudaStream_t>(stream));
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaFree(ws);
+    return rc;
+}
+int mst_kernel_gelu_bf16(const void* u, void* y, const void* dy, void* du, int64_t n, void* stream) {
+    MST_REQUIRE(u && (y || (dy && du)), "mst_kernel_gelu_bf16: null argument");
+    if (y) MST_PROPAGATE(launch_gelu_fwd(static_cast<const bf16*>(u), static_cast<bf16*>(y), n, num_sms_current(), static_cast<cudaStream_t>(stream)));
+    if (dy) MST_PROPAGATE(launch_gelu_bwd(static_cast<const bf16*>(u), static_cast<const bf16*>(dy), static_cast<bf16*>(du), n, num_sms_current(),
+                                          static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int mst_kernel_transpose_bf16(const void* in, void* out, float* colsum, int32_t M, int32_t C, int32_t Mpad, void* stream) {
+    MST_REQUIRE(in && out, "mst_kernel_transpose_bf16: null argument");
+    return launch_transpose_colsum(static_cast<const bf16*>(in), C, static_cast<bf16*>(out), colsum, M, C, Mpad, static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_attention_bwd_bf16(const void* qkv, const void* o, const void* dO, void* dqkv, int32_t BD, int32_t N, int32_t heads, void* stream) {
+    MST_REQUIRE(qkv && o && dO && dqkv, "mst_kernel_attention_bwd_bf16: null argument");
+    return launch_attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dO), static_cast<bf16*>(dqkv),
+                                BD, N, heads, static_cast<cudaStream_t>(stream));
+}
 int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream) {
     MST_REQUIRE(x && rowstat, "mst_kernel_row_stats_bf16: null argument");
     return launch_row_stats(static_cast<const bf16*>(x), rowstat, rows, E, eps, static_cast<cudaStream_t>(stream));

@@ -73,7 +73,8 @@ enum EpiMode : int {
     // (x - mean(x)) . (gamma W[n,:]) -- the mean subtraction happens inside the MMA; bias[n] = b[n] + sum_k beta[k] W[n,k];
     // rowstat[row] = rstd:   LN(x) W^T + b  =  rstd * acc + bias[n]
     EPI_LN_BIAS = 5,
-    EPI_LN_BIAS_GELU = 6
+    EPI_LN_BIAS_GELU = 6,
+    EPI_RAW_F32 = 7     // out[row, n] = acc as fp32 (weight gradients: dW = dY^T X, train_enc.cu); no bias
 };
 
 struct EpiParams {
@@ -248,5 +249,15 @@ int launch_slice_train_backward(const float* enc, const float* dlogits, const fl
                                 float* const* grads, float* denc, int B, int D, int E, int heads, int C, cudaStream_t stream);
 int launch_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int step,
                  float grad_scale, int num_sms, cudaStream_t stream);
+
+// ---- encoder backward pieces (train_enc.cu) ----
+size_t ln_bwd_workspace_bytes(int E);
+int launch_ln_bwd(const bf16* x, int64_t x_row_stride, const bf16* dy, const float* dy_f32, const bf16* dres, const float* gamma, bf16* dx,
+                  float* dgamma, float* dbeta, int rows, int E, float eps, float* workspace, cudaStream_t stream);
+int launch_gelu_fwd(const bf16* u, bf16* y, int64_t n, int num_sms, cudaStream_t stream);
+int launch_gelu_bwd(const bf16* u, const bf16* dy, bf16* du, int64_t n, int num_sms, cudaStream_t stream);
+int launch_transpose_colsum(const bf16* in, int64_t ld, bf16* out, float* colsum, int M, int C, int Mpad, cudaStream_t stream);
+int launch_transpose_f32_to_bf16(const float* W, bf16* Wt, int N, int K, cudaStream_t stream);
+int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream);
 
 }  // namespace mst

@@ -316,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     }
     // bias cache (EPI_PATCH has no bias vector)
     const bool ln_fold = mode == EPI_LN_BIAS || mode == EPI_LN_BIAS_GELU;
-    const bool bias_cached = mode != EPI_PATCH && (kResident || N <= L::BIAS_FLOATS);
+    const bool bias_cached = mode != EPI_PATCH && mode != EPI_RAW_F32 && (kResident || N <= L::BIAS_FLOATS);
     if (bias_cached && warp >= 4) {
         const int cnt = kResident ? BN : N;
         const float* src = ep.bias + (kResident ? n_fixed * BN : 0);
@@ -458,13 +458,24 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             const bool row_ok = row < M;
             const int col0 = hf * COLS_PER_WARP;                  // first column of this warp inside the tile
             const int nbase = n_blk * BN + col0;                  // ... and in the output
-            const float* bias0 = bias_cached ? sBias + (kResident ? col0 : nbase) : (mode == EPI_PATCH ? nullptr : ep.bias + nbase);
+            const float* bias0 = bias_cached ? sBias + (kResident ? col0 : nbase)
+                                             : ((mode == EPI_PATCH || mode == EPI_RAW_F32) ? nullptr : ep.bias + nbase);
             float rstat = 0.f;
             if (ln_fold && row_ok) rstat = __ldg(ep.rowstat + row);
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + col0);
 
             const bool dbg_w = kDbgTiming && ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
             auto process = [&](const uint32_t (&r)[32], int c) {
+                if (mode == EPI_RAW_F32) {   // weight gradients: the fp32 accumulators as they are (small outputs: per-lane row stores)
+                    if (row_ok) {
+                        float4* po = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + row * ep.ldo + nbase + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            po[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                                __uint_as_float(r[4 * i + 3]));
+                    }
+                    return;
+                }
                 uint32_t o[16];
                 const long long p0 = MST_DBG_CLOCK();
                 const int n0 = nbase + c * 32;
@@ -722,6 +733,7 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(K % BK == 0, "gemm: K=%d must be a multiple of %d", K, BK);
     MST_REQUIRE(N % 192 == 0 || N % 128 == 0, "gemm: N=%d must be a multiple of 192 or 128", N);
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
+    MST_REQUIRE(mode != EPI_RAW_F32 || (K > 384 && N % 192 == 0), "gemm: fp32 output is wired for the streaming schedule (K > 384, N %% 192 == 0)");
     // in-place residual update: `out += acc + bias` as 16-byte vector reductions (no residual read by the SM)
     const bool want_stats = ep.rowstat_out != nullptr;
     if (ep.rowpart_out != nullptr) {

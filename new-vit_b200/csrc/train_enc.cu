@@ -1,0 +1,478 @@
+// Backward pass of the DINOv2 encoder (BASELINE.json config 5 with the default, un-frozen construction: main_train.py:110-126 trains
+// every parameter of dino.py:56-103).  bf16 activations and activation gradients, fp32 weight gradients, fp32 statistics.
+//
+// The heavy contractions reuse the tcgen05 GEMM of gemm_tc.cu:
+//   dgrad   dX = dY . W          ->  gemm(A = dY [M, N_out], weight = W^T [K_in, N_out])            (bf16 out)
+//   wgrad   dW = dY^T . X        ->  gemm(A = dY^T [N_out, M], weight = X^T [K_in, M], fp32 out)     (EPI_RAW_F32)
+// This file holds what sits between them: the transposes that turn token-major activations into K-major operands (with the bias
+// gradient = column sums on the way), LayerNorm backward, GELU forward / backward, the attention backward (warp-level tensor cores:
+// recomputes the 257 x 257 probabilities per (slice, head) from q, k and the saved row log-sum-exp; nothing N x N touches HBM),
+// and the small gradients of the patch embedding / position table / class token.
+#include <math_constants.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mst {
+
+namespace {
+__device__ __forceinline__ float wsum32(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm backward, one warp per row (E = 32 * EPL, EPL <= 32), eps as in the forward (1e-6 encoder):
+//   xhat = (x - mean) rstd;  g = dy * gamma;  dx = rstd (g - mean(g) - xhat mean(g xhat)) (+ dres)
+//   dgamma += dy * xhat, dbeta += dy: per-CTA partial sums [gridDim.x][2][E], reduced by ln_bwd_reduce_kernel
+// row_map (nullable): dy / dres / dx rows are 0..rows-1, the x row of row r is row_map_stride * r (the CLS rows of the final norm)
+// ---------------------------------------------------------------------------------------------------
+template <int EPL>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x, int64_t x_row_stride, const bf16* __restrict__ dy,
+                                                      const float* __restrict__ dy_f32, const bf16* __restrict__ dres,
+                                                      const float* __restrict__ gamma, bf16* __restrict__ dx, float* __restrict__ partial,
+                                                      int rows, float eps) {
+    constexpr int E = EPL * 32;
+    __shared__ float red[2][E];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) (&red[0][0])[i] = 0.f;
+    __syncthreads();
+    float gam[EPL], dg[EPL], db[EPL];
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) { gam[i] = gamma[lane + 32 * i]; dg[i] = 0.f; db[i] = 0.f; }
+    for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+        const bf16* xr = x + static_cast<int64_t>(r) * x_row_stride;
+        float xv[EPL], dyv[EPL];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            xv[i] = __bfloat162float(xr[lane + 32 * i]);
+            dyv[i] = dy ? __bfloat162float(dy[static_cast<int64_t>(r) * E + lane + 32 * i]) : dy_f32[static_cast<int64_t>(r) * E + lane + 32 * i];
+            s += xv[i];
+        }
+        const float mean = wsum32(s) * (1.0f / E);
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) { const float d = xv[i] - mean; q = fmaf(d, d, q); }
+        const float rstd = rsqrtf(wsum32(q) * (1.0f / E) + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            xv[i] = (xv[i] - mean) * rstd;            // xhat
+            const float g = dyv[i] * gam[i];
+            s1 += g; s2 = fmaf(g, xv[i], s2);
+            dg[i] = fmaf(dyv[i], xv[i], dg[i]);
+            db[i] += dyv[i];
+        }
+        const float m1 = wsum32(s1) * (1.0f / E), m2 = wsum32(s2) * (1.0f / E);
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) {
+            float v = rstd * (dyv[i] * gam[i] - m1 - xv[i] * m2);
+            if (dres) v += __bfloat162float(dres[static_cast<int64_t>(r) * E + lane + 32 * i]);
+            dx[static_cast<int64_t>(r) * E + lane + 32 * i] = __float2bfloat16_rn(v);
+        }
+    }
+    (void)warp;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) { atomicAdd(&red[0][lane + 32 * i], dg[i]); atomicAdd(&red[1][lane + 32 * i], db[i]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) partial[static_cast<int64_t>(blockIdx.x) * 2 * E + i] = (&red[0][0])[i];
+}
+// dgamma[e] (+)= sum over CTAs of partial[.][0][e], dbeta likewise
+__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nparts, int E, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * E) return;
+    float a = 0.f;
+    for (int p = 0; p < nparts; ++p) a += partial[static_cast<int64_t>(p) * 2 * E + i];
+    if (i < E) dgamma[i] = a; else dbeta[i - E] = a;
+}
+constexpr int LN_BWD_GRID = 592;   // 4 CTAs per SM
+size_t ln_bwd_workspace_bytes(int E) { return static_cast<size_t>(LN_BWD_GRID) * 2 * E * sizeof(float); }
+
+int launch_ln_bwd(const bf16* x, int64_t x_row_stride, const bf16* dy, const float* dy_f32, const bf16* dres, const float* gamma, bf16* dx,
+                  float* dgamma, float* dbeta, int rows, int E, float eps, float* workspace, cudaStream_t stream) {
+    MST_REQUIRE(E == 384 || E == 768, "LayerNorm backward: E=%d unsupported (384 / 768)", E);
+    MST_REQUIRE((dy != nullptr) != (dy_f32 != nullptr), "LayerNorm backward: exactly one of dy (bf16) / dy_f32");
+    int grid = (rows + 7) / 8;
+    grid = grid < 1 ? 1 : (grid > LN_BWD_GRID ? LN_BWD_GRID : grid);
+    if (E == 384) ln_bwd_kernel<12><<<grid, 256, 0, stream>>>(x, x_row_stride, dy, dy_f32, dres, gamma, dx, workspace, rows, eps);
+    else ln_bwd_kernel<24><<<grid, 256, 0, stream>>>(x, x_row_stride, dy, dy_f32, dres, gamma, dx, workspace, rows, eps);
+    MST_CHECK_CUDA(cudaGetLastError());
+    ln_bwd_reduce_kernel<<<(2 * E + 255) / 256, 256, 0, stream>>>(workspace, grid, E, dgamma, dbeta);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GELU (mlp.py:36, exact erf form in the reference).  Forward in training = the inference epilogue's function (common.cuh
+// gelu_tanh_fit, |deviation from erf-GELU| <= 2.5e-5) so that a training forward equals an inference forward bit for bit;
+// backward = the derivative of the exact form, Phi(u) + u phi(u).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ u, bf16* __restrict__ y, int64_t n8) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4*>(u)[i];
+        uint4 o;
+        const uint32_t* ai = reinterpret_cast<const uint32_t*>(&a);
+        uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(ai[j]);
+            oi[j] = pack_bf16x2(gelu_tanh_fit(f.x), gelu_tanh_fit(f.y));
+        }
+        reinterpret_cast<uint4*>(y)[i] = o;
+    }
+}
+__device__ __forceinline__ float gelu_grad(float u) {
+    const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
+    return fmaf(u, pdf, cdf);
+}
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ u, const bf16* __restrict__ dy, bf16* __restrict__ du, int64_t n8) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const uint4 a = reinterpret_cast<const uint4*>(u)[i], d = reinterpret_cast<const uint4*>(dy)[i];
+        uint4 o;
+        const uint32_t* ai = reinterpret_cast<const uint32_t*>(&a);
+        const uint32_t* di = reinterpret_cast<const uint32_t*>(&d);
+        uint32_t* oi = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(ai[j]), g = unpack_bf16x2(di[j]);
+            oi[j] = pack_bf16x2(g.x * gelu_grad(f.x), g.y * gelu_grad(f.y));
+        }
+        reinterpret_cast<uint4*>(du)[i] = o;
+    }
+}
+int launch_gelu_fwd(const bf16* u, bf16* y, int64_t n, int num_sms, cudaStream_t stream) {
+    MST_REQUIRE(n % 8 == 0, "gelu: element count must be a multiple of 8");
+    gelu_fwd_kernel<<<num_sms * 8, 256, 0, stream>>>(u, y, n / 8);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+int launch_gelu_bwd(const bf16* u, const bf16* dy, bf16* du, int64_t n, int num_sms, cudaStream_t stream) {
+    MST_REQUIRE(n % 8 == 0, "gelu backward: element count must be a multiple of 8");
+    gelu_bwd_kernel<<<num_sms * 8, 256, 0, stream>>>(u, dy, du, n / 8);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// in [M, C] bf16 (row stride ld) -> out [C, Mpad] bf16 (columns M..Mpad-1 zero), 64 x 64 tiles through shared memory;
+// colsum (nullable) [C] fp32 += column sums (the bias gradient of the Linear whose dY this is): one atomicAdd per column and CTA.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_colsum_kernel(const bf16* __restrict__ in, int64_t ld, bf16* __restrict__ out,
+                                                                float* __restrict__ colsum, int M, int C, int Mpad) {
+    __shared__ bf16 tile[64][66];
+    const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
+    // load: rows m0 + r, 64 columns (2 per lane)
+    for (int r = ty; r < 64; r += 8) {
+        const int m = m0 + r;
+        uint32_t v = 0u;
+        if (m < M) v = *reinterpret_cast<const uint32_t*>(in + static_cast<int64_t>(m) * ld + c0 + 2 * tx);
+        *reinterpret_cast<uint32_t*>(&tile[r][2 * tx]) = v;
+    }
+    __syncthreads();
+    // store: out rows c0 + c, 64 consecutive m (2 per lane)
+    for (int c = ty; c < 64; c += 8) {
+        const bf16 a = tile[2 * tx][c], b = tile[2 * tx + 1][c];
+        if (m0 + 2 * tx < Mpad) {
+            __nv_bfloat162 p;
+            p.x = a; p.y = b;
+            *reinterpret_cast<__nv_bfloat162*>(out + static_cast<int64_t>(c0 + c) * Mpad + m0 + 2 * tx) = p;
+        }
+        if (colsum) {
+            float s = __bfloat162float(a) + __bfloat162float(b);
+            s = wsum32(s);
+            if (tx == 0) atomicAdd(colsum + c0 + c, s);
+        }
+    }
+}
+int launch_transpose_colsum(const bf16* in, int64_t ld, bf16* out, float* colsum, int M, int C, int Mpad, cudaStream_t stream) {
+    MST_REQUIRE(C % 64 == 0 && Mpad % 64 == 0 && Mpad >= M && ld % 2 == 0, "transpose: C=%d Mpad=%d M=%d unsupported", C, Mpad, M);
+    dim3 grid(Mpad / 64, C / 64);
+    transpose_colsum_kernel<<<grid, 256, 0, stream>>>(in, ld, out, colsum, M, C, Mpad);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// W [N, K] fp32 (nn.Linear layout) -> Wt [K, N] bf16 (the dgrad GEMM's weight operand), optional per-row scale of W
+__global__ void __launch_bounds__(256) transpose_f32_to_bf16_kernel(const float* __restrict__ W, bf16* __restrict__ Wt, int N, int K) {
+    __shared__ float tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = (n0 + r < N && k0 + tx < K) ? W[static_cast<int64_t>(n0 + r) * K + k0 + tx] : 0.f;
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (k0 + r < K && n0 + tx < N) Wt[static_cast<int64_t>(k0 + r) * N + n0 + tx] = __float2bfloat16_rn(tile[tx][r]);
+}
+int launch_transpose_f32_to_bf16(const float* W, bf16* Wt, int N, int K, cudaStream_t stream) {
+    dim3 grid((N + 31) / 32, (K + 31) / 32);
+    transpose_f32_to_bf16_kernel<<<grid, 256, 0, stream>>>(W, Wt, N, K);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mst
+
+namespace mst {
+
+// ---------------------------------------------------------------------------------------------------
+// Attention backward (attention.py:56-69), head_dim 64, one CTA per (slice, head), warp-level tensor cores (mma.sync m16n8k16).
+//   qkv [BD*N, 3E] bf16 with q pre-scaled by 1/8 (as the forward's qkv GEMM writes it), o [BD*N, E] the forward output,
+//   dO  [BD*N, E]  ->  dqkv [BD*N, 3E]: d/d(q_raw) = 1/8 dS K,  d/dk = dS^T q,  d/dv = P^T dO
+// Q, K, V and dO of the item sit in shared memory (XOR-swizzled 16-byte chunks, as attention_mma.cu).  Three phases:
+//   1  D_i = dO_i . O_i  and  lse_i = log2 sum_j 2^(s_ij log2e)   (one query block of 16 rows per warp, online over key chunks)
+//   2  dQ:  per query block, per 32-key chunk:  P = 2^(S log2e - lse), dP = dO V^T, dS = P (dP - D), dQ += dS K
+//   3  dK, dV: per 16-key block, per 32-query chunk, the transposed products:  P^T from K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
+// The N x N probabilities exist only as register fragments.
+// ---------------------------------------------------------------------------------------------------
+namespace attb {
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// A-operand fragments of 16 rows (g, g+8) x 64 dims from a swizzled [rows][128 B] shared-memory tile
+__device__ __forceinline__ void load_a(uint32_t (&a)[4][4], const uint8_t* tile, int r0, int r1, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        a[ks][0] = *reinterpret_cast<const uint32_t*>(tile + r0 * 128 + (((2 * ks) ^ (r0 & 7)) << 4) + 4 * t);
+        a[ks][1] = *reinterpret_cast<const uint32_t*>(tile + r1 * 128 + (((2 * ks) ^ (r1 & 7)) << 4) + 4 * t);
+        a[ks][2] = *reinterpret_cast<const uint32_t*>(tile + r0 * 128 + (((2 * ks + 1) ^ (r0 & 7)) << 4) + 4 * t);
+        a[ks][3] = *reinterpret_cast<const uint32_t*>(tile + r1 * 128 + (((2 * ks + 1) ^ (r1 & 7)) << 4) + 4 * t);
+    }
+}
+// acc[nb] (16 x 8) = A (16 x 64) . B[row0 + nb*8 .. +8]^T for nb < 4: B rows are the "n" index, K-major (ldmatrix, no transpose)
+__device__ __forceinline__ void mma_rows(float (&acc)[4][4], const uint32_t (&a)[4][4], uint32_t tile_u32, int row0, int lane) {
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+        acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+        const int row = row0 + nb * 8 + (lane & 7);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int c = half * 4 + (lane >> 3);
+            uint32_t b[4];
+            ldmatrix_x4(b, tile_u32 + row * 128 + ((c ^ (row & 7)) << 4));
+            mma_bf16_16816(acc[nb], a[2 * half], b[0], b[1]);
+            mma_bf16_16816(acc[nb], a[2 * half + 1], b[2], b[3]);
+        }
+    }
+}
+// out (16 x 64) += A (16 x 32, from the C fragments c[4][4] of a 16 x 32 block) . B[row0 .. row0+32] (32 x 64, ldmatrix transposed)
+__device__ __forceinline__ void mma_cols(float (&out)[8][4], const float (&c)[4][4], uint32_t tile_u32, int row0, int lane) {
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16x2(c[2 * kk][0], c[2 * kk][1]);
+        pa[1] = pack_bf16x2(c[2 * kk][2], c[2 * kk][3]);
+        pa[2] = pack_bf16x2(c[2 * kk + 1][0], c[2 * kk + 1][1]);
+        pa[3] = pack_bf16x2(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+        const int row = row0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+        for (int dn = 0; dn < 8; dn += 2) {
+            const int ch = dn + (lane >> 4);
+            uint32_t b[4];
+            ldmatrix_x4_trans(b, tile_u32 + row * 128 + ((ch ^ (row & 7)) << 4));
+            mma_bf16_16816(out[dn], pa, b[0], b[1]);
+            mma_bf16_16816(out[dn + 1], pa, b[2], b[3]);
+        }
+    }
+}
+}  // namespace attb
+
+__global__ void __launch_bounds__(attb::THREADS, 1)
+attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
+                     int N, int heads, int NKP) {
+    using namespace attb;
+    extern __shared__ __align__(128) uint8_t smem_ab[];
+    uint8_t* Qs = smem_ab;
+    uint8_t* Ks = Qs + NKP * 128;
+    uint8_t* Vs = Ks + NKP * 128;
+    uint8_t* Gs = Vs + NKP * 128;                                   // dO
+    float* lse = reinterpret_cast<float*>(Gs + NKP * 128);          // [NKP] log2-domain log-sum-exp (+inf for padded rows)
+    float* Dv = lse + NKP;                                          // [NKP] dO_i . O_i
+    const int s = blockIdx.x / heads, h = blockIdx.x % heads;
+    const int E = heads * 64;
+    const int64_t ld = 3 * E;
+    const bf16* qbase = qkv + static_cast<int64_t>(s) * N * ld + h * 64;
+    const bf16* obase = o + static_cast<int64_t>(s) * N * E + h * 64;
+    const bf16* gbase = dO + static_cast<int64_t>(s) * N * E + h * 64;
+    bf16* dbase = dqkv + static_cast<int64_t>(s) * N * ld + h * 64;
+    const uint32_t qs_u = smem_u32(Qs), ks_u = smem_u32(Ks), vs_u = smem_u32(Vs), gs_u = smem_u32(Gs);
+
+    for (int idx = threadIdx.x; idx < NKP * 8; idx += THREADS) {
+        const int r = idx >> 3, c = idx & 7;
+        const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
+        if (r < N) {
+            const bf16* g = qbase + r * ld + c * 8;
+            cp_async_16(qs_u + off, g);
+            cp_async_16(ks_u + off, g + E);
+            cp_async_16(vs_u + off, g + 2 * E);
+            cp_async_16(gs_u + off, gbase + static_cast<int64_t>(r) * E + c * 8);
+        } else {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(Qs + off) = z; *reinterpret_cast<uint4*>(Ks + off) = z;
+            *reinterpret_cast<uint4*>(Vs + off) = z; *reinterpret_cast<uint4*>(Gs + off) = z;
+        }
+    }
+    cp_async_commit_wait_all();
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int n_rb = (N + 15) >> 4;       // 16-row blocks
+    const int n_ch = NKP >> 5;            // 32-row chunks (NKP is a multiple of 32)
+
+    // ---- phase 1: D_i and lse_i ----
+    for (int i = threadIdx.x; i < NKP; i += THREADS) {
+        float d = 0.f;
+        if (i < N) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 a = *reinterpret_cast<const uint4*>(Gs + i * 128 + ((c ^ (i & 7)) << 4));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(i) * E + c * 8));
+                const uint32_t* ai = reinterpret_cast<const uint32_t*>(&a);
+                const uint32_t* bi = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 x = unpack_bf16x2(ai[j]), y = unpack_bf16x2(bi[j]);
+                    d = fmaf(x.x, y.x, d); d = fmaf(x.y, y.y, d);
+                }
+            }
+        }
+        Dv[i] = d;
+    }
+    for (int rb = warp; rb < (NKP >> 4); rb += WARPS) {
+        if (rb >= n_rb) {   // rows beyond N: probabilities are defined as 0
+            if (lane < 16) lse[rb * 16 + lane] = CUDART_INF_F;
+            continue;
+        }
+        uint32_t qa[4][4];
+        load_a(qa, Qs, rb * 16 + g, rb * 16 + g + 8, t);
+        float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+        for (int ch = 0; ch < n_ch; ++ch) {
+            float sacc[4][4];
+            mma_rows(sacc, qa, ks_u, ch * 32, lane);
+            float cm0 = -CUDART_INF_F, cm1 = -CUDART_INF_F;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const int key = ch * 32 + nb * 8 + 2 * t;
+                if (key >= N) { sacc[nb][0] = -CUDART_INF_F; sacc[nb][2] = -CUDART_INF_F; }
+                if (key + 1 >= N) { sacc[nb][1] = -CUDART_INF_F; sacc[nb][3] = -CUDART_INF_F; }
+                cm0 = fmaxf(cm0, fmaxf(sacc[nb][0], sacc[nb][1]));
+                cm1 = fmaxf(cm1, fmaxf(sacc[nb][2], sacc[nb][3]));
+            }
+            cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+            cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+            if (cm0 == -CUDART_INF_F && cm1 == -CUDART_INF_F) continue;   // a chunk of padding keys only (warp-uniform per quad pair)
+            const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+            float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                rs0 += exp2f((sacc[nb][0] - mn0) * LOG2E) + exp2f((sacc[nb][1] - mn0) * LOG2E);
+                rs1 += exp2f((sacc[nb][2] - mn1) * LOG2E) + exp2f((sacc[nb][3] - mn1) * LOG2E);
+            }
+            l0 = l0 * exp2f((m0 - mn0) * LOG2E) + rs0;
+            l1 = l1 * exp2f((m1 - mn1) * LOG2E) + rs1;
+            m0 = mn0; m1 = mn1;
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        if (t == 0) {
+            const int r0 = rb * 16 + g, r1 = r0 + 8;
+            lse[r0] = r0 < N ? m0 * LOG2E + log2f(l0) : CUDART_INF_F;
+            lse[r1] = r1 < N ? m1 * LOG2E + log2f(l1) : CUDART_INF_F;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: dQ (queries as rows) ----
+    for (int rb = warp; rb < n_rb; rb += WARPS) {
+        const int r0 = rb * 16 + g, r1 = r0 + 8;
+        uint32_t qa[4][4], ga[4][4];
+        load_a(qa, Qs, r0, r1, t);
+        load_a(ga, Gs, r0, r1, t);
+        const float ls0 = lse[r0], ls1 = lse[r1], d0 = Dv[r0], d1 = Dv[r1];
+        float dq[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+        for (int ch = 0; ch < n_ch; ++ch) {
+            float sacc[4][4], dp[4][4];
+            mma_rows(sacc, qa, ks_u, ch * 32, lane);
+            mma_rows(dp, ga, vs_u, ch * 32, lane);
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const int key = ch * 32 + nb * 8 + 2 * t;
+                const bool v0 = key < N, v1 = key + 1 < N;
+                const float p00 = v0 ? exp2f(fmaf(sacc[nb][0], LOG2E, -ls0)) : 0.f, p01 = v1 ? exp2f(fmaf(sacc[nb][1], LOG2E, -ls0)) : 0.f;
+                const float p10 = v0 ? exp2f(fmaf(sacc[nb][2], LOG2E, -ls1)) : 0.f, p11 = v1 ? exp2f(fmaf(sacc[nb][3], LOG2E, -ls1)) : 0.f;
+                sacc[nb][0] = p00 * (dp[nb][0] - d0); sacc[nb][1] = p01 * (dp[nb][1] - d0);     // dS
+                sacc[nb][2] = p10 * (dp[nb][2] - d1); sacc[nb][3] = p11 * (dp[nb][3] - d1);
+            }
+            mma_cols(dq, sacc, ks_u, ch * 32, lane);
+        }
+        if (r0 < N) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld);
+#pragma unroll
+            for (int dn = 0; dn < 8; ++dn) dst[dn * 4 + t] = pack_bf16x2(dq[dn][0] * 0.125f, dq[dn][1] * 0.125f);
+        }
+        if (r1 < N) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld);
+#pragma unroll
+            for (int dn = 0; dn < 8; ++dn) dst[dn * 4 + t] = pack_bf16x2(dq[dn][2] * 0.125f, dq[dn][3] * 0.125f);
+        }
+    }
+
+    // ---- phase 3: dK, dV (keys as rows) ----
+    for (int kb = warp; kb < n_rb; kb += WARPS) {
+        const int r0 = kb * 16 + g, r1 = r0 + 8;
+        uint32_t ka[4][4], va[4][4];
+        load_a(ka, Ks, r0, r1, t);
+        load_a(va, Vs, r0, r1, t);
+        float dk[8][4], dv[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+        for (int ch = 0; ch < n_ch; ++ch) {
+            float st[4][4], dpt[4][4];
+            mma_rows(st, ka, qs_u, ch * 32, lane);       // S^T[key, query] = k . q'
+            mma_rows(dpt, va, gs_u, ch * 32, lane);      // dP^T[key, query] = v . dO
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const int qi = ch * 32 + nb * 8 + 2 * t;
+                const float la = lse[qi], lb = lse[qi + 1], da = Dv[qi], dbq = Dv[qi + 1];
+                const float p00 = exp2f(fmaf(st[nb][0], LOG2E, -la)), p01 = exp2f(fmaf(st[nb][1], LOG2E, -lb));   // lse = +inf for padding
+                const float p10 = exp2f(fmaf(st[nb][2], LOG2E, -la)), p11 = exp2f(fmaf(st[nb][3], LOG2E, -lb));
+                st[nb][0] = p00; st[nb][1] = p01; st[nb][2] = p10; st[nb][3] = p11;
+                dpt[nb][0] = p00 * (dpt[nb][0] - da); dpt[nb][1] = p01 * (dpt[nb][1] - dbq);
+                dpt[nb][2] = p10 * (dpt[nb][2] - da); dpt[nb][3] = p11 * (dpt[nb][3] - dbq);
+            }
+            mma_cols(dv, st, gs_u, ch * 32, lane);       // dV += P^T dO
+            mma_cols(dk, dpt, qs_u, ch * 32, lane);      // dK += dS^T q'
+        }
+        if (r0 < N) {
+            uint32_t* dK = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld + E);
+            uint32_t* dV = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld + 2 * E);
+#pragma unroll
+            for (int dn = 0; dn < 8; ++dn) { dK[dn * 4 + t] = pack_bf16x2(dk[dn][0], dk[dn][1]); dV[dn * 4 + t] = pack_bf16x2(dv[dn][0], dv[dn][1]); }
+        }
+        if (r1 < N) {
+            uint32_t* dK = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld + E);
+            uint32_t* dV = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld + 2 * E);
+#pragma unroll
+            for (int dn = 0; dn < 8; ++dn) { dK[dn * 4 + t] = pack_bf16x2(dk[dn][2], dk[dn][3]); dV[dn * 4 + t] = pack_bf16x2(dv[dn][2], dv[dn][3]); }
+        }
+    }
+}
+
+int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream) {
+    const int NKP = ((N + 31) / 32) * 32;
+    const size_t smem = static_cast<size_t>(NKP) * (4 * 128 + 8);
+    MST_REQUIRE(smem <= 227 * 1024, "attention backward: N=%d tokens do not fit shared memory", N);
+    MST_SET_DYN_SMEM(attention_bwd_kernel, 227 * 1024);
+    attention_bwd_kernel<<<BD * heads, attb::THREADS, smem, stream>>>(qkv, o, dO, dqkv, N, heads, NKP);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mst
