@@ -178,6 +178,21 @@ MST_API int mst_slice_train_backward(mst_handle h /* nullable */, const float* e
 MST_API int mst_adamw(mst_handle h /* nullable */, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
               float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* Training step of the whole model (BASELINE.json config 5 as main_train.py:110-126 runs it: every parameter trainable): the encoder's
+ * forward with every block's activations kept, and its backward pass.  bf16 activations and activation gradients, fp32 weight
+ * gradients.  Supported: the vendored-factory construction (no LayerScale, no registers) at the position table's own patch grid.
+ *   mst_train_forward   src as mst_forward; enc_cls [B*D, E] fp32 = the encoder output per slice (feeds mst_slice_train_forward)
+ *   mst_set_grad        register (or clear, with NULL) the caller-owned fp32 gradient buffer of one encoder tensor by state_dict name
+ *   mst_train_backward  denc [B*D, E] fp32 = d loss / d enc_cls (mst_slice_train_backward's denc); overwrites every registered gradient
+ *                       buffer (all encoder.* tensors except mask_token must be registered); same workspace as the forward, untouched
+ *                       in between.  The weights must not change between forward and backward. */
+MST_API int mst_train_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W, size_t* bytes);
+MST_API int mst_train_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int32_t D, int32_t H, int32_t W, float* enc_cls,
+                      void* workspace, size_t workspace_bytes, void* stream);
+MST_API int mst_set_grad(mst_handle h, const char* name, float* dev_fp32, int64_t numel);
+MST_API int mst_train_backward(mst_handle h, const float* denc, int32_t B, int32_t D, int32_t H, int32_t W, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Instrumentation: kernels launched by this handle so far; per-category device time (CUDA events recorded on the
  * caller's stream around every launch between begin and end; end synchronises the device).  `ms`/`launches` must
  * hold at least 32 entries; mst_profile_categories() names them, comma separated, in order. */

@@ -84,6 +84,10 @@ def lib():
     L.mst_slice_train_forward.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
     L.mst_slice_train_backward.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     L.mst_adamw.argtypes = [vp, vp, vp, vp, vp, i64, fl, fl, fl, fl, fl, i32, fl, vp]
+    L.mst_train_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(sz)]
+    L.mst_train_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp, sz, vp]
+    L.mst_set_grad.argtypes = [vp, ctypes.c_char_p, vp, i64]
+    L.mst_train_backward.argtypes = [vp, vp, i32, i32, i32, i32, vp, sz, vp]
     L.mst_profile_begin.argtypes = [vp]
     L.mst_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), i32]
     L.mst_launch_count.argtypes = [vp]

@@ -1,5 +1,6 @@
 // C ABI (include/mst_b200.h): handle, weight store + packing, forward orchestration, saliency.
 #include <stdarg.h>
+#include <algorithm>
 #include <map>
 #include <type_traits>
 #include <string>
@@ -201,7 +202,12 @@ struct mst_handle_s {
     std::map<std::string, float*> master;       // canonical name -> device fp32 (owned)
     std::map<std::string, int64_t> expected;    // canonical name -> numel
     std::map<std::string, bool> have;
-    std::vector<void*> owned;                   // packed buffers
+    std::vector<void*> owned;                   // packed buffers, in allocation order
+    std::vector<size_t> owned_bytes;            // ... and their sizes: a re-finalize (every optimizer step when training) reuses them
+    size_t owned_cursor = 0;
+    std::map<std::string, float*> grad_ptr;     // canonical name -> caller-owned fp32 gradient buffer (mst_set_grad)
+    std::vector<void*> wT;                      // per layer x {qkv, proj, fc1, fc2}: bf16 W^T, the weight operand of the dgrad GEMMs
+    float* zero_bias = nullptr;                 // 4 * embed_dim zeros (the dgrad GEMMs carry no bias)
     std::vector<mst::Layer> layers;
     void* wpatch = nullptr;
     float *posb = nullptr, *cls_pos0 = nullptr;
@@ -276,9 +282,22 @@ static std::string canonical_name(const std::string& name) {
 
 template <typename T>
 static int alloc_dev(mst_handle h, T** p, size_t count) {
+    const size_t bytes = count * sizeof(T) ? count * sizeof(T) : 16;
+    if (h->owned_cursor < h->owned.size() && h->owned_bytes[h->owned_cursor] == bytes) {   // re-finalize: same layout, same buffer
+        *p = static_cast<T*>(h->owned[h->owned_cursor++]);
+        return 0;
+    }
     void* q = nullptr;
-    MST_CHECK_CUDA(cudaMalloc(&q, count * sizeof(T) ? count * sizeof(T) : 16));
-    h->owned.push_back(q);
+    MST_CHECK_CUDA(cudaMalloc(&q, bytes));
+    if (h->owned_cursor < h->owned.size()) {
+        cudaFree(h->owned[h->owned_cursor]);
+        h->owned[h->owned_cursor] = q;
+        h->owned_bytes[h->owned_cursor] = bytes;
+    } else {
+        h->owned.push_back(q);
+        h->owned_bytes.push_back(bytes);
+    }
+    h->owned_cursor++;
     *p = static_cast<T*>(q);
     return 0;
 }
@@ -628,6 +647,285 @@ static int forward_t(mst_handle h, const void* src, int src_dtype, int B, int D,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// training step of the encoder (bf16): forward that keeps every block's activations, and the backward pass over them
+// (kernels: train_enc.cu; contractions: the tcgen05 GEMM).  Reference: Lightning's step, base_model.py:148-170, on the
+// default un-frozen construction (dino.py:56-103); dropout / drop-path are 0 there, so train == eval arithmetic.
+// ---------------------------------------------------------------------------------------------------
+struct TrainLayer { bf16 *x_in, *qkv, *ao, *x_mid, *u, *hid; };
+struct TrainWs {
+    bf16* A0;                       // im2col of the input [BD*P, KP]
+    std::vector<TrainLayer> L;
+    bf16* x_out;                    // residual stream after the last block [M, E]
+    float* rowstat;                 // [M]
+    // backward scratch
+    bf16 *dX, *dXm, *dln, *dao, *dqkv, *dhid, *ln, *Ta, *Tb;
+    float* lnws;                    // LayerNorm-backward partials
+    float* wg;                      // [KP, E] fp32: patch weight gradient, transposed
+    int Mpad;
+    size_t total;
+};
+static TrainWs carve_train(const mst_config& c, int B, int D, int H, int W, uint8_t* base) {
+    const int64_t E = c.embed_dim, BD = static_cast<int64_t>(B) * D, P = static_cast<int64_t>(H / 14) * (W / 14), N = P + 1, M = BD * N;
+    const int64_t Mpad = (std::max(M, BD * P) + 63) / 64 * 64;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~static_cast<size_t>(255); return p; };
+    TrainWs w;
+    w.Mpad = static_cast<int>(Mpad);
+    w.A0 = static_cast<bf16*>(take(BD * P * KP * 2));
+    w.L.resize(c.depth);
+    for (int l = 0; l < c.depth; ++l) {
+        w.L[l].x_in = static_cast<bf16*>(take(M * E * 2));
+        w.L[l].qkv = static_cast<bf16*>(take(M * 3 * E * 2));
+        w.L[l].ao = static_cast<bf16*>(take(M * E * 2));
+        w.L[l].x_mid = static_cast<bf16*>(take(M * E * 2));
+        w.L[l].u = static_cast<bf16*>(take(M * 4 * E * 2));
+        w.L[l].hid = static_cast<bf16*>(take(M * 4 * E * 2));
+    }
+    w.x_out = static_cast<bf16*>(take(M * E * 2));
+    w.rowstat = static_cast<float*>(take(M * 4));
+    w.dX = static_cast<bf16*>(take(M * E * 2));
+    w.dXm = static_cast<bf16*>(take(M * E * 2));
+    w.dln = static_cast<bf16*>(take(M * E * 2));
+    w.dao = static_cast<bf16*>(take(M * E * 2));
+    w.dqkv = static_cast<bf16*>(take(M * 3 * E * 2));
+    w.dhid = static_cast<bf16*>(take(M * 4 * E * 2));
+    w.ln = static_cast<bf16*>(take(M * E * 2));
+    w.Ta = static_cast<bf16*>(take(4 * E * Mpad * 2));
+    w.Tb = static_cast<bf16*>(take(4 * E * Mpad * 2));
+    w.lnws = static_cast<float*>(take(ln_bwd_workspace_bytes(static_cast<int>(E))));
+    w.wg = static_cast<float*>(take(static_cast<size_t>(KP) * E * 4));
+    w.total = off;
+    return w;
+}
+
+static int check_trainable(mst_handle h, int H, int W) {
+    const mst_config& c = h->cfg;
+    MST_REQUIRE(c.precision == MST_PRECISION_BF16, "encoder training runs in bf16 (construct with precision='bf16')");
+    MST_REQUIRE(c.embed_dim == 384 || c.embed_dim == 768, "encoder training: embed_dim %d unsupported (384 / 768)", c.embed_dim);
+    MST_REQUIRE(c.num_registers == 0, "encoder training: register tokens are not supported");
+    int Mg = 1;
+    while ((Mg + 1) * (Mg + 1) <= c.pos_tokens - 1) ++Mg;
+    MST_REQUIRE(H / 14 == Mg && W / 14 == Mg && Mg * Mg == c.pos_tokens - 1,
+                "encoder training needs the position table's own grid (%d x %d patches); resampled tables have no backward here", Mg, Mg);
+    for (int i = 0; i < c.depth; ++i)
+        MST_REQUIRE(!h->have.count("encoder.blocks." + std::to_string(i) + ".ls1.gamma"), "encoder training: LayerScale is not supported");
+    return 0;
+}
+
+// W^T in bf16 for the four Linears of every block, from the fp32 master weights (refreshed by mst_train_forward: the weights
+// change every optimizer step)
+static int refresh_dgrad_weights(mst_handle h, cudaStream_t st) {
+    const int E = h->cfg.embed_dim, depth = h->cfg.depth;
+    if (h->wT.empty()) {
+        const size_t sz[4] = {static_cast<size_t>(3) * E * E, static_cast<size_t>(E) * E, static_cast<size_t>(4) * E * E, static_cast<size_t>(4) * E * E};
+        for (int l = 0; l < depth; ++l)
+            for (int k = 0; k < 4; ++k) {
+                void* q = nullptr;
+                MST_CHECK_CUDA(cudaMalloc(&q, sz[k] * 2));
+                h->wT.push_back(q);
+            }
+        MST_CHECK_CUDA(cudaMalloc(&h->zero_bias, static_cast<size_t>(4) * E * 4));
+        MST_CHECK_CUDA(cudaMemsetAsync(h->zero_bias, 0, static_cast<size_t>(4) * E * 4, st));
+    }
+    for (int l = 0; l < depth; ++l) {
+        const std::string p = "encoder.blocks." + std::to_string(l) + ".";
+        MST_PROPAGATE(launch_transpose_f32_to_bf16(h->master[p + "attn.qkv.weight"], static_cast<bf16*>(h->wT[4 * l + 0]), 3 * E, E, st));
+        MST_PROPAGATE(launch_transpose_f32_to_bf16(h->master[p + "attn.proj.weight"], static_cast<bf16*>(h->wT[4 * l + 1]), E, E, st));
+        MST_PROPAGATE(launch_transpose_f32_to_bf16(h->master[p + "mlp.fc1.weight"], static_cast<bf16*>(h->wT[4 * l + 2]), 4 * E, E, st));
+        MST_PROPAGATE(launch_transpose_f32_to_bf16(h->master[p + "mlp.fc2.weight"], static_cast<bf16*>(h->wT[4 * l + 3]), E, 4 * E, st));
+    }
+    h->launches += 4ull * depth;
+    return 0;
+}
+
+static int train_forward(mst_handle h, const void* src, int src_dtype, int B, int D, int H, int W, float* enc_out, const TrainWs& ws,
+                         cudaStream_t st) {
+    const mst_config& c = h->cfg;
+    const int E = c.embed_dim, BD = B * D, P = (H / 14) * (W / 14), N = P + 1, M = BD * N;
+    const float* posb = nullptr;
+    MST_PROPAGATE(pos_for_grid(h, H / 14, W / 14, &posb, st));
+    MST_LAUNCH(CAT_IM2COL, launch_im2col<bf16>(src, src_dtype, ws.A0, ws.L[0].x_in, h->cls_pos0, nullptr, 0, BD, H, W, KP, E, 0, D, st));
+    {
+        EpiParams ep{};
+        ep.posb = posb; ep.P = P; ep.R = 0; ep.out = ws.L[0].x_in; ep.ldo = E;
+        MST_LAUNCH(CAT_GEMM_PATCH, Ops<bf16>::gemm(h, ws.A0, KP, h->wpatch, BD * P, E, KP, EPI_PATCH, ep, st));
+    }
+    for (int l = 0; l < c.depth; ++l) {
+        const Layer& L = h->layers[l];
+        const TrainLayer& T = ws.L[l];
+        bf16* x_next = l + 1 < c.depth ? ws.L[l + 1].x_in : ws.x_out;
+        MST_REQUIRE(L.fold_qkv, "encoder training needs the LayerNorm-folded weight packing");
+        MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(T.x_in, ws.rowstat, M, E, 1e-6f, st));
+        {
+            EpiParams ep{};
+            ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = T.qkv; ep.ldo = 3 * E;
+            MST_LAUNCH(CAT_GEMM_QKV, Ops<bf16>::gemm(h, T.x_in, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
+        }
+        MST_LAUNCH(CAT_ATTENTION, Ops<bf16>::attention(h, T.qkv, T.ao, BD, N, c.enc_heads, st));
+        {
+            EpiParams ep{};
+            ep.bias = L.bproj; ep.res = T.x_in; ep.ldr = E; ep.out = T.x_mid; ep.ldo = E;
+            MST_LAUNCH(CAT_GEMM_PROJ, Ops<bf16>::gemm(h, T.ao, E, L.wproj, M, E, E, EPI_BIAS_RES, ep, st));
+        }
+        MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(T.x_mid, ws.rowstat, M, E, 1e-6f, st));
+        if (L.fold_fc1) {
+            EpiParams ep{};
+            ep.bias = L.bfc1; ep.rowstat = ws.rowstat; ep.out = T.u; ep.ldo = 4 * E;
+            MST_LAUNCH(CAT_GEMM_FC1, Ops<bf16>::gemm(h, T.x_mid, E, L.wfc1, M, 4 * E, E, EPI_LN_BIAS, ep, st));
+        } else {   // the last block's fc1 is packed un-folded (inference runs it behind a real LayerNorm on the CLS rows)
+            MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<bf16, bf16>(T.x_mid, E, ws.ln, E, L.n2w, L.n2b, M, E, 1e-6f, st)));
+            EpiParams ep{};
+            ep.bias = L.bfc1; ep.out = T.u; ep.ldo = 4 * E;
+            MST_LAUNCH(CAT_GEMM_FC1, Ops<bf16>::gemm(h, ws.ln, E, L.wfc1, M, 4 * E, E, EPI_BIAS, ep, st));
+        }
+        MST_LAUNCH(CAT_GEMM_FC1, launch_gelu_fwd(T.u, T.hid, static_cast<int64_t>(M) * 4 * E, h->num_sms, st));
+        {
+            EpiParams ep{};
+            ep.bias = L.bfc2; ep.res = T.x_mid; ep.ldr = E; ep.out = x_next; ep.ldo = E;
+            MST_LAUNCH(CAT_GEMM_FC2, Ops<bf16>::gemm(h, T.hid, 4 * E, L.wfc2, M, E, 4 * E, EPI_BIAS_RES, ep, st));
+        }
+    }
+    // final encoder LayerNorm on the CLS rows (vision_transformer.py:263-265,329), fp32 out
+    MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<bf16, float>(ws.x_out, static_cast<int64_t>(N) * E, enc_out, E, h->master["encoder.norm.weight"],
+                                                         h->master["encoder.norm.bias"], BD, E, 1e-6f, st)));
+    return 0;
+}
+
+// ---- small gradient kernels of the token assembly (vision_transformer.py:219-220, patch_embed.py:75-77) ----
+// dX rows of token t summed over the slices: dpos[t] (token 0 also = dcls); conv-bias gradient = sum over the patch tokens
+__global__ void __launch_bounds__(128) token_grads_kernel(const bf16* __restrict__ dX, float* __restrict__ dpos, float* __restrict__ dcls,
+                                                           int BD, int N, int E) {
+    const int t = blockIdx.x;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        float a = 0.f;
+        for (int s = 0; s < BD; ++s) a += __bfloat162float(dX[(static_cast<int64_t>(s) * N + t) * E + e]);
+        dpos[static_cast<int64_t>(t) * E + e] = a;
+        if (t == 0 && dcls) dcls[e] = a;
+    }
+}
+__global__ void __launch_bounds__(128) conv_bias_grad_kernel(const float* __restrict__ dpos, float* __restrict__ dbias, int N, int E) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    float a = 0.f;
+    for (int t = 1; t < N; ++t) a += dpos[static_cast<int64_t>(t) * E + e];
+    dbias[e] = a;
+}
+// patch rows of dX (token rows 1.. of every slice) gathered contiguously: [BD*P, E]
+__global__ void __launch_bounds__(256) gather_patch_rows_kernel(const bf16* __restrict__ dX, bf16* __restrict__ out, int64_t rows, int P, int E) {
+    const int64_t n8 = rows * (E / 8);
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / (E / 8);
+        const int c = static_cast<int>(i - r * (E / 8));
+        const int64_t srow = (r / P) * (P + 1) + 1 + r % P;
+        reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(dX + srow * E)[c];
+    }
+}
+// wg [KP, E] fp32 (= dWsum^T) -> conv weight gradient [E, 3, 14, 14]: the three input channels carry the same gray image
+// (dino.py:127), so each gets the gradient of the channel-summed weight
+__global__ void conv_weight_grad_kernel(const float* __restrict__ wg, float* __restrict__ dW, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= E * 3 * 196) return;
+    const int n = i / (3 * 196), c = i % 196;
+    dW[i] = wg[static_cast<int64_t>(c) * E + n];
+}
+
+static float* grad_of(mst_handle h, const std::string& name) {
+    auto it = h->grad_ptr.find(name);
+    return it == h->grad_ptr.end() ? nullptr : it->second;
+}
+
+// dW = dY^T X (fp32) and db = column sums of dY, for Y = X W^T + b with dY [M, Nout], X [M, Kin]
+static int linear_wgrad(mst_handle h, const bf16* dY, int Nout, const bf16* X, int Kin, int M, const TrainWs& ws, float* dW, float* db,
+                        cudaStream_t st) {
+    if (db) MST_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Nout) * 4, st));
+    MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(dY, Nout, ws.Ta, db, M, Nout, ws.Mpad, st));
+    MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(X, Kin, ws.Tb, nullptr, M, Kin, ws.Mpad, st));
+    EpiParams ep{};
+    ep.out = dW; ep.ldo = Kin;
+    MST_LAUNCH(CAT_TRAIN_BACKWARD, gemm_bf16_tc(ws.Ta, ws.Tb, Nout, Kin, ws.Mpad, EPI_RAW_F32, ep, h->num_sms, st));
+    return 0;
+}
+// dX = dY W (bf16): the dgrad GEMM against W^T
+static int linear_dgrad(mst_handle h, const bf16* dY, int Nout, const void* WT, int Kin, int M, bf16* dX, cudaStream_t st) {
+    EpiParams ep{};
+    ep.bias = h->zero_bias; ep.out = dX; ep.ldo = Kin;
+    MST_LAUNCH(CAT_TRAIN_BACKWARD, gemm_bf16_tc(dY, static_cast<const bf16*>(WT), M, Kin, Nout, EPI_BIAS, ep, h->num_sms, st));
+    return 0;
+}
+
+static int train_backward(mst_handle h, const float* denc, int B, int D, int H, int W, const TrainWs& ws, cudaStream_t st) {
+    const mst_config& c = h->cfg;
+    const int E = c.embed_dim, BD = B * D, P = (H / 14) * (W / 14), N = P + 1, M = BD * N;
+    const int64_t ME = static_cast<int64_t>(M) * E;
+    float scratch_needed = 0.f; (void)scratch_needed;
+    // every gradient buffer must have been registered
+    auto need = [&](const std::string& n) -> float* { return grad_of(h, n); };
+    // final norm on the CLS rows: dX = 0 except the CLS rows
+    MST_CHECK_CUDA(cudaMemsetAsync(ws.dX, 0, ME * 2, st));
+    {
+        float* dg = need("encoder.norm.weight"); float* db = need("encoder.norm.bias");
+        MST_REQUIRE(dg && db, "mst_train_backward: gradient buffers of encoder.norm.* were not set");
+        // rows of dy / dx are the BD CLS rows; x rows are N*E apart; dx is written compactly into ws.dln and scattered below
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_ln_bwd(ws.x_out, static_cast<int64_t>(N) * E, nullptr, denc, nullptr, h->master["encoder.norm.weight"],
+                                                     ws.dln, dg, db, BD, E, 1e-6f, ws.lnws, st));
+        MST_CHECK_CUDA(cudaMemcpy2DAsync(ws.dX, static_cast<size_t>(N) * E * 2, ws.dln, static_cast<size_t>(E) * 2, static_cast<size_t>(E) * 2, BD,
+                                         cudaMemcpyDeviceToDevice, st));
+    }
+    for (int l = c.depth - 1; l >= 0; --l) {
+        const std::string p = "encoder.blocks." + std::to_string(l) + ".";
+        const TrainLayer& T = ws.L[l];
+        float *gqw = need(p + "attn.qkv.weight"), *gqb = need(p + "attn.qkv.bias"), *gpw = need(p + "attn.proj.weight"), *gpb = need(p + "attn.proj.bias");
+        float *g1w = need(p + "mlp.fc1.weight"), *g1b = need(p + "mlp.fc1.bias"), *g2w = need(p + "mlp.fc2.weight"), *g2b = need(p + "mlp.fc2.bias");
+        float *n1w = need(p + "norm1.weight"), *n1b = need(p + "norm1.bias"), *n2w = need(p + "norm2.weight"), *n2b = need(p + "norm2.bias");
+        MST_REQUIRE(gqw && gqb && gpw && gpb && g1w && g1b && g2w && g2b && n1w && n1b && n2w && n2b,
+                    "mst_train_backward: gradient buffers of block %d were not set", l);
+        // ---- x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))                                   (block.py:113, mlp.py:34-40) ----
+        MST_PROPAGATE(linear_wgrad(h, ws.dX, E, T.hid, 4 * E, M, ws, g2w, g2b, st));
+        MST_PROPAGATE(linear_dgrad(h, ws.dX, E, h->wT[4 * l + 3], 4 * E, M, ws.dhid, st));
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_gelu_bwd(T.u, ws.dhid, ws.dhid, static_cast<int64_t>(M) * 4 * E, h->num_sms, st));   // du, in place
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, (launch_layernorm<bf16, bf16>(T.x_mid, E, ws.ln, E, h->master[p + "norm2.weight"], h->master[p + "norm2.bias"],
+                                                                     M, E, 1e-6f, st)));
+        MST_PROPAGATE(linear_wgrad(h, ws.dhid, 4 * E, ws.ln, E, M, ws, g1w, g1b, st));
+        MST_PROPAGATE(linear_dgrad(h, ws.dhid, 4 * E, h->wT[4 * l + 2], E, M, ws.dln, st));
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_ln_bwd(T.x_mid, E, ws.dln, nullptr, ws.dX, h->master[p + "norm2.weight"], ws.dXm, n2w, n2b, M, E, 1e-6f,
+                                                     ws.lnws, st));
+        // ---- x_mid = x_in + proj(attn(LN1(x_in)))                                         (block.py:112, attention.py:56-69) ----
+        MST_PROPAGATE(linear_wgrad(h, ws.dXm, E, T.ao, E, M, ws, gpw, gpb, st));
+        MST_PROPAGATE(linear_dgrad(h, ws.dXm, E, h->wT[4 * l + 1], E, M, ws.dao, st));
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_attention_bwd(T.qkv, T.ao, ws.dao, ws.dqkv, BD, N, c.enc_heads, st));
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, (launch_layernorm<bf16, bf16>(T.x_in, E, ws.ln, E, h->master[p + "norm1.weight"], h->master[p + "norm1.bias"],
+                                                                     M, E, 1e-6f, st)));
+        MST_PROPAGATE(linear_wgrad(h, ws.dqkv, 3 * E, ws.ln, E, M, ws, gqw, gqb, st));
+        MST_PROPAGATE(linear_dgrad(h, ws.dqkv, 3 * E, h->wT[4 * l + 0], E, M, ws.dln, st));
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_ln_bwd(T.x_in, E, ws.dln, nullptr, ws.dXm, h->master[p + "norm1.weight"], ws.dX, n1w, n1b, M, E, 1e-6f,
+                                                     ws.lnws, st));
+    }
+    // ---- token assembly: x[s, 0] = cls + pos[0]; x[s, 1 + p] = conv(patch p) + bias + pos[1 + p] ----
+    float *gpos = need("encoder.pos_embed"), *gcls = need("encoder.cls_token"), *gcw = need("encoder.patch_embed.proj.weight"),
+          *gcb = need("encoder.patch_embed.proj.bias");
+    MST_REQUIRE(gpos && gcls && gcw && gcb, "mst_train_backward: gradient buffers of the patch embedding / position table were not set");
+    token_grads_kernel<<<N, 128, 0, st>>>(ws.dX, gpos, gcls, BD, N, E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    conv_bias_grad_kernel<<<(E + 127) / 128, 128, 0, st>>>(gpos, gcb, N, E);
+    MST_CHECK_CUDA(cudaGetLastError());
+    {
+        const int64_t rows = static_cast<int64_t>(BD) * P;
+        gather_patch_rows_kernel<<<h->num_sms * 4, 256, 0, st>>>(ws.dX, ws.dXm, rows, P, E);
+        MST_CHECK_CUDA(cudaGetLastError());
+        // dWsum^T [KP, E] = A0^T dXpatch: A = A0^T [KP rows, rows], weight = dXpatch^T [E rows, rows]
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(ws.A0, KP, ws.Ta, nullptr, static_cast<int>(rows), KP, ws.Mpad, st));
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(ws.dXm, E, ws.Tb, nullptr, static_cast<int>(rows), E, ws.Mpad, st));
+        EpiParams ep{};
+        ep.out = ws.wg; ep.ldo = E;
+        MST_LAUNCH(CAT_TRAIN_BACKWARD, gemm_bf16_tc(ws.Ta, ws.Tb, KP, E, ws.Mpad, EPI_RAW_F32, ep, h->num_sms, st));
+        conv_weight_grad_kernel<<<(E * 3 * 196 + 255) / 256, 256, 0, st>>>(ws.wg, gcw, E);
+        MST_CHECK_CUDA(cudaGetLastError());
+        h->launches += 4;
+    }
+    return 0;
+}
+
 }  // namespace mst
 
 // ---------------------------------------------------------------------------------------------------
@@ -690,6 +988,8 @@ int mst_destroy(mst_handle h) {
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     for (auto& kv : h->master) cudaFree(kv.second);
     for (void* p : h->owned) cudaFree(p);
+    for (void* p : h->wT) cudaFree(p);
+    if (h->zero_bias) cudaFree(h->zero_bias);
     for (auto& kv : h->pos_cache) cudaFree(kv.second);
     for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
     delete h;
@@ -721,9 +1021,8 @@ int mst_finalize_weights(mst_handle h, void* stream) {
     MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     MST_CHECK_CUDA(cudaStreamSynchronize(st));
-    drop_graphs(h);   // captured forwards hold the old packed-weight pointers
-    for (void* p : h->owned) cudaFree(p);
-    h->owned.clear();
+    drop_graphs(h);   // captured forwards were taken with the old weights' values in some kernels' constant parameters
+    h->owned_cursor = 0;   // packed buffers are reused in allocation order (same architecture => same sizes)
     if (h->cfg.precision == MST_PRECISION_BF16) {
         MST_PROPAGATE(tma_init());
         MST_PROPAGATE(finalize_t<bf16>(h, st));
@@ -966,6 +1265,51 @@ int mst_adamw(mst_handle h, float* p, const float* g, float* m, float* v, int64_
     MST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     MST_LAUNCH(CAT_ADAMW, launch_adamw(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, sms, st));
     return 0;
+}
+
+int mst_train_workspace_bytes(mst_handle h, int32_t B, int32_t D, int32_t H, int32_t W, size_t* bytes) {
+    MST_REQUIRE(h && bytes, "mst_train_workspace_bytes: null argument");
+    MST_PROPAGATE(check_shape(h, B, D, H, W));
+    MST_PROPAGATE(check_trainable(h, H, W));
+    *bytes = carve_train(h->cfg, B, D, H, W, nullptr).total;
+    return 0;
+}
+int mst_set_grad(mst_handle h, const char* name, float* dev_fp32, int64_t numel) {
+    MST_REQUIRE(h && name, "mst_set_grad: null argument");
+    const std::string key = canonical_name(name);
+    auto it = h->expected.find(key);
+    MST_REQUIRE(it != h->expected.end(), "mst_set_grad: unknown tensor '%s'", name);
+    MST_REQUIRE(dev_fp32 == nullptr || it->second == numel, "mst_set_grad: '%s' has %lld elements, expected %lld", name, (long long)numel,
+                (long long)it->second);
+    if (dev_fp32) h->grad_ptr[key] = dev_fp32; else h->grad_ptr.erase(key);
+    return 0;
+}
+int mst_train_forward(mst_handle h, const void* src, int32_t src_dtype, int32_t B, int32_t D, int32_t H, int32_t W, float* enc_cls,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    MST_REQUIRE(h && src && enc_cls && workspace, "mst_train_forward: null argument");
+    MST_REQUIRE(h->finalized, "mst_train_forward: weights not finalized");
+    MST_REQUIRE(src_dtype >= MST_SRC_F32 && src_dtype <= MST_SRC_F16, "mst_train_forward: bad src_dtype %d", src_dtype);
+    MST_PROPAGATE(check_shape(h, B, D, H, W));
+    MST_PROPAGATE(check_trainable(h, H, W));
+    MST_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "mst_train_forward: workspace must be 256-byte aligned");
+    TrainWs ws = carve_train(h->cfg, B, D, H, W, static_cast<uint8_t*>(workspace));
+    MST_REQUIRE(ws.total <= workspace_bytes, "mst_train_forward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    set_pdl(false);
+    return train_forward(h, src, src_dtype, B, D, H, W, enc_cls, ws, static_cast<cudaStream_t>(stream));
+}
+int mst_train_backward(mst_handle h, const float* denc, int32_t B, int32_t D, int32_t H, int32_t W, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+    MST_REQUIRE(h && denc && workspace, "mst_train_backward: null argument");
+    MST_PROPAGATE(check_shape(h, B, D, H, W));
+    MST_PROPAGATE(check_trainable(h, H, W));
+    TrainWs ws = carve_train(h->cfg, B, D, H, W, static_cast<uint8_t*>(workspace));
+    MST_REQUIRE(ws.total <= workspace_bytes, "mst_train_backward: workspace too small (%zu < %zu)", workspace_bytes, ws.total);
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    set_pdl(false);
+    MST_PROPAGATE(refresh_dgrad_weights(h, st));
+    return train_backward(h, denc, B, D, H, W, ws, st);
 }
 
 const char* mst_profile_categories(void) { return kCatNames; }

@@ -129,7 +129,7 @@ __device__ __forceinline__ float gelu_grad(float u) {
     const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
     return fmaf(u, pdf, cdf);
 }
-__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ u, const bf16* __restrict__ dy, bf16* __restrict__ du, int64_t n8) {
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ u, const bf16* dy, bf16* du, int64_t n8) {   // du may alias dy
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const uint4 a = reinterpret_cast<const uint4*>(u)[i], d = reinterpret_cast<const uint4*>(dy)[i];
         uint4 o;

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from new_vit_b200 import _cabi, synth
 from new_vit_b200._cabi import MSTError  # noqa: F401
-from new_vit_b200.training import SLICE_PARAM_NAMES, LightningSurface, SliceHeadFunction
+from new_vit_b200.training import SLICE_PARAM_NAMES, EncoderFunction, LightningSurface, SliceHeadFunction
 
 
 # ---- parameter containers that reproduce the reference's module tree (names only; never called) ----
@@ -351,7 +351,7 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
         # (torch optimizers) or by the flag FusedAdamW raises.  The training path reads the slice transformer's live parameters
         # and needs only the (frozen) encoder packed, so optimizer steps do not trigger a re-pack there.
         train_path = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        encoder_only = train_path or bool(kwargs.get("_encoder_only", False))
+        encoder_only = (train_path or bool(kwargs.get("_encoder_only", False))) and not any(p.requires_grad for p in self.encoder.parameters())
         stale = (self._param_version(encoder_only=True) != getattr(self, "_synced_version", (None, None))[0] if encoder_only else
                  (self._param_version() != getattr(self, "_synced_version", (None, None))[1] or getattr(self, "_params_stepped", False)))
         if self._dirty or self._handle is None or stale:
@@ -499,29 +499,36 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
         """train()-mode forward with autograd: the encoder runs as in inference (it must be frozen: its backward pass is not
         built), the slice transformer + head run in the differentiable CUDA path.  Dropouts are 0 and drop_path is 0 in the
         reference (dino.py:89), so train-mode arithmetic equals eval-mode arithmetic."""
-        if any(p.requires_grad for p in self.encoder.parameters()):
+        train_encoder = any(p.requires_grad for p in self.encoder.parameters())
+        if train_encoder and (self.precision != 'bf16' or self.num_registers or any(k.endswith("ls1.gamma") for k in self.state_dict())):
             raise NotImplementedError(
-                "training the encoder is not built (no encoder backward kernels): construct with freeze=True (dino.py:69-71) "
-                "or call .eval() / torch.no_grad() for inference")
+                "the encoder's backward pass is built for precision='bf16' on the vendored-factory architecture (no LayerScale, no "
+                "registers): construct with freeze=True (dino.py:69-71) to train the slice transformer + head only")
         if (self.slice_fusion_type != 'transformer' or hasattr(self, "bottleneck") or hasattr(self, "slice_pos_emb")
                 or self.rotary is not None or not self.enable_linear):
             raise NotImplementedError("the differentiable slice path covers the default construction (dino.py:84-103: transformer "
                                       "fusion, no bottleneck / slice position embedding / rotary, linear head)")
         B, C, D, H, W = source.shape
-        was_training = self.training
-        self.training = False                       # (re-enters forward() on the inference path; submodules are parameter holders)
-        try:
-            with torch.no_grad():
-                self.forward(source, src_key_padding_mask=src_key_padding_mask, return_enc_cls=True, _encoder_only=True)
-        finally:
-            self.training = was_training
-        enc = self._enc_cls.view(B, D, -1)
+        if train_encoder:
+            # every parameter trains (main_train.py:110-126 on the default construction): the encoder's CUDA training forward keeps
+            # its activations for the CUDA backward pass; all tensors of encoder.* take part, in state_dict order
+            named = [(n, p) for n, p in self.named_parameters() if n.startswith("encoder.")]
+            enc = EncoderFunction.apply(self, source, tuple(n for n, _ in named), *[p for _, p in named]).view(B, D, -1)
+        else:
+            was_training = self.training
+            self.training = False                   # (re-enters forward() on the inference path; submodules are parameter holders)
+            try:
+                with torch.no_grad():
+                    self.forward(source, src_key_padding_mask=src_key_padding_mask, return_enc_cls=True, _encoder_only=True)
+            finally:
+                self.training = was_training
+            enc = self._enc_cls.view(B, D, -1)
         mask = None
         if src_key_padding_mask is not None:
             mask = src_key_padding_mask.to(self.device).to(torch.uint8).contiguous()
         sd = dict(self.named_parameters())
         params = [sd[n] for n in SLICE_PARAM_NAMES]
-        return SliceHeadFunction.apply(self._handle, enc, mask, synth.SLICE_HEADS, False, *params)
+        return SliceHeadFunction.apply(self._handle, enc, mask, synth.SLICE_HEADS, train_encoder, *params)
 
     # -- instrumentation ------------------------------------------------------------------------------------
     def launch_count(self):

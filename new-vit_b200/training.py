@@ -79,6 +79,54 @@ class SliceHeadFunction(torch.autograd.Function):
         return (None, denc, None, None, None, *grads)
 
 
+class EncoderFunction(torch.autograd.Function):
+    """enc_cls [B*D, E] = DINOv2 encoder(source) with the CUDA training forward (every block's activations kept in `workspace`) and
+    the CUDA backward pass (csrc/train_enc.cu, api.cu train_forward / train_backward).  `params` are the encoder's parameters in
+    `names` order; their gradients come back as fp32 tensors written by mst_train_backward."""
+
+    @staticmethod
+    def forward(ctx, model, source, names, *params):
+        L = _cabi.lib()
+        dev = model.device
+        B, C, D, H, W = source.shape
+        E = model.encoder.embed_dim
+        if model.precision == 'bf16' and source.dtype in (torch.bfloat16, torch.float16):
+            src_dt = source.dtype
+        else:
+            src_dt = torch.float32
+        with torch.cuda.device(dev):
+            x = source.to(dev).to(src_dt).contiguous()
+            need = ctypes.c_size_t()
+            _cabi.check(L.mst_train_workspace_bytes(model._handle, B, D, H, W, ctypes.byref(need)))
+            ws = getattr(model, "_train_workspace", None)
+            if ws is None or ws.numel() < need.value or ws.device != dev:
+                model._train_workspace = None
+                ws = model._train_workspace = torch.empty(need.value, device=dev, dtype=torch.uint8)
+            enc = torch.empty((B * D, E), device=dev, dtype=torch.float32)
+            _cabi.check(L.mst_train_forward(model._handle, _cabi.ptr(x), _cabi.SRC_DTYPE[str(src_dt)], B, D, H, W, _cabi.ptr(enc), _cabi.ptr(ws),
+                                            ws.numel(), _stream()))
+        ctx.model, ctx.shape, ctx.names, ctx.ws = model, (B, D, H, W), names, ws
+        ctx.save_for_backward(*params)
+        return enc
+
+    @staticmethod
+    def backward(ctx, denc):
+        L = _cabi.lib()
+        model, (B, D, H, W), params = ctx.model, ctx.shape, ctx.saved_tensors
+        with torch.cuda.device(model.device):
+            grads = []
+            for n, p in zip(ctx.names, params):
+                if n == "encoder.mask_token":          # never read by the path (vision_transformer.py:216 masks=None)
+                    grads.append(None)
+                    continue
+                g = torch.empty(p.shape, device=p.device, dtype=torch.float32)
+                _cabi.check(L.mst_set_grad(model._handle, n.encode(), _cabi.ptr(g), g.numel()))
+                grads.append(g)
+            _cabi.check(L.mst_train_backward(model._handle, _cabi.ptr(denc.contiguous().float()), B, D, H, W, _cabi.ptr(ctx.ws), ctx.ws.numel(),
+                                             _stream()))
+        return (None, None, None, *grads)
+
+
 class FusedAdamW(torch.optim.Optimizer):
     """torch.optim.AdamW's update (decoupled weight decay, bias correction, eps outside the sqrt) as ONE kernel over a flat
     fp32 buffer per parameter group (mst_adamw).  The parameters are re-pointed at views of the flat buffer, so `.grad` written by

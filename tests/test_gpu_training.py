@@ -135,3 +135,54 @@ def test_unfrozen_encoder_training_is_refused_clearly():
         m(torch.zeros(1, 1, 2, 28, 28))
     m.eval()
     assert m(torch.zeros(1, 1, 2, 28, 28)).shape == (1, 2)       # inference under grad mode stays the inference path
+
+
+def _cosine(a, b):
+    return float(F.cosine_similarity(a.reshape(-1).double(), b.reshape(-1).double(), dim=0))
+
+
+def test_full_training_step_matches_reference_golden():
+    """Every parameter trainable (the construction main_train.py:36-37,110-126 trains): bf16 CUDA forward + backward of the whole
+    model against the fp32 gradients of the REAL reference (tests/golden/train_s_full_b2.npz: every 61st element of every
+    gradient + its norm).  bf16 activations / activation gradients: direction (cosine) and size (norm) per tensor."""
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    meta, g = load_golden("train_s_full_b2")
+    sd = synth.make_state_dict("s", 2, seed=meta["wseed"], variant="peaky", img_size=meta["H"])
+    x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
+    mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"])
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    m.train()
+    opt = m.configure_optimizers()[0]
+    opt.zero_grad()
+    batch = {"source": x, "target": g["target"].cuda(), "src_key_padding_mask": mask}
+    loss = m.training_step(batch, 0)
+    assert abs(float(loss) - float(g["loss"])) <= 2e-2
+    loss.backward()
+    params = dict(m.named_parameters())
+    assert params["encoder.mask_token"].grad is None
+    worst = {}
+    for n in meta["trainable"]:
+        got = params[n].grad.detach().cpu().reshape(-1)
+        want = g["grad." + n]
+        cos = _cosine(got[::meta["stride"]], want)
+        ratio = float(got.norm()) / max(float(g["norm." + n]), 1e-30)
+        worst[n] = (cos, ratio)
+    bad = {n: v for n, v in worst.items() if not (v[0] >= 0.98 and 0.9 <= v[1] <= 1.1)
+           # the key bias of every attention has an exactly-zero gradient (softmax rows sum to 1): pure rounding noise on both sides
+           and not n.endswith("attn.qkv.bias") and not n.endswith("in_proj_bias")}
+    assert not bad, bad
+    for n in meta["trainable"]:
+        if n.endswith("attn.qkv.bias"):   # ... so compare its q and v thirds only
+            E = 384
+            got = params[n].grad.detach().cpu()
+            idx = torch.arange(0, 3 * E)[::meta["stride"]]
+            keep = (idx < E) | (idx >= 2 * E)
+            assert _cosine(got[idx][keep], g["grad." + n][keep]) >= 0.98, n
+    # one optimizer step over all 22.5 M parameters, then a consistent eval forward
+    before = params["encoder.blocks.0.3.mlp.fc1.weight"].detach().clone()
+    opt.step()
+    assert float((params["encoder.blocks.0.3.mlp.fc1.weight"].detach() - before).abs().max()) > 0
+    m.eval()
+    with torch.no_grad():
+        assert torch.isfinite(m(x, src_key_padding_mask=mask)).all()

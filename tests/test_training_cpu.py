@@ -101,3 +101,34 @@ def test_liere_mirrors_the_reference():
             assert str(e.value) == errs[(B, D)]
         with torch.no_grad():
             assert ref(torch.zeros(1, 1, 32, 56, 56)).shape == (1, 2)     # the one shape it evaluates
+
+
+def oracle_full_train_step(sd, x, mask, target):
+    """Every parameter trainable (main_train.py:110-126 on the default construction): the oracle's functions under torch autograd."""
+    params = {k: v.clone().float().requires_grad_(True) for k, v in sd.items() if k != "encoder.mask_token"}
+    full = dict(sd)
+    full.update(params)
+    B, C, D, H, W = x.shape
+    img = x.float().permute(0, 2, 1, 3, 4).reshape(B * D, H, W)[:, None].repeat(1, 3, 1, 1)
+    enc, _ = O.encoder_forward(full, img, params["encoder.pos_embed"].shape[-1] // 64)
+    tok = torch.cat([params["cls_token"].repeat(B, 1, 1), enc.reshape(B, D, -1)], dim=1)
+    kpm = None if mask is None else torch.cat([torch.zeros((B, 1), dtype=torch.bool), mask.bool()], dim=1)
+    y, _ = O.slice_transformer(full, tok, kpm)
+    logits = F.linear(y[:, 0], params["linear.weight"], params["linear.bias"])
+    loss = F.cross_entropy(logits, target)
+    loss.backward()
+    return logits.detach(), loss.detach(), {n: p.grad for n, p in params.items()}
+
+
+def test_oracle_autograd_matches_reference_gradients_full_model():
+    meta, g = load_golden("train_s_full_b2")
+    sd = synth.make_state_dict("s", 2, seed=meta["wseed"], variant="peaky", img_size=meta["H"])
+    x = synth.make_volume(meta["B"], meta["D"], meta["H"], meta["W"], seed=meta["vseed"])
+    mask = synth.make_padding_mask(meta["B"], meta["D"], seed=meta["vseed"])
+    logits, loss, grads = oracle_full_train_step(sd, x, mask, g["target"])
+    torch.testing.assert_close(loss.reshape(1), g["loss"], rtol=1e-5, atol=1e-6)
+    assert len(meta["trainable"]) == 167           # all 168 tensors but encoder.mask_token (never read)
+    for n in meta["trainable"]:
+        got = grads[n].reshape(-1)
+        torch.testing.assert_close(got[::meta["stride"]], g["grad." + n], rtol=2e-3, atol=2e-5 * float(g["norm." + n]) + 1e-10,
+                                   msg=lambda m, n=n: f"{n}: {m}")
