@@ -230,32 +230,43 @@ def run_extras(model_s, dev, rank, world, timed, peaks):
                              "ms_per_step": ms, "volumes_per_sec": 64 / (ms * 1e-3), "algorithmic_bytes": by,
                              "gbs": by / ms / 1e6, "frac_of_hbm_peak": by / ms / 1e6 / hbm}
     del raw
-    # ---- config 5, frozen-encoder construction (freeze=True, dino.py:69-71): forward + CE loss + backward + gradient all-reduce
-    #      (NCCL, when world > 1) + AdamW, 8 volumes per GPU (the encoder's backward pass is not built: it runs without gradient) ----
-    mt = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", freeze=True).to(dev)
-    mt.load_state_dict(synth.make_state_dict("s", 2, seed=0))
-    mt.train()
-    opt = mt.configure_optimizers()[0]
-    xt = synth.make_volume(8, D, H, H, seed=300 + rank).to(dev)
-    batch = {"source": xt, "target": torch.randint(0, 2, (8,), device=dev), "uid": ["x"] * 8}
+    # ---- config 5: training step = forward + CrossEntropy + backward + gradient all-reduce (NCCL, when world > 1) + AdamW,
+    #      8 volumes per GPU (base_model.py:148-170,103-110; main_train.py:110-126).  Two constructions: every parameter trainable
+    #      (the default, what main_train.py trains) and freeze=True (dino.py:69-71: slice transformer + head only) ----
+    for key, frozen in (("config5_train", False), ("config5_train_frozen_encoder", True)):
+        mt = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", freeze=frozen).to(dev)
+        mt.load_state_dict(synth.make_state_dict("s", 2, seed=0))
+        mt.train()
+        opt = mt.configure_optimizers()[0]
+        xt = synth.make_volume(8, D, H, H, seed=300 + rank).to(dev)
+        batch = {"source": xt, "target": torch.randint(0, 2, (8,), device=dev), "uid": ["x"] * 8}
 
-    def train_step():
-        opt.zero_grad()
-        loss = mt.training_step(batch, 0)
-        loss.backward()
-        opt.step()
-        return loss
-    for _ in range(3):
-        train_step()
-    ms = timed(train_step, 10)
-    trainable = sum(p.numel() for p in mt.parameters() if p.requires_grad)
-    out["config5_train_frozen_encoder"] = {
-        "workload": f"config 5 (frozen encoder): training step fwd + CrossEntropy + bwd + {'NCCL gradient all-reduce + ' if world > 1 else ''}"
-                    f"AdamW, 8 volumes x 32 x 224x224 per GPU x {world} GPU; trainable = slice transformer + head ({trainable} parameters); "
-                    "the encoder runs forward-only (its backward kernels are not built)",
-        "value": 8 * world / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms, "trainable_parameters": trainable,
-        "grad_allreduce_bytes": trainable * 4 if world > 1 else 0, "loss": float(train_step())}
-    del mt, opt, xt, batch
+        def train_step():
+            opt.zero_grad()
+            loss = mt.training_step(batch, 0)
+            loss.backward()
+            opt.step()
+            return loss
+        for _ in range(3):
+            train_step()
+        ms = timed(train_step, 10)
+        mt.profile_begin()
+        for _ in range(3):
+            train_step()
+        prof = mt.profile_end()
+        trainable = sum(p.numel() for p in mt.parameters() if p.requires_grad)
+        # forward = 1x the algorithmic matmul FLOPs, backward = 2x (dgrad + wgrad) for what trains
+        fl = flops_per_volume(32) * (1 if frozen else 3) * 8
+        out[key] = {
+            "workload": f"config 5{' (frozen encoder)' if frozen else ''}: training step fwd + CrossEntropy + bwd + "
+                        f"{'NCCL gradient all-reduce + ' if world > 1 else ''}AdamW, bf16, 8 volumes x 32 x 224x224 per GPU x {world} GPU; "
+                        f"{trainable} trainable parameters" + ("; the encoder runs forward-only" if frozen else " (all of them)"),
+            "value": 8 * world / (ms * 1e-3), "unit": "volumes/s", "ms_per_step": ms, "trainable_parameters": trainable,
+            "grad_allreduce_bytes": trainable * 4 if world > 1 else 0, "loss": float(train_step().detach()),
+            "model_tflops": fl * world / (ms * 1e-3) / 1e12,
+            "ms_by_category": {k: round(v[0] / 3, 3) for k, v in prof.items() if v[1]}}
+        del mt, opt, xt, batch
+        torch.cuda.empty_cache()
     # ---- config 4 ----
     torch.cuda.empty_cache()
     mb = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", model_size="b", img_size=252).to(dev).eval()

@@ -128,13 +128,19 @@ def test_fused_adamw_matches_torch():
             torch.testing.assert_close(q.detach(), p.detach(), rtol=2e-6, atol=2e-7)
 
 
-def test_unfrozen_encoder_training_is_refused_clearly():
+def test_unsupported_training_configurations_say_so():
+    """The encoder's backward pass exists for bf16 at the position table's own grid; everything else raises a clear error, and
+    inference under grad mode stays the inference path."""
     from new_vit_b200 import DinoV2ClassifierSlice
-    m = DinoV2ClassifierSlice(1, 2, pretrained=False).cuda().train()
+    from new_vit_b200._cabi import MSTError
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="fp32").cuda().train()
     with pytest.raises(NotImplementedError, match="freeze=True"):
+        m(torch.zeros(1, 1, 2, 224, 224))
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16").cuda().train()
+    with pytest.raises(MSTError, match="position table's own grid"):
         m(torch.zeros(1, 1, 2, 28, 28))
     m.eval()
-    assert m(torch.zeros(1, 1, 2, 28, 28)).shape == (1, 2)       # inference under grad mode stays the inference path
+    assert m(torch.zeros(1, 1, 2, 28, 28)).shape == (1, 2)
 
 
 def _cosine(a, b):
@@ -157,10 +163,10 @@ def test_full_training_step_matches_reference_golden():
     opt.zero_grad()
     batch = {"source": x, "target": g["target"].cuda(), "src_key_padding_mask": mask}
     loss = m.training_step(batch, 0)
-    assert abs(float(loss) - float(g["loss"])) <= 2e-2
+    assert abs(float(loss.detach()) - float(g["loss"])) <= 2e-2
     loss.backward()
     params = dict(m.named_parameters())
-    assert params["encoder.mask_token"].grad is None
+    assert float(params["encoder.mask_token"].grad.abs().max()) == 0.0      # never read by the path: no gradient
     worst = {}
     for n in meta["trainable"]:
         got = params[n].grad.detach().cpu().reshape(-1)
@@ -168,7 +174,7 @@ def test_full_training_step_matches_reference_golden():
         cos = _cosine(got[::meta["stride"]], want)
         ratio = float(got.norm()) / max(float(g["norm." + n]), 1e-30)
         worst[n] = (cos, ratio)
-    bad = {n: v for n, v in worst.items() if not (v[0] >= 0.98 and 0.9 <= v[1] <= 1.1)
+    bad = {n: v for n, v in worst.items() if not (v[0] >= 0.99 and 0.95 <= v[1] <= 1.05)
            # the key bias of every attention has an exactly-zero gradient (softmax rows sum to 1): pure rounding noise on both sides
            and not n.endswith("attn.qkv.bias") and not n.endswith("in_proj_bias")}
     assert not bad, bad
