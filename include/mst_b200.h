@@ -78,6 +78,9 @@ MST_API int mst_destroy(mst_handle h);
  * "ls1.gamma"/"ls2.gamma").  dev_fp32 holds `numel` fp32 values on the device.  "encoder.mask_token" is
  * accepted and ignored (unused by the path). */
 MST_API int mst_set_weight(mst_handle h, const char* name, const float* dev_fp32, int64_t numel, void* stream);
+/* The same for `count` tensors in one call (names / dev_fp32 / numel are HOST arrays): what a training loop does every step. */
+MST_API int mst_set_weights(mst_handle h, int32_t count, const char* const* names, const float* const* dev_fp32, const int64_t* numel,
+                    void* stream);
 /* Pack the weights for the selected precision (bf16 conversion, 1/8 attention scale folded into Wq/bq,
  * LayerScale folded into proj/fc2, conv weight summed over the 3 identical RGB channels, slice-transformer
  * matrices transposed).  Fails if a required tensor was never set.  Synchronises `stream`. */

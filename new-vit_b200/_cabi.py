@@ -53,6 +53,7 @@ def lib():
     L.mst_create.argtypes = [ctypes.POINTER(MstConfig), ctypes.POINTER(vp)]
     L.mst_destroy.argtypes = [vp]
     L.mst_set_weight.argtypes = [vp, ctypes.c_char_p, vp, i64, vp]
+    L.mst_set_weights.argtypes = [vp, i32, vp, vp, vp, vp]
     L.mst_finalize_weights.argtypes = [vp, vp]
     L.mst_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(sz)]
     L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]

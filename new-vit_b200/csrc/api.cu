@@ -79,31 +79,62 @@ __global__ void __launch_bounds__(128) pack_linear_ln_kernel(const float* __rest
         qb[k] = __bfloat16_as_ushort(__float2bfloat16_rn(t));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double r = 0.0;
-        for (int k = 0; k < K; ++k) r += static_cast<double>(bf16_bits_to_float(qb[k]));
-        for (int iter = 0; iter < 64; ++iter) {
-            // the single one-step move (of an element not moved yet) that brings the row sum closest to zero
-            int best = -1;
-            uint16_t best_bits = 0;
-            double best_abs = fabs(r), best_d = 0.0;
-            for (int k = 0; k < K; ++k) {
-                const uint16_t bits = qb[k];
-                if ((bits & 0x7f80) == 0 || tk[k] == 3.0e38f) continue;     // zero / subnormal, or already moved
-                const float qv = bf16_bits_to_float(bits);
-                const bool up = r < 0.0;                                   // the row sum must grow
-                const uint16_t nb = (up == (qv > 0.f)) ? bits + 1 : bits - 1;
-                if ((nb & 0x7f80) == 0x7f80 || (nb & 0x7f80) == 0) continue;
-                const double d = static_cast<double>(bf16_bits_to_float(nb)) - static_cast<double>(qv);
-                if (fabs(r + d) < best_abs) { best_abs = fabs(r + d); best = k; best_bits = nb; best_d = d; }
-            }
-            if (best < 0) break;
-            qb[best] = best_bits;
-            tk[best] = 3.0e38f;   // marks the element as moved
-            r += best_d;
-        }
-        bd[n] = b[n] * f + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
+    // row sum of the rounded values (exact in double), then the greedy single-step moves, searched by the whole CTA
+    __shared__ double rsum[4];
+    __shared__ double cand_abs[4];
+    __shared__ int cand_k[4];
+    __shared__ double r_now;
+    {
+        double part = 0.0;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) part += static_cast<double>(bf16_bits_to_float(qb[k]));
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if ((threadIdx.x & 31) == 0) rsum[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) r_now = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
+        __syncthreads();
     }
+    for (int iter = 0; iter < 64; ++iter) {
+        const double r = r_now;
+        // the single one-step move (of an element not moved yet) that brings the row sum closest to zero
+        double best_abs = fabs(r);
+        int best = -1;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const uint16_t bits = qb[k];
+            if ((bits & 0x7f80) == 0 || tk[k] == 3.0e38f) continue;     // zero / subnormal, or already moved
+            const float qv = bf16_bits_to_float(bits);
+            const bool up = r < 0.0;                                   // the row sum must grow
+            const uint16_t nb = (up == (qv > 0.f)) ? bits + 1 : bits - 1;
+            if ((nb & 0x7f80) == 0x7f80 || (nb & 0x7f80) == 0) continue;
+            const double d = static_cast<double>(bf16_bits_to_float(nb)) - static_cast<double>(qv);
+            if (fabs(r + d) < best_abs) { best_abs = fabs(r + d); best = k; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {   // (ties: the smaller index, so the result does not depend on the reduction shape)
+            const double oa = __shfl_xor_sync(0xffffffffu, best_abs, o);
+            const int ok = __shfl_xor_sync(0xffffffffu, best, o);
+            if (ok >= 0 && (oa < best_abs || (oa == best_abs && (best < 0 || ok < best)))) { best_abs = oa; best = ok; }
+        }
+        if ((threadIdx.x & 31) == 0) { cand_abs[threadIdx.x >> 5] = best_abs; cand_k[threadIdx.x >> 5] = best; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double ba = fabs(r);
+            int bk = -1;
+            for (int w = 0; w < 4; ++w)
+                if (cand_k[w] >= 0 && (cand_abs[w] < ba || (cand_abs[w] == ba && bk >= 0 && cand_k[w] < bk))) { ba = cand_abs[w]; bk = cand_k[w]; }
+            if (bk >= 0) {
+                const uint16_t bits = qb[bk];
+                const float qv = bf16_bits_to_float(bits);
+                const uint16_t nb = ((r < 0.0) == (qv > 0.f)) ? bits + 1 : bits - 1;
+                r_now = r + (static_cast<double>(bf16_bits_to_float(nb)) - static_cast<double>(qv));
+                qb[bk] = nb;
+                tk[bk] = 3.0e38f;   // marks the element as moved
+            }
+            cand_k[0] = bk;
+        }
+        __syncthreads();
+        if (cand_k[0] < 0) break;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bd[n] = b[n] * f + ((red[1][0] + red[1][1]) + (red[1][2] + red[1][3]));
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) Wd[static_cast<int64_t>(n) * K + k] = __ushort_as_bfloat16(qb[k]);
 }
@@ -151,8 +182,9 @@ struct Layer {
 namespace mst {
 enum Cat { CAT_IM2COL = 0, CAT_GEMM_PATCH, CAT_LAYERNORM, CAT_GEMM_QKV, CAT_ATTENTION, CAT_GEMM_PROJ, CAT_GEMM_FC1,
            CAT_GEMM_FC2, CAT_CLS_ATTENTION, CAT_GEMM_CLS_ROWS, CAT_SLICE_FUSION, CAT_FULL_MAPS, CAT_SALIENCY_COMBINE,
-           CAT_SALIENCY_UPSAMPLE, CAT_PREPARE_VOLUME, CAT_TRAIN_FORWARD, CAT_TRAIN_BACKWARD, CAT_ADAMW, NUM_CAT };
-static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps,saliency_combine,saliency_upsample,prepare_volume,train_slice_forward,train_slice_backward,adamw";
+           CAT_SALIENCY_UPSAMPLE, CAT_PREPARE_VOLUME, CAT_TRAIN_FORWARD, CAT_TRAIN_BACKWARD, CAT_ADAMW,
+           CAT_BWD_ATTENTION, CAT_BWD_WGRAD, CAT_BWD_DGRAD, CAT_BWD_TRANSPOSE, CAT_BWD_POINTWISE, CAT_WEIGHT_PACK, NUM_CAT };
+static const char* kCatNames = "im2col,gemm_patch,layernorm,gemm_qkv,attention,gemm_proj,gemm_fc1,gemm_fc2,cls_attention,gemm_cls_rows,slice_fusion,full_maps,saliency_combine,saliency_upsample,prepare_volume,train_slice_forward,train_slice_backward,adamw,bwd_attention,bwd_wgrad_gemm,bwd_dgrad_gemm,bwd_transpose,bwd_layernorm_gelu,weight_pack";
 struct Profiler {
     bool on = false;
     std::vector<cudaEvent_t> pool;
@@ -839,18 +871,18 @@ static float* grad_of(mst_handle h, const std::string& name) {
 static int linear_wgrad(mst_handle h, const bf16* dY, int Nout, const bf16* X, int Kin, int M, const TrainWs& ws, float* dW, float* db,
                         cudaStream_t st) {
     if (db) MST_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Nout) * 4, st));
-    MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(dY, Nout, ws.Ta, db, M, Nout, ws.Mpad, st));
-    MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(X, Kin, ws.Tb, nullptr, M, Kin, ws.Mpad, st));
+    MST_LAUNCH(CAT_BWD_TRANSPOSE, launch_transpose_colsum(dY, Nout, ws.Ta, db, M, Nout, ws.Mpad, st));
+    MST_LAUNCH(CAT_BWD_TRANSPOSE, launch_transpose_colsum(X, Kin, ws.Tb, nullptr, M, Kin, ws.Mpad, st));
     EpiParams ep{};
     ep.out = dW; ep.ldo = Kin;
-    MST_LAUNCH(CAT_TRAIN_BACKWARD, gemm_bf16_tc(ws.Ta, ws.Tb, Nout, Kin, ws.Mpad, EPI_RAW_F32, ep, h->num_sms, st));
+    MST_LAUNCH(CAT_BWD_WGRAD, gemm_bf16_tc(ws.Ta, ws.Tb, Nout, Kin, ws.Mpad, EPI_RAW_F32, ep, h->num_sms, st));
     return 0;
 }
 // dX = dY W (bf16): the dgrad GEMM against W^T
 static int linear_dgrad(mst_handle h, const bf16* dY, int Nout, const void* WT, int Kin, int M, bf16* dX, cudaStream_t st) {
     EpiParams ep{};
     ep.bias = h->zero_bias; ep.out = dX; ep.ldo = Kin;
-    MST_LAUNCH(CAT_TRAIN_BACKWARD, gemm_bf16_tc(dY, static_cast<const bf16*>(WT), M, Kin, Nout, EPI_BIAS, ep, h->num_sms, st));
+    MST_LAUNCH(CAT_BWD_DGRAD, gemm_bf16_tc(dY, static_cast<const bf16*>(WT), M, Kin, Nout, EPI_BIAS, ep, h->num_sms, st));
     return 0;
 }
 
@@ -867,7 +899,7 @@ static int train_backward(mst_handle h, const float* denc, int B, int D, int H, 
         float* dg = need("encoder.norm.weight"); float* db = need("encoder.norm.bias");
         MST_REQUIRE(dg && db, "mst_train_backward: gradient buffers of encoder.norm.* were not set");
         // rows of dy / dx are the BD CLS rows; x rows are N*E apart; dx is written compactly into ws.dln and scattered below
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_ln_bwd(ws.x_out, static_cast<int64_t>(N) * E, nullptr, denc, nullptr, h->master["encoder.norm.weight"],
+        MST_LAUNCH(CAT_BWD_POINTWISE, launch_ln_bwd(ws.x_out, static_cast<int64_t>(N) * E, nullptr, denc, nullptr, h->master["encoder.norm.weight"],
                                                      ws.dln, dg, db, BD, E, 1e-6f, ws.lnws, st));
         MST_CHECK_CUDA(cudaMemcpy2DAsync(ws.dX, static_cast<size_t>(N) * E * 2, ws.dln, static_cast<size_t>(E) * 2, static_cast<size_t>(E) * 2, BD,
                                          cudaMemcpyDeviceToDevice, st));
@@ -883,22 +915,22 @@ static int train_backward(mst_handle h, const float* denc, int B, int D, int H, 
         // ---- x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))                                   (block.py:113, mlp.py:34-40) ----
         MST_PROPAGATE(linear_wgrad(h, ws.dX, E, T.hid, 4 * E, M, ws, g2w, g2b, st));
         MST_PROPAGATE(linear_dgrad(h, ws.dX, E, h->wT[4 * l + 3], 4 * E, M, ws.dhid, st));
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_gelu_bwd(T.u, ws.dhid, ws.dhid, static_cast<int64_t>(M) * 4 * E, h->num_sms, st));   // du, in place
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, (launch_layernorm<bf16, bf16>(T.x_mid, E, ws.ln, E, h->master[p + "norm2.weight"], h->master[p + "norm2.bias"],
+        MST_LAUNCH(CAT_BWD_POINTWISE, launch_gelu_bwd(T.u, ws.dhid, ws.dhid, static_cast<int64_t>(M) * 4 * E, h->num_sms, st));   // du, in place
+        MST_LAUNCH(CAT_BWD_POINTWISE, (launch_layernorm<bf16, bf16>(T.x_mid, E, ws.ln, E, h->master[p + "norm2.weight"], h->master[p + "norm2.bias"],
                                                                      M, E, 1e-6f, st)));
         MST_PROPAGATE(linear_wgrad(h, ws.dhid, 4 * E, ws.ln, E, M, ws, g1w, g1b, st));
         MST_PROPAGATE(linear_dgrad(h, ws.dhid, 4 * E, h->wT[4 * l + 2], E, M, ws.dln, st));
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_ln_bwd(T.x_mid, E, ws.dln, nullptr, ws.dX, h->master[p + "norm2.weight"], ws.dXm, n2w, n2b, M, E, 1e-6f,
+        MST_LAUNCH(CAT_BWD_POINTWISE, launch_ln_bwd(T.x_mid, E, ws.dln, nullptr, ws.dX, h->master[p + "norm2.weight"], ws.dXm, n2w, n2b, M, E, 1e-6f,
                                                      ws.lnws, st));
         // ---- x_mid = x_in + proj(attn(LN1(x_in)))                                         (block.py:112, attention.py:56-69) ----
         MST_PROPAGATE(linear_wgrad(h, ws.dXm, E, T.ao, E, M, ws, gpw, gpb, st));
         MST_PROPAGATE(linear_dgrad(h, ws.dXm, E, h->wT[4 * l + 1], E, M, ws.dao, st));
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_attention_bwd(T.qkv, T.ao, ws.dao, ws.dqkv, BD, N, c.enc_heads, st));
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, (launch_layernorm<bf16, bf16>(T.x_in, E, ws.ln, E, h->master[p + "norm1.weight"], h->master[p + "norm1.bias"],
+        MST_LAUNCH(CAT_BWD_ATTENTION, launch_attention_bwd(T.qkv, T.ao, ws.dao, ws.dqkv, BD, N, c.enc_heads, st));
+        MST_LAUNCH(CAT_BWD_POINTWISE, (launch_layernorm<bf16, bf16>(T.x_in, E, ws.ln, E, h->master[p + "norm1.weight"], h->master[p + "norm1.bias"],
                                                                      M, E, 1e-6f, st)));
         MST_PROPAGATE(linear_wgrad(h, ws.dqkv, 3 * E, ws.ln, E, M, ws, gqw, gqb, st));
         MST_PROPAGATE(linear_dgrad(h, ws.dqkv, 3 * E, h->wT[4 * l + 0], E, M, ws.dln, st));
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_ln_bwd(T.x_in, E, ws.dln, nullptr, ws.dXm, h->master[p + "norm1.weight"], ws.dX, n1w, n1b, M, E, 1e-6f,
+        MST_LAUNCH(CAT_BWD_POINTWISE, launch_ln_bwd(T.x_in, E, ws.dln, nullptr, ws.dXm, h->master[p + "norm1.weight"], ws.dX, n1w, n1b, M, E, 1e-6f,
                                                      ws.lnws, st));
     }
     // ---- token assembly: x[s, 0] = cls + pos[0]; x[s, 1 + p] = conv(patch p) + bias + pos[1 + p] ----
@@ -914,11 +946,11 @@ static int train_backward(mst_handle h, const float* denc, int B, int D, int H, 
         gather_patch_rows_kernel<<<h->num_sms * 4, 256, 0, st>>>(ws.dX, ws.dXm, rows, P, E);
         MST_CHECK_CUDA(cudaGetLastError());
         // dWsum^T [KP, E] = A0^T dXpatch: A = A0^T [KP rows, rows], weight = dXpatch^T [E rows, rows]
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(ws.A0, KP, ws.Ta, nullptr, static_cast<int>(rows), KP, ws.Mpad, st));
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, launch_transpose_colsum(ws.dXm, E, ws.Tb, nullptr, static_cast<int>(rows), E, ws.Mpad, st));
+        MST_LAUNCH(CAT_BWD_TRANSPOSE, launch_transpose_colsum(ws.A0, KP, ws.Ta, nullptr, static_cast<int>(rows), KP, ws.Mpad, st));
+        MST_LAUNCH(CAT_BWD_TRANSPOSE, launch_transpose_colsum(ws.dXm, E, ws.Tb, nullptr, static_cast<int>(rows), E, ws.Mpad, st));
         EpiParams ep{};
         ep.out = ws.wg; ep.ldo = E;
-        MST_LAUNCH(CAT_TRAIN_BACKWARD, gemm_bf16_tc(ws.Ta, ws.Tb, KP, E, ws.Mpad, EPI_RAW_F32, ep, h->num_sms, st));
+        MST_LAUNCH(CAT_BWD_WGRAD, gemm_bf16_tc(ws.Ta, ws.Tb, KP, E, ws.Mpad, EPI_RAW_F32, ep, h->num_sms, st));
         conv_weight_grad_kernel<<<(E * 3 * 196 + 255) / 256, 256, 0, st>>>(ws.wg, gcw, E);
         MST_CHECK_CUDA(cudaGetLastError());
         h->launches += 4;
@@ -1012,6 +1044,12 @@ int mst_set_weight(mst_handle h, const char* name, const float* dev_fp32, int64_
     MST_CHECK_CUDA(cudaMemcpyAsync(dst, dev_fp32, numel * sizeof(float), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     h->have[key] = true;
     h->finalized = false;
+    return 0;
+}
+
+int mst_set_weights(mst_handle h, int32_t count, const char* const* names, const float* const* dev_fp32, const int64_t* numel, void* stream) {
+    MST_REQUIRE(h && names && dev_fp32 && numel && count >= 0, "mst_set_weights: null argument");
+    for (int i = 0; i < count; ++i) MST_PROPAGATE(mst_set_weight(h, names[i], dev_fp32[i], numel[i], stream));
     return 0;
 }
 

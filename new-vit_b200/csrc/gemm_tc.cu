@@ -275,6 +275,10 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     const int n_tiles = N / BN;
     const int m_tiles = (M + BMT - 1) / BMT;
     const int kchunks = K / BK;
+    // split-K (weight gradients: few output tiles, a contraction over all tokens): mode_flags >> 16 units share one output tile, each
+    // takes a contiguous range of k-chunks and adds its partial product to the (zero-initialised) fp32 output
+    const int ksplit = kResident ? 1 : max(1, mode_flags >> 16);
+    const int kper = (kchunks + ksplit - 1) / ksplit;
 
     // tile sequence of this CTA (cta_group::2: of this CTA pair -- both CTAs walk the same tiles, 128 rows each)
     const int unit = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
@@ -291,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         t_first = unit; t_step = units;
         t_count = unit < m_tiles ? ((m_tiles - unit + units - 1) / units) * n_tiles : 0;
     } else {
-        const int total = m_tiles * n_tiles;
+        const int total = m_tiles * n_tiles * ksplit;
         t_first = unit; t_step = units;
         t_count = t_first < total ? (total - t_first + t_step - 1) / t_step : 0;
     }
@@ -349,8 +353,10 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < t_count; ++it) {
                 const int t = t_first + it * t_step;
-                const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : t / n_tiles);
-                const int n_blk = kResident ? n_fixed : (seqn ? it % n_tiles : t % n_tiles);
+                const int tt = t / ksplit, kpart = t - tt * ksplit;
+                const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : tt / n_tiles);
+                const int n_blk = kResident ? n_fixed : (seqn ? it % n_tiles : tt % n_tiles);
+                const int kc0 = kpart * kper, kc1 = min(kchunks, kc0 + kper);
                 // (streaming mode: prefetching there made fc2 13 % slower -- every CTA of an m-block row would issue the same
                 //  prefetches -- so it is limited to the resident schedule, where one cluster per m-group issues them)
                 if (kResident && n_fixed < MC && it + kPrefetchTiles < t_count) {
@@ -360,7 +366,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     for (int kc = 0; kc < kchunks; ++kc)
                         tma_prefetch_l2_2d(&tmA, kc * BK, m_pf * BMT + row_off + (MCAST ? static_cast<int>(cta_rank) * (BM / MC) : 0));
                 }
-                for (int kc = 0; kc < kchunks; ++kc) {
+                for (int kc = kc0; kc < kc1; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (TWO) {
                         const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
@@ -405,7 +411,9 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             gd[0] += MST_DBG_CLOCK() - g0;
             tc_fence_after_sync();
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-            for (int kc = 0; kc < kchunks; ++kc) {
+            const int kpart_m = (t_first + it * t_step) % ksplit;
+            const int kc0 = kpart_m * kper, kc1 = min(kchunks, kc0 + kper);
+            for (int kc = kc0; kc < kc1; ++kc) {
                 const long long g1 = MST_DBG_CLOCK();
                 mbar_wait(&full_bar[stage], phase);
                 gd[1] += MST_DBG_CLOCK() - g1;
@@ -417,18 +425,18 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     for (int k = 0; k < BK / 16; ++k) {
                         if (TWO)
                             umma_bf16_ss_pair(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
-                                              (kc | k) != 0 ? 1u : 0u);
+                                              (kc != kc0 || k != 0) ? 1u : 0u);
                         else
                             umma_bf16_ss(d_tmem, make_desc(a_lo + 2 * k, kDescHi), make_desc(b_lo + 2 * k, kDescHi), idesc,
-                                         (kc | k) != 0 ? 1u : 0u);
+                                         (kc != kc0 || k != 0) ? 1u : 0u);
                     }
                     if (TWO) {
                         umma_commit_pair(&empty_bar[stage], 0x3);                          // both CTAs refill their slot
-                        if (kc == kchunks - 1) umma_commit_pair(&tfull_bar[acc], 0x3);      // both epilogues read their half
+                        if (kc == kc1 - 1) umma_commit_pair(&tfull_bar[acc], 0x3);          // both epilogues read their half
                     } else {
                         if (MCAST) umma_commit_multicast(&empty_bar[stage], (1u << MC) - 1);  // every CTA of the cluster refills this slot
                         else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-                        if (kc == kchunks - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+                        if (kc == kc1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
                     }
                 }
                 __syncwarp();
@@ -451,8 +459,9 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
         const bool stats_on = (L::STAT_BYTES > 0 && seqn) || (kResident && ep.rowpart_out != nullptr);
         for (int it = 0; it < t_count; ++it) {
             const int t = t_first + it * t_step;
-            const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : t / n_tiles);
-            const int n_blk = kResident ? n_fixed : (seqn ? it % n_tiles : t % n_tiles);
+            const int tt = t / ksplit;
+            const int m_blk = kResident ? t : (seqn ? t_first + (it / n_tiles) * t_step : tt / n_tiles);
+            const int n_blk = kResident ? n_fixed : (seqn ? it % n_tiles : tt % n_tiles);
             const int row0 = m_blk * BMT + row_off + q * 32;
             const int64_t row = static_cast<int64_t>(row0) + lane;
             const bool row_ok = row < M;
@@ -466,13 +475,21 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
 
             const bool dbg_w = kDbgTiming && ep.dbg != nullptr && blockIdx.x == 0 && e == 0 && lane == 0;
             auto process = [&](const uint32_t (&r)[32], int c) {
-                if (mode == EPI_RAW_F32) {   // weight gradients: the fp32 accumulators as they are (small outputs: per-lane row stores)
+                if (mode == EPI_RAW_F32) {   // weight gradients: the fp32 accumulators as they are (small outputs: per-lane row accesses)
                     if (row_ok) {
-                        float4* po = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + row * ep.ldo + nbase + c * 32);
+                        float* pf = static_cast<float*>(ep.out) + row * ep.ldo + nbase + c * 32;
+                        if (ksplit > 1) {        // split-K partial: fp32 vector reductions into the zero-initialised output
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            po[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
-                                                __uint_as_float(r[4 * i + 3]));
+                            for (int i = 0; i < 8; ++i)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(pf + 4 * i), "f"(__uint_as_float(r[4 * i])),
+                                             "f"(__uint_as_float(r[4 * i + 1])), "f"(__uint_as_float(r[4 * i + 2])), "f"(__uint_as_float(r[4 * i + 3]))
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(pf)[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                        }
                     }
                     return;
                 }
@@ -686,7 +703,9 @@ static int launch_cfg(const TmaDesc& tmA, const TmaDesc& tmB, const TmaDesc& tmC
         if (gs > m_tiles) gs = m_tiles;
         grid = gs * n_tiles * CPU_;
     } else {
-        grid = (m_tiles * n_tiles < units ? m_tiles * n_tiles : units) * CPU_;
+        const int ksplit = (mode >> 16) > 1 ? (mode >> 16) : 1;
+        const long long total = static_cast<long long>(m_tiles) * n_tiles * ksplit;
+        grid = static_cast<int>(total < units ? total : units) * CPU_;
     }
     if (MCAST) {
         cudaLaunchConfig_t cfg{};
@@ -734,6 +753,20 @@ int gemm_bf16_tc(const bf16* A, const bf16* W, int M, int N, int K, int mode, co
     MST_REQUIRE(N % 192 == 0 || N % 128 == 0, "gemm: N=%d must be a multiple of 192 or 128", N);
     MST_REQUIRE(ep.ldo % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
     MST_REQUIRE(mode != EPI_RAW_F32 || (K > 384 && N % 192 == 0), "gemm: fp32 output is wired for the streaming schedule (K > 384, N %% 192 == 0)");
+    if (mode == EPI_RAW_F32) {
+        // few output tiles, a long contraction: split K so that every SM pair has work (partials meet by fp32 reductions, so the
+        // output is zeroed first; the summation order across the splits is not fixed)
+        const int tiles = ((M + 255) / 256) * (N / 192);
+        int ks = (num_sms / 2) / (tiles > 0 ? tiles : 1);
+        const int kchunks = K / BK;
+        if (ks > kchunks / 8) ks = kchunks / 8;    // at least 8 k-chunks per unit
+        if (ks > 64) ks = 64;
+        while (ks > 1 && (ks - 1) * ((kchunks + ks - 1) / ks) >= kchunks) --ks;   // every unit gets a non-empty range of k-chunks
+        if (ks > 1) {
+            MST_CHECK_CUDA(cudaMemsetAsync(ep.out, 0, static_cast<size_t>(M) * ep.ldo * sizeof(float), stream));
+            mode |= ks << 16;
+        }
+    }
     // in-place residual update: `out += acc + bias` as 16-byte vector reductions (no residual read by the SM)
     const bool want_stats = ep.rowstat_out != nullptr;
     if (ep.rowpart_out != nullptr) {

@@ -163,34 +163,65 @@ int launch_gelu_bwd(const bf16* u, const bf16* dy, bf16* du, int64_t n, int num_
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) transpose_colsum_kernel(const bf16* __restrict__ in, int64_t ld, bf16* __restrict__ out,
                                                                 float* __restrict__ colsum, int M, int C, int Mpad) {
-    __shared__ bf16 tile[64][66];
+    // 64 (tokens) x 64 (features) tile held as 32-bit words (two adjacent features per word), rows padded to 33 words.
+    // Load: 8 lanes read one token row's 128 bytes (16-byte loads).  Store: 8 lanes write 64 consecutive tokens of one feature
+    // row (128 contiguous bytes), each lane gathering its 8 tokens from 8 tile rows (one PRMT per output word).
+    __shared__ uint32_t tile[64][33];
+    __shared__ float csum[64];
     const int m0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
-    // load: rows m0 + r, 64 columns (2 per lane)
-    for (int r = ty; r < 64; r += 8) {
-        const int m = m0 + r;
-        uint32_t v = 0u;
-        if (m < M) v = *reinterpret_cast<const uint32_t*>(in + static_cast<int64_t>(m) * ld + c0 + 2 * tx);
-        *reinterpret_cast<uint32_t*>(&tile[r][2 * tx]) = v;
-    }
+    if (threadIdx.x < 64) csum[threadIdx.x] = 0.f;
     __syncthreads();
-    // store: out rows c0 + c, 64 consecutive m (2 per lane)
-    for (int c = ty; c < 64; c += 8) {
-        const bf16 a = tile[2 * tx][c], b = tile[2 * tx + 1][c];
-        if (m0 + 2 * tx < Mpad) {
-            __nv_bfloat162 p;
-            p.x = a; p.y = b;
-            *reinterpret_cast<__nv_bfloat162*>(out + static_cast<int64_t>(c0 + c) * Mpad + m0 + 2 * tx) = p;
+    {
+        const int q = threadIdx.x & 7;
+        float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            const int r = pass * 32 + (threadIdx.x >> 3), m = m0 + r;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (m < M) v = __ldg(reinterpret_cast<const uint4*>(in + static_cast<int64_t>(m) * ld + c0 + 8 * q));
+            tile[r][4 * q + 0] = v.x; tile[r][4 * q + 1] = v.y; tile[r][4 * q + 2] = v.z; tile[r][4 * q + 3] = v.w;
+            if (colsum) {
+                float2 f;
+                f = unpack_bf16x2(v.x); cs[0] += f.x; cs[1] += f.y;
+                f = unpack_bf16x2(v.y); cs[2] += f.x; cs[3] += f.y;
+                f = unpack_bf16x2(v.z); cs[4] += f.x; cs[5] += f.y;
+                f = unpack_bf16x2(v.w); cs[6] += f.x; cs[7] += f.y;
+            }
         }
         if (colsum) {
-            float s = __bfloat162float(a) + __bfloat162float(b);
-            s = wsum32(s);
-            if (tx == 0) atomicAdd(colsum + c0 + c, s);
+            // lanes q, q+8, q+16, q+24 of a warp hold the same 8 columns
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+                cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+            }
+            if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(&csum[8 * q + j], cs[j]);
+            }
         }
     }
+    __syncthreads();
+    {
+        const int mg = threadIdx.x & 7, cw = threadIdx.x >> 3;   // 8 tokens mg*8.., feature pair cw (features 2cw, 2cw+1)
+        uint32_t w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = tile[mg * 8 + j][cw];
+        uint4 lo, hi;   // feature 2cw: low halves; feature 2cw+1: high halves
+        lo.x = __byte_perm(w[0], w[1], 0x5410); lo.y = __byte_perm(w[2], w[3], 0x5410);
+        lo.z = __byte_perm(w[4], w[5], 0x5410); lo.w = __byte_perm(w[6], w[7], 0x5410);
+        hi.x = __byte_perm(w[0], w[1], 0x7632); hi.y = __byte_perm(w[2], w[3], 0x7632);
+        hi.z = __byte_perm(w[4], w[5], 0x7632); hi.w = __byte_perm(w[6], w[7], 0x7632);
+        bf16* o0 = out + static_cast<int64_t>(c0 + 2 * cw) * Mpad + m0 + mg * 8;
+        *reinterpret_cast<uint4*>(o0) = lo;
+        *reinterpret_cast<uint4*>(o0 + Mpad) = hi;
+    }
+    if (colsum && threadIdx.x < 64) atomicAdd(colsum + c0 + threadIdx.x, csum[threadIdx.x]);
 }
 int launch_transpose_colsum(const bf16* in, int64_t ld, bf16* out, float* colsum, int M, int C, int Mpad, cudaStream_t stream) {
-    MST_REQUIRE(C % 64 == 0 && Mpad % 64 == 0 && Mpad >= M && ld % 2 == 0, "transpose: C=%d Mpad=%d M=%d unsupported", C, Mpad, M);
+    MST_REQUIRE(C % 64 == 0 && Mpad % 64 == 0 && Mpad >= M && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "transpose: C=%d Mpad=%d M=%d ld=%lld unsupported", C, Mpad, M, (long long)ld);
     dim3 grid(Mpad / 64, C / 64);
     transpose_colsum_kernel<<<grid, 256, 0, stream>>>(in, ld, out, colsum, M, C, Mpad);
     MST_CHECK_CUDA(cudaGetLastError());
@@ -229,8 +260,7 @@ namespace mst {
 // The N x N probabilities exist only as register fragments.
 // ---------------------------------------------------------------------------------------------------
 namespace attb {
-constexpr int WARPS = 8;
-constexpr int THREADS = WARPS * 32;
+constexpr int MAX_WARPS = 12;     // warps = ceil(row blocks / 2): 17 blocks of 16 rows (N = 257) -> 9 warps, two rounds per phase
 constexpr float LOG2E = 1.4426950408889634f;
 
 // A-operand fragments of 16 rows (g, g+8) x 64 dims from a swizzled [rows][128 B] shared-memory tile
@@ -281,7 +311,7 @@ __device__ __forceinline__ void mma_cols(float (&out)[8][4], const float (&c)[4]
 }
 }  // namespace attb
 
-__global__ void __launch_bounds__(attb::THREADS, 1)
+__global__ void __launch_bounds__(attb::MAX_WARPS * 32, 1)
 attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
                      int N, int heads, int NKP) {
     using namespace attb;
@@ -301,6 +331,7 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, c
     bf16* dbase = dqkv + static_cast<int64_t>(s) * N * ld + h * 64;
     const uint32_t qs_u = smem_u32(Qs), ks_u = smem_u32(Ks), vs_u = smem_u32(Vs), gs_u = smem_u32(Gs);
 
+    const int THREADS = blockDim.x, WARPS = blockDim.x >> 5;
     for (int idx = threadIdx.x; idx < NKP * 8; idx += THREADS) {
         const int r = idx >> 3, c = idx & 7;
         const uint32_t off = r * 128 + ((c ^ (r & 7)) << 4);
@@ -470,7 +501,9 @@ int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* d
     const size_t smem = static_cast<size_t>(NKP) * (4 * 128 + 8);
     MST_REQUIRE(smem <= 227 * 1024, "attention backward: N=%d tokens do not fit shared memory", N);
     MST_SET_DYN_SMEM(attention_bwd_kernel, 227 * 1024);
-    attention_bwd_kernel<<<BD * heads, attb::THREADS, smem, stream>>>(qkv, o, dO, dqkv, N, heads, NKP);
+    int warps = ((N + 15) / 16 + 1) / 2;
+    warps = warps < 4 ? 4 : (warps > attb::MAX_WARPS ? attb::MAX_WARPS : warps);
+    attention_bwd_kernel<<<BD * heads, warps * 32, smem, stream>>>(qkv, o, dO, dqkv, N, heads, NKP);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

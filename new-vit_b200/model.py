@@ -317,11 +317,14 @@ class DinoV2ClassifierSlice(LightningSurface, nn.Module):
             self._static = {}
         with torch.cuda.device(dev):
             stream = _cabi.ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-            keep = []
+            names, keep = [], []
             for name, t in self.state_dict().items():
-                t32 = t.detach().to(device=dev, dtype=torch.float32).contiguous()
-                keep.append(t32)
-                _cabi.check(L.mst_set_weight(self._handle, name.encode(), _cabi.ptr(t32), t32.numel(), stream))
+                names.append(name.encode())
+                keep.append(t.detach().to(device=dev, dtype=torch.float32).contiguous())
+            n = len(names)
+            _cabi.check(L.mst_set_weights(self._handle, n, (_cabi.ctypes.c_char_p * n)(*names),
+                                          (_cabi.ctypes.c_void_p * n)(*[t.data_ptr() for t in keep]),
+                                          (_cabi.ctypes.c_int64 * n)(*[t.numel() for t in keep]), stream))
             _cabi.check(L.mst_finalize_weights(self._handle, stream))
         self._dirty = False
         self._synced_version = (self._param_version(encoder_only=True), self._param_version())
