@@ -38,7 +38,8 @@ enum { MST_SRC_F32 = 0, MST_SRC_BF16 = 1, MST_SRC_F16 = 2 };
  * reference dino.py:33-103 (model_size -> embed_dim/depth/enc_heads per vision_transformer.py:340-396). */
 typedef struct mst_config {
     int32_t embed_dim;   /* 384 (ViT-S/14), 768 (ViT-B/14), 1024 (ViT-L/14); head_dim is always 64 */
-    int32_t depth;       /* encoder blocks, 12 for S/B */
+    int32_t depth;       /* encoder blocks, 12 for S/B; 0 = no encoder: a slice-transformer head for another backbone's features
+                            (mst_slice_head_forward), embed_dim then is that backbone's feature width */
     int32_t enc_heads;   /* embed_dim / 64 */
     int32_t slice_heads; /* 12 (dino.py:87) */
     int32_t out_ch;      /* classes (dino.py:103) */
@@ -116,6 +117,13 @@ MST_API int mst_forward(mst_handle h, const void* src, int32_t src_dtype, int32_
  * captured call alive and unchanged in address; results are identical to the eager path.  mst_graph_replays counts replays. */
 MST_API int mst_set_graph_threshold(mst_handle h, int64_t max_tokens);
 MST_API unsigned long long mst_graph_replays(mst_handle h);
+
+/* The slice transformer + head on its own (MST-ResNet, reference mst/models/resnet.py:127-198, shares it): a handle created
+ * with depth = 0 holds only cls_token, slice_fusion.* and linear.* (embed_dim = the backbone's feature width, e.g. 512 with 16 heads
+ * for ResNet-34, resnet.py:152-170).  feats [B, D, embed_dim] fp32 = the backbone's per-slice features; scratch holds
+ * B * (D + 1) * embed_dim floats; outputs as mst_forward's. */
+MST_API int mst_slice_head_forward(mst_handle h, const float* feats, int32_t B, int32_t D, const uint8_t* pad_mask, float* logits, float* feat,
+                           float* slice_cls, float* scratch, void* stream);
 
 /* get_plane_attention / get_slice_attention / get_attention_maps (dino.py:173-202) and the caller's
  * head-mean + reshape + trilinear upsample (scripts/main_predict.py:73-74,100,161-162), batched.

@@ -57,6 +57,7 @@ def lib():
     L.mst_finalize_weights.argtypes = [vp, vp]
     L.mst_workspace_bytes.argtypes = [vp, i32, i32, i32, i32, ctypes.POINTER(sz)]
     L.mst_forward.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.mst_slice_head_forward.argtypes = [vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mst_saliency.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.mst_rollout.argtypes = [vp, i32, i32, i32, vp, vp, vp]
     L.mst_pos_embed.argtypes = [vp, i32, i32, vp, vp]

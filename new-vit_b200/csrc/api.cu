@@ -256,6 +256,7 @@ static size_t elem_size(const mst_config& c) { return c.precision == MST_PRECISI
 static void expected_names(mst_handle h) {
     const int E = h->cfg.embed_dim, C = h->cfg.out_ch, Es = h->slice_emb();
     auto& x = h->expected;
+    if (h->cfg.depth > 0) {
     x["encoder.cls_token"] = E;
     if (h->cfg.num_registers > 0) x["encoder.register_tokens"] = static_cast<int64_t>(h->cfg.num_registers) * E;
     x["encoder.pos_embed"] = static_cast<int64_t>(h->cfg.pos_tokens) * E;
@@ -271,6 +272,7 @@ static void expected_names(mst_handle h) {
         x[p + "mlp.fc2.weight"] = 4LL * E * E; x[p + "mlp.fc2.bias"] = E;
     }
     x["encoder.norm.weight"] = E; x["encoder.norm.bias"] = E;
+    }   // depth == 0: a slice-transformer head on its own (MST-ResNet, resnet.py:127-198): no encoder tensors
     if (h->cfg.use_bottleneck) { x["bottleneck.weight"] = 1LL * Es * E; x["bottleneck.bias"] = Es; }  // dino.py:75-77
     if (h->cfg.slice_fusion == SLICE_FUSION_TRANSFORMER) {                                             // dino.py:80-97
         if (h->cfg.use_slice_pos_emb) x["slice_pos_emb.weight"] = 256LL * Es;
@@ -370,7 +372,7 @@ static int transposed(mst_handle h, const std::string& name, int N, int K, const
 
 template <typename T>
 static int finalize_t(mst_handle h, cudaStream_t st) {
-    const int E = h->cfg.embed_dim, P = h->cfg.pos_tokens - 1;
+    const int E = h->cfg.embed_dim, P = h->cfg.depth > 0 ? h->cfg.pos_tokens - 1 : 0;
     for (auto& kv : h->pos_cache) cudaFree(kv.second);
     h->pos_cache.clear();
     h->layers.assign(h->cfg.depth, Layer());
@@ -400,16 +402,18 @@ static int finalize_t(mst_handle h, cudaStream_t st) {
             MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc1.weight", p + "mlp.fc1.bias", nullptr, 0, 1.f, 4 * E, E, &L.wfc1, &L.bfc1, st));
         MST_PROPAGATE(pack_linear<T>(h, p + "mlp.fc2.weight", p + "mlp.fc2.bias", g2, 0, 1.f, E, 4 * E, &L.wfc2, &L.bfc2, st));
     }
-    T* wp;
-    MST_PROPAGATE(alloc_dev<T>(h, &wp, static_cast<size_t>(E) * KP));
-    pack_patch_kernel<T><<<256, 256, 0, st>>>(h->master["encoder.patch_embed.proj.weight"], wp, E);
-    MST_CHECK_CUDA(cudaGetLastError());
-    h->wpatch = wp;
-    MST_PROPAGATE(alloc_dev<float>(h, &h->posb, static_cast<size_t>(P) * E));
-    MST_PROPAGATE(alloc_dev<float>(h, &h->cls_pos0, E));
-    pack_pos_kernel<<<256, 256, 0, st>>>(h->master["encoder.pos_embed"], h->master["encoder.cls_token"],
-                                         h->master["encoder.patch_embed.proj.bias"], h->posb, h->cls_pos0, P, E);
-    MST_CHECK_CUDA(cudaGetLastError());
+    if (h->cfg.depth > 0) {
+        T* wp;
+        MST_PROPAGATE(alloc_dev<T>(h, &wp, static_cast<size_t>(E) * KP));
+        pack_patch_kernel<T><<<256, 256, 0, st>>>(h->master["encoder.patch_embed.proj.weight"], wp, E);
+        MST_CHECK_CUDA(cudaGetLastError());
+        h->wpatch = wp;
+        MST_PROPAGATE(alloc_dev<float>(h, &h->posb, static_cast<size_t>(P) * E));
+        MST_PROPAGATE(alloc_dev<float>(h, &h->cls_pos0, E));
+        pack_pos_kernel<<<256, 256, 0, st>>>(h->master["encoder.pos_embed"], h->master["encoder.cls_token"],
+                                             h->master["encoder.patch_embed.proj.bias"], h->posb, h->cls_pos0, P, E);
+        MST_CHECK_CUDA(cudaGetLastError());
+    }
     const std::string q = "slice_fusion.layers.0.";
     SliceWeights& s = h->sw;
     s = SliceWeights{};
@@ -972,11 +976,21 @@ const char* mst_last_error(void) { return g_err.c_str(); }
 
 int mst_create(const mst_config* cfg, mst_handle* out) {
     MST_REQUIRE(cfg && out, "mst_create: null argument");
-    MST_REQUIRE(cfg->embed_dim == 384 || cfg->embed_dim == 768 || cfg->embed_dim == 1024,
-                "mst_create: embed_dim %d unsupported (384/768/1024)", cfg->embed_dim);
-    MST_REQUIRE(cfg->enc_heads * 64 == cfg->embed_dim, "mst_create: enc_heads*64 must equal embed_dim");
-    MST_REQUIRE(cfg->depth >= 1 && cfg->out_ch >= 1 && cfg->pos_tokens >= 2, "mst_create: bad depth/out_ch/pos_tokens");
-    MST_REQUIRE(cfg->slice_heads >= 1 && cfg->slice_heads <= 16 && cfg->embed_dim % cfg->slice_heads == 0, "mst_create: bad slice_heads");
+    if (cfg->depth == 0) {   // slice-transformer head only (features come from the caller's backbone: MST-ResNet, resnet.py:127-198)
+        MST_REQUIRE(cfg->embed_dim >= 32 && cfg->embed_dim <= 1024 && cfg->embed_dim % 32 == 0,
+                    "mst_create: a slice-transformer head takes 32 <= embed_dim <= 1024, a multiple of 32 (got %d)", cfg->embed_dim);
+        MST_REQUIRE(cfg->slice_fusion == MST_FUSION_TRANSFORMER && !cfg->use_bottleneck && !cfg->use_slice_pos_emb && cfg->rotary == MST_ROTARY_NONE,
+                    "mst_create: the head-only handle is the plain slice transformer (resnet.py:155-170)");
+    } else {
+        MST_REQUIRE(cfg->embed_dim == 384 || cfg->embed_dim == 768 || cfg->embed_dim == 1024,
+                    "mst_create: embed_dim %d unsupported (384/768/1024)", cfg->embed_dim);
+        MST_REQUIRE(cfg->enc_heads * 64 == cfg->embed_dim, "mst_create: enc_heads*64 must equal embed_dim");
+        MST_REQUIRE(cfg->pos_tokens >= 2, "mst_create: bad pos_tokens");
+    }
+    MST_REQUIRE(cfg->depth >= 0 && cfg->out_ch >= 1, "mst_create: bad depth/out_ch");
+    MST_REQUIRE(cfg->slice_heads >= 1 && cfg->slice_heads <= 16 && cfg->embed_dim % cfg->slice_heads == 0 &&
+                    (cfg->embed_dim / (cfg->use_bottleneck ? 4 : 1) / cfg->slice_heads) % 8 == 0,
+                "mst_create: bad slice_heads (head dimension must be a multiple of 8)");
     MST_REQUIRE(cfg->precision == MST_PRECISION_FP32 || cfg->precision == MST_PRECISION_BF16, "mst_create: bad precision");
     MST_REQUIRE(cfg->num_registers >= 0 && cfg->num_registers <= 16, "mst_create: bad num_registers %d", cfg->num_registers);
     MST_REQUIRE(cfg->slice_fusion >= MST_FUSION_TRANSFORMER && cfg->slice_fusion <= MST_FUSION_AVERAGE, "mst_create: bad slice_fusion %d",
@@ -1188,10 +1202,24 @@ int mst_set_graph_threshold(mst_handle h, int64_t max_tokens) {
 }
 unsigned long long mst_graph_replays(mst_handle h) { return h ? h->graph_replays : 0; }
 
+int mst_slice_head_forward(mst_handle h, const float* feats, int32_t B, int32_t D, const uint8_t* pad_mask, float* logits, float* feat,
+                           float* slice_cls, float* scratch, void* stream) {
+    MST_REQUIRE(h && feats && scratch && (logits || !h->cfg.enable_linear), "mst_slice_head_forward: null argument");
+    MST_REQUIRE(h->finalized, "mst_slice_head_forward: weights not finalized");
+    MST_REQUIRE(B >= 1 && D >= 1, "empty batch: B=%d D=%d", B, D);
+    MST_REQUIRE(h->cfg.slice_fusion == MST_FUSION_TRANSFORMER && !h->cfg.use_bottleneck, "mst_slice_head_forward: transformer fusion without bottleneck");
+    MST_CHECK_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const mst_config& c = h->cfg;
+    MST_LAUNCH(CAT_SLICE_FUSION, launch_slice_fusion(feats, pad_mask, h->sw, scratch, c.enable_linear ? logits : nullptr, feat, slice_cls, B, D,
+                                                 c.embed_dim, c.embed_dim, c.slice_heads, c.out_ch, c.slice_fusion, 0, st));
+    return 0;
+}
+
 int mst_saliency(mst_handle h, const float* plane_cls, const float* slice_cls, int32_t B, int32_t D, int32_t enc_heads,
                  int32_t slice_heads, int32_t skip_tokens, int32_t gh, int32_t gw, int32_t H, int32_t W, int32_t tta, float* attn_maps,
                  float* plane_attn, float* slice_attn, float* coarse, float* full, void* stream) {
-    MST_REQUIRE(plane_cls && slice_cls, "mst_saliency: null argument");
+    MST_REQUIRE(slice_cls && (plane_cls || (!attn_maps && !plane_attn && !coarse && !full)), "mst_saliency: null argument");
     MST_REQUIRE(B >= 1 && D >= 1 && gh >= 1 && gw >= 1 && skip_tokens >= 1, "mst_saliency: empty input");
     MST_REQUIRE(coarse != nullptr || full == nullptr, "mst_saliency: the full-resolution map needs the coarse buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);

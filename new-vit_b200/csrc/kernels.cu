@@ -921,6 +921,7 @@ __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __re
         // dino.py:193-194) and the slice heads' weights S[b,h,1+d] / sum_j S[b,h,1+j] (dino.py:174-176)
         for (int task = warp; task < heads + sheads; task += nwarps) {
             if (task < heads) {
+                if (!plane_cls) continue;   // slice weights only (MST-ResNet's get_slice_attention, resnet.py:201-210)
                 const float* pr = plane_cls + (sv * heads + task) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
                 float t = 0.f;
                 for (int i = 1 + lane; i < P; i += 32) t += pr[i];
@@ -941,7 +942,7 @@ __global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __re
         wslice /= sheads;                                                           // mean over the slice heads (dino.py:181)
         for (int i = threadIdx.x; i < P; i += blockDim.x) {
             float msum = 0.f;
-            for (int h = 0; h < heads; ++h) {
+            for (int h = 0; plane_cls && h < heads; ++h) {
                 const float* pr = plane_cls + (sv * heads + h) * N + skip;
                 const float a = (i == 0) ? 0.f : pr[i] / hsum[h];                   // dino.py:193-194
                 const float m = wslice * a;                                         // dino.py:201

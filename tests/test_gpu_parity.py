@@ -403,3 +403,37 @@ def test_small_batches_replay_a_cuda_graph_with_identical_results():
         for _ in range(3):
             yh = m(xs[0], src_key_padding_mask=None)
         assert torch.equal(yh, eager(xs[0].cuda()))
+
+
+def test_mst_resnet_shares_the_slice_transformer_kernel():
+    """MST-ResNet (resnet.py:127-198) = a per-slice 2D ResNet (library backbone) + the SAME slice transformer as
+    MST-DINOv2 with d_model 512, 16 heads.  The head runs in slice_fusion_kernel through the head-only handle; checked against the
+    oracle's slice transformer on the backbone's own features, with a padding mask, plus get_slice_attention."""
+    from new_vit_b200 import ResNetSliceTrans, synth
+    from oracle import mst_oracle as O
+    torch.manual_seed(3)
+    m = ResNetSliceTrans(in_ch=1, out_ch=2, model=18, pretrained=False).cuda().eval()
+    sd = m.state_dict()
+    assert "cls_token" in sd and "slice_fusion.layers.0.self_attn.in_proj_weight" in sd and "linear.weight" in sd and "model.conv1.weight" in sd
+    assert tuple(sd["cls_token"].shape) == (1, 1, 512) and tuple(sd["slice_fusion.layers.0.linear1.weight"].shape) == (512, 512)
+    with torch.no_grad():   # non-trivial LayerNorm / bias values
+        for k, v in sd.items():
+            if not k.startswith("model.") and v.dim() == 1:
+                v.add_(0.05 * torch.randn_like(v))
+    m.load_state_dict(sd)
+    B, D = 3, 9
+    x = synth.make_volume(B, D, 64, 64, seed=9)
+    mask = synth.make_padding_mask(B, D, seed=1)
+    with torch.no_grad():
+        y = m(x, src_key_padding_mask=mask, save_attn=True).cpu()
+        sl = m.get_slice_attention().cpu()
+        xb = x.cuda().repeat(1, 3, 1, 1, 1).permute(0, 2, 1, 3, 4).reshape(B * D, 3, 64, 64)
+        feats = m.model(xb).reshape(B, D, -1).cpu()
+    cpu = {k: v.detach().cpu().float() for k, v in m.state_dict().items()}
+    tok = torch.cat([cpu["cls_token"].repeat(B, 1, 1), feats], dim=1)
+    kpm = torch.cat([torch.zeros((B, 1), dtype=torch.bool), mask], dim=1)
+    ref, w = O.slice_transformer(cpu, tok, kpm, heads=16)
+    want = F.linear(ref[:, 0], cpu["linear.weight"], cpu["linear.bias"])
+    torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(sl, O.get_slice_attention(w[:, :, 0, :]), rtol=1e-4, atol=1e-8)
+    assert sl.shape == (B * D, 1, 1) and (sl.reshape(B, D)[mask] == 0).all()
