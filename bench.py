@@ -428,7 +428,7 @@ def main():
         kernels = {}
         traffic = {}
         try:  # DRAM bytes per launch from the committed ncu --set full capture of this workload (profiles/)
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
                 traffic = json.load(f)
         except Exception:
             pass
@@ -450,7 +450,9 @@ def main():
                 kernels[k] = {"ms_per_step": m_ / args.steps, "launches_per_step": n_ / args.steps, "share": (m_ / args.steps) / tot if tot else 0}
                 if k in models and n_ and args.precision == "bf16":
                     fl, by = models[k]
-                    ms_launch = m_ / n_   # (the last block's shorter launches are included in the average: < 1 % effect)
+                    # qkv of ViT-S is two kernels per block (features 0..1023 on gemm_wt + the 128-feature tail): one logical launch
+                    logical = n_ / 2 if (k == "gemm_qkv" and n_ / args.steps > 1.5 * 12) else n_
+                    ms_launch = m_ / logical   # (the last block's shorter launches are included in the average: < 1 % effect)
                     t_tensor, t_hbm = fl / (peaks["bf16_tflops_sustained"] * 1e12), by / (peaks["hbm_gbs"] * 1e9)
                     kernels[k].update({"ms_per_launch": ms_launch, "tflops": fl / ms_launch / 1e9, "gbs": by / ms_launch / 1e6,
                                        "bound": "tensor" if t_tensor >= t_hbm else "hbm",
@@ -466,7 +468,7 @@ def main():
                             "peak": peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"],
                             "unit": "TFLOP/s" if tensor else "GB/s", "ms_per_launch": kt["ms_per_launch"],
                             "algorithmic_flops_per_launch": fl, "algorithmic_bytes_per_launch": by,
-                            "traffic": traffic.get(top), "traffic_src": "static: profiles/r01_ncu_traffic.json (one ncu --set full capture of this "
+                            "traffic": traffic.get(top), "traffic_src": "static: profiles/r02_ncu_traffic.json (one ncu --set full capture of this "
                             "workload; refreshed by profiles/ncu_traffic.py, not measured in this run)", "share_of_step": kt["share"],
                             "peak_kind": f"{peaks['_src']} sustained (kernel timed inside a long step)"}
                 roof_top["frac"] = roof_top["achieved"] / roof_top["peak"]

@@ -32,7 +32,8 @@ enum { MST_FUSION_TRANSFORMER = 0, MST_FUSION_LINEAR = 1, MST_FUSION_AVERAGE = 2
 enum { MST_ROTARY_NONE = 0, MST_ROTARY_ROPE = 1, MST_ROTARY_LIRE = 2 };
 /* element type of the `source` volume handed to mst_forward.  The bf16 path rounds every voxel to bf16 before the patch GEMM
  * anyway, so a bf16 upload is bit-identical to an fp32 one at half the host-to-device bytes. */
-enum { MST_SRC_F32 = 0, MST_SRC_BF16 = 1, MST_SRC_F16 = 2 };
+enum { MST_SRC_F32 = 0, MST_SRC_BF16 = 1, MST_SRC_F16 = 2,
+       MST_SRC_I16 = 3, MST_SRC_U16 = 4 /* raw scanner voxels: mst_prepare_volume only */ };
 
 /* Architecture of one DinoV2ClassifierSlice instance.  Replaces the constructor arguments of
  * reference dino.py:33-103 (model_size -> embed_dim/depth/enc_heads per vision_transformer.py:340-396). */
@@ -157,13 +158,14 @@ MST_API int mst_quantile(const float* data, int64_t n, int32_t items, const doub
  * (mst/data/datasets/dataset_3d_duke.py:36-47 with image_resize / resample None and the random augmentations off):
  * tio.Flip(1) -> CropOrPad((W,H,D), padding_mode='minimum') (augmentations/augmentations_3d.py:144-195) ->
  * ZNormalization(percentiles, mask = (x > min) & (x < max)) (:41-86) -> ImageOrSubjectToTensor swapaxes(1,-1) (:23-29).
- *   src   [items, W0, H0, D0] fp32 (torchio's [C=1, W, H, D] per item)      out [items, 1, D, H, W] fp32 (the model's `source`)
+ *   src   [items, W0, H0, D0] fp32, or the raw int16 / uint16 voxels (2 bytes per voxel over PCIe; widened on the device into
+ *         the workspace, which mst_prepare_volume_workspace_bytes sizes for it) (torchio's [C=1, W, H, D] per item)      out [items, 1, D, H, W] fp32 (the model's `source`)
  *   q_lo, q_hi  percentiles / 100 (0.005, 0.995), clamped before the statistics; flip_h = 1 for tio.Flip(1)
  *   stats nullable [items, 8] fp64: min, max, cutoff_lo, cutoff_hi, mean, std, masked voxels, status
  *         (status 0 ok; 1 std == 0 and 2 empty mask: the reference raises RuntimeError, augmentations_3d.py:75-84)
  * W*H*D must be a multiple of 4. */
 MST_API int mst_prepare_volume_workspace_bytes(int32_t items, int32_t W0, int32_t H0, int32_t D0, size_t* bytes);
-MST_API int mst_prepare_volume(mst_handle h /* nullable: instrumentation only */, const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H,
+MST_API int mst_prepare_volume(mst_handle h /* nullable: instrumentation only */, const void* src, int32_t src_dtype /* MST_SRC_F32 / _I16 / _U16 */, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H,
                        int32_t D, int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
                        size_t workspace_bytes, void* stream);
 

@@ -64,7 +64,7 @@ def lib():
     L.mst_quantile_workspace_bytes.argtypes = [i32, i32, ctypes.POINTER(sz)]
     L.mst_quantile.argtypes = [vp, i64, i32, vp, i32, vp, vp, sz, vp]
     L.mst_prepare_volume_workspace_bytes.argtypes = [i32, i32, i32, i32, ctypes.POINTER(sz)]
-    L.mst_prepare_volume.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, ctypes.c_float, ctypes.c_float, vp, vp, vp, sz, vp]
+    L.mst_prepare_volume.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, ctypes.c_float, ctypes.c_float, vp, vp, vp, sz, vp]
     L.mst_kernel_gemm_bf16.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_gemm_bf16_ln.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     L.mst_kernel_pack_linear_ln.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]

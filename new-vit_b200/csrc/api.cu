@@ -1271,22 +1271,31 @@ int mst_quantile(const float* data, int64_t n, int32_t items, const double* q_de
 
 int mst_prepare_volume_workspace_bytes(int32_t items, int32_t W0, int32_t H0, int32_t D0, size_t* bytes) {
     MST_REQUIRE(bytes && items >= 1 && W0 >= 1 && H0 >= 1 && D0 >= 1, "mst_prepare_volume_workspace_bytes: bad argument");
-    *bytes = prepare_volume_workspace_bytes(items, W0, H0, D0);
+    *bytes = prepare_volume_workspace_bytes(items, W0, H0, D0) + prepare_volume_raw_bytes(items, W0, H0, D0);
     return 0;
 }
-int mst_prepare_volume(mst_handle h, const float* src, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H, int32_t D,
+int mst_prepare_volume(mst_handle h, const void* src_any, int32_t src_dtype, int32_t items, int32_t W0, int32_t H0, int32_t D0, int32_t W, int32_t H, int32_t D,
                        int32_t flip_h, float q_lo, float q_hi, float* out, double* stats, void* workspace,
                        size_t workspace_bytes, void* stream) {
-    MST_REQUIRE(src && out && workspace, "mst_prepare_volume: null argument");
+    MST_REQUIRE(src_any && out && workspace, "mst_prepare_volume: null argument");
+    MST_REQUIRE(src_dtype == MST_SRC_F32 || src_dtype == MST_SRC_I16 || src_dtype == MST_SRC_U16, "mst_prepare_volume: bad src_dtype %d", src_dtype);
     MST_REQUIRE(items >= 1 && W0 >= 1 && H0 >= 1 && D0 >= 1 && W >= 1 && H >= 1 && D >= 1, "mst_prepare_volume: bad shape");
     MST_REQUIRE(q_lo >= 0.f && q_lo <= q_hi && q_hi <= 1.f, "mst_prepare_volume: quantiles must satisfy 0 <= q_lo <= q_hi <= 1");
-    MST_REQUIRE(workspace_bytes >= prepare_volume_workspace_bytes(items, W0, H0, D0), "mst_prepare_volume: workspace too small");
+    const size_t base_bytes = prepare_volume_workspace_bytes(items, W0, H0, D0);
+    MST_REQUIRE(workspace_bytes >= base_bytes + (src_dtype == MST_SRC_F32 ? 0 : prepare_volume_raw_bytes(items, W0, H0, D0)),
+                "mst_prepare_volume: workspace too small");
     int dev = 0, sms = 0;
     MST_CHECK_CUDA(cudaGetDevice(&dev));
     MST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     mst_handle_s none;
     if (!h) h = &none;
+    const float* src = static_cast<const float*>(src_any);
+    if (src_dtype != MST_SRC_F32) {   // raw int16 / uint16 voxels: widen on the device (the host-to-device copy carried 2 bytes per voxel)
+        float* raw = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + base_bytes);
+        MST_LAUNCH(CAT_PREPARE_VOLUME, launch_raw_to_f32(src_any, src_dtype, raw, static_cast<int64_t>(items) * W0 * H0 * D0, sms, st));
+        src = raw;
+    }
     MST_LAUNCH(CAT_PREPARE_VOLUME, launch_prepare_volume(src, items, W0, H0, D0, W, H, D, flip_h, q_lo, q_hi, out, stats, workspace, sms, st));
     h->launches += launch_prepare_volume_count(W0, H0, D0, W, H, D) - 1;   // the chain is several kernels, timed as one category
     return 0;

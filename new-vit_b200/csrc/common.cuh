@@ -234,6 +234,8 @@ int launch_quantile(const float* data, int64_t n, int items, const double* q_dev
 // ---- input pipeline in front of the forward (prep.cu) -----------------------
 size_t prepare_volume_workspace_bytes(int items, int W0, int H0, int D0);
 int launch_prepare_volume_count(int W0, int H0, int D0, int W, int H, int D);
+size_t prepare_volume_raw_bytes(int items, int W0, int H0, int D0);
+int launch_raw_to_f32(const void* in, int dtype, float* out, int64_t n, int num_sms, cudaStream_t stream);
 int launch_prepare_volume(const float* src, int items, int W0, int H0, int D0, int W, int H, int D, int flip_h, float q_lo,
                           float q_hi, float* out, double* stats, void* workspace, int num_sms, cudaStream_t stream);
 

@@ -895,76 +895,67 @@ int launch_slice_fusion(const float* enc_cls, const uint8_t* pad_mask, const Sli
 // Saliency combiner (reference dino.py:173-202 + scripts/main_predict.py:73-74,100) and the x14 upsampler
 // (main_predict.py:161-162: trilinear with depth scale 1 == per-slice bilinear, align_corners=False).
 // ---------------------------------------------------------------------------------------------------
-// nvar = 1: one CTA per slice.  nvar = 8 (test-time augmentation, main_predict.py:147-158): plane_cls / slice_cls hold the 8 flipped
-// variants of every volume, variant-major ([8*B*D, ...] / [8*B, ...]); the CTA of output slice (b, d) walks the variants in the
-// script's order, un-flips each variant's coarse map (flip of dims 2/3/4 = depth / grid rows / grid columns) and averages, so the
-// x14 upsample runs ONCE on the averaged coarse map as the script does (:161-162).
-__global__ void __launch_bounds__(256) saliency_combine_kernel(const float* __restrict__ plane_cls, const float* __restrict__ slice_cls,
-                                                                int B, int D, int heads, int sheads, int gh, int gw, int skip, int nvar,
-                                                                float* __restrict__ attn_maps, float* __restrict__ plane_attn,
-                                                                float* __restrict__ slice_attn, float* __restrict__ coarse) {
-    extern __shared__ float sm[];  // acc[P] | tot[P] | hsum[32] | whd[32]
-    const int P = gh * gw;
-    float* acc = sm;
-    float* tot = sm + P;
-    float* hsum = tot + P;     // per encoder head: sum of the CLS->patch probabilities, patch 0 excluded
-    float* whd = hsum + 32;    // per slice head: this slice's renormalised weight
-    const int s = blockIdx.x, b = s / D, d = s % D, L = D + 1, N = P + skip;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+// One WARP per output slice (8 slices per CTA, no block-wide synchronisation: the kernel is a few hundred loads per slice and was
+// latency-bound as one CTA per slice).  nvar = 8 (test-time augmentation, main_predict.py:147-158): plane_cls / slice_cls hold the
+// 8 flipped variants of every volume, variant-major ([8*B*D, ...] / [8*B, ...]); the warp of output slice (b, d) walks the variants
+// in the script's order, un-flips each variant's coarse map (flip of dims 2/3/4 = depth / grid rows / grid columns) through its
+// shared-memory row and averages, so the x14 upsample runs ONCE on the averaged coarse map as the script does (:161-162).
+constexpr int SAL_WARPS = 8;
+__global__ void __launch_bounds__(SAL_WARPS * 32) saliency_combine_kernel(const float* __restrict__ plane_cls, const float* __restrict__ slice_cls,
+                                                                            int B, int D, int heads, int sheads, int gh, int gw, int skip,
+                                                                            int nvar, float* __restrict__ attn_maps, float* __restrict__ plane_attn,
+                                                                            float* __restrict__ slice_attn, float* __restrict__ coarse) {
+    extern __shared__ float sm[];  // per warp: acc[P] | tot[P]
+    const int P = gh * gw, L = D + 1, N = P + skip;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * SAL_WARPS + warp;
+    if (s >= B * D) return;
+    float* acc = sm + static_cast<int64_t>(warp) * 2 * P;
+    float* tot = acc + P;
+    const int b = s / D, d = s - b * D;
     float wtot = 0.f;
     for (int v = 0; v < nvar; ++v) {
         const bool flip_d = (0xB2 >> v) & 1, flip_h = (0xD4 >> v) & 1, flip_w = (0xE8 >> v) & 1;
         const int bv = v * B + b, dv = flip_d ? D - 1 - d : d;
         const int64_t sv = static_cast<int64_t>(bv) * D + dv;
-        __syncthreads();   // acc / hsum / whd of the previous variant have been consumed
-        // one warp per reduction, all of them in flight at once: the encoder heads' renormalisation sums (patch 0 := 0,
-        // dino.py:193-194) and the slice heads' weights S[b,h,1+d] / sum_j S[b,h,1+j] (dino.py:174-176)
-        for (int task = warp; task < heads + sheads; task += nwarps) {
-            if (task < heads) {
-                if (!plane_cls) continue;   // slice weights only (MST-ResNet's get_slice_attention, resnet.py:201-210)
-                const float* pr = plane_cls + (sv * heads + task) * N + skip;  // drop CLS (+ registers) (dino.py:191-192)
-                float t = 0.f;
-                for (int i = 1 + lane; i < P; i += 32) t += pr[i];
-                t = warp_sum(t);
-                if (lane == 0) hsum[task] = t;
-            } else {
-                const int h = task - heads;
-                const float* sr = slice_cls + (static_cast<int64_t>(bv) * sheads + h) * L + 1;
-                float t = 0.f;
-                for (int j = lane; j < D; j += 32) t += sr[j];
-                t = warp_sum(t);
-                if (lane == 0) whd[h] = sr[dv] / t;
-            }
-        }
-        __syncthreads();
+        // slice weight: mean over the slice heads of S[b,h,1+d] / sum_j S[b,h,1+j]                    (dino.py:174-181)
         float wslice = 0.f;
-        for (int h = 0; h < sheads; ++h) wslice += whd[h];
-        wslice /= sheads;                                                           // mean over the slice heads (dino.py:181)
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
-            float msum = 0.f;
-            for (int h = 0; plane_cls && h < heads; ++h) {
-                const float* pr = plane_cls + (sv * heads + h) * N + skip;
-                const float a = (i == 0) ? 0.f : pr[i] / hsum[h];                   // dino.py:193-194
-                const float m = wslice * a;                                         // dino.py:201
+        for (int h = 0; h < sheads; ++h) {
+            const float* sr = slice_cls + (static_cast<int64_t>(bv) * sheads + h) * L + 1;
+            float t = 0.f;
+            for (int j = lane; j < D; j += 32) t += sr[j];
+            t = warp_sum(t);
+            wslice += sr[dv] / t;
+        }
+        wslice /= sheads;
+        __syncwarp();
+        for (int i = lane; i < P; i += 32) acc[i] = 0.f;
+        for (int h = 0; plane_cls && h < heads; ++h) {
+            const float* pr = plane_cls + (sv * heads + h) * N + skip;   // drop CLS (+ registers)          (dino.py:191-192)
+            float t = 0.f;
+            for (int i = 1 + lane; i < P; i += 32) t += pr[i];          // patch 0 := 0                      (dino.py:193)
+            t = warp_sum(t);
+            for (int i = lane; i < P; i += 32) {
+                const float a = (i == 0) ? 0.f : pr[i] / t;             // dino.py:194
+                const float m = wslice * a;                             // dino.py:201
                 if (attn_maps) attn_maps[(sv * heads + h) * P + i] = m;
                 if (plane_attn) plane_attn[(sv * heads + h) * P + i] = a;
-                msum += m;
+                acc[i] += m;
             }
-            acc[i] = msum / heads;                                                  // head mean (main_predict.py:73-74)
         }
-        __syncthreads();
-        // un-flipped into the output orientation, summed in the script's order (main_predict.py:157)
-        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        __syncwarp();
+        // head mean (main_predict.py:73-74), un-flipped into the output orientation, summed in the script's order (:157)
+        for (int i = lane; i < P; i += 32) {
             const int y = i / gw, x = i - y * gw;
-            const float m = acc[(flip_h ? gh - 1 - y : y) * gw + (flip_w ? gw - 1 - x : x)];
+            const float m = acc[(flip_h ? gh - 1 - y : y) * gw + (flip_w ? gw - 1 - x : x)] / heads;
             tot[i] = v == 0 ? m : tot[i] + m;
         }
         wtot = v == 0 ? wslice : wtot + wslice;
     }
     const float inv = 1.0f / nvar;   // exact (1 or 1/8)
     if (coarse)
-        for (int i = threadIdx.x; i < P; i += blockDim.x) coarse[static_cast<int64_t>(s) * P + i] = tot[i] * inv;
-    if (slice_attn && threadIdx.x == 0) slice_attn[s] = wtot * inv;
+        for (int i = lane; i < P; i += 32) coarse[static_cast<int64_t>(s) * P + i] = tot[i] * inv;
+    if (slice_attn && lane == 0) slice_attn[s] = wtot * inv;
 }
 
 // x(H/gh) bilinear upsample, align_corners=False (== F.interpolate 'trilinear' with depth scale 1, main_predict.py:161-162):
@@ -1021,8 +1012,12 @@ int launch_saliency_combine(const float* plane_cls, const float* slice_cls, int 
     const int P = gh * gw, BD = B * D;
     MST_REQUIRE(!tta || (attn_maps == nullptr && plane_attn == nullptr), "saliency: the per-head maps are per variant; with tta only coarse / slice_attn");
     MST_REQUIRE(heads <= 32 && slice_heads <= 32, "saliency: at most 32 heads");
-    saliency_combine_kernel<<<BD, 256, (2 * P + 64) * sizeof(float), stream>>>(plane_cls, slice_cls, B, D, heads, slice_heads, gh, gw, skip,
-                                                                              tta ? 8 : 1, attn_maps, plane_attn, slice_attn, coarse);
+    const size_t smem = static_cast<size_t>(SAL_WARPS) * 2 * P * sizeof(float);
+    MST_REQUIRE(smem <= 200 * 1024, "saliency: a %d x %d patch grid needs %zu bytes of shared memory", gh, gw, smem);
+    MST_SET_DYN_SMEM(saliency_combine_kernel, 200 * 1024);
+    saliency_combine_kernel<<<(BD + SAL_WARPS - 1) / SAL_WARPS, SAL_WARPS * 32, smem, stream>>>(plane_cls, slice_cls, B, D, heads, slice_heads, gh,
+                                                                                                gw, skip, tta ? 8 : 1, attn_maps, plane_attn,
+                                                                                                slice_attn, coarse);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

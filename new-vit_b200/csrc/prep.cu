@@ -482,6 +482,21 @@ size_t prepare_volume_workspace_bytes(int items, int W0, int H0, int D0) {
     return align256(static_cast<size_t>(items) * sizeof(PrepState)) +
            align256(static_cast<size_t>(items) * margin_floats(W0, H0, D0) * sizeof(float));
 }
+// raw scanner voxels (int16 / uint16, as the HDF5 / DICOM files hold them) -> fp32, so that the host-to-device copy of the raw-data
+// route carries 2 bytes per voxel; the fp32 copy lives in the caller's workspace behind the state of prepare_volume
+template <typename TI>
+__global__ void __launch_bounds__(256) raw_to_f32_kernel(const TI* __restrict__ in, float* __restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        out[i] = static_cast<float>(in[i]);
+}
+size_t prepare_volume_raw_bytes(int items, int W0, int H0, int D0) { return align256(static_cast<size_t>(items) * W0 * H0 * D0 * sizeof(float)); }
+int launch_raw_to_f32(const void* in, int dtype, float* out, int64_t n, int num_sms, cudaStream_t stream) {
+    if (dtype == 3) raw_to_f32_kernel<int16_t><<<num_sms * 8, 256, 0, stream>>>(static_cast<const int16_t*>(in), out, n);
+    else if (dtype == 4) raw_to_f32_kernel<uint16_t><<<num_sms * 8, 256, 0, stream>>>(static_cast<const uint16_t*>(in), out, n);
+    else MST_REQUIRE(false, "prepare_volume: source dtype %d is not int16 / uint16", dtype);
+    MST_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 // kernels one launch_prepare_volume call issues: init, (7 marginal-minimum tables when an axis is padded), gather,
 // RADIX_PASSES x (histogram, pick), cutoff, moments, finalize, normalize

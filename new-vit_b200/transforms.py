@@ -30,7 +30,9 @@ def duke_transform(data, image_crop=(224, 224, 32), percentiles=(0.5, 99.5), fli
         data = data[:, 0]
     if data.dim() != 4:
         raise ValueError("duke_transform: expected [W,H,D], [items,W,H,D] or [items,1,W,H,D]")
-    data = data.detach().to(torch.float32).contiguous()
+    # raw scanner voxels stay 2 bytes wide until they are on the device (half the host-to-device bytes of the raw-data route)
+    raw_code = {torch.int16: 3, torch.uint16: 4}.get(data.dtype, 0)
+    data = data.detach().contiguous() if raw_code else data.detach().to(torch.float32).contiguous()
     items, W0, H0, D0 = data.shape
     W, H, D = (int(v) for v in image_crop)
     if (W * H * D) % 4:
@@ -44,7 +46,7 @@ def duke_transform(data, image_crop=(224, 224, 32), percentiles=(0.5, 99.5), fli
         _cabi.check(L.mst_prepare_volume_workspace_bytes(items, W0, H0, D0, ct.byref(need)))
         ws = torch.empty(need.value, dtype=torch.uint8, device=data.device)
         stream = ct.c_void_p(torch.cuda.current_stream().cuda_stream)
-        _cabi.check(L.mst_prepare_volume(None, _cabi.ptr(data), items, W0, H0, D0, W, H, D, 1 if flip else 0,
+        _cabi.check(L.mst_prepare_volume(None, _cabi.ptr(data), raw_code, items, W0, H0, D0, W, H, D, 1 if flip else 0,
                                          ct.c_float(percentiles[0] / 100.0), ct.c_float(percentiles[1] / 100.0),
                                          _cabi.ptr(out), _cabi.ptr(stats), _cabi.ptr(ws), need.value, stream))
         if check:

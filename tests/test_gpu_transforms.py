@@ -116,3 +116,15 @@ def test_duke_transform_errors():
         duke_transform(x, image_crop=(16, 16, 8))                              # masked values all equal: std 0
     with pytest.raises(ValueError):
         duke_transform(torch.zeros(2, 2, 8, 8, 8, device="cuda"))              # two channels
+
+
+def test_raw_int16_volumes_are_widened_on_the_device():
+    """The raw-data route: int16 / uint16 scanner voxels cross PCIe 2 bytes wide and are widened by the library; bit-identical to
+    handing over the same values as fp32."""
+    import torch
+    from new_vit_b200 import duke_transform
+    g = torch.Generator().manual_seed(5)
+    raw = torch.randint(-200, 3000, (3, 64, 60, 36), generator=g, dtype=torch.int16)
+    want = duke_transform(raw.float().cuda(), (56, 56, 32))
+    got = duke_transform(raw.cuda(), (56, 56, 32))
+    assert torch.equal(got, want)
