@@ -522,11 +522,8 @@ template <> struct Ops<bf16> {
         return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, mode, ep, h->num_sms, st);
     }
     static int attention(mst_handle h, const void* qkv, void* out, int BD, int N, int heads, cudaStream_t st) {
-        if (N == 257) {   // ViT @224: the specialised tcgen05 kernels (16 softmax warps)
-            static const int seq = exp_env("MST_ATTN_SEQ", 1);   // 1: all sixteen warps on one tile at a time; 0: two teams of eight
-            if (seq) return launch_attention_tc257s(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
+        if (N == 257)   // ViT @224: the specialised tcgen05 kernel (16 softmax warps in two teams)
             return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, h->num_sms, st);
-        }
         static const int use_tcg = exp_env("MST_ATTN_TCG", 1);   // 0: A-B comparisons
         if (use_tcg && attention_tcg_supported(N))
             return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, h->num_sms, st);
@@ -1505,13 +1502,9 @@ int mst_kernel_gemm_f32(const float* A, const float* W, int32_t M, int32_t N, in
 }
 int mst_kernel_attention_bf16(const void* qkv, void* out, int32_t BD, int32_t N, int32_t heads, void* stream) {
     MST_REQUIRE(qkv && out, "mst_kernel_attention_bf16: null argument");
-    if (N == 257) {
-        static const int seq = exp_env("MST_ATTN_SEQ", 1);
-        if (seq) return launch_attention_tc257s(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
-                                                static_cast<cudaStream_t>(stream));
+    if (N == 257)
         return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
                                          static_cast<cudaStream_t>(stream));
-    }
     if (attention_tcg_supported(N))
         return launch_attention_tcg(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, N, heads, num_sms_current(),
                                     static_cast<cudaStream_t>(stream));

@@ -195,8 +195,7 @@ int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, 
 // columns): attention_tc16.cu
 int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
                               long long* dbg = nullptr);
-// all sixteen softmax warps on one tile at a time, the two TMEM buffers alternating between consecutive tiles: attention_tc16s.cu
-int launch_attention_tc257s(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream, long long* dbg = nullptr);
+
 // tcgen05 attention for any token count 17 <= N <= 360 (attention_tcg.cu); N == 257 keeps its specialised kernels
 bool attention_tcg_supported(int N);
 int launch_attention_tcg(const bf16* qkv, bf16* out, int BD, int N, int heads, int num_sms, cudaStream_t stream);

@@ -117,26 +117,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         }
     }
 }
-// The same wait for warps that are NOT on the critical path (TMA producers waiting for a free ring slot, MMA issuers waiting for
-// the epilogue / softmax warps, side warps waiting for data): between polls the warp sleeps kSleepNs, so it stops competing for
-// the issue slots of its SM sub-partition.  A polling warp issues an instruction every few cycles; ncu on the attention kernel
-// attributed 24 % of ALL executed instructions to this loop -- four waiting warps, one per sub-partition, next to the sixteen
-// softmax warps that bound the kernel.
-template <int kSleepNs>
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    uint32_t spins = 0;
-    uint64_t t0 = 0;
-    do {
-        __nanosleep(kSleepNs);
-        if ((++spins & 0x3FF) == 0) {
-            const uint64_t t = globaltimer_ns();
-            if (t0 == 0) t0 = t;
-            else if (t - t0 > MST_MBAR_TIMEOUT_NS) asm volatile("trap;");
-        }
-    } while (!mbar_try_wait(bar, parity));
-}
-
 // ----------------------------------------------------------------------------------------------
 // Programmatic dependent launch (MST_PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
 // start while the kernel before it in the stream drains; nothing the earlier kernel wrote may be touched (and nothing it
