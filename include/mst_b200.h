@@ -234,12 +234,15 @@ MST_API int mst_kernel_gemm_bf16_res_stats(const void* A, const void* W, int32_t
                                    float* rowstat_out, float eps, void* stream);
 /* Encoder backward pieces (csrc/train_enc.cu), kernel level:
  *   gemm f32out   out[M,N] fp32 = A[M,K] W[N,K]^T (weight gradients dW = dY^T X on transposed activations; K > 384, N % 192 == 0)
+ *   wgrad         dW [Nout, Kin] fp32 = dY[M, Nout]^T X[M, Kin] and db [Nout] fp32 (nullable) = column sums of dY, from the ROW-MAJOR
+ *                 activations (MN-major tensor-core operands, no transposes); Nout % 128 == 0, Kin % 192 == 0; both outputs overwritten
  *   ln_bwd        dx = LayerNorm backward of dy at x (+ dres), dgamma / dbeta [E] fp32 (E = 384 / 768); synchronises the stream
  *   gelu          y = GELU(u) (y != NULL) and / or du = dy * GELU'(u) (dy, du != NULL); n % 8 == 0
  *   transpose     out [C, Mpad] = in [M, C]^T zero-padded to Mpad columns; colsum [C] fp32 (nullable) += column sums of `in`
  *   attention_bwd dqkv [BD*N, 3E] from qkv (q pre-scaled by 1/8), the forward output o and dO, both [BD*N, E]; d/dq is w.r.t. the
  *                 UN-scaled q projection (attention.py:58-60) */
 MST_API int mst_kernel_gemm_bf16_f32out(const void* A, const void* W, int32_t M, int32_t N, int32_t K, float* out, void* stream);
+MST_API int mst_kernel_wgrad_bf16(const void* dY, const void* X, int32_t M, int32_t Nout, int32_t Kin, float* dW, float* db, void* stream);
 MST_API int mst_kernel_ln_bwd_bf16(const void* x, const void* dy, const void* dres, const float* gamma, void* dx, float* dgamma,
                            float* dbeta, int32_t rows, int32_t E, float eps, void* stream);
 MST_API int mst_kernel_gelu_bf16(const void* u, void* y, const void* dy, void* du, int64_t n, void* stream);

@@ -70,6 +70,7 @@ def lib():
     L.mst_kernel_pack_linear_ln.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp]
     L.mst_kernel_gemm_bf16_res_stats.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, ctypes.c_float, vp]
     L.mst_kernel_gemm_bf16_f32out.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.mst_kernel_wgrad_bf16.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     L.mst_kernel_ln_bwd_bf16.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, ctypes.c_float, vp]
     L.mst_kernel_gelu_bf16.argtypes = [vp, vp, vp, vp, i64, vp]
     L.mst_kernel_transpose_bf16.argtypes = [vp, vp, vp, i32, i32, i32, vp]

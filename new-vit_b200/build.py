@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmst_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "gemm_wt.cu", "attention_tc16.cu", "attention_tcg.cu", "attention_mma.cu", "kernels.cu", "extras.cu", "prep.cu", "train.cu", "train_enc.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "gemm_wt.cu", "attention_tc16.cu", "attention_tcg.cu", "attention_mma.cu", "kernels.cu", "extras.cu", "prep.cu", "train.cu", "train_enc.cu", "gemm_wgrad.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -830,14 +830,30 @@ static int train_forward(mst_handle h, const void* src, int src_dtype, int B, in
 
 // ---- small gradient kernels of the token assembly (vision_transformer.py:219-220, patch_embed.py:75-77) ----
 // dX rows of token t summed over the slices: dpos[t] (token 0 also = dcls); conv-bias gradient = sum over the patch tokens
-__global__ void __launch_bounds__(128) token_grads_kernel(const bf16* __restrict__ dX, float* __restrict__ dpos, float* __restrict__ dcls,
+__global__ void __launch_bounds__(768) token_grads_kernel(const bf16* __restrict__ dX, float* __restrict__ dpos, float* __restrict__ dcls,
                                                            int BD, int N, int E) {
-    const int t = blockIdx.x;
+    // one CTA per token: E / 8 lanes of eight features x (768 / lanes) slice groups, 16-byte loads, groups summed in a fixed order
+    extern __shared__ float tg_part[];          // [groups][E]
+    const int t = blockIdx.x, lanes = E / 8, groups = blockDim.x / lanes;
+    const int l = threadIdx.x % lanes, g = threadIdx.x / lanes;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = g; s < BD; s += groups) {
+        const uint4 v = *reinterpret_cast<const uint4*>(dX + (static_cast<int64_t>(s) * N + t) * E + 8 * l);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {   // bf16 -> fp32: the bits are the upper half of the float
+            a[2 * j] += __uint_as_float(w[j] << 16);
+            a[2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tg_part[g * E + 8 * l + j] = a[j];
+    __syncthreads();
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        float a = 0.f;
-        for (int s = 0; s < BD; ++s) a += __bfloat162float(dX[(static_cast<int64_t>(s) * N + t) * E + e]);
-        dpos[static_cast<int64_t>(t) * E + e] = a;
-        if (t == 0 && dcls) dcls[e] = a;
+        float r = 0.f;
+        for (int k = 0; k < groups; ++k) r += tg_part[k * E + e];
+        dpos[static_cast<int64_t>(t) * E + e] = r;
+        if (t == 0 && dcls) dcls[e] = r;
     }
 }
 __global__ void __launch_bounds__(128) conv_bias_grad_kernel(const float* __restrict__ dpos, float* __restrict__ dbias, int N, int E) {
@@ -874,6 +890,10 @@ static float* grad_of(mst_handle h, const std::string& name) {
 // dW = dY^T X (fp32) and db = column sums of dY, for Y = X W^T + b with dY [M, Nout], X [M, Kin]
 static int linear_wgrad(mst_handle h, const bf16* dY, int Nout, const bf16* X, int Kin, int M, const TrainWs& ws, float* dW, float* db,
                         cudaStream_t st) {
+    if (wgrad_tc_supported(Nout, Kin)) {   // operands read as they lie (MN-major descriptors), bias gradient in the same kernel
+        MST_LAUNCH(CAT_BWD_WGRAD, launch_wgrad_tc(dY, Nout, X, Kin, M, dW, db, h->num_sms, st));
+        return 0;
+    }
     if (db) MST_CHECK_CUDA(cudaMemsetAsync(db, 0, static_cast<size_t>(Nout) * 4, st));
     MST_LAUNCH(CAT_BWD_TRANSPOSE, launch_transpose_colsum(dY, Nout, ws.Ta, db, M, Nout, ws.Mpad, st));
     MST_LAUNCH(CAT_BWD_TRANSPOSE, launch_transpose_colsum(X, Kin, ws.Tb, nullptr, M, Kin, ws.Mpad, st));
@@ -941,7 +961,10 @@ static int train_backward(mst_handle h, const float* denc, int B, int D, int H, 
     float *gpos = need("encoder.pos_embed"), *gcls = need("encoder.cls_token"), *gcw = need("encoder.patch_embed.proj.weight"),
           *gcb = need("encoder.patch_embed.proj.bias");
     MST_REQUIRE(gpos && gcls && gcw && gcb, "mst_train_backward: gradient buffers of the patch embedding / position table were not set");
-    token_grads_kernel<<<N, 128, 0, st>>>(ws.dX, gpos, gcls, BD, N, E);
+    {
+        const int lanes = E / 8, groups = 768 / lanes;     // E = 384 / 768 / 1024: 48 x 16, 96 x 8, 128 x 6
+        token_grads_kernel<<<N, lanes * groups, static_cast<size_t>(groups) * E * 4, st>>>(ws.dX, gpos, gcls, BD, N, E);
+    }
     MST_CHECK_CUDA(cudaGetLastError());
     conv_bias_grad_kernel<<<(E + 127) / 128, 128, 0, st>>>(gpos, gcb, N, E);
     MST_CHECK_CUDA(cudaGetLastError());
@@ -1452,6 +1475,12 @@ int mst_kernel_gemm_bf16_f32out(const void* A, const void* W, int32_t M, int32_t
     ep.out = out; ep.ldo = N;
     return gemm_bf16_tc(static_cast<const bf16*>(A), static_cast<const bf16*>(W), M, N, K, EPI_RAW_F32, ep, num_sms_current(),
                         static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_wgrad_bf16(const void* dY, const void* X, int32_t M, int32_t Nout, int32_t Kin, float* dW, float* db, void* stream) {
+    MST_REQUIRE(dY && X && dW, "mst_kernel_wgrad_bf16: null argument");
+    MST_REQUIRE(wgrad_tc_supported(Nout, Kin), "mst_kernel_wgrad_bf16: Nout must be a multiple of 128 and Kin of 192 (got %d, %d)", Nout, Kin);
+    return launch_wgrad_tc(static_cast<const bf16*>(dY), Nout, static_cast<const bf16*>(X), Kin, M, dW, db, num_sms_current(),
+                           static_cast<cudaStream_t>(stream));
 }
 int mst_kernel_ln_bwd_bf16(const void* x, const void* dy, const void* dres, const float* gamma, void* dx, float* dgamma, float* dbeta,
                            int32_t rows, int32_t E, float eps, void* stream) {

@@ -261,6 +261,8 @@ int launch_gelu_fwd(const bf16* u, bf16* y, int64_t n, int num_sms, cudaStream_t
 int launch_gelu_bwd(const bf16* u, const bf16* dy, bf16* du, int64_t n, int num_sms, cudaStream_t stream);
 int launch_transpose_colsum(const bf16* in, int64_t ld, bf16* out, float* colsum, int M, int C, int Mpad, cudaStream_t stream);
 int launch_transpose_f32_to_bf16(const float* W, bf16* Wt, int N, int K, cudaStream_t stream);
+bool wgrad_tc_supported(int Nout, int Kin);
+int launch_wgrad_tc(const bf16* dY, int Nout, const bf16* X, int Kin, int M, float* dW, float* db, int num_sms, cudaStream_t stream);
 int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream);
 
 }  // namespace mst

@@ -33,24 +33,42 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
                                                       const float* __restrict__ dy_f32, const bf16* __restrict__ dres,
                                                       const float* __restrict__ gamma, bf16* __restrict__ dx, float* __restrict__ partial,
                                                       int rows, float eps) {
-    constexpr int E = EPL * 32;
+    // lane -> elements 4 lane + 128 g + {0..3}, g < EPL / 4: every load and store of a warp is 256 contiguous bytes
+    constexpr int E = EPL * 32, G = EPL / 4;
+    static_assert(EPL % 4 == 0, "row length must be a multiple of 128");
     __shared__ float red[2][E];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) (&red[0][0])[i] = 0.f;
     __syncthreads();
     float gam[EPL], dg[EPL], db[EPL];
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) { gam[i] = gamma[lane + 32 * i]; dg[i] = 0.f; db[i] = 0.f; }
+    for (int g = 0; g < G; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(gamma + 128 * g + 4 * lane);
+        gam[4 * g] = v.x; gam[4 * g + 1] = v.y; gam[4 * g + 2] = v.z; gam[4 * g + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) { dg[i] = 0.f; db[i] = 0.f; }
+    auto load4 = [&](const bf16* p, float* o) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    };
     for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
         const bf16* xr = x + static_cast<int64_t>(r) * x_row_stride;
+        const int64_t ro = static_cast<int64_t>(r) * E;
         float xv[EPL], dyv[EPL];
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            xv[i] = __bfloat162float(xr[lane + 32 * i]);
-            dyv[i] = dy ? __bfloat162float(dy[static_cast<int64_t>(r) * E + lane + 32 * i]) : dy_f32[static_cast<int64_t>(r) * E + lane + 32 * i];
-            s += xv[i];
+        for (int g = 0; g < G; ++g) {
+            load4(xr + 128 * g + 4 * lane, xv + 4 * g);
+            if (dy) load4(dy + ro + 128 * g + 4 * lane, dyv + 4 * g);
+            else {
+                const float4 v = *reinterpret_cast<const float4*>(dy_f32 + ro + 128 * g + 4 * lane);
+                dyv[4 * g] = v.x; dyv[4 * g + 1] = v.y; dyv[4 * g + 2] = v.z; dyv[4 * g + 3] = v.w;
+            }
         }
+#pragma unroll
+        for (int i = 0; i < EPL; ++i) s += xv[i];
         const float mean = wsum32(s) * (1.0f / E);
         float q = 0.f;
 #pragma unroll
@@ -67,26 +85,40 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
         }
         const float m1 = wsum32(s1) * (1.0f / E), m2 = wsum32(s2) * (1.0f / E);
 #pragma unroll
-        for (int i = 0; i < EPL; ++i) {
-            float v = rstd * (dyv[i] * gam[i] - m1 - xv[i] * m2);
-            if (dres) v += __bfloat162float(dres[static_cast<int64_t>(r) * E + lane + 32 * i]);
-            dx[static_cast<int64_t>(r) * E + lane + 32 * i] = __float2bfloat16_rn(v);
+        for (int g = 0; g < G; ++g) {
+            float v[4], rs[4] = {0.f, 0.f, 0.f, 0.f};
+            if (dres) load4(dres + ro + 128 * g + 4 * lane, rs);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = rstd * (dyv[4 * g + j] * gam[4 * g + j] - m1 - xv[4 * g + j] * m2) + rs[j];
+            *reinterpret_cast<uint2*>(dx + ro + 128 * g + 4 * lane) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
         }
     }
-    (void)warp;
 #pragma unroll
-    for (int i = 0; i < EPL; ++i) { atomicAdd(&red[0][lane + 32 * i], dg[i]); atomicAdd(&red[1][lane + 32 * i], db[i]); }
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&red[0][128 * g + 4 * lane + j], dg[4 * g + j]);
+            atomicAdd(&red[1][128 * g + 4 * lane + j], db[4 * g + j]);
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * E; i += blockDim.x) partial[static_cast<int64_t>(blockIdx.x) * 2 * E + i] = (&red[0][0])[i];
 }
-// dgamma[e] (+)= sum over CTAs of partial[.][0][e], dbeta likewise
-__global__ void ln_bwd_reduce_kernel(const float* __restrict__ partial, int nparts, int E, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * E) return;
+// dgamma[e] = sum over CTAs of partial[.][0][e], dbeta likewise: one CTA per 32 columns, 8 partial rows in flight per column,
+// summed in a fixed order (the result does not depend on scheduling)
+__global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restrict__ partial, int nparts, int E, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta) {
+    __shared__ float acc[8][33];
+    const int c = threadIdx.x & 31, g = threadIdx.x >> 5, i = blockIdx.x * 32 + c;
     float a = 0.f;
-    for (int p = 0; p < nparts; ++p) a += partial[static_cast<int64_t>(p) * 2 * E + i];
-    if (i < E) dgamma[i] = a; else dbeta[i - E] = a;
+    for (int p = g; p < nparts; p += 8) a += partial[static_cast<int64_t>(p) * 2 * E + i];
+    acc[g][c] = a;
+    __syncthreads();
+    if (g == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += acc[k][c];
+        if (i < E) dgamma[i] = t; else dbeta[i - E] = t;
+    }
 }
 constexpr int LN_BWD_GRID = 592;   // 4 CTAs per SM
 size_t ln_bwd_workspace_bytes(int E) { return static_cast<size_t>(LN_BWD_GRID) * 2 * E * sizeof(float); }
@@ -100,7 +132,7 @@ int launch_ln_bwd(const bf16* x, int64_t x_row_stride, const bf16* dy, const flo
     if (E == 384) ln_bwd_kernel<12><<<grid, 256, 0, stream>>>(x, x_row_stride, dy, dy_f32, dres, gamma, dx, workspace, rows, eps);
     else ln_bwd_kernel<24><<<grid, 256, 0, stream>>>(x, x_row_stride, dy, dy_f32, dres, gamma, dx, workspace, rows, eps);
     MST_CHECK_CUDA(cudaGetLastError());
-    ln_bwd_reduce_kernel<<<(2 * E + 255) / 256, 256, 0, stream>>>(workspace, grid, E, dgamma, dbeta);
+    ln_bwd_reduce_kernel<<<2 * E / 32, 256, 0, stream>>>(workspace, grid, E, dgamma, dbeta);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -108,7 +140,7 @@ int launch_ln_bwd(const bf16* x, int64_t x_row_stride, const bf16* dy, const flo
 // ---------------------------------------------------------------------------------------------------
 // GELU (mlp.py:36, exact erf form in the reference).  Forward in training = the inference epilogue's function (common.cuh
 // gelu_tanh_fit, |deviation from erf-GELU| <= 2.5e-5) so that a training forward equals an inference forward bit for bit;
-// backward = the derivative of the exact form, Phi(u) + u phi(u).
+// backward = Phi(u) + u phi(u), the derivative of the exact form, evaluated with the forward's fit of Phi.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ u, bf16* __restrict__ y, int64_t n8) {
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -124,10 +156,16 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const bf16* __restrict__ 
         reinterpret_cast<uint4*>(y)[i] = o;
     }
 }
+// d/du of u Phi(u) = Phi(u) + u phi(u): Phi from the forward's tanh fit, phi by one ex2 (|error| < 3e-4 including tanh.approx,
+// an eighth of the bf16 step of the result; erff + expf made this kernel instruction-bound at half the HBM rate)
 __device__ __forceinline__ float gelu_grad(float u) {
-    const float cdf = 0.5f * (1.0f + erff(u * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * u * u);
-    return fmaf(u, pdf, cdf);
+    float t;
+    const float uu = u * u, x2 = fminf(uu, 64.0f);
+    float p = fmaf(-3.51516788e-04f, x2, 3.70056460e-02f);
+    p = fmaf(p, x2, 7.97507884e-01f);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u * p));
+    const float pdf = 0.3989422804014327f * ex2_approx(-0.72134752044448f * uu);
+    return fmaf(u, pdf, fmaf(0.5f, t, 0.5f));
 }
 __global__ void __launch_bounds__(256) gelu_bwd_kernel(const bf16* __restrict__ u, const bf16* dy, bf16* du, int64_t n8) {   // du may alias dy
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {

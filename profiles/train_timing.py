@@ -12,10 +12,12 @@ x = synth.make_volume(8, 32, 224, 224, seed=1).cuda()
 batch = {"source": x, "target": torch.randint(0, 2, (8,), device="cuda")}
 def sync(): torch.cuda.synchronize(); return time.perf_counter()
 for it in range(4):
+    if it == 3: torch.cuda.cudart().cudaProfilerStart()   # ncu --profile-from-start off: one steady-state step
     t0 = sync(); opt.zero_grad(); m.sync_weights(); t1 = sync()
     loss = m.training_step(batch, 0); t2 = sync()
     loss.backward(); t3 = sync()
     opt.step(); t4 = sync()
+    if it == 3: torch.cuda.cudart().cudaProfilerStop()
     print(f"iter {it}: zero_grad+repack {1e3*(t1-t0):.2f} ms  forward {1e3*(t2-t1):.2f}  backward {1e3*(t3-t2):.2f}  adamw {1e3*(t4-t3):.2f}  loss {float(loss.detach()):.4f}")
 m.profile_begin()
 loss = m.training_step(batch, 0); loss.backward()

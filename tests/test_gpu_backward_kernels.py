@@ -114,3 +114,25 @@ def test_weight_gradient_gemm_fp32_out(Nout, Kin, M):
     torch.cuda.synchronize()
     want = dY.float().t() @ X.float()
     torch.testing.assert_close(out, want, rtol=2e-3, atol=2e-3 * float(want.abs().max()))
+
+
+@pytest.mark.parametrize("Nout,Kin,M", [(1536, 384, 8256), (384, 1536, 4160), (1152, 384, 1000), (384, 384, 65792), (128, 192, 37),
+                                        (2304, 768, 5200)])
+@pytest.mark.parametrize("bias", [True, False])
+def test_weight_gradient_from_row_major_activations(Nout, Kin, M, bias):
+    """dW = dY^T X and db = colsum(dY) read from the row-major activations (MN-major tcgen05 operands; ragged token tails are
+    zero-filled by TMA).  Outputs are overwritten, not accumulated."""
+    cabi, L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(3 * Nout + Kin + M)
+    dY = (torch.randn(M, Nout, device="cuda", generator=g) * 0.1).bfloat16()
+    X = torch.randn(M, Kin, device="cuda", generator=g).bfloat16()
+    dW = torch.full((Nout, Kin), float("nan"), device="cuda")
+    db = torch.full((Nout,), float("nan"), device="cuda") if bias else None
+    cabi.check(L.mst_kernel_wgrad_bf16(cabi.ptr(dY), cabi.ptr(X), M, Nout, Kin, cabi.ptr(dW), cabi.ptr(db) if bias else None, _stream()))
+    torch.cuda.synchronize()
+    want = dY.float().t() @ X.float()
+    torch.testing.assert_close(dW, want, rtol=2e-3, atol=2e-3 * float(want.abs().max()))
+    if bias:
+        wb = dY.float().sum(0)
+        torch.testing.assert_close(db, wb, rtol=1e-4, atol=1e-4 * float(wb.abs().max()) + 1e-4)
+
