@@ -298,7 +298,7 @@ namespace mst {
 // The N x N probabilities exist only as register fragments.
 // ---------------------------------------------------------------------------------------------------
 namespace attb {
-constexpr int MAX_WARPS = 12;     // warps = ceil(row blocks / 2): 17 blocks of 16 rows (N = 257) -> 9 warps, two rounds per phase
+constexpr int MAX_WARPS = 12;     // 384 threads x 168 registers fill the register file
 constexpr float LOG2E = 1.4426950408889634f;
 
 // A-operand fragments of 16 rows (g, g+8) x 64 dims from a swizzled [rows][128 B] shared-memory tile
@@ -314,17 +314,21 @@ __device__ __forceinline__ void load_a(uint32_t (&a)[4][4], const uint8_t* tile,
 // acc[nb] (16 x 8) = A (16 x 64) . B[row0 + nb*8 .. +8]^T for nb < 4: B rows are the "n" index, K-major (ldmatrix, no transpose)
 __device__ __forceinline__ void mma_rows(float (&acc)[4][4], const uint32_t (&a)[4][4], uint32_t tile_u32, int row0, int lane) {
 #pragma unroll
-    for (int nb = 0; nb < 4; ++nb) {
-        acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
-        const int row = row0 + nb * 8 + (lane & 7);
+    for (int nb = 0; nb < 4; ++nb) acc[nb][0] = acc[nb][1] = acc[nb][2] = acc[nb][3] = 0.f;
+    // issue order: consecutive MMAs write different accumulators (a dependent pair back to back waits out the MMA latency)
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int c = half * 4 + (lane >> 3);
-            uint32_t b[4];
-            ldmatrix_x4(b, tile_u32 + row * 128 + ((c ^ (row & 7)) << 4));
-            mma_bf16_16816(acc[nb], a[2 * half], b[0], b[1]);
-            mma_bf16_16816(acc[nb], a[2 * half + 1], b[2], b[3]);
+    for (int half = 0; half < 2; ++half) {
+        const int c = half * 4 + (lane >> 3);
+        uint32_t b[4][4];
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) {
+            const int row = row0 + nb * 8 + (lane & 7);
+            ldmatrix_x4(b[nb], tile_u32 + row * 128 + ((c ^ (row & 7)) << 4));
         }
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) mma_bf16_16816(acc[nb], a[2 * half], b[nb][0], b[nb][1]);
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) mma_bf16_16816(acc[nb], a[2 * half + 1], b[nb][2], b[nb][3]);
     }
 }
 // out (16 x 64) += A (16 x 32, from the C fragments c[4][4] of a 16 x 32 block) . B[row0 .. row0+32] (32 x 64, ldmatrix transposed)
@@ -424,11 +428,16 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, c
             float sacc[4][4];
             mma_rows(sacc, qa, ks_u, ch * 32, lane);
             float cm0 = -CUDART_INF_F, cm1 = -CUDART_INF_F;
+            if (ch * 32 + 32 > N) {   // only the last chunk(s) hold padding keys
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int key = ch * 32 + nb * 8 + 2 * t;
+                    if (key >= N) { sacc[nb][0] = -CUDART_INF_F; sacc[nb][2] = -CUDART_INF_F; }
+                    if (key + 1 >= N) { sacc[nb][1] = -CUDART_INF_F; sacc[nb][3] = -CUDART_INF_F; }
+                }
+            }
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                const int key = ch * 32 + nb * 8 + 2 * t;
-                if (key >= N) { sacc[nb][0] = -CUDART_INF_F; sacc[nb][2] = -CUDART_INF_F; }
-                if (key + 1 >= N) { sacc[nb][1] = -CUDART_INF_F; sacc[nb][3] = -CUDART_INF_F; }
                 cm0 = fmaxf(cm0, fmaxf(sacc[nb][0], sacc[nb][1]));
                 cm1 = fmaxf(cm1, fmaxf(sacc[nb][2], sacc[nb][3]));
             }
@@ -439,11 +448,11 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, c
             float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
-                rs0 += exp2f((sacc[nb][0] - mn0) * LOG2E) + exp2f((sacc[nb][1] - mn0) * LOG2E);
-                rs1 += exp2f((sacc[nb][2] - mn1) * LOG2E) + exp2f((sacc[nb][3] - mn1) * LOG2E);
+                rs0 += ex2_approx((sacc[nb][0] - mn0) * LOG2E) + ex2_approx((sacc[nb][1] - mn0) * LOG2E);
+                rs1 += ex2_approx((sacc[nb][2] - mn1) * LOG2E) + ex2_approx((sacc[nb][3] - mn1) * LOG2E);
             }
-            l0 = l0 * exp2f((m0 - mn0) * LOG2E) + rs0;
-            l1 = l1 * exp2f((m1 - mn1) * LOG2E) + rs1;
+            l0 = l0 * ex2_approx((m0 - mn0) * LOG2E) + rs0;
+            l1 = l1 * ex2_approx((m1 - mn1) * LOG2E) + rs1;
             m0 = mn0; m1 = mn1;
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
@@ -456,80 +465,90 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, c
     }
     __syncthreads();
 
-    // ---- phase 2: dQ (queries as rows) ----
-    for (int rb = warp; rb < n_rb; rb += WARPS) {
-        const int r0 = rb * 16 + g, r1 = r0 + 8;
-        uint32_t qa[4][4], ga[4][4];
-        load_a(qa, Qs, r0, r1, t);
-        load_a(ga, Gs, r0, r1, t);
-        const float ls0 = lse[r0], ls1 = lse[r1], d0 = Dv[r0], d1 = Dv[r1];
-        float dq[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
-        for (int ch = 0; ch < n_ch; ++ch) {
-            float sacc[4][4], dp[4][4];
-            mma_rows(sacc, qa, ks_u, ch * 32, lane);
-            mma_rows(dp, ga, vs_u, ch * 32, lane);
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const int key = ch * 32 + nb * 8 + 2 * t;
-                const bool v0 = key < N, v1 = key + 1 < N;
-                const float p00 = v0 ? exp2f(fmaf(sacc[nb][0], LOG2E, -ls0)) : 0.f, p01 = v1 ? exp2f(fmaf(sacc[nb][1], LOG2E, -ls0)) : 0.f;
-                const float p10 = v0 ? exp2f(fmaf(sacc[nb][2], LOG2E, -ls1)) : 0.f, p11 = v1 ? exp2f(fmaf(sacc[nb][3], LOG2E, -ls1)) : 0.f;
-                sacc[nb][0] = p00 * (dp[nb][0] - d0); sacc[nb][1] = p01 * (dp[nb][1] - d0);     // dS
-                sacc[nb][2] = p10 * (dp[nb][2] - d1); sacc[nb][3] = p11 * (dp[nb][3] - d1);
+    // ---- phases 2 and 3 read the same tiles and write disjoint outputs: ONE pool of 2 n_rb work units over all warps, the longer
+    //      dK/dV units first (N = 257: 34 units on 12 warps = 3 rounds instead of 2 + 2 on 9 warps) ----
+    for (int u = warp; u < 2 * n_rb; u += WARPS) {
+        if (u >= n_rb) {   // dQ of one 16-query block (queries as rows)
+            const int rb = u - n_rb;
+            const int r0 = rb * 16 + g, r1 = r0 + 8;
+            uint32_t qa[4][4], ga[4][4];
+            load_a(qa, Qs, r0, r1, t);
+            load_a(ga, Gs, r0, r1, t);
+            const float ls0 = lse[r0], ls1 = lse[r1], d0 = Dv[r0], d1 = Dv[r1];
+            float dq[8][4];
+    #pragma unroll
+            for (int i = 0; i < 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+            for (int ch = 0; ch < n_ch; ++ch) {
+                float sacc[4][4], dp[4][4];
+                mma_rows(sacc, qa, ks_u, ch * 32, lane);
+                mma_rows(dp, ga, vs_u, ch * 32, lane);
+                if (ch * 32 + 32 > N) {   // padding keys (zero K rows give S = 0, not -inf): only in the last chunk(s)
+    #pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        const int key = ch * 32 + nb * 8 + 2 * t;
+                        if (key >= N) { sacc[nb][0] = -CUDART_INF_F; sacc[nb][2] = -CUDART_INF_F; }
+                        if (key + 1 >= N) { sacc[nb][1] = -CUDART_INF_F; sacc[nb][3] = -CUDART_INF_F; }
+                    }
+                }
+    #pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const float p00 = ex2_approx(fmaf(sacc[nb][0], LOG2E, -ls0)), p01 = ex2_approx(fmaf(sacc[nb][1], LOG2E, -ls0));
+                    const float p10 = ex2_approx(fmaf(sacc[nb][2], LOG2E, -ls1)), p11 = ex2_approx(fmaf(sacc[nb][3], LOG2E, -ls1));
+                    sacc[nb][0] = p00 * (dp[nb][0] - d0); sacc[nb][1] = p01 * (dp[nb][1] - d0);     // dS
+                    sacc[nb][2] = p10 * (dp[nb][2] - d1); sacc[nb][3] = p11 * (dp[nb][3] - d1);
+                }
+                mma_cols(dq, sacc, ks_u, ch * 32, lane);
             }
-            mma_cols(dq, sacc, ks_u, ch * 32, lane);
-        }
-        if (r0 < N) {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld);
-#pragma unroll
-            for (int dn = 0; dn < 8; ++dn) dst[dn * 4 + t] = pack_bf16x2(dq[dn][0] * 0.125f, dq[dn][1] * 0.125f);
-        }
-        if (r1 < N) {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld);
-#pragma unroll
-            for (int dn = 0; dn < 8; ++dn) dst[dn * 4 + t] = pack_bf16x2(dq[dn][2] * 0.125f, dq[dn][3] * 0.125f);
-        }
-    }
-
-    // ---- phase 3: dK, dV (keys as rows) ----
-    for (int kb = warp; kb < n_rb; kb += WARPS) {
-        const int r0 = kb * 16 + g, r1 = r0 + 8;
-        uint32_t ka[4][4], va[4][4];
-        load_a(ka, Ks, r0, r1, t);
-        load_a(va, Vs, r0, r1, t);
-        float dk[8][4], dv[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
-        for (int ch = 0; ch < n_ch; ++ch) {
-            float st[4][4], dpt[4][4];
-            mma_rows(st, ka, qs_u, ch * 32, lane);       // S^T[key, query] = k . q'
-            mma_rows(dpt, va, gs_u, ch * 32, lane);      // dP^T[key, query] = v . dO
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const int qi = ch * 32 + nb * 8 + 2 * t;
-                const float la = lse[qi], lb = lse[qi + 1], da = Dv[qi], dbq = Dv[qi + 1];
-                const float p00 = exp2f(fmaf(st[nb][0], LOG2E, -la)), p01 = exp2f(fmaf(st[nb][1], LOG2E, -lb));   // lse = +inf for padding
-                const float p10 = exp2f(fmaf(st[nb][2], LOG2E, -la)), p11 = exp2f(fmaf(st[nb][3], LOG2E, -lb));
-                st[nb][0] = p00; st[nb][1] = p01; st[nb][2] = p10; st[nb][3] = p11;
-                dpt[nb][0] = p00 * (dpt[nb][0] - da); dpt[nb][1] = p01 * (dpt[nb][1] - dbq);
-                dpt[nb][2] = p10 * (dpt[nb][2] - da); dpt[nb][3] = p11 * (dpt[nb][3] - dbq);
+            if (r0 < N) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld);
+    #pragma unroll
+                for (int dn = 0; dn < 8; ++dn) dst[dn * 4 + t] = pack_bf16x2(dq[dn][0] * 0.125f, dq[dn][1] * 0.125f);
             }
-            mma_cols(dv, st, gs_u, ch * 32, lane);       // dV += P^T dO
-            mma_cols(dk, dpt, qs_u, ch * 32, lane);      // dK += dS^T q'
-        }
-        if (r0 < N) {
-            uint32_t* dK = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld + E);
-            uint32_t* dV = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld + 2 * E);
-#pragma unroll
-            for (int dn = 0; dn < 8; ++dn) { dK[dn * 4 + t] = pack_bf16x2(dk[dn][0], dk[dn][1]); dV[dn * 4 + t] = pack_bf16x2(dv[dn][0], dv[dn][1]); }
-        }
-        if (r1 < N) {
-            uint32_t* dK = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld + E);
-            uint32_t* dV = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld + 2 * E);
-#pragma unroll
-            for (int dn = 0; dn < 8; ++dn) { dK[dn * 4 + t] = pack_bf16x2(dk[dn][2], dk[dn][3]); dV[dn * 4 + t] = pack_bf16x2(dv[dn][2], dv[dn][3]); }
+            if (r1 < N) {
+                uint32_t* dst = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld);
+    #pragma unroll
+                for (int dn = 0; dn < 8; ++dn) dst[dn * 4 + t] = pack_bf16x2(dq[dn][2] * 0.125f, dq[dn][3] * 0.125f);
+            }
+    
+        } else {           // dK, dV of one 16-key block (keys as rows)
+            const int kb = u;
+            const int r0 = kb * 16 + g, r1 = r0 + 8;
+            uint32_t ka[4][4], va[4][4];
+            load_a(ka, Ks, r0, r1, t);
+            load_a(va, Vs, r0, r1, t);
+            float dk[8][4], dv[8][4];
+    #pragma unroll
+            for (int i = 0; i < 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+            for (int ch = 0; ch < n_ch; ++ch) {
+                float st[4][4], dpt[4][4];
+                mma_rows(st, ka, qs_u, ch * 32, lane);       // S^T[key, query] = k . q'
+                mma_rows(dpt, va, gs_u, ch * 32, lane);      // dP^T[key, query] = v . dO
+    #pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    const int qi = ch * 32 + nb * 8 + 2 * t;
+                    const float la = lse[qi], lb = lse[qi + 1], da = Dv[qi], dbq = Dv[qi + 1];
+                    const float p00 = ex2_approx(fmaf(st[nb][0], LOG2E, -la)), p01 = ex2_approx(fmaf(st[nb][1], LOG2E, -lb));   // lse = +inf for padding
+                    const float p10 = ex2_approx(fmaf(st[nb][2], LOG2E, -la)), p11 = ex2_approx(fmaf(st[nb][3], LOG2E, -lb));
+                    st[nb][0] = p00; st[nb][1] = p01; st[nb][2] = p10; st[nb][3] = p11;
+                    dpt[nb][0] = p00 * (dpt[nb][0] - da); dpt[nb][1] = p01 * (dpt[nb][1] - dbq);
+                    dpt[nb][2] = p10 * (dpt[nb][2] - da); dpt[nb][3] = p11 * (dpt[nb][3] - dbq);
+                }
+                mma_cols(dv, st, gs_u, ch * 32, lane);       // dV += P^T dO
+                mma_cols(dk, dpt, qs_u, ch * 32, lane);      // dK += dS^T q'
+            }
+            if (r0 < N) {
+                uint32_t* dK = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld + E);
+                uint32_t* dV = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r0) * ld + 2 * E);
+    #pragma unroll
+                for (int dn = 0; dn < 8; ++dn) { dK[dn * 4 + t] = pack_bf16x2(dk[dn][0], dk[dn][1]); dV[dn * 4 + t] = pack_bf16x2(dv[dn][0], dv[dn][1]); }
+            }
+            if (r1 < N) {
+                uint32_t* dK = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld + E);
+                uint32_t* dV = reinterpret_cast<uint32_t*>(dbase + static_cast<int64_t>(r1) * ld + 2 * E);
+    #pragma unroll
+                for (int dn = 0; dn < 8; ++dn) { dK[dn * 4 + t] = pack_bf16x2(dk[dn][2], dk[dn][3]); dV[dn * 4 + t] = pack_bf16x2(dv[dn][2], dv[dn][3]); }
+            }
+    
         }
     }
 }
@@ -539,7 +558,7 @@ int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* d
     const size_t smem = static_cast<size_t>(NKP) * (4 * 128 + 8);
     MST_REQUIRE(smem <= 227 * 1024, "attention backward: N=%d tokens do not fit shared memory", N);
     MST_SET_DYN_SMEM(attention_bwd_kernel, 227 * 1024);
-    int warps = ((N + 15) / 16 + 1) / 2;
+    int warps = 2 * ((N + 15) / 16);      // one pool of 2 x (row blocks) units for the dQ and dK/dV phases
     warps = warps < 4 ? 4 : (warps > attb::MAX_WARPS ? attb::MAX_WARPS : warps);
     attention_bwd_kernel<<<BD * heads, warps * 32, smem, stream>>>(qkv, o, dO, dqkv, N, heads, NKP);
     MST_CHECK_CUDA(cudaGetLastError());
