@@ -703,7 +703,8 @@ struct TrainWs {
 };
 static TrainWs carve_train(const mst_config& c, int B, int D, int H, int W, uint8_t* base) {
     const int64_t E = c.embed_dim, BD = static_cast<int64_t>(B) * D, P = static_cast<int64_t>(H / 14) * (W / 14), N = P + 1, M = BD * N;
-    const int64_t Mpad = (std::max(M, BD * P) + 63) / 64 * 64;
+    // (>= 448: the fp32-output GEMM that contracts over the padded token dimension runs on the streaming schedule, K > 384)
+    const int64_t Mpad = std::max<int64_t>(448, (std::max(M, BD * P) + 63) / 64 * 64);
     size_t off = 0;
     auto take = [&](size_t bytes) { void* p = base ? base + off : nullptr; off += (bytes + 255) & ~static_cast<size_t>(255); return p; };
     TrainWs w;

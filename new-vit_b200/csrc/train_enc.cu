@@ -1,13 +1,14 @@
 // Backward pass of the DINOv2 encoder (BASELINE.json config 5 with the default, un-frozen construction: main_train.py:110-126 trains
 // every parameter of dino.py:56-103).  bf16 activations and activation gradients, fp32 weight gradients, fp32 statistics.
 //
-// The heavy contractions reuse the tcgen05 GEMM of gemm_tc.cu:
-//   dgrad   dX = dY . W          ->  gemm(A = dY [M, N_out], weight = W^T [K_in, N_out])            (bf16 out)
-//   wgrad   dW = dY^T . X        ->  gemm(A = dY^T [N_out, M], weight = X^T [K_in, M], fp32 out)     (EPI_RAW_F32)
-// This file holds what sits between them: the transposes that turn token-major activations into K-major operands (with the bias
-// gradient = column sums on the way), LayerNorm backward, GELU forward / backward, the attention backward (warp-level tensor cores:
-// recomputes the 257 x 257 probabilities per (slice, head) from q, k and the saved row log-sum-exp; nothing N x N touches HBM),
-// and the small gradients of the patch embedding / position table / class token.
+// The heavy contractions are tcgen05 GEMMs:
+//   dgrad   dX = dY . W          ->  gemm_tc.cu, gemm(A = dY [M, N_out], weight = W^T [K_in, N_out])          (bf16 out)
+//   wgrad   dW = dY^T . X        ->  gemm_wgrad.cu, MN-major operands straight from the row-major activations  (fp32 out, bias gradient too);
+//                                    shapes that kernel does not take go through the transposes below and gemm_tc.cu's EPI_RAW_F32
+// This file holds what sits between them: LayerNorm backward, GELU forward / backward, the attention backward (warp-level tensor cores:
+// recomputes the 257 x 257 probabilities per (slice, head) from q, k and the row log-sum-exp; nothing N x N touches HBM), the fallback
+// transposes (token-major -> K-major operands, with the bias gradient = column sums on the way), and the small gradients of the patch
+// embedding / position table / class token.
 #include <math_constants.h>
 #include "common.cuh"
 #include "ptx.cuh"

@@ -192,3 +192,36 @@ def test_full_training_step_matches_reference_golden():
     m.eval()
     with torch.no_grad():
         assert torch.isfinite(m(x, src_key_padding_mask=mask)).all()
+
+
+def test_vit_b_training_step_matches_oracle_autograd():
+    """ViT-B/14 (config 4's encoder) with every parameter trainable: E = 768 exercises the other instantiations of the backward kernels
+    (LayerNorm backward EPL = 24, weight-gradient tiles 18 x 4 / 6 x 16, 12 heads).  Reference = the oracle under torch autograd on the CPU
+    (pinned to the live reference's gradients by tests/test_training_cpu.py), one small volume."""
+    from test_training_cpu import oracle_full_train_step
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    B, D, H = 1, 3, 112
+    sd = synth.make_state_dict("b", 2, seed=5, variant="peaky", img_size=H)
+    x = synth.make_volume(B, D, H, H, seed=9)
+    target = torch.tensor([1])
+    _, loss_ref, grads = oracle_full_train_step(sd, x, None, target)
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16", model_size="b", img_size=H).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    opt = m.configure_optimizers()[0]
+    opt.zero_grad()
+    loss = m.training_step({"source": x, "target": target.cuda()}, 0)
+    assert abs(float(loss.detach()) - float(loss_ref)) <= 2e-2
+    loss.backward()
+    bad = {}
+    for n, p in m.named_parameters():
+        if n == "encoder.mask_token" or n.endswith("attn.qkv.bias") or n.endswith("in_proj_bias"):
+            continue     # no gradient / an exactly-zero third (see the ViT-S test)
+        want = grads[n]
+        got = p.grad.detach().cpu()
+        if float(want.norm()) < 1e-12:
+            continue
+        cos, ratio = _cosine(got, want), float(got.norm()) / float(want.norm())
+        if not (cos >= 0.99 and 0.95 <= ratio <= 1.05):
+            bad[n] = (cos, ratio)
+    assert not bad, bad
