@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(wt::THREADS, 1)
 gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaDesc tmC, const bf16* __restrict__ W,
                int M, int N, int n_pairs, EpiParams ep) {
     using namespace wt;
+    const int xp = kDbgTiming ? ep.P : 0;   // experiment bits (mainloop / epilogue ceilings): compiled out of the product build
     constexpr bool LNF = MODE == EPI_LN_BIAS || MODE == EPI_LN_BIAS_GELU;
     constexpr bool GELU = MODE == EPI_BIAS_GELU || MODE == EPI_LN_BIAS_GELU;
     extern __shared__ uint8_t smem_raw[];
@@ -150,7 +151,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
         if (lane == 0) {
             // ===================== TMA producer =====================
             int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < ((ep.P & 4) ? 0 : t_count); ++it) {   // (experiment 4: no operand traffic at all)
+            for (int it = 0; it < ((xp & 4) ? 0 : t_count); ++it) {   // (experiment 4: no operand traffic at all)
                 const int tok0 = (t_first + it * groups) * NT + static_cast<int>(cta_rank) * NTH;
                 // One pair per group pulls a later token tile into L2 (the other pairs of the group read the same rows):
                 // under load an HBM miss costs more than the ring covers, an L2 hit does not.
@@ -189,7 +190,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
 #pragma unroll
             for (int s2 = 0; s2 < SPT; ++s2) {   // unrolled: the weight (A) addresses in TMEM are compile-time offsets
                 const long long g1 = MST_DBG_CLOCK();
-                if (!(ep.P & 4)) mbar_wait(&full_bar[stage], phase);
+                if (!(xp & 4)) mbar_wait(&full_bar[stage], phase);
                 if (dbg) gd[1] += MST_DBG_CLOCK() - g1;
                 tc_fence_after_sync();
                 const uint32_t b_lo = b_lo0 + stage * (STAGE_BYTES >> 4);
@@ -199,7 +200,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
                         umma_bf16_ts_pair(d_tmem, tmem_base + static_cast<uint32_t>((s2 * 4 * CPS + k) * 8),
                                           make_desc(b_lo + (k >> 2) * (CHUNK_BYTES >> 4) + 2 * (k & 3), kDescHi), idesc,
                                           (s2 | k) != 0 ? 1u : 0u);
-                    if (!(ep.P & 4)) umma_commit_pair(&empty_bar[stage], 0x3);      // both CTAs refill their slot
+                    if (!(xp & 4)) umma_commit_pair(&empty_bar[stage], 0x3);      // both CTAs refill their slot
                     if (s2 == SPT - 1) umma_commit_pair(&tfull_bar[acc], 0x3);      // both CTAs' teams read their half
                 }
                 __syncwarp();
@@ -220,7 +221,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
         uint8_t* stg = smem + STG_OFF + e * 2 * STG_TILE;
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(W_COLS + team * NT + half * 64);
         const bool store_ok = feat0 < N;
-        const bool skip_epi = (ep.P & 1) != 0;   // experiment: mainloop ceiling (accumulators are read and dropped)
+        const bool skip_epi = (xp & 1) != 0;   // experiment: mainloop ceiling (accumulators are read and dropped)
         const bool dbg_all = kDbgTiming && ep.dbg != nullptr && blockIdx.x < 2 && lane == 0;
         long long busy = 0, waitt = 0;
         float* rsb = reinterpret_cast<float*>(smem + RS_OFF) + e * 64;   // this warp's 64 rstd values of the current tile
@@ -262,7 +263,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
                 }
             };
             if (skip_epi) {
-                if (!(ep.P & 2)) {   // (experiment 2: not even the TMEM reads)
+                if (!(xp & 2)) {   // (experiment 2: not even the TMEM reads)
                     uint32_t r0[16];
                     for (int g = 0; g < 4; ++g) { tmem_ld_32x32b_x16(taddr0 + g * 16, r0); tmem_ld_wait(); }
                 }
@@ -306,7 +307,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
             auto write_out = [&](int c) {   // the finished [32 tokens][32 features] tile c -> global
                 uint8_t* tile = stg + c * STG_TILE;
                 const int tok0 = tok_tile + c * 32;
-                if (ep.P & 16) {   // (experiment 16: vector stores instead of the TMA store)
+                if (xp & 16) {   // (experiment 16: vector stores instead of the TMA store)
                     __syncwarp();
                     if (store_ok) {
 #pragma unroll
@@ -321,7 +322,7 @@ gemm_wt_kernel(const __grid_constant__ TmaDesc tmX, const __grid_constant__ TmaD
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0 && store_ok && !(ep.P & 8)) {   // (experiment 8: everything but the store itself)
+                if (lane == 0 && store_ok && !(xp & 8)) {   // (experiment 8: everything but the store itself)
                     tma_store_2d(&tmC, tile, feat0, tok0);   // rows >= M are clipped by the tensor map
                     tma_store_commit();
                 }
