@@ -21,6 +21,7 @@ def test_shard_volumes_partitions_exactly():
 
 class _FakeModel(torch.nn.Module):
     """Stands in for the CUDA model on CPU: one 'logit' pair per volume computed from the volume itself."""
+    out_ch = 2     # read by predict_sharded on a rank whose shard is empty
 
     def forward(self, source, save_attn=False, src_key_padding_mask=None):
         s = source.reshape(source.shape[0], -1)
@@ -46,7 +47,7 @@ def _worker(rank, world, port, total, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("total", [8, 5])
+@pytest.mark.parametrize("total", [8, 5, 1])   # 1: the second rank's shard is empty
 def test_predict_sharded_gloo_world2(total):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
