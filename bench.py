@@ -265,6 +265,12 @@ def run_extras(model_s, dev, rank, world, timed, peaks):
             "grad_allreduce_bytes": trainable * 4 if world > 1 else 0, "loss": float(train_step().detach()),
             "model_tflops": fl * world / (ms * 1e-3) / 1e12,
             "ms_by_category": {k: round(v[0] / 3, 3) for k, v in prof.items() if v[1]}}
+        if world > 1:
+            # every rank saw different volumes and the same all-reduced gradient: the parameters must still be bit-identical
+            chk = torch.stack([p.detach().double().sum() for p in mt.parameters() if p.requires_grad]).sum().reshape(1)
+            allc = [torch.zeros_like(chk) for _ in range(world)]
+            torch.distributed.all_gather(allc, chk)
+            out[key]["ranks_in_sync"] = bool(all(float(c) == float(allc[0]) for c in allc))
         del mt, opt, xt, batch
         torch.cuda.empty_cache()
     # ---- config 4 ----
