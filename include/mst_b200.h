@@ -249,6 +249,11 @@ MST_API int mst_kernel_gelu_bf16(const void* u, void* y, const void* dy, void* d
 MST_API int mst_kernel_transpose_bf16(const void* in, void* out, float* colsum, int32_t M, int32_t C, int32_t Mpad, void* stream);
 MST_API int mst_kernel_attention_bwd_bf16(const void* qkv, const void* o, const void* dO, void* dqkv, int32_t BD, int32_t N, int32_t heads,
                                   void* stream);
+/* the N = 257 forward kernel with the log2-domain row log-sum-exp lse [BD*heads, 257] kept (what the training forward runs), and the
+ * backward pass that takes it instead of recomputing it */
+MST_API int mst_kernel_attention_lse_bf16(const void* qkv, void* out, float* lse, int32_t BD, int32_t heads, void* stream);
+MST_API int mst_kernel_attention_bwd_lse_bf16(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, int32_t BD,
+                                              int32_t N, int32_t heads, void* stream);
 MST_API int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream);
 /* profiling aid: same as mst_kernel_gemm_bf16, plus cycle counters of CTA 0 (8 x int64: MMA warp wait-for-accumulator,
  * wait-for-operands, total, tiles; epilogue warp 0 wait-for-MMA, TMEM read, math+store) */

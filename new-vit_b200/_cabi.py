@@ -75,6 +75,8 @@ def lib():
     L.mst_kernel_gelu_bf16.argtypes = [vp, vp, vp, vp, i64, vp]
     L.mst_kernel_transpose_bf16.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.mst_kernel_attention_bwd_bf16.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    L.mst_kernel_attention_lse_bf16.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.mst_kernel_attention_bwd_lse_bf16.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
     L.mst_kernel_row_stats_bf16.argtypes = [vp, vp, i32, i32, ctypes.c_float, vp]
     L.mst_debug_gemm_timing.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     L.mst_kernel_gemm_f32.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]

@@ -688,7 +688,7 @@ static int forward_t(mst_handle h, const void* src, int src_dtype, int B, int D,
 // (kernels: train_enc.cu; contractions: the tcgen05 GEMM).  Reference: Lightning's step, base_model.py:148-170, on the
 // default un-frozen construction (dino.py:56-103); dropout / drop-path are 0 there, so train == eval arithmetic.
 // ---------------------------------------------------------------------------------------------------
-struct TrainLayer { bf16 *x_in, *qkv, *ao, *x_mid, *u, *hid; };
+struct TrainLayer { bf16 *x_in, *qkv, *ao, *x_mid, *u, *hid; float* lse; };
 struct TrainWs {
     bf16* A0;                       // im2col of the input [BD*P, KP]
     std::vector<TrainLayer> L;
@@ -718,6 +718,7 @@ static TrainWs carve_train(const mst_config& c, int B, int D, int H, int W, uint
         w.L[l].x_mid = static_cast<bf16*>(take(M * E * 2));
         w.L[l].u = static_cast<bf16*>(take(M * 4 * E * 2));
         w.L[l].hid = static_cast<bf16*>(take(M * 4 * E * 2));
+        w.L[l].lse = static_cast<float*>(take(static_cast<size_t>(M) * c.enc_heads * 4));   // row log-sum-exp per (slice, head, token)
     }
     w.x_out = static_cast<bf16*>(take(M * E * 2));
     w.rowstat = static_cast<float*>(take(M * 4));
@@ -799,7 +800,10 @@ static int train_forward(mst_handle h, const void* src, int src_dtype, int B, in
             ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = T.qkv; ep.ldo = 3 * E;
             MST_LAUNCH(CAT_GEMM_QKV, Ops<bf16>::gemm(h, T.x_in, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
         }
-        MST_LAUNCH(CAT_ATTENTION, Ops<bf16>::attention(h, T.qkv, T.ao, BD, N, c.enc_heads, st));
+        if (N == 257)   // the specialised kernel keeps the row log-sum-exp for the backward pass
+            MST_LAUNCH(CAT_ATTENTION, launch_attention_tc257x16(T.qkv, T.ao, BD, c.enc_heads, h->num_sms, st, nullptr, T.lse));
+        else
+            MST_LAUNCH(CAT_ATTENTION, Ops<bf16>::attention(h, T.qkv, T.ao, BD, N, c.enc_heads, st));
         {
             EpiParams ep{};
             ep.bias = L.bproj; ep.res = T.x_in; ep.ldr = E; ep.out = T.x_mid; ep.ldo = E;
@@ -950,7 +954,7 @@ static int train_backward(mst_handle h, const float* denc, int B, int D, int H, 
         // ---- x_mid = x_in + proj(attn(LN1(x_in)))                                         (block.py:112, attention.py:56-69) ----
         MST_PROPAGATE(linear_wgrad(h, ws.dXm, E, T.ao, E, M, ws, gpw, gpb, st));
         MST_PROPAGATE(linear_dgrad(h, ws.dXm, E, h->wT[4 * l + 1], E, M, ws.dao, st));
-        MST_LAUNCH(CAT_BWD_ATTENTION, launch_attention_bwd(T.qkv, T.ao, ws.dao, ws.dqkv, BD, N, c.enc_heads, st));
+        MST_LAUNCH(CAT_BWD_ATTENTION, launch_attention_bwd(T.qkv, T.ao, ws.dao, ws.dqkv, BD, N, c.enc_heads, st, N == 257 ? T.lse : nullptr));
         MST_LAUNCH(CAT_BWD_POINTWISE, (launch_layernorm<bf16, bf16>(T.x_in, E, ws.ln, E, h->master[p + "norm1.weight"], h->master[p + "norm1.bias"],
                                                                      M, E, 1e-6f, st)));
         MST_PROPAGATE(linear_wgrad(h, ws.dqkv, 3 * E, ws.ln, E, M, ws, gqw, gqb, st));
@@ -1509,6 +1513,17 @@ int mst_kernel_attention_bwd_bf16(const void* qkv, const void* o, const void* dO
     MST_REQUIRE(qkv && o && dO && dqkv, "mst_kernel_attention_bwd_bf16: null argument");
     return launch_attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dO), static_cast<bf16*>(dqkv),
                                 BD, N, heads, static_cast<cudaStream_t>(stream));
+}
+int mst_kernel_attention_lse_bf16(const void* qkv, void* out, float* lse, int32_t BD, int32_t heads, void* stream) {
+    MST_REQUIRE(qkv && out && lse, "mst_kernel_attention_lse_bf16: null argument");
+    return launch_attention_tc257x16(static_cast<const bf16*>(qkv), static_cast<bf16*>(out), BD, heads, num_sms_current(),
+                                     static_cast<cudaStream_t>(stream), nullptr, lse);
+}
+int mst_kernel_attention_bwd_lse_bf16(const void* qkv, const void* o, const void* dO, const float* lse, void* dqkv, int32_t BD, int32_t N,
+                                      int32_t heads, void* stream) {
+    MST_REQUIRE(qkv && o && dO && lse && dqkv, "mst_kernel_attention_bwd_lse_bf16: null argument");
+    return launch_attention_bwd(static_cast<const bf16*>(qkv), static_cast<const bf16*>(o), static_cast<const bf16*>(dO), static_cast<bf16*>(dqkv),
+                                BD, N, heads, static_cast<cudaStream_t>(stream), lse);
 }
 int mst_kernel_row_stats_bf16(const void* x, float* rowstat, int32_t rows, int32_t E, float eps, void* stream) {
     MST_REQUIRE(x && rowstat, "mst_kernel_row_stats_bf16: null argument");

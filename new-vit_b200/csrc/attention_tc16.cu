@@ -156,11 +156,13 @@ __device__ __forceinline__ float dot8_16(const uint4& u, const float* q, float a
 #undef ATT_T
 #define ATT_T(i) do { if (dbg_on) { const long long _t = clock64(); dbg_acc[i] += _t - dbg_t; dbg_t = _t; } } while (0)
 
-template <int kPolyPairs>
+// kLse (training forward): the log2-domain row log-sum-exp  lse[item][token] = max * log2e + log2(sum)  is written for the backward
+// pass (train_enc.cu), which then skips its own recomputation; the inference instantiations do not carry the code.
+template <int kPolyPairs, bool kLse = false>
 __global__ void __launch_bounds__(atc16::THREADS, 1)
 attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_constant__ TmaDesc map16,
                        const __grid_constant__ TmaDesc mapO, const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                       int num_items, int heads, long long* __restrict__ dbg) {
+                       int num_items, int heads, long long* __restrict__ dbg, float* __restrict__ lse_out) {
     using namespace atc16;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -349,8 +351,11 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&sp_done[tm]);
             named_bar_sync(bar_id, 64);
-            const float inv = 1.0f / (sum + st[(2 + (ch ^ 1)) * 128 + row]);
+            const float tot = sum + st[(2 + (ch ^ 1)) * 128 + row];
+            const float inv = 1.0f / tot;
             const float p0 = st[4 * 128 + row];
+            if (kLse && ch == 0)
+                lse_out[static_cast<int64_t>(blockIdx.x + it * gridDim.x) * N_TOK + 1 + tm * 128 + row] = mb + log2f(tot);
             // ---- epilogue: O columns [64 + 32 ch, +32) of this warp's rows + p0 * v_cls, 1/l, bf16, 64-byte row pieces ----
             mbar_wait(&o_full[tm], par);
             tc_fence_after_sync();
@@ -503,7 +508,9 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
                 const float ma = merge[0], mb2 = merge[68], mc = merge[136];
                 const float mm = fmaxf(ma, fmaxf(mb2, mc));
                 const float wa = ex2_approx((ma - mm) * LOG2E), wb = ex2_approx((mb2 - mm) * LOG2E), wc = ex2_approx((mc - mm) * LOG2E);
-                const float inv = 1.0f / (merge[1] * wa + merge[69] * wb + merge[137] * wc);
+                const float tot = merge[1] * wa + merge[69] * wb + merge[137] * wc;
+                const float inv = 1.0f / tot;
+                if (kLse && lane == 0) lse_out[static_cast<int64_t>(item) * N_TOK] = mm * LOG2E + log2f(tot);
                 const float o0 = (merge[4 + 2 * lane] * wa + merge[72 + 2 * lane] * wb + merge[140 + 2 * lane] * wc) * inv;
                 const float o1 = (merge[5 + 2 * lane] * wa + merge[73 + 2 * lane] * wb + merge[141 + 2 * lane] * wc) * inv;
                 reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(s) * N_TOK) * E + h * 64)[lane] = pack_bf16x2(o0, o1);
@@ -520,7 +527,7 @@ attention_tc257x16_kernel(const __grid_constant__ TmaDesc map128, const __grid_c
     }
 }
 
-int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream, long long* dbg) {
+int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream, long long* dbg, float* lse_out) {
     using namespace atc16;
     const int E = heads * 64;
     TmaDesc m128, m16, mO;
@@ -530,9 +537,13 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     static const int poly = exp_env("MST_ATTN_POLY", 7);  // experiments: 0 = all exponentials on MUFU
     // 7 of 16 pairs on the polynomial: measured optimum (kernel 0.547 ms with 0, 0.495 / 0.469 / 0.510 / 0.499 / 0.569 ms with
     // 6 / 7 / 8 / 10 / 12 of 16, config-2 shape, profiles/attn_timing.py)
-    auto kern = poly == 0 ? attention_tc257x16_kernel<0> : attention_tc257x16_kernel<7>;
+    auto kern = lse_out != nullptr ? attention_tc257x16_kernel<7, true> : (poly == 0 ? attention_tc257x16_kernel<0> : attention_tc257x16_kernel<7>);
     MST_SET_DYN_SMEM(attention_tc257x16_kernel<0>, DYN_BYTES);
     MST_SET_DYN_SMEM(attention_tc257x16_kernel<7>, DYN_BYTES);
+    {
+        auto kl = attention_tc257x16_kernel<7, true>;
+        MST_SET_DYN_SMEM(kl, DYN_BYTES);
+    }
     const int items = BD * heads;
     const int grid = items < num_sms ? items : num_sms;
     cudaLaunchConfig_t cfg{};
@@ -541,7 +552,7 @@ int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int
     pattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pattr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = pattr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, m128, m16, mO, qkv, out, items, heads, dbg));
+    MST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, m128, m16, mO, qkv, out, items, heads, dbg, lse_out));
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -194,7 +194,7 @@ int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, 
 // tcgen05 attention for N == 257 tokens (ViT @224), sixteen softmax warps (two per TMEM lane quadrant and tile, splitting the key
 // columns): attention_tc16.cu
 int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
-                              long long* dbg = nullptr);
+                              long long* dbg = nullptr, float* lse_out = nullptr);   // lse_out [BD*heads, 257]: training forward
 
 // tcgen05 attention for any token count 17 <= N <= 360 (attention_tcg.cu); N == 257 keeps its specialised kernels
 bool attention_tcg_supported(int N);
@@ -263,6 +263,7 @@ int launch_transpose_colsum(const bf16* in, int64_t ld, bf16* out, float* colsum
 int launch_transpose_f32_to_bf16(const float* W, bf16* Wt, int N, int K, cudaStream_t stream);
 bool wgrad_tc_supported(int Nout, int Kin);
 int launch_wgrad_tc(const bf16* dY, int Nout, const bf16* X, int Kin, int M, float* dW, float* db, int num_sms, cudaStream_t stream);
-int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream);
+int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream,
+                         const float* lse = nullptr);   // lse [BD*heads, N] from the forward (nullable: recomputed)
 
 }  // namespace mst

@@ -293,7 +293,8 @@ namespace mst {
 //   qkv [BD*N, 3E] bf16 with q pre-scaled by 1/8 (as the forward's qkv GEMM writes it), o [BD*N, E] the forward output,
 //   dO  [BD*N, E]  ->  dqkv [BD*N, 3E]: d/d(q_raw) = 1/8 dS K,  d/dk = dS^T q,  d/dv = P^T dO
 // Q, K, V and dO of the item sit in shared memory (XOR-swizzled 16-byte chunks, as attention_mma.cu).  Three phases:
-//   1  D_i = dO_i . O_i  and  lse_i = log2 sum_j 2^(s_ij log2e)   (one query block of 16 rows per warp, online over key chunks)
+//   1  D_i = dO_i . O_i  and  lse_i = log2 sum_j 2^(s_ij log2e)   (one query block of 16 rows per warp, online over key chunks;
+//      skipped when the forward kernel saved lse: N = 257)
 //   2  dQ:  per query block, per 32-key chunk:  P = 2^(S log2e - lse), dP = dO V^T, dS = P (dP - D), dQ += dS K
 //   3  dK, dV: per 16-key block, per 32-query chunk, the transposed products:  P^T from K Q^T, dP^T = V dO^T, dV += P^T dO, dK += dS^T Q
 // The N x N probabilities exist only as register fragments.
@@ -356,7 +357,7 @@ __device__ __forceinline__ void mma_cols(float (&out)[8][4], const float (&c)[4]
 
 __global__ void __launch_bounds__(attb::MAX_WARPS * 32, 1)
 attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ dO, bf16* __restrict__ dqkv,
-                     int N, int heads, int NKP) {
+                     const float* __restrict__ lse_in, int N, int heads, int NKP) {
     using namespace attb;
     extern __shared__ __align__(128) uint8_t smem_ab[];
     uint8_t* Qs = smem_ab;
@@ -417,7 +418,10 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, c
         }
         Dv[i] = d;
     }
-    for (int rb = warp; rb < (NKP >> 4); rb += WARPS) {
+    if (lse_in != nullptr) {   // the forward kernel kept the row log-sum-exp (attention_tc16.cu, kLse): nothing to recompute
+        for (int i = threadIdx.x; i < NKP; i += THREADS) lse[i] = i < N ? lse_in[static_cast<int64_t>(blockIdx.x) * N + i] : CUDART_INF_F;
+    }
+    for (int rb = lse_in != nullptr ? (NKP >> 4) : warp; rb < (NKP >> 4); rb += WARPS) {
         if (rb >= n_rb) {   // rows beyond N: probabilities are defined as 0
             if (lane < 16) lse[rb * 16 + lane] = CUDART_INF_F;
             continue;
@@ -554,14 +558,15 @@ attention_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, c
     }
 }
 
-int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream) {
+int launch_attention_bwd(const bf16* qkv, const bf16* o, const bf16* dO, bf16* dqkv, int BD, int N, int heads, cudaStream_t stream,
+                         const float* lse) {
     const int NKP = ((N + 31) / 32) * 32;
     const size_t smem = static_cast<size_t>(NKP) * (4 * 128 + 8);
     MST_REQUIRE(smem <= 227 * 1024, "attention backward: N=%d tokens do not fit shared memory", N);
     MST_SET_DYN_SMEM(attention_bwd_kernel, 227 * 1024);
     int warps = 2 * ((N + 15) / 16);      // one pool of 2 x (row blocks) units for the dQ and dK/dV phases
     warps = warps < 4 ? 4 : (warps > attb::MAX_WARPS ? attb::MAX_WARPS : warps);
-    attention_bwd_kernel<<<BD * heads, warps * 32, smem, stream>>>(qkv, o, dO, dqkv, N, heads, NKP);
+    attention_bwd_kernel<<<BD * heads, warps * 32, smem, stream>>>(qkv, o, dO, dqkv, lse, N, heads, NKP);
     MST_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

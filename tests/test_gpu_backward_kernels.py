@@ -51,6 +51,36 @@ def test_attention_backward(BD, N, heads):
         torch.testing.assert_close(a, b, rtol=5e-2, atol=2e-2 * float(b.abs().max()))
 
 
+def test_forward_keeps_the_row_log_sum_exp_for_the_backward():
+    """N = 257: the tcgen05 forward kernel writes lse = log2 sum_j exp(s_ij) per (slice, head, token); the backward pass fed with it
+    gives the gradients of the recomputing path (same kernel, phase 1 skipped)."""
+    cabi, L = _lib()
+    BD, N, heads = 3, 257, 6
+    E = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(BD * N, 3 * E, device="cuda", generator=g)
+    qkv[:, :E] *= 0.6
+    qkv[5, :E] *= 6.0                      # one peaky query row
+    qkv = qkv.bfloat16()
+    dO = (torch.randn(BD * N, E, device="cuda", generator=g) * 0.5).bfloat16()
+    o = torch.empty(BD * N, E, device="cuda", dtype=torch.bfloat16)
+    lse = torch.full((BD * heads, N), float("nan"), device="cuda")
+    cabi.check(L.mst_kernel_attention_lse_bf16(cabi.ptr(qkv), cabi.ptr(o), cabi.ptr(lse), BD, heads, _stream()))
+    q, k, _ = qkv.float().reshape(BD, N, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    want = torch.logsumexp(q @ k.transpose(-2, -1), dim=-1).reshape(BD * heads, N) * 1.4426950408889634
+    torch.testing.assert_close(lse, want, rtol=0, atol=2e-3)
+    o2 = torch.empty_like(o)
+    cabi.check(L.mst_kernel_attention_bf16(cabi.ptr(qkv), cabi.ptr(o2), BD, N, heads, _stream()))
+    assert torch.equal(o, o2)              # the output does not depend on whether lse is kept
+    a = torch.full((BD * N, 3 * E), float("nan"), device="cuda", dtype=torch.bfloat16)
+    b = torch.full_like(a, float("nan"))
+    cabi.check(L.mst_kernel_attention_bwd_bf16(cabi.ptr(qkv), cabi.ptr(o), cabi.ptr(dO), cabi.ptr(a), BD, N, heads, _stream()))
+    cabi.check(L.mst_kernel_attention_bwd_lse_bf16(cabi.ptr(qkv), cabi.ptr(o), cabi.ptr(dO), cabi.ptr(lse), cabi.ptr(b), BD, N, heads, _stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(b.float()).all()
+    assert _relerr(b.float(), a.float()) <= 4e-3
+
+
 @pytest.mark.parametrize("rows,E", [(1000, 384), (7, 384), (4099, 768)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_layernorm_backward(rows, E, with_res):
