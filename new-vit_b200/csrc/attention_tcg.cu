@@ -1,4 +1,4 @@
-// Encoder attention on tcgen05 for ANY token count N <= 448 (head_dim 64):  config 4 of BASELINE.json runs ViT-B/14 at
+// Encoder attention on tcgen05 for ANY token count 17 <= N <= 352 (head_dim 64):  config 4 of BASELINE.json runs ViT-B/14 at
 // 252x252 = 325 tokens, registers add 4, other input sizes give other N; N == 257 has its own specialised kernel
 // (attention_tc16.cu).        out[s, i, h*64:(h+1)*64] = softmax(q_i . K^T) V        (reference layers/attention.py:56-69)
 //

@@ -196,7 +196,7 @@ int launch_attention_bf16(const bf16* qkv, bf16* out, int BD, int N, int heads, 
 int launch_attention_tc257x16(const bf16* qkv, bf16* out, int BD, int heads, int num_sms, cudaStream_t stream,
                               long long* dbg = nullptr, float* lse_out = nullptr);   // lse_out [BD*heads, 257]: training forward
 
-// tcgen05 attention for any token count 17 <= N <= 360 (attention_tcg.cu); N == 257 keeps its specialised kernels
+// tcgen05 attention for any token count 17 <= N <= 352 (attention_tcg.cu); N == 257 keeps its specialised kernels
 bool attention_tcg_supported(int N);
 int launch_attention_tcg(const bf16* qkv, bf16* out, int BD, int N, int heads, int num_sms, cudaStream_t stream);
 int launch_attention_f32(const float* qkv, float* out, int BD, int N, int heads, cudaStream_t stream);

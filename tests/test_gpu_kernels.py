@@ -96,7 +96,7 @@ def _attn_ref(qkv, BD, N, heads):
     return (p @ v).transpose(1, 2).reshape(BD * N, E)
 
 
-# N == 257: attention_tc257_kernel; 17 <= N <= 360: attention_tcg_kernel (one or two S chunks, one to four query tiles,
+# N == 257: attention_tc257_kernel; 17 <= N <= 352: attention_tcg_kernel (one or two S chunks, one to four query tiles,
 # ragged last tile / key padding); N == 16 and N == 400: the warp-MMA kernel.  (40, 325, 12) gives every SM more than one item.
 @pytest.mark.parametrize("BD,N,heads", [(3, 257, 6), (2, 65, 6), (2, 325, 12), (1, 16, 6), (2, 33, 6), (1, 17, 6), (3, 109, 6),
                                         (2, 261, 6), (40, 325, 12), (2, 352, 6), (1, 400, 6), (70, 129, 6)])
