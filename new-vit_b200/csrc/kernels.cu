@@ -406,10 +406,10 @@ template int launch_cls_attention<bf16>(const bf16*, bf16*, float*, int, int, in
 
 // ---------------------------------------------------------------------------------------------------
 // fp32 CUDA-core attention (fp32 parity mode only): one CTA per (slice, head), K and V in shared memory.
-// softmax(q k^T) v with q pre-scaled (attention.py:56-69).  N <= 384.
+// softmax(q k^T) v with q pre-scaled (attention.py:56-69).  N <= 431 (K and V of one head in 227 KB).
 // ---------------------------------------------------------------------------------------------------
 constexpr int ATT32_WARPS = 8;
-constexpr int ATT32_MAXJ = 12;
+constexpr int ATT32_MAXJ = 14;   // 32-key register groups per query row: N <= 448 by registers, <= 431 by shared memory
 __global__ void __launch_bounds__(ATT32_WARPS * 32) attention_f32_kernel(const float* __restrict__ qkv,
                                                                           float* __restrict__ out, int N, int heads) {
     extern __shared__ float sm[];

@@ -437,3 +437,44 @@ def test_mst_resnet_shares_the_slice_transformer_kernel():
     torch.testing.assert_close(y, want, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(sl, O.get_slice_attention(w[:, :, 0, :]), rtol=1e-4, atol=1e-8)
     assert sl.shape == (B * D, 1, 1) and (sl.reshape(B, D)[mask] == 0).all()
+
+
+# explicit token counts at the edges of the attention kernels' ranges: 17 (smallest tcgen05), 343 / 352 (largest), 362 / 401 (warp MMA)
+EDGE_SHAPES = {100: (2, 3, 56, 56), 101: (1, 4, 252, 266), 102: (2, 2, 182, 378), 103: (1, 3, 266, 266), 104: (1, 2, 280, 280), 105: (1, 2, 280, 280)}
+
+
+@pytest.mark.parametrize("seed", list(range(8)) + sorted(EDGE_SHAPES))
+def test_random_shapes_against_oracle(seed):
+    """Randomly drawn shapes (batch 1..5, 1..40 slices, H and W independent multiples of 14 in 56..280 -> 17..401 tokens, so every
+    attention kernel and the resampled position table take part), random padding masks, both precisions, init and peaky weights:
+    logits, features and attention maps against the oracle; fp32 also the plane attention element-wise."""
+    import random
+    from new_vit_b200 import synth
+    from oracle import mst_oracle as O
+    rng = random.Random(1000 + seed)
+    B, D = rng.randint(1, 5), rng.choice([1, 2, 3, 5, 8, 13, 21, 32, 40])
+    H, W = 14 * rng.randint(4, 20), 14 * rng.randint(4, 20)
+    while B * D * (H // 14) * (W // 14) > 60000:      # keep the CPU oracle to a few seconds
+        D = max(1, D // 2)
+    if seed in EDGE_SHAPES:
+        B, D, H, W = EDGE_SHAPES[seed]
+    precision = "fp32" if seed % 2 == 0 else "bf16"
+    variant = "peaky" if seed % 3 else "init"
+    sd = synth.make_state_dict("s", 2, seed=40 + seed, variant=variant)
+    x = synth.make_volume(B, D, H, W, seed=70 + seed)
+    mask = synth.make_padding_mask(B, D, seed=seed) if (D > 2 and seed % 4 != 3) else None
+    ref = O.forward(sd, x, mask)
+    m = _model(sd, precision, 224)                     # 224-trained position table, resampled to (H, W) like the reference
+    r = _run(m, x, mask)
+    info = f"B={B} D={D} H={H} W={W} {precision} {variant} mask={mask is not None}"
+    err = (r["logits"] - ref["logits"]).abs().max().item()
+    if precision == "fp32":
+        assert err <= 1e-4 * max(ref["logits"].abs().max().item(), 1.0), info
+        torch.testing.assert_close(r["feat"], ref["feat"], rtol=1e-3, atol=1e-4, msg=lambda s: f"{info}: {s}")
+        torch.testing.assert_close(r["plane_attn"], O.get_plane_attention(ref["plane_cls"]), rtol=3e-4, atol=1e-9, msg=lambda s: f"{info}: {s}")
+    else:
+        assert err <= 2e-2, info
+    assert _cos(r["attn_maps"], O.get_attention_maps(ref["plane_cls"], ref["slice_cls"])) >= 0.999, info
+    if mask is not None and bool(mask.any()):      # masked slices weigh exactly 0
+        sa = r["slice_attn"].reshape(B, D)
+        assert float(sa[mask].abs().max()) == 0.0, info
