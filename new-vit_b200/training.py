@@ -114,17 +114,35 @@ class EncoderFunction(torch.autograd.Function):
         L = _cabi.lib()
         model, (B, D, H, W), params = ctx.model, ctx.shape, ctx.saved_tensors
         with torch.cuda.device(model.device):
-            grads = []
-            for n, p in zip(ctx.names, params):
-                if n == "encoder.mask_token":          # never read by the path (vision_transformer.py:216 masks=None)
-                    grads.append(None)
-                    continue
-                g = torch.empty(p.shape, device=p.device, dtype=torch.float32)
-                _cabi.check(L.mst_set_grad(model._handle, n.encode(), _cabi.ptr(g), g.numel()))
-                grads.append(g)
+            # One flat fp32 buffer receives every gradient of the encoder; it and its registration with the library (mst_set_grad)
+            # are kept across steps (167 allocations and ctypes calls per step otherwise).
+            cache = getattr(model, "_enc_grad_cache", None)
+            key = (tuple(ctx.names), tuple(tuple(p.shape) for p in params), str(model.device), getattr(model._handle, "value", id(model._handle)))
+            if cache is None or cache["key"] != key:
+                sizes = [(p.numel() + 3) // 4 * 4 for p in params]
+                flat = torch.empty(sum(sizes), device=model.device, dtype=torch.float32)
+                views, off = [], 0
+                for n, p, sz in zip(ctx.names, params, sizes):
+                    if n == "encoder.mask_token":          # never read by the path (vision_transformer.py:216 masks=None)
+                        views.append(None)
+                    else:
+                        g = flat[off:off + p.numel()].view(p.shape)
+                        _cabi.check(L.mst_set_grad(model._handle, n.encode(), _cabi.ptr(g), g.numel()))
+                        views.append(g)
+                    off += sz
+                cache = model._enc_grad_cache = {"key": key, "flat": flat, "views": views}
+            views = cache["views"]
             _cabi.check(L.mst_train_backward(model._handle, _cabi.ptr(denc.contiguous().float()), B, D, H, W, _cabi.ptr(ctx.ws), ctx.ws.numel(),
                                              _stream()))
-        return (None, None, None, *grads)
+            # With .grad already allocated (FusedAdamW keeps them as views of its flat buffer) the gradients are accumulated by ONE
+            # multi-tensor add instead of 167 AccumulateGrad launches; otherwise autograd gets them as usual (copies: the flat buffer
+            # is overwritten by the next backward pass).
+            named = dict(model.named_parameters())
+            live = [(named[n], g) for n, g in zip(ctx.names, views) if g is not None]
+            if all(p.grad is not None and p.grad.dtype == torch.float32 and p.grad.device == g.device for p, g in live):
+                torch._foreach_add_([p.grad for p, _ in live], [g for _, g in live])
+                return (None, None, None) + (None,) * len(views)
+        return (None, None, None, *[None if g is None else g.clone() for g in views])
 
 
 class FusedAdamW(torch.optim.Optimizer):
