@@ -27,7 +27,7 @@ role = {
 }
 out = ["# One config-5 training step (8 volumes x 32 x 224^2, ViT-S, every parameter trainable) -- ncu launch list, round 2 final code\n",
        "`ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none python profiles/train_timing.py` (the 4th step; cold-cache,",
-       "serialised per-launch times: shares, not absolutes).  %d launches, %.2f ms summed; the un-profiled step is 23.8 ms wall (`bench.py`" % (nl, tot / 1000),
+       "serialised per-launch times: shares, not absolutes).  %d launches, %.2f ms summed; the un-profiled step is 22.3 ms wall (`bench.py`" % (nl, tot / 1000),
        "extras.config5_train), of which 2.3 ms is host time of the weight re-pack.  Raw list: `r02_train_launches.csv`; host-side phase times:",
        "`r02_train_timing.txt`; this table: `python profiles/train_summary.py`.\n",
        "| kernel | launches | total us | per launch us | share | role |", "|---|---|---|---|---|---|"]
