@@ -244,6 +244,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
     constexpr bool TWO = PAIR == 2;
     constexpr int BMT = TWO ? 2 * BM : BM;  // rows of one tile (the pair's 256-row tile in cta_group::2 mode)
     const int mode = mode_flags & 0xff;
+    const int xp_flags = kDbgTiming ? mode_flags : 0;   // experiment bits 0x100 / 0x200 (mainloop / epilogue ceilings): compiled out of the product
     constexpr bool kResident = KCH > 0;
     constexpr uint32_t kTmemCols = (2 * BN <= 256) ? 256 : 512;
     constexpr int EPI_WARPS = L::EPI_WARPS;
@@ -567,7 +568,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
                     if (c == CHUNKS_PER_WARP - 1) {
                         fence_proxy_async_smem();
                         __syncwarp();
-                        if (lane == 0 && !(mode_flags & 0x200)) {
+                        if (lane == 0 && !(xp_flags & 0x200)) {
                             if (mode == EPI_BIAS_ACCUM) tma_reduce_add_2d(&tmC, stg, nbase, row0);
                             else tma_store_2d(&tmC, stg, nbase, row0);
                             tma_store_commit();
@@ -609,7 +610,7 @@ gemm_tc_kernel(const __grid_constant__ TmaDesc tmA, const __grid_constant__ TmaD
             mbar_wait(&tfull_bar[acc], acc_phase);
             const long long e1 = MST_DBG_CLOCK();
             tc_fence_after_sync();
-            if (mode_flags & 0x100) {  // experiment: mainloop ceiling (no epilogue work at all)
+            if (xp_flags & 0x100) {  // experiment: mainloop ceiling (no epilogue work at all)
                 release_tmem();
                 acc ^= 1; if (acc == 0) acc_phase ^= 1;
                 continue;
