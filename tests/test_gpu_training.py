@@ -225,3 +225,42 @@ def test_vit_b_training_step_matches_oracle_autograd():
         if not (cos >= 0.99 and 0.95 <= ratio <= 1.05):
             bad[n] = (cos, ratio)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("B,D,masked", [(1, 1, False), (3, 5, True), (2, 7, False)])
+def test_full_training_step_on_other_batch_shapes(B, D, masked):
+    """Whole-model gradients at batch / slice counts the goldens do not cover (one slice per volume: two slice-transformer tokens; odd
+    counts; padding masks), against the oracle under torch autograd (pinned to the live reference by tests/test_training_cpu.py)."""
+    from test_training_cpu import oracle_full_train_step
+    from new_vit_b200 import DinoV2ClassifierSlice, synth
+    sd = synth.make_state_dict("s", 2, seed=21 + B, variant="peaky")
+    x = synth.make_volume(B, D, 224, 224, seed=5 + D)
+    mask = synth.make_padding_mask(B, D, seed=B) if masked else None
+    target = torch.arange(B) % 2
+    _, loss_ref, grads = oracle_full_train_step(sd, x, mask, target)
+    m = DinoV2ClassifierSlice(1, 2, pretrained=False, precision="bf16").cuda()
+    m.load_state_dict(sd)
+    m.train()
+    opt = m.configure_optimizers()[0]
+    opt.zero_grad()
+    batch = {"source": x, "target": target.cuda()}
+    if mask is not None:
+        batch["src_key_padding_mask"] = mask
+    loss = m.training_step(batch, 0)
+    assert abs(float(loss.detach()) - float(loss_ref)) <= 2e-2
+    loss.backward()
+    bad = {}
+    for n, p in m.named_parameters():
+        if n == "encoder.mask_token" or n.endswith("attn.qkv.bias") or n.endswith("in_proj_bias"):
+            continue
+        want, got = grads[n], p.grad.detach().cpu()
+        if float(want.norm()) < 1e-12:
+            assert float(got.norm()) < 1e-6, n
+            continue
+        cos, ratio = _cosine(got, want), float(got.norm()) / float(want.norm())
+        if not (cos >= 0.99 and 0.95 <= ratio <= 1.05):
+            bad[n] = (cos, ratio)
+    assert not bad, bad
+    opt.step()                           # a second step on the updated weights stays finite
+    opt.zero_grad()
+    assert torch.isfinite(m.training_step(batch, 1).detach())
