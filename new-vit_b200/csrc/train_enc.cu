@@ -54,18 +54,46 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
         const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
         o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
     };
-    for (int r = blockIdx.x * nw + warp; r < rows; r += gridDim.x * nw) {
+    // E = 384 with bf16 dy (every LayerNorm of the blocks): the NEXT row's x / dy / dres are requested (raw, 8 bytes per piece) before
+    // this row's four warp reductions, so a warp always has loads in flight -- one row at a time left the kernel at 3.6 TB/s.
+    constexpr bool kPrefetch = EPL == 12;
+    const bool pf = kPrefetch && dy != nullptr;
+    const int r_first = blockIdx.x * nw + warp, r_step = gridDim.x * nw;
+    uint2 nx[G], ndy[G], nrs[G];
+    auto request = [&](int r) {
+        const bf16* xr = x + static_cast<int64_t>(r) * x_row_stride;
+        const int64_t ro = static_cast<int64_t>(r) * E;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            nx[g] = *reinterpret_cast<const uint2*>(xr + 128 * g + 4 * lane);
+            ndy[g] = *reinterpret_cast<const uint2*>(dy + ro + 128 * g + 4 * lane);
+            nrs[g] = dres ? *reinterpret_cast<const uint2*>(dres + ro + 128 * g + 4 * lane) : make_uint2(0u, 0u);
+        }
+    };
+    auto unpack4 = [&](const uint2& u, float* o) {
+        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    };
+    if (pf && r_first < rows) request(r_first);
+    for (int r = r_first; r < rows; r += r_step) {
         const bf16* xr = x + static_cast<int64_t>(r) * x_row_stride;
         const int64_t ro = static_cast<int64_t>(r) * E;
         float xv[EPL], dyv[EPL];
+        uint2 crs[G];
         float s = 0.f;
+        if (pf) {
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-            load4(xr + 128 * g + 4 * lane, xv + 4 * g);
-            if (dy) load4(dy + ro + 128 * g + 4 * lane, dyv + 4 * g);
-            else {
-                const float4 v = *reinterpret_cast<const float4*>(dy_f32 + ro + 128 * g + 4 * lane);
-                dyv[4 * g] = v.x; dyv[4 * g + 1] = v.y; dyv[4 * g + 2] = v.z; dyv[4 * g + 3] = v.w;
+            for (int g = 0; g < G; ++g) { unpack4(nx[g], xv + 4 * g); unpack4(ndy[g], dyv + 4 * g); crs[g] = nrs[g]; }
+            if (r + r_step < rows) request(r + r_step);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                load4(xr + 128 * g + 4 * lane, xv + 4 * g);
+                if (dy) load4(dy + ro + 128 * g + 4 * lane, dyv + 4 * g);
+                else {
+                    const float4 v = *reinterpret_cast<const float4*>(dy_f32 + ro + 128 * g + 4 * lane);
+                    dyv[4 * g] = v.x; dyv[4 * g + 1] = v.y; dyv[4 * g + 2] = v.z; dyv[4 * g + 3] = v.w;
+                }
             }
         }
 #pragma unroll
@@ -88,7 +116,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const bf16* __restrict__ x,
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             float v[4], rs[4] = {0.f, 0.f, 0.f, 0.f};
-            if (dres) load4(dres + ro + 128 * g + 4 * lane, rs);
+            if (pf) unpack4(crs[g], rs);
+            else if (dres) load4(dres + ro + 128 * g + 4 * lane, rs);
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = rstd * (dyv[4 * g + j] * gam[4 * g + j] - m1 - xv[4 * g + j] * m2) + rs[j];
             *reinterpret_cast<uint2*>(dx + ro + 128 * g + 4 * lane) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
