@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) ln_bwd_reduce_kernel(const float* __restr
         if (i < E) dgamma[i] = t; else dbeta[i - E] = t;
     }
 }
-constexpr int LN_BWD_GRID = 592;   // 4 CTAs per SM
+constexpr int LN_BWD_GRID = 296;   // 2 CTAs per SM are resident (128 registers x 256 threads); fewer partials for the reduce
 size_t ln_bwd_workspace_bytes(int E) { return static_cast<size_t>(LN_BWD_GRID) * 2 * E * sizeof(float); }
 
 int launch_ln_bwd(const bf16* x, int64_t x_row_stride, const bf16* dy, const float* dy_f32, const bf16* dres, const float* gamma, bf16* dx,
