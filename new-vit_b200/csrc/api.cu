@@ -549,6 +549,29 @@ template <> struct Ops<float> {
         if (h->prof.on) { cudaEventRecord(h->prof.next(), st); h->prof.recs.push_back({cat, _e0, _e0 + 1}); } \
     } while (0)
 
+// qkv = LN1(x) W^T + b with the LayerNorm folded into the GEMM (rowstat = rstd of every row), inference and training forward.
+// ViT-S: 1152 features = 4.5 pairs of 128.  The first 1024 run on the weights-in-TMEM kernel (whole cta_group::2 pairs, sixteen
+// epilogue warps), the last 128 (the tail of V) on the streaming 128-wide tile kernel: two launches, the second one HBM-bound (it
+// re-reads the rows), together faster than one launch of the weights-in-smem kernel.  (Small batches keep the single launch: below
+// ~150 m-tiles both halves are latency, not throughput.)
+template <typename T>
+static int qkv_ln_folded(mst_handle h, const void* x, const Layer& L, const float* rowstat, void* qkv, int M, int E, cudaStream_t st) {
+    EpiParams ep{};
+    ep.bias = L.bqkv; ep.rowstat = rowstat; ep.out = qkv; ep.ldo = 3 * E;
+    static const int qkv_split = exp_env("MST_QKV_SPLIT", 1);
+    if (qkv_split && sizeof(T) == 2 && E == 384 && gemm_wt_enabled() && M >= 32768) {
+        MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 1024, E, EPI_LN_BIAS, ep, st));
+        EpiParams ep2 = ep;
+        ep2.bias = L.bqkv + 1024;
+        ep2.out = static_cast<T*>(qkv) + 1024;
+        MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, static_cast<const T*>(L.wqkv) + static_cast<size_t>(1024) * E, M, 128, E,
+                                              EPI_LN_BIAS, ep2, st));
+    } else {
+        MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
+    }
+    return 0;
+}
+
 template <typename T>
 static int forward_t(mst_handle h, const void* src, int src_dtype, int B, int D, int H, int W, const uint8_t* pad_mask, int tta,
                      float* logits, float* feat, float* enc_cls_out, float* plane_cls, float* slice_cls, float* full_maps,
@@ -582,23 +605,7 @@ static int forward_t(mst_handle h, const void* src, int src_dtype, int B, int D,
             if (!stats_from_fc2)   // (blocks >= 1: the previous block's fc2 epilogue has already written them)
                 MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(reinterpret_cast<const bf16*>(x), ws.rowstat, M, E, 1e-6f, st));
             stats_from_fc2 = false;
-            EpiParams ep{};
-            ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = ws.qkv; ep.ldo = 3 * E;
-            // ViT-S: 1152 features = 4.5 pairs of 128.  The first 1024 run on the weights-in-TMEM kernel (whole cta_group::2 pairs,
-            // sixteen epilogue warps), the last 128 (the tail of V) on the streaming 128-wide tile kernel: two launches, the
-            // second one HBM-bound (it re-reads the rows), together faster than one launch of the weights-in-smem kernel.
-            // (Small batches keep the single launch: below ~150 m-tiles both halves are latency, not throughput.)
-            static const int qkv_split = exp_env("MST_QKV_SPLIT", 1);
-            if (qkv_split && sizeof(T) == 2 && E == 384 && gemm_wt_enabled() && M >= 32768) {
-                MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 1024, E, EPI_LN_BIAS, ep, st));
-                EpiParams ep2 = ep;
-                ep2.bias = L.bqkv + 1024;
-                ep2.out = static_cast<T*>(ws.qkv) + 1024;
-                MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, static_cast<const T*>(L.wqkv) + static_cast<size_t>(1024) * E, M, 128, E,
-                                                      EPI_LN_BIAS, ep2, st));
-            } else {
-                MST_LAUNCH(CAT_GEMM_QKV, Ops<T>::gemm(h, x, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
-            }
+            MST_PROPAGATE((qkv_ln_folded<T>(h, x, L, ws.rowstat, ws.qkv, M, E, st)));
         } else {
             MST_LAUNCH(CAT_LAYERNORM, (launch_layernorm<T, T>(x, E, xn, E, L.n1w, L.n1b, M, E, 1e-6f, st)));
             EpiParams ep{};
@@ -795,11 +802,7 @@ static int train_forward(mst_handle h, const void* src, int src_dtype, int B, in
         bf16* x_next = l + 1 < c.depth ? ws.L[l + 1].x_in : ws.x_out;
         MST_REQUIRE(L.fold_qkv, "encoder training needs the LayerNorm-folded weight packing");
         MST_LAUNCH(CAT_LAYERNORM, launch_row_stats(T.x_in, ws.rowstat, M, E, 1e-6f, st));
-        {
-            EpiParams ep{};
-            ep.bias = L.bqkv; ep.rowstat = ws.rowstat; ep.out = T.qkv; ep.ldo = 3 * E;
-            MST_LAUNCH(CAT_GEMM_QKV, Ops<bf16>::gemm(h, T.x_in, E, L.wqkv, M, 3 * E, E, EPI_LN_BIAS, ep, st));
-        }
+        MST_PROPAGATE((qkv_ln_folded<bf16>(h, T.x_in, L, ws.rowstat, T.qkv, M, E, st)));
         if (N == 257)   // the specialised kernel keeps the row log-sum-exp for the backward pass
             MST_LAUNCH(CAT_ATTENTION, launch_attention_tc257x16(T.qkv, T.ao, BD, c.enc_heads, h->num_sms, st, nullptr, T.lse));
         else
